@@ -1,0 +1,249 @@
+/*
+ * gg_plan.h — plain-C description of the slice of a Greengage plan that the
+ * B200 executor accelerates.  These PODs are what crosses the C-ABI
+ * (include/ggb200.h): no pointers, fixed-size arrays, so the same bytes can be
+ * produced by the C host executor (greengage_b200/host), by ctypes, or by a
+ * Postgres-side translator walking Plan/Expr trees.
+ *
+ * Everything here mirrors a reference structure; the citation says which:
+ *   gg_attr / gg_tupdesc  <- Form_pg_attribute / TupleDesc
+ *                            (src/include/catalog/pg_attribute.h, access/tupdesc.h)
+ *   gg_expr               <- Var / Const / OpExpr / BoolExpr / NullTest
+ *                            (src/include/nodes/primnodes.h), funcid = pg_proc OID
+ *   gg_aggref             <- Aggref + pg_aggregate row (catalog/pg_aggregate.h:161-220)
+ *   gg_scan / gg_agg / gg_hashjoin / gg_sort / gg_motion
+ *                         <- SeqScan / Agg / HashJoin+Hash / Sort / Motion
+ *                            (src/include/nodes/plannodes.h)
+ * Type ids and function ids are the catalog OIDs, so a translator is a tree walk.
+ */
+#ifndef GG_PLAN_H
+#define GG_PLAN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- storage constants (configure.in:284-296, storage/bufpage.h:153-166) ---- */
+#define GG_BLCKSZ            32768
+#define GG_PAGE_HEADER_SIZE  24          /* SizeOfPageHeaderData */
+#define GG_ITEMID_SIZE       4
+#define GG_MAXALIGN(x)       (((uint64_t)(x) + 7) & ~(uint64_t)7)
+#define GG_PD_ALL_VISIBLE    0x0004      /* bufpage.h:178 */
+#define GG_PAGE_VERSION      14          /* PG_PAGE_LAYOUT_VERSION, bufpage.h:207 */
+#define GG_LP_NORMAL         1           /* storage/itemid.h:34-40 */
+
+/* heap tuple header (access/htup_details.h:139-196) */
+#define GG_HEAP_HDR_SIZE       23        /* offsetof(HeapTupleHeaderData, t_bits) */
+#define GG_HEAP_HASNULL        0x0001
+#define GG_HEAP_HASVARWIDTH    0x0002
+#define GG_HEAP_HASEXTERNAL    0x0004
+#define GG_HEAP_XMIN_COMMITTED 0x0100
+#define GG_HEAP_XMIN_INVALID   0x0200
+#define GG_HEAP_XMIN_FROZEN    0x0300
+#define GG_HEAP_XMAX_INVALID   0x0800
+#define GG_HEAP_NATTS_MASK     0x07FF
+#define GG_FROZEN_XID          2         /* FrozenTransactionId, access/transam.h */
+
+/* ---- type OIDs (src/include/catalog/pg_type.h) ---- */
+#define GG_BOOLOID       16
+#define GG_INT8OID       20
+#define GG_INT4OID       23
+#define GG_TEXTOID       25
+#define GG_FLOAT8OID     701
+#define GG_BPCHAROID     1042
+#define GG_VARCHAROID    1043
+#define GG_DATEOID       1082
+#define GG_TIMESTAMPOID  1114
+
+/* ---- function OIDs (pg_proc.h; values checked against the reference's generated fmgroids.h) ---- */
+#define GG_F_INT4EQ 65
+#define GG_F_INT4LT 66
+#define GG_F_INT4NE 144
+#define GG_F_INT4GT 147
+#define GG_F_INT4LE 149
+#define GG_F_INT4GE 150
+#define GG_F_FLOAT8MUL 216
+#define GG_F_FLOAT8DIV 217
+#define GG_F_FLOAT8PL 218
+#define GG_F_FLOAT8MI 219
+#define GG_F_FLOAT8EQ 293
+#define GG_F_FLOAT8NE 294
+#define GG_F_FLOAT8LT 295
+#define GG_F_FLOAT8LE 296
+#define GG_F_FLOAT8GT 297
+#define GG_F_FLOAT8GE 298
+#define GG_F_I4TOD 316
+#define GG_F_INT8EQ 467
+#define GG_F_INT8NE 468
+#define GG_F_INT8LT 469
+#define GG_F_INT8GT 470
+#define GG_F_INT8LE 471
+#define GG_F_INT8GE 472
+#define GG_F_INT48 481          /* int4 -> int8 cast */
+#define GG_F_I8TOD 482
+#define GG_F_BPCHAREQ 1048
+#define GG_F_BPCHARNE 1053
+#define GG_F_DATE_EQ 1086
+#define GG_F_DATE_LT 1087
+#define GG_F_DATE_LE 1088
+#define GG_F_DATE_GT 1089
+#define GG_F_DATE_GE 1090
+#define GG_F_DATE_NE 1091
+#define GG_F_DATE_LT_TIMESTAMP 2338
+#define GG_F_DATE_LE_TIMESTAMP 2339
+#define GG_F_DATE_EQ_TIMESTAMP 2340
+#define GG_F_DATE_GT_TIMESTAMP 2341
+#define GG_F_DATE_GE_TIMESTAMP 2342
+#define GG_F_DATE_NE_TIMESTAMP 2343
+
+/* aggregate OIDs (pg_aggregate.h:156-220) */
+#define GG_AGG_AVG_FLOAT8   2105   /* float8_accum / float8_avg / float8_combine, state float8[3] "{0,0,0}" */
+#define GG_AGG_SUM_INT4     2108   /* int4_sum / - / int8pl, state int8 init NULL */
+#define GG_AGG_SUM_FLOAT8   2111   /* float8pl / - / float8pl, state float8 init NULL (strict: first value) */
+#define GG_AGG_MAX_INT8     2115
+#define GG_AGG_MAX_INT4     2116
+#define GG_AGG_MAX_FLOAT8   2120
+#define GG_AGG_MAX_DATE     2122
+#define GG_AGG_MIN_INT8     2131
+#define GG_AGG_MIN_INT4     2132
+#define GG_AGG_MIN_FLOAT8   2136
+#define GG_AGG_MIN_DATE     2138
+#define GG_AGG_COUNT_ANY    2147   /* int8inc_any / - / int8pl, init 0 */
+#define GG_AGG_COUNT_STAR   2803   /* int8inc / - / int8pl, init 0 */
+
+/* ---- limits of the accelerated subset ---- */
+#define GG_MAX_ATTS        32
+#define GG_MAX_EXPR_NODES  96
+#define GG_MAX_AGGS        16
+#define GG_MAX_KEYS        4       /* group / sort / hash key columns */
+#define GG_MAX_TLIST       16
+
+/* ---- tuple descriptor ---- */
+typedef struct gg_attr {
+	int32_t atttypid;
+	int32_t atttypmod;      /* bpchar(n)/varchar(n): n + 4 (VARHDRSZ), else -1 */
+	int16_t attlen;         /* >0 fixed, -1 varlena */
+	int8_t  attalign;       /* 'c' 's' 'i' 'd' (tupmacs.h:121-130) */
+	int8_t  attbyval;
+	int8_t  attnotnull;
+	int8_t  pad[3];
+} gg_attr;                  /* 16 bytes */
+
+typedef struct gg_tupdesc {
+	int32_t natts;
+	int32_t pad;
+	gg_attr attrs[GG_MAX_ATTS];
+} gg_tupdesc;
+
+/* ---- expressions: flat pool, children by index ---- */
+enum gg_expr_kind {
+	GG_E_VAR = 1,      /* varno (0 = outer/scan, 1 = inner), varattno 1-based */
+	GG_E_CONST = 2,    /* constvalue = Datum bits; strings: <=8 blank-stripped bytes packed LSB-first, constlen */
+	GG_E_FUNC = 3,     /* OpExpr/FuncExpr with funcid (strict) */
+	GG_E_AND = 4,      /* BoolExpr, 2 args (execQual.c ExecEvalAnd 3-valued logic) */
+	GG_E_OR = 5,
+	GG_E_NOT = 6,
+	GG_E_ISNULL = 7,   /* NullTest IS NULL */
+	GG_E_ISNOTNULL = 8
+};
+
+typedef struct gg_expr {
+	int32_t kind;
+	int32_t funcid;
+	int32_t rettype;        /* type OID of the result */
+	int16_t varno;
+	int16_t varattno;
+	int32_t nargs;
+	int32_t args[2];
+	int32_t constisnull;
+	int32_t constlen;       /* string constants: blank-stripped length */
+	int64_t constvalue;
+} gg_expr;                  /* 40 bytes */
+
+typedef struct gg_exprpool {
+	int32_t nnodes;
+	int32_t pad;
+	gg_expr nodes[GG_MAX_EXPR_NODES];
+} gg_exprpool;
+
+/* ---- aggregates ---- */
+enum gg_aggstage {          /* primnodes.h:257-264 AggStage */
+	GG_AGGSTAGE_NORMAL = 0,
+	GG_AGGSTAGE_PARTIAL = 1,   /* transfn, emit transition state (nodeAgg.c:975-979) */
+	GG_AGGSTAGE_FINAL = 3      /* combinefn over partial states, then finalfn (nodeAgg.c:2123-2148) */
+};
+
+typedef struct gg_aggref {
+	int32_t aggfnoid;       /* GG_AGG_* */
+	int32_t arg;            /* root node of the argument expression; -1 for count(*).
+	                         * FINAL stage: index of the input column carrying the partial state. */
+} gg_aggref;
+
+/* One aggregate value as it crosses the ABI.  NORMAL/FINAL: the SQL result
+ * (f[0] for float8 results, i for int8 results).  PARTIAL: the transition
+ * state exactly as the reference ships it through Motion (SURVEY App. A
+ * "two-stage interchange"): sum(float8) -> f[0] (isnull if no input),
+ * avg(float8) -> f[0..2] = {N, sumX, sumX2}, count -> i, sum(int4) -> i. */
+typedef struct gg_aggval {
+	double  f[3];
+	int64_t i;
+	int32_t isnull;
+	int32_t pad;
+} gg_aggval;                /* 40 bytes */
+
+/* One output row of an Agg: group keys (Datum bits; strings packed like consts) + aggregate values. */
+typedef struct gg_aggrow {
+	int64_t   key[GG_MAX_KEYS];
+	int32_t   keylen[GG_MAX_KEYS];     /* string keys: stripped length; else 0 */
+	int32_t   keyisnull[GG_MAX_KEYS];
+	gg_aggval agg[GG_MAX_AGGS];
+} gg_aggrow;
+
+/* ---- plan nodes ---- */
+typedef struct gg_scan {            /* SeqScan + its qual (nodeSeqscan.c, execScan.c:111) */
+	gg_tupdesc desc;
+	int32_t    qual;                /* root in the pool, -1 = none; NULL result = not passed (execQual.c:6260) */
+	int32_t    pad;
+} gg_scan;
+
+typedef struct gg_agg {             /* Agg (AGG_HASHED or AGG_PLAIN when numCols==0), nodeAgg.c */
+	int32_t   aggstage;
+	int32_t   numCols;
+	int32_t   grpCol[GG_MAX_KEYS];      /* expr roots of the grouping columns (Vars of the input) */
+	int32_t   numAggs;
+	int32_t   pad;
+	gg_aggref aggs[GG_MAX_AGGS];
+} gg_agg;
+
+enum gg_jointype {                  /* nodes/nodes.h JoinType */
+	GG_JOIN_INNER = 0, GG_JOIN_LEFT = 1, GG_JOIN_SEMI = 4, GG_JOIN_ANTI = 5
+};
+
+typedef struct gg_hashjoin {        /* HashJoin + Hash (nodeHashjoin.c, nodeHash.c) */
+	int32_t jointype;
+	int32_t nkeys;
+	int32_t outerkey[GG_MAX_KEYS];      /* expr roots over the outer tuple (varno 0) */
+	int32_t innerkey[GG_MAX_KEYS];      /* expr roots over the inner tuple (varno 1) */
+	int32_t joinqual;                   /* extra join qual over both sides, -1 = none */
+	int32_t pad;
+} gg_hashjoin;
+
+typedef struct gg_sortkey {         /* Sort.sortColIdx/sortOperators/nullsFirst (plannodes.h Sort) */
+	int32_t col;                        /* 0-based column of the input row */
+	int32_t typid;
+	int32_t desc;                       /* 1 = DESC */
+	int32_t nulls_first;
+} gg_sortkey;
+
+enum gg_motiontype {                /* plannodes.h MotionType */
+	GG_MOTION_HASH = 0,                 /* Redistribute */
+	GG_MOTION_FIXED = 1,                /* Broadcast / Gather */
+	GG_MOTION_EXPLICIT = 2
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_PLAN_H */
