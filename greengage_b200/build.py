@@ -1,0 +1,70 @@
+"""In-tree build of the product libraries (no JIT cache: the .so files travel with the repo snapshot).
+
+  libggb200.so  hand-written CUDA for sm_100a + the C-ABI (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
+  libgghost.so  host C (gcc): executor-node surface, synthetic loader
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+BUILD = os.path.join(ROOT, "build")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
+CU_SOURCES = ["gg_abi.cu", "gg_scanagg.cu", "gg_compile.cpp"]
+HOST_SOURCES = ["gg_synth.c"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _all_headers():
+    hs = []
+    for d in (CSRC, HOST, os.path.join(ROOT, "include")):
+        for f in os.listdir(d):
+            if f.endswith((".h", ".cuh")):
+                hs.append(os.path.join(d, f))
+    return hs
+
+
+def build_device(verbose=False, force=False):
+    os.makedirs(BUILD, exist_ok=True)
+    objs = []
+    hdrs = _all_headers()
+    for src in [s for s in os.listdir(CSRC) if s.endswith((".cu", ".cpp"))]:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(BUILD, src.rsplit(".", 1)[0] + ".o")
+        if force or _newer(obj, [path] + hdrs):
+            cmd = [NVCC] + NVFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            subprocess.check_call(cmd)
+        objs.append(obj)
+    out = os.path.join(HERE, "libggb200.so")
+    if force or _newer(out, objs):
+        subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", out] + objs)
+    return out
+
+
+def build_host(force=False):
+    out = os.path.join(HERE, "libgghost.so")
+    srcs = [os.path.join(HOST, s) for s in os.listdir(HOST) if s.endswith(".c")]
+    if force or _newer(out, srcs + _all_headers()):
+        subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-Wall", "-ffp-contract=off", "-pthread", "-shared",
+                               "-o", out] + srcs + ["-lm"])
+    return out
+
+
+def build_all(verbose=False, force=False):
+    return build_device(verbose, force), build_host(force)
+
+
+if __name__ == "__main__":
+    print(build_all(verbose="-v" in sys.argv, force="-f" in sys.argv))

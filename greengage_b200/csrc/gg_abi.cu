@@ -1,0 +1,200 @@
+/*
+ * gg_abi.cu — engine, relation and host-staging entry points of include/ggb200.h.
+ * The operator entry points live next to their kernels (gg_scanagg.cu, gg_join.cu, ...).
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "gg_engine.h"
+
+static thread_local char g_err[512] = "";
+
+void gg_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+
+int gg_cuda_fail(cudaError_t e, const char *what)
+{
+	gg_set_error("CUDA error %d (%s) in %s", (int) e, cudaGetErrorString(e), what);
+	cudaGetLastError();
+	return GG_ERR_CUDA;
+}
+
+int gg_errflags_to_code(uint32_t f)
+{
+	f &= ~(uint32_t) GGP_EF_INFO_MASK;
+	if (!f) return GG_OK;
+	if (f & GGP_EF_BADPAGE) { gg_set_error("corrupted page or tuple pointers"); return GG_ERR_BADPAGE; }
+	if (f & GGP_EF_VISIBILITY) { gg_set_error("tuple visibility needs clog/snapshot (not frozen)"); return GG_ERR_VISIBILITY; }
+	if (f & GGP_EF_NOTNULL_VIOLATED) { gg_set_error("NULL found in a column declared NOT NULL"); return GG_ERR_BADPAGE; }
+	if (f & GGP_EF_FLOAT_OVERFLOW) { gg_set_error("value out of range: overflow"); return GG_ERR_FLOAT_OVERFLOW; }
+	if (f & GGP_EF_FLOAT_UNDERFLOW) { gg_set_error("value out of range: underflow"); return GG_ERR_FLOAT_UNDERFLOW; }
+	if (f & GGP_EF_DIV_ZERO) { gg_set_error("division by zero"); return GG_ERR_DIV_ZERO; }
+	if (f & GGP_EF_INT_OVERFLOW) { gg_set_error("bigint out of range"); return GG_ERR_INT_OVERFLOW; }
+	if (f & GGP_EF_DATE_RANGE) { gg_set_error("date out of range for timestamp"); return GG_ERR_DATE_RANGE; }
+	if (f & GGP_EF_STRING_TOO_LONG) { gg_set_error("string value longer than 8 bytes (or toasted) in a GPU expression"); return GG_ERR_UNSUPPORTED; }
+	if (f & GGP_EF_GROUP_OVERFLOW) { gg_set_error("more groups than the GPU aggregate holds"); return GG_ERR_UNSUPPORTED; }
+	if (f & GGP_EF_TABLE_FULL) { gg_set_error("hash table full"); return GG_ERR_NOMEM; }
+	gg_set_error("device error flags 0x%x", f);
+	return GG_ERR_CUDA;
+}
+
+extern "C" {
+
+const char *gg_last_error(void) { return g_err; }
+
+const char *gg_strerror(int code)
+{
+	switch (code)
+	{
+		case GG_OK: return "ok";
+		case GG_ERR_CUDA: return "CUDA error";
+		case GG_ERR_FLOAT_OVERFLOW: return "value out of range: overflow";
+		case GG_ERR_FLOAT_UNDERFLOW: return "value out of range: underflow";
+		case GG_ERR_DIV_ZERO: return "division by zero";
+		case GG_ERR_INT_OVERFLOW: return "bigint out of range";
+		case GG_ERR_UNSUPPORTED: return "plan not supported on the GPU path";
+		case GG_ERR_VISIBILITY: return "tuple visibility needs clog/snapshot";
+		case GG_ERR_NOMEM: return "out of memory";
+		case GG_ERR_BADPAGE: return "corrupted page";
+		case GG_ERR_ARG: return "bad argument";
+		case GG_ERR_DATE_RANGE: return "date out of range for timestamp";
+	}
+	return "unknown error";
+}
+
+int gg_engine_create(int device, gg_engine **out)
+{
+	int ndev = 0;
+	if (!out) return GG_ERR_ARG;
+	*out = nullptr;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+	{
+		/* no CPU fallback: the product path fails loudly without a GPU */
+		gg_set_error("no CUDA device available (%s): the B200 engine has no CPU fallback",
+		             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+		cudaGetLastError();
+		return GG_ERR_CUDA;
+	}
+	if (device < 0 || device >= ndev) { gg_set_error("device %d out of range (%d devices)", device, ndev); return GG_ERR_ARG; }
+	GG_CUDA(cudaSetDevice(device));
+	gg_engine *eng = new gg_engine();
+	eng->device = device;
+	cudaDeviceProp prop;
+	GG_CUDA(cudaGetDeviceProperties(&prop, device));
+	eng->sm_count = prop.multiProcessorCount;
+	eng->smem_optin = prop.sharedMemPerBlockOptin;
+	GG_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+	GG_CUDA(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+	GG_CUDA(cudaEventCreate(&eng->ev_start));
+	GG_CUDA(cudaEventCreate(&eng->ev_stop));
+	*out = eng;
+	return GG_OK;
+}
+
+void gg_engine_free(gg_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	cudaStreamSynchronize(e->copy_stream);
+	cudaEventDestroy(e->ev_start);
+	cudaEventDestroy(e->ev_stop);
+	cudaStreamDestroy(e->stream);
+	cudaStreamDestroy(e->copy_stream);
+	delete e;
+}
+
+int gg_engine_sm_count(gg_engine *e) { return e ? e->sm_count : 0; }
+
+int gg_engine_sync(gg_engine *e)
+{
+	if (!e) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(e->device));
+	GG_CUDA(cudaStreamSynchronize(e->copy_stream));
+	GG_CUDA(cudaStreamSynchronize(e->stream));
+	return GG_OK;
+}
+
+int gg_engine_last_kernel_ms(gg_engine *e, float *ms)
+{
+	if (!e || !ms) return GG_ERR_ARG;
+	if (!e->timed) { *ms = 0; return GG_OK; }
+	GG_CUDA(cudaEventSynchronize(e->ev_stop));
+	GG_CUDA(cudaEventElapsedTime(ms, e->ev_start, e->ev_stop));
+	return GG_OK;
+}
+
+uint64_t gg_engine_launch_count(gg_engine *e) { return e ? e->launches : 0; }
+
+int gg_relation_create(gg_engine *e, uint64_t nblocks, gg_relation **out)
+{
+	if (!e || !out) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(e->device));
+	gg_relation *r = new gg_relation();
+	r->eng = e;
+	r->nblocks = nblocks;
+	r->owned = true;
+	cudaError_t err = cudaMalloc((void **) &r->pages, (size_t) (nblocks ? nblocks : 1) * GG_BLCKSZ);
+	if (err != cudaSuccess) { delete r; return gg_cuda_fail(err, "cudaMalloc(relation)"); }
+	*out = r;
+	return GG_OK;
+}
+
+int gg_relation_attach(gg_engine *e, void *device_pages, uint64_t nblocks, gg_relation **out)
+{
+	if (!e || !out || (!device_pages && nblocks)) return GG_ERR_ARG;
+	if (((uintptr_t) device_pages) & 15) { gg_set_error("relation base must be 16-byte aligned for TMA"); return GG_ERR_ARG; }
+	gg_relation *r = new gg_relation();
+	r->eng = e;
+	r->pages = (uint8_t *) device_pages;
+	r->nblocks = nblocks;
+	r->owned = false;
+	*out = r;
+	return GG_OK;
+}
+
+int gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks)
+{
+	if (!r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(r->eng->device));
+	GG_CUDA(cudaMemcpyAsync(r->pages + first_block * GG_BLCKSZ, host_pages, (size_t) nblocks * GG_BLCKSZ,
+	                        cudaMemcpyHostToDevice, r->eng->stream));
+	return GG_OK;
+}
+
+int gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uint64_t nblocks)
+{
+	if (!r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(r->eng->device));
+	GG_CUDA(cudaMemcpyAsync(host_pages, r->pages + first_block * GG_BLCKSZ, (size_t) nblocks * GG_BLCKSZ,
+	                        cudaMemcpyDeviceToHost, r->eng->stream));
+	GG_CUDA(cudaStreamSynchronize(r->eng->stream));
+	return GG_OK;
+}
+
+uint64_t gg_relation_nblocks(gg_relation *r) { return r ? r->nblocks : 0; }
+void *gg_relation_device_ptr(gg_relation *r) { return r ? r->pages : nullptr; }
+
+void gg_relation_free(gg_relation *r)
+{
+	if (!r) return;
+	if (r->owned && r->pages) { cudaSetDevice(r->eng->device); cudaFree(r->pages); }
+	delete r;
+}
+
+int gg_host_alloc(uint64_t bytes, void **out)
+{
+	if (!out) return GG_ERR_ARG;
+	GG_CUDA(cudaHostAlloc(out, (size_t) bytes, cudaHostAllocDefault));
+	return GG_OK;
+}
+
+void gg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  /* extern "C" */

@@ -1,0 +1,33 @@
+/*
+ * gg_engine.h — host-side objects behind the opaque handles of include/ggb200.h.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "gg_program.h"
+#include "../../include/ggb200.h"
+
+struct gg_engine {
+	int device = 0;
+	int sm_count = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;       /* compute */
+	cudaStream_t copy_stream = nullptr;  /* H2D staging */
+	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+	bool timed = false;
+	uint64_t launches = 0;
+};
+
+struct gg_relation {
+	gg_engine *eng = nullptr;
+	uint8_t *pages = nullptr;
+	uint64_t nblocks = 0;
+	bool owned = false;
+};
+
+void gg_set_error(const char *fmt, ...);
+int  gg_cuda_fail(cudaError_t e, const char *what);
+int  gg_errflags_to_code(uint32_t flags);
+
+#define GG_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return gg_cuda_fail(_e, #call); } while (0)

@@ -1,0 +1,115 @@
+"""Thin object wrappers over the C-ABI (include/ggb200.h).  No operator logic lives here."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, dev_lib
+
+
+class Engine:
+    """One GPU segment (gg_engine).  Fails loudly when no CUDA device is usable: there is no CPU fallback."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(dev_lib().gg_engine_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            dev_lib().gg_engine_free(self.h)
+            self.h = C.c_void_p()
+
+    def sync(self):
+        check(dev_lib().gg_engine_sync(self.h))
+
+    @property
+    def sm_count(self):
+        return dev_lib().gg_engine_sm_count(self.h)
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        check(dev_lib().gg_engine_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return dev_lib().gg_engine_launch_count(self.h)
+
+
+class Relation:
+    """Heap pages resident in HBM (gg_relation)."""
+
+    def __init__(self, eng, nblocks=None, host_pages=None, device_ptr=None):
+        self.eng = eng
+        self.h = C.c_void_p()
+        L = dev_lib()
+        if device_ptr is not None:
+            check(L.gg_relation_attach(eng.h, C.c_void_p(device_ptr), nblocks, C.byref(self.h)))
+        else:
+            if host_pages is not None:
+                nblocks = host_pages.size // capi.GG_BLCKSZ
+            check(L.gg_relation_create(eng.h, nblocks, C.byref(self.h)))
+            if host_pages is not None and nblocks:
+                self.load(0, host_pages)
+                eng.sync()
+        self.nblocks = nblocks
+
+    def load(self, first_block, host_pages):
+        nb = host_pages.size // capi.GG_BLCKSZ
+        check(dev_lib().gg_relation_load(self.h, first_block, host_pages.ctypes.data_as(C.c_void_p), nb))
+
+    def read(self, first_block=0, nblocks=None):
+        nblocks = self.nblocks - first_block if nblocks is None else nblocks
+        out = np.empty(nblocks * capi.GG_BLCKSZ, dtype=np.uint8)
+        check(dev_lib().gg_relation_read(self.h, first_block, out.ctypes.data_as(C.c_void_p), nblocks))
+        return out
+
+    def device_ptr(self):
+        return dev_lib().gg_relation_device_ptr(self.h)
+
+    def free(self):
+        if self.h:
+            dev_lib().gg_relation_free(self.h)
+            self.h = C.c_void_p()
+
+
+class ScanAgg:
+    """SeqScan -> qual -> Agg pipeline (gg_scanagg)."""
+
+    def __init__(self, eng, scan, agg, pool):
+        self.eng = eng
+        self.h = C.c_void_p()
+        self.agg = agg
+        check(dev_lib().gg_scanagg_create(eng.h, C.byref(scan), C.byref(agg), C.byref(pool), C.byref(self.h)))
+
+    def run(self, rel, first_block=0, nblocks=None):
+        nblocks = rel.nblocks - first_block if nblocks is None else nblocks
+        check(dev_lib().gg_scanagg_run(self.h, rel.h, first_block, nblocks))
+
+    def run_host(self, host_ptr, nblocks):
+        check(dev_lib().gg_scanagg_run_host(self.h, C.c_void_p(host_ptr), nblocks))
+
+    def reset(self):
+        check(dev_lib().gg_scanagg_reset(self.h))
+
+    def fetch(self, cap=4096):
+        out = (capi.gg_aggrow * cap)()
+        n = C.c_int(0)
+        sc, ps = C.c_uint64(0), C.c_uint64(0)
+        check(dev_lib().gg_scanagg_fetch(self.h, out, cap, C.byref(n), C.byref(sc), C.byref(ps)))
+        return [out[i] for i in range(n.value)], sc.value, ps.value
+
+    def free(self):
+        if self.h:
+            dev_lib().gg_scanagg_free(self.h)
+            self.h = C.c_void_p()
+
+
+def agg_final(eng, agg, rows, cap=4096):
+    arr = (capi.gg_aggrow * max(len(rows), 1))()
+    for i, r in enumerate(rows):
+        C.memmove(C.byref(arr[i]), C.byref(r), C.sizeof(capi.gg_aggrow))
+    out = (capi.gg_aggrow * cap)()
+    n = C.c_int(0)
+    check(dev_lib().gg_agg_final(eng.h, C.byref(agg), arr, len(rows), out, cap, C.byref(n)))
+    return [out[i] for i in range(n.value)]

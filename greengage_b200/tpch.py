@@ -1,0 +1,96 @@
+"""TPC-H-shaped plans and synthetic relations used by tests and bench.py.
+
+q1_plan() builds exactly the reference's Q1 (src/test/regress/output/rpt_tpch.source:288-307):
+the scan qual is planned as date_le_timestamp against a timestamp constant
+(src/test/regress/expected/tpch500GB.out:1782).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import (AGG_AVG_FLOAT8, AGG_COUNT_STAR, AGG_SUM_FLOAT8, BOOLOID, BPCHAROID, DATEOID, FLOAT8OID,
+                   TIMESTAMPOID, ExprPool)
+
+USECS_PER_DAY = 86400000000
+D_1998_12_01 = -396          # days since 2000-01-01
+
+# attribute numbers (1-based) of the columns Q1 touches, per table layout
+LI_WIDE_COLS = dict(orderkey=1, quantity=5, extendedprice=6, discount=7, tax=8, returnflag=9, linestatus=10, shipdate=11)
+LI_NARROW_COLS = dict(orderkey=1, quantity=2, extendedprice=3, discount=4, tax=5, returnflag=6, linestatus=7, shipdate=8)
+
+
+def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_days=90, desc=None):
+    """Q1: scan + filter + group by (l_returnflag, l_linestatus) + 4 sums, 3 avgs, count(*)."""
+    cols = LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS
+    desc = desc or capi.synth_tupdesc(table)
+    p = ExprPool()
+    qty = p.var(cols["quantity"], FLOAT8OID)
+    price = p.var(cols["extendedprice"], FLOAT8OID)
+    disc = p.var(cols["discount"], FLOAT8OID)
+    tax = p.var(cols["tax"], FLOAT8OID)
+    flag = p.var(cols["returnflag"], BPCHAROID)
+    status = p.var(cols["linestatus"], BPCHAROID)
+    shipdate = p.var(cols["shipdate"], DATEOID)
+    cutoff = p.const(TIMESTAMPOID, (D_1998_12_01 - interval_days) * USECS_PER_DAY)
+    qual = p.func(capi.F_DATE_LE_TIMESTAMP, BOOLOID, shipdate, cutoff)
+    one = p.const(FLOAT8OID, 1.0)
+    disc_price = p.func(capi.F_FLOAT8MUL, FLOAT8OID, price, p.func(capi.F_FLOAT8MI, FLOAT8OID, one, disc))
+    disc_price2 = p.func(capi.F_FLOAT8MUL, FLOAT8OID, price, p.func(capi.F_FLOAT8MI, FLOAT8OID, one, disc))
+    charge = p.func(capi.F_FLOAT8MUL, FLOAT8OID, disc_price2, p.func(capi.F_FLOAT8PL, FLOAT8OID, one, tax))
+    scan = capi.make_scan(desc, qual)
+    agg = capi.make_agg(stage, [flag, status], [
+        (AGG_SUM_FLOAT8, qty), (AGG_SUM_FLOAT8, price), (AGG_SUM_FLOAT8, disc_price), (AGG_SUM_FLOAT8, charge),
+        (AGG_AVG_FLOAT8, qty), (AGG_AVG_FLOAT8, price), (AGG_AVG_FLOAT8, disc), (AGG_COUNT_STAR, -1)])
+    return scan, agg, p.pool
+
+
+def q1_final_agg(agg):
+    """The FINAL-stage Agg above the Redistribute Motion: same aggregates, grpCol carries key type OIDs."""
+    fin = capi.gg_agg()
+    C.memmove(C.byref(fin), C.byref(agg), C.sizeof(capi.gg_agg))
+    fin.aggstage = capi.AGGSTAGE_FINAL
+    fin.grpCol[0] = BPCHAROID
+    fin.grpCol[1] = BPCHAROID
+    return fin
+
+
+def count_star_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL):
+    """BASELINE config 0: SELECT count(*) FROM t"""
+    desc = capi.synth_tupdesc(table)
+    p = ExprPool()
+    scan = capi.make_scan(desc, -1)
+    agg = capi.make_agg(stage, [], [(AGG_COUNT_STAR, -1)])
+    return scan, agg, p.pool
+
+
+def synth_spec(table, ncand, seed=42, nsegs=1, seg=0, policy=capi.DIST_RANDOM, norders=None):
+    s = capi.gg_synth_spec()
+    s.table, s.policy, s.seed, s.ncand = table, policy, seed, ncand
+    if norders is None:
+        norders = ncand if table == capi.TAB_ORDERS else max(ncand // 4, 1)
+    s.norders, s.nsegs, s.seg = norders, nsegs, seg
+    return s
+
+
+def synth_measure(spec, nthreads=None):
+    nthreads = nthreads or min(os.cpu_count() or 1, 64)
+    nb, nr = C.c_uint64(0), C.c_uint64(0)
+    assert capi.host_lib().gg_synth_measure(C.byref(spec), nthreads, C.byref(nb), C.byref(nr)) == 0
+    return nb.value, nr.value
+
+
+def synth_generate(spec, out=None, nthreads=None):
+    """Generate this segment's pages into a numpy uint8 array (or a caller-provided buffer address)."""
+    nthreads = nthreads or min(os.cpu_count() or 1, 64)
+    nb, nr = synth_measure(spec, nthreads)
+    if out is None:
+        out = np.empty(nb * capi.GG_BLCKSZ, dtype=np.uint8)
+        ptr = out.ctypes.data_as(C.c_void_p)
+    else:
+        ptr = C.c_void_p(out)
+    nb2, nr2 = C.c_uint64(0), C.c_uint64(0)
+    rc = capi.host_lib().gg_synth_generate(C.byref(spec), nthreads, ptr, nb, C.byref(nb2), C.byref(nr2))
+    assert rc == 0 and nb2.value == nb
+    return out, nb, nr

@@ -1,0 +1,139 @@
+/*
+ * ggb200.h — C-ABI of the B200 segment engine (libggb200.so).
+ *
+ * This is the drop-in boundary for the Greengage executor hot path: plain
+ * pointers, sizes and the PODs of gg_plan.h; no torch, no C++ types.  The
+ * per-node C functions of src/backend/executor/execProcnode.c (ExecInitNode
+ * :255, ExecProcNode :925, ExecEndNode :1315) are mirrored by the host layer in
+ * greengage_b200/host/gg_executor.c, which drives the device through exactly
+ * these entry points.  INTEGRATION.md shows the binding a maintainer adds on
+ * the Postgres side.
+ *
+ * Conventions:
+ *   - every call returns 0 or a negative GG_ERR_* code; gg_last_error() has the
+ *     text.  The C wrapper on the Postgres side turns a non-zero return into
+ *     ereport(ERROR, ...) (utils/elog.h:190); nothing here longjmps or throws.
+ *   - handles own device memory; gg_*_free() is what a
+ *     MemoryContextRegisterResetCallback / ResourceReleaseCallback calls
+ *     (utils/palloc.h:190, resowner.c:551).
+ *   - one engine per process and GPU (one QE process per segment and slice,
+ *     src/backend/cdb/dispatcher/README.md:9-18); calls are made from one thread.
+ *   - there is NO CPU fallback: if no CUDA device is usable, gg_engine_create fails.
+ */
+#ifndef GGB200_H
+#define GGB200_H
+
+#include <stdint.h>
+#include "gg_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_OK                   0
+#define GG_ERR_CUDA            (-1)    /* CUDA runtime error (text in gg_last_error) */
+#define GG_ERR_FLOAT_OVERFLOW  (-2)    /* "value out of range: overflow", float_utils.h:28 */
+#define GG_ERR_FLOAT_UNDERFLOW (-3)
+#define GG_ERR_DIV_ZERO        (-4)
+#define GG_ERR_INT_OVERFLOW    (-5)    /* "bigint out of range", int8.c:526,694 */
+#define GG_ERR_UNSUPPORTED     (-6)    /* plan shape outside the accelerated subset: caller keeps the CPU node */
+#define GG_ERR_VISIBILITY      (-7)    /* a tuple needs clog/snapshot to decide visibility (tqual.c:997) */
+#define GG_ERR_NOMEM           (-8)
+#define GG_ERR_BADPAGE         (-9)    /* page header fails the PageAddItem sanity rules (bufpage.c:196-204) */
+#define GG_ERR_ARG             (-10)
+#define GG_ERR_DATE_RANGE      (-11)   /* "date out of range for timestamp", date.c:471 */
+
+typedef struct gg_engine   gg_engine;     /* one GPU segment: device, streams, scratch */
+typedef struct gg_relation gg_relation;   /* heap pages resident in HBM (replaces bufmgr/smgr for the scan) */
+typedef struct gg_scanagg  gg_scanagg;    /* compiled SeqScan -> qual -> Agg pipeline */
+typedef struct gg_joinagg  gg_joinagg;    /* compiled SeqScan ⋈ Hash(SeqScan) -> Agg pipeline */
+typedef struct gg_sorter   gg_sorter;     /* device sort of fixed-width rows */
+
+const char *gg_last_error(void);
+const char *gg_strerror(int code);
+
+/* ---- engine (one per segment process) ---- */
+int  gg_engine_create(int device, gg_engine **out);
+void gg_engine_free(gg_engine *e);
+int  gg_engine_sm_count(gg_engine *e);
+int  gg_engine_sync(gg_engine *e);
+/* CUDA-event timing of the last *_run call on the engine's stream, in milliseconds */
+int  gg_engine_last_kernel_ms(gg_engine *e, float *ms);
+/* number of kernels the engine has launched since creation (bench.py's gpu_launches) */
+uint64_t gg_engine_launch_count(gg_engine *e);
+
+/* ---- relations: heap pages in device memory ----
+ * Replaces heap_beginscan/heapgetpage's ReadBufferExtended path
+ * (src/backend/access/heap/heapam.c:312-463, storage/buffer/bufmgr.c:315): the
+ * segment's pages live in HBM as one contiguous array of 32 KB blocks. */
+int  gg_relation_create(gg_engine *e, uint64_t nblocks, gg_relation **out);
+/* wrap device memory owned by the caller (e.g. a torch tensor); not freed by gg_relation_free */
+int  gg_relation_attach(gg_engine *e, void *device_pages, uint64_t nblocks, gg_relation **out);
+/* host -> device copy of nblocks pages starting at first_block (async on the engine's copy stream
+ * when host_pages is pinned; gg_engine_sync or the next *_run orders it) */
+int  gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks);
+int  gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uint64_t nblocks);
+uint64_t gg_relation_nblocks(gg_relation *r);
+void *gg_relation_device_ptr(gg_relation *r);
+void gg_relation_free(gg_relation *r);
+
+/* pinned host staging (cudaHostAlloc), for callers without their own pinned buffers */
+int  gg_host_alloc(uint64_t bytes, void **out);
+void gg_host_free(void *p);
+
+/* ---- SeqScan -> qual -> Agg ----
+ * Replaces ExecAgg(AGG_HASHED|AGG_PLAIN) over ExecSeqScan
+ * (nodeAgg.c:1123, execHHashagg.c:905, nodeSeqscan.c:128, execScan.c:111).
+ * Output rows follow gg_aggrow (group keys + aggregate values; PARTIAL stage
+ * emits transition states).  Row order is unspecified, as for a hash aggregate. */
+int  gg_scanagg_create(gg_engine *e, const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
+                       gg_scanagg **out);
+/* run over blocks [first_block, first_block+nblocks) of a resident relation; accumulates into the
+ * pipeline's state, so several ranges (or relations) can be fed before fetching */
+int  gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t nblocks);
+/* streamed variant: pages come from HOST memory (pinned or pageable); H2D copies are chunked and
+ * overlapped with the kernel on two streams.  This is the end-to-end path bench.py's `e2e` times. */
+int  gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks);
+int  gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
+                      uint64_t *rows_scanned, uint64_t *rows_passed);
+int  gg_scanagg_reset(gg_scanagg *p);
+void gg_scanagg_free(gg_scanagg *p);
+
+/* FINAL-stage Agg over partial rows gathered from the segments (combine functions,
+ * nodeAgg.c:2123-2148).  agg->grpCol[i] carries the key type OIDs. */
+int  gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
+                  gg_aggrow *out, int outcap, int *nout);
+
+/* ---- HashJoin (+ Agg on top) ----
+ * Replaces MultiExecHash + ExecHashJoin (nodeHash.c:88, nodeHashjoin.c:512):
+ * build from the inner relation, probe with the outer relation, feed matches
+ * to the aggregate without materialising the join. */
+int  gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
+                       const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out);
+int  gg_joinagg_build(gg_joinagg *p, gg_relation *inner, uint64_t first_block, uint64_t nblocks);
+int  gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, uint64_t nblocks);
+int  gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined);
+void gg_joinagg_free(gg_joinagg *p);
+
+/* ---- Sort ----
+ * Replaces tuplesort_begin_heap_mk/puttupleslot/performsort/gettupleslot
+ * (tuplesort_mk.c:771,1154,1378,1668) for fixed-width rows: rows is n x ncols
+ * int64 Datum columns in device or host memory; perm receives the sorted order. */
+int  gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols,
+                  const int64_t *host_rows, const uint8_t *host_nulls, uint64_t n, uint64_t *host_perm);
+
+/* ---- Motion ----
+ * Redistribute routing (nodeMotion.c:1481-1687, cdbhash.c:191-287) on device:
+ * projects the hash-key and payload columns of every qualifying tuple, computes
+ * the destination segment bit-exactly, and scatters fixed-width rows into
+ * per-destination regions of out_rows.  counts[nsegs] receives rows per destination. */
+int  gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
+                         const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
+                         int nsegs, gg_relation *r, uint64_t first_block, uint64_t nblocks,
+                         void *device_out_rows, uint64_t out_cap_rows,
+                         uint64_t *host_counts, uint64_t *host_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGB200_H */
