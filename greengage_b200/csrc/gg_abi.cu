@@ -198,3 +198,14 @@ int gg_host_alloc(uint64_t bytes, void **out)
 void gg_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }  /* extern "C" */
+
+/* debugging aid: compile a SeqScan->Agg plan and list the accumulator-machine program (no GPU needed) */
+extern "C" int gg_debug_disasm_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, char *buf, int cap)
+{
+	ggp_program prog;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	char msg[256];
+	int rc = ggp_compile_scanagg(scan, agg, pool, &prog, aggmap, msg, sizeof msg);
+	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
+	return ggp_disasm(&prog, buf, cap);
+}

@@ -6,8 +6,9 @@
  * eligibility (anything outside the accelerated subset returns
  * GG_ERR_UNSUPPORTED so the caller keeps the CPU node), referenced columns get
  * slots, attcacheoff is precomputed the way slot_deform_tuple memoises it
- * (heaptuple.c:1160-1190), and every expression is flattened to accumulator
- * code (gg_program.h).
+ * (heaptuple.c:1160-1190), and the scan qual, the grouping keys and every
+ * aggregate argument are flattened into one accumulator-machine program
+ * (gg_program.h).
  */
 #include <cstdio>
 #include <cstring>
@@ -26,7 +27,9 @@ struct Ctx {
 	const gg_tupdesc *idesc;
 	char *err;
 	int errlen;
-	int temps_used;
+	int temps_busy;           /* bit t: temporary t holds a live value */
+	int npersist;
+	int persist_root[4], persist_temp[4];   /* common subexpressions kept in temporaries for later aggregate arguments */
 	bool failed;
 };
 
@@ -44,13 +47,53 @@ int loadtype_of(int32_t typid)
 {
 	switch (typid)
 	{
-		case GG_INT4OID: case GG_DATEOID: return GGP_LD_I4;
-		case GG_INT8OID: case GG_FLOAT8OID: case GG_TIMESTAMPOID: return GGP_LD_I8;
-		case GG_BPCHAROID: return GGP_LD_BPCHAR;
-		case GG_VARCHAROID: case GG_TEXTOID: return GGP_LD_VARCHAR;
-		case GG_BOOLOID: return GGP_LD_BOOL;
+		case GG_INT4OID: case GG_DATEOID: return GGP_LT_I4;
+		case GG_INT8OID: case GG_FLOAT8OID: case GG_TIMESTAMPOID: return GGP_LT_I8;
+		case GG_BPCHAROID: return GGP_LT_BPCHAR;
+		case GG_VARCHAROID: case GG_TEXTOID: return GGP_LT_VARCHAR;
+		case GG_BOOLOID: return GGP_LT_BOOL;
 	}
 	return 0;
+}
+
+long align_nominal(long off, char a)
+{
+	switch (a) { case 'i': return (off + 3) & ~3L; case 'c': return off; case 'd': return (off + 7) & ~7L; default: return (off + 1) & ~1L; }
+}
+
+/* attcacheoff as slot_deform_tuple memoises it (heaptuple.c:1160-1200): valid for the fixed-width
+ * prefix, and for the first varlena iff its offset is already aligned */
+void init_side(ggp_side *s, const gg_tupdesc *d)
+{
+	memset(s, 0, sizeof *s);
+	s->natts = d->natts;
+	for (int i = 0; i < d->natts && i < GG_MAX_ATTS; i++)
+	{
+		s->att[i].attlen = d->attrs[i].attlen;
+		s->att[i].attalign = d->attrs[i].attalign;
+		s->att[i].slot = -1;
+		s->att[i].cacheoff = -1;
+		s->att[i].notnull = d->attrs[i].attnotnull;
+	}
+	long off = 0;
+	s->first_walk = s->natts;
+	for (int i = 0; i < s->natts; i++)
+	{
+		if (s->att[i].attlen == -1)
+		{
+			if (off == align_nominal(off, s->att[i].attalign))
+			{
+				s->att[i].cacheoff = (int16_t) off;
+				s->first_walk = i + 1;      /* the varlena's own offset is constant; what follows is not */
+			}
+			else
+				s->first_walk = i;
+			break;
+		}
+		off = align_nominal(off, s->att[i].attalign);
+		s->att[i].cacheoff = (int16_t) off;
+		off += s->att[i].attlen;
+	}
 }
 
 /* slot of (varno, attno), allocating on first use */
@@ -86,186 +129,41 @@ int add_const(Ctx &c, int64_t v, bool isnull)
 	return p->nconst++;
 }
 
-void emit(Ctx &c, int op, int src, int idx, int aux = 0)
+bool is_col_op(int op)
 {
-	ggp_program *p = c.prog;
-	if (p->ncode >= GGP_MAX_CODE) { fail(c, "expression program too long"); return; }
-	ggp_op o;
-	o.op = (uint8_t) op; o.src = (uint8_t) src; o.idx = (uint8_t) idx; o.aux = (uint8_t) aux;
-	p->code[p->ncode++] = o;
-}
-
-bool is_leaf(const gg_expr &e) { return e.kind == GG_E_VAR || e.kind == GG_E_CONST; }
-
-void leaf_operand(Ctx &c, const gg_expr &e, int *src, int *idx)
-{
-	if (e.kind == GG_E_VAR)
+	switch (op)
 	{
-		*src = e.varno == 1 ? GGP_SRC_ICOL : GGP_SRC_COL;
-		*idx = col_slot(c, e.varno, e.varattno);
-	}
-	else
-	{
-		*src = GGP_SRC_CONST;
-		*idx = add_const(c, e.constvalue, e.constisnull != 0);
-	}
-}
-
-int swap_cc(int cc)
-{
-	switch (cc) { case GGP_LT: return GGP_GT; case GGP_LE: return GGP_GE; case GGP_GT: return GGP_LT; case GGP_GE: return GGP_LE; }
-	return cc;
-}
-
-struct BinInfo { int op, rop, cc; bool isbin; bool commut; };
-
-/* map a pg_proc OID to machine ops */
-bool func_info(int funcid, BinInfo *b, int *unary_op)
-{
-	*unary_op = 0;
-	b->isbin = true; b->commut = false; b->cc = 0; b->rop = 0;
-	switch (funcid)
-	{
-		case GG_F_FLOAT8PL:  b->op = GGP_F8ADD; b->rop = GGP_F8ADD; b->commut = true; return true;
-		case GG_F_FLOAT8MUL: b->op = GGP_F8MUL; b->rop = GGP_F8MUL; b->commut = true; return true;
-		case GG_F_FLOAT8MI:  b->op = GGP_F8SUB; b->rop = GGP_F8RSUB; return true;
-		case GG_F_FLOAT8DIV: b->op = GGP_F8DIV; b->rop = GGP_F8RDIV; return true;
-#define CMPCASE(F, OP, CC) case F: b->op = OP; b->rop = OP; b->cc = CC; return true;
-		CMPCASE(GG_F_FLOAT8LT, GGP_CMPF8, GGP_LT) CMPCASE(GG_F_FLOAT8LE, GGP_CMPF8, GGP_LE)
-		CMPCASE(GG_F_FLOAT8EQ, GGP_CMPF8, GGP_EQ) CMPCASE(GG_F_FLOAT8NE, GGP_CMPF8, GGP_NE)
-		CMPCASE(GG_F_FLOAT8GT, GGP_CMPF8, GGP_GT) CMPCASE(GG_F_FLOAT8GE, GGP_CMPF8, GGP_GE)
-		CMPCASE(GG_F_INT4LT, GGP_CMPI, GGP_LT) CMPCASE(GG_F_INT4LE, GGP_CMPI, GGP_LE)
-		CMPCASE(GG_F_INT4EQ, GGP_CMPI, GGP_EQ) CMPCASE(GG_F_INT4NE, GGP_CMPI, GGP_NE)
-		CMPCASE(GG_F_INT4GT, GGP_CMPI, GGP_GT) CMPCASE(GG_F_INT4GE, GGP_CMPI, GGP_GE)
-		CMPCASE(GG_F_INT8LT, GGP_CMPI, GGP_LT) CMPCASE(GG_F_INT8LE, GGP_CMPI, GGP_LE)
-		CMPCASE(GG_F_INT8EQ, GGP_CMPI, GGP_EQ) CMPCASE(GG_F_INT8NE, GGP_CMPI, GGP_NE)
-		CMPCASE(GG_F_INT8GT, GGP_CMPI, GGP_GT) CMPCASE(GG_F_INT8GE, GGP_CMPI, GGP_GE)
-		CMPCASE(GG_F_DATE_LT, GGP_CMPI, GGP_LT) CMPCASE(GG_F_DATE_LE, GGP_CMPI, GGP_LE)
-		CMPCASE(GG_F_DATE_EQ, GGP_CMPI, GGP_EQ) CMPCASE(GG_F_DATE_NE, GGP_CMPI, GGP_NE)
-		CMPCASE(GG_F_DATE_GT, GGP_CMPI, GGP_GT) CMPCASE(GG_F_DATE_GE, GGP_CMPI, GGP_GE)
-		CMPCASE(GG_F_BPCHAREQ, GGP_CMPSTR, GGP_EQ) CMPCASE(GG_F_BPCHARNE, GGP_CMPSTR, GGP_NE)
-#undef CMPCASE
-		case GG_F_INT48: b->isbin = false; *unary_op = -1; return true;     /* loads already sign-extend */
-		case GG_F_I4TOD: case GG_F_I8TOD: b->isbin = false; *unary_op = GGP_I2F8; return true;
+		case GGP_LD_C4: case GGP_LD_C8: case GGP_LD_BP: case GGP_LD_VS: case GGP_LD_BOOL:
+		case GGP_ADD_C: case GGP_SUB_C: case GGP_RSUB_C: case GGP_MUL_C: case GGP_DIV_C: case GGP_RDIV_C:
+		case GGP_CMPF_C: case GGP_CMPI_C4: case GGP_CMPI_C8:
+			return true;
 	}
 	return false;
 }
 
-int date_ts_cc(int funcid)
+void emit(Ctx &c, int op, int idx = 0, int aux = 0)
 {
-	switch (funcid)
+	ggp_program *p = c.prog;
+	if (p->ncode >= GGP_MAX_CODE - 1) { fail(c, "expression program too long"); return; }
+	ggp_op o;
+	memset(&o, 0, sizeof o);
+	o.op = (uint8_t) op; o.idx = (uint8_t) idx; o.aux = (uint8_t) aux;
+	o.off = 0xFFFF;
+	if (is_col_op(op))
 	{
-		case GG_F_DATE_LT_TIMESTAMP: return GGP_LT; case GG_F_DATE_LE_TIMESTAMP: return GGP_LE;
-		case GG_F_DATE_EQ_TIMESTAMP: return GGP_EQ; case GG_F_DATE_GT_TIMESTAMP: return GGP_GT;
-		case GG_F_DATE_GE_TIMESTAMP: return GGP_GE; case GG_F_DATE_NE_TIMESTAMP: return GGP_NE;
+		const ggp_side *s = (idx & 0x80) ? c.inner : c.outer;
+		int a = s->colatt[idx & 0x7F];
+		if (s->att[a].cacheoff >= 0) o.off = (uint16_t) s->att[a].cacheoff;
 	}
-	return -1;
+	p->code[p->ncode++] = o;
 }
 
-void gen(Ctx &c, int root);
-
-/* acc = acc OP right-subtree */
-void gen_binary(Ctx &c, const gg_expr &e, int op, int rop, int cc, bool commut)
+/* attach a post-action to the op that produced the current accumulator value */
+ggp_op *last_op(Ctx &c, int start)
 {
-	const gg_expr &l = c.pool->nodes[e.args[0]];
-	const gg_expr &r = c.pool->nodes[e.args[1]];
-	int src, idx;
-
-	if (is_leaf(r))
-	{
-		gen(c, e.args[0]);
-		leaf_operand(c, r, &src, &idx);
-		emit(c, op, src, idx, cc);
-	}
-	else if (is_leaf(l))
-	{
-		/* evaluate the complex right side, then apply with the leaf on the LEFT */
-		gen(c, e.args[1]);
-		leaf_operand(c, l, &src, &idx);
-		if (commut) emit(c, op, src, idx, cc);
-		else if (op == GGP_CMPF8 || op == GGP_CMPI || op == GGP_CMPSTR) emit(c, op, src, idx, swap_cc(cc));
-		else emit(c, rop, src, idx, cc);
-	}
-	else
-	{
-		gen(c, e.args[0]);
-		if (c.temps_used >= 4) { fail(c, "expression too deep"); return; }
-		int t = c.temps_used++;
-		emit(c, GGP_STORE, GGP_SRC_TEMP, t);
-		gen(c, e.args[1]);
-		/* acc = right, temp = left: need left OP right */
-		if (commut) emit(c, op, GGP_SRC_TEMP, t, cc);
-		else if (op == GGP_CMPF8 || op == GGP_CMPI || op == GGP_CMPSTR) emit(c, op, GGP_SRC_TEMP, t, swap_cc(cc));
-		else emit(c, rop, GGP_SRC_TEMP, t, cc);
-		c.temps_used--;
-	}
-}
-
-void gen(Ctx &c, int root)
-{
-	if (c.failed) return;
-	if (root < 0 || root >= c.pool->nnodes) { fail(c, "bad expression index %d", root); return; }
-	const gg_expr &e = c.pool->nodes[root];
-	int src, idx;
-
-	switch (e.kind)
-	{
-		case GG_E_VAR:
-		case GG_E_CONST:
-			leaf_operand(c, e, &src, &idx);
-			emit(c, GGP_LOAD, src, idx);
-			return;
-		case GG_E_FUNC:
-		{
-			int cc = date_ts_cc(e.funcid);
-			if (cc >= 0)
-			{
-				/* date_xx_timestamp(date, ts): promote the date, then integer compare (date.c:560-640) */
-				gen(c, e.args[0]);
-				emit(c, GGP_DATE2TS, 0, 0);
-				const gg_expr &r = c.pool->nodes[e.args[1]];
-				if (is_leaf(r)) { leaf_operand(c, r, &src, &idx); emit(c, GGP_CMPI, src, idx, cc); }
-				else
-				{
-					if (c.temps_used >= 4) { fail(c, "expression too deep"); return; }
-					int t = c.temps_used++;
-					emit(c, GGP_STORE, GGP_SRC_TEMP, t);
-					gen(c, e.args[1]);
-					emit(c, GGP_CMPI, GGP_SRC_TEMP, t, swap_cc(cc));
-					c.temps_used--;
-				}
-				return;
-			}
-			BinInfo b; int un;
-			if (!func_info(e.funcid, &b, &un)) { fail(c, "function %d not supported on the GPU path", e.funcid); return; }
-			if (!b.isbin)
-			{
-				gen(c, e.args[0]);
-				if (un > 0) emit(c, un, 0, 0);
-				return;
-			}
-			gen_binary(c, e, b.op, b.rop, b.cc, b.commut);
-			return;
-		}
-		case GG_E_AND:
-		case GG_E_OR:
-			gen_binary(c, e, e.kind == GG_E_AND ? GGP_AND : GGP_OR, 0, 0, true);
-			return;
-		case GG_E_NOT: gen(c, e.args[0]); emit(c, GGP_NOT, 0, 0); return;
-		case GG_E_ISNULL: gen(c, e.args[0]); emit(c, GGP_ISNULL, 0, 0); c.prog->nullable = 1; return;
-		case GG_E_ISNOTNULL: gen(c, e.args[0]); emit(c, GGP_ISNOTNULL, 0, 0); c.prog->nullable = 1; return;
-	}
-	fail(c, "expression kind %d not supported", e.kind);
-}
-
-ggp_span gen_span(Ctx &c, int root)
-{
-	ggp_span s;
-	s.start = (int16_t) c.prog->ncode;
-	c.temps_used = 0;
-	gen(c, root);
-	s.len = (int16_t) (c.prog->ncode - s.start);
-	return s;
+	ggp_program *p = c.prog;
+	if (p->ncode <= start) emit(c, GGP_NOP);
+	return &p->code[p->ncode - 1];
 }
 
 bool expr_equal(const gg_exprpool *pool, int a, int b)
@@ -287,46 +185,281 @@ bool expr_equal(const gg_exprpool *pool, int a, int b)
 	}
 }
 
-void init_side(ggp_side *s, const gg_tupdesc *d)
+/* does tree `root` contain a subtree equal to `sub`? */
+bool contains(const gg_exprpool *pool, int root, int sub)
 {
-	memset(s, 0, sizeof *s);
-	s->natts = d->natts;
-	for (int i = 0; i < d->natts && i < GG_MAX_ATTS; i++)
+	if (root < 0) return false;
+	if (expr_equal(pool, root, sub)) return true;
+	const gg_expr &e = pool->nodes[root];
+	if (e.kind == GG_E_VAR || e.kind == GG_E_CONST) return false;
+	for (int i = 0; i < e.nargs && i < 2; i++)
+		if (contains(pool, e.args[i], sub)) return true;
+	return false;
+}
+
+/* operand kinds a binary op can take directly */
+enum { OPD_NONE = 0, OPD_C8, OPD_C4, OPD_STR, OPD_K, OPD_T };
+struct Operand { int kind; int idx; };
+
+/* a node that can be used as a direct operand: Var, Const, or a subtree already kept in a temporary */
+Operand operand_of(Ctx &c, int root)
+{
+	Operand o = { OPD_NONE, 0 };
+	const gg_expr &e = c.pool->nodes[root];
+	for (int i = 0; i < c.npersist; i++)
+		if (expr_equal(c.pool, c.persist_root[i], root)) { o.kind = OPD_T; o.idx = c.persist_temp[i]; return o; }
+	if (e.kind == GG_E_VAR)
 	{
-		s->att[i].attlen = d->attrs[i].attlen;
-		s->att[i].attalign = d->attrs[i].attalign;
-		s->att[i].slot = -1;
-		s->att[i].cacheoff = -1;
-		s->att[i].notnull = d->attrs[i].attnotnull;
+		int slot = col_slot(c, e.varno, e.varattno);
+		const ggp_side *s = e.varno == 1 ? c.inner : c.outer;
+		if (c.failed) return o;
+		int lt = s->coltype[slot];
+		o.idx = slot | (e.varno == 1 ? 0x80 : 0);
+		o.kind = lt == GGP_LT_I4 ? OPD_C4 : lt == GGP_LT_I8 ? OPD_C8 : OPD_STR;
+		if (lt == GGP_LT_BOOL) o.kind = OPD_NONE;
+	}
+	else if (e.kind == GG_E_CONST)
+	{
+		o.kind = OPD_K;
+		o.idx = add_const(c, e.constvalue, e.constisnull != 0);
+	}
+	return o;
+}
+
+int swap_cc(int cc)
+{
+	switch (cc) { case GGP_LT: return GGP_GT; case GGP_LE: return GGP_GE; case GGP_GT: return GGP_LT; case GGP_GE: return GGP_LE; }
+	return cc;
+}
+
+enum { K_F8ADD = 1, K_F8SUB, K_F8MUL, K_F8DIV, K_CMPF, K_CMPI, K_CMPS, K_AND, K_OR };
+struct BinInfo { int k, cc; bool isbin; };
+
+bool func_info(int funcid, BinInfo *b, int *unary_op)
+{
+	*unary_op = 0;
+	b->isbin = true; b->cc = 0;
+	switch (funcid)
+	{
+		case GG_F_FLOAT8PL:  b->k = K_F8ADD; return true;
+		case GG_F_FLOAT8MUL: b->k = K_F8MUL; return true;
+		case GG_F_FLOAT8MI:  b->k = K_F8SUB; return true;
+		case GG_F_FLOAT8DIV: b->k = K_F8DIV; return true;
+#define CMPCASE(F, K, CC) case F: b->k = K; b->cc = CC; return true;
+		CMPCASE(GG_F_FLOAT8LT, K_CMPF, GGP_LT) CMPCASE(GG_F_FLOAT8LE, K_CMPF, GGP_LE)
+		CMPCASE(GG_F_FLOAT8EQ, K_CMPF, GGP_EQ) CMPCASE(GG_F_FLOAT8NE, K_CMPF, GGP_NE)
+		CMPCASE(GG_F_FLOAT8GT, K_CMPF, GGP_GT) CMPCASE(GG_F_FLOAT8GE, K_CMPF, GGP_GE)
+		CMPCASE(GG_F_INT4LT, K_CMPI, GGP_LT) CMPCASE(GG_F_INT4LE, K_CMPI, GGP_LE)
+		CMPCASE(GG_F_INT4EQ, K_CMPI, GGP_EQ) CMPCASE(GG_F_INT4NE, K_CMPI, GGP_NE)
+		CMPCASE(GG_F_INT4GT, K_CMPI, GGP_GT) CMPCASE(GG_F_INT4GE, K_CMPI, GGP_GE)
+		CMPCASE(GG_F_INT8LT, K_CMPI, GGP_LT) CMPCASE(GG_F_INT8LE, K_CMPI, GGP_LE)
+		CMPCASE(GG_F_INT8EQ, K_CMPI, GGP_EQ) CMPCASE(GG_F_INT8NE, K_CMPI, GGP_NE)
+		CMPCASE(GG_F_INT8GT, K_CMPI, GGP_GT) CMPCASE(GG_F_INT8GE, K_CMPI, GGP_GE)
+		CMPCASE(GG_F_DATE_LT, K_CMPI, GGP_LT) CMPCASE(GG_F_DATE_LE, K_CMPI, GGP_LE)
+		CMPCASE(GG_F_DATE_EQ, K_CMPI, GGP_EQ) CMPCASE(GG_F_DATE_NE, K_CMPI, GGP_NE)
+		CMPCASE(GG_F_DATE_GT, K_CMPI, GGP_GT) CMPCASE(GG_F_DATE_GE, K_CMPI, GGP_GE)
+		CMPCASE(GG_F_BPCHAREQ, K_CMPS, GGP_EQ) CMPCASE(GG_F_BPCHARNE, K_CMPS, GGP_NE)
+#undef CMPCASE
+		case GG_F_INT48: b->isbin = false; *unary_op = -1; return true;     /* loads already sign-extend */
+		case GG_F_I4TOD: case GG_F_I8TOD: b->isbin = false; *unary_op = GGP_I2F8; return true;
+	}
+	return false;
+}
+
+int date_ts_cc(int funcid)
+{
+	switch (funcid)
+	{
+		case GG_F_DATE_LT_TIMESTAMP: return GGP_LT; case GG_F_DATE_LE_TIMESTAMP: return GGP_LE;
+		case GG_F_DATE_EQ_TIMESTAMP: return GGP_EQ; case GG_F_DATE_GT_TIMESTAMP: return GGP_GT;
+		case GG_F_DATE_GE_TIMESTAMP: return GGP_GE; case GG_F_DATE_NE_TIMESTAMP: return GGP_NE;
+	}
+	return -1;
+}
+
+void gen(Ctx &c, int root);
+
+void emit_load(Ctx &c, const Operand &o, int root)
+{
+	const gg_expr &e = c.pool->nodes[root];
+	switch (o.kind)
+	{
+		case OPD_C8: emit(c, GGP_LD_C8, o.idx); return;
+		case OPD_C4: emit(c, GGP_LD_C4, o.idx); return;
+		case OPD_K: emit(c, GGP_LD_K, o.idx); return;
+		case OPD_T: emit(c, GGP_LD_T, o.idx); return;
+		case OPD_STR: emit(c, e.rettype == GG_BPCHAROID ? GGP_LD_BP : GGP_LD_VS, o.idx); return;
+	}
+	if (e.kind == GG_E_VAR && !c.failed)      /* bool column */
+	{
+		emit(c, GGP_LD_BOOL, col_slot(c, e.varno, e.varattno) | (e.varno == 1 ? 0x80 : 0));
+		return;
+	}
+	fail(c, "operand cannot be loaded");
+}
+
+/* acc = acc OP operand (reversed=false) or operand OP acc (reversed=true) */
+void emit_binop(Ctx &c, int k, int cc, const Operand &o, bool reversed)
+{
+	int base = 0;
+	switch (k)
+	{
+		case K_F8ADD: base = GGP_ADD_C; break;
+		case K_F8MUL: base = GGP_MUL_C; break;
+		case K_F8SUB: base = reversed ? GGP_RSUB_C : GGP_SUB_C; break;
+		case K_F8DIV: base = reversed ? GGP_RDIV_C : GGP_DIV_C; break;
+		case K_CMPF:
+			if (reversed) cc = swap_cc(cc);
+			if (o.kind == OPD_C8) emit(c, GGP_CMPF_C, o.idx, cc);
+			else if (o.kind == OPD_K) emit(c, GGP_CMPF_K, o.idx, cc);
+			else if (o.kind == OPD_T) emit(c, GGP_CMPF_T, o.idx, cc);
+			else fail(c, "float8 comparison with a non-float8 operand");
+			return;
+		case K_CMPI:
+			if (reversed) cc = swap_cc(cc);
+			if (o.kind == OPD_C8) emit(c, GGP_CMPI_C8, o.idx, cc);
+			else if (o.kind == OPD_C4) emit(c, GGP_CMPI_C4, o.idx, cc);
+			else if (o.kind == OPD_K) emit(c, GGP_CMPI_K, o.idx, cc);
+			else if (o.kind == OPD_T) emit(c, GGP_CMPI_T, o.idx, cc);
+			else fail(c, "integer comparison with a non-integer operand");
+			return;
+		case K_CMPS:
+			if (o.kind == OPD_K) emit(c, GGP_CMPS_K, o.idx, cc);
+			else if (o.kind == OPD_T) emit(c, GGP_CMPS_T, o.idx, cc);
+			else fail(c, "string comparison operand must be a constant or a temporary");
+			return;
+		case K_AND: case K_OR:
+			if (o.kind != OPD_T) { fail(c, "boolean operand must be a temporary"); return; }
+			emit(c, k == K_AND ? GGP_AND_T : GGP_OR_T, o.idx);
+			return;
+	}
+	if (o.kind == OPD_C8) emit(c, base, o.idx);
+	else if (o.kind == OPD_K) emit(c, base + 1, o.idx);
+	else if (o.kind == OPD_T) emit(c, base + 2, o.idx);
+	else fail(c, "float8 arithmetic on a non-float8 operand (missing cast)");
+}
+
+int alloc_temp(Ctx &c)
+{
+	for (int t = 0; t < 4; t++)
+		if (!(c.temps_busy & (1 << t))) { c.temps_busy |= 1 << t; return t; }
+	fail(c, "expression too deep");
+	return 0;
+}
+
+/* temp[t] = acc, as a post-action of the op that produced acc */
+void store_temp(Ctx &c, int t)
+{
+	ggp_op *o = &c.prog->code[c.prog->ncode - 1];
+	if (c.prog->ncode == 0 || (o->flags & GGP_F_ST)) { emit(c, GGP_NOP); o = &c.prog->code[c.prog->ncode - 1]; }
+	o->flags |= GGP_F_ST;
+	o->aux = (uint8_t) ((o->aux & ~0x30) | (t << 4));
+}
+
+void gen_binary(Ctx &c, int lroot, int rroot, int k, int cc)
+{
+	bool commut = (k == K_F8ADD || k == K_F8MUL || k == K_AND || k == K_OR);
+	bool logical = (k == K_AND || k == K_OR);
+	Operand ro = operand_of(c, rroot), lo = operand_of(c, lroot);
+	if (logical)
+	{
+		/* AND/OR take their second operand from a temporary only */
+		if (ro.kind != OPD_T) ro.kind = OPD_NONE;
+		if (lo.kind != OPD_T) lo.kind = OPD_NONE;
+	}
+	if (k == K_CMPS)
+	{
+		if (ro.kind == OPD_STR) ro.kind = OPD_NONE;     /* two string columns: one goes through a temp */
+		if (lo.kind == OPD_STR) lo.kind = OPD_NONE;
+	}
+	if (ro.kind != OPD_NONE)
+	{
+		gen(c, lroot);
+		emit_binop(c, k, cc, ro, false);
+	}
+	else if (lo.kind != OPD_NONE)
+	{
+		gen(c, rroot);
+		emit_binop(c, k, cc, lo, !commut);
+	}
+	else
+	{
+		gen(c, lroot);
+		int t = alloc_temp(c);
+		store_temp(c, t);
+		gen(c, rroot);
+		Operand to = { OPD_T, t };
+		emit_binop(c, k, cc, to, !commut);
+		c.temps_busy &= ~(1 << t);
 	}
 }
 
-long align_nominal(long off, char a)
+void gen(Ctx &c, int root)
 {
-	switch (a) { case 'i': return (off + 3) & ~3L; case 'c': return off; case 'd': return (off + 7) & ~7L; default: return (off + 1) & ~1L; }
-}
+	if (c.failed) return;
+	if (root < 0 || root >= c.pool->nnodes) { fail(c, "bad expression index %d", root); return; }
+	const gg_expr &e = c.pool->nodes[root];
+	Operand o = operand_of(c, root);
+	if (o.kind != OPD_NONE || e.kind == GG_E_VAR) { emit_load(c, o, root); return; }
 
-/* attcacheoff as slot_deform_tuple memoises it (heaptuple.c:1160-1200): valid for the fixed-width
- * prefix, and for the first varlena iff its offset is already aligned */
-void finish_side(ggp_side *s)
-{
-	long off = 0;
-	int i;
-	s->first_walk = s->natts;
-	for (i = 0; i < s->natts; i++)
+	switch (e.kind)
 	{
-		if (s->att[i].attlen == -1)
+		case GG_E_FUNC:
 		{
-			if (off == align_nominal(off, s->att[i].attalign)) s->att[i].cacheoff = (int16_t) off;
-			else { s->first_walk = i; break; }
-			s->first_walk = i + 1;      /* offset of the varlena itself is constant; what follows is not */
-			break;
+			int cc = date_ts_cc(e.funcid);
+			if (cc >= 0)
+			{
+				/* date_xx_timestamp(date, ts): promote the date, then integer compare (date.c:560-640) */
+				Operand ro = operand_of(c, e.args[1]);
+				if (ro.kind == OPD_K || ro.kind == OPD_C8 || ro.kind == OPD_T)
+				{
+					gen(c, e.args[0]);
+					emit(c, GGP_DATE2TS);
+					emit_binop(c, K_CMPI, cc, ro, false);
+				}
+				else
+				{
+					gen(c, e.args[1]);
+					int t = alloc_temp(c);
+					store_temp(c, t);
+					gen(c, e.args[0]);
+					emit(c, GGP_DATE2TS);
+					Operand to = { OPD_T, t };
+					emit_binop(c, K_CMPI, cc, to, false);
+					c.temps_busy &= ~(1 << t);
+				}
+				return;
+			}
+			BinInfo b; int un;
+			if (!func_info(e.funcid, &b, &un)) { fail(c, "function %d not supported on the GPU path", e.funcid); return; }
+			if (!b.isbin)
+			{
+				gen(c, e.args[0]);
+				if (un > 0) emit(c, un);
+				return;
+			}
+			gen_binary(c, e.args[0], e.args[1], b.k, b.cc);
+			return;
 		}
-		off = align_nominal(off, s->att[i].attalign);
-		s->att[i].cacheoff = (int16_t) off;
-		off += s->att[i].attlen;
+		case GG_E_AND:
+		case GG_E_OR:
+			gen_binary(c, e.args[0], e.args[1], e.kind == GG_E_AND ? K_AND : K_OR, 0);
+			return;
+		case GG_E_NOT: gen(c, e.args[0]); emit(c, GGP_NOT); return;
+		case GG_E_ISNULL: gen(c, e.args[0]); emit(c, GGP_ISNULL); c.prog->nullable = 1; return;
+		case GG_E_ISNOTNULL: gen(c, e.args[0]); emit(c, GGP_ISNOTNULL); c.prog->nullable = 1; return;
 	}
-	if (s->first_walk > s->natts) s->first_walk = s->natts;
+	fail(c, "expression kind %d not supported", e.kind);
+}
+
+/* generate an expression whose value must end in a fresh op (so that post-actions can attach) */
+ggp_op *gen_value(Ctx &c, int root)
+{
+	int start = c.prog->ncode;
+	c.temps_busy = 0;
+	for (int i = 0; i < c.npersist; i++) c.temps_busy |= 1 << c.persist_temp[i];
+	gen(c, root);
+	return last_op(c, start);
 }
 
 }  // namespace
@@ -336,9 +469,9 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 {
 	Ctx c;
 	memset(prog, 0, sizeof *prog);
+	memset(&c, 0, sizeof c);
 	c.pool = pool; c.prog = prog; c.outer = &prog->outer; c.inner = nullptr;
 	c.odesc = &scan->desc; c.idesc = nullptr; c.err = err; c.errlen = errlen;
-	c.temps_used = 0; c.failed = false;
 	if (err && errlen) err[0] = 0;
 
 	if (scan->desc.natts < 0 || scan->desc.natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return GG_ERR_UNSUPPORTED; }
@@ -350,12 +483,17 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 	}
 	init_side(&prog->outer, &scan->desc);
 
-	if (scan->qual >= 0) prog->qual = gen_span(c, scan->qual);
+	/* ---- scan qual ---- */
+	if (scan->qual >= 0)
+	{
+		ggp_op *o = gen_value(c, scan->qual);
+		if (!c.failed) o->flags |= GGP_F_FILTER;
+	}
+	/* ---- grouping keys ---- */
 	if (agg->numCols < 0 || agg->numCols > GG_MAX_KEYS) fail(c, "too many grouping columns");
 	prog->nkeys = agg->numCols;
 	for (int i = 0; i < agg->numCols && !c.failed; i++)
 	{
-		prog->key[i] = gen_span(c, agg->grpCol[i]);
 		int32_t t = pool->nodes[agg->grpCol[i]].rettype;
 		switch (t)
 		{
@@ -364,12 +502,24 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 			case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID: prog->keytype[i] = 3; break;
 			default: fail(c, "grouping column type %d not supported", t);
 		}
+		ggp_op *o = gen_value(c, agg->grpCol[i]);
+		if (c.failed) break;
+		if (o->flags & GGP_F_KEY) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+		o->flags |= GGP_F_KEY;
+		o->aux = (uint8_t) ((o->aux & 0x3F) | (i << 6));
+		if (i == agg->numCols - 1) o->flags |= GGP_F_GROUP;
+	}
+	if (agg->numCols == 0 && !c.failed)
+	{
+		emit(c, GGP_NOP);
+		prog->code[prog->ncode - 1].flags |= GGP_F_GROUP;
 	}
 	if (agg->numAggs < 0 || agg->numAggs > GG_MAX_AGGS) fail(c, "too many aggregates");
 	if (agg->aggstage == GG_AGGSTAGE_FINAL) fail(c, "FINAL stage runs through gg_agg_final");
 
-	/* aggregate arguments -> deduplicated accumulator columns */
+	/* ---- aggregate arguments -> deduplicated accumulator columns ---- */
 	int accroot[GGP_MAX_ACCS];
+	bool needsq[GGP_MAX_ACCS];
 	for (int i = 0; i < agg->numAggs && !c.failed; i++)
 	{
 		const gg_aggref &ar = agg->aggs[i];
@@ -391,8 +541,7 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 		int found = -1;
 		for (int j = 0; j < prog->nacc; j++)
 		{
-			bool compat = prog->acckind[j] == kind ||
-				(kind == GGP_ACC_COUNT && prog->acckind[j] != GGP_ACC_COUNT) ;
+			bool compat = prog->acckind[j] == kind || (kind == GGP_ACC_COUNT && prog->acckind[j] != GGP_ACC_COUNT);
 			if (compat && expr_equal(pool, accroot[j], ar.arg)) { found = j; break; }
 		}
 		if (found < 0)
@@ -400,13 +549,78 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 			if (prog->nacc >= GGP_MAX_ACCS) { fail(c, "too many distinct aggregate arguments"); continue; }
 			found = prog->nacc++;
 			accroot[found] = ar.arg;
+			needsq[found] = false;
 			prog->acckind[found] = (uint8_t) kind;
-			prog->acc[found] = gen_span(c, ar.arg);
 		}
-		if (sq) prog->accsq[found] = 1;
+		if (sq) needsq[found] = true;
 		aggmap[i].col = found;
 	}
-	finish_side(&prog->outer);
+	/* value slots: column j -> slot j; sums of squares get the slots after them */
+	prog->nslots = prog->nacc;
+	for (int j = 0; j < prog->nacc; j++)
+	{
+		prog->accsq[j] = -1;
+		if (needsq[j]) prog->accsq[j] = (int8_t) prog->nslots++;
+	}
+	if (prog->nslots > GGP_MAX_SLOTS) fail(c, "too many aggregate value slots");
+	/* A complex argument that reappears inside a later argument stays in a temporary
+	 * (e.g. Q1's l_extendedprice*(1-l_discount) inside sum_charge). */
+	c.npersist = 0;
+	for (int j = 0; j < prog->nacc && !c.failed; j++)
+	{
+		ggp_op *o = gen_value(c, accroot[j]);
+		if (c.failed) break;
+		const gg_expr &e = pool->nodes[accroot[j]];
+		bool complex_expr = !(e.kind == GG_E_VAR || e.kind == GG_E_CONST);
+		bool reused = false;
+		for (int k = j + 1; k < prog->nacc && complex_expr; k++)
+			if (contains(pool, accroot[k], accroot[j]) && !expr_equal(pool, accroot[k], accroot[j])) reused = true;
+		if (reused && c.npersist < 2 && operand_of(c, accroot[j]).kind != OPD_T)
+		{
+			int t = alloc_temp(c);
+			store_temp(c, t);
+			o = &prog->code[prog->ncode - 1];
+			c.persist_root[c.npersist] = accroot[j];
+			c.persist_temp[c.npersist] = t;
+			c.npersist++;
+		}
+		if (o->flags & (GGP_F_OUT | GGP_F_OUTSQ)) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+		o->flags |= GGP_F_OUT;
+		o->out = (uint8_t) j;
+		if (prog->accsq[j] >= 0) { o->flags |= GGP_F_OUTSQ; o->out2 = (uint8_t) prog->accsq[j]; }
+	}
+	emit(c, GGP_END);
+	c.npersist = 0;
+
+	/* private-accumulator kernel: NOT NULL float8 sums only */
+	prog->priv_ok = !prog->nullable;
+	for (int j = 0; j < prog->nacc; j++)
+		if (prog->acckind[j] != GGP_ACC_F8SUM) prog->priv_ok = 0;
 	if (c.failed) return GG_ERR_UNSUPPORTED;
 	return GG_OK;
+}
+
+/* human-readable listing of a compiled program (debugging, DESIGN.md examples) */
+int ggp_disasm(const ggp_program *p, char *buf, int cap)
+{
+	static const char *const N[] = { "END", "LD_C4", "LD_C8", "LD_BP", "LD_VS", "LD_BOOL", "LD_K", "LD_T",
+		"ADD_C", "ADD_K", "ADD_T", "SUB_C", "SUB_K", "SUB_T", "RSUB_C", "RSUB_K", "RSUB_T", "MUL_C", "MUL_K", "MUL_T",
+		"DIV_C", "DIV_K", "DIV_T", "RDIV_C", "RDIV_K", "RDIV_T", "CMPF_C", "CMPF_K", "CMPF_T",
+		"CMPI_C4", "CMPI_C8", "CMPI_K", "CMPI_T", "CMPS_K", "CMPS_T", "DATE2TS", "I2F8", "AND_T", "OR_T",
+		"NOT", "ISNULL", "ISNOTNULL", "NOP" };
+	int n = 0;
+	for (int i = 0; i < p->ncode && n < cap - 96; i++)
+	{
+		const ggp_op &o = p->code[i];
+		n += snprintf(buf + n, (size_t) (cap - n), "%3d %-8s idx=%-3d cc=%d off=%-5d", i,
+		              o.op < GGP_NOPS ? N[o.op] : "?", o.idx, o.aux & 7, o.off == 0xFFFF ? -1 : (int) o.off);
+		if (o.flags & GGP_F_ST) n += snprintf(buf + n, (size_t) (cap - n), " ST t%d", (o.aux >> 4) & 3);
+		if (o.flags & GGP_F_FILTER) n += snprintf(buf + n, (size_t) (cap - n), " FILTER");
+		if (o.flags & GGP_F_KEY) n += snprintf(buf + n, (size_t) (cap - n), " KEY%d", (o.aux >> 6) & 3);
+		if (o.flags & GGP_F_GROUP) n += snprintf(buf + n, (size_t) (cap - n), " GROUP");
+		if (o.flags & GGP_F_OUT) n += snprintf(buf + n, (size_t) (cap - n), " OUT%d", o.out);
+		if (o.flags & GGP_F_OUTSQ) n += snprintf(buf + n, (size_t) (cap - n), " OUTSQ%d", o.out2);
+		n += snprintf(buf + n, (size_t) (cap - n), "\n");
+	}
+	return n;
 }

@@ -1,9 +1,11 @@
 /*
  * gg_device.cuh — device-side building blocks shared by the kernels:
  *   - mbarrier / TMA bulk-copy PTX wrappers (sm_100a)
+ *   - shared-memory accessors on 32-bit shared addresses (pages are staged in shared memory;
+ *     explicit ld.shared keeps address arithmetic 32-bit and off the generic path)
  *   - heap page / tuple decoding (bufpage.h:153, itemid.h:24, htup_details.h:139,
  *     tupmacs.h:23-175, postgres.h:158-300 big-endian varlena headers)
- *   - the accumulator-machine interpreter for compiled expressions (gg_program.h)
+ *   - the accumulator-machine interpreter for compiled plans (gg_program.h)
  *   - bit-exact Jenkins hash / cdbhash / jump-consistent-hash (hashfunc.c:241-552,
  *     cdbhash.c:191-287,549-560)
  */
@@ -21,42 +23,56 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
 	return (uint32_t) __cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init()
 {
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
 	uint32_t done;
-	uint32_t addr = smem_u32(bar);
-	do
-	{
-		asm volatile(
-			"{\n\t.reg .pred p;\n\t"
-			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			"selp.u32 %0, 1, 0, p;\n\t}"
-			: "=r"(done) : "r"(addr), "r"(parity) : "memory");
-	} while (!done);
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	return done != 0;
+}
+/* wait with back-off: a waiting warp must not steal issue slots from the working ones */
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned sleep_ns)
+{
+	while (!mbar_try_wait(bar, parity))
+		__nanosleep(sleep_ns);
 }
 /* TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP) */
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar)
 {
 	asm volatile(
 		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+		::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
+
+/* shared-memory accessors on 32-bit shared addresses */
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double ldsf64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v)); }
+__device__ __forceinline__ void stsf64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 
 /* ---------------- hashing: bit-exact with hashfunc.c ---------------- */
 __device__ __forceinline__ uint32_t rot32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
@@ -65,10 +81,6 @@ __device__ __forceinline__ uint32_t rot32(uint32_t x, int k) { return (x << k) |
 	{ c ^= b; c -= rot32(b, 14); a ^= c; a -= rot32(c, 11); b ^= a; b -= rot32(a, 25); \
 	  c ^= b; c -= rot32(b, 16); a ^= c; a -= rot32(c, 4);  b ^= a; b -= rot32(a, 14); \
 	  c ^= b; c -= rot32(b, 24); }
-#define GGD_MIX(a, b, c) \
-	{ a -= c; a ^= rot32(c, 4);  c += b; b -= a; b ^= rot32(a, 6);  a += c; \
-	  c -= b; c ^= rot32(b, 8);  b += a; a -= c; a ^= rot32(c, 16); c += b; \
-	  b -= a; b ^= rot32(a, 19); a += c; c -= b; c ^= rot32(b, 4);  b += a; }
 
 /* hash_uint32, hashfunc.c:527 */
 __device__ __forceinline__ uint32_t hash_uint32(uint32_t k)
@@ -79,7 +91,7 @@ __device__ __forceinline__ uint32_t hash_uint32(uint32_t k)
 	GGD_FINAL(a, b, c);
 	return c;
 }
-/* hash_any over <= 8 bytes held LSB-first in a register (hashfunc.c:302; tail switch cases 1..8) */
+/* hash_any over <= 8 bytes held LSB-first in a register (hashfunc.c:302; tail switch cases 0..8) */
 __device__ __forceinline__ uint32_t hash_any_le8(uint64_t v, int len)
 {
 	uint32_t a, b, c;
@@ -127,7 +139,7 @@ __device__ __forceinline__ int32_t jump_consistent_hash(uint64_t key, int32_t ns
 	return (int32_t) b;
 }
 
-/* ---------------- tuple decoding ---------------- */
+/* ---------------- tuple decoding (all addresses are 32-bit shared addresses) ---------------- */
 __device__ __forceinline__ uint32_t align_nominal(uint32_t off, int attalign)
 {
 	/* tupmacs.h:121-130 */
@@ -135,40 +147,43 @@ __device__ __forceinline__ uint32_t align_nominal(uint32_t off, int attalign)
 	return (off + m) & ~m;
 }
 /* VARSIZE_ANY for inline datums, postgres.h:276.  0x80 (external TOAST pointer) and
- * compressed 4-byte headers are reported through *bad. */
-__device__ __forceinline__ uint32_t varsize_any(const uint8_t *p, bool *bad)
+ * compressed 4-byte headers are reported through bad. */
+__device__ __forceinline__ uint32_t varsize_any(uint32_t p, bool &bad)
 {
-	uint32_t h = p[0];
+	uint32_t h = lds8(p);
 	if (h & 0x80)
 	{
-		if (h == 0x80) { *bad = true; return 4; }
+		if (h == 0x80) { bad = true; return 4; }
 		return h & 0x7F;
 	}
-	if (h & 0x40) *bad = true;   /* compressed in line */
-	uint32_t l = ((h & 0x3F) << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3];
-	if (l < 4) { *bad = true; return 4; }
+	if (h & 0x40) bad = true;   /* compressed in line */
+	uint32_t l = ((h & 0x3F) << 24) | (lds8(p + 1) << 16) | (lds8(p + 2) << 8) | lds8(p + 3);
+	if (l < 4) { bad = true; return 4; }
 	return l;
 }
 
 /* Per-lane view of one tuple after the attribute walk */
 struct TupleView {
-	const uint8_t *tp;      /* start of user data (tuple + t_hoff) */
+	uint32_t tp;            /* shared address of the start of user data (tuple + t_hoff) */
 	uint32_t colnull;       /* bit s: column slot s is NULL */
 };
 
 /* The attribute walk: slot_deform_tuple (heaptuple.c:1119-1213) restricted to the attributes the
- * program references.  Offsets of referenced columns go to offs[slot*32 + lane] (shared memory).
- * Returns false (and sets err bits) if the tuple is malformed. */
-__device__ __forceinline__ void walk_tuple(const ggp_side &S, const uint8_t *tup, uint32_t tuplen,
-                                           uint16_t *offs, int lane, TupleView &tv, uint32_t &err)
+ * program references.  Offsets go to offs + (slot*32 + lane)*2 (shared memory).
+ *   fast == true  (no tuple of the warp carries a null bitmap): columns with a constant offset
+ *                 (attcacheoff) are addressed by the constant baked into the program; only the
+ *                 attributes from the first varlena on are walked and stored.
+ *   fast == false every referenced column gets its per-lane offset stored. */
+__device__ __forceinline__ void walk_tuple(const ggp_side &S, uint32_t tup, uint32_t tuplen, bool fast,
+                                           uint32_t offs, int lane, TupleView &tv, uint32_t &err)
 {
-	uint32_t infomask = *(const uint16_t *) (tup + 20);
-	uint32_t tnatts = *(const uint16_t *) (tup + 18) & GG_HEAP_NATTS_MASK;
-	uint32_t hoff = tup[22];
-	bool hasnulls = (infomask & GG_HEAP_HASNULL) != 0;
-	const uint8_t *bp = tup + GG_HEAP_HDR_SIZE;
-	const uint8_t *tp = tup + hoff;
-	uint32_t datalen = tuplen > hoff ? tuplen - hoff : 0;
+	const uint32_t infomask = lds16(tup + 20);
+	const uint32_t tnatts = lds16(tup + 18) & GG_HEAP_NATTS_MASK;
+	const uint32_t hoff = lds8(tup + 22);
+	const bool hasnulls = (infomask & GG_HEAP_HASNULL) != 0;
+	const uint32_t bp = tup + GG_HEAP_HDR_SIZE;
+	const uint32_t tp = tup + hoff;
+	const uint32_t datalen = tuplen > hoff ? tuplen - hoff : 0;
 	uint32_t colnull = 0;
 	bool bad = false;
 	int a0 = 0;
@@ -178,23 +193,28 @@ __device__ __forceinline__ void walk_tuple(const ggp_side &S, const uint8_t *tup
 	if (!hasnulls)
 	{
 		a0 = S.first_walk > 0 ? S.first_walk - 1 : 0;
-		if (a0 >= S.natts_walk) a0 = S.natts_walk;     /* everything referenced has a constant offset */
-		/* constant offsets (attcacheoff) for the fixed-width prefix */
-		for (int s = 0; s < S.ncols; s++)
+		if (a0 > S.natts_walk) a0 = S.natts_walk;
+		if (!fast)
 		{
-			int a = S.colatt[s];
-			if (a < a0 || a0 == S.natts_walk)
+			/* some other lane has NULLs: the program reads per-lane offsets, so publish the constants */
+			for (int s = 0; s < S.ncols; s++)
 			{
-				if ((uint32_t) a < tnatts) offs[s * 32 + lane] = (uint16_t) S.att[a].cacheoff;
-				else colnull |= 1u << s;               /* attribute added after the tuple was written */
+				int a = S.colatt[s];
+				if (a < a0) sts16(offs + (uint32_t) (s * 32 + lane) * 2, (uint32_t) S.att[a].cacheoff);
 			}
+		}
+		if (tnatts < (uint32_t) S.natts_walk)
+		{
+			/* attributes added after the tuple was written read as NULL (heaptuple.c:1252) */
+			for (int s = 0; s < S.ncols; s++)
+				if ((uint32_t) S.colatt[s] >= tnatts) colnull |= 1u << s;
 		}
 		if (a0 < S.natts_walk) off = a0 > 0 ? (uint32_t) S.att[a0].cacheoff : 0;
 	}
 	for (int a = a0; a < S.natts_walk; a++)
 	{
 		const ggp_attr at = S.att[a];
-		if ((uint32_t) a >= tnatts || (hasnulls && !(bp[a >> 3] & (1 << (a & 7)))))
+		if ((uint32_t) a >= tnatts || (hasnulls && !(lds8(bp + (a >> 3)) & (1u << (a & 7)))))
 		{
 			if (at.slot >= 0) colnull |= 1u << at.slot;
 			continue;
@@ -202,53 +222,46 @@ __device__ __forceinline__ void walk_tuple(const ggp_side &S, const uint8_t *tup
 		if (at.attlen == -1)
 		{
 			/* att_align_pointer: a zero byte is padding (or an aligned 4-byte header) */
-			if (off < datalen && tp[off] == 0) off = align_nominal(off, at.attalign);
+			if (off < datalen && lds8(tp + off) == 0) off = align_nominal(off, at.attalign);
 		}
 		else
 			off = align_nominal(off, at.attalign);
-		if (at.slot >= 0) offs[at.slot * 32 + lane] = (uint16_t) off;
+		if (at.slot >= 0) sts16(offs + (uint32_t) (at.slot * 32 + lane) * 2, off);
 		if (off >= datalen) { bad = true; break; }
-		off += at.attlen > 0 ? (uint32_t) at.attlen : varsize_any(tp + off, &bad);
+		off += at.attlen > 0 ? (uint32_t) at.attlen : varsize_any(tp + off, bad);
 		if (off > datalen) { bad = true; break; }
 	}
 	if (bad) err |= GGP_EF_BADPAGE;
 	tv.colnull = colnull;
 }
 
-/* load a referenced column into the 64-bit accumulator */
-__device__ __forceinline__ uint64_t load_col(const ggp_side &S, int slot, const TupleView &tv,
-                                             const uint16_t *offs, int lane, uint32_t &err)
+/* short string column -> <= 8 bytes packed LSB-first (VARDATA_ANY / VARSIZE_ANY_EXHDR, postgres.h:276-300;
+ * bcTruelen for bpchar, varchar.c:653) */
+__device__ __forceinline__ uint64_t load_str(uint32_t p, bool strip, uint32_t &err)
 {
-	const uint8_t *p = tv.tp + offs[slot * 32 + lane];
-	switch (S.coltype[slot])
+	uint32_t h = lds8(p), len, d;
+	if (h & 0x80)
 	{
-		case GGP_LD_I4: return (uint64_t) (int64_t) * (const int32_t *) p;
-		case GGP_LD_I8: return *(const uint64_t *) p;
-		case GGP_LD_BOOL: return (uint64_t) (p[0] != 0);
-		default:
+		if (h == 0x82)                                    /* the common char(1) / 1-byte value */
 		{
-			/* short string: VARDATA_ANY / VARSIZE_ANY_EXHDR, then bcTruelen for bpchar (varchar.c:653) */
-			uint32_t h = p[0], len;
-			const uint8_t *d;
-			if (h & 0x80)
-			{
-				if (h == 0x80) { err |= GGP_EF_STRING_TOO_LONG; return 0; }
-				len = (h & 0x7F) - 1; d = p + 1;
-			}
-			else
-			{
-				if (h & 0x40) { err |= GGP_EF_STRING_TOO_LONG; return 0; }
-				len = ((((h & 0x3F) << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3])) - 4;
-				d = p + 4;
-			}
-			if (S.coltype[slot] == GGP_LD_BPCHAR)
-				while (len > 0 && d[len - 1] == ' ') len--;
-			if (len > 8) { err |= GGP_EF_STRING_TOO_LONG; return 0; }
-			uint64_t v = 0;
-			for (uint32_t i = 0; i < len; i++) v |= (uint64_t) d[i] << (8 * i);
-			return v;
+			uint32_t b = lds8(p + 1);
+			return (strip && b == ' ') ? 0 : b;
 		}
+		if (h == 0x80) { err |= GGP_EF_STRING_TOO_LONG; return 0; }     /* TOAST pointer */
+		len = (h & 0x7F) - 1; d = p + 1;
 	}
+	else
+	{
+		if (h & 0x40) { err |= GGP_EF_STRING_TOO_LONG; return 0; }      /* compressed in line */
+		len = ((((h & 0x3F) << 24) | (lds8(p + 1) << 16) | (lds8(p + 2) << 8) | lds8(p + 3))) - 4;
+		d = p + 4;
+	}
+	if (strip)
+		while (len > 0 && lds8(d + len - 1) == ' ') len--;
+	if (len > 8) { err |= GGP_EF_STRING_TOO_LONG; return 0; }
+	uint64_t v = 0;
+	for (uint32_t i = 0; i < len; i++) v |= (uint64_t) lds8(d + i) << (8 * i);
+	return v;
 }
 
 __device__ __forceinline__ int f8_cmp(double a, double b)
@@ -272,116 +285,153 @@ __device__ __forceinline__ bool test_cc(int c, int cc)
 	}
 }
 __device__ __forceinline__ bool f8_isinf(double x) { return fabs(x) == __longlong_as_double(0x7ff0000000000000LL); }
+__device__ __forceinline__ bool f8_finite(double x) { return fabs(x) < __longlong_as_double(0x7ff0000000000000LL); }
 
-/* Run one compiled expression.  Result in acc/accnull.  NULLABLE=false compiles the null tracking out. */
-template <bool NULLABLE, bool HAS_INNER>
-__device__ __forceinline__ void run_span(const ggp_program &P, ggp_span sp,
-                                         const TupleView &tv, const uint16_t *offs,
-                                         const ggp_side *IS, const TupleView *itv, const uint16_t *ioffs,
-                                         int lane, uint64_t &acc, bool &accnull, uint32_t &err)
+/* CHECKFLOATVAL (float_utils.h:28), evaluated only when the result is not finite or is zero */
+__device__ __noinline__ uint32_t f8_check_slow(int kind /* 0 add/sub, 1 mul, 2 div */, double x, double y, double r)
 {
-	uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+	uint32_t e = 0;
+	if (f8_isinf(r) && !(f8_isinf(x) || f8_isinf(y))) e |= GGP_EF_FLOAT_OVERFLOW;
+	if (kind == 1 && r == 0.0 && !(x == 0.0 || y == 0.0)) e |= GGP_EF_FLOAT_UNDERFLOW;
+	if (kind == 2 && r == 0.0 && x != 0.0) e |= GGP_EF_FLOAT_UNDERFLOW;
+	return e;
+}
+
+/* normalise a grouping key so that bitwise equality == SQL equality for grouping */
+__device__ __forceinline__ uint64_t normalize_key(uint64_t v, int keytype)
+{
+	if (keytype == 2)
+	{
+		double d = __longlong_as_double((long long) v);
+		if (d == 0.0) return 0;                               /* -0 = +0 (float8eq) */
+		if (d != d) return 0x7ff8000000000000ull;             /* all NaNs are equal (float.c:964) */
+	}
+	return v;
+}
+
+/* Everything a running program needs to reach its operands */
+struct EvalCtx {
+	const ggp_program *P;
+	TupleView tv;           /* outer / scan tuple */
+	uint32_t offs;          /* shared address of its per-lane column offsets [slot*32 + lane] u16 */
+	bool fast;              /* constant offsets usable (no tuple of the warp has NULLs) */
+	const ggp_side *IS;     /* inner side (joins) or nullptr */
+	TupleView itv;
+	uint32_t ioffs;
+	bool ifast;
+	int lane;
+};
+
+/* The accumulator machine.  `Sink` receives the post-actions:
+ *     bool filter(bool pass)              -> row still live?
+ *     void key(int k, uint64_t v, bool n)
+ *     void group()
+ *     void out(int slot, double v, bool n)
+ * `live` = this lane carries a row that still counts; dead lanes keep executing (the op stream is
+ * warp-uniform) but raise no errors and produce no effects. */
+template <bool NULLABLE, bool HAS_INNER, class Sink>
+__device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &err, Sink &sink)
+{
+	const ggp_program &P = *X.P;
+	uint64_t acc = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+	bool accnull = false;
 	uint32_t tnull = 0;
-	acc = 0;
-	accnull = false;
-	const int end = sp.start + sp.len;
-	for (int pc = sp.start; pc < end; pc++)
+
+#define GG_COLADDR(O) \
+	((HAS_INNER && ((O).idx & 0x80)) \
+	 ? (X.itv.tp + ((X.ifast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.ioffs + (uint32_t) ((((O).idx & 0x7F) * 32) + X.lane) * 2))) \
+	 : (X.tv.tp + ((X.fast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.offs + (uint32_t) (((O).idx * 32) + X.lane) * 2))))
+#define GG_COLNULL(O) (NULLABLE && (((HAS_INNER && ((O).idx & 0x80)) ? (X.itv.colnull >> ((O).idx & 0x7F)) : (X.tv.colnull >> (O).idx)) & 1))
+#define GG_TEMP(IDX) ((IDX) == 0 ? t0 : (IDX) == 1 ? t1 : (IDX) == 2 ? t2 : t3)
+#define GG_TNULL(IDX) (NULLABLE && ((tnull >> (IDX)) & 1))
+#define GG_KNULL(IDX) (NULLABLE && ((P.constnull >> (IDX)) & 1))
+#define GG_D(V) __longlong_as_double((long long) (V))
+#define GG_ACCD GG_D(acc)
+#define GG_F8(KIND, EXPR, XV, YV, SN) \
+	{ const double x = (XV), y = (YV), r = (EXPR); const bool isn = NULLABLE && (accnull || (SN)); \
+	  if (!f8_finite(r) || ((KIND) != 0 && r == 0.0)) { if (live && !isn) err |= f8_check_slow((KIND), x, y, r); } \
+	  acc = (uint64_t) __double_as_longlong(r); accnull = isn; }
+#define GG_COLF8(O, SN, V) const bool SN = GG_COLNULL(O); const double V = SN ? 1.0 : ldsf64(GG_COLADDR(O));
+
+	for (int pc = 0;; pc++)
 	{
 		const ggp_op o = P.code[pc];
-		uint64_t sv = 0;
-		bool sn = false;
-		switch (o.src)
+		const int op = o.op;
+		/* most frequent first; the op stream is uniform across the warp, so these branches never diverge */
+		if (op == GGP_LD_C8) { accnull = GG_COLNULL(o); acc = accnull ? 0 : lds64(GG_COLADDR(o)); }
+		else if (op == GGP_MUL_C) { GG_COLF8(o, sn, v) GG_F8(1, __dmul_rn(x, y), GG_ACCD, v, sn) }
+		else if (op == GGP_MUL_T) { GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) }
+		else if (op == GGP_LD_K) { acc = (uint64_t) P.consts[o.idx]; accnull = GG_KNULL(o.idx); }
+		else if (op == GGP_ADD_C) { GG_COLF8(o, sn, v) GG_F8(0, __dadd_rn(x, y), GG_ACCD, v, sn) }
+		else if (op == GGP_SUB_C) { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), GG_ACCD, v, sn) }
+		else if (op == GGP_END) break;
+		else if (op == GGP_LD_C4) { accnull = GG_COLNULL(o); acc = accnull ? 0 : (uint64_t) (int64_t) (int32_t) lds32(GG_COLADDR(o)); }
+		else if (op == GGP_CMPI_K) { const int64_t y = P.consts[o.idx], x = (int64_t) acc;
+			acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); }
+		else if (op == GGP_LD_BP) { uint32_t e2 = 0; accnull = GG_COLNULL(o); acc = accnull ? 0 : load_str(GG_COLADDR(o), true, e2); if (live) err |= e2; }
+		else switch (op)
 		{
-			case GGP_SRC_COL:
-				if (NULLABLE) sn = (tv.colnull >> o.idx) & 1;
-				if (!sn) sv = load_col(P.outer, o.idx, tv, offs, lane, err);
-				break;
-			case GGP_SRC_ICOL:
-				if (HAS_INNER)
-				{
-					if (NULLABLE) sn = (itv->colnull >> o.idx) & 1;
-					if (!sn) sv = load_col(*IS, o.idx, *itv, ioffs, lane, err);
-				}
-				break;
-			case GGP_SRC_CONST:
-				sv = (uint64_t) P.consts[o.idx];
-				if (NULLABLE) sn = (P.constnull >> o.idx) & 1;
-				break;
-			case GGP_SRC_TEMP:
-				sv = o.idx == 0 ? t0 : o.idx == 1 ? t1 : o.idx == 2 ? t2 : t3;
-				if (NULLABLE) sn = (tnull >> o.idx) & 1;
-				break;
-			default: break;
-		}
-		switch (o.op)
-		{
-			case GGP_LOAD: acc = sv; accnull = sn; break;
-			case GGP_STORE:
-				if (o.idx == 0) t0 = acc; else if (o.idx == 1) t1 = acc; else if (o.idx == 2) t2 = acc; else t3 = acc;
-				if (NULLABLE) tnull = (tnull & ~(1u << o.idx)) | ((uint32_t) accnull << o.idx);
-				break;
-			case GGP_F8ADD: case GGP_F8SUB: case GGP_F8RSUB: case GGP_F8MUL: case GGP_F8DIV: case GGP_F8RDIV:
+			case GGP_LD_VS: { uint32_t e2 = 0; accnull = GG_COLNULL(o); acc = accnull ? 0 : load_str(GG_COLADDR(o), false, e2); if (live) err |= e2; } break;
+			case GGP_LD_BOOL: accnull = GG_COLNULL(o); acc = accnull ? 0 : (uint64_t) (lds8(GG_COLADDR(o)) != 0); break;
+			case GGP_LD_T: acc = GG_TEMP(o.idx); accnull = GG_TNULL(o.idx); break;
+			case GGP_ADD_K: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
+			case GGP_ADD_T: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
+			case GGP_SUB_K: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
+			case GGP_SUB_T: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
+			case GGP_RSUB_C: { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), v, GG_ACCD, sn) } break;
+			case GGP_RSUB_K: GG_F8(0, __dsub_rn(x, y), GG_D(P.consts[o.idx]), GG_ACCD, GG_KNULL(o.idx)) break;
+			case GGP_RSUB_T: GG_F8(0, __dsub_rn(x, y), GG_D(GG_TEMP(o.idx)), GG_ACCD, GG_TNULL(o.idx)) break;
+			case GGP_MUL_K: GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
+			case GGP_DIV_C: case GGP_DIV_K: case GGP_DIV_T: case GGP_RDIV_C: case GGP_RDIV_K: case GGP_RDIV_T:
 			{
-				double x = __longlong_as_double((long long) acc), y = __longlong_as_double((long long) sv), r;
-				if (o.op == GGP_F8RSUB || o.op == GGP_F8RDIV) { double t = x; x = y; y = t; }
-				bool isnull = NULLABLE && (accnull || sn);
-				if (o.op == GGP_F8ADD) r = __dadd_rn(x, y);
-				else if (o.op == GGP_F8SUB || o.op == GGP_F8RSUB) r = __dsub_rn(x, y);
-				else if (o.op == GGP_F8MUL) r = __dmul_rn(x, y);
-				else
-				{
-					if (y == 0.0 && !isnull) err |= GGP_EF_DIV_ZERO;
-					r = __ddiv_rn(x, y);
-				}
-				if (!isnull)
-				{
-					/* CHECKFLOATVAL, float_utils.h:28 */
-					if (f8_isinf(r) && !(f8_isinf(x) || f8_isinf(y))) err |= GGP_EF_FLOAT_OVERFLOW;
-					if (o.op == GGP_F8MUL && r == 0.0 && !(x == 0.0 || y == 0.0)) err |= GGP_EF_FLOAT_UNDERFLOW;
-					if ((o.op == GGP_F8DIV || o.op == GGP_F8RDIV) && r == 0.0 && x != 0.0 && y != 0.0) err |= GGP_EF_FLOAT_UNDERFLOW;
-				}
-				acc = (uint64_t) __double_as_longlong(r);
-				accnull = isnull;
+				/* float8div (float.c:808): division by zero is its own error */
+				const int v3 = (op - GGP_DIV_C) % 3;
+				const bool rev = op >= GGP_RDIV_C;
+				bool sn;
+				double v;
+				if (v3 == 0) { sn = GG_COLNULL(o); v = sn ? 1.0 : ldsf64(GG_COLADDR(o)); }
+				else if (v3 == 1) { sn = GG_KNULL(o.idx); v = GG_D(P.consts[o.idx]); }
+				else { sn = GG_TNULL(o.idx); v = GG_D(GG_TEMP(o.idx)); }
+				const double xn = rev ? v : GG_ACCD, yd = rev ? GG_ACCD : v;
+				if (live && !(NULLABLE && (accnull || sn)) && yd == 0.0) err |= GGP_EF_DIV_ZERO;
+				GG_F8(2, __ddiv_rn(x, y), xn, yd, sn)
 				break;
 			}
-			case GGP_CMPF8:
-				acc = test_cc(f8_cmp(__longlong_as_double((long long) acc), __longlong_as_double((long long) sv)), o.aux);
-				if (NULLABLE) accnull = accnull || sn;
-				break;
-			case GGP_CMPI:
-			{
-				int64_t x = (int64_t) acc, y = (int64_t) sv;
-				acc = test_cc((x > y) - (x < y), o.aux);
-				if (NULLABLE) accnull = accnull || sn;
-				break;
-			}
-			case GGP_CMPSTR:
-				acc = (o.aux == GGP_EQ) ? (acc == sv) : (acc != sv);
-				if (NULLABLE) accnull = accnull || sn;
-				break;
+			case GGP_CMPF_C: { GG_COLF8(o, sn, v) acc = test_cc(f8_cmp(GG_ACCD, v), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
+			case GGP_CMPF_K: acc = test_cc(f8_cmp(GG_ACCD, GG_D(P.consts[o.idx])), o.aux & 7); if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); break;
+			case GGP_CMPF_T: acc = test_cc(f8_cmp(GG_ACCD, GG_D(GG_TEMP(o.idx))), o.aux & 7); if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); break;
+			case GGP_CMPI_C4: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) (int32_t) lds32(GG_COLADDR(o)), x = (int64_t) acc;
+				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
+			case GGP_CMPI_C8: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) lds64(GG_COLADDR(o)), x = (int64_t) acc;
+				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
+			case GGP_CMPI_T: { const int64_t y = (int64_t) GG_TEMP(o.idx), x = (int64_t) acc;
+				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); } break;
+			case GGP_CMPS_K: acc = ((o.aux & 7) == GGP_EQ) ? (acc == (uint64_t) P.consts[o.idx]) : (acc != (uint64_t) P.consts[o.idx]);
+				if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); break;
+			case GGP_CMPS_T: acc = ((o.aux & 7) == GGP_EQ) ? (acc == GG_TEMP(o.idx)) : (acc != GG_TEMP(o.idx));
+				if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); break;
 			case GGP_DATE2TS:
 			{
-				/* date2timestamp, date.c:457 */
-				int32_t d = (int32_t) acc;
+				/* date2timestamp, date.c:457: +-infinity map to +-infinity; otherwise days * USECS_PER_DAY,
+				 * "date out of range for timestamp" when that overflows int64 (|d| > 106751991) */
+				const int32_t d = (int32_t) acc;
 				int64_t r;
 				if (d == INT32_MIN) r = INT64_MIN;
 				else if (d == INT32_MAX) r = INT64_MAX;
 				else
 				{
-					r = (int64_t) d * 86400000000LL;      /* wraps like the reference's int64 multiply */
-					if (r / 86400000000LL != d && !(NULLABLE && accnull)) err |= GGP_EF_DATE_RANGE;
+					r = (int64_t) d * 86400000000LL;
+					if ((d > 106751991 || d < -106751991) && live && !(NULLABLE && accnull)) err |= GGP_EF_DATE_RANGE;
 				}
 				acc = (uint64_t) r;
 				break;
 			}
-			case GGP_I2F8:
-				acc = (uint64_t) __double_as_longlong((double) (int64_t) acc);
-				break;
-			case GGP_AND:
-			case GGP_OR:
+			case GGP_I2F8: acc = (uint64_t) __double_as_longlong((double) (int64_t) acc); break;
+			case GGP_AND_T:
+			case GGP_OR_T:
 			{
-				bool a = acc != 0, b = sv != 0, an = NULLABLE && accnull, bn = NULLABLE && sn;
-				if (o.op == GGP_AND)
+				const bool a = acc != 0, b = GG_TEMP(o.idx) != 0, an = NULLABLE && accnull, bn = GG_TNULL(o.idx);
+				if (op == GGP_AND_T)
 				{
 					if ((!an && !a) || (!bn && !b)) { acc = 0; accnull = false; }
 					else if (an || bn) { acc = 0; accnull = true; }
@@ -398,21 +448,33 @@ __device__ __forceinline__ void run_span(const ggp_program &P, ggp_span sp,
 			case GGP_NOT: acc = (acc == 0); break;
 			case GGP_ISNULL: acc = accnull; accnull = false; break;
 			case GGP_ISNOTNULL: acc = !accnull; accnull = false; break;
-			default: break;
+			default: break;                         /* GGP_NOP */
+		}
+
+		if (o.flags)
+		{
+			if (o.flags & GGP_F_ST)
+			{
+				const int t = (o.aux >> 4) & 3;
+				if (t == 0) t0 = acc; else if (t == 1) t1 = acc; else if (t == 2) t2 = acc; else t3 = acc;
+				if (NULLABLE) tnull = (tnull & ~(1u << t)) | ((uint32_t) accnull << t);
+			}
+			if (o.flags & GGP_F_FILTER) live = sink.filter(live && !accnull && acc != 0);
+			if (o.flags & GGP_F_KEY) sink.key((o.aux >> 6) & 3, acc, accnull);
+			if (o.flags & GGP_F_GROUP) live = sink.group(live);
+			if (o.flags & GGP_F_OUT) sink.out(o.out, GG_ACCD, accnull);
+			if (o.flags & GGP_F_OUTSQ) { const double v = GG_ACCD; sink.out(o.out2, __dmul_rn(v, v), accnull); }
 		}
 	}
-}
-
-/* normalise a grouping key so that bitwise equality == SQL equality for grouping */
-__device__ __forceinline__ uint64_t normalize_key(uint64_t v, int keytype)
-{
-	if (keytype == 2)
-	{
-		double d = __longlong_as_double((long long) v);
-		if (d == 0.0) return 0;                               /* -0 = +0 (float8eq) */
-		if (d != d) return 0x7ff8000000000000ull;             /* all NaNs are equal (float.c:964) */
-	}
-	return v;
+#undef GG_COLADDR
+#undef GG_COLNULL
+#undef GG_TEMP
+#undef GG_TNULL
+#undef GG_KNULL
+#undef GG_F8
+#undef GG_ACCD
+#undef GG_D
+#undef GG_COLF8
 }
 
 }  // namespace ggd

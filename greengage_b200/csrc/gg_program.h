@@ -3,11 +3,13 @@
  * structures and hands to the kernels as a __grid_constant__ parameter.
  *
  * The reference evaluates Expr trees with one fmgr call per node per row
- * (execQual.c:2169,6260; SURVEY §8a rows 5,7).  Here the tree is flattened once
- * per plan into an accumulator machine: one 64-bit accumulator + null flag and
- * four temporaries per lane, every lane of a warp running the same op on its
- * own tuple.  Each op is a single IEEE/integer operation applied in the same
- * order as the tree, so per-row values are bit-identical to the reference's.
+ * (execQual.c:2169,6260; SURVEY §8a rows 5,7).  Here the whole per-row work of
+ * a SeqScan -> qual -> Agg slice — scan qual, grouping keys, every aggregate
+ * argument — is flattened once per plan into ONE straight-line program for an
+ * accumulator machine: a 64-bit accumulator + null flag and four temporaries
+ * per lane, every lane of a warp running the same op on its own tuple.  Each
+ * arithmetic op is a single IEEE/integer operation applied in the same order as
+ * the tree, so per-row values are bit-identical to the reference's.
  */
 #ifndef GG_PROGRAM_H
 #define GG_PROGRAM_H
@@ -17,53 +19,66 @@
 
 #define GGP_MAX_COLS    16     /* distinct referenced columns per side */
 #define GGP_MAX_CONSTS  24
-#define GGP_MAX_CODE    224
+#define GGP_MAX_CODE    160
 #define GGP_MAX_ACCS    16     /* accumulator columns (deduplicated aggregate arguments) */
-#define GGP_MAX_PAIRS   128    /* fast path: groups x accumulator columns held in registers */
-#define GGP_FAST_GROUPS 32     /* fast path: groups per block table */
+#define GGP_MAX_SLOTS   24     /* value slots: columns + their sums of squares */
+#define GGP_MAX_PAIRS   128    /* transposed kernel: (group, slot) pairs held in registers across a warp */
+#define GGP_FAST_GROUPS 32     /* groups per block table */
 
 /* how a referenced column is loaded into the 64-bit accumulator */
 enum ggp_loadtype {
-	GGP_LD_I4 = 1,       /* int4/date: sign-extended */
-	GGP_LD_I8 = 2,       /* int8/timestamp/float8 bits */
-	GGP_LD_BPCHAR = 3,   /* short string, trailing blanks stripped (bcTruelen), <= 8 bytes packed LSB-first */
-	GGP_LD_VARCHAR = 4,  /* short string, not stripped */
-	GGP_LD_BOOL = 5
+	GGP_LT_I4 = 1,       /* int4/date: sign-extended */
+	GGP_LT_I8 = 2,       /* int8/timestamp/float8 bits */
+	GGP_LT_BPCHAR = 3,   /* short string, trailing blanks stripped (bcTruelen), <= 8 bytes packed LSB-first */
+	GGP_LT_VARCHAR = 4,  /* short string, not stripped */
+	GGP_LT_BOOL = 5
 };
 
-enum ggp_src {           /* operand kinds */
-	GGP_SRC_NONE = 0,
-	GGP_SRC_COL = 1,     /* column slot of the outer (scan) tuple */
-	GGP_SRC_CONST = 2,
-	GGP_SRC_TEMP = 3,
-	GGP_SRC_ICOL = 4     /* column slot of the inner tuple (joins) */
-};
-
+/* Opcodes.  Operation and operand kind are fused into one opcode.  Operand suffixes: _C column (8-byte
+ * load), _C4 int4/date column (sign-extended), _K constant, _T temporary.  idx = slot/const/temp index;
+ * idx bit 7 on a column operand = inner tuple of a join.  aux bits 0-2 = ggp_cc for compares. */
 enum ggp_opcode {
-	GGP_LOAD = 1,        /* acc = src */
-	GGP_STORE,           /* temp[idx] = acc */
-	GGP_F8ADD, GGP_F8SUB, GGP_F8RSUB, GGP_F8MUL, GGP_F8DIV, GGP_F8RDIV,   /* float.c:782-850 incl. CHECKFLOATVAL */
-	GGP_CMPF8,           /* acc = float8_cmp_internal(acc, src) cc  (float.c:964) ; cc in aux */
-	GGP_CMPI,            /* acc = (int64)acc cc (int64)src */
-	GGP_CMPSTR,          /* acc = packed strings equal / not equal (bpchareq on stripped bytes) */
-	GGP_DATE2TS,         /* acc = date2timestamp(acc)  (date.c:457) */
-	GGP_I2F8,            /* acc = (double)(int64)acc   (i4tod / i8tod) */
-	GGP_AND, GGP_OR,     /* 3-valued, src = temp/col/const (execQual.c:3404,3455) */
-	GGP_NOT, GGP_ISNULL, GGP_ISNOTNULL
+	GGP_END = 0,
+	GGP_LD_C4, GGP_LD_C8, GGP_LD_BP, GGP_LD_VS, GGP_LD_BOOL, GGP_LD_K, GGP_LD_T,
+	GGP_ADD_C, GGP_ADD_K, GGP_ADD_T,            /* float8pl   (float.c:782) */
+	GGP_SUB_C, GGP_SUB_K, GGP_SUB_T,            /* float8mi   acc - x */
+	GGP_RSUB_C, GGP_RSUB_K, GGP_RSUB_T,         /*            x - acc */
+	GGP_MUL_C, GGP_MUL_K, GGP_MUL_T,            /* float8mul */
+	GGP_DIV_C, GGP_DIV_K, GGP_DIV_T,            /* float8div  acc / x */
+	GGP_RDIV_C, GGP_RDIV_K, GGP_RDIV_T,         /*            x / acc */
+	GGP_CMPF_C, GGP_CMPF_K, GGP_CMPF_T,         /* float8_cmp_internal(acc, x) cc  (float.c:964) */
+	GGP_CMPI_C4, GGP_CMPI_C8, GGP_CMPI_K, GGP_CMPI_T,   /* signed 64-bit compare */
+	GGP_CMPS_K, GGP_CMPS_T,                     /* packed strings equal / not equal (bpchareq on stripped bytes) */
+	GGP_DATE2TS,                                /* date2timestamp (date.c:457) */
+	GGP_I2F8,                                   /* i4tod / i8tod */
+	GGP_AND_T, GGP_OR_T,                        /* 3-valued (execQual.c:3404,3455) */
+	GGP_NOT, GGP_ISNULL, GGP_ISNOTNULL,
+	GGP_NOP,                                    /* carries post-actions only */
+	GGP_NOPS
 };
 
 enum ggp_cc { GGP_LT = 0, GGP_LE, GGP_EQ, GGP_NE, GGP_GT, GGP_GE };
 
+/* post-actions, applied to the accumulator after the op, in this order */
+#define GGP_F_ST      0x01     /* temp[(aux >> 4) & 3] = acc */
+#define GGP_F_FILTER  0x02     /* the row passes only if acc is TRUE (NULL is not true, execQual.c:6300) */
+#define GGP_F_KEY     0x04     /* grouping key [(aux >> 6) & 3] = acc */
+#define GGP_F_GROUP   0x08     /* all keys known: find/insert the group */
+#define GGP_F_OUT     0x10     /* value slot[out] = acc */
+#define GGP_F_OUTSQ   0x20     /* value slot[out2] = acc * acc  (float8_accum's sumX2, float.c:1878) */
+
 typedef struct ggp_op {
-	uint8_t op;
-	uint8_t src;         /* ggp_src */
-	uint8_t idx;         /* slot / const / temp index */
-	uint8_t aux;         /* cc for compares */
-} ggp_op;
+	uint8_t  op;
+	uint8_t  idx;
+	uint8_t  aux;
+	uint8_t  flags;
+	uint16_t off;        /* column operand: constant offset (attcacheoff) usable when the tuple has no NULLs, else 0xFFFF */
+	uint8_t  out, out2;
+} ggp_op;                /* 8 bytes */
 
 /* accumulator column kinds */
 enum ggp_acckind {
-	GGP_ACC_F8SUM = 1,   /* sum and (if sq) sum of squares of a float8 expression + non-null count */
+	GGP_ACC_F8SUM = 1,   /* sum (and, through a second slot, sum of squares) of a float8 expression */
 	GGP_ACC_F8MIN, GGP_ACC_F8MAX,
 	GGP_ACC_I8SUM, GGP_ACC_I8MIN, GGP_ACC_I8MAX,
 	GGP_ACC_COUNT        /* non-null count only (count(expr)); count(*) needs no column */
@@ -82,14 +97,12 @@ typedef struct ggp_attr {
 typedef struct ggp_side {
 	int32_t natts;           /* attributes in the descriptor */
 	int32_t natts_walk;      /* walk attributes [0, natts_walk) : highest referenced attno */
-	int32_t first_walk;      /* first attribute whose offset is not a constant (no-NULL tuples start walking here) */
+	int32_t first_walk;      /* first attribute whose offset is not a constant (no-NULL tuples start walking at first_walk-1) */
 	int32_t ncols;
 	ggp_attr att[GG_MAX_ATTS];
 	uint8_t  coltype[GGP_MAX_COLS];   /* ggp_loadtype per slot */
 	uint8_t  colatt[GGP_MAX_COLS];    /* 0-based attribute per slot */
 } ggp_side;
-
-typedef struct ggp_span { int16_t start, len; } ggp_span;
 
 typedef struct ggp_program {
 	ggp_side outer;
@@ -98,15 +111,14 @@ typedef struct ggp_program {
 	int64_t  consts[GGP_MAX_CONSTS];
 	int32_t  constnull;      /* bit i: const i is NULL */
 	int32_t  ncode;
-	ggp_op   code[GGP_MAX_CODE];
-	ggp_span qual;           /* len 0: no qual */
+	ggp_op   code[GGP_MAX_CODE];     /* qual (FILTER) ; keys (KEY.., GROUP) ; aggregate arguments (OUT/OUTSQ) ; END */
 	int32_t  nkeys;
-	ggp_span key[GG_MAX_KEYS];
 	uint8_t  keytype[GG_MAX_KEYS];    /* 1 int, 2 float8 (normalise -0/NaN), 3 string */
-	int32_t  nacc;
-	ggp_span acc[GGP_MAX_ACCS];
+	int32_t  nacc;           /* accumulator columns */
 	uint8_t  acckind[GGP_MAX_ACCS];
-	uint8_t  accsq[GGP_MAX_ACCS];     /* float8 sum also needs sum of squares (avg's float8_accum state) */
+	int8_t   accsq[GGP_MAX_ACCS];     /* value slot of the column's sum of squares (avg's float8_accum state), or -1 */
+	int32_t  nslots;         /* value slots = nacc + number of sum-of-squares slots; slot j < nacc is column j */
+	int32_t  priv_ok;        /* 1: every column is a NOT NULL float8 sum => private-accumulator kernel applies */
 } ggp_program;
 
 /* One partial group record: what a block (or a segment, for the FINAL stage) knows about one group.
@@ -127,7 +139,7 @@ typedef struct ggp_grec {
 #define GGP_EF_DIV_ZERO         0x04
 #define GGP_EF_VISIBILITY       0x08
 #define GGP_EF_BADPAGE          0x10
-#define GGP_EF_GROUP_OVERFLOW   0x20   /* more groups than the fast path holds: rerun on the general path */
+#define GGP_EF_GROUP_OVERFLOW   0x20   /* more groups than the kernel variant holds: rerun on a wider variant */
 #define GGP_EF_STRING_TOO_LONG  0x40
 #define GGP_EF_DATE_RANGE       0x80
 #define GGP_EF_NOTNULL_VIOLATED 0x100
@@ -145,6 +157,7 @@ struct ggp_aggmap {          /* how each Aggref reads the accumulator columns */
 };
 int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
                         ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen);
+int ggp_disasm(const ggp_program *p, char *buf, int cap);
 #endif
 
 #endif /* GG_PROGRAM_H */

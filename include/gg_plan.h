@@ -215,6 +215,8 @@ typedef struct gg_agg {             /* Agg (AGG_HASHED or AGG_PLAIN when numCols
 	int32_t   numAggs;
 	int32_t   pad;
 	gg_aggref aggs[GG_MAX_AGGS];
+	int64_t   numGroups;                /* planner's estimate (Agg.numGroups, plannodes.h); 0 = unknown.
+	                                     * Sizes the hash table as in create_agg_hash_table (execHHashagg.c:810) */
 } gg_agg;
 
 enum gg_jointype {                  /* nodes/nodes.h JoinType */
