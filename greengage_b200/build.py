@@ -36,20 +36,38 @@ def _all_headers():
     return hs
 
 
+def embed_sources():
+    """The kernel headers as string literals, for run-time plan specialisation (gg_jit.cpp)."""
+    files = [("gg_plan_h", os.path.join(ROOT, "include", "gg_plan.h")), ("gg_program_h", os.path.join(CSRC, "gg_program.h")),
+             ("gg_device_cuh", os.path.join(CSRC, "gg_device.cuh")), ("gg_scanagg_kernel_cuh", os.path.join(CSRC, "gg_scanagg_kernel.cuh"))]
+    out = os.path.join(BUILD, "gg_jit_sources.inc")
+    if not _newer(out, [f for _, f in files]):
+        return out
+    with open(out, "w") as fo:
+        for name, path in files:
+            text = open(path).read()
+            fo.write("static const char *const kSrc_%s =\n" % name)
+            for i in range(0, len(text), 8000):        # string literals are limited in length; concatenate pieces
+                fo.write('R"GGSRC(%s)GGSRC"\n' % text[i:i + 8000])
+            fo.write(";\n")
+    return out
+
+
 def build_device(verbose=False, force=False):
     os.makedirs(BUILD, exist_ok=True)
+    embed_sources()
     objs = []
-    hdrs = _all_headers()
+    hdrs = _all_headers() + [os.path.join(BUILD, "gg_jit_sources.inc")]
     for src in [s for s in os.listdir(CSRC) if s.endswith((".cu", ".cpp"))]:
         path = os.path.join(CSRC, src)
         obj = os.path.join(BUILD, src.rsplit(".", 1)[0] + ".o")
         if force or _newer(obj, [path] + hdrs):
-            cmd = [NVCC] + NVFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [NVCC] + NVFLAGS + ["-I", BUILD] + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             subprocess.check_call(cmd)
         objs.append(obj)
     out = os.path.join(HERE, "libggb200.so")
     if force or _newer(out, objs):
-        subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", out] + objs)
+        subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", out] + objs + ["-ldl"])
     return out
 
 

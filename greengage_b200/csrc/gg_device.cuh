@@ -173,66 +173,85 @@ struct TupleView {
  *   fast == true  (no tuple of the warp carries a null bitmap): columns with a constant offset
  *                 (attcacheoff) are addressed by the constant baked into the program; only the
  *                 attributes from the first varlena on are walked and stored.
- *   fast == false every referenced column gets its per-lane offset stored. */
+ *   fast == false every referenced column gets its per-lane offset stored.
+ * The walk is split into begin / one step per attribute / end so that a plan-specialised kernel can
+ * emit the steps with literal attribute properties (everything then folds at compile time). */
+struct WalkState {
+	uint32_t tup, tp, bp, datalen, tnatts, off, colnull;
+	bool hasnulls, bad;
+};
+
+__device__ __forceinline__ void walk_begin(WalkState &W, uint32_t tup, uint32_t tuplen)
+{
+	const uint32_t infomask = lds16(tup + 20);
+	const uint32_t hoff = lds8(tup + 22);
+	W.tup = tup;
+	W.tnatts = lds16(tup + 18) & GG_HEAP_NATTS_MASK;
+	W.hasnulls = (infomask & GG_HEAP_HASNULL) != 0;
+	W.bp = tup + GG_HEAP_HDR_SIZE;
+	W.tp = tup + hoff;
+	W.datalen = tuplen > hoff ? tuplen - hoff : 0;
+	W.colnull = 0;
+	W.bad = false;
+	W.off = 0;
+}
+/* publish the constant offset of a column in the fixed prefix (only needed when !fast) */
+__device__ __forceinline__ void walk_publish_const(WalkState &W, int slot, int att, int cacheoff, uint32_t offs, int lane)
+{
+	if ((uint32_t) att >= W.tnatts) W.colnull |= 1u << slot;    /* added after the tuple was written: NULL (heaptuple.c:1252) */
+	else sts16(offs + (uint32_t) (slot * 32 + lane) * 2, (uint32_t) cacheoff);
+}
+/* one attribute of the walk */
+__device__ __forceinline__ void walk_step(WalkState &W, int a, int attlen, int attalign, int slot, uint32_t offs, int lane)
+{
+	if (W.bad) return;
+	if ((uint32_t) a >= W.tnatts || (W.hasnulls && !(lds8(W.bp + (a >> 3)) & (1u << (a & 7)))))
+	{
+		if (slot >= 0) W.colnull |= 1u << slot;
+		return;
+	}
+	uint32_t off = W.off;
+	if (attlen == -1)
+	{
+		/* att_align_pointer: a zero byte is padding (or an aligned 4-byte header) */
+		if (off < W.datalen && lds8(W.tp + off) == 0) off = align_nominal(off, attalign);
+	}
+	else
+		off = align_nominal(off, attalign);
+	if (slot >= 0) sts16(offs + (uint32_t) (slot * 32 + lane) * 2, off);
+	if (off >= W.datalen) { W.bad = true; return; }
+	off += attlen > 0 ? (uint32_t) attlen : varsize_any(W.tp + off, W.bad);
+	if (off > W.datalen) W.bad = true;
+	W.off = off;
+}
+
+/* table-driven walk (the interpreter path) */
 __device__ __forceinline__ void walk_tuple(const ggp_side &S, uint32_t tup, uint32_t tuplen, bool fast,
                                            uint32_t offs, int lane, TupleView &tv, uint32_t &err)
 {
-	const uint32_t infomask = lds16(tup + 20);
-	const uint32_t tnatts = lds16(tup + 18) & GG_HEAP_NATTS_MASK;
-	const uint32_t hoff = lds8(tup + 22);
-	const bool hasnulls = (infomask & GG_HEAP_HASNULL) != 0;
-	const uint32_t bp = tup + GG_HEAP_HDR_SIZE;
-	const uint32_t tp = tup + hoff;
-	const uint32_t datalen = tuplen > hoff ? tuplen - hoff : 0;
-	uint32_t colnull = 0;
-	bool bad = false;
+	WalkState W;
+	walk_begin(W, tup, tuplen);
 	int a0 = 0;
-	uint32_t off = 0;
-
-	tv.tp = tp;
-	if (!hasnulls)
+	if (!W.hasnulls)
 	{
 		a0 = S.first_walk > 0 ? S.first_walk - 1 : 0;
 		if (a0 > S.natts_walk) a0 = S.natts_walk;
-		if (!fast)
-		{
-			/* some other lane has NULLs: the program reads per-lane offsets, so publish the constants */
+		if (!fast || W.tnatts < (uint32_t) S.natts_walk)
 			for (int s = 0; s < S.ncols; s++)
 			{
 				int a = S.colatt[s];
-				if (a < a0) sts16(offs + (uint32_t) (s * 32 + lane) * 2, (uint32_t) S.att[a].cacheoff);
+				if (a < a0) walk_publish_const(W, s, a, S.att[a].cacheoff, offs, lane);
 			}
-		}
-		if (tnatts < (uint32_t) S.natts_walk)
-		{
-			/* attributes added after the tuple was written read as NULL (heaptuple.c:1252) */
-			for (int s = 0; s < S.ncols; s++)
-				if ((uint32_t) S.colatt[s] >= tnatts) colnull |= 1u << s;
-		}
-		if (a0 < S.natts_walk) off = a0 > 0 ? (uint32_t) S.att[a0].cacheoff : 0;
+		if (a0 < S.natts_walk) W.off = a0 > 0 ? (uint32_t) S.att[a0].cacheoff : 0;
 	}
 	for (int a = a0; a < S.natts_walk; a++)
 	{
 		const ggp_attr at = S.att[a];
-		if ((uint32_t) a >= tnatts || (hasnulls && !(lds8(bp + (a >> 3)) & (1u << (a & 7)))))
-		{
-			if (at.slot >= 0) colnull |= 1u << at.slot;
-			continue;
-		}
-		if (at.attlen == -1)
-		{
-			/* att_align_pointer: a zero byte is padding (or an aligned 4-byte header) */
-			if (off < datalen && lds8(tp + off) == 0) off = align_nominal(off, at.attalign);
-		}
-		else
-			off = align_nominal(off, at.attalign);
-		if (at.slot >= 0) sts16(offs + (uint32_t) (at.slot * 32 + lane) * 2, off);
-		if (off >= datalen) { bad = true; break; }
-		off += at.attlen > 0 ? (uint32_t) at.attlen : varsize_any(tp + off, bad);
-		if (off > datalen) { bad = true; break; }
+		walk_step(W, a, at.attlen, at.attalign, at.slot, offs, lane);
 	}
-	if (bad) err |= GGP_EF_BADPAGE;
-	tv.colnull = colnull;
+	if (W.bad) err |= GGP_EF_BADPAGE;
+	tv.tp = W.tp;
+	tv.colnull = W.colnull;
 }
 
 /* short string column -> <= 8 bytes packed LSB-first (VARDATA_ANY / VARSIZE_ANY_EXHDR, postgres.h:276-300;
@@ -311,160 +330,159 @@ __device__ __forceinline__ uint64_t normalize_key(uint64_t v, int keytype)
 
 /* Everything a running program needs to reach its operands */
 struct EvalCtx {
-	const ggp_program *P;
+	const ggp_program *P;   /* interpreter path only */
 	TupleView tv;           /* outer / scan tuple */
 	uint32_t offs;          /* shared address of its per-lane column offsets [slot*32 + lane] u16 */
 	bool fast;              /* constant offsets usable (no tuple of the warp has NULLs) */
-	const ggp_side *IS;     /* inner side (joins) or nullptr */
-	TupleView itv;
+	TupleView itv;          /* inner tuple (joins) */
 	uint32_t ioffs;
 	bool ifast;
 	int lane;
 };
 
-/* The accumulator machine.  `Sink` receives the post-actions:
- *     bool filter(bool pass)              -> row still live?
- *     void key(int k, uint64_t v, bool n)
- *     void group()
- *     void out(int slot, double v, bool n)
- * `live` = this lane carries a row that still counts; dead lanes keep executing (the op stream is
- * warp-uniform) but raise no errors and produce no effects. */
-template <bool NULLABLE, bool HAS_INNER, class Sink>
-__device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &err, Sink &sink)
-{
-	const ggp_program &P = *X.P;
-	uint64_t acc = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-	bool accnull = false;
-	uint32_t tnull = 0;
+/* registers of the accumulator machine */
+struct MachState {
+	uint64_t acc, t0, t1, t2, t3;
+	uint32_t tnull;
+	bool accnull;
+	bool live;              /* this lane carries a row that still counts; dead lanes keep executing (the op
+	                         * stream is warp-uniform) but raise no errors and produce no effects */
+	__device__ __forceinline__ void reset(bool l) { acc = t0 = t1 = t2 = t3 = 0; tnull = 0; accnull = false; live = l; }
+};
 
+/* One op of the accumulator machine, including its post-actions.  `o` is passed by value: on the
+ * interpreter path it comes from the program table; in a plan-specialised kernel it is a literal and
+ * the whole function folds down to the few instructions of that one op.  KF(idx) yields constant idx.
+ * `Sink` receives the post-actions:
+ *     bool filter(bool pass)  /  void key(int k, uint64_t v, bool n)  /  bool group(bool live)
+ *     void out(int slot, double v, bool n) */
+template <bool NULLABLE, bool HAS_INNER, class Sink, class KF>
+__device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const KF &KV, uint32_t constnull,
+                                        MachState &M, uint32_t &err, Sink &sink)
+{
 #define GG_COLADDR(O) \
 	((HAS_INNER && ((O).idx & 0x80)) \
 	 ? (X.itv.tp + ((X.ifast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.ioffs + (uint32_t) ((((O).idx & 0x7F) * 32) + X.lane) * 2))) \
 	 : (X.tv.tp + ((X.fast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.offs + (uint32_t) (((O).idx * 32) + X.lane) * 2))))
 #define GG_COLNULL(O) (NULLABLE && (((HAS_INNER && ((O).idx & 0x80)) ? (X.itv.colnull >> ((O).idx & 0x7F)) : (X.tv.colnull >> (O).idx)) & 1))
-#define GG_TEMP(IDX) ((IDX) == 0 ? t0 : (IDX) == 1 ? t1 : (IDX) == 2 ? t2 : t3)
-#define GG_TNULL(IDX) (NULLABLE && ((tnull >> (IDX)) & 1))
-#define GG_KNULL(IDX) (NULLABLE && ((P.constnull >> (IDX)) & 1))
+#define GG_TEMP(IDX) ((IDX) == 0 ? M.t0 : (IDX) == 1 ? M.t1 : (IDX) == 2 ? M.t2 : M.t3)
+#define GG_TNULL(IDX) (NULLABLE && ((M.tnull >> (IDX)) & 1))
+#define GG_KNULL(IDX) (NULLABLE && ((constnull >> (IDX)) & 1))
 #define GG_D(V) __longlong_as_double((long long) (V))
-#define GG_ACCD GG_D(acc)
+#define GG_ACCD GG_D(M.acc)
 #define GG_F8(KIND, EXPR, XV, YV, SN) \
-	{ const double x = (XV), y = (YV), r = (EXPR); const bool isn = NULLABLE && (accnull || (SN)); \
-	  if (!f8_finite(r) || ((KIND) != 0 && r == 0.0)) { if (live && !isn) err |= f8_check_slow((KIND), x, y, r); } \
-	  acc = (uint64_t) __double_as_longlong(r); accnull = isn; }
+	{ const double x = (XV), y = (YV), r = (EXPR); const bool isn = NULLABLE && (M.accnull || (SN)); \
+	  if (!f8_finite(r) || ((KIND) != 0 && r == 0.0)) { if (M.live && !isn) err |= f8_check_slow((KIND), x, y, r); } \
+	  M.acc = (uint64_t) __double_as_longlong(r); M.accnull = isn; }
 #define GG_COLF8(O, SN, V) const bool SN = GG_COLNULL(O); const double V = SN ? 1.0 : ldsf64(GG_COLADDR(O));
 
-	for (int pc = 0;; pc++)
+	const int op = o.op;
+	/* most frequent first; the op stream is uniform across the warp, so these branches never diverge */
+	if (op == GGP_LD_C8) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : lds64(GG_COLADDR(o)); }
+	else if (op == GGP_MUL_C) { GG_COLF8(o, sn, v) GG_F8(1, __dmul_rn(x, y), GG_ACCD, v, sn) }
+	else if (op == GGP_MUL_T) { GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) }
+	else if (op == GGP_LD_K) { M.acc = (uint64_t) KV(o.idx); M.accnull = GG_KNULL(o.idx); }
+	else if (op == GGP_ADD_C) { GG_COLF8(o, sn, v) GG_F8(0, __dadd_rn(x, y), GG_ACCD, v, sn) }
+	else if (op == GGP_SUB_C) { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), GG_ACCD, v, sn) }
+	else if (op == GGP_LD_C4) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (uint64_t) (int64_t) (int32_t) lds32(GG_COLADDR(o)); }
+	else if (op == GGP_CMPI_K) { const int64_t y = KV(o.idx), x = (int64_t) M.acc;
+		M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_KNULL(o.idx); }
+	else if (op == GGP_LD_BP) { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : load_str(GG_COLADDR(o), true, e2); if (M.live) err |= e2; }
+	else switch (op)
 	{
-		const ggp_op o = P.code[pc];
-		const int op = o.op;
-		/* most frequent first; the op stream is uniform across the warp, so these branches never diverge */
-		if (op == GGP_LD_C8) { accnull = GG_COLNULL(o); acc = accnull ? 0 : lds64(GG_COLADDR(o)); }
-		else if (op == GGP_MUL_C) { GG_COLF8(o, sn, v) GG_F8(1, __dmul_rn(x, y), GG_ACCD, v, sn) }
-		else if (op == GGP_MUL_T) { GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) }
-		else if (op == GGP_LD_K) { acc = (uint64_t) P.consts[o.idx]; accnull = GG_KNULL(o.idx); }
-		else if (op == GGP_ADD_C) { GG_COLF8(o, sn, v) GG_F8(0, __dadd_rn(x, y), GG_ACCD, v, sn) }
-		else if (op == GGP_SUB_C) { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), GG_ACCD, v, sn) }
-		else if (op == GGP_END) break;
-		else if (op == GGP_LD_C4) { accnull = GG_COLNULL(o); acc = accnull ? 0 : (uint64_t) (int64_t) (int32_t) lds32(GG_COLADDR(o)); }
-		else if (op == GGP_CMPI_K) { const int64_t y = P.consts[o.idx], x = (int64_t) acc;
-			acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); }
-		else if (op == GGP_LD_BP) { uint32_t e2 = 0; accnull = GG_COLNULL(o); acc = accnull ? 0 : load_str(GG_COLADDR(o), true, e2); if (live) err |= e2; }
-		else switch (op)
+		case GGP_LD_VS: { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : load_str(GG_COLADDR(o), false, e2); if (M.live) err |= e2; } break;
+		case GGP_LD_BOOL: M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (uint64_t) (lds8(GG_COLADDR(o)) != 0); break;
+		case GGP_LD_T: M.acc = GG_TEMP(o.idx); M.accnull = GG_TNULL(o.idx); break;
+		case GGP_ADD_K: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(KV(o.idx)), GG_KNULL(o.idx)) break;
+		case GGP_ADD_T: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
+		case GGP_SUB_K: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(KV(o.idx)), GG_KNULL(o.idx)) break;
+		case GGP_SUB_T: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
+		case GGP_RSUB_C: { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), v, GG_ACCD, sn) } break;
+		case GGP_RSUB_K: GG_F8(0, __dsub_rn(x, y), GG_D(KV(o.idx)), GG_ACCD, GG_KNULL(o.idx)) break;
+		case GGP_RSUB_T: GG_F8(0, __dsub_rn(x, y), GG_D(GG_TEMP(o.idx)), GG_ACCD, GG_TNULL(o.idx)) break;
+		case GGP_MUL_K: GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(KV(o.idx)), GG_KNULL(o.idx)) break;
+		case GGP_DIV_C: case GGP_DIV_K: case GGP_DIV_T: case GGP_RDIV_C: case GGP_RDIV_K: case GGP_RDIV_T:
 		{
-			case GGP_LD_VS: { uint32_t e2 = 0; accnull = GG_COLNULL(o); acc = accnull ? 0 : load_str(GG_COLADDR(o), false, e2); if (live) err |= e2; } break;
-			case GGP_LD_BOOL: accnull = GG_COLNULL(o); acc = accnull ? 0 : (uint64_t) (lds8(GG_COLADDR(o)) != 0); break;
-			case GGP_LD_T: acc = GG_TEMP(o.idx); accnull = GG_TNULL(o.idx); break;
-			case GGP_ADD_K: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
-			case GGP_ADD_T: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
-			case GGP_SUB_K: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
-			case GGP_SUB_T: GG_F8(0, __dsub_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
-			case GGP_RSUB_C: { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), v, GG_ACCD, sn) } break;
-			case GGP_RSUB_K: GG_F8(0, __dsub_rn(x, y), GG_D(P.consts[o.idx]), GG_ACCD, GG_KNULL(o.idx)) break;
-			case GGP_RSUB_T: GG_F8(0, __dsub_rn(x, y), GG_D(GG_TEMP(o.idx)), GG_ACCD, GG_TNULL(o.idx)) break;
-			case GGP_MUL_K: GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(P.consts[o.idx]), GG_KNULL(o.idx)) break;
-			case GGP_DIV_C: case GGP_DIV_K: case GGP_DIV_T: case GGP_RDIV_C: case GGP_RDIV_K: case GGP_RDIV_T:
-			{
-				/* float8div (float.c:808): division by zero is its own error */
-				const int v3 = (op - GGP_DIV_C) % 3;
-				const bool rev = op >= GGP_RDIV_C;
-				bool sn;
-				double v;
-				if (v3 == 0) { sn = GG_COLNULL(o); v = sn ? 1.0 : ldsf64(GG_COLADDR(o)); }
-				else if (v3 == 1) { sn = GG_KNULL(o.idx); v = GG_D(P.consts[o.idx]); }
-				else { sn = GG_TNULL(o.idx); v = GG_D(GG_TEMP(o.idx)); }
-				const double xn = rev ? v : GG_ACCD, yd = rev ? GG_ACCD : v;
-				if (live && !(NULLABLE && (accnull || sn)) && yd == 0.0) err |= GGP_EF_DIV_ZERO;
-				GG_F8(2, __ddiv_rn(x, y), xn, yd, sn)
-				break;
-			}
-			case GGP_CMPF_C: { GG_COLF8(o, sn, v) acc = test_cc(f8_cmp(GG_ACCD, v), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
-			case GGP_CMPF_K: acc = test_cc(f8_cmp(GG_ACCD, GG_D(P.consts[o.idx])), o.aux & 7); if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); break;
-			case GGP_CMPF_T: acc = test_cc(f8_cmp(GG_ACCD, GG_D(GG_TEMP(o.idx))), o.aux & 7); if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); break;
-			case GGP_CMPI_C4: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) (int32_t) lds32(GG_COLADDR(o)), x = (int64_t) acc;
-				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
-			case GGP_CMPI_C8: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) lds64(GG_COLADDR(o)), x = (int64_t) acc;
-				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || sn; } break;
-			case GGP_CMPI_T: { const int64_t y = (int64_t) GG_TEMP(o.idx), x = (int64_t) acc;
-				acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); } break;
-			case GGP_CMPS_K: acc = ((o.aux & 7) == GGP_EQ) ? (acc == (uint64_t) P.consts[o.idx]) : (acc != (uint64_t) P.consts[o.idx]);
-				if (NULLABLE) accnull = accnull || GG_KNULL(o.idx); break;
-			case GGP_CMPS_T: acc = ((o.aux & 7) == GGP_EQ) ? (acc == GG_TEMP(o.idx)) : (acc != GG_TEMP(o.idx));
-				if (NULLABLE) accnull = accnull || GG_TNULL(o.idx); break;
-			case GGP_DATE2TS:
-			{
-				/* date2timestamp, date.c:457: +-infinity map to +-infinity; otherwise days * USECS_PER_DAY,
-				 * "date out of range for timestamp" when that overflows int64 (|d| > 106751991) */
-				const int32_t d = (int32_t) acc;
-				int64_t r;
-				if (d == INT32_MIN) r = INT64_MIN;
-				else if (d == INT32_MAX) r = INT64_MAX;
-				else
-				{
-					r = (int64_t) d * 86400000000LL;
-					if ((d > 106751991 || d < -106751991) && live && !(NULLABLE && accnull)) err |= GGP_EF_DATE_RANGE;
-				}
-				acc = (uint64_t) r;
-				break;
-			}
-			case GGP_I2F8: acc = (uint64_t) __double_as_longlong((double) (int64_t) acc); break;
-			case GGP_AND_T:
-			case GGP_OR_T:
-			{
-				const bool a = acc != 0, b = GG_TEMP(o.idx) != 0, an = NULLABLE && accnull, bn = GG_TNULL(o.idx);
-				if (op == GGP_AND_T)
-				{
-					if ((!an && !a) || (!bn && !b)) { acc = 0; accnull = false; }
-					else if (an || bn) { acc = 0; accnull = true; }
-					else { acc = 1; accnull = false; }
-				}
-				else
-				{
-					if ((!an && a) || (!bn && b)) { acc = 1; accnull = false; }
-					else if (an || bn) { acc = 0; accnull = true; }
-					else { acc = 0; accnull = false; }
-				}
-				break;
-			}
-			case GGP_NOT: acc = (acc == 0); break;
-			case GGP_ISNULL: acc = accnull; accnull = false; break;
-			case GGP_ISNOTNULL: acc = !accnull; accnull = false; break;
-			default: break;                         /* GGP_NOP */
+			/* float8div (float.c:808): division by zero is its own error */
+			const int v3 = (op - GGP_DIV_C) % 3;
+			const bool rev = op >= GGP_RDIV_C;
+			bool sn;
+			double v;
+			if (v3 == 0) { sn = GG_COLNULL(o); v = sn ? 1.0 : ldsf64(GG_COLADDR(o)); }
+			else if (v3 == 1) { sn = GG_KNULL(o.idx); v = GG_D(KV(o.idx)); }
+			else { sn = GG_TNULL(o.idx); v = GG_D(GG_TEMP(o.idx)); }
+			const double xn = rev ? v : GG_ACCD, yd = rev ? GG_ACCD : v;
+			if (M.live && !(NULLABLE && (M.accnull || sn)) && yd == 0.0) err |= GGP_EF_DIV_ZERO;
+			GG_F8(2, __ddiv_rn(x, y), xn, yd, sn)
+			break;
 		}
+		case GGP_CMPF_C: { GG_COLF8(o, sn, v) M.acc = test_cc(f8_cmp(GG_ACCD, v), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
+		case GGP_CMPF_K: M.acc = test_cc(f8_cmp(GG_ACCD, GG_D(KV(o.idx))), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_KNULL(o.idx); break;
+		case GGP_CMPF_T: M.acc = test_cc(f8_cmp(GG_ACCD, GG_D(GG_TEMP(o.idx))), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_TNULL(o.idx); break;
+		case GGP_CMPI_C4: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) (int32_t) lds32(GG_COLADDR(o)), x = (int64_t) M.acc;
+			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
+		case GGP_CMPI_C8: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) lds64(GG_COLADDR(o)), x = (int64_t) M.acc;
+			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
+		case GGP_CMPI_T: { const int64_t y = (int64_t) GG_TEMP(o.idx), x = (int64_t) M.acc;
+			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_TNULL(o.idx); } break;
+		case GGP_CMPS_K: M.acc = ((o.aux & 7) == GGP_EQ) ? (M.acc == (uint64_t) KV(o.idx)) : (M.acc != (uint64_t) KV(o.idx));
+			if (NULLABLE) M.accnull = M.accnull || GG_KNULL(o.idx); break;
+		case GGP_CMPS_T: M.acc = ((o.aux & 7) == GGP_EQ) ? (M.acc == GG_TEMP(o.idx)) : (M.acc != GG_TEMP(o.idx));
+			if (NULLABLE) M.accnull = M.accnull || GG_TNULL(o.idx); break;
+		case GGP_DATE2TS:
+		{
+			/* date2timestamp, date.c:457: +-infinity map to +-infinity; otherwise days * USECS_PER_DAY,
+			 * "date out of range for timestamp" when that overflows int64 (|d| > 106751991) */
+			const int32_t d = (int32_t) M.acc;
+			int64_t r;
+			if (d == INT32_MIN) r = INT64_MIN;
+			else if (d == INT32_MAX) r = INT64_MAX;
+			else
+			{
+				r = (int64_t) d * 86400000000LL;
+				if ((d > 106751991 || d < -106751991) && M.live && !(NULLABLE && M.accnull)) err |= GGP_EF_DATE_RANGE;
+			}
+			M.acc = (uint64_t) r;
+			break;
+		}
+		case GGP_I2F8: M.acc = (uint64_t) __double_as_longlong((double) (int64_t) M.acc); break;
+		case GGP_AND_T:
+		case GGP_OR_T:
+		{
+			const bool a = M.acc != 0, b = GG_TEMP(o.idx) != 0, an = NULLABLE && M.accnull, bn = GG_TNULL(o.idx);
+			if (op == GGP_AND_T)
+			{
+				if ((!an && !a) || (!bn && !b)) { M.acc = 0; M.accnull = false; }
+				else if (an || bn) { M.acc = 0; M.accnull = true; }
+				else { M.acc = 1; M.accnull = false; }
+			}
+			else
+			{
+				if ((!an && a) || (!bn && b)) { M.acc = 1; M.accnull = false; }
+				else if (an || bn) { M.acc = 0; M.accnull = true; }
+				else { M.acc = 0; M.accnull = false; }
+			}
+			break;
+		}
+		case GGP_NOT: M.acc = (M.acc == 0); break;
+		case GGP_ISNULL: M.acc = M.accnull; M.accnull = false; break;
+		case GGP_ISNOTNULL: M.acc = !M.accnull; M.accnull = false; break;
+		default: break;                         /* GGP_NOP, GGP_END */
+	}
 
-		if (o.flags)
+	if (o.flags)
+	{
+		if (o.flags & GGP_F_ST)
 		{
-			if (o.flags & GGP_F_ST)
-			{
-				const int t = (o.aux >> 4) & 3;
-				if (t == 0) t0 = acc; else if (t == 1) t1 = acc; else if (t == 2) t2 = acc; else t3 = acc;
-				if (NULLABLE) tnull = (tnull & ~(1u << t)) | ((uint32_t) accnull << t);
-			}
-			if (o.flags & GGP_F_FILTER) live = sink.filter(live && !accnull && acc != 0);
-			if (o.flags & GGP_F_KEY) sink.key((o.aux >> 6) & 3, acc, accnull);
-			if (o.flags & GGP_F_GROUP) live = sink.group(live);
-			if (o.flags & GGP_F_OUT) sink.out(o.out, GG_ACCD, accnull);
-			if (o.flags & GGP_F_OUTSQ) { const double v = GG_ACCD; sink.out(o.out2, __dmul_rn(v, v), accnull); }
+			const int t = (o.aux >> 4) & 3;
+			if (t == 0) M.t0 = M.acc; else if (t == 1) M.t1 = M.acc; else if (t == 2) M.t2 = M.acc; else M.t3 = M.acc;
+			if (NULLABLE) M.tnull = (M.tnull & ~(1u << t)) | ((uint32_t) M.accnull << t);
 		}
+		if (o.flags & GGP_F_FILTER) M.live = sink.filter(M.live && !M.accnull && M.acc != 0);
+		if (o.flags & GGP_F_KEY) sink.key((o.aux >> 6) & 3, M.acc, M.accnull);
+		if (o.flags & GGP_F_GROUP) M.live = sink.group(M.live);
+		if (o.flags & GGP_F_OUT) sink.out(o.out, GG_ACCD, M.accnull);
+		if (o.flags & GGP_F_OUTSQ) { const double v = GG_ACCD; sink.out(o.out2, __dmul_rn(v, v), M.accnull); }
 	}
 #undef GG_COLADDR
 #undef GG_COLNULL
@@ -475,6 +493,27 @@ __device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &
 #undef GG_ACCD
 #undef GG_D
 #undef GG_COLF8
+}
+
+/* the interpreter: walk the program table */
+struct DynConsts {
+	const ggp_program *P;
+	__device__ __forceinline__ int64_t operator()(int i) const { return P->consts[i]; }
+};
+template <bool NULLABLE, bool HAS_INNER, class Sink>
+__device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &err, Sink &sink)
+{
+	const ggp_program &P = *X.P;
+	MachState M;
+	M.reset(live);
+	DynConsts KV;
+	KV.P = &P;
+	for (int pc = 0;; pc++)
+	{
+		const ggp_op o = P.code[pc];
+		if (o.op == GGP_END) break;
+		exec_op<NULLABLE, HAS_INNER>(o, X, KV, (uint32_t) P.constnull, M, err, sink);
+	}
 }
 
 }  // namespace ggd

@@ -1,0 +1,27 @@
+/*
+ * gg_jit.h — plan-specialised kernels.
+ *
+ * The interpreter kernels (gg_scanagg.cu) run any supported plan.  For a plan that will scan a
+ * large relation, the same kernel body (gg_scanagg_kernel.cuh) is compiled once more with the
+ * plan's program expanded into straight-line exec_op()/walk_step() calls carrying literal
+ * operands, so the compiler folds dispatch, operand decoding, constant offsets and attribute
+ * properties away — the role PostgreSQL's own expression JIT plays on the CPU.  Compilation uses
+ * NVRTC (dlopen'ed; optional) for sm_100a and the result is cached per (program, variant).
+ * Without NVRTC, or with GGB200_JIT=0, the interpreter kernels are used: same results.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "gg_program.h"
+
+struct gg_jit_kernel {
+	cudaLibrary_t lib = nullptr;
+	cudaKernel_t kernel = nullptr;
+	double compile_ms = 0;
+};
+
+/* C++ source of the specialised translation unit (also used to pre-generate kernels offline) */
+std::string gg_jit_scanagg_source(const ggp_program *prog, int mode);
+/* compile (or fetch from the cache) the specialised scan+agg kernel; returns nullptr and fills err when JIT is
+ * unavailable or fails */
+gg_jit_kernel *gg_jit_scanagg(const ggp_program *prog, int mode, int device, char *err, int errlen);

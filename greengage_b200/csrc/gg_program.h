@@ -150,7 +150,7 @@ typedef struct ggp_grec {
 
 typedef struct ggp_acckinds { uint8_t k[GGP_MAX_ACCS]; } ggp_acckinds;
 
-#ifdef __cplusplus
+#if defined(__cplusplus) && !defined(__CUDACC_RTC__)
 /* host-side compiler (gg_compile.cpp) */
 struct ggp_aggmap {          /* how each Aggref reads the accumulator columns */
 	int32_t col;             /* accumulator column, -1 for count(*) */

@@ -1,544 +1,22 @@
 /*
- * gg_scanagg.cu — fused heap SeqScan -> qual -> projection -> partial HashAggregate.
- *
- * Replaces, for one segment, the per-tuple loop
- *   ExecAgg -> agg_hash_initial_pass -> ExecSeqScan -> heap_getnext -> heapgetpage
- *   (nodeAgg.c:1123, execHHashagg.c:905, nodeSeqscan.c:128, heapam.c:312-463,767-1006;
- *    SURVEY §3.3 hot loops B and C)
- * with one persistent, warp-specialised kernel:
- *
- *   producer warp    TMA bulk-copies whole 32 KB heap pages HBM -> shared-memory ring
- *                    (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP)
- *   consumer warps   lane = one line pointer: ItemId decode, visibility, attribute walk
- *                    (slot_deform_tuple semantics), then ONE compiled program per row
- *                    (gg_program.h): scan qual -> grouping keys -> group lookup in a per-block
- *                    key table -> aggregate arguments
- *   accumulate       MODE_PRIV: every consumer thread owns a private (group x value-slot) float8
- *                               accumulator array in shared memory, laid out [group][slot][thread]
- *                               so a warp's 32 read-modify-writes hit 32 different banks:
- *                               3 instructions per value, no atomics, no shuffles
- *                    MODE_TR  : "lane owns (group, slot)": the warp's 32 values are transposed
- *                               through shared memory and folded by the owning lane into
- *                               registers (<= 32 groups, <= 128 pairs; min/max/int sums, NULLs)
- *                    Reduction trees are fixed => sums are deterministic run to run.
- *   epilogue         threads -> one record per group and block -> global; a single-block merge
- *                    kernel folds records with equal keys, again in a fixed order.
- *
- * HBM-bound by construction: algorithmic bytes = nblocks * 32768, each read exactly once.
+ * gg_scanagg.cu — SeqScan -> qual -> Agg: the ahead-of-time kernels (interpreter path), the merge
+ * kernel, and the host pipeline behind gg_scanagg_* / gg_agg_final (include/ggb200.h).
+ * The kernel body lives in gg_scanagg_kernel.cuh so that gg_jit.cpp can instantiate it again,
+ * specialised for one plan.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "gg_device.cuh"
+#include "gg_scanagg_kernel.cuh"
 #include "gg_engine.h"
+#include "gg_jit.h"
 
 using namespace ggd;
-
-#define GG_NROUNDS (GGP_MAX_PAIRS / 32)
-
-enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2 };
-
-struct ScanAggParams {
-	const uint8_t *pages;
-	uint64_t nblocks;
-	ggp_grec *block_recs;                 /* [gridDim.x][GGP_FAST_GROUPS] */
-	uint32_t *errflags;
-	unsigned long long *counters;         /* [0] rows scanned (visible), [1] rows passed */
-	int nstage;
-	int gcap;                             /* groups this variant holds per block */
-	int scratch_per_warp;                 /* bytes: column offsets (+ TR: transposed values, group ids, null masks) */
-	uint32_t scratch_off;                 /* byte offsets from the start of dynamic shared memory */
-	uint32_t cnt_off, acc_off;            /* MODE_PRIV: per-thread row counts [gcap][NT] u32, sums [gcap][nslots][NT] f64 */
-};
-
-struct BlockTable {                       /* per-block group table in shared memory */
-	uint64_t key[GGP_FAST_GROUPS][GG_MAX_KEYS];
-	uint32_t keynull[GGP_FAST_GROUPS];
-	volatile int n;
-	int lock;
-};
-
-__device__ __forceinline__ bool key_eq(const BlockTable *T, int i, const uint64_t *k, uint32_t knull, int nkeys)
-{
-	if (T->keynull[i] != knull) return false;
-	for (int c = 0; c < nkeys; c++)
-		if (T->key[i][c] != k[c]) return false;
-	return true;
-}
-
-/* find the group of each lane's key, inserting new groups under a block-level lock
- * (lookup_agg_hash_entry, execHHashagg.c:456: NULL keys compare equal to each other) */
-__device__ __forceinline__ int find_or_insert(BlockTable *T, const uint64_t *k, uint32_t knull, int nkeys,
-                                              int gcap, bool want, int lane, uint32_t &err)
-{
-	int gid = -1;
-	bool need = want;
-	if (need)
-	{
-		int n = T->n;
-		for (int i = 0; i < n; i++)
-			if (key_eq(T, i, k, knull, nkeys)) { gid = i; break; }
-		need = gid < 0;
-	}
-	unsigned m = __ballot_sync(GG_FULL_MASK, need);
-	while (m)
-	{
-		int leader = __ffs(m) - 1;
-		if (lane == leader)
-		{
-			while (atomicCAS(&T->lock, 0, 1) != 0) { }
-			__threadfence_block();
-			int n = T->n, found = -1;
-			for (int i = 0; i < n; i++)
-				if (key_eq(T, i, k, knull, nkeys)) { found = i; break; }
-			if (found < 0)
-			{
-				if (n < gcap)
-				{
-					for (int c = 0; c < GG_MAX_KEYS; c++) T->key[n][c] = c < nkeys ? k[c] : 0;
-					T->keynull[n] = knull;
-					__threadfence_block();
-					T->n = n + 1;
-					found = n;
-				}
-				else
-					err |= GGP_EF_GROUP_OVERFLOW;
-			}
-			__threadfence_block();
-			atomicExch(&T->lock, 0);
-			gid = found;
-			need = false;
-		}
-		__syncwarp();
-		if (need)
-		{
-			int n = T->n;
-			for (int i = 0; i < n; i++)
-				if (key_eq(T, i, k, knull, nkeys)) { gid = i; break; }
-			need = gid < 0;
-		}
-		m = __ballot_sync(GG_FULL_MASK, need);
-	}
-	return gid;
-}
-
-/* post-action sink shared by the kernel variants */
-template <int MODE>
-struct RowSink {
-	const ggp_program *P;
-	BlockTable *T;
-	uint64_t k0, k1, k2, k3;
-	uint32_t knull;
-	int nkeys, gcap, lane, gid;
-	uint32_t *err;
-	unsigned long long npassed;
-	bool nonfinite;
-	/* MODE_PRIV */
-	uint32_t acc_thread;         /* shared address of this thread's slot-0/group-0 accumulator */
-	uint32_t cnt_thread;
-	uint32_t gstride, sstride, cstride;
-	/* MODE_TR */
-	uint32_t sv;                 /* shared address of the warp's transposed values [slot][33] f64 */
-	uint32_t vnull;
-
-	__device__ __forceinline__ void begin_row()
-	{
-		k0 = k1 = k2 = k3 = 0; knull = 0; gid = -1; vnull = 0;
-	}
-	__device__ __forceinline__ bool filter(bool pass) { return pass; }
-	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
-	{
-		if (isnull) { knull |= 1u << kc; return; }
-		v = normalize_key(v, P->keytype[kc]);
-		if (kc == 0) k0 = v; else if (kc == 1) k1 = v; else if (kc == 2) k2 = v; else k3 = v;
-	}
-	__device__ __forceinline__ bool group(bool live)
-	{
-		if (nkeys == 0) gid = live ? 0 : -1;
-		else
-		{
-			uint64_t k[GG_MAX_KEYS] = { k0, k1, k2, k3 };
-			gid = find_or_insert(T, k, knull, nkeys, gcap, live, lane, *err);
-		}
-		if (live) npassed++;
-		if (MODE == MODE_PRIV && gid >= 0)
-		{
-			uint32_t a = cnt_thread + (uint32_t) gid * cstride;
-			sts32(a, lds32(a) + 1);
-		}
-		return gid >= 0;
-	}
-	__device__ __forceinline__ void out(int slot, double v, bool isnull)
-	{
-		if (MODE == MODE_PRIV)
-		{
-			if (gid >= 0)
-			{
-				uint32_t a = acc_thread + (uint32_t) gid * gstride + (uint32_t) slot * sstride;
-				stsf64(a, __dadd_rn(ldsf64(a), v));
-				nonfinite |= !f8_finite(v);
-			}
-		}
-		else
-		{
-			stsf64(sv + (uint32_t) (slot * 33 + lane) * 8, v);
-			if (isnull) vnull |= 1u << slot;
-			else if (gid >= 0) nonfinite |= !f8_finite(v);
-		}
-	}
-};
 
 template <int MODE>
 __global__ void __launch_bounds__(MODE == MODE_PRIV ? 480 : 256, MODE == MODE_PRIV ? 1 : 2)
 gg_scanagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
-	constexpr bool NULLABLE = (MODE == MODE_TRN);
-	extern __shared__ __align__(128) uint8_t smem[];
-	const int nstage = prm.nstage;
-	const int ncons = (blockDim.x >> 5) - 1;          /* consumer warps; the last warp is the producer */
-	const int NT = ncons * 32;                         /* consumer threads */
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-	const uint32_t smem_base = smem_u32(smem);
-	const uint32_t ring = smem_base;
-	const uint32_t full_bar = ring + (uint32_t) nstage * GG_BLCKSZ;
-	const uint32_t empty_bar = full_bar + (uint32_t) nstage * 8;
-	BlockTable *T = (BlockTable *) (smem + (size_t) nstage * GG_BLCKSZ + (size_t) nstage * 16);
-
-	const int nkeys = P.nkeys;
-	const int nslots = P.nslots;
-	const int V = nslots > 0 ? nslots : 1;
-	const int gcap = prm.gcap;
-
-	if (threadIdx.x == 0)
-	{
-		for (int s = 0; s < nstage; s++)
-		{
-			mbar_init(full_bar + s * 8, 1);
-			mbar_init(empty_bar + s * 8, ncons);
-		}
-		T->n = (nkeys == 0) ? 1 : 0;               /* plain aggregation: the single group always exists */
-		T->lock = 0;
-		if (nkeys == 0) { T->keynull[0] = 0; for (int c = 0; c < GG_MAX_KEYS; c++) T->key[0][c] = 0; }
-		mbar_fence_init();
-	}
-	if (MODE == MODE_PRIV && warp < ncons)
-	{
-		/* zero this thread's private accumulators */
-		for (int g = 0; g < gcap; g++)
-		{
-			sts32(smem_base + prm.cnt_off + (uint32_t) (g * NT + (int) threadIdx.x) * 4, 0);
-			for (int s = 0; s < nslots; s++)
-				sts64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + s) * NT + (int) threadIdx.x) * 8, 0);
-		}
-	}
-	__syncthreads();
-
-	/* pages of this block: blockIdx.x, +gridDim.x, ... */
-	const uint64_t first = blockIdx.x, stride = gridDim.x;
-	const uint64_t npages = first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0;
-
-	/* MODE_TR accumulators: round r of this lane owns pair p = r*32+lane -> (g = p / V, slot = p % V) */
-	double acc_sum[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	uint32_t acc_cnt[MODE == MODE_PRIV ? 1 : GG_NROUNDS], acc_n[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	int pair_g[MODE == MODE_PRIV ? 1 : GG_NROUNDS], pair_j[MODE == MODE_PRIV ? 1 : GG_NROUNDS], pair_kind[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	if (MODE != MODE_PRIV)
-	{
-#pragma unroll
-		for (int r = 0; r < GG_NROUNDS; r++)
-		{
-			int p = r * 32 + lane;
-			pair_g[r] = p / V;
-			pair_j[r] = p % V;
-			pair_kind[r] = P.nacc == 0 ? GGP_ACC_COUNT : (pair_j[r] < P.nacc ? P.acckind[pair_j[r]] : GGP_ACC_F8SUM);
-			acc_sum[r] = 0.0; acc_cnt[r] = 0; acc_n[r] = 0;
-		}
-	}
-	uint32_t err = 0;
-	unsigned long long n_scanned = 0, n_passed = 0;
-
-	if (warp == ncons)
-	{
-		/* ===== producer: one elected lane streams pages through the ring ===== */
-		if (lane == 0)
-		{
-			for (uint64_t it = 0; it < npages; it++)
-			{
-				int s = (int) (it % nstage);
-				uint32_t ph = (uint32_t) ((it / nstage) & 1);
-				mbar_wait(empty_bar + s * 8, ph ^ 1, 256);
-				mbar_arrive_expect_tx(full_bar + s * 8, GG_BLCKSZ);
-				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ,
-				            prm.pages + (first + it * stride) * (uint64_t) GG_BLCKSZ, GG_BLCKSZ, full_bar + s * 8);
-			}
-		}
-	}
-	else
-	{
-		/* ===== consumers ===== */
-		const uint32_t myscr = smem_base + prm.scratch_off + (uint32_t) warp * prm.scratch_per_warp;
-		const uint32_t offs = myscr;                                               /* [ncols][32] u16 */
-		const uint32_t sv = myscr + ((P.outer.ncols * 64 + 15) & ~15);             /* TR: [V][33] f64 */
-		const uint32_t sg = sv + (uint32_t) V * 33 * 8;                            /* TR: [32] i32 group of each tuple, -1 = none */
-		const uint32_t snull = sg + 128;                                           /* TR: [32] u32 bit s: value slot s is NULL */
-
-		EvalCtx X;
-		X.P = &P; X.offs = offs; X.IS = nullptr; X.ioffs = 0; X.ifast = false; X.lane = lane;
-		X.itv.tp = 0; X.itv.colnull = 0;
-		RowSink<MODE> sink;
-		sink.P = &P; sink.T = T; sink.nkeys = nkeys; sink.gcap = gcap; sink.lane = lane; sink.err = &err;
-		sink.npassed = 0; sink.nonfinite = false;
-		sink.acc_thread = smem_base + prm.acc_off + threadIdx.x * 8;
-		sink.cnt_thread = smem_base + prm.cnt_off + threadIdx.x * 4;
-		sink.sstride = (uint32_t) NT * 8;
-		sink.gstride = (uint32_t) nslots * NT * 8;
-		sink.cstride = (uint32_t) NT * 4;
-		sink.sv = sv;
-
-		for (uint64_t it = 0; it < npages; it++)
-		{
-			int s = (int) (it % nstage);
-			uint32_t ph = (uint32_t) ((it / nstage) & 1);
-			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 32);
-			__syncwarp();
-			const uint32_t pg = ring + (uint32_t) s * GG_BLCKSZ;
-
-			/* page header, bufpage.h:153-166; sanity rules of PageAddItem (bufpage.c:196-204) */
-			const uint32_t w2 = lds32(pg + 8), w3 = lds32(pg + 12), w4 = lds32(pg + 16);
-			const uint32_t pd_flags = w2 >> 16, pd_lower = w3 & 0xFFFF, pd_upper = w3 >> 16, pd_special = w4 & 0xFFFF;
-			int nitems = 0;
-			if (pd_lower < GG_PAGE_HEADER_SIZE || pd_lower > pd_upper || pd_upper > pd_special || pd_special > GG_BLCKSZ)
-			{
-				/* an all-zero page is a valid empty page (PageIsNew) */
-				if (pd_upper != 0 || pd_lower != 0) err |= GGP_EF_BADPAGE;
-			}
-			else
-				nitems = (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2);
-			const bool all_visible = (pd_flags & GG_PD_ALL_VISIBLE) != 0;     /* heapam.c:391 */
-			const int nchunks = (nitems + 31) >> 5;
-
-			for (int c = (int) ((warp + it) % ncons); c < nchunks; c += ncons)
-			{
-				const int idx = c * 32 + lane;
-				bool live = false;
-				uint32_t tup = pg, tuplen = 64;
-				if (idx < nitems)
-				{
-					/* ItemIdData: lp_off:15 | lp_flags:2 | lp_len:15 (itemid.h:24-29) */
-					const uint32_t lp = lds32(pg + GG_PAGE_HEADER_SIZE + idx * 4);
-					const uint32_t lp_off = lp & 0x7FFF, lp_flags = (lp >> 15) & 3, lp_len = lp >> 17;
-					if (lp_flags == GG_LP_NORMAL)
-					{
-						if (lp_off < pd_upper || lp_off + lp_len > pd_special || lp_len < GG_HEAP_HDR_SIZE + 1 || (lp_off & 7))
-							err |= GGP_EF_BADPAGE;
-						else
-						{
-							tup = pg + lp_off;
-							tuplen = lp_len;
-							live = true;
-						}
-					}
-				}
-				/* t_infomask2 | t_infomask | t_hoff live in bytes 18..22 of the header (htup_details.h:139-162) */
-				const uint32_t hw = lds32(tup + 20);                 /* infomask (lo 16) | t_hoff (byte 2) */
-				const uint32_t infomask = hw & 0xFFFF, hoff = (hw >> 16) & 0xFF;
-				if (live && !all_visible)
-				{
-					/* HeapTupleSatisfiesMVCC fast path (tqual.c:1009,1119): frozen xmin + invalid xmax */
-					if ((infomask & GG_HEAP_XMIN_FROZEN) == GG_HEAP_XMIN_FROZEN && (infomask & GG_HEAP_XMAX_INVALID)) { }
-					else if ((infomask & GG_HEAP_XMIN_INVALID) && !(infomask & GG_HEAP_XMIN_COMMITTED)) live = false;
-					else { err |= GGP_EF_VISIBILITY; live = false; }
-				}
-				if (live && (hoff > tuplen || (hoff & 7) || hoff < 24)) { err |= GGP_EF_BADPAGE; live = false; }
-
-				/* dead lanes get a harmless view (the page header) so that the warp-uniform program can run */
-				const bool hasnulls = live && (infomask & GG_HEAP_HASNULL);
-				const bool fast = !__any_sync(GG_FULL_MASK, hasnulls);
-				X.fast = fast;
-				X.tv.tp = pg;
-				X.tv.colnull = 0;
-				if (live)
-				{
-					n_scanned++;
-					const uint32_t e0 = err;
-					walk_tuple(P.outer, tup, tuplen, fast, offs, lane, X.tv, err);
-					if (err != e0 && (err & GGP_EF_BADPAGE)) live = false;
-					if (!NULLABLE && X.tv.colnull) { err |= GGP_EF_NOTNULL_VIOLATED; live = false; }
-				}
-				if (!live)
-				{
-					/* offsets of walked columns must be readable: point them at offset 0 */
-					X.tv.tp = pg;
-					for (int sl = 0; sl < P.outer.ncols; sl++) sts16(offs + (uint32_t) (sl * 32 + lane) * 2, 0);
-					X.fast = false;
-				}
-				/* X.fast must be warp-uniform only in the sense that every lane reads valid memory:
-				 * a dead lane with fast=false reads offset 0 of the page, which is always mapped */
-
-				sink.begin_row();
-				run_prog<NULLABLE, false>(X, live, err, sink);
-
-				if (MODE != MODE_PRIV)
-				{
-					sts32(sg + lane * 4, (uint32_t) sink.gid);
-					if (NULLABLE) sts32(snull + lane * 4, sink.vnull);
-					__syncwarp();
-
-					/* ---- lane-owns-(group, slot) accumulate ---- */
-					const int G = T->n;
-#pragma unroll
-					for (int r = 0; r < GG_NROUNDS; r++)
-					{
-						if (r * 32 < G * V)              /* warp-uniform */
-						{
-							const int g = pair_g[r], j = pair_j[r], kind = pair_kind[r];
-							double s0 = acc_sum[r];
-							uint32_t cnt = acc_cnt[r], nn = acc_n[r];
-#pragma unroll 8
-							for (int i = 0; i < 32; i++)
-							{
-								if ((int) lds32(sg + i * 4) == g)
-								{
-									cnt++;
-									bool isn = NULLABLE && ((lds32(snull + i * 4) >> j) & 1);
-									if (!isn && P.nacc > 0)
-									{
-										double v = ldsf64(sv + (uint32_t) (j * 33 + i) * 8);
-										if (kind == GGP_ACC_F8SUM) s0 = __dadd_rn(s0, v);
-										else if (kind == GGP_ACC_I8SUM)
-											s0 = __longlong_as_double(__double_as_longlong(s0) + __double_as_longlong(v));
-										else if (kind == GGP_ACC_F8MIN) { if (nn == 0 || f8_cmp(v, s0) < 0) s0 = v; }
-										else if (kind == GGP_ACC_F8MAX) { if (nn == 0 || f8_cmp(v, s0) > 0) s0 = v; }
-										else if (kind == GGP_ACC_I8MIN) { if (nn == 0 || __double_as_longlong(v) < __double_as_longlong(s0)) s0 = v; }
-										else if (kind == GGP_ACC_I8MAX) { if (nn == 0 || __double_as_longlong(v) > __double_as_longlong(s0)) s0 = v; }
-										nn++;
-									}
-								}
-							}
-							acc_sum[r] = s0; acc_cnt[r] = cnt; acc_n[r] = nn;
-						}
-					}
-					__syncwarp();
-				}
-			}
-			__syncwarp();
-			if (lane == 0) mbar_arrive(empty_bar + s * 8);
-		}
-		n_passed = sink.npassed;
-		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
-	}
-
-	/* ===== epilogue: threads -> block records, all in fixed order ===== */
-	__syncthreads();
-	if (warp < ncons)
-	{
-		/* per-warp counters and error bits */
-		for (int o = 16; o > 0; o >>= 1)
-		{
-			n_scanned += __shfl_xor_sync(GG_FULL_MASK, n_scanned, o);
-			n_passed += __shfl_xor_sync(GG_FULL_MASK, n_passed, o);
-			err |= __shfl_xor_sync(GG_FULL_MASK, err, o);
-		}
-		if (lane == 0)
-		{
-			if (n_scanned) atomicAdd(&prm.counters[0], n_scanned);
-			if (n_passed) atomicAdd(&prm.counters[1], n_passed);
-			if (err) atomicOr(prm.errflags, err);
-		}
-	}
-	const int G = T->n;
-	ggp_grec *out = prm.block_recs + (size_t) blockIdx.x * GGP_FAST_GROUPS;
-	for (int g = G + (int) threadIdx.x; g < GGP_FAST_GROUPS; g += blockDim.x) out[g].valid = 0;
-
-	if (MODE == MODE_PRIV)
-	{
-		/* one warp per (group, slot): lane l folds threads l, l+32, ... in order, then a fixed butterfly */
-		for (int e = warp; e < G * V; e += (int) (blockDim.x >> 5))
-		{
-			const int g = e / V, sl = e % V;
-			double s0 = 0.0;
-			unsigned long long cnt = 0;
-			for (int t = lane; t < NT; t += 32)
-			{
-				if (nslots > 0) s0 = __dadd_rn(s0, ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + sl) * NT + t) * 8));
-				if (sl == 0) cnt += lds32(smem_base + prm.cnt_off + (uint32_t) (g * NT + t) * 4);
-			}
-			for (int o = 16; o > 0; o >>= 1)
-			{
-				s0 = __dadd_rn(s0, __shfl_xor_sync(GG_FULL_MASK, s0, o));
-				cnt += __shfl_xor_sync(GG_FULL_MASK, cnt, o);
-			}
-			if (lane == 0)
-			{
-				if (nslots > 0)
-				{
-					if (sl < P.nacc) { out[g].sum[sl] = s0; if (P.accsq[sl] < 0) out[g].sumsq[sl] = 0.0; }
-					else
-						for (int j = 0; j < P.nacc; j++)
-							if (P.accsq[j] == sl) out[g].sumsq[j] = s0;
-				}
-				if (sl == 0)
-				{
-					out[g].count = cnt;
-					for (int j = 0; j < P.nacc; j++) out[g].n[j] = cnt;     /* NOT NULL inputs: every row counts */
-					out[g].keynull = T->keynull[g];
-					for (int c = 0; c < GG_MAX_KEYS; c++) out[g].key[c] = T->key[g][c];
-					out[g].valid = 1;
-				}
-			}
-		}
-		return;
-	}
-
-	struct Red { double sum; unsigned long long cnt, n; };
-	Red *red = (Red *) smem;                       /* [ncons][GGP_MAX_PAIRS]: 21 KB for 7 warps, inside the ring */
-	if (warp < ncons)
-	{
-#pragma unroll
-		for (int r = 0; r < GG_NROUNDS; r++)
-		{
-			Red x;
-			x.sum = acc_sum[r]; x.cnt = acc_cnt[r]; x.n = acc_n[r];
-			red[warp * GGP_MAX_PAIRS + r * 32 + lane] = x;
-		}
-	}
-	__syncthreads();
-	for (int p = threadIdx.x; p < GGP_MAX_PAIRS; p += blockDim.x)
-	{
-		int g = p / V, sl = p % V;
-		if (g >= G || g >= GGP_FAST_GROUPS) continue;
-		int kind = P.nacc == 0 ? GGP_ACC_COUNT : (sl < P.nacc ? P.acckind[sl] : GGP_ACC_F8SUM);
-		double s0 = 0.0;
-		unsigned long long cnt = 0, nn = 0;
-		for (int w = 0; w < ncons; w++)
-		{
-			Red x = red[w * GGP_MAX_PAIRS + p];
-			cnt += x.cnt;
-			if (x.n)
-			{
-				if (kind == GGP_ACC_F8SUM) s0 = __dadd_rn(s0, x.sum);
-				else if (kind == GGP_ACC_I8SUM) s0 = __longlong_as_double(__double_as_longlong(s0) + __double_as_longlong(x.sum));
-				else if (kind == GGP_ACC_F8MIN) { if (nn == 0 || f8_cmp(x.sum, s0) < 0) s0 = x.sum; }
-				else if (kind == GGP_ACC_F8MAX) { if (nn == 0 || f8_cmp(x.sum, s0) > 0) s0 = x.sum; }
-				else if (kind == GGP_ACC_I8MIN) { if (nn == 0 || __double_as_longlong(x.sum) < __double_as_longlong(s0)) s0 = x.sum; }
-				else if (kind == GGP_ACC_I8MAX) { if (nn == 0 || __double_as_longlong(x.sum) > __double_as_longlong(s0)) s0 = x.sum; }
-				nn += x.n;
-			}
-		}
-		if (P.nacc > 0)
-		{
-			if (sl < P.nacc) { out[g].sum[sl] = s0; out[g].n[sl] = nn; if (P.accsq[sl] < 0) out[g].sumsq[sl] = 0.0; }
-			else
-				for (int j = 0; j < P.nacc; j++)
-					if (P.accsq[j] == sl) out[g].sumsq[j] = s0;
-		}
-		if (sl == 0)
-		{
-			out[g].count = cnt;
-			out[g].keynull = T->keynull[g];
-			for (int c = 0; c < GG_MAX_KEYS; c++) out[g].key[c] = T->key[g][c];
-			out[g].valid = 1;
-		}
-	}
+	scanagg_body<MODE, DynPlan>(P, prm);
 }
 
 /* ---- merge kernel: fold group records with equal keys, in record order (deterministic) ----
@@ -720,6 +198,7 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 /* =====================================================================================
  * host side: the pipeline object behind gg_scanagg_* (include/ggb200.h)
  * ===================================================================================== */
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -737,6 +216,7 @@ struct gg_scanagg {
 	int mode = MODE_PRIV;           /* kernel variant; escalates PRIV -> TR when a run overflows its group capacity */
 	int ctas_per_sm = 2, gcap = 0;
 	uint32_t scratch_off = 0, cnt_off = 0, acc_off = 0;
+	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
 	size_t smem = 0;
 	/* device state */
 	ggp_grec *recs = nullptr;       /* [GG_MERGE_CAP (previous merged)] ++ [grid * GGP_FAST_GROUPS (block records)] */
@@ -804,6 +284,12 @@ static int scanagg_configure(gg_scanagg *p)
 		if (p->smem < 32 * 1024) p->smem = 32 * 1024;             /* the epilogue reuses the ring as reduction scratch */
 	}
 	p->grid = e->sm_count * p->ctas_per_sm;
+	{
+		char jmsg[512];
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, e->device, jmsg, sizeof jmsg);
+		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
+		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	}
 	if (p->mode == MODE_PRIV)
 		GG_CUDA(cudaFuncSetAttribute(gg_scanagg_kernel<MODE_PRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 	else if (p->mode == MODE_TR)
@@ -828,7 +314,12 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	prm.scratch_off = p->scratch_off;
 	prm.cnt_off = p->cnt_off;
 	prm.acc_off = p->acc_off;
-	if (p->mode == MODE_PRIV)
+	if (p->jit)
+	{
+		void *args[] = { (void *) &p->prog, (void *) &prm };
+		GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
+	}
+	else if (p->mode == MODE_PRIV)
 		gg_scanagg_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	else if (p->mode == MODE_TR)
 		gg_scanagg_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
@@ -920,7 +411,6 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
 	int rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream);
 	if (rc) return rc;
-	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
@@ -929,18 +419,9 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 /* Streamed end-to-end path: pages live in HOST memory (the segment's shared buffers / file cache).
  * Double-buffered 256 MB chunks: H2D on the copy stream overlaps the scan kernel of the previous
  * chunk on the compute stream. */
-static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks);
-
 int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 {
 	if (!p || (!host_pages && nblocks)) return GG_ERR_ARG;
-	int rc = scanagg_stream_host(p, host_pages, nblocks);
-	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks });
-	return rc;
-}
-
-static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
-{
 	gg_engine *e = p->eng;
 	GG_CUDA(cudaSetDevice(e->device));
 	const uint64_t chunk = GG_STREAM_CHUNK_BLOCKS;
@@ -1060,26 +541,6 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	GG_CUDA(cudaMemcpy(&flags, p->d_err, sizeof flags, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(counters, p->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(&n, p->d_nout, sizeof n, cudaMemcpyDeviceToHost));
-	if ((flags & GGP_EF_GROUP_OVERFLOW) && p->mode == MODE_PRIV)
-	{
-		/* more groups than the private-accumulator variant holds (the planner's numGroups was low or
-		 * absent): replay the fed inputs on the transposed variant, like the reference's hybrid hash
-		 * aggregate re-reading spilled input (execHHashagg.c:1093) */
-		std::vector<gg_scanagg::Fed> replay = p->fed;
-		p->mode = p->prog.nullable ? MODE_TRN : MODE_TR;
-		int rc2 = scanagg_configure(p);
-		if (rc2) return rc2;
-		p->nrecs_total = GG_MERGE_CAP + p->grid * GGP_FAST_GROUPS;
-		rc2 = gg_scanagg_reset(p);
-		if (rc2) return rc2;
-		for (const auto &f : replay)
-		{
-			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream) : scanagg_stream_host(p, f.host, f.nblocks);
-			if (rc2) return rc2;
-		}
-		p->fed = replay;
-		return gg_scanagg_fetch(p, out, outcap, nout, rows_scanned, rows_passed);
-	}
 	if (rows_scanned) *rows_scanned = counters[0];
 	if (rows_passed) *rows_passed = counters[1];
 	int rc = gg_errflags_to_code(flags);
