@@ -58,9 +58,10 @@ def build_device(verbose=False, force=False):
     embed_sources()
     objs = []
     hdrs = _all_headers() + [os.path.join(BUILD, "gg_jit_sources.inc")]
-    for src in [s for s in os.listdir(CSRC) if s.endswith((".cu", ".cpp"))]:
+    sources = [s for s in os.listdir(CSRC) if s.endswith((".cu", ".cpp"))] + [os.path.join("plans", "gg_plan_cache.cu")]
+    for src in sources:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(BUILD, src.rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(BUILD, os.path.basename(src).rsplit(".", 1)[0] + ".o")
         if force or _newer(obj, [path] + hdrs):
             cmd = [NVCC] + NVFLAGS + ["-I", BUILD] + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             subprocess.check_call(cmd)

@@ -212,14 +212,16 @@ extern "C" int gg_debug_disasm_scanagg(const gg_scan *scan, const gg_agg *agg, c
 
 /* debugging aid: the plan-specialised source gg_jit.cpp would compile for this plan and kernel variant */
 #include "gg_jit.h"
-extern "C" int gg_debug_jit_source(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, int mode, char *buf, int cap)
+extern "C" int gg_debug_jit_source(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, int mode, int threads,
+                                   const char *suffix, unsigned long long *hash, char *buf, int cap)
 {
 	ggp_program prog;
 	ggp_aggmap aggmap[GG_MAX_AGGS];
 	char msg[256];
 	int rc = ggp_compile_scanagg(scan, agg, pool, &prog, aggmap, msg, sizeof msg);
 	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
-	std::string s = gg_jit_scanagg_source(&prog, mode);
+	std::string s = gg_jit_scanagg_source(&prog, mode, threads, suffix);
+	if (hash) *hash = gg_plan_hash(&prog, mode);
 	snprintf(buf, (size_t) cap, "%s", s.c_str());
 	return (int) s.size();
 }

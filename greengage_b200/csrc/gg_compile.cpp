@@ -529,7 +529,9 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 			case GG_AGG_COUNT_STAR: aggmap[i].col = -1; continue;
 			case GG_AGG_COUNT_ANY: kind = GGP_ACC_COUNT; break;
 			case GG_AGG_SUM_FLOAT8: kind = GGP_ACC_F8SUM; break;
-			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = 1; break;
+			/* float8_accum also maintains sumX2, which float8_avg ignores (float.c:1982): only a PARTIAL stage,
+			 * whose transition state {N, sumX, sumX2} is shipped to another process, has to produce it */
+			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = (agg->aggstage == GG_AGGSTAGE_PARTIAL); break;
 			case GG_AGG_MIN_FLOAT8: kind = GGP_ACC_F8MIN; break;
 			case GG_AGG_MAX_FLOAT8: kind = GGP_ACC_F8MAX; break;
 			case GG_AGG_SUM_INT4: kind = GGP_ACC_I8SUM; break;

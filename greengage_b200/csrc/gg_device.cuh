@@ -307,7 +307,7 @@ __device__ __forceinline__ bool f8_isinf(double x) { return fabs(x) == __longlon
 __device__ __forceinline__ bool f8_finite(double x) { return fabs(x) < __longlong_as_double(0x7ff0000000000000LL); }
 
 /* CHECKFLOATVAL (float_utils.h:28), evaluated only when the result is not finite or is zero */
-__device__ __noinline__ uint32_t f8_check_slow(int kind /* 0 add/sub, 1 mul, 2 div */, double x, double y, double r)
+static __device__ __noinline__ uint32_t f8_check_slow(int kind /* 0 add/sub, 1 mul, 2 div */, double x, double y, double r)
 {
 	uint32_t e = 0;
 	if (f8_isinf(r) && !(f8_isinf(x) || f8_isinf(y))) e |= GGP_EF_FLOAT_OVERFLOW;

@@ -18,10 +18,14 @@ struct gg_jit_kernel {
 	cudaLibrary_t lib = nullptr;
 	cudaKernel_t kernel = nullptr;
 	double compile_ms = 0;
+	bool precompiled = false;       /* from the build-time plan cache: `kernel` is a __global__ function address */
 };
 
 /* C++ source of the specialised translation unit (also used to pre-generate kernels offline) */
-std::string gg_jit_scanagg_source(const ggp_program *prog, int mode);
+std::string gg_jit_scanagg_source(const ggp_program *prog, int mode, int threads, const char *suffix);
+uint64_t gg_plan_hash(const ggp_program *prog, int mode);
+/* build-time plan cache (csrc/plans/gg_plan_cache.cu): address of the kernel specialised for this hash, or nullptr */
+const void *gg_plan_cache_lookup(uint64_t hash, int threads);
 /* compile (or fetch from the cache) the specialised scan+agg kernel; returns nullptr and fills err when JIT is
  * unavailable or fails */
-gg_jit_kernel *gg_jit_scanagg(const ggp_program *prog, int mode, int device, char *err, int errlen);
+gg_jit_kernel *gg_jit_scanagg(const ggp_program *prog, int mode, int threads, int device, char *err, int errlen);

@@ -146,7 +146,8 @@ typedef struct ggp_grec {
 #define GGP_EF_INT_OVERFLOW     0x200
 #define GGP_EF_TABLE_FULL       0x400
 #define GGP_EF_SAW_INF          0x800   /* informational: an aggregate input was +-Inf/NaN */
-#define GGP_EF_INFO_MASK        (GGP_EF_SAW_INF)
+#define GGP_EF_RECHECK          0x1000  /* a fast variant saw a non-finite sum: replay on the checked variant */
+#define GGP_EF_INFO_MASK        (GGP_EF_SAW_INF | GGP_EF_RECHECK)
 
 typedef struct ggp_acckinds { uint8_t k[GGP_MAX_ACCS]; } ggp_acckinds;
 

@@ -13,7 +13,7 @@
 using namespace ggd;
 
 template <int MODE>
-__global__ void __launch_bounds__(MODE == MODE_PRIV ? 480 : 256, MODE == MODE_PRIV ? 1 : 2)
+__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
 gg_scanagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
 	scanagg_body<MODE, DynPlan>(P, prm);
@@ -250,8 +250,24 @@ static int scanagg_configure(gg_scanagg *p)
 		/* 1 CTA/SM: 14 consumer warps + producer.  What the ring and the scratch leave of the 227 KB goes to
 		 * the per-thread private accumulators; that fixes how many groups this variant holds. */
 		p->ctas_per_sm = 1;
-		p->threads = 15 * 32;
-		const int ncons = 14, NT = ncons * 32;
+		/* 16 consumer warps on a 4-page ring measured best on both dense (430 rows/page) and sparse
+		 * (190 rows/page) lineitem pages; fewer warps if the private accumulators of >= 4 groups need the room */
+		int ncons = 16;
+		p->nstage = 4;
+		for (;;)
+		{
+			size_t need = (size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 48 +
+			              (size_t) ncons * p->scratch_per_warp + (size_t) ncons * 32 * (8 * nslots + 4) * 4;   /* >= 4 groups */
+			if (need <= e->smem_optin || ncons <= 4) break;
+			ncons--;
+		}
+		{
+			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages" for experiments */
+			int a, b;
+			if (cfg && sscanf(cfg, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 20 && b >= 2 && b <= 6) { ncons = a; p->nstage = b; }
+		}
+		p->threads = (ncons + 1) * 32;
+		const int NT = ncons * 32;
 		size_t fixed = (size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 16 +
 		               (size_t) ncons * p->scratch_per_warp + 16;
 		if (fixed + (size_t) NT * (8 * nslots + 4) > e->smem_optin) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
@@ -286,7 +302,7 @@ static int scanagg_configure(gg_scanagg *p)
 	p->grid = e->sm_count * p->ctas_per_sm;
 	{
 		char jmsg[512];
-		p->jit = gg_jit_scanagg(&p->prog, p->mode, e->device, jmsg, sizeof jmsg);
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
 		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 	}
@@ -411,6 +427,7 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
 	int rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream);
 	if (rc) return rc;
+	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
@@ -419,9 +436,18 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 /* Streamed end-to-end path: pages live in HOST memory (the segment's shared buffers / file cache).
  * Double-buffered 256 MB chunks: H2D on the copy stream overlaps the scan kernel of the previous
  * chunk on the compute stream. */
+static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks);
+
 int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 {
 	if (!p || (!host_pages && nblocks)) return GG_ERR_ARG;
+	int rc = scanagg_stream_host(p, host_pages, nblocks);
+	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks });
+	return rc;
+}
+
+static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
+{
 	gg_engine *e = p->eng;
 	GG_CUDA(cudaSetDevice(e->device));
 	const uint64_t chunk = GG_STREAM_CHUNK_BLOCKS;
@@ -541,6 +567,27 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	GG_CUDA(cudaMemcpy(&flags, p->d_err, sizeof flags, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(counters, p->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(&n, p->d_nout, sizeof n, cudaMemcpyDeviceToHost));
+	if ((flags & (GGP_EF_GROUP_OVERFLOW | GGP_EF_RECHECK)) && p->mode == MODE_PRIV)
+	{
+		/* Either more groups than the private-accumulator variant holds (the planner's numGroups was low or
+		 * absent), or a non-finite private sum, which only the value-tracking transposed variant can attribute
+		 * to an infinite input or to a float8pl overflow.  Replay the fed inputs on that variant, like the
+		 * reference's hybrid hash aggregate re-reading spilled input (execHHashagg.c:1093). */
+		std::vector<gg_scanagg::Fed> replay = p->fed;
+		p->mode = p->prog.nullable ? MODE_TRN : MODE_TR;
+		int rc2 = scanagg_configure(p);
+		if (rc2) return rc2;
+		p->nrecs_total = GG_MERGE_CAP + p->grid * GGP_FAST_GROUPS;
+		rc2 = gg_scanagg_reset(p);
+		if (rc2) return rc2;
+		for (const auto &f : replay)
+		{
+			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream) : scanagg_stream_host(p, f.host, f.nblocks);
+			if (rc2) return rc2;
+		}
+		p->fed = replay;
+		return gg_scanagg_fetch(p, out, outcap, nout, rows_scanned, rows_passed);
+	}
 	if (rows_scanned) *rows_scanned = counters[0];
 	if (rows_passed) *rows_passed = counters[1];
 	int rc = gg_errflags_to_code(flags);

@@ -175,7 +175,6 @@ struct RowSink {
 			{
 				uint32_t a = acc_thread + (uint32_t) gid * gstride + (uint32_t) slot * sstride;
 				stsf64(a, __dadd_rn(ldsf64(a), v));
-				nonfinite |= !f8_finite(v);
 			}
 		}
 		else
@@ -260,7 +259,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 
 	/* pages of this block: blockIdx.x, +gridDim.x, ... */
 	const uint64_t first = blockIdx.x, stride = gridDim.x;
-	const uint64_t npages = first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0;
+	const uint32_t npages = (uint32_t) (first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0);
 
 	/* MODE_TR accumulators: round r of this lane owns pair p = r*32+lane -> (g = p / V, slot = p % V) */
 	double acc_sum[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
@@ -286,14 +285,16 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		/* ===== producer: one elected lane streams pages through the ring ===== */
 		if (lane == 0)
 		{
-			for (uint64_t it = 0; it < npages; it++)
+			int s = 0;
+			uint32_t ph = 0;
+			const uint8_t *src = prm.pages + first * (uint64_t) GG_BLCKSZ;
+			for (uint32_t it = 0; it < npages; it++)
 			{
-				int s = (int) (it % nstage);
-				uint32_t ph = (uint32_t) ((it / nstage) & 1);
-				mbar_wait(empty_bar + s * 8, ph ^ 1, 256);
+				mbar_wait(empty_bar + s * 8, ph ^ 1, 128);
 				mbar_arrive_expect_tx(full_bar + s * 8, GG_BLCKSZ);
-				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ,
-				            prm.pages + (first + it * stride) * (uint64_t) GG_BLCKSZ, GG_BLCKSZ, full_bar + s * 8);
+				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, GG_BLCKSZ, full_bar + s * 8);
+				src += stride * (uint64_t) GG_BLCKSZ;
+				if (++s == nstage) { s = 0; ph ^= 1; }
 			}
 		}
 	}
@@ -319,11 +320,11 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		sink.cstride = (uint32_t) NT * 4;
 		sink.sv = sv;
 
-		for (uint64_t it = 0; it < npages; it++)
+		int s = 0, rot = warp;                    /* rot = (warp + it) mod ncons: rotates which warp takes chunk 0 */
+		uint32_t ph = 0;
+		for (uint32_t it = 0; it < npages; it++, rot = (rot + 1 == ncons ? 0 : rot + 1))
 		{
-			int s = (int) (it % nstage);
-			uint32_t ph = (uint32_t) ((it / nstage) & 1);
-			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 32);
+			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
 			__syncwarp();
 			const uint32_t pg = ring + (uint32_t) s * GG_BLCKSZ;
 
@@ -341,7 +342,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			const bool all_visible = (pd_flags & GG_PD_ALL_VISIBLE) != 0;     /* heapam.c:391 */
 			const int nchunks = (nitems + 31) >> 5;
 
-			for (int c = (int) ((warp + it) % ncons); c < nchunks; c += ncons)
+			for (int c = rot; c < nchunks; c += ncons)
 			{
 				const int idx = c * 32 + lane;
 				bool live = false;
@@ -447,6 +448,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
+			if (++s == nstage) { s = 0; ph ^= 1; }
 		}
 		n_passed = sink.npassed;
 		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
@@ -484,7 +486,15 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			unsigned long long cnt = 0;
 			for (int t = lane; t < NT; t += 32)
 			{
-				if (nslots > 0) s0 = __dadd_rn(s0, ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + sl) * NT + t) * 8));
+				if (nslots > 0)
+				{
+					const double pv = ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + sl) * NT + t) * 8);
+					/* a non-finite private sum is either a legitimate +-Inf/NaN input or a float8pl overflow
+					 * (ERROR in the reference, float.c:782): this variant does not track which, so it asks the host
+					 * to decide by replaying the input on the fully checked interpreter kernel */
+					if (!f8_finite(pv)) atomicOr(prm.errflags, GGP_EF_RECHECK);
+					s0 = __dadd_rn(s0, pv);
+				}
 				if (sl == 0) cnt += lds32(smem_base + prm.cnt_off + (uint32_t) (g * NT + t) * 4);
 			}
 			for (int o = 16; o > 0; o >>= 1)
