@@ -128,6 +128,10 @@ def host_lib():
                                    C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         L.gg_synth_orderkey.argtypes = [C.c_uint64]
         L.gg_synth_orderkey.restype = C.c_int64
+        L.gg_cdbhash_route.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.c_int, C.c_int]
+        L.gg_hash_any.argtypes = [C.c_char_p, C.c_int]
+        L.gg_hash_any.restype = C.c_uint32
         _host = L
     return _host
 
@@ -152,6 +156,12 @@ def dev_lib():
         L.gg_engine_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.gg_engine_launch_count.argtypes = [vp]
         L.gg_engine_launch_count.restype = u64
+        L.gg_engine_timer_start.argtypes = [vp]
+        L.gg_engine_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        L.gg_engine_stream.argtypes = [vp]
+        L.gg_engine_stream.restype = vp
+        L.gg_scanagg_scan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+        L.gg_scanagg_variant.argtypes = [vp]
         L.gg_relation_create.argtypes = [vp, u64, C.POINTER(vp)]
         L.gg_relation_attach.argtypes = [vp, vp, u64, C.POINTER(vp)]
         L.gg_relation_load.argtypes = [vp, u64, vp, u64]

@@ -132,6 +132,29 @@ int gg_engine_last_kernel_ms(gg_engine *e, float *ms)
 
 uint64_t gg_engine_launch_count(gg_engine *e) { return e ? e->launches : 0; }
 
+int gg_engine_timer_start(gg_engine *e)
+{
+	if (!e) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(e->device));
+	if (!e->ev_t0) { GG_CUDA(cudaEventCreate(&e->ev_t0)); GG_CUDA(cudaEventCreate(&e->ev_t1)); }
+	/* the copy stream may hold the first work of the timed region: make the start event cover it */
+	GG_CUDA(cudaEventRecord(e->ev_t0, e->stream));
+	GG_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_t0, 0));
+	return GG_OK;
+}
+
+int gg_engine_timer_stop(gg_engine *e, float *ms)
+{
+	if (!e || !ms || !e->ev_t0) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(e->device));
+	GG_CUDA(cudaEventRecord(e->ev_t1, e->stream));
+	GG_CUDA(cudaEventSynchronize(e->ev_t1));
+	GG_CUDA(cudaEventElapsedTime(ms, e->ev_t0, e->ev_t1));
+	return GG_OK;
+}
+
+void *gg_engine_stream(gg_engine *e) { return e ? (void *) e->stream : nullptr; }
+
 int gg_relation_create(gg_engine *e, uint64_t nblocks, gg_relation **out)
 {
 	if (!e || !out) return GG_ERR_ARG;

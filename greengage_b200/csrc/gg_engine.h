@@ -15,6 +15,7 @@ struct gg_engine {
 	cudaStream_t stream = nullptr;       /* compute */
 	cudaStream_t copy_stream = nullptr;  /* H2D staging */
 	cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+	cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      /* gg_engine_timer_start/stop */
 	bool timed = false;
 	uint64_t launches = 0;
 };

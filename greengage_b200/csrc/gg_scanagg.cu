@@ -216,6 +216,8 @@ struct gg_scanagg {
 	int mode = MODE_PRIV;           /* kernel variant; escalates PRIV -> TR when a run overflows its group capacity */
 	int ctas_per_sm = 2, gcap = 0;
 	uint32_t scratch_off = 0, cnt_off = 0, acc_off = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
+	size_t kev_used = 0;
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
 	size_t smem = 0;
 	/* device state */
@@ -330,6 +332,14 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	prm.scratch_off = p->scratch_off;
 	prm.cnt_off = p->cnt_off;
 	prm.acc_off = p->acc_off;
+	if (p->kev_used == p->kev.size())
+	{
+		cudaEvent_t a, b;
+		GG_CUDA(cudaEventCreate(&a));
+		GG_CUDA(cudaEventCreate(&b));
+		p->kev.push_back({ a, b });
+	}
+	GG_CUDA(cudaEventRecord(p->kev[p->kev_used].first, st));
 	if (p->jit)
 	{
 		void *args[] = { (void *) &p->prog, (void *) &prm };
@@ -342,6 +352,8 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	else
 		gg_scanagg_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	GG_CUDA(cudaGetLastError());
+	GG_CUDA(cudaEventRecord(p->kev[p->kev_used].second, st));
+	p->kev_used++;
 	e->launches++;
 	/* fold the block records (and the previously merged groups) */
 	ggp_acckinds kinds;
@@ -416,6 +428,7 @@ int gg_scanagg_reset(gg_scanagg *p)
 	GG_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(uint32_t), st));
 	GG_CUDA(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), st));
 	p->has_state = false;
+	p->kev_used = 0;
 	return GG_OK;
 }
 
@@ -603,9 +616,33 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	return GG_OK;
 }
 
+int gg_scanagg_scan_kernel_ms(gg_scanagg *p, float *ms, int *launches)
+{
+	if (!p || !ms) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(p->eng->device));
+	float tot = 0;
+	for (size_t i = 0; i < p->kev_used; i++)
+	{
+		float t = 0;
+		GG_CUDA(cudaEventSynchronize(p->kev[i].second));
+		GG_CUDA(cudaEventElapsedTime(&t, p->kev[i].first, p->kev[i].second));
+		tot += t;
+	}
+	*ms = tot;
+	if (launches) *launches = (int) p->kev_used;
+	return GG_OK;
+}
+
+int gg_scanagg_variant(gg_scanagg *p)
+{
+	if (!p) return -1;
+	return p->mode + (p->jit ? (p->jit->precompiled ? 16 : 32) : 0);
+}
+
 void gg_scanagg_free(gg_scanagg *p)
 {
 	if (!p) return;
+	for (auto &ev : p->kev) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
 	cudaSetDevice(p->eng->device);
 	cudaStreamSynchronize(p->eng->stream);
 	cudaFree(p->recs); cudaFree(p->merged); cudaFree(p->vidx); cudaFree(p->vmap);

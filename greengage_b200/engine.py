@@ -35,6 +35,26 @@ class Engine:
     def launch_count(self):
         return dev_lib().gg_engine_launch_count(self.h)
 
+    def timer_start(self):
+        check(dev_lib().gg_engine_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(dev_lib().gg_engine_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+
+def host_alloc(nbytes):
+    """Pinned host memory (cudaHostAlloc) as (address, numpy view)."""
+    p = C.c_void_p()
+    check(dev_lib().gg_host_alloc(nbytes, C.byref(p)))
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    return p.value, arr
+
+
+def host_free(addr):
+    dev_lib().gg_host_free(C.c_void_p(addr))
+
 
 class Relation:
     """Heap pages resident in HBM (gg_relation)."""
@@ -98,6 +118,14 @@ class ScanAgg:
         sc, ps = C.c_uint64(0), C.c_uint64(0)
         check(dev_lib().gg_scanagg_fetch(self.h, out, cap, C.byref(n), C.byref(sc), C.byref(ps)))
         return [out[i] for i in range(n.value)], sc.value, ps.value
+
+    def scan_kernel_ms(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        check(dev_lib().gg_scanagg_scan_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def variant(self):
+        return dev_lib().gg_scanagg_variant(self.h)
 
     def free(self):
         if self.h:

@@ -1,0 +1,96 @@
+"""Motion for host-resident rows: Redistribute / Gather of the (few) partial-aggregate rows a slice emits.
+
+Replaces execMotionSender / execMotionUnsortedReceiver over the UDP interconnect
+(src/backend/executor/nodeMotion.c:270-374,378; src/backend/cdb/motion/ic_udpifc.c) with collectives on
+one communicator (torch.distributed: NCCL over NVLink on the GPU box, gloo in CPU tests): a count
+exchange followed by an all-to-all-v of fixed-width row records.  Routing is libgghost's gg_cdbhash_route:
+cdbhash + jump consistent hash, bit-exact with src/backend/cdb/cdbhash.c:191-287.  EOS is implicit in
+collective completion (SendEndOfStream, cdbmotion.c:532, has nothing left to do).
+Bulk redistribution of scanned rows is done on the device (csrc/gg_motion.cu).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+ROW_BYTES = C.sizeof(capi.gg_aggrow)
+
+
+def route_aggrow(row, key_typids, nsegs):
+    n = len(key_typids)
+    t = (C.c_int32 * n)(*key_typids)
+    v = (C.c_int64 * n)(*[row.key[i] for i in range(n)])
+    ln = (C.c_int32 * n)(*[row.keylen[i] for i in range(n)])
+    nu = (C.c_int32 * n)(*[row.keyisnull[i] for i in range(n)])
+    return capi.host_lib().gg_cdbhash_route(t, v, ln, nu, n, nsegs)
+
+
+def _rows_to_bytes(rows):
+    buf = np.zeros(len(rows) * ROW_BYTES, dtype=np.uint8)
+    for i, r in enumerate(rows):
+        buf[i * ROW_BYTES:(i + 1) * ROW_BYTES] = np.frombuffer(bytes(r), dtype=np.uint8)
+    return buf
+
+
+def _bytes_to_rows(buf):
+    n = buf.size // ROW_BYTES
+    out = []
+    raw = buf.tobytes()
+    for i in range(n):
+        out.append(capi.gg_aggrow.from_buffer_copy(raw[i * ROW_BYTES:(i + 1) * ROW_BYTES]))
+    return out
+
+
+def _tensor(arr, device):
+    import torch
+    t = torch.from_numpy(arr)
+    return t.to(device) if device is not None else t
+
+
+def redistribute_aggrows(rows, key_typids, device=None, group=None):
+    """Redistribute Motion (MOTIONTYPE_HASH) of aggregate rows on their grouping keys.
+    Returns the rows routed to this rank."""
+    import torch
+    import torch.distributed as dist
+    nsegs = dist.get_world_size(group)
+    dest = [route_aggrow(r, key_typids, nsegs) for r in rows]
+    order = sorted(range(len(rows)), key=lambda i: dest[i])
+    send_counts = np.zeros(nsegs, dtype=np.int64)
+    for d in dest:
+        send_counts[d] += 1
+    sendbuf = _rows_to_bytes([rows[i] for i in order])
+    sc = _tensor(send_counts.copy(), device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.cpu().numpy()
+    st = _tensor(sendbuf if sendbuf.size else np.zeros(0, dtype=np.uint8), device)
+    rt = torch.empty(int(recv_counts.sum()) * ROW_BYTES, dtype=torch.uint8, device=st.device)
+    dist.all_to_all_single(rt, st, output_split_sizes=[int(c) * ROW_BYTES for c in recv_counts],
+                           input_split_sizes=[int(c) * ROW_BYTES for c in send_counts], group=group)
+    return _bytes_to_rows(rt.cpu().numpy())
+
+
+def gather_aggrows(rows, dst=0, device=None, group=None):
+    """Gather Motion (MOTIONTYPE_FIXED to one receiver): rows of all ranks on `dst`, in sender order."""
+    import torch
+    import torch.distributed as dist
+    nsegs = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    cnt = _tensor(np.array([len(rows)], dtype=np.int64), device)
+    counts = [torch.empty_like(cnt) for _ in range(nsegs)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(counts) if counts else 0
+    pad = np.zeros(mx * ROW_BYTES, dtype=np.uint8)
+    b = _rows_to_bytes(rows)
+    pad[:b.size] = b
+    t = _tensor(pad, device)
+    bufs = [torch.empty_like(t) for _ in range(nsegs)]
+    dist.all_gather(bufs, t, group=group)
+    if rank != dst:
+        return []
+    out = []
+    for r in range(nsegs):
+        out.extend(_bytes_to_rows(bufs[r].cpu().numpy()[:counts[r] * ROW_BYTES]))
+    return out

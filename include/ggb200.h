@@ -61,6 +61,11 @@ int  gg_engine_sync(gg_engine *e);
 int  gg_engine_last_kernel_ms(gg_engine *e, float *ms);
 /* number of kernels the engine has launched since creation (bench.py's gpu_launches) */
 uint64_t gg_engine_launch_count(gg_engine *e);
+/* CUDA events on the engine's compute stream bracketing any number of calls (bench.py's timed region) */
+int  gg_engine_timer_start(gg_engine *e);
+int  gg_engine_timer_stop(gg_engine *e, float *ms);
+/* the engine's compute stream (cudaStream_t), for callers that order their own work against it */
+void *gg_engine_stream(gg_engine *e);
 
 /* ---- relations: heap pages in device memory ----
  * Replaces heap_beginscan/heapgetpage's ReadBufferExtended path
@@ -98,6 +103,11 @@ int  gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
                       uint64_t *rows_scanned, uint64_t *rows_passed);
 int  gg_scanagg_reset(gg_scanagg *p);
 void gg_scanagg_free(gg_scanagg *p);
+/* introspection for benchmarks: summed CUDA-event duration of the scan kernel launches since the last reset and
+ * their count; and which kernel variant runs (0 private accumulators, 1 transposed, 2 transposed+NULLs;
+ * +16 plan-specialised at build time, +32 plan-specialised at run time) */
+int  gg_scanagg_scan_kernel_ms(gg_scanagg *p, float *ms, int *launches);
+int  gg_scanagg_variant(gg_scanagg *p);
 
 /* FINAL-stage Agg over partial rows gathered from the segments (combine functions,
  * nodeAgg.c:2123-2148).  agg->grpCol[i] carries the key type OIDs. */

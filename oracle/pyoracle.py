@@ -16,6 +16,11 @@ _lib = None
 _ref = None
 
 
+
+class or_datum(C.Structure):
+    _fields_ = [("v", C.c_int64), ("len", C.c_int32), ("isnull", C.c_int32), ("ptr", C.c_void_p)]
+
+
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
     if os.path.isdir("/root/reference/src"):
@@ -77,6 +82,8 @@ def lib():
                                         C.POINTER(capi.gg_exprpool), vp, u64, i32,
                                         C.POINTER(capi.gg_aggrow), i32, C.POINTER(i32),
                                         C.POINTER(C.c_double), C.POINTER(u64)]
+        L.or_eval.argtypes = [C.POINTER(capi.gg_exprpool), i32, vp, vp, C.POINTER(or_datum)]
+        L.or_bctruelen.argtypes = [C.c_char_p, i32]
         L.or_strerror.restype = C.c_char_p
         L.or_strerror.argtypes = [i32]
         _lib = L
@@ -123,6 +130,13 @@ def ref_lib():
         R.ref_date_cmp_timestamp.argtypes = [i32, i32, i64, C.POINTER(i32)]
         _ref = R
     return _ref
+
+
+def eval_expr(pool, root):
+    """Evaluate a row-independent expression (constants only). Returns (rc, value_bits, isnull)."""
+    d = or_datum()
+    rc = lib().or_eval(C.byref(pool), root, None, None, C.byref(d))
+    return rc, d.v, d.isnull
 
 
 class OracleError(RuntimeError):

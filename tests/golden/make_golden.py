@@ -1,0 +1,264 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE ITSELF.  Run in the build container
+(needs /root/reference and oracle/_ref/libggref.so, built by `make -C oracle/ref_build`).
+
+  hash_kat.json     hash_any / hash_uint32 / hashint4 / hashint8 / hashfloat8 / hashbpchar / bpchareq and
+                    cdbhash+jump-consistent-hash routing, computed by the reference's own hashfunc.o,
+                    varchar.o and cdbhash.o
+  heap_kat.json     tuples formed by the reference's heap_form_tuple (heaptuple.o) for rows with NULLs,
+                    short and long varlenas, and what its heap_deform_tuple reads back
+  float_kat.json    float8pl/mi/mul/div incl. overflow/underflow/div-by-zero ERRORs, float8 comparisons,
+                    float8_accum / float8_combine / float8_avg, int8inc / int8pl overflow, date vs timestamp
+  lineitem_q1.npz   the reference's own regression data (src/test/regress/data/lineitem_small.csv + lineitem.csv,
+                    loaded into heap_lineitem by input/rpt_tpch.source:98-99), columns as arrays
+  q1_expected.json  the reference's golden Q1 answer over that data (output/rpt_tpch.source:309-315)
+"""
+import ctypes as C
+import json
+import os
+import random
+import re
+import struct
+import sys
+from datetime import date
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from greengage_b200 import capi  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+REF = "/root/reference"
+R = po.ref_lib()
+assert R is not None, "build oracle/_ref first: make -C oracle/ref_build"
+rng = random.Random(20260922)
+
+
+def f2b(x):
+    return struct.unpack("<q", struct.pack("<d", x))[0]
+
+
+def hash_kat():
+    out = {"hash_any": [], "hash_uint32": [], "hashint4": [], "hashint8": [], "hashfloat8": [], "hashbpchar": [],
+           "bpchareq": [], "route": []}
+    fixed = [b"", b"A", b"N", b"R", b"F", b"O", b"hello world!", b"0123456789ab", b"0123456789abc", b"x" * 23, b"y" * 24, b"z" * 25]
+    for b in fixed + [bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 64))) for _ in range(300)]:
+        out["hash_any"].append([b.hex(), R.ref_hash_any(b, len(b))])
+    for v in [0, 1, 42, 0xFFFFFFFF, 0x80000000] + [rng.getrandbits(32) for _ in range(200)]:
+        out["hash_uint32"].append([v, R.ref_hash_uint32(v)])
+    for v in [0, 1, -1, 2 ** 31 - 1, -2 ** 31] + [rng.getrandbits(32) - 2 ** 31 for _ in range(200)]:
+        out["hashint4"].append([v, R.ref_hashint4(v)])
+    for v in [0, 1, -1, 2 ** 63 - 1, -2 ** 63, 2 ** 32, -2 ** 32, 2 ** 31, -2 ** 31 - 1] + [rng.getrandbits(64) - 2 ** 63 for _ in range(300)]:
+        out["hashint8"].append([str(v), R.ref_hashint8(v)])
+    for x in [0.0, -0.0, 1.0, -1.0, 0.1, 1e300, -1e-300, float("inf"), float("-inf"), float("nan")] + [rng.uniform(-1e6, 1e6) for _ in range(200)]:
+        out["hashfloat8"].append([str(f2b(x)), R.ref_hashfloat8(x)])
+    strs = [b"A", b"A ", b"A   ", b" A", b"", b"   ", b"DELIVER IN PERSON        ", b"DELIVER IN PERSON", b"abc  def  "]
+    strs += [bytes(rng.choice(b"ab ") for _ in range(rng.randint(0, 12))) for _ in range(200)]
+    for s in strs:
+        out["hashbpchar"].append([s.hex(), R.ref_hashbpchar(s, len(s))])
+    for _ in range(300):
+        a, b = rng.choice(strs), rng.choice(strs)
+        out["bpchareq"].append([a.hex(), b.hex(), R.ref_bpchareq(a, len(a), b, len(b))])
+    # routing: cdbhashinit/cdbhash/cdbhashreduce with real hash functions
+    typs = [20, 23, 701, 1042]
+    for _ in range(1500):
+        nkeys = rng.randint(1, 3)
+        nsegs = rng.choice([1, 2, 3, 4, 5, 7, 8, 16, 31, 64, 100, 1000])
+        t, v, ln, nu = [], [], [], []
+        for k in range(nkeys):
+            ty = rng.choice(typs)
+            isn = rng.random() < 0.1
+            if ty == 20:
+                val, l = rng.getrandbits(64) - 2 ** 63, 0
+            elif ty == 23:
+                val, l = rng.getrandbits(32) - 2 ** 31, 0
+            elif ty == 701:
+                val, l = f2b(rng.choice([0.0, -0.0, 1.5, rng.uniform(-1e9, 1e9)])), 0
+            else:
+                s = bytes(rng.choice(b"ANRFO") for _ in range(rng.randint(0, 8)))
+                val, l = int.from_bytes(s.ljust(8, b"\0"), "little", signed=True), len(s)
+            t.append(ty); v.append(val); ln.append(l); nu.append(1 if isn else 0)
+        seg = R.ref_cdbhash_route((C.c_int32 * nkeys)(*t), (C.c_int64 * nkeys)(*v), (C.c_int32 * nkeys)(*ln),
+                                  (C.c_int32 * nkeys)(*nu), nkeys, nsegs)
+        out["route"].append({"typ": t, "val": [str(x) for x in v], "len": ln, "null": nu, "nsegs": nsegs, "seg": seg})
+    json.dump(out, open(os.path.join(HERE, "hash_kat.json"), "w"))
+    print("hash_kat.json", {k: len(v) for k, v in out.items()})
+
+
+def heap_kat():
+    """tuples formed by the reference's heap_form_tuple"""
+    out = []
+    descs = [("li_wide", capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)), ("orders", capi.synth_tupdesc(capi.TAB_ORDERS))]
+    # a descriptor with nullable columns, a long varlena and odd alignments
+    d = capi.gg_tupdesc()
+    spec = [(23, 4, 'i', 1), (1042, -1, 'i', 0), (20, 8, 'd', 1), (1043, -1, 'i', 0), (701, 8, 'd', 1), (1082, 4, 'i', 1), (1043, -1, 'i', 0), (23, 4, 'i', 1), (20, 8, 'd', 1)]
+    d.natts = len(spec)
+    for i, (t, l, al, bv) in enumerate(spec):
+        a = d.attrs[i]
+        a.atttypid, a.attlen, a.attalign, a.attbyval, a.attnotnull, a.atttypmod = t, l, ord(al), bv, 0, -1
+    descs.append(("mixed", d))
+    for name, desc in descs:
+        n = desc.natts
+        for case in range(60):
+            vals, lens, nulls, pyvals = (C.c_int64 * n)(), (C.c_int32 * n)(), (C.c_uint8 * n)(), []
+            keep = []
+            for i in range(n):
+                a = desc.attrs[i]
+                isnull = name == "mixed" and rng.random() < 0.25
+                nulls[i] = 1 if isnull else 0
+                if isnull:
+                    pyvals.append(None)
+                    continue
+                if a.attlen == -1:
+                    ln = rng.choice([0, 1, 2, 5, 25, 43, 126, 127, 200]) if name == "mixed" else rng.randint(1, 44)
+                    s = bytes(rng.choice(b"abcdefg hij") for _ in range(ln))
+                    buf = C.create_string_buffer(s, max(len(s), 1))
+                    keep.append(buf)
+                    vals[i] = C.addressof(buf)
+                    lens[i] = len(s)
+                    pyvals.append(s.hex())
+                elif a.atttypid == 701:
+                    x = rng.choice([0.0, 1.0, -2.5, rng.uniform(-1e5, 1e5)])
+                    vals[i] = f2b(x)
+                    pyvals.append(str(f2b(x)))
+                elif a.attlen == 4:
+                    x = rng.getrandbits(32) - 2 ** 31
+                    vals[i] = x
+                    pyvals.append(str(x))
+                else:
+                    x = rng.getrandbits(64) - 2 ** 63
+                    vals[i] = x
+                    pyvals.append(str(x))
+            outbuf = (C.c_uint8 * 2048)()
+            ln = R.ref_heap_form_tuple(n, desc.attrs, vals, lens, nulls, outbuf, 2048)
+            tup = bytes(outbuf[:ln])
+            dv, dn = (C.c_int64 * n)(), (C.c_uint8 * n)()
+            tb = (C.c_uint8 * ln).from_buffer_copy(tup)
+            R.ref_heap_deform_tuple(n, desc.attrs, tb, ln, dv, dn)
+            out.append({"desc": name, "values": pyvals, "tuple": tup.hex(),
+                        "deform": [str(dv[i]) for i in range(n)], "deform_null": [int(dn[i]) for i in range(n)]})
+    meta = {}
+    for name, desc in descs:
+        meta[name] = [[desc.attrs[i].atttypid, desc.attrs[i].attlen, chr(desc.attrs[i].attalign), desc.attrs[i].attbyval] for i in range(desc.natts)]
+    json.dump({"descs": meta, "cases": out}, open(os.path.join(HERE, "heap_kat.json"), "w"))
+    print("heap_kat.json", len(out))
+
+
+def float_kat():
+    out = {"arith": [], "cmp": [], "accum": [], "combine": [], "avg": [], "int8inc": [], "int8pl": [], "date_ts": []}
+    specials = [0.0, -0.0, 1.0, -1.0, 0.5, 1e308, -1e308, 1.7976931348623157e308, 4.9e-324, 1e-308, 1e-200, 1e200,
+                float("inf"), float("-inf"), float("nan"), 3.14, 100.25, 0.07]
+    vals = specials + [rng.uniform(-1e6, 1e6) for _ in range(40)]
+    err = C.c_int32(0)
+    for fn in ("pl", "mi", "mul", "div"):
+        f = getattr(R, "ref_float8" + fn)
+        for _ in range(400):
+            a, b = rng.choice(vals), rng.choice(vals)
+            r = f(a, b, C.byref(err))
+            out["arith"].append([fn, str(f2b(a)), str(f2b(b)), int(err.value), str(f2b(r)) if not err.value else "0",
+                                 R.ref_last_error().decode() if err.value and hasattr(R.ref_last_error, "restype") else ""])
+    for _ in range(400):
+        a, b = rng.choice(vals), rng.choice(vals)
+        out["cmp"].append([str(f2b(a)), str(f2b(b)), R.ref_float8eq(a, b), R.ref_float8lt(a, b), R.ref_float8le(a, b), R.ref_btfloat8cmp(a, b)])
+    for _ in range(100):
+        st = (C.c_double * 3)(0.0, 0.0, 0.0)
+        seq = [rng.choice([1.0, 2.5, 1e307, 1e308, -1e308, 1e154, 1e155, 3.0, float("inf")]) for _ in range(rng.randint(1, 6))]
+        errs = []
+        for x in seq:
+            R.ref_float8_accum(st, x, C.byref(err))
+            errs.append(int(err.value))
+            if err.value:
+                break
+        out["accum"].append([[str(f2b(x)) for x in seq], errs, [str(f2b(st[i])) for i in range(3)]])
+    for _ in range(100):
+        a = (C.c_double * 3)(float(rng.randint(0, 5)), rng.choice(vals[:14]), abs(rng.choice(vals[:12])))
+        b = (C.c_double * 3)(float(rng.randint(0, 5)), rng.choice(vals[:14]), abs(rng.choice(vals[:12])))
+        a0 = [str(f2b(a[i])) for i in range(3)]
+        R.ref_float8_combine(a, b, C.byref(err))
+        out["combine"].append([a0, [str(f2b(b[i])) for i in range(3)], int(err.value), [str(f2b(a[i])) for i in range(3)]])
+    isn = C.c_int32(0)
+    for _ in range(60):
+        st = (C.c_double * 3)(float(rng.choice([0, 1, 2, 7, 1000])), rng.choice(vals[:12]), 1.0)
+        r = R.ref_float8_avg(st, C.byref(isn))
+        out["avg"].append([[str(f2b(st[i])) for i in range(3)], int(isn.value), str(f2b(r))])
+    for v in [0, 1, -1, 2 ** 63 - 2, 2 ** 63 - 1, -2 ** 63]:
+        r = R.ref_int8inc(v, C.byref(err))
+        out["int8inc"].append([str(v), int(err.value), str(r)])
+    ints = [0, 1, -1, 2 ** 63 - 1, -2 ** 63, 2 ** 62, -2 ** 62, 12345]
+    for a in ints:
+        for b in ints:
+            r = R.ref_int8pl(a, b, C.byref(err))
+            out["int8pl"].append([str(a), str(b), int(err.value), str(r)])
+    US = 86400000000
+    dates = [0, 1, -1, -396, -504, 10957, -2921, 2 ** 31 - 1, -2 ** 31, 106751991, 106751992, -106751991, -106751992]
+    tss = [0, -396 * US, -504 * US, -504 * US + 1, -504 * US - 1, 2 ** 63 - 1, -2 ** 63, 12345678901234]
+    for op in range(6):
+        for d in dates:
+            for ts in tss:
+                r = R.ref_date_cmp_timestamp(op, d, ts, C.byref(err))
+                out["date_ts"].append([op, d, str(ts), int(err.value), int(r)])
+    json.dump(out, open(os.path.join(HERE, "float_kat.json"), "w"))
+    print("float_kat.json", {k: len(v) for k, v in out.items()})
+
+
+def lineitem_fixture():
+    rows = []
+    for fn in ("lineitem_small.csv", "lineitem.csv"):      # load order of input/rpt_tpch.source:98-99
+        for ln in open(os.path.join(REF, "src/test/regress/data", fn), encoding="latin1"):
+            f = ln.rstrip("\n").split("|")
+            if len(f) >= 16:
+                rows.append(f[:16])
+    epoch = date(2000, 1, 1)
+
+    def d2i(s):
+        y, m, d = map(int, s.split("-"))
+        return (date(y, m, d) - epoch).days
+
+    instr = sorted({r[13] for r in rows})
+    modes = sorted({r[14] for r in rows})
+    np.savez_compressed(
+        os.path.join(HERE, "lineitem_q1.npz"),
+        orderkey=np.array([int(r[0]) for r in rows], dtype=np.int64),
+        partkey=np.array([int(r[1]) for r in rows], dtype=np.int32),
+        suppkey=np.array([int(r[2]) for r in rows], dtype=np.int32),
+        linenumber=np.array([int(r[3]) for r in rows], dtype=np.int32),
+        quantity=np.array([float(r[4]) for r in rows]), extendedprice=np.array([float(r[5]) for r in rows]),
+        discount=np.array([float(r[6]) for r in rows]), tax=np.array([float(r[7]) for r in rows]),
+        returnflag=np.array([ord(r[8]) for r in rows], dtype=np.uint8),
+        linestatus=np.array([ord(r[9]) for r in rows], dtype=np.uint8),
+        shipdate=np.array([d2i(r[10]) for r in rows], dtype=np.int32),
+        commitdate=np.array([d2i(r[11]) for r in rows], dtype=np.int32),
+        receiptdate=np.array([d2i(r[12]) for r in rows], dtype=np.int32),
+        shipinstruct=np.array([instr.index(r[13]) for r in rows], dtype=np.uint8),
+        shipmode=np.array([modes.index(r[14]) for r in rows], dtype=np.uint8),
+        comment_len=np.array([len(r[15].encode("latin1")) for r in rows], dtype=np.uint8),
+        shipinstruct_names=np.array(instr), shipmode_names=np.array(modes))
+    # the golden answer, parsed from the reference's expected output
+    txt = open(os.path.join(REF, "src/test/regress/output/rpt_tpch.source")).read().splitlines()
+    exp = []
+    for i, ln in enumerate(txt):
+        if "l_shipdate <= date '1998-12-01' - interval '108 day'" in ln and "heap_lineitem" in "\n".join(txt[i - 4:i]):
+            j = i
+            while not txt[j].startswith("----------+"):
+                j += 1
+            j += 1
+            while txt[j].strip().startswith("mpph1"):
+                f = [x.strip() for x in txt[j].split("|")]
+                exp.append({"returnflag": f[1], "linestatus": f[2], "sum_qty": f[3], "sum_base_price": f[4],
+                            "sum_disc_price": f[5], "sum_charge": f[6], "avg_qty": f[7], "avg_price": f[8],
+                            "avg_disc": f[9], "count_order": int(f[10])})
+                j += 1
+            break
+    assert len(exp) == 4, exp
+    json.dump({"source": "src/test/regress/output/rpt_tpch.source:288-315", "interval_days": 108, "rows": exp,
+               "nrows_loaded": len(rows)}, open(os.path.join(HERE, "q1_expected.json"), "w"), indent=1)
+    print("lineitem_q1.npz", len(rows), "rows; q1_expected.json", exp[0])
+
+
+if __name__ == "__main__":
+    R.ref_last_error.restype = C.c_char_p
+    hash_kat()
+    heap_kat()
+    float_kat()
+    lineitem_fixture()
