@@ -432,6 +432,20 @@ void gen(Ctx &c, int root)
 			}
 			BinInfo b; int un;
 			if (!func_info(e.funcid, &b, &un)) { fail(c, "function %d not supported on the GPU path", e.funcid); return; }
+			/* the argument types must be the function's own (a planner never emits anything else; a
+			 * hand-built plan that does is refused rather than reinterpreting Datum bits) */
+			{
+				auto is_int = [](int32_t t) { return t == GG_INT4OID || t == GG_INT8OID || t == GG_DATEOID || t == GG_TIMESTAMPOID; };
+				auto is_str = [](int32_t t) { return t == GG_BPCHAROID || t == GG_VARCHAROID || t == GG_TEXTOID; };
+				int32_t t0 = c.pool->nodes[e.args[0]].rettype;
+				int32_t t1 = b.isbin ? c.pool->nodes[e.args[1]].rettype : t0;
+				bool ok = true;
+				if (b.isbin && (b.k == K_F8ADD || b.k == K_F8SUB || b.k == K_F8MUL || b.k == K_F8DIV || b.k == K_CMPF)) ok = t0 == GG_FLOAT8OID && t1 == GG_FLOAT8OID;
+				else if (b.isbin && b.k == K_CMPI) ok = is_int(t0) && is_int(t1);
+				else if (b.isbin && b.k == K_CMPS) ok = is_str(t0) && is_str(t1);
+				else if (!b.isbin) ok = is_int(t0);
+				if (!ok) { fail(c, "function %d applied to arguments of type %d, %d", e.funcid, t0, t1); return; }
+			}
 			if (!b.isbin)
 			{
 				gen(c, e.args[0]);

@@ -160,7 +160,7 @@ typedef struct gg_expr {
 	int32_t constisnull;
 	int32_t constlen;       /* string constants: blank-stripped length */
 	int64_t constvalue;
-} gg_expr;                  /* 40 bytes */
+} gg_expr;                  /* 48 bytes */
 
 typedef struct gg_exprpool {
 	int32_t nnodes;

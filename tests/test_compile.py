@@ -1,0 +1,63 @@
+"""Plan compiler (host side, no GPU): expression trees -> accumulator-machine program; eligibility."""
+import ctypes as C
+
+import pytest
+
+from _util import make_desc
+from greengage_b200 import capi, tpch
+from greengage_b200.capi import ExprPool
+
+L = capi.dev_lib()
+L.gg_debug_disasm_scanagg.argtypes = [C.POINTER(capi.gg_scan), C.POINTER(capi.gg_agg), C.POINTER(capi.gg_exprpool), C.c_char_p, C.c_int]
+
+
+def disasm(scan, agg, pool):
+    buf = C.create_string_buffer(1 << 16)
+    n = L.gg_debug_disasm_scanagg(C.byref(scan), C.byref(agg), C.byref(pool), buf, 1 << 16)
+    if n < 0:
+        raise capi.GGError(n, L.gg_last_error().decode())
+    return buf.value.decode().splitlines()
+
+
+def test_q1_program_shape():
+    lines = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE))
+    ops = [ln.split()[1] for ln in lines]
+    assert ops[:3] == ["LD_C4", "DATE2TS", "CMPI_K"] and "FILTER" in lines[2]
+    assert "KEY0" in lines[3] and "KEY1" in lines[4] and "GROUP" in lines[4]
+    # l_extendedprice*(1-l_discount) is computed once and reused for sum_charge
+    assert sum(1 for o in ops if o == "SUB_C") == 1 and sum(1 for o in ops if o.startswith("MUL")) == 2
+    # single-stage plan: float8_avg ignores sumX2, so no sums of squares are produced
+    assert not any("OUTSQ" in ln for ln in lines)
+    assert ops[-1] == "END"
+    # constant offsets of the fixed-width prefix are baked in; l_linestatus/l_shipdate come from the walk
+    assert "off=24" in lines[5] and "off=-1" in lines[4]
+    part = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
+    assert sum(1 for ln in part if "OUTSQ" in ln) == 3          # avg's transition state {N, sumX, sumX2}
+
+
+def test_unsupported_plans_are_refused():
+    desc = make_desc([(1700, -1, 'i', 0), (capi.FLOAT8OID, 8, 'd', 1)])       # numeric column
+    p = ExprPool()
+    scan = capi.make_scan(desc, -1)
+    with pytest.raises(capi.GGError) as e:
+        disasm(scan, capi.make_agg(0, [], [(capi.AGG_SUM_FLOAT8, p.var(1, 1700))]), p.pool)
+    assert e.value.code == -6
+    p = ExprPool()
+    with pytest.raises(capi.GGError):
+        disasm(scan, capi.make_agg(0, [], [(2114, p.var(2, capi.FLOAT8OID))]), p.pool)     # sum(numeric)
+    p = ExprPool()
+    with pytest.raises(capi.GGError):                                                       # float8 op on an int column without a cast
+        disasm(capi.make_scan(make_desc([(capi.INT4OID, 4, 'i', 1)]), -1),
+               capi.make_agg(0, [], [(capi.AGG_SUM_FLOAT8, p.func(capi.F_FLOAT8PL, capi.FLOAT8OID, p.var(1, capi.INT4OID), p.const(capi.FLOAT8OID, 1.0)))]), p.pool)
+
+
+def test_deep_expression_uses_temporaries():
+    desc = make_desc([(capi.FLOAT8OID, 8, 'd', 1, 1)] * 4)
+    p = ExprPool()
+    a, b, c, d = (p.var(i + 1, capi.FLOAT8OID) for i in range(4))
+    e = p.func(capi.F_FLOAT8MI, capi.FLOAT8OID, p.func(capi.F_FLOAT8MUL, capi.FLOAT8OID, a, b),
+               p.func(capi.F_FLOAT8DIV, capi.FLOAT8OID, c, d))
+    lines = disasm(capi.make_scan(desc, -1), capi.make_agg(0, [], [(capi.AGG_SUM_FLOAT8, e)]), p.pool)
+    ops = [ln.split()[1] for ln in lines]
+    # a plain aggregate opens with the (key-less) GROUP action
+    assert ops == ["NOP", "LD_C8", "MUL_C", "LD_C8", "DIV_C", "RSUB_T", "END"] and "GROUP" in lines[0] and "ST t0" in lines[2]
