@@ -120,27 +120,32 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 			}
 			mm = __ballot_sync(GG_FULL_MASK, need);
 		}
-		if (k < nvalid) vmap[k] = f;
+		if (k < nvalid) vmap[vidx[k]] = f;          /* merged group of record vidx[k], indexed by RECORD */
 	}
 	__threadfence();
 	__syncthreads();
 
-	/* C: fold.  One warp per (merged group, column): lane l folds valid records l, l+32, ... in order,
-	 * then the 32 partials are combined by a fixed butterfly => deterministic result. */
+	/* C: fold.  One warp per (merged group, column).  Records come in sets of GGP_FAST_GROUPS (one set per
+	 * producing block; a set holds a group at most once).  Lane l folds sets l, l+32, ... in order and the 32
+	 * partials are combined by a fixed butterfly, so the summation tree depends only on WHICH block produced a
+	 * record, never on the order in which groups were discovered => bit-identical results run to run. */
 	const int n = s_nout;
 	if (tid == 0) *nout = n;
 	const int V = nacc > 0 ? nacc : 1;
 	const bool saw_inf = (*errflags & GGP_EF_SAW_INF) != 0;
+	const int nsets = (nrecs + GGP_FAST_GROUPS - 1) / GGP_FAST_GROUPS;
 	for (int t = warp; t < n * V; t += (int) (blockDim.x >> 5))
 	{
 		int mg = t / V, j = t % V;
 		int kind = nacc > 0 ? kinds.k[j] : GGP_ACC_COUNT;
 		double s0 = 0.0, s1 = 0.0;
 		unsigned long long cnt = 0, nn = 0;
-		for (int k = lane; k < nvalid; k += 32)
+		for (int set = lane; set < nsets; set += 32)
+		for (int slot = 0; slot < GGP_FAST_GROUPS; slot++)
 		{
-			if (vmap[k] != mg) continue;
-			const ggp_grec &x = recs[vidx[k]];
+			const int i = set * GGP_FAST_GROUPS + slot;
+			if (i >= nrecs || !recs[i].valid || vmap[i] != mg) continue;
+			const ggp_grec &x = recs[i];
 			cnt += x.count;
 			if (nacc > 0 && x.n[j])
 			{
