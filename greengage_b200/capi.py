@@ -183,6 +183,16 @@ def dev_lib():
         L.gg_scanagg_free.argtypes = [vp]
         L.gg_scanagg_free.restype = None
         L.gg_agg_final.argtypes = [vp, C.POINTER(gg_agg), C.POINTER(gg_aggrow), i32, C.POINTER(gg_aggrow), i32, C.POINTER(i32)]
+        L.gg_joinagg_create.argtypes = [vp, C.POINTER(gg_scan), C.POINTER(gg_scan), C.POINTER(gg_hashjoin), C.POINTER(gg_agg),
+                                        C.POINTER(gg_exprpool), C.POINTER(vp)]
+        L.gg_joinagg_build.argtypes = [vp, vp, u64, u64]
+        L.gg_joinagg_probe.argtypes = [vp, vp, u64, u64]
+        L.gg_joinagg_probe_host.argtypes = [vp, vp, u64]
+        L.gg_joinagg_fetch.argtypes = [vp, C.POINTER(gg_aggrow), i32, C.POINTER(i32), C.POINTER(u64)]
+        L.gg_joinagg_reset.argtypes = [vp]
+        L.gg_joinagg_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.gg_joinagg_free.argtypes = [vp]
+        L.gg_joinagg_free.restype = None
         _dev = L
     return _dev
 
@@ -281,6 +291,18 @@ def make_agg(stage, grpcols, aggs, num_groups=0):
         a.aggs[i].aggfnoid = fn
         a.aggs[i].arg = arg
     return a
+
+
+def make_hashjoin(jointype, outerkeys, innerkeys, joinqual=-1):
+    """HashJoin.hashclauses as (outer expr, inner expr) pairs + the residual join qual (plannodes.h HashJoin)."""
+    h = gg_hashjoin()
+    h.jointype = jointype
+    h.nkeys = len(outerkeys)
+    for i, (o, n) in enumerate(zip(outerkeys, innerkeys)):
+        h.outerkey[i] = o
+        h.innerkey[i] = n
+    h.joinqual = joinqual
+    return h
 
 
 def synth_tupdesc(table):

@@ -30,6 +30,7 @@ struct Ctx {
 	int temps_busy;           /* bit t: temporary t holds a live value */
 	int npersist;
 	int persist_root[4], persist_temp[4];   /* common subexpressions kept in temporaries for later aggregate arguments */
+	bool inner_as_outer;      /* build program of a join: the inner tuple is the scanned one */
 	bool failed;
 };
 
@@ -99,8 +100,10 @@ void init_side(ggp_side *s, const gg_tupdesc *d)
 /* slot of (varno, attno), allocating on first use */
 int col_slot(Ctx &c, int varno, int attno)
 {
-	ggp_side *s = varno == 1 ? c.inner : c.outer;
-	const gg_tupdesc *d = varno == 1 ? c.idesc : c.odesc;
+	const bool inner = varno == 1 && !c.inner_as_outer;
+	if (c.inner_as_outer && varno != 1) { fail(c, "outer Var in an inner-only expression"); return 0; }
+	ggp_side *s = inner ? c.inner : c.outer;
+	const gg_tupdesc *d = inner ? c.idesc : c.odesc;
 
 	if (!s || !d) { fail(c, "Var references a side that does not exist (varno %d)", varno); return 0; }
 	if (attno < 1 || attno > d->natts) { fail(c, "Var attno %d out of range", attno); return 0; }
@@ -115,6 +118,7 @@ int col_slot(Ctx &c, int varno, int attno)
 	s->colatt[slot] = (uint8_t) a;
 	if (a + 1 > s->natts_walk) s->natts_walk = a + 1;
 	if (!d->attrs[a].attnotnull) c.prog->nullable = 1;
+	if (inner && slot >= GGP_MAX_PAYLOAD) { fail(c, "too many inner columns referenced above the join"); return 0; }
 	return slot;
 }
 
@@ -149,9 +153,9 @@ void emit(Ctx &c, int op, int idx = 0, int aux = 0)
 	memset(&o, 0, sizeof o);
 	o.op = (uint8_t) op; o.idx = (uint8_t) idx; o.aux = (uint8_t) aux;
 	o.off = 0xFFFF;
-	if (is_col_op(op))
+	if (is_col_op(op) && !(idx & 0x80))
 	{
-		const ggp_side *s = (idx & 0x80) ? c.inner : c.outer;
+		const ggp_side *s = c.outer;
 		int a = s->colatt[idx & 0x7F];
 		if (s->att[a].cacheoff >= 0) o.off = (uint16_t) s->att[a].cacheoff;
 	}
@@ -211,10 +215,11 @@ Operand operand_of(Ctx &c, int root)
 	if (e.kind == GG_E_VAR)
 	{
 		int slot = col_slot(c, e.varno, e.varattno);
-		const ggp_side *s = e.varno == 1 ? c.inner : c.outer;
+		const bool inner = e.varno == 1 && !c.inner_as_outer;
+		const ggp_side *s = inner ? c.inner : c.outer;
 		if (c.failed) return o;
 		int lt = s->coltype[slot];
-		o.idx = slot | (e.varno == 1 ? 0x80 : 0);
+		o.idx = slot | (inner ? 0x80 : 0);
 		o.kind = lt == GGP_LT_I4 ? OPD_C4 : lt == GGP_LT_I8 ? OPD_C8 : OPD_STR;
 		if (lt == GGP_LT_BOOL) o.kind = OPD_NONE;
 	}
@@ -292,7 +297,7 @@ void emit_load(Ctx &c, const Operand &o, int root)
 	}
 	if (e.kind == GG_E_VAR && !c.failed)      /* bool column */
 	{
-		emit(c, GGP_LD_BOOL, col_slot(c, e.varno, e.varattno) | (e.varno == 1 ? 0x80 : 0));
+		emit(c, GGP_LD_BOOL, col_slot(c, e.varno, e.varattno) | ((e.varno == 1 && !c.inner_as_outer) ? 0x80 : 0));
 		return;
 	}
 	fail(c, "operand cannot be loaded");
@@ -478,31 +483,12 @@ ggp_op *gen_value(Ctx &c, int root)
 
 }  // namespace
 
-int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
-                        ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen)
+/* grouping keys, GROUP and the aggregate arguments: the part of the row program that is the same for a
+ * plain scan and for the per-match segment of a join */
+static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 {
-	Ctx c;
-	memset(prog, 0, sizeof *prog);
-	memset(&c, 0, sizeof c);
-	c.pool = pool; c.prog = prog; c.outer = &prog->outer; c.inner = nullptr;
-	c.odesc = &scan->desc; c.idesc = nullptr; c.err = err; c.errlen = errlen;
-	if (err && errlen) err[0] = 0;
-
-	if (scan->desc.natts < 0 || scan->desc.natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return GG_ERR_UNSUPPORTED; }
-	for (int i = 0; i < scan->desc.natts; i++)
-	{
-		const gg_attr &a = scan->desc.attrs[i];
-		if (!(a.attlen == -1 || a.attlen == 1 || a.attlen == 2 || a.attlen == 4 || a.attlen == 8))
-		{ fail(c, "attribute %d: attlen %d not supported", i + 1, a.attlen); return GG_ERR_UNSUPPORTED; }
-	}
-	init_side(&prog->outer, &scan->desc);
-
-	/* ---- scan qual ---- */
-	if (scan->qual >= 0)
-	{
-		ggp_op *o = gen_value(c, scan->qual);
-		if (!c.failed) o->flags |= GGP_F_FILTER;
-	}
+	ggp_program *prog = c.prog;
+	const gg_exprpool *pool = c.pool;
 	/* ---- grouping keys ---- */
 	if (agg->numCols < 0 || agg->numCols > GG_MAX_KEYS) fail(c, "too many grouping columns");
 	prog->nkeys = agg->numCols;
@@ -557,8 +543,15 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 		int found = -1;
 		for (int j = 0; j < prog->nacc; j++)
 		{
-			bool compat = prog->acckind[j] == kind || (kind == GGP_ACC_COUNT && prog->acckind[j] != GGP_ACC_COUNT);
-			if (compat && expr_equal(pool, accroot[j], ar.arg)) { found = j; break; }
+			/* every column kind also counts its non-NULL inputs, so count(x) rides on any column over x —
+			 * and a column created for count(x) is upgraded when sum/min/max(x) comes later */
+			bool compat = prog->acckind[j] == kind || kind == GGP_ACC_COUNT || prog->acckind[j] == GGP_ACC_COUNT;
+			if (compat && expr_equal(pool, accroot[j], ar.arg))
+			{
+				found = j;
+				if (prog->acckind[j] == GGP_ACC_COUNT) prog->acckind[j] = (uint8_t) kind;
+				break;
+			}
 		}
 		if (found < 0)
 		{
@@ -612,7 +605,159 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 	prog->priv_ok = !prog->nullable;
 	for (int j = 0; j < prog->nacc; j++)
 		if (prog->acckind[j] != GGP_ACC_F8SUM) prog->priv_ok = 0;
+}
+
+
+int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
+                        ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen)
+{
+	Ctx c;
+	memset(prog, 0, sizeof *prog);
+	memset(&c, 0, sizeof c);
+	c.pool = pool; c.prog = prog; c.outer = &prog->outer; c.inner = nullptr;
+	c.odesc = &scan->desc; c.idesc = nullptr; c.err = err; c.errlen = errlen;
+	if (err && errlen) err[0] = 0;
+
+	if (scan->desc.natts < 0 || scan->desc.natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return GG_ERR_UNSUPPORTED; }
+	for (int i = 0; i < scan->desc.natts; i++)
+	{
+		const gg_attr &a = scan->desc.attrs[i];
+		if (!(a.attlen == -1 || a.attlen == 1 || a.attlen == 2 || a.attlen == 4 || a.attlen == 8))
+		{ fail(c, "attribute %d: attlen %d not supported", i + 1, a.attlen); return GG_ERR_UNSUPPORTED; }
+	}
+	init_side(&prog->outer, &scan->desc);
+
+	/* ---- scan qual ---- */
+	if (scan->qual >= 0)
+	{
+		ggp_op *o = gen_value(c, scan->qual);
+		if (!c.failed) o->flags |= GGP_F_FILTER;
+	}
+	compile_agg_part(c, agg, aggmap);
 	if (c.failed) return GG_ERR_UNSUPPORTED;
+	return GG_OK;
+}
+
+static bool check_desc(Ctx &c, const gg_tupdesc *d)
+{
+	if (d->natts < 0 || d->natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return false; }
+	for (int i = 0; i < d->natts; i++)
+	{
+		const gg_attr &a = d->attrs[i];
+		if (!(a.attlen == -1 || a.attlen == 1 || a.attlen == 2 || a.attlen == 4 || a.attlen == 8))
+		{ fail(c, "attribute %d: attlen %d not supported", i + 1, a.attlen); return false; }
+	}
+	return true;
+}
+
+static int join_keytype(int32_t t)
+{
+	switch (t)
+	{
+		case GG_INT4OID: case GG_INT8OID: case GG_DATEOID: case GG_TIMESTAMPOID: case GG_BOOLOID: return 1;
+		case GG_FLOAT8OID: return 2;
+		case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID: return 3;
+	}
+	return 0;
+}
+
+/* HashJoin + Agg: see ggp_joinprog in gg_program.h.  Stands where ExecInitHashJoin / ExecInitHash prepare
+ * hj_OuterHashKeys / hashkeys and the hash functions (nodeHashjoin.c:540-750, nodeHash.c:270-450). */
+int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
+                     const gg_exprpool *pool, ggp_joinprog *jp, ggp_aggmap *aggmap, char *err, int errlen)
+{
+	Ctx c;
+	memset(jp, 0, sizeof *jp);
+	memset(&c, 0, sizeof c);
+	c.pool = pool; c.err = err; c.errlen = errlen;
+	if (err && errlen) err[0] = 0;
+	if (hj->nkeys < 1 || hj->nkeys > 2) { fail(c, "hash join with %d keys not supported (1 or 2)", hj->nkeys); return GG_ERR_UNSUPPORTED; }
+	if (!(hj->jointype == GG_JOIN_INNER || hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_SEMI || hj->jointype == GG_JOIN_ANTI))
+	{ fail(c, "join type %d not supported", hj->jointype); return GG_ERR_UNSUPPORTED; }
+	jp->nkeys = hj->nkeys;
+	jp->jointype = hj->jointype;
+
+	/* ---- probe program: outer tuple scanned, inner columns = payload slots ---- */
+	c.prog = &jp->probe;
+	c.outer = &jp->probe.outer;
+	ggp_side innerside;
+	c.inner = &innerside;
+	c.odesc = &outer->desc;
+	c.idesc = &inner->desc;
+	if (!check_desc(c, &outer->desc) || !check_desc(c, &inner->desc)) return GG_ERR_UNSUPPORTED;
+	init_side(&jp->probe.outer, &outer->desc);
+	init_side(&innerside, &inner->desc);
+	if (outer->qual >= 0)
+	{
+		ggp_op *o = gen_value(c, outer->qual);
+		if (!c.failed) o->flags |= GGP_F_FILTER;
+	}
+	for (int k = 0; k < hj->nkeys && !c.failed; k++)
+	{
+		int kt = join_keytype(pool->nodes[hj->outerkey[k]].rettype);
+		int kti = join_keytype(pool->nodes[hj->innerkey[k]].rettype);
+		if (!kt || kt != kti) { fail(c, "join key %d: types %d / %d not hash-joinable on the GPU path", k, pool->nodes[hj->outerkey[k]].rettype, pool->nodes[hj->innerkey[k]].rettype); break; }
+		jp->keytype[k] = (uint8_t) kt;
+		ggp_op *o = gen_value(c, hj->outerkey[k]);
+		if (c.failed) break;
+		if (o->flags & GGP_F_KEY) { emit(c, GGP_NOP); o = &jp->probe.code[jp->probe.ncode - 1]; }
+		o->flags |= GGP_F_KEY;
+		o->aux = (uint8_t) ((o->aux & 0x3F) | (k << 6));
+		if (k == hj->nkeys - 1) o->flags |= GGP_F_PROBE;
+	}
+	jp->probe_pc = jp->probe.ncode;
+	if (hj->joinqual >= 0 && !c.failed)
+	{
+		ggp_op *o = gen_value(c, hj->joinqual);
+		if (!c.failed) o->flags |= GGP_F_FILTER;
+	}
+	if (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI) jp->probe.nullable = 1;   /* null-extended inner side */
+	if (!c.failed) compile_agg_part(c, agg, aggmap);
+	jp->npayload = innerside.ncols;
+	if (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI) { jp->probe.nullable = 1; jp->probe.priv_ok = 0; }
+
+	/* ---- build program: inner tuple scanned; keys, then the payload columns in slot order ---- */
+	Ctx b;
+	memset(&b, 0, sizeof b);
+	b.pool = pool; b.err = err; b.errlen = errlen;
+	b.failed = c.failed;
+	b.prog = &jp->build;
+	b.outer = &jp->build.outer;
+	b.inner = nullptr;
+	b.odesc = &inner->desc;
+	b.idesc = nullptr;
+	b.inner_as_outer = true;
+	init_side(&jp->build.outer, &inner->desc);
+	if (inner->qual >= 0 && !b.failed)
+	{
+		ggp_op *o = gen_value(b, inner->qual);
+		if (!b.failed) o->flags |= GGP_F_FILTER;
+	}
+	for (int k = 0; k < hj->nkeys && !b.failed; k++)
+	{
+		ggp_op *o = gen_value(b, hj->innerkey[k]);
+		if (b.failed) break;
+		if (o->flags & GGP_F_KEY) { emit(b, GGP_NOP); o = &jp->build.code[jp->build.ncode - 1]; }
+		o->flags |= GGP_F_KEY;
+		o->aux = (uint8_t) ((o->aux & 0x3F) | (k << 6));
+		if (k == hj->nkeys - 1) o->flags |= GGP_F_GROUP;       /* keys complete: claim the hash-table slot */
+	}
+	for (int p = 0; p < innerside.ncols && !b.failed; p++)
+	{
+		/* payload slot p = inner attribute colatt[p], loaded the way the probe side expects to read it */
+		int att = innerside.colatt[p];
+		int slot = col_slot(b, 1, att + 1);
+		if (b.failed) break;
+		int lt = innerside.coltype[p];
+		emit(b, lt == GGP_LT_I4 ? GGP_LD_C4 : lt == GGP_LT_I8 ? GGP_LD_C8 : lt == GGP_LT_BPCHAR ? GGP_LD_BP : lt == GGP_LT_VARCHAR ? GGP_LD_VS : GGP_LD_BOOL, slot);
+		ggp_op *o = &jp->build.code[jp->build.ncode - 1];
+		o->flags |= GGP_F_OUT;
+		o->out = (uint8_t) p;
+	}
+	if (!b.failed) emit(b, GGP_END);
+	jp->build.nkeys = hj->nkeys;
+	for (int k = 0; k < hj->nkeys; k++) jp->build.keytype[k] = jp->keytype[k];
+	if (c.failed || b.failed) return GG_ERR_UNSUPPORTED;
 	return GG_OK;
 }
 
@@ -634,6 +779,7 @@ int ggp_disasm(const ggp_program *p, char *buf, int cap)
 		if (o.flags & GGP_F_FILTER) n += snprintf(buf + n, (size_t) (cap - n), " FILTER");
 		if (o.flags & GGP_F_KEY) n += snprintf(buf + n, (size_t) (cap - n), " KEY%d", (o.aux >> 6) & 3);
 		if (o.flags & GGP_F_GROUP) n += snprintf(buf + n, (size_t) (cap - n), " GROUP");
+		if (o.flags & GGP_F_PROBE) n += snprintf(buf + n, (size_t) (cap - n), " PROBE");
 		if (o.flags & GGP_F_OUT) n += snprintf(buf + n, (size_t) (cap - n), " OUT%d", o.out);
 		if (o.flags & GGP_F_OUTSQ) n += snprintf(buf + n, (size_t) (cap - n), " OUTSQ%d", o.out2);
 		n += snprintf(buf + n, (size_t) (cap - n), "\n");

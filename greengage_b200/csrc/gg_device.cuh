@@ -334,9 +334,9 @@ struct EvalCtx {
 	TupleView tv;           /* outer / scan tuple */
 	uint32_t offs;          /* shared address of its per-lane column offsets [slot*32 + lane] u16 */
 	bool fast;              /* constant offsets usable (no tuple of the warp has NULLs) */
-	TupleView itv;          /* inner tuple (joins) */
-	uint32_t ioffs;
-	bool ifast;
+	const uint64_t *ipay;   /* joins: the matched hash-table entry's payload = the inner columns, already loaded
+	                         * (sign-extended / packed) by the build program; slot i = inner column slot i */
+	uint32_t ipaynull;      /* bit i: inner column slot i is NULL (all ones for a null-extended row) */
 	int lane;
 };
 
@@ -360,11 +360,12 @@ template <bool NULLABLE, bool HAS_INNER, class Sink, class KF>
 __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const KF &KV, uint32_t constnull,
                                         MachState &M, uint32_t &err, Sink &sink)
 {
-#define GG_COLADDR(O) \
-	((HAS_INNER && ((O).idx & 0x80)) \
-	 ? (X.itv.tp + ((X.ifast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.ioffs + (uint32_t) ((((O).idx & 0x7F) * 32) + X.lane) * 2))) \
-	 : (X.tv.tp + ((X.fast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.offs + (uint32_t) (((O).idx * 32) + X.lane) * 2))))
-#define GG_COLNULL(O) (NULLABLE && (((HAS_INNER && ((O).idx & 0x80)) ? (X.itv.colnull >> ((O).idx & 0x7F)) : (X.tv.colnull >> (O).idx)) & 1))
+#define GG_COLADDR(O) (X.tv.tp + ((X.fast && (O).off != 0xFFFF) ? (uint32_t) (O).off : lds16(X.offs + (uint32_t) (((O).idx * 32) + X.lane) * 2)))
+#define GG_ISINNER(O) (HAS_INNER && ((O).idx & 0x80))
+#define GG_INNERVAL(O) (__ldg(X.ipay + ((O).idx & 0x7F)))
+#define GG_COL64(O) (GG_ISINNER(O) ? GG_INNERVAL(O) : lds64(GG_COLADDR(O)))
+#define GG_COLI4(O) (GG_ISINNER(O) ? GG_INNERVAL(O) : (uint64_t) (int64_t) (int32_t) lds32(GG_COLADDR(O)))
+#define GG_COLNULL(O) (NULLABLE && ((GG_ISINNER(O) ? (X.ipaynull >> ((O).idx & 0x7F)) : (X.tv.colnull >> (O).idx)) & 1))
 #define GG_TEMP(IDX) ((IDX) == 0 ? M.t0 : (IDX) == 1 ? M.t1 : (IDX) == 2 ? M.t2 : M.t3)
 #define GG_TNULL(IDX) (NULLABLE && ((M.tnull >> (IDX)) & 1))
 #define GG_KNULL(IDX) (NULLABLE && ((constnull >> (IDX)) & 1))
@@ -374,24 +375,24 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 	{ const double x = (XV), y = (YV), r = (EXPR); const bool isn = NULLABLE && (M.accnull || (SN)); \
 	  if (!f8_finite(r) || ((KIND) != 0 && r == 0.0)) { if (M.live && !isn) err |= f8_check_slow((KIND), x, y, r); } \
 	  M.acc = (uint64_t) __double_as_longlong(r); M.accnull = isn; }
-#define GG_COLF8(O, SN, V) const bool SN = GG_COLNULL(O); const double V = SN ? 1.0 : ldsf64(GG_COLADDR(O));
+#define GG_COLF8(O, SN, V) const bool SN = GG_COLNULL(O); const double V = SN ? 1.0 : GG_D(GG_COL64(O));
 
 	const int op = o.op;
 	/* most frequent first; the op stream is uniform across the warp, so these branches never diverge */
-	if (op == GGP_LD_C8) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : lds64(GG_COLADDR(o)); }
+	if (op == GGP_LD_C8) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : GG_COL64(o); }
 	else if (op == GGP_MUL_C) { GG_COLF8(o, sn, v) GG_F8(1, __dmul_rn(x, y), GG_ACCD, v, sn) }
 	else if (op == GGP_MUL_T) { GG_F8(1, __dmul_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) }
 	else if (op == GGP_LD_K) { M.acc = (uint64_t) KV(o.idx); M.accnull = GG_KNULL(o.idx); }
 	else if (op == GGP_ADD_C) { GG_COLF8(o, sn, v) GG_F8(0, __dadd_rn(x, y), GG_ACCD, v, sn) }
 	else if (op == GGP_SUB_C) { GG_COLF8(o, sn, v) GG_F8(0, __dsub_rn(x, y), GG_ACCD, v, sn) }
-	else if (op == GGP_LD_C4) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (uint64_t) (int64_t) (int32_t) lds32(GG_COLADDR(o)); }
+	else if (op == GGP_LD_C4) { M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : GG_COLI4(o); }
 	else if (op == GGP_CMPI_K) { const int64_t y = KV(o.idx), x = (int64_t) M.acc;
 		M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_KNULL(o.idx); }
-	else if (op == GGP_LD_BP) { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : load_str(GG_COLADDR(o), true, e2); if (M.live) err |= e2; }
+	else if (op == GGP_LD_BP) { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (GG_ISINNER(o) ? GG_INNERVAL(o) : load_str(GG_COLADDR(o), true, e2)); if (M.live) err |= e2; }
 	else switch (op)
 	{
-		case GGP_LD_VS: { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : load_str(GG_COLADDR(o), false, e2); if (M.live) err |= e2; } break;
-		case GGP_LD_BOOL: M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (uint64_t) (lds8(GG_COLADDR(o)) != 0); break;
+		case GGP_LD_VS: { uint32_t e2 = 0; M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (GG_ISINNER(o) ? GG_INNERVAL(o) : load_str(GG_COLADDR(o), false, e2)); if (M.live) err |= e2; } break;
+		case GGP_LD_BOOL: M.accnull = GG_COLNULL(o); M.acc = M.accnull ? 0 : (GG_ISINNER(o) ? GG_INNERVAL(o) : (uint64_t) (lds8(GG_COLADDR(o)) != 0)); break;
 		case GGP_LD_T: M.acc = GG_TEMP(o.idx); M.accnull = GG_TNULL(o.idx); break;
 		case GGP_ADD_K: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(KV(o.idx)), GG_KNULL(o.idx)) break;
 		case GGP_ADD_T: GG_F8(0, __dadd_rn(x, y), GG_ACCD, GG_D(GG_TEMP(o.idx)), GG_TNULL(o.idx)) break;
@@ -408,20 +409,27 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 			const bool rev = op >= GGP_RDIV_C;
 			bool sn;
 			double v;
-			if (v3 == 0) { sn = GG_COLNULL(o); v = sn ? 1.0 : ldsf64(GG_COLADDR(o)); }
+			if (v3 == 0) { sn = GG_COLNULL(o); v = sn ? 1.0 : GG_D(GG_COL64(o)); }
 			else if (v3 == 1) { sn = GG_KNULL(o.idx); v = GG_D(KV(o.idx)); }
 			else { sn = GG_TNULL(o.idx); v = GG_D(GG_TEMP(o.idx)); }
 			const double xn = rev ? v : GG_ACCD, yd = rev ? GG_ACCD : v;
-			if (M.live && !(NULLABLE && (M.accnull || sn)) && yd == 0.0) err |= GGP_EF_DIV_ZERO;
-			GG_F8(2, __ddiv_rn(x, y), xn, yd, sn)
+			if (yd == 0.0)
+			{
+				/* ereport(division by zero) comes before the division and its CHECKFLOATVAL (float.c:818) */
+				const bool isn = NULLABLE && (M.accnull || sn);
+				if (M.live && !isn) err |= GGP_EF_DIV_ZERO;
+				M.acc = (uint64_t) __double_as_longlong(__ddiv_rn(xn, yd)); M.accnull = isn;
+			}
+			else
+				GG_F8(2, __ddiv_rn(x, y), xn, yd, sn)
 			break;
 		}
 		case GGP_CMPF_C: { GG_COLF8(o, sn, v) M.acc = test_cc(f8_cmp(GG_ACCD, v), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
 		case GGP_CMPF_K: M.acc = test_cc(f8_cmp(GG_ACCD, GG_D(KV(o.idx))), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_KNULL(o.idx); break;
 		case GGP_CMPF_T: M.acc = test_cc(f8_cmp(GG_ACCD, GG_D(GG_TEMP(o.idx))), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_TNULL(o.idx); break;
-		case GGP_CMPI_C4: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) (int32_t) lds32(GG_COLADDR(o)), x = (int64_t) M.acc;
+		case GGP_CMPI_C4: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) GG_COLI4(o), x = (int64_t) M.acc;
 			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
-		case GGP_CMPI_C8: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) lds64(GG_COLADDR(o)), x = (int64_t) M.acc;
+		case GGP_CMPI_C8: { const bool sn = GG_COLNULL(o); const int64_t y = sn ? 0 : (int64_t) GG_COL64(o), x = (int64_t) M.acc;
 			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || sn; } break;
 		case GGP_CMPI_T: { const int64_t y = (int64_t) GG_TEMP(o.idx), x = (int64_t) M.acc;
 			M.acc = test_cc((x > y) - (x < y), o.aux & 7); if (NULLABLE) M.accnull = M.accnull || GG_TNULL(o.idx); } break;
@@ -485,6 +493,10 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 		if (o.flags & GGP_F_OUTSQ) { const double v = GG_ACCD; sink.out(o.out2, __dmul_rn(v, v), M.accnull); }
 	}
 #undef GG_COLADDR
+#undef GG_ISINNER
+#undef GG_INNERVAL
+#undef GG_COL64
+#undef GG_COLI4
 #undef GG_COLNULL
 #undef GG_TEMP
 #undef GG_TNULL
@@ -500,20 +512,26 @@ struct DynConsts {
 	const ggp_program *P;
 	__device__ __forceinline__ int64_t operator()(int i) const { return P->consts[i]; }
 };
+/* ops [pc0, pc1) — or up to END — on machine state M (joins run the program in two pieces) */
 template <bool NULLABLE, bool HAS_INNER, class Sink>
-__device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &err, Sink &sink)
+__device__ __forceinline__ void run_range(const EvalCtx &X, MachState &M, int pc0, int pc1, uint32_t &err, Sink &sink)
 {
 	const ggp_program &P = *X.P;
-	MachState M;
-	M.reset(live);
 	DynConsts KV;
 	KV.P = &P;
-	for (int pc = 0;; pc++)
+	for (int pc = pc0; pc < pc1; pc++)
 	{
 		const ggp_op o = P.code[pc];
 		if (o.op == GGP_END) break;
 		exec_op<NULLABLE, HAS_INNER>(o, X, KV, (uint32_t) P.constnull, M, err, sink);
 	}
+}
+template <bool NULLABLE, bool HAS_INNER, class Sink>
+__device__ __forceinline__ void run_prog(const EvalCtx &X, bool live, uint32_t &err, Sink &sink)
+{
+	MachState M;
+	M.reset(live);
+	run_range<NULLABLE, HAS_INNER>(X, M, 0, GGP_MAX_CODE, err, sink);
 }
 
 }  // namespace ggd

@@ -66,6 +66,7 @@ enum ggp_cc { GGP_LT = 0, GGP_LE, GGP_EQ, GGP_NE, GGP_GT, GGP_GE };
 #define GGP_F_GROUP   0x08     /* all keys known: find/insert the group */
 #define GGP_F_OUT     0x10     /* value slot[out] = acc */
 #define GGP_F_OUTSQ   0x20     /* value slot[out2] = acc * acc  (float8_accum's sumX2, float.c:1878) */
+#define GGP_F_PROBE   0x40     /* join pipelines: the probing row's join keys are complete; what follows runs once per match */
 
 typedef struct ggp_op {
 	uint8_t  op;
@@ -121,6 +122,23 @@ typedef struct ggp_program {
 	int32_t  priv_ok;        /* 1: every column is a NOT NULL float8 sum => private-accumulator kernel applies */
 } ggp_program;
 
+/* HashJoin (+ Agg on top): two programs.
+ *   build  runs over every inner tuple:  [inner qual FILTER]  join keys KEY k..  payload columns OUT p..
+ *   probe  runs over every outer tuple:  [outer qual FILTER]  join keys KEY k.. PROBE
+ *          and then once per matching inner row, with the payload visible as "inner columns":
+ *          [join qual FILTER]  grouping keys KEY k.. GROUP  aggregate arguments OUT/OUTSQ
+ * The payload is exactly the set of inner columns referenced above the join (Vars with varno 1). */
+#define GGP_MAX_PAYLOAD 8
+typedef struct ggp_joinprog {
+	ggp_program build;
+	ggp_program probe;       /* probe.nkeys/keytype describe the GROUPING keys of the aggregate above the join */
+	int32_t nkeys;           /* join keys */
+	int32_t npayload;
+	int32_t jointype;        /* gg_jointype */
+	int32_t probe_pc;        /* first op of the per-match segment of `probe` */
+	uint8_t keytype[GG_MAX_KEYS];
+} ggp_joinprog;
+
 /* One partial group record: what a block (or a segment, for the FINAL stage) knows about one group.
  * The merge kernel folds records with equal keys in a fixed order, so results are deterministic. */
 typedef struct ggp_grec {
@@ -159,6 +177,8 @@ struct ggp_aggmap {          /* how each Aggref reads the accumulator columns */
 int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
                         ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen);
 int ggp_disasm(const ggp_program *p, char *buf, int cap);
+int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
+                     const gg_exprpool *pool, ggp_joinprog *jp, ggp_aggmap *aggmap, char *err, int errlen);
 #endif
 
 #endif /* GG_PROGRAM_H */

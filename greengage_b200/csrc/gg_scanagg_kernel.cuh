@@ -35,7 +35,33 @@ namespace ggd {
 
 #define GG_NROUNDS (GGP_MAX_PAIRS / 32)
 
-enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2 };
+enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2,
+       MODE_BUILD = 3 };   /* Hash node: scan the inner relation into the join hash table (no aggregation) */
+
+/* Join hash table (Hash / HashJoin, nodeHash.c:88-176,906-1222): open addressing, linear probing, one
+ * slot per inner row (duplicate keys simply occupy successive slots), entries of `stride` 64-bit words:
+ *   [0]            bit 63 occupied | bits 32..39 payload-NULL mask | bits 0..31 hash
+ *   [1 .. nkeys]   join keys, normalised so that bitwise equality is SQL equality
+ *   [1+nkeys ..]   payload = the inner columns referenced above the join, loaded by the build program
+ * Sized by the host to >= 2x the inner row count, so a probe always ends at an empty slot. */
+struct JoinTable {
+	unsigned long long *ent;
+	uint32_t mask;                        /* slots - 1 (power of two) */
+	uint32_t stride;                      /* 64-bit words per entry */
+	int nkeys, npayload;
+	int jointype;                         /* gg_jointype */
+	int probe_pc;                         /* probe program: first op of the per-match segment */
+	uint32_t keytypes;                    /* join keys, 2 bits each */
+	unsigned long long *nbuilt;           /* rows inserted */
+};
+#define GG_HT_OCCUPIED 0x8000000000000000ull
+
+__device__ __forceinline__ uint64_t join_hash(uint64_t k0, uint64_t k1)
+{
+	uint64_t h = k0 ^ (k1 * 0x9E3779B97F4A7C15ull);
+	h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+	return h;
+}
 
 struct ScanAggParams {
 	const uint8_t *pages;
@@ -48,6 +74,7 @@ struct ScanAggParams {
 	int scratch_per_warp;                 /* bytes: column offsets (+ TR: transposed values, group ids, null masks) */
 	uint32_t scratch_off;                 /* byte offsets from the start of dynamic shared memory */
 	uint32_t cnt_off, acc_off;            /* MODE_PRIV: per-thread row counts [gcap][NT] u32, sums [gcap][nslots][NT] f64 */
+	JoinTable jt;                         /* joins only */
 };
 
 struct BlockTable {                       /* per-block group table in shared memory */
@@ -122,7 +149,7 @@ __device__ __forceinline__ int find_or_insert(BlockTable *T, const uint64_t *k, 
 }
 
 /* post-action sink shared by the kernel variants */
-template <int MODE>
+template <int MODE, bool JOIN = false>
 struct RowSink {
 	uint32_t keytypes;           /* 2 bits per key: 1 int, 2 float8, 3 string */
 	BlockTable *T;
@@ -139,12 +166,23 @@ struct RowSink {
 	/* MODE_TR */
 	uint32_t sv;                 /* shared address of the warp's transposed values [slot][33] f64 */
 	uint32_t vnull;
+	/* joins: per-match segment */
+	bool jq;                     /* did the join qual pass for this match */
+	bool nullext;                /* this lane emits its null-extended row (LEFT / ANTI): the join qual does not apply */
+	bool suppress;               /* ANTI probing a match: evaluate the join qual, emit nothing */
 
 	__device__ __forceinline__ void begin_row()
 	{
 		k0 = k1 = k2 = k3 = 0; knull = 0; gid = -1; vnull = 0;
 	}
 	__device__ __forceinline__ bool filter(bool pass) { return pass; }
+	/* the join qual, in the per-match segment of a join pipeline (ExecHashJoin_guts, nodeHashjoin.c:330-420) */
+	__device__ __forceinline__ bool filter_match(bool pass)
+	{
+		if (nullext) return true;
+		jq = pass;
+		return pass && !suppress;
+	}
 	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
 	{
 		if (isnull) { knull |= 1u << kc; return; }
@@ -153,6 +191,7 @@ struct RowSink {
 	}
 	__device__ __forceinline__ bool group(bool live)
 	{
+		if (JOIN && suppress) live = false;
 		if (nkeys == 0) gid = live ? 0 : -1;
 		else
 		{
@@ -186,6 +225,65 @@ struct RowSink {
 	}
 };
 
+/* the per-match segment of a join pipeline: FILTER there is the join qual */
+template <class S>
+struct MatchSink {
+	S &s;
+	__device__ __forceinline__ bool filter(bool pass) { return s.filter_match(pass); }
+	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull) { s.key(kc, v, isnull); }
+	__device__ __forceinline__ bool group(bool live) { return s.group(live); }
+	__device__ __forceinline__ void out(int slot, double v, bool isnull) { s.out(slot, v, isnull); }
+};
+
+/* Hash node (MultiExecHash -> ExecHashTableInsert, nodeHash.c:88-176,906): KEY = join key, GROUP = claim a slot
+ * once the keys are known, OUT = payload column.  A row with a NULL join key is never inserted: it cannot
+ * match a strict equality operator (nodeHash.c:1070-1077). */
+struct BuildSink {
+	JoinTable jt;
+	uint64_t k0, k1;
+	uint32_t knull;
+	unsigned long long *e;
+	unsigned long long npassed;
+	uint32_t *err;
+	bool nonfinite;
+	int gid;
+	uint32_t vnull;
+	__device__ __forceinline__ void begin_row() { k0 = k1 = 0; knull = 0; e = nullptr; }
+	__device__ __forceinline__ bool filter(bool pass) { return pass; }
+	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
+	{
+		if (isnull) { knull |= 1u << kc; return; }
+		v = normalize_key(v, (int) ((jt.keytypes >> (2 * kc)) & 3));
+		if (kc == 0) k0 = v; else k1 = v;
+	}
+	__device__ __forceinline__ bool group(bool live)
+	{
+		if (!live || knull) return false;
+		const uint64_t h = join_hash(k0, k1);
+		const unsigned long long hdr = GG_HT_OCCUPIED | (uint32_t) h;
+		uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
+		for (uint32_t tries = 0; tries <= jt.mask; tries++)
+		{
+			unsigned long long *c = jt.ent + (size_t) slot * jt.stride;
+			if (atomicCAS(c, 0ull, hdr) == 0ull) { e = c; break; }
+			slot = (slot + 1) & jt.mask;
+		}
+		if (!e) { *err |= GGP_EF_TABLE_FULL; return false; }
+		e[1] = k0;
+		if (jt.nkeys > 1) e[2] = k1;
+		npassed++;
+		return true;
+	}
+	__device__ __forceinline__ void out(int slot, double v, bool isnull)
+	{
+		if (!e) return;
+		if (isnull) atomicOr(e, 1ull << (32 + slot));
+		else e[1 + jt.nkeys + slot] = (unsigned long long) __double_as_longlong(v);
+	}
+};
+template <int MODE, bool JOIN> struct SinkSel { typedef RowSink<MODE, JOIN> type; };
+template <bool JOIN> struct SinkSel<MODE_BUILD, JOIN> { typedef BuildSink type; };
+
 /* How the kernel reaches the plan.  DynPlan interprets the program table it receives as a kernel
  * parameter; a plan-specialised translation unit (gg_jit.cpp) defines a StaticPlan whose run()/walk()
  * are the same exec_op()/walk_step() calls with literal arguments, so they fold at compile time. */
@@ -203,6 +301,11 @@ struct DynPlan {
 	{
 		run_prog<NULLABLE, false>(X, live, err, sink);
 	}
+	template <bool NULLABLE, class Sink>
+	__device__ static __forceinline__ void run_range(const EvalCtx &X, MachState &M, int pc0, int pc1, uint32_t &err, Sink &sink)
+	{
+		ggd::run_range<NULLABLE, true>(X, M, pc0, pc1, err, sink);
+	}
 	__device__ static __forceinline__ void walk(const ggp_program &P, uint32_t tup, uint32_t tuplen, bool fast,
 	                                            uint32_t offs, int lane, TupleView &tv, uint32_t &err)
 	{
@@ -210,10 +313,11 @@ struct DynPlan {
 	}
 };
 
-template <int MODE, class PL>
+template <int MODE, class PL, bool JOIN = false>
 __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAggParams &prm)
 {
-	constexpr bool NULLABLE = (MODE == MODE_TRN);
+	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD);
+	constexpr bool TRMODE = (MODE == MODE_TR || MODE == MODE_TRN);
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int nstage = prm.nstage;
 	const int ncons = (blockDim.x >> 5) - 1;          /* consumer warps; the last warp is the producer */
@@ -262,10 +366,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	const uint32_t npages = (uint32_t) (first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0);
 
 	/* MODE_TR accumulators: round r of this lane owns pair p = r*32+lane -> (g = p / V, slot = p % V) */
-	double acc_sum[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	uint32_t acc_cnt[MODE == MODE_PRIV ? 1 : GG_NROUNDS], acc_n[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	int pair_g[MODE == MODE_PRIV ? 1 : GG_NROUNDS], pair_j[MODE == MODE_PRIV ? 1 : GG_NROUNDS], pair_kind[MODE == MODE_PRIV ? 1 : GG_NROUNDS];
-	if (MODE != MODE_PRIV)
+	double acc_sum[TRMODE ? GG_NROUNDS : 1];
+	uint32_t acc_cnt[TRMODE ? GG_NROUNDS : 1], acc_n[TRMODE ? GG_NROUNDS : 1];
+	int pair_g[TRMODE ? GG_NROUNDS : 1], pair_j[TRMODE ? GG_NROUNDS : 1], pair_kind[TRMODE ? GG_NROUNDS : 1];
+	if (TRMODE)
 	{
 #pragma unroll
 		for (int r = 0; r < GG_NROUNDS; r++)
@@ -308,17 +412,23 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		const uint32_t snull = sg + 128;                                           /* TR: [32] u32 bit s: value slot s is NULL */
 
 		EvalCtx X;
-		X.P = &P; X.offs = offs; X.ioffs = 0; X.ifast = false; X.lane = lane;
-		X.itv.tp = 0; X.itv.colnull = 0;
-		RowSink<MODE> sink;
-		sink.keytypes = PL::keytypes(P); sink.T = T; sink.nkeys = nkeys; sink.gcap = gcap; sink.lane = lane; sink.err = &err;
-		sink.npassed = 0; sink.nonfinite = false;
-		sink.acc_thread = smem_base + prm.acc_off + threadIdx.x * 8;
-		sink.cnt_thread = smem_base + prm.cnt_off + threadIdx.x * 4;
-		sink.sstride = (uint32_t) NT * 8;
-		sink.gstride = (uint32_t) nslots * NT * 8;
-		sink.cstride = (uint32_t) NT * 4;
-		sink.sv = sv;
+		X.P = &P; X.offs = offs; X.lane = lane;
+		X.ipay = (const uint64_t *) prm.jt.ent; X.ipaynull = 0;
+		typename SinkSel<MODE, JOIN>::type sink;
+		sink.err = &err; sink.npassed = 0; sink.nonfinite = false; sink.gid = -1; sink.vnull = 0;
+		if constexpr (MODE == MODE_BUILD)
+			sink.jt = prm.jt;
+		else
+		{
+			sink.keytypes = PL::keytypes(P); sink.T = T; sink.nkeys = nkeys; sink.gcap = gcap; sink.lane = lane;
+			sink.acc_thread = smem_base + prm.acc_off + threadIdx.x * 8;
+			sink.cnt_thread = smem_base + prm.cnt_off + threadIdx.x * 4;
+			sink.sstride = (uint32_t) NT * 8;
+			sink.gstride = (uint32_t) nslots * NT * 8;
+			sink.cstride = (uint32_t) NT * 4;
+			sink.sv = sv;
+			sink.jq = false; sink.nullext = false; sink.suppress = false;
+		}
 
 		int s = 0, rot = warp;                    /* rot = (warp + it) mod ncons: rotates which warp takes chunk 0 */
 		uint32_t ph = 0;
@@ -400,11 +510,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				/* X.fast must be warp-uniform only in the sense that every lane reads valid memory:
 				 * a dead lane with fast=false reads offset 0 of the page, which is always mapped */
 
-				sink.begin_row();
-				PL::template run<NULLABLE>(X, live, err, sink);
-
-				if (MODE != MODE_PRIV)
+				/* ---- lane-owns-(group, slot) accumulate of the 32 rows the warp just evaluated ---- */
+				auto tr_accumulate = [&]()
 				{
+
 					sts32(sg + lane * 4, (uint32_t) sink.gid);
 					if (NULLABLE) sts32(snull + lane * 4, sink.vnull);
 					__syncwarp();
@@ -444,6 +553,72 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 						}
 					}
 					__syncwarp();
+				
+				};
+
+				sink.begin_row();
+				if constexpr (!JOIN)
+				{
+					PL::template run<NULLABLE>(X, live, err, sink);
+					if constexpr (TRMODE) tr_accumulate();
+				}
+				else
+				{
+					/* ExecHashJoin_guts (nodeHashjoin.c:78-509): HJ_NEED_NEW_OUTER = the first program piece (outer
+					 * qual + join keys); HJ_SCAN_BUCKET = the probe loop; every match runs the second piece (join
+					 * qual, grouping keys, aggregate arguments) with the matched entry's payload as inner columns;
+					 * HJ_FILL_OUTER_TUPLE = the null-extended run for LEFT / ANTI */
+					const JoinTable &jt = prm.jt;
+					const bool fill_outer = jt.jointype == GG_JOIN_LEFT || jt.jointype == GG_JOIN_ANTI;
+					const bool single = jt.jointype == GG_JOIN_SEMI || jt.jointype == GG_JOIN_ANTI;
+					MachState M1;
+					M1.reset(live);
+					const uint32_t gkt = sink.keytypes;
+					sink.keytypes = jt.keytypes;
+					PL::template run_range<NULLABLE>(X, M1, 0, jt.probe_pc, err, sink);
+					sink.keytypes = gkt;
+					const uint64_t jk0 = sink.k0, jk1 = sink.k1;
+					const bool jknull = sink.knull != 0;
+					bool pending = M1.live && (fill_outer || !jknull);     /* a NULL key matches nothing (nodeHash.c:1070) */
+					bool probing = pending && !jknull;
+					bool matched = false;
+					const uint64_t h = join_hash(jk0, jk1);
+					uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
+					for (;;)
+					{
+						bool have = false;
+						unsigned long long hdr = 0;
+						const unsigned long long *e = jt.ent;
+						if (probing)
+						{
+							for (;;)
+							{
+								e = jt.ent + (size_t) slot * jt.stride;
+								hdr = __ldg(e);
+								slot = (slot + 1) & jt.mask;
+								if (hdr == 0) { probing = false; break; }
+								if ((uint32_t) hdr == (uint32_t) h && __ldg(e + 1) == jk0 && (jt.nkeys < 2 || __ldg(e + 2) == jk1)) { have = true; break; }
+							}
+						}
+						bool nullext = false;
+						if (pending && !probing && !have) { nullext = fill_outer && !matched; pending = false; }
+						if (!__any_sync(GG_FULL_MASK, have || nullext)) break;
+
+						MachState M2 = M1;
+						M2.live = have || nullext;
+						X.ipay = (const uint64_t *) (e + 1 + jt.nkeys);
+						X.ipaynull = nullext ? 0xFFFFFFFFu : (uint32_t) (hdr >> 32) & 0xFFu;
+						sink.begin_row();
+						sink.jq = have; sink.nullext = nullext; sink.suppress = have && jt.jointype == GG_JOIN_ANTI;
+						MatchSink<decltype(sink)> ms = { sink };
+						PL::template run_range<NULLABLE>(X, M2, jt.probe_pc, GGP_MAX_CODE, err, ms);
+						if (have && sink.jq)
+						{
+							matched = true;
+							if (single) { probing = false; pending = false; }
+						}
+						if constexpr (TRMODE) tr_accumulate();
+					}
 				}
 			}
 			__syncwarp();
@@ -471,6 +646,12 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			if (n_passed) atomicAdd(&prm.counters[1], n_passed);
 			if (err) atomicOr(prm.errflags, err);
 		}
+	}
+	if constexpr (MODE == MODE_BUILD)
+	{
+		/* n_passed was folded across the warp above */
+		if (warp < ncons && lane == 0 && n_passed) atomicAdd(prm.jt.nbuilt, n_passed);
+		return;
 	}
 	const int G = T->n;
 	ggp_grec *out = prm.block_recs + (size_t) blockIdx.x * GGP_FAST_GROUPS;

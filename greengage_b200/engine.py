@@ -133,6 +133,48 @@ class ScanAgg:
             self.h = C.c_void_p()
 
 
+class JoinAgg:
+    """SeqScan(outer) ⋈ Hash(SeqScan(inner)) -> Agg pipeline (gg_joinagg)."""
+
+    def __init__(self, eng, outer, inner, hj, agg, pool):
+        self.eng = eng
+        self.h = C.c_void_p()
+        check(dev_lib().gg_joinagg_create(eng.h, C.byref(outer), C.byref(inner), C.byref(hj), C.byref(agg), C.byref(pool),
+                                          C.byref(self.h)))
+
+    def build(self, rel, first_block=0, nblocks=None):
+        nblocks = rel.nblocks - first_block if nblocks is None else nblocks
+        check(dev_lib().gg_joinagg_build(self.h, rel.h, first_block, nblocks))
+
+    def probe(self, rel, first_block=0, nblocks=None):
+        nblocks = rel.nblocks - first_block if nblocks is None else nblocks
+        check(dev_lib().gg_joinagg_probe(self.h, rel.h, first_block, nblocks))
+
+    def probe_host(self, host_ptr, nblocks):
+        check(dev_lib().gg_joinagg_probe_host(self.h, C.c_void_p(host_ptr), nblocks))
+
+    def reset(self):
+        check(dev_lib().gg_joinagg_reset(self.h))
+
+    def fetch(self, cap=4096):
+        out = (capi.gg_aggrow * cap)()
+        n = C.c_int(0)
+        nj = C.c_uint64(0)
+        check(dev_lib().gg_joinagg_fetch(self.h, out, cap, C.byref(n), C.byref(nj)))
+        return [out[i] for i in range(n.value)], nj.value
+
+    def stats(self):
+        rb, tb = C.c_uint64(0), C.c_uint64(0)
+        bms, pms = C.c_float(0), C.c_float(0)
+        check(dev_lib().gg_joinagg_stats(self.h, C.byref(rb), C.byref(tb), C.byref(bms), C.byref(pms)))
+        return {"rows_built": rb.value, "table_bytes": tb.value, "build_ms": bms.value, "probe_ms": pms.value}
+
+    def free(self):
+        if self.h:
+            dev_lib().gg_joinagg_free(self.h)
+            self.h = C.c_void_p()
+
+
 def agg_final(eng, agg, rows, cap=4096):
     arr = (capi.gg_aggrow * max(len(rows), 1))()
     for i, r in enumerate(rows):

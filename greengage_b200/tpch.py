@@ -65,6 +65,45 @@ def count_star_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL):
     return scan, agg, p.pool
 
 
+ORDERS_COLS = dict(orderkey=1, custkey=2, orderstatus=3, totalprice=4, orderdate=5, orderpriority=6, clerk=7,
+                   shippriority=8, comment=9)
+D_1995_03_15 = -1753
+
+
+def join_plan(table=capi.TAB_LINEITEM_NARROW, kind="count", jointype=capi.JOIN_INNER, li_desc=None, ord_desc=None):
+    """lineitem ⋈ orders on l_orderkey = o_orderkey (BASELINE config 2), Agg on top.
+    kind "count":  SELECT count(*)
+    kind "q3ish":  SELECT o_orderstatus, count(*), sum(l_extendedprice * (1 - l_discount)), min(o_orderdate)
+                   WHERE o_orderdate < date '1995-03-15' AND l_shipdate > o_orderdate  (join qual)  GROUP BY o_orderstatus
+    Var numbering: varno 0 = outer (lineitem, the probe side), varno 1 = inner (orders, hashed)."""
+    cols = LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS
+    li_desc = li_desc or capi.synth_tupdesc(table)
+    ord_desc = ord_desc or capi.synth_tupdesc(capi.TAB_ORDERS)
+    p = ExprPool()
+    lkey = p.var(cols["orderkey"], capi.INT8OID, varno=0)
+    okey = p.var(ORDERS_COLS["orderkey"], capi.INT8OID, varno=1)
+    if kind == "count":
+        outer = capi.make_scan(li_desc, -1)
+        inner = capi.make_scan(ord_desc, -1)
+        hj = capi.make_hashjoin(jointype, [lkey], [okey])
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(AGG_COUNT_STAR, -1)])
+        return outer, inner, hj, agg, p.pool
+    odate = p.var(ORDERS_COLS["orderdate"], DATEOID, varno=1)
+    ostatus = p.var(ORDERS_COLS["orderstatus"], BPCHAROID, varno=1)
+    price = p.var(cols["extendedprice"], FLOAT8OID, varno=0)
+    disc = p.var(cols["discount"], FLOAT8OID, varno=0)
+    shipdate = p.var(cols["shipdate"], DATEOID, varno=0)
+    iqual = p.func(capi.F_DATE_LT, BOOLOID, odate, p.const(DATEOID, D_1995_03_15))
+    jqual = p.func(capi.F_DATE_GT, BOOLOID, shipdate, odate)
+    one = p.const(FLOAT8OID, 1.0)
+    rev = p.func(capi.F_FLOAT8MUL, FLOAT8OID, price, p.func(capi.F_FLOAT8MI, FLOAT8OID, one, disc))
+    outer = capi.make_scan(li_desc, -1)
+    inner = capi.make_scan(ord_desc, iqual)
+    hj = capi.make_hashjoin(jointype, [lkey], [okey], jqual)
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [ostatus], [(AGG_COUNT_STAR, -1), (AGG_SUM_FLOAT8, rev), (capi.AGG_MIN_DATE, odate)])
+    return outer, inner, hj, agg, p.pool
+
+
 def synth_spec(table, ncand, seed=42, nsegs=1, seg=0, policy=capi.DIST_RANDOM, norders=None):
     s = capi.gg_synth_spec()
     s.table, s.policy, s.seed, s.ncand = table, policy, seed, ncand

@@ -122,7 +122,10 @@ int  gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner,
                        const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out);
 int  gg_joinagg_build(gg_joinagg *p, gg_relation *inner, uint64_t first_block, uint64_t nblocks);
 int  gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, uint64_t nblocks);
+int  gg_joinagg_probe_host(gg_joinagg *p, const void *host_pages, uint64_t nblocks);   /* outer pages in host memory, streamed */
 int  gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined);
+int  gg_joinagg_reset(gg_joinagg *p);      /* ExecReScanHashJoin with the hash table kept (nodeHashjoin.c:1015-1050) */
+int  gg_joinagg_stats(gg_joinagg *p, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms);
 void gg_joinagg_free(gg_joinagg *p);
 
 /* ---- Sort ----

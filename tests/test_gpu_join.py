@@ -1,0 +1,103 @@
+"""GPU parity tests for SeqScan ⋈ Hash(SeqScan) -> Agg through the C-ABI (gg_joinagg_*), against the oracle's
+Hash / HashJoin restatement (oracle/or_join.c; pinned by tests/test_oracle_join.py).
+Bar: joined-row counts, keys and integer aggregates bit-exact; float8 sums within 1e-6 relative."""
+import numpy as np
+import pytest
+
+from _util import assert_aggrows_match
+from greengage_b200 import capi, tpch
+from oracle import pyoracle as po
+from test_oracle_join import join_nodes, small_relations
+
+pytestmark = pytest.mark.gpu
+
+JOINTYPES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from greengage_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def gpu_joinagg(eng, outer, inner, hj, agg, pool, opages, ipages, host=False, twice=False):
+    from greengage_b200.engine import JoinAgg, Relation
+    ja = JoinAgg(eng, outer, inner, hj, agg, pool)
+    orel = Relation(eng, host_pages=opages) if opages.size else Relation(eng, nblocks=0)
+    irel = Relation(eng, host_pages=ipages) if ipages.size else Relation(eng, nblocks=0)
+    try:
+        ja.build(irel)
+        if host:
+            ja.probe_host(opages.ctypes.data, opages.size // capi.GG_BLCKSZ)
+        else:
+            ja.probe(orel)
+        rows, nj = ja.fetch()
+        if twice:                                   # rescan with the hash table kept
+            ja.reset()
+            ja.probe(orel)
+            rows2, nj2 = ja.fetch()
+            assert nj2 == nj and len(rows2) == len(rows)
+        return rows, nj, ja.stats()
+    finally:
+        ja.free()
+        orel.free()
+        irel.free()
+
+
+@pytest.mark.parametrize("jointype", JOINTYPES)
+@pytest.mark.parametrize("nkeys", [1, 2])
+@pytest.mark.parametrize("with_qual", [False, True])
+def test_small_relations_duplicates_and_nulls(eng, jointype, nkeys, with_qual):
+    odesc, idesc, orows, onulls, irows, inulls, opages, ipages = small_relations()
+    p, outer, inner, hj = join_nodes(odesc, idesc, jointype, nkeys, with_qual)
+    grp = [p.var(2, capi.BPCHAROID, 1)] if jointype in (capi.JOIN_INNER, capi.JOIN_LEFT) else [p.var(2, capi.BPCHAROID, 0)]
+    aggs = [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID, 0))]
+    if jointype in (capi.JOIN_INNER, capi.JOIN_LEFT):
+        aggs += [(capi.AGG_SUM_INT4, p.var(3, capi.INT4OID, 1)), (capi.AGG_COUNT_ANY, p.var(1, capi.INT4OID, 1))]
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, grp, aggs)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, p.pool, opages, ipages)
+    got, nj, st = gpu_joinagg(eng, outer, inner, hj, agg, p.pool, opages, ipages)
+    assert nj == nj_want
+    assert_aggrows_match(got, want, agg)
+
+
+@pytest.mark.parametrize("kind,jointype", [("count", capi.JOIN_INNER), ("q3ish", capi.JOIN_INNER), ("q3ish", capi.JOIN_LEFT),
+                                           ("count", capi.JOIN_ANTI), ("count", capi.JOIN_SEMI)])
+def test_lineitem_orders_synth_vs_oracle(eng, kind, jointype):
+    """BASELINE config 2 shape at a size the oracle finishes in seconds: lineitem ⋈ orders on int64 keys.
+    orders holds fewer rows than lineitem references, so outer rows without a partner exist."""
+    li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 300_000, seed=3, norders=60_000))
+    od, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 45_000, seed=3))
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, kind, jointype)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, pool, li, od)
+    got, nj, st = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od, twice=True)
+    assert st["rows_built"] <= nod
+    assert nj == nj_want and nj > 0
+    assert_aggrows_match(got, want, agg)
+    got_h, nj_h, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od, host=True)
+    assert nj_h == nj_want
+    assert_aggrows_match(got_h, want, agg)
+
+
+def test_empty_sides(eng):
+    li, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 5000, seed=4))
+    od, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 1250, seed=4))
+    empty = np.zeros(0, dtype=np.uint8)
+    for jt in (capi.JOIN_INNER, capi.JOIN_LEFT):
+        outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "count", jt)
+        for op, ip in ((li, empty), (empty, od)):
+            want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, pool, op, ip)
+            got, nj, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, op, ip)
+            assert nj == nj_want
+            assert_aggrows_match(got, want, agg)
+
+
+def test_unsupported_join_shapes_are_refused(eng):
+    from greengage_b200.engine import JoinAgg
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "count")
+    hj.jointype = 2                                   # JOIN_FULL: the CPU node keeps it
+    with pytest.raises(capi.GGError) as e:
+        JoinAgg(eng, outer, inner, hj, agg, pool)
+    assert e.value.code == -6
