@@ -68,7 +68,9 @@ def build_device(verbose=False, force=False):
         objs.append(obj)
     out = os.path.join(HERE, "libggb200.so")
     if force or _newer(out, objs):
-        subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", out] + objs + ["-ldl"])
+        # link to a temporary name and rename: a repo snapshot taken meanwhile never sees a half-written library
+        subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", out + ".tmp"] + objs + ["-ldl"])
+        os.replace(out + ".tmp", out)
     return out
 
 
@@ -77,7 +79,8 @@ def build_host(force=False):
     srcs = [os.path.join(HOST, s) for s in os.listdir(HOST) if s.endswith(".c")]
     if force or _newer(out, srcs + _all_headers()):
         subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-Wall", "-ffp-contract=off", "-pthread", "-shared",
-                               "-o", out] + srcs + ["-lm"])
+                               "-o", out + ".tmp"] + srcs + ["-lm"])
+        os.replace(out + ".tmp", out)
     return out
 
 

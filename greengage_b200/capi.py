@@ -51,7 +51,7 @@ class gg_attr(C.Structure):
 
 
 class gg_tupdesc(C.Structure):
-    _fields_ = [("natts", C.c_int32), ("pad", C.c_int32), ("attrs", gg_attr * GG_MAX_ATTS)]
+    _fields_ = [("natts", C.c_int32), ("format", C.c_int32), ("attrs", gg_attr * GG_MAX_ATTS)]
 
 
 class gg_expr(C.Structure):
@@ -193,6 +193,11 @@ def dev_lib():
         L.gg_joinagg_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.gg_joinagg_free.argtypes = [vp]
         L.gg_joinagg_free.restype = None
+        L.gg_sort_rows.argtypes = [vp, C.POINTER(gg_sortkey), i32, i32, vp, vp, u64, vp]
+        L.gg_sort_device.argtypes = [vp, C.POINTER(gg_sortkey), i32, i32, vp, vp, u64, vp, C.POINTER(i32)]
+        L.gg_relation_attach_rows.argtypes = [vp, vp, u64, i32, C.POINTER(vp)]
+        L.gg_motion_partition.argtypes = [vp, C.POINTER(gg_scan), C.POINTER(gg_exprpool), C.POINTER(C.c_int32), i32,
+                                          C.POINTER(C.c_int32), i32, i32, vp, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         _dev = L
     return _dev
 
@@ -303,6 +308,29 @@ def make_hashjoin(jointype, outerkeys, innerkeys, joinqual=-1):
         h.innerkey[i] = n
     h.joinqual = joinqual
     return h
+
+
+def make_sortkey(col, typid, desc=False, nulls_first=None):
+    """Sort.sortColIdx / sortOperators / nullsFirst; PostgreSQL's default is NULLS LAST for ASC, NULLS FIRST for DESC."""
+    k = gg_sortkey()
+    k.col, k.typid, k.desc = col, typid, int(desc)
+    k.nulls_first = int(desc if nulls_first is None else nulls_first)
+    return k
+
+
+FMT_HEAP, FMT_DATUMROWS = 0, 1
+
+
+def rows_tupdesc(typids, notnull=None):
+    """Descriptor of GG_FMT_DATUMROWS rows (what a receiving Motion delivers): one 64-bit word per column."""
+    d = gg_tupdesc()
+    d.natts = len(typids)
+    d.format = FMT_DATUMROWS
+    for i, t in enumerate(typids):
+        a = d.attrs[i]
+        a.atttypid, a.atttypmod, a.attlen, a.attalign, a.attbyval = t, -1, 8, ord("d"), 1
+        a.attnotnull = int(bool(notnull[i])) if notnull is not None else 0
+    return d
 
 
 def synth_tupdesc(table):

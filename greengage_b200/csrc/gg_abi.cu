@@ -182,6 +182,24 @@ int gg_relation_attach(gg_engine *e, void *device_pages, uint64_t nblocks, gg_re
 	return GG_OK;
 }
 
+/* rows a receiving Motion delivered (GG_FMT_DATUMROWS, gg_plan.h): scanned in 32 KB chunks of whole rows.
+ * The buffer must extend at least 16 bytes past the last row (bulk copies move multiples of 16 bytes). */
+int gg_relation_attach_rows(gg_engine *e, void *device_rows, uint64_t nrows, int ncols, gg_relation **out)
+{
+	if (!e || !out || (!device_rows && nrows) || ncols < 1 || ncols > GG_MAX_ATTS) return GG_ERR_ARG;
+	if (((uintptr_t) device_rows) & 15) { gg_set_error("row buffer must be 16-byte aligned for TMA"); return GG_ERR_ARG; }
+	gg_relation *r = new gg_relation();
+	const uint64_t per_chunk = (GG_BLCKSZ / (8ull * (1 + ncols))) & ~1ull;
+	r->eng = e;
+	r->pages = (uint8_t *) device_rows;
+	r->rowwords = 1 + ncols;
+	r->nrows = nrows;
+	r->nblocks = (nrows + per_chunk - 1) / per_chunk;
+	r->owned = false;
+	*out = r;
+	return GG_OK;
+}
+
 int gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks)
 {
 	if (!r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;

@@ -68,6 +68,21 @@ void init_side(ggp_side *s, const gg_tupdesc *d)
 {
 	memset(s, 0, sizeof *s);
 	s->natts = d->natts;
+	if (d->format == GG_FMT_DATUMROWS)
+	{
+		/* every column is one 64-bit word at a constant offset behind the NULL-mask word */
+		s->rowwords = 1 + d->natts;
+		s->first_walk = d->natts;
+		for (int i = 0; i < d->natts && i < GG_MAX_ATTS; i++)
+		{
+			s->att[i].attlen = 8;
+			s->att[i].attalign = 'd';
+			s->att[i].slot = -1;
+			s->att[i].cacheoff = (int16_t) (8 * i);
+			s->att[i].notnull = d->attrs[i].attnotnull;
+		}
+		return;
+	}
 	for (int i = 0; i < d->natts && i < GG_MAX_ATTS; i++)
 	{
 		s->att[i].attlen = d->attrs[i].attlen;
@@ -111,6 +126,7 @@ int col_slot(Ctx &c, int varno, int attno)
 	if (s->att[a].slot >= 0) return s->att[a].slot;
 	int lt = loadtype_of(d->attrs[a].atttypid);
 	if (!lt) { fail(c, "column %d: type %d not supported on the GPU path", attno, d->attrs[a].atttypid); return 0; }
+	if (d->format == GG_FMT_DATUMROWS) lt = GGP_LT_I8;       /* already in loaded form */
 	if (s->ncols >= GGP_MAX_COLS) { fail(c, "too many referenced columns"); return 0; }
 	int slot = s->ncols++;
 	s->att[a].slot = (int8_t) slot;
@@ -641,6 +657,7 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 static bool check_desc(Ctx &c, const gg_tupdesc *d)
 {
 	if (d->natts < 0 || d->natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return false; }
+	if (d->format == GG_FMT_DATUMROWS) return true;
 	for (int i = 0; i < d->natts; i++)
 	{
 		const gg_attr &a = d->attrs[i];
@@ -758,6 +775,60 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	jp->build.nkeys = hj->nkeys;
 	for (int k = 0; k < hj->nkeys; k++) jp->build.keytype[k] = jp->keytype[k];
 	if (c.failed || b.failed) return GG_ERR_UNSUPPORTED;
+	return GG_OK;
+}
+
+/* Redistribute Motion (nodeMotion.c:1481-1687): which tuples go where, and what travels */
+int ggp_compile_motion(const gg_scan *scan, const gg_exprpool *pool, const int32_t *hashkeys, int nkeys,
+                       const int32_t *payload, int npayload, ggp_program *prog, uint8_t *hashtype,
+                       char *err, int errlen)
+{
+	Ctx c;
+	memset(prog, 0, sizeof *prog);
+	memset(&c, 0, sizeof c);
+	c.pool = pool; c.prog = prog; c.outer = &prog->outer; c.odesc = &scan->desc; c.err = err; c.errlen = errlen;
+	if (err && errlen) err[0] = 0;
+	if (nkeys < 1 || nkeys > GG_MAX_KEYS) { fail(c, "motion with %d hash keys not supported", nkeys); return GG_ERR_UNSUPPORTED; }
+	if (npayload < 1 || npayload > GGP_MAX_ACCS) { fail(c, "motion with %d output columns not supported (1..%d)", npayload, GGP_MAX_ACCS); return GG_ERR_UNSUPPORTED; }
+	if (!check_desc(c, &scan->desc)) return GG_ERR_UNSUPPORTED;
+	init_side(&prog->outer, &scan->desc);
+	if (scan->qual >= 0)
+	{
+		ggp_op *o = gen_value(c, scan->qual);
+		if (!c.failed) o->flags |= GGP_F_FILTER;
+	}
+	for (int k = 0; k < nkeys && !c.failed; k++)
+	{
+		switch (pool->nodes[hashkeys[k]].rettype)
+		{
+			case GG_INT4OID: case GG_DATEOID: hashtype[k] = GGP_HT_INT4; break;
+			case GG_INT8OID: case GG_TIMESTAMPOID: hashtype[k] = GGP_HT_INT8; break;
+			case GG_FLOAT8OID: hashtype[k] = GGP_HT_FLOAT8; break;
+			case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID: hashtype[k] = GGP_HT_STR; break;
+			case GG_BOOLOID: hashtype[k] = GGP_HT_BOOL; break;
+			default: fail(c, "hash key %d: type %d has no GPU hash function", k, pool->nodes[hashkeys[k]].rettype); break;
+		}
+		if (c.failed) break;
+		ggp_op *o = gen_value(c, hashkeys[k]);
+		if (c.failed) break;
+		if (o->flags & GGP_F_KEY) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+		o->flags |= GGP_F_KEY;
+		o->aux = (uint8_t) ((o->aux & 0x3F) | (k << 6));
+		if (k == nkeys - 1) o->flags |= GGP_F_GROUP;
+	}
+	for (int p = 0; p < npayload && !c.failed; p++)
+	{
+		if (!loadtype_of(pool->nodes[payload[p]].rettype)) { fail(c, "output column %d: type %d not supported", p, pool->nodes[payload[p]].rettype); break; }
+		ggp_op *o = gen_value(c, payload[p]);
+		if (c.failed) break;
+		if (o->flags & (GGP_F_OUT | GGP_F_GROUP)) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+		o->flags |= GGP_F_OUT;
+		o->out = (uint8_t) p;
+	}
+	if (!c.failed) emit(c, GGP_END);
+	prog->nkeys = nkeys;
+	prog->nslots = npayload;
+	if (c.failed) return GG_ERR_UNSUPPORTED;
 	return GG_OK;
 }
 

@@ -23,7 +23,9 @@ struct gg_engine {
 struct gg_relation {
 	gg_engine *eng = nullptr;
 	uint8_t *pages = nullptr;
-	uint64_t nblocks = 0;
+	uint64_t nblocks = 0;            /* heap: pages; datum rows: 32 KB chunks of whole rows */
+	int rowwords = 0;                /* 0: heap pages; else GG_FMT_DATUMROWS with this many 64-bit words per row */
+	uint64_t nrows = 0;              /* datum rows only */
 	bool owned = false;
 };
 

@@ -100,6 +100,8 @@ typedef struct ggp_side {
 	int32_t natts_walk;      /* walk attributes [0, natts_walk) : highest referenced attno */
 	int32_t first_walk;      /* first attribute whose offset is not a constant (no-NULL tuples start walking at first_walk-1) */
 	int32_t ncols;
+	int32_t rowwords;        /* 0: heap pages; > 0: datum rows (GG_FMT_DATUMROWS) of this many 64-bit words */
+	int32_t pad;
 	ggp_attr att[GG_MAX_ATTS];
 	uint8_t  coltype[GGP_MAX_COLS];   /* ggp_loadtype per slot */
 	uint8_t  colatt[GGP_MAX_COLS];    /* 0-based attribute per slot */
@@ -167,6 +169,9 @@ typedef struct ggp_grec {
 #define GGP_EF_RECHECK          0x1000  /* a fast variant saw a non-finite sum: replay on the checked variant */
 #define GGP_EF_INFO_MASK        (GGP_EF_SAW_INF | GGP_EF_RECHECK)
 
+/* how a Motion hash key is hashed (cdbhash.c:215-287: the type's default hash opclass function) */
+enum ggp_hashtype { GGP_HT_INT4 = 1, GGP_HT_INT8, GGP_HT_FLOAT8, GGP_HT_STR, GGP_HT_BOOL };
+
 typedef struct ggp_acckinds { uint8_t k[GGP_MAX_ACCS]; } ggp_acckinds;
 
 #if defined(__cplusplus) && !defined(__CUDACC_RTC__)
@@ -177,6 +182,10 @@ struct ggp_aggmap {          /* how each Aggref reads the accumulator columns */
 int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
                         ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen);
 int ggp_disasm(const ggp_program *p, char *buf, int cap);
+/* Redistribute Motion: scan qual FILTER ; hash keys KEY.. GROUP (= route + claim an output row) ; payload OUT.. */
+int ggp_compile_motion(const gg_scan *scan, const gg_exprpool *pool, const int32_t *hashkeys, int nkeys,
+                       const int32_t *payload, int npayload, ggp_program *prog, uint8_t *hashtype /* [GG_MAX_KEYS] */,
+                       char *err, int errlen);
 int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
                      const gg_exprpool *pool, ggp_joinprog *jp, ggp_aggmap *aggmap, char *err, int errlen);
 #endif

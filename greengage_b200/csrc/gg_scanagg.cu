@@ -35,6 +35,13 @@ gg_joinbuild_kernel(const __grid_constant__ ggp_program P, const ScanAggParams p
 	scanagg_body<MODE_BUILD, DynPlan>(P, prm);
 }
 
+/* sending Motion: route every qualifying row and write it into its destination's region */
+__global__ void __launch_bounds__(256, 2)
+gg_motion_part_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
+{
+	scanagg_body<MODE_PART, DynPlan>(P, prm);
+}
+
 /* upper bound on the inner rows = line pointers of the pages (exact for a freshly loaded relation) */
 __global__ void gg_count_lp_kernel(const uint8_t *pages, uint64_t nblocks, unsigned long long *out)
 {
@@ -265,7 +272,7 @@ struct gg_scanagg {
 	unsigned long long *d_counters = nullptr;
 	int nrecs_total = 0, nrecs_cap = 0;
 	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
-	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; };
+	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; };
 	std::vector<Fed> fed;
 	bool has_state = false;
 	/* host staging for the streamed path */
@@ -363,7 +370,7 @@ static int scanagg_configure(gg_scanagg *p)
 	return GG_OK;
 }
 
-static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st)
+static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0)
 {
 	gg_engine *e = p->eng;
 	ScanAggParams prm;
@@ -379,6 +386,8 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	prm.cnt_off = p->cnt_off;
 	prm.acc_off = p->acc_off;
 	prm.jt = p->jt;
+	memset(&prm.mo, 0, sizeof prm.mo);
+	prm.nrows = nrows;
 	if (p->kev_used == p->kev.size())
 	{
 		cudaEvent_t a, b;
@@ -499,12 +508,14 @@ int gg_scanagg_reset(gg_scanagg *p)
 int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t nblocks)
 {
 	if (!p || !r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	if (r->rowwords != p->prog.outer.rowwords) { gg_set_error("relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
+	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	gg_engine *e = p->eng;
 	GG_CUDA(cudaSetDevice(e->device));
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
-	int rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream);
+	int rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream, r->nrows);
 	if (rc) return rc;
-	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks });
+	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
@@ -518,8 +529,9 @@ static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t n
 int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 {
 	if (!p || (!host_pages && nblocks)) return GG_ERR_ARG;
+	if (p->prog.outer.rowwords) { gg_set_error("datum rows are device-resident; the streamed path takes heap pages"); return GG_ERR_ARG; }
 	int rc = scanagg_stream_host(p, host_pages, nblocks);
-	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks });
+	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0 });
 	return rc;
 }
 
@@ -659,7 +671,7 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 		if (rc2) return rc2;
 		for (const auto &f : replay)
 		{
-			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream) : scanagg_stream_host(p, f.host, f.nblocks);
+			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows) : scanagg_stream_host(p, f.host, f.nblocks);
 			if (rc2) return rc2;
 		}
 		p->fed = replay;
@@ -884,6 +896,8 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, uint64_t nblocks)
 {
 	if (!j || !inner || first_block + nblocks > inner->nblocks) return GG_ERR_ARG;
+	if (inner->rowwords != j->jp.build.outer.rowwords) { gg_set_error("inner relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
+	if (inner->rowwords && (first_block != 0 || nblocks != inner->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	gg_engine *e = j->eng;
 	cudaStream_t st = e->stream;
 	GG_CUDA(cudaSetDevice(e->device));
@@ -891,12 +905,15 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
 	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 2 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaEventRecord(j->ev0, st));
-	gg_count_lp_kernel<<<e->sm_count, 256, 0, st>>>(pages, nblocks, j->d_cnt);
-	GG_CUDA(cudaGetLastError());
-	e->launches++;
-	unsigned long long nlp = 0;
-	GG_CUDA(cudaMemcpyAsync(&nlp, j->d_cnt, sizeof nlp, cudaMemcpyDeviceToHost, st));
-	GG_CUDA(cudaStreamSynchronize(st));
+	unsigned long long nlp = inner->nrows;
+	if (!inner->rowwords)
+	{
+		gg_count_lp_kernel<<<e->sm_count, 256, 0, st>>>(pages, nblocks, j->d_cnt);
+		GG_CUDA(cudaGetLastError());
+		e->launches++;
+		GG_CUDA(cudaMemcpyAsync(&nlp, j->d_cnt, sizeof nlp, cudaMemcpyDeviceToHost, st));
+		GG_CUDA(cudaStreamSynchronize(st));
+	}
 	uint64_t slots = 1024;
 	while (slots < 2 * (uint64_t) nlp) slots <<= 1;
 	if (slots > (1ull << 31)) { gg_set_error("inner relation too large for one hash table (%llu rows)", nlp); return GG_ERR_NOMEM; }
@@ -929,6 +946,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	prm.scratch_per_warp = ((j->jp.build.outer.ncols * 64 + 15) & ~15) + 16;
 	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 	prm.jt = jt;
+	prm.nrows = inner->nrows;
 	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
 	gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
 	GG_CUDA(cudaGetLastError());
@@ -976,6 +994,77 @@ int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes,
 	if (build_ms) *build_ms = j->build_ms;
 	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
 	return GG_OK;
+}
+
+/* Redistribute Motion, sending side.  out region d = rows [d * cap, d * cap + counts[d]) with cap = out_cap_rows / nsegs. */
+int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
+                        const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
+                        int nsegs, gg_relation *r, uint64_t first_block, uint64_t nblocks,
+                        void *device_out_rows, uint64_t out_cap_rows,
+                        uint64_t *host_counts, uint64_t *host_offsets)
+{
+	if (!e || !scan || !pool || !hashkeys || !payload || !r || !host_counts || nsegs < 1 || nsegs > 1024 ||
+	    first_block + nblocks > r->nblocks || (!device_out_rows && out_cap_rows))
+		return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(e->device));
+	static ggp_program prog;              /* 3 KB: kept off the stack */
+	uint8_t hashtype[GG_MAX_KEYS] = { 0 };
+	char msg[256];
+	int rc = ggp_compile_motion(scan, pool, hashkeys, nkeys, payload, npayload, &prog, hashtype, msg, sizeof msg);
+	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
+	if (r->rowwords != prog.outer.rowwords) { gg_set_error("relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
+	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
+	cudaStream_t st = e->stream;
+	unsigned long long *d_state = nullptr;          /* [nsegs] cursors, [1] error flags, [2] counters */
+	GG_CUDA(cudaMalloc((void **) &d_state, (size_t) (nsegs + 4) * 8));
+	cudaError_t ce = cudaMemsetAsync(d_state, 0, (size_t) (nsegs + 4) * 8, st);
+	ScanAggParams prm;
+	memset(&prm, 0, sizeof prm);
+	prm.pages = r->pages + first_block * GG_BLCKSZ;
+	prm.nblocks = nblocks;
+	prm.nrows = r->nrows;
+	prm.errflags = (uint32_t *) (d_state + nsegs);
+	prm.counters = d_state + nsegs + 1;
+	prm.nstage = 2;
+	const int ncons = 7;
+	prm.scratch_per_warp = ((prog.outer.ncols * 64 + 15) & ~15) + 16;
+	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
+	prm.mo.rows = (unsigned long long *) device_out_rows;
+	prm.mo.cursor = d_state;
+	prm.mo.cap = (out_cap_rows / (uint64_t) nsegs) & ~1ull;      /* even: every region starts 16-byte aligned */
+	prm.mo.nsegs = nsegs;
+	prm.mo.rowwords = 1 + npayload;
+	for (int k = 0; k < nkeys; k++) prm.mo.hashtypes |= (uint32_t) hashtype[k] << (4 * k);
+	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
+	if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gg_motion_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_start, st);
+	if (ce == cudaSuccess)
+	{
+		gg_motion_part_kernel<<<e->sm_count * 2, 256, smem, st>>>(prog, prm);
+		ce = cudaGetLastError();
+		e->launches++;
+	}
+	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_stop, st);
+	e->timed = true;
+	std::vector<unsigned long long> host((size_t) nsegs + 4);
+	if (ce == cudaSuccess) ce = cudaMemcpyAsync(host.data(), d_state, (size_t) (nsegs + 4) * 8, cudaMemcpyDeviceToHost, st);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+	cudaFree(d_state);
+	if (ce != cudaSuccess) return gg_cuda_fail(ce, "gg_motion_partition");
+	uint32_t flags = (uint32_t) host[(size_t) nsegs];
+	for (int d = 0; d < nsegs; d++)
+	{
+		host_counts[d] = host[(size_t) d] < prm.mo.cap ? host[(size_t) d] : prm.mo.cap;
+		if (host_offsets) host_offsets[d] = (uint64_t) d * prm.mo.cap;
+	}
+	if (flags & GGP_EF_TABLE_FULL)
+	{
+		unsigned long long need = 0;
+		for (int d = 0; d < nsegs; d++) if (host[(size_t) d] > need) need = host[(size_t) d];
+		gg_set_error("motion output region too small: a destination receives %llu rows, capacity %llu", need, (unsigned long long) prm.mo.cap);
+		return GG_ERR_NOMEM;
+	}
+	return gg_errflags_to_code(flags);
 }
 
 void gg_joinagg_free(gg_joinagg *j)

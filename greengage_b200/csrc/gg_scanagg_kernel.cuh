@@ -36,7 +36,18 @@ namespace ggd {
 #define GG_NROUNDS (GGP_MAX_PAIRS / 32)
 
 enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2,
-       MODE_BUILD = 3 };   /* Hash node: scan the inner relation into the join hash table (no aggregation) */
+       MODE_BUILD = 3,     /* Hash node: scan the inner relation into the join hash table (no aggregation) */
+       MODE_PART = 4 };    /* sending Motion: route every row by cdbhash and write it into its destination's region */
+
+/* Redistribute Motion, sending side (nodeMotion.c:1481-1687 + cdbhash.c:173-287): output = nsegs regions of
+ * `cap` datum rows (GG_FMT_DATUMROWS) each; cursor[d] counts the rows claimed for destination d. */
+struct MotionOut {
+	unsigned long long *rows;             /* [nsegs][cap][rowwords] */
+	unsigned long long *cursor;           /* [nsegs] */
+	uint64_t cap;
+	int nsegs, rowwords;
+	uint32_t hashtypes;                   /* 4 bits per hash key: ggp_hashtype */
+};
 
 /* Join hash table (Hash / HashJoin, nodeHash.c:88-176,906-1222): open addressing, linear probing, one
  * slot per inner row (duplicate keys simply occupy successive slots), entries of `stride` 64-bit words:
@@ -75,6 +86,8 @@ struct ScanAggParams {
 	uint32_t scratch_off;                 /* byte offsets from the start of dynamic shared memory */
 	uint32_t cnt_off, acc_off;            /* MODE_PRIV: per-thread row counts [gcap][NT] u32, sums [gcap][nslots][NT] f64 */
 	JoinTable jt;                         /* joins only */
+	MotionOut mo;                         /* MODE_PART only */
+	uint64_t nrows;                       /* datum-row input: total rows (pages/nblocks then describe 32 KB chunks of rows) */
 };
 
 struct BlockTable {                       /* per-block group table in shared memory */
@@ -281,7 +294,65 @@ struct BuildSink {
 		else e[1 + jt.nkeys + slot] = (unsigned long long) __double_as_longlong(v);
 	}
 };
+/* sending Motion: KEY = distribution key (cdbhash), GROUP = route (cdbhashreduce: jump consistent hash) and claim
+ * a row of the destination's region, OUT = column that travels */
+struct PartSink {
+	MotionOut mo;
+	uint32_t h;
+	unsigned long long *row;
+	unsigned long long nullmask;
+	unsigned long long npassed;
+	uint32_t *err;
+	bool nonfinite;
+	int gid, lane;
+	uint32_t vnull;
+	__device__ __forceinline__ void begin_row() { h = 0; row = nullptr; nullmask = 0; }
+	__device__ __forceinline__ bool filter(bool pass) { return pass; }
+	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
+	{
+		uint32_t hk = 0;
+		if (!isnull)
+		{
+			const int t = (int) ((mo.hashtypes >> (4 * kc)) & 15);
+			if (t == GGP_HT_INT4) hk = hash_uint32((uint32_t) v);
+			else if (t == GGP_HT_INT8) hk = hashint8((int64_t) v);
+			else if (t == GGP_HT_FLOAT8) hk = hashfloat8(v);
+			else if (t == GGP_HT_BOOL) hk = hash_uint32((uint32_t) (int32_t) (int8_t) v);
+			else
+			{
+				int len = 0;
+				while (len < 8 && ((v >> (8 * len)) & 0xff)) len++;
+				hk = hash_any_le8(v, len);
+			}
+		}
+		h = cdbhash_add(h, hk, isnull);
+	}
+	__device__ __forceinline__ bool group(bool live)
+	{
+		const int dest = jump_consistent_hash((uint64_t) h, mo.nsegs);
+		/* one atomic per destination present in the warp */
+		const uint32_t peers = __match_any_sync(GG_FULL_MASK, live ? (uint32_t) dest : 0x80000000u + (uint32_t) lane);
+		const int leader = __ffs(peers) - 1;
+		unsigned long long base = 0;
+		if (live && lane == leader) base = atomicAdd(&mo.cursor[dest], (unsigned long long) __popc(peers));
+		base = __shfl_sync(GG_FULL_MASK, base, leader);
+		if (!live) return false;
+		const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+		if (pos >= mo.cap) { *err |= GGP_EF_TABLE_FULL; return false; }
+		row = mo.rows + ((uint64_t) dest * mo.cap + pos) * (uint64_t) mo.rowwords;
+		row[0] = 0;
+		npassed++;
+		return true;
+	}
+	__device__ __forceinline__ void out(int slot, double v, bool isnull)
+	{
+		if (!row) return;
+		if (isnull) { nullmask |= 1ull << slot; row[0] = nullmask; row[1 + slot] = 0; }
+		else row[1 + slot] = (unsigned long long) __double_as_longlong(v);
+	}
+};
 template <int MODE, bool JOIN> struct SinkSel { typedef RowSink<MODE, JOIN> type; };
+template <bool JOIN> struct SinkSel<MODE_PART, JOIN> { typedef PartSink type; };
 template <bool JOIN> struct SinkSel<MODE_BUILD, JOIN> { typedef BuildSink type; };
 
 /* How the kernel reaches the plan.  DynPlan interprets the program table it receives as a kernel
@@ -292,6 +363,7 @@ struct DynPlan {
 	__device__ static __forceinline__ int nslots(const ggp_program &P) { return P.nslots; }
 	__device__ static __forceinline__ int nacc(const ggp_program &P) { return P.nacc; }
 	__device__ static __forceinline__ int ncols(const ggp_program &P) { return P.outer.ncols; }
+	__device__ static __forceinline__ int rowwords(const ggp_program &P) { return P.outer.rowwords; }
 	__device__ static __forceinline__ uint32_t keytypes(const ggp_program &P)
 	{
 		return (uint32_t) P.keytype[0] | ((uint32_t) P.keytype[1] << 2) | ((uint32_t) P.keytype[2] << 4) | ((uint32_t) P.keytype[3] << 6);
@@ -316,7 +388,7 @@ struct DynPlan {
 template <int MODE, class PL, bool JOIN = false>
 __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAggParams &prm)
 {
-	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD);
+	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD || MODE == MODE_PART);
 	constexpr bool TRMODE = (MODE == MODE_TR || MODE == MODE_TRN);
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int nstage = prm.nstage;
@@ -361,6 +433,12 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	}
 	__syncthreads();
 
+	/* input format: heap pages, or 32 KB chunks of fixed-width datum rows (what a receiving Motion delivers) */
+	const uint32_t rowwords = (uint32_t) PL::rowwords(P);
+	const uint32_t rowbytes = rowwords * 8;
+	const uint32_t rows_per_chunk = rowwords ? ((GG_BLCKSZ / rowbytes) & ~1u) : 0;
+	const uint32_t chunk_bytes = rowwords ? rows_per_chunk * rowbytes : GG_BLCKSZ;
+
 	/* pages of this block: blockIdx.x, +gridDim.x, ... */
 	const uint64_t first = blockIdx.x, stride = gridDim.x;
 	const uint32_t npages = (uint32_t) (first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0);
@@ -391,13 +469,17 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		{
 			int s = 0;
 			uint32_t ph = 0;
-			const uint8_t *src = prm.pages + first * (uint64_t) GG_BLCKSZ;
+			const uint8_t *src = prm.pages + first * (uint64_t) chunk_bytes;
 			for (uint32_t it = 0; it < npages; it++)
 			{
 				mbar_wait(empty_bar + s * 8, ph ^ 1, 128);
-				mbar_arrive_expect_tx(full_bar + s * 8, GG_BLCKSZ);
-				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, GG_BLCKSZ, full_bar + s * 8);
-				src += stride * (uint64_t) GG_BLCKSZ;
+				/* datum rows: the last chunk is short; bulk copies move multiples of 16 bytes */
+				uint32_t nbytes = chunk_bytes;
+				if (rowwords && first + (uint64_t) it * stride == prm.nblocks - 1)
+					nbytes = (uint32_t) (((prm.nrows - (prm.nblocks - 1) * (uint64_t) rows_per_chunk) * rowbytes + 15) & ~15ull);
+				mbar_arrive_expect_tx(full_bar + s * 8, nbytes);
+				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, nbytes, full_bar + s * 8);
+				src += stride * (uint64_t) chunk_bytes;
 				if (++s == nstage) { s = 0; ph ^= 1; }
 			}
 		}
@@ -418,6 +500,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		sink.err = &err; sink.npassed = 0; sink.nonfinite = false; sink.gid = -1; sink.vnull = 0;
 		if constexpr (MODE == MODE_BUILD)
 			sink.jt = prm.jt;
+		else if constexpr (MODE == MODE_PART)
+		{
+			sink.mo = prm.mo; sink.lane = lane;
+		}
 		else
 		{
 			sink.keytypes = PL::keytypes(P); sink.T = T; sink.nkeys = nkeys; sink.gcap = gcap; sink.lane = lane;
@@ -442,7 +528,13 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			const uint32_t w2 = lds32(pg + 8), w3 = lds32(pg + 12), w4 = lds32(pg + 16);
 			const uint32_t pd_flags = w2 >> 16, pd_lower = w3 & 0xFFFF, pd_upper = w3 >> 16, pd_special = w4 & 0xFFFF;
 			int nitems = 0;
-			if (pd_lower < GG_PAGE_HEADER_SIZE || pd_lower > pd_upper || pd_upper > pd_special || pd_special > GG_BLCKSZ)
+			if (rowwords)
+			{
+				const uint64_t chunk = first + (uint64_t) it * stride;
+				const uint64_t left = prm.nrows - chunk * rows_per_chunk;
+				nitems = (int) (left < rows_per_chunk ? left : rows_per_chunk);
+			}
+			else if (pd_lower < GG_PAGE_HEADER_SIZE || pd_lower > pd_upper || pd_upper > pd_special || pd_special > GG_BLCKSZ)
 			{
 				/* an all-zero page is a valid empty page (PageIsNew) */
 				if (pd_upper != 0 || pd_lower != 0) err |= GGP_EF_BADPAGE;
@@ -457,6 +549,26 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				const int idx = c * 32 + lane;
 				bool live = false;
 				uint32_t tup = pg, tuplen = 64;
+				if (rowwords)
+				{
+					/* datum row: NULL mask word, then one word per column at constant offsets */
+					live = idx < nitems;
+					const uint32_t rp = pg + (live ? (uint32_t) idx * rowbytes : 0);
+					X.fast = true;
+					X.tv.tp = rp + 8;
+					X.tv.colnull = 0;
+					if (live)
+					{
+						n_scanned++;
+						uint32_t cn = 0;
+						const uint64_t mask = lds64(rp);
+						for (int sl = 0; sl < ncols; sl++) cn |= (uint32_t) ((mask >> P.outer.colatt[sl]) & 1) << sl;
+						X.tv.colnull = cn;
+						if (!NULLABLE && cn) { err |= GGP_EF_NOTNULL_VIOLATED; live = false; }
+					}
+				}
+				else
+				{
 				if (idx < nitems)
 				{
 					/* ItemIdData: lp_off:15 | lp_flags:2 | lp_len:15 (itemid.h:24-29) */
@@ -509,6 +621,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				}
 				/* X.fast must be warp-uniform only in the sense that every lane reads valid memory:
 				 * a dead lane with fast=false reads offset 0 of the page, which is always mapped */
+				}
 
 				/* ---- lane-owns-(group, slot) accumulate of the 32 rows the warp just evaluated ---- */
 				auto tr_accumulate = [&]()
@@ -647,6 +760,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			if (err) atomicOr(prm.errflags, err);
 		}
 	}
+	if constexpr (MODE == MODE_PART) return;
 	if constexpr (MODE == MODE_BUILD)
 	{
 		/* n_passed was folded across the warp above */

@@ -93,6 +93,34 @@ class Relation:
             self.h = C.c_void_p()
 
 
+class RowRelation:
+    """Datum rows (GG_FMT_DATUMROWS) in device memory, scanned like a heap relation (gg_relation_attach_rows)."""
+
+    def __init__(self, eng, device_ptr, nrows, ncols):
+        self.eng = eng
+        self.h = C.c_void_p()
+        self.nrows, self.ncols = nrows, ncols
+        check(dev_lib().gg_relation_attach_rows(eng.h, C.c_void_p(device_ptr), nrows, ncols, C.byref(self.h)))
+        self.nblocks = dev_lib().gg_relation_nblocks(self.h)
+
+    def free(self):
+        if self.h:
+            dev_lib().gg_relation_free(self.h)
+            self.h = C.c_void_p()
+
+
+def motion_partition(eng, scan, pool, hashkeys, payload, nsegs, rel, out_ptr, out_cap_rows, first_block=0, nblocks=None):
+    """Sending side of a Redistribute Motion on the device; returns (counts, offsets) in rows per destination."""
+    nblocks = rel.nblocks - first_block if nblocks is None else nblocks
+    hk = (C.c_int32 * len(hashkeys))(*hashkeys)
+    pl = (C.c_int32 * len(payload))(*payload)
+    counts = (C.c_uint64 * nsegs)()
+    offs = (C.c_uint64 * nsegs)()
+    check(dev_lib().gg_motion_partition(eng.h, C.byref(scan), C.byref(pool), hk, len(hashkeys), pl, len(payload), nsegs,
+                                        rel.h, first_block, nblocks, C.c_void_p(out_ptr), out_cap_rows, counts, offs))
+    return list(counts), list(offs)
+
+
 class ScanAgg:
     """SeqScan -> qual -> Agg pipeline (gg_scanagg)."""
 
@@ -173,6 +201,20 @@ class JoinAgg:
         if self.h:
             dev_lib().gg_joinagg_free(self.h)
             self.h = C.c_void_p()
+
+
+def sort_rows(eng, keys, rows, nulls=None):
+    """Sort n x ncols int64 Datum rows (host numpy) on the device; returns the sorted permutation (uint64)."""
+    import numpy as np
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    n, ncols = rows.shape
+    ka = (capi.gg_sortkey * len(keys))(*keys)
+    perm = np.zeros(n, dtype=np.uint64)
+    if nulls is not None:
+        nulls = np.ascontiguousarray(nulls, dtype=np.uint8)
+    check(dev_lib().gg_sort_rows(eng.h, ka, len(keys), ncols, rows.ctypes.data,
+                                 nulls.ctypes.data if nulls is not None else None, n, perm.ctypes.data))
+    return perm
 
 
 def agg_final(eng, agg, rows, cap=4096):

@@ -21,9 +21,10 @@ LI_WIDE_COLS = dict(orderkey=1, quantity=5, extendedprice=6, discount=7, tax=8, 
 LI_NARROW_COLS = dict(orderkey=1, quantity=2, extendedprice=3, discount=4, tax=5, returnflag=6, linestatus=7, shipdate=8)
 
 
-def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_days=90, desc=None):
-    """Q1: scan + filter + group by (l_returnflag, l_linestatus) + 4 sums, 3 avgs, count(*)."""
-    cols = LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS
+def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_days=90, desc=None, cols=None):
+    """Q1: scan + filter + group by (l_returnflag, l_linestatus) + 4 sums, 3 avgs, count(*).
+    `desc` / `cols` override the relation layout (e.g. datum rows a Motion delivered)."""
+    cols = cols or (LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS)
     desc = desc or capi.synth_tupdesc(table)
     p = ExprPool()
     qty = p.var(cols["quantity"], FLOAT8OID)
@@ -70,26 +71,28 @@ ORDERS_COLS = dict(orderkey=1, custkey=2, orderstatus=3, totalprice=4, orderdate
 D_1995_03_15 = -1753
 
 
-def join_plan(table=capi.TAB_LINEITEM_NARROW, kind="count", jointype=capi.JOIN_INNER, li_desc=None, ord_desc=None):
+def join_plan(table=capi.TAB_LINEITEM_NARROW, kind="count", jointype=capi.JOIN_INNER, li_desc=None, ord_desc=None,
+              li_cols=None, ord_cols=None):
     """lineitem ⋈ orders on l_orderkey = o_orderkey (BASELINE config 2), Agg on top.
     kind "count":  SELECT count(*)
     kind "q3ish":  SELECT o_orderstatus, count(*), sum(l_extendedprice * (1 - l_discount)), min(o_orderdate)
                    WHERE o_orderdate < date '1995-03-15' AND l_shipdate > o_orderdate  (join qual)  GROUP BY o_orderstatus
     Var numbering: varno 0 = outer (lineitem, the probe side), varno 1 = inner (orders, hashed)."""
-    cols = LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS
+    cols = li_cols or (LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS)
+    ocols = ord_cols or ORDERS_COLS
     li_desc = li_desc or capi.synth_tupdesc(table)
     ord_desc = ord_desc or capi.synth_tupdesc(capi.TAB_ORDERS)
     p = ExprPool()
     lkey = p.var(cols["orderkey"], capi.INT8OID, varno=0)
-    okey = p.var(ORDERS_COLS["orderkey"], capi.INT8OID, varno=1)
+    okey = p.var(ocols["orderkey"], capi.INT8OID, varno=1)
     if kind == "count":
         outer = capi.make_scan(li_desc, -1)
         inner = capi.make_scan(ord_desc, -1)
         hj = capi.make_hashjoin(jointype, [lkey], [okey])
         agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(AGG_COUNT_STAR, -1)])
         return outer, inner, hj, agg, p.pool
-    odate = p.var(ORDERS_COLS["orderdate"], DATEOID, varno=1)
-    ostatus = p.var(ORDERS_COLS["orderstatus"], BPCHAROID, varno=1)
+    odate = p.var(ocols["orderdate"], DATEOID, varno=1)
+    ostatus = p.var(ocols["orderstatus"], BPCHAROID, varno=1)
     price = p.var(cols["extendedprice"], FLOAT8OID, varno=0)
     disc = p.var(cols["discount"], FLOAT8OID, varno=0)
     shipdate = p.var(cols["shipdate"], DATEOID, varno=0)

@@ -131,9 +131,19 @@ typedef struct gg_attr {
 	int8_t  pad[3];
 } gg_attr;                  /* 16 bytes */
 
+/* How the tuples of a relation are laid out in device memory.
+ *   GG_FMT_HEAP       32 KB heap pages (bufpage.h / htup_details.h), what SeqScan reads from storage
+ *   GG_FMT_DATUMROWS  fixed-width rows of 64-bit words: word 0 = NULL mask (bit i: column i is NULL), word 1+i =
+ *                     column i as a Datum in loaded form (int4/date sign-extended, float8 bits, short strings
+ *                     packed LSB-first, bpchar blank-stripped).  This is what a receiving Motion hands to the
+ *                     node above it — the device analogue of the MinimalTuples tupser.c serialises
+ *                     (cdbmotion.c:378-470): every operator that scans heap pages also scans these rows. */
+#define GG_FMT_HEAP      0
+#define GG_FMT_DATUMROWS 1
+
 typedef struct gg_tupdesc {
 	int32_t natts;
-	int32_t pad;
+	int32_t format;         /* GG_FMT_* */
 	gg_attr attrs[GG_MAX_ATTS];
 } gg_tupdesc;
 

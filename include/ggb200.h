@@ -47,7 +47,6 @@ typedef struct gg_engine   gg_engine;     /* one GPU segment: device, streams, s
 typedef struct gg_relation gg_relation;   /* heap pages resident in HBM (replaces bufmgr/smgr for the scan) */
 typedef struct gg_scanagg  gg_scanagg;    /* compiled SeqScan -> qual -> Agg pipeline */
 typedef struct gg_joinagg  gg_joinagg;    /* compiled SeqScan ⋈ Hash(SeqScan) -> Agg pipeline */
-typedef struct gg_sorter   gg_sorter;     /* device sort of fixed-width rows */
 
 const char *gg_last_error(void);
 const char *gg_strerror(int code);
@@ -74,6 +73,10 @@ void *gg_engine_stream(gg_engine *e);
 int  gg_relation_create(gg_engine *e, uint64_t nblocks, gg_relation **out);
 /* wrap device memory owned by the caller (e.g. a torch tensor); not freed by gg_relation_free */
 int  gg_relation_attach(gg_engine *e, void *device_pages, uint64_t nblocks, gg_relation **out);
+/* wrap rows a receiving Motion delivered (GG_FMT_DATUMROWS, gg_plan.h): nrows rows of 1 + ncols 64-bit words.  Every
+ * operator that scans heap pages also scans these, given a tuple descriptor with format = GG_FMT_DATUMROWS.  The
+ * buffer must be 16-byte aligned and extend 16 bytes past the last row. */
+int  gg_relation_attach_rows(gg_engine *e, void *device_rows, uint64_t nrows, int ncols, gg_relation **out);
 /* host -> device copy of nblocks pages starting at first_block (async on the engine's copy stream
  * when host_pages is pinned; gg_engine_sync or the next *_run orders it) */
 int  gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks);
@@ -134,12 +137,19 @@ void gg_joinagg_free(gg_joinagg *p);
  * int64 Datum columns in device or host memory; perm receives the sorted order. */
 int  gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols,
                   const int64_t *host_rows, const uint8_t *host_nulls, uint64_t n, uint64_t *host_perm);
+/* the same sort over rows already resident on the device; dev_perm receives n uint32 row numbers,
+ * passes (optional) the number of radix passes executed */
+int  gg_sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const int64_t *dev_rows,
+                    const uint8_t *dev_nulls, uint64_t n, uint32_t *dev_perm, int *passes);
 
 /* ---- Motion ----
- * Redistribute routing (nodeMotion.c:1481-1687, cdbhash.c:191-287) on device:
- * projects the hash-key and payload columns of every qualifying tuple, computes
- * the destination segment bit-exactly, and scatters fixed-width rows into
- * per-destination regions of out_rows.  counts[nsegs] receives rows per destination. */
+ * Sending side of a Redistribute Motion (nodeMotion.c:1481-1687, cdbhash.c:173-287) on the device: evaluates the
+ * scan qual, the hash-key expressions and the expressions that travel for every tuple, computes the destination
+ * segment bit-exactly (cdbhash + jump consistent hash), and writes GG_FMT_DATUMROWS rows of 1 + npayload words into
+ * the destination's region of device_out_rows: region d = rows [d * cap, d * cap + host_counts[d]) with
+ * cap = (out_cap_rows / nsegs) rounded down to even; host_offsets[d] = d * cap.  GG_ERR_NOMEM if a region overflows
+ * (gg_last_error says how many rows the fullest destination receives).  The exchange itself is an all-to-all of the
+ * regions over NCCL (greengage_b200/motion.py); the receiver wraps what it got with gg_relation_attach_rows. */
 int  gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
                          const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
                          int nsegs, gg_relation *r, uint64_t first_block, uint64_t nblocks,

@@ -28,9 +28,7 @@ def test_device_library_exports_every_declared_symbol():
     assert len(decl) > 25
     exp = _exported(os.path.join(ROOT, "greengage_b200", "libggb200.so"))
     missing = [s for s in decl if s not in exp]
-    # entry points of §8 rows scheduled after the scan/agg slice are declared ahead of their kernels
-    planned = {"gg_sort_rows", "gg_motion_partition"}
-    assert [s for s in missing if s not in planned] == [], missing
+    assert missing == [], missing
 
 
 def test_host_library_exports_every_declared_symbol():
