@@ -60,7 +60,7 @@ def test_multi_key_with_nulls_and_specials(eng, desc, nulls_first):
     n = 20_000
     specials = np.array([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1.5, -1.5, 1e-300, -1e300])
     f = np.where(rng.random(n) < 0.3, rng.choice(specials, n), rng.normal(size=n) * 100).astype(np.float64)
-    s = np.array([capi.pack_str("".join(rng.choice(list("ABC "), rng.integers(0, 4))), True) for _ in range(n)], dtype=np.int64)
+    s = np.array([capi.pack_str("".join(rng.choice(list("ABC "), rng.integers(0, 4))), True)[0] for _ in range(n)], dtype=np.int64)
     i4 = rng.integers(-5, 5, n).astype(np.int64)
     d = rng.integers(-40000, 40000, n).astype(np.int64)
     rows = np.stack([i4, f.view(np.int64), s, d], axis=1)
@@ -74,7 +74,7 @@ def test_multi_key_with_nulls_and_specials(eng, desc, nulls_first):
 def test_q1_order_by(eng):
     """ORDER BY l_returnflag, l_linestatus over the four Q1 groups (rpt_tpch.source:307)."""
     from greengage_b200.engine import sort_rows
-    rows = np.array([[capi.pack_str(a), capi.pack_str(b)] for a, b in (("R", "F"), ("N", "O"), ("A", "F"), ("N", "F"))], dtype=np.int64)
+    rows = np.array([[capi.pack_str(a)[0], capi.pack_str(b)[0]] for a, b in (("R", "F"), ("N", "O"), ("A", "F"), ("N", "F"))], dtype=np.int64)
     keys = [capi.make_sortkey(0, capi.BPCHAROID), capi.make_sortkey(1, capi.BPCHAROID)]
     perm = sort_rows(eng, keys, rows)
     assert perm.tolist() == [2, 3, 1, 0]
