@@ -1,7 +1,8 @@
 """In-tree build of the product libraries (no JIT cache: the .so files travel with the repo snapshot).
 
   libggb200.so  hand-written CUDA for sm_100a + the C-ABI (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
-  libgghost.so  host C (gcc): executor-node surface, synthetic loader
+  libgghost.so  host C (gcc): synthetic loader, Motion routing
+  libggexec.so  host C (gcc): the executor-node surface (ExecInitNode/ExecProcNode/ExecEndNode) over libggb200.so
 """
 import os
 import subprocess
@@ -74,9 +75,20 @@ def build_device(verbose=False, force=False):
     return out
 
 
+def build_exec(force=False):
+    """libggexec.so: the executor-node surface (host C) above the C-ABI of libggb200.so"""
+    out = os.path.join(HERE, "libggexec.so")
+    srcs = [os.path.join(HOST, "gg_executor.c"), os.path.join(HOST, "gg_motion_host.c")]
+    if force or _newer(out, srcs + _all_headers() + [os.path.join(HERE, "libggb200.so")]):
+        subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-Wall", "-Wextra", "-std=gnu11", "-shared", "-o", out + ".tmp"] + srcs +
+                              ["-L", HERE, "-lggb200", "-Wl,-rpath,$ORIGIN"])
+        os.replace(out + ".tmp", out)
+    return out
+
+
 def build_host(force=False):
     out = os.path.join(HERE, "libgghost.so")
-    srcs = [os.path.join(HOST, s) for s in os.listdir(HOST) if s.endswith(".c")]
+    srcs = [os.path.join(HOST, s) for s in os.listdir(HOST) if s.endswith(".c") and s != "gg_executor.c"]
     if force or _newer(out, srcs + _all_headers()):
         subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-Wall", "-ffp-contract=off", "-pthread", "-shared",
                                "-o", out + ".tmp"] + srcs + ["-lm"])
@@ -85,7 +97,7 @@ def build_host(force=False):
 
 
 def build_all(verbose=False, force=False):
-    return build_device(verbose, force), build_host(force)
+    return build_device(verbose, force), build_host(force), build_exec(force)
 
 
 if __name__ == "__main__":

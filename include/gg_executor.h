@@ -1,0 +1,147 @@
+/*
+ * gg_executor.h — the executor-node surface of the B200 segment engine (libggexec.so, host C).
+ *
+ * Mirrors what a Greengage QE runs for its slice of a plan:
+ *     ExecInitNode   src/backend/executor/execProcnode.c:255
+ *     ExecProcNode   src/backend/executor/execProcnode.c:925   (one TupleTableSlot per call, NULL = end)
+ *     ExecEndNode    src/backend/executor/execProcnode.c:1315
+ *     ExecReScan     src/backend/executor/execAmi.c:76
+ *     ExecSquelchNode src/backend/executor/execAmi.c:641
+ * with the node types of the accelerated path (plannodes.h): SeqScan, Agg, Hash, HashJoin, Sort, Motion.
+ * Names keep the reference's, prefixed Gg.  The plan tree is what the Postgres-side translator of
+ * INTEGRATION.md §2 builds from the real Plan tree; expressions live in one gg_exprpool.
+ *
+ * What ExecInitNode does differently from the reference: it FUSES the slice into device pipelines
+ *     Agg <- SeqScan                         one scan+aggregate kernel      (gg_scanagg_*)
+ *     Agg <- HashJoin(SeqScan, Hash(SeqScan)) build kernel + probe kernel   (gg_joinagg_*)
+ *     Sort <- any of the above                device radix sort             (gg_sort_rows)
+ *     Motion <- any of the above              rows handed to the transport  (GgMotionTransport)
+ * and returns NULL with GgExecLastError() set when a node or a shape is outside the accelerated subset, so the
+ * caller keeps the CPU nodes for that subtree (there is no CPU implementation behind this API).
+ */
+#ifndef GG_EXECUTOR_H
+#define GG_EXECUTOR_H
+
+#include <stdint.h>
+#include "ggb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum GgNodeTag {            /* nodes/nodes.h NodeTag, the accelerated subset */
+	T_GgSeqScan = 1,
+	T_GgAgg,
+	T_GgHash,
+	T_GgHashJoin,
+	T_GgSort,
+	T_GgMotion
+} GgNodeTag;
+
+typedef enum GgMotionType {         /* plannodes.h MotionType */
+	GG_MOTIONTYPE_GATHER = 0,       /* all segments -> one receiver (MOTIONTYPE_FIXED with one target) */
+	GG_MOTIONTYPE_HASH = 1,         /* Redistribute on hashExprs */
+	GG_MOTIONTYPE_BROADCAST = 2
+} GgMotionType;
+
+#define GG_MAX_SORTKEYS 4
+#define GG_MAX_OUTCOLS (GG_MAX_KEYS + 3 * GG_MAX_AGGS)
+
+/* Plan nodes (plannodes.h Plan and friends) */
+typedef struct GgPlan {
+	GgNodeTag type;
+	struct GgPlan *lefttree;        /* outerPlan */
+	struct GgPlan *righttree;       /* innerPlan */
+	int32_t qual;                   /* implicit-AND qual folded into one expression root, -1 = none */
+} GgPlan;
+
+typedef struct GgSeqScan {
+	GgPlan plan;
+	int32_t scanrelid;              /* index into GgEState.relations */
+	gg_tupdesc desc;
+} GgSeqScan;
+
+typedef struct GgAgg {
+	GgPlan plan;
+	gg_agg agg;                     /* aggstrategy is implied: numCols == 0 plain, else hashed */
+} GgAgg;
+
+typedef struct GgHash {
+	GgPlan plan;                    /* lefttree: the inner SeqScan */
+} GgHash;
+
+typedef struct GgHashJoin {
+	GgPlan plan;                    /* lefttree: outer SeqScan; righttree: Hash */
+	gg_hashjoin hj;
+} GgHashJoin;
+
+typedef struct GgSort {
+	GgPlan plan;
+	int32_t numCols;
+	gg_sortkey keys[GG_MAX_SORTKEYS];   /* col = 0-based output column of the child */
+} GgSort;
+
+typedef struct GgMotion {
+	GgPlan plan;
+	int32_t motionType;             /* GgMotionType */
+	int32_t numHashCols;
+	int32_t hashCol[GG_MAX_KEYS];   /* Redistribute: 0-based output columns of the child that are hashed */
+	int32_t motionID;
+} GgMotion;
+
+/* TupleTableSlot holding a virtual tuple (tuptable.h:117-175): Datums + null flags */
+typedef struct GgTupleTableSlot {
+	int32_t  tts_nvalid;
+	int32_t  tts_isempty;
+	int64_t  tts_values[GG_MAX_OUTCOLS];
+	uint8_t  tts_isnull[GG_MAX_OUTCOLS];
+	int32_t  tts_typid[GG_MAX_OUTCOLS];     /* Datum type per column (what the Motion / Sort above needs) */
+	int32_t  tts_len[GG_MAX_OUTCOLS];       /* byte length for packed strings */
+} GgTupleTableSlot;
+#define GgTupIsNull(slot) ((slot) == NULL || (slot)->tts_isempty)
+
+/* The interconnect behind a Motion node.  exchange() is called once by the sending half with every row this
+ * segment produced, already routed (dest[i] = receiving segment); it returns the rows this segment receives.
+ * greengage_b200/motion.py provides one over torch.distributed (NCCL / gloo); with nsegs == 1 the built-in
+ * loopback is used. */
+typedef struct GgRowBatch {
+	int32_t ncols;
+	int64_t nrows;
+	int64_t *values;                /* [nrows][ncols] */
+	uint8_t *isnull;                /* [nrows][ncols] */
+} GgRowBatch;
+
+typedef struct GgMotionTransport {
+	void *ctx;
+	/* 0 = ok.  `out` is filled with malloc'd arrays the executor frees. */
+	int (*exchange)(void *ctx, int motionID, int motionType, const GgRowBatch *send, const int32_t *dest, GgRowBatch *out);
+} GgMotionTransport;
+
+#define GG_MAX_RELATIONS 16
+
+/* EState (execnodes.h:360): per-query executor state */
+typedef struct GgEState {
+	gg_engine *engine;
+	const gg_exprpool *pool;
+	gg_relation *relations[GG_MAX_RELATIONS];   /* scanrelid -> heap pages resident on the device */
+	int32_t nsegs, segindex;                    /* GpIdentity.numsegments / segindex */
+	GgMotionTransport *transport;               /* NULL: loopback (nsegs must be 1) */
+	uint64_t es_processed;                      /* rows the top node has returned */
+} GgEState;
+
+typedef struct GgPlanState GgPlanState;        /* execnodes.h PlanState */
+
+GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags);
+GgTupleTableSlot *GgExecProcNode(GgPlanState *node);
+void GgExecEndNode(GgPlanState *node);
+int  GgExecReScan(GgPlanState *node);
+void GgExecSquelchNode(GgPlanState *node);
+const char *GgExecLastError(void);
+int  GgExecLastErrorCode(void);                /* GG_ERR_* of the failure, GG_OK if none */
+/* introspection: which device pipeline a state node was fused into ("scanagg", "joinagg", "sort", "motion") */
+const char *GgExecNodeKind(GgPlanState *node);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_EXECUTOR_H */

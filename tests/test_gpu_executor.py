@@ -1,0 +1,111 @@
+"""The executor-node surface end to end on the GPU: plans are built the way the Postgres-side translator builds
+them, run through GgExecInitNode / GgExecProcNode / GgExecEndNode, and checked against the reference's golden Q1
+answer (ORDER BY included) and the oracle."""
+import numpy as np
+import pytest
+
+from _util import assert_aggrows_match, golden, lineitem_fixture_pages
+from greengage_b200 import capi, executor as ex, tpch
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from greengage_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def b2f(v):
+    return np.int64(v).view(np.float64).item()
+
+
+def q1_sorted_plan(b, scan, agg, two_stage):
+    keys = [capi.make_sortkey(0, capi.BPCHAROID), capi.make_sortkey(1, capi.BPCHAROID)]
+    ss = b.seqscan(0, scan.desc, scan.qual)
+    if not two_stage:
+        return b.sort(b.agg(ss, agg), keys)
+    part = capi.gg_agg.from_buffer_copy(bytes(agg))
+    part.aggstage = capi.AGGSTAGE_PARTIAL
+    fin = tpch.q1_final_agg(part)
+    # Gather Motion <- Sort <- Agg(FINAL) <- Redistribute Motion <- Agg(PARTIAL) <- SeqScan   (tpch500GB.out:1771-1782)
+    return b.motion(b.sort(b.agg(b.motion(b.agg(ss, part), ex.MOTION_HASH, [0, 1], 1), fin), keys), ex.MOTION_GATHER, [], 2)
+
+
+@pytest.mark.parametrize("two_stage", [False, True])
+def test_q1_end_to_end_matches_the_reference_answer(eng, two_stage):
+    from greengage_b200.engine import Relation
+    desc, pages, n = lineitem_fixture_pages()
+    exp = golden("q1_expected.json")
+    scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL, interval_days=exp["interval_days"], desc=desc)
+    rel = Relation(eng, host_pages=pages)
+    b = ex.PlanBuilder()
+    x = ex.Executor(eng, pool, [rel], q1_sorted_plan(b, scan, agg, two_stage))
+    try:
+        assert x.kind() == ("motion" if two_stage else "sort")
+        rows = x.rows()
+        want = exp["rows"]
+        assert len(rows) == len(want)
+        for (v, nl, ty, ln), w in zip(rows, want):                 # ORDER BY l_returnflag, l_linestatus
+            assert capi.unpack_str(v[0], ln[0]) == w["returnflag"] and capi.unpack_str(v[1], ln[1]) == w["linestatus"]
+            assert v[9] == w["count_order"]
+            for col, name in ((2, "sum_qty"), (3, "sum_base_price"), (4, "sum_disc_price"), (5, "sum_charge"),
+                              (6, "avg_qty"), (7, "avg_price"), (8, "avg_disc")):
+                assert abs(b2f(v[col]) - float(w[name])) <= 1e-6 * abs(float(w[name])), (name, b2f(v[col]), w[name])
+        assert x.rows() == []                                       # end of stream stays end of stream
+        x.rescan()
+        assert len(x.rows()) == len(want)                           # ExecReScan runs the slice again
+        x.rescan()
+        assert len(x.rows(limit=2)) == 2 and x.rows() == []          # squelched after LIMIT
+    finally:
+        x.end()
+        rel.free()
+
+
+def test_join_through_the_node_surface(eng):
+    from greengage_b200.engine import Relation
+    li, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 100_000, seed=6, norders=20_000))
+    od, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 15_000, seed=6))
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "q3ish", capi.JOIN_INNER)
+    want, _ = po.hashjoin_agg(outer, inner, hj, agg, pool, li, od)
+    lrel, orel = Relation(eng, host_pages=li), Relation(eng, host_pages=od)
+    b = ex.PlanBuilder()
+    plan = b.sort(b.agg(b.hashjoin(b.seqscan(0, outer.desc, outer.qual), b.hash(b.seqscan(1, inner.desc, inner.qual)), hj), agg),
+                  [capi.make_sortkey(0, capi.BPCHAROID, desc=True)])
+    x = ex.Executor(eng, pool, [lrel, orel], plan)
+    try:
+        rows = x.rows()
+        keys = [capi.unpack_str(v[0], ln[0]) for v, nl, ty, ln in rows]
+        assert keys == sorted(keys, reverse=True) and len(rows) == len(want)
+        by = {r.key[0]: r for r in want}
+        for v, nl, ty, ln in rows:
+            w = by[v[0]]
+            assert v[1] == w.agg[0].i and v[3] == w.agg[2].i
+            assert abs(b2f(v[2]) - w.agg[1].f[0]) <= 1e-6 * abs(w.agg[1].f[0])
+    finally:
+        x.end()
+        lrel.free()
+        orel.free()
+
+
+def test_device_errors_surface_through_exec_proc_node(eng):
+    from _util import make_desc
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import Relation
+    desc = make_desc([(capi.FLOAT8OID, 8, "d", 1, 1), (capi.FLOAT8OID, 8, "d", 1, 1)])
+    pages = po.build_pages(desc, [[1.0, 0.0]])
+    p = ExprPool()
+    agg = capi.make_agg(0, [], [(capi.AGG_SUM_FLOAT8, p.func(capi.F_FLOAT8DIV, capi.FLOAT8OID, p.var(1, capi.FLOAT8OID), p.var(2, capi.FLOAT8OID)))])
+    rel = Relation(eng, host_pages=pages)
+    b = ex.PlanBuilder()
+    x = ex.Executor(eng, p.pool, [rel], b.agg(b.seqscan(0, desc), agg))
+    try:
+        with pytest.raises(ex.ExecError) as e:
+            x.rows()
+        assert e.value.code == -4 and "division by zero" in str(e.value)
+    finally:
+        x.end()
+        rel.free()
