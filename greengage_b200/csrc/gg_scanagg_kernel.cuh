@@ -516,9 +516,13 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			sink.jq = false; sink.nullext = false; sink.suppress = false;
 		}
 
-		int s = 0, rot = warp;                    /* rot = (warp + it) mod ncons: rotates which warp takes chunk 0 */
+		/* Chunks (32 line pointers) are dealt round-robin over the consumer warps ACROSS pages: chunk c of this page
+		 * goes to warp (dealt + c) mod ncons, dealt = chunks of all earlier pages.  Consecutive pages therefore land
+		 * on disjoint warp sets, so the pages in flight in the ring are processed concurrently instead of queueing
+		 * behind the same few warps. */
+		int s = 0, dealt = 0;
 		uint32_t ph = 0;
-		for (uint32_t it = 0; it < npages; it++, rot = (rot + 1 == ncons ? 0 : rot + 1))
+		for (uint32_t it = 0; it < npages; it++)
 		{
 			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
 			__syncwarp();
@@ -544,7 +548,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			const bool all_visible = (pd_flags & GG_PD_ALL_VISIBLE) != 0;     /* heapam.c:391 */
 			const int nchunks = (nitems + 31) >> 5;
 
-			for (int c = rot; c < nchunks; c += ncons)
+			int c0 = warp - dealt;
+			if (c0 < 0) c0 += ncons;
+			dealt = (dealt + nchunks) % ncons;
+			for (int c = c0; c < nchunks; c += ncons)
 			{
 				const int idx = c * 32 + lane;
 				bool live = false;
