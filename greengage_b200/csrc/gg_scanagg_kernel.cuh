@@ -550,7 +550,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 
 			int c0 = warp - dealt;
 			if (c0 < 0) c0 += ncons;
-			dealt = (dealt + nchunks) % ncons;
+			dealt += nchunks;
+			while (dealt >= ncons) dealt -= ncons;          /* nchunks <= 37: a handful of subtractions beats a division */
 			for (int c = c0; c < nchunks; c += ncons)
 			{
 				const int idx = c * 32 + lane;
