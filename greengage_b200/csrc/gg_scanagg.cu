@@ -35,6 +35,60 @@ gg_joinbuild_kernel(const __grid_constant__ ggp_program P, const ScanAggParams p
 	scanagg_body<MODE_BUILD, DynPlan>(P, prm);
 }
 
+/* general HashAggregate (any number of groups): scan + probe side variants */
+template <bool JOIN>
+__global__ void __launch_bounds__(256, 2)
+gg_hashagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
+{
+	scanagg_body<MODE_HASH, DynPlan, JOIN>(P, prm);
+}
+
+/* MIN/MAX start from the identity of their comparison; everything else from zero (the table is memset first) */
+__global__ void gg_hashagg_init_kernel(HashAggTable ha)
+{
+	for (int j = 0; j < ha.nacc; j++)
+	{
+		const int kind = ha.acckind[j];
+		unsigned long long init;
+		if (kind == GGP_ACC_F8MIN) init = 0x7ff8000000000000ull;              /* NaN sorts above everything */
+		else if (kind == GGP_ACC_F8MAX) init = 0xfff0000000000000ull;         /* -Infinity */
+		else if (kind == GGP_ACC_I8MIN) init = 0x7fffffffffffffffull;
+		else if (kind == GGP_ACC_I8MAX) init = 0x8000000000000000ull;
+		else continue;
+		unsigned long long *a = (unsigned long long *) (ha.acc + (uint64_t) j * ha.cap);
+		for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < ha.cap; i += (uint64_t) gridDim.x * blockDim.x) a[i] = init;
+	}
+}
+
+/* table -> group records (order unspecified, like a hash aggregate's output) */
+__global__ void gg_hashagg_emit_kernel(HashAggTable ha, ggp_grec *out, unsigned long long outcap, unsigned long long *nout,
+                                       uint32_t *errflags)
+{
+	const bool saw_inf = (*errflags & GGP_EF_SAW_INF) != 0;
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < ha.cap; i += (uint64_t) gridDim.x * blockDim.x)
+	{
+		const unsigned long long h = ha.hdr[i];
+		if (!(h >> 63)) continue;
+		const unsigned long long at = atomicAdd(nout, 1ull);
+		if (at >= outcap) continue;
+		ggp_grec r;
+		memset(&r, 0, sizeof r);
+		for (int c = 0; c < GG_MAX_KEYS; c++) r.key[c] = ha.keys[i * GG_MAX_KEYS + c];
+		r.keynull = (uint32_t) (h >> 32) & 0xF;
+		r.valid = 1;
+		r.count = ha.cnt[i];
+		for (int j = 0; j < ha.nacc; j++)
+		{
+			r.sum[j] = ha.acc[(uint64_t) j * ha.cap + i];
+			r.sumsq[j] = ha.sq ? ha.sq[(uint64_t) j * ha.cap + i] : 0.0;
+			r.n[j] = ha.accn[(uint64_t) j * ha.cap + i];
+			/* float8pl's CHECKFLOATVAL (float.c:782): an infinite sum of finite inputs is an overflow */
+			if (ha.acckind[j] == GGP_ACC_F8SUM && !saw_inf && r.n[j] && !f8_finite(r.sum[j])) atomicOr(errflags, GGP_EF_FLOAT_OVERFLOW);
+		}
+		out[at] = r;
+	}
+}
+
 /* sending Motion: route every qualifying row and write it into its destination's region */
 __global__ void __launch_bounds__(256, 2)
 gg_motion_part_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
@@ -262,6 +316,10 @@ struct gg_scanagg {
 	size_t kev_used = 0;
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
 	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
+	HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */
+	void *ha_mem = nullptr;
+	uint64_t ha_cap = 0;
+	unsigned long long *d_nout64 = nullptr;
 	JoinTable jt = {};
 	size_t smem = 0;
 	/* device state */
@@ -288,7 +346,7 @@ static int scanagg_configure(gg_scanagg *p)
 	const int nslots = p->prog.nslots;
 	const int V = nslots > 0 ? nslots : 1;
 	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
-	if (p->mode != MODE_PRIV) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
+	if (p->mode == MODE_TR || p->mode == MODE_TRN) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
 	p->scratch_per_warp = (scr + 15) & ~15;
 	p->nstage = 3;
 	if (p->mode == MODE_PRIV)
@@ -346,6 +404,13 @@ static int scanagg_configure(gg_scanagg *p)
 		if (p->smem < 32 * 1024) p->smem = 32 * 1024;             /* the epilogue reuses the ring as reduction scratch */
 	}
 	p->grid = e->sm_count * p->ctas_per_sm;
+	if (p->mode == MODE_HASH)
+	{
+		p->jit = nullptr;
+		if (p->is_join) GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+		else GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+		return GG_OK;
+	}
 	if (p->is_join)
 	{
 		p->jit = nullptr;
@@ -370,6 +435,41 @@ static int scanagg_configure(gg_scanagg *p)
 	return GG_OK;
 }
 
+/* (re)allocate and initialise the HBM group table of the general HashAggregate */
+static int hashagg_alloc(gg_scanagg *p, uint64_t cap)
+{
+	cudaStream_t st = p->eng->stream;
+	const ggp_program &P = p->prog;
+	bool anysq = false;
+	for (int j = 0; j < P.nacc; j++) anysq = anysq || P.accsq[j] >= 0;
+	if (p->ha_mem && p->ha_cap != cap) { GG_CUDA(cudaStreamSynchronize(st)); cudaFree(p->ha_mem); p->ha_mem = nullptr; }
+	const size_t words = (size_t) cap * (1 + GG_MAX_KEYS + 1 + (size_t) P.nacc * (2 + (anysq ? 1 : 0)));
+	if (!p->ha_mem)
+	{
+		cudaError_t ce = cudaMalloc(&p->ha_mem, words * 8);
+		if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("group table of %zu bytes does not fit in device memory", words * 8); return GG_ERR_NOMEM; }
+	}
+	p->ha_cap = cap;
+	unsigned long long *w = (unsigned long long *) p->ha_mem;
+	HashAggTable &ha = p->ha;
+	memset(&ha, 0, sizeof ha);
+	ha.cap = cap;
+	ha.hdr = w; w += cap;
+	ha.keys = w; w += cap * GG_MAX_KEYS;
+	ha.cnt = w; w += cap;
+	ha.acc = (double *) w; w += cap * (size_t) P.nacc;
+	ha.accn = w; w += cap * (size_t) P.nacc;
+	ha.sq = anysq ? (double *) w : nullptr;
+	ha.nacc = P.nacc; ha.nkeys = P.nkeys;
+	memcpy(ha.acckind, P.acckind, sizeof ha.acckind);
+	for (int j = 0; j < P.nacc; j++) if (P.accsq[j] >= 0 && P.accsq[j] < GGP_MAX_SLOTS) ha.sqcol[P.accsq[j]] = (uint8_t) j;
+	GG_CUDA(cudaMemsetAsync(p->ha_mem, 0, words * 8, st));
+	gg_hashagg_init_kernel<<<p->eng->sm_count * 4, 256, 0, st>>>(ha);
+	GG_CUDA(cudaGetLastError());
+	p->eng->launches++;
+	return GG_OK;
+}
+
 static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0)
 {
 	gg_engine *e = p->eng;
@@ -388,6 +488,7 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	prm.jt = p->jt;
 	memset(&prm.mo, 0, sizeof prm.mo);
 	prm.nrows = nrows;
+	prm.ha = p->ha;
 	if (p->kev_used == p->kev.size())
 	{
 		cudaEvent_t a, b;
@@ -396,9 +497,20 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 		p->kev.push_back({ a, b });
 	}
 	GG_CUDA(cudaEventRecord(p->kev[p->kev_used].first, st));
+	if (p->is_join && !p->jt.ent) { gg_set_error("probe before build"); return GG_ERR_ARG; }
+	if (p->mode == MODE_HASH)
+	{
+		if (p->is_join) gg_hashagg_kernel<true><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		else gg_hashagg_kernel<false><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		GG_CUDA(cudaGetLastError());
+		GG_CUDA(cudaEventRecord(p->kev[p->kev_used].second, st));
+		p->kev_used++;
+		e->launches++;
+		p->has_state = true;
+		return GG_OK;
+	}
 	if (p->is_join)
 	{
-		if (!p->jt.ent) { gg_set_error("probe before build"); return GG_ERR_ARG; }
 		if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 		else gg_joinprobe_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	}
@@ -449,10 +561,20 @@ static int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 		const char *force = getenv("GGB200_SCAN_MODE");       /* experiments: 0 PRIV, 1 TR, 2 TRN */
 		if (force) { int m = atoi(force); if (m == MODE_PRIV && !p->prog.priv_ok) m = MODE_TR; if (p->prog.nullable) m = MODE_TRN; p->mode = m; }
 	}
+	{
+		const char *force = getenv("GGB200_SCAN_MODE");
+		if (force && atoi(force) == MODE_HASH) p->mode = MODE_HASH;
+	}
 	rc = scanagg_configure(p);
 	if (rc == GG_OK && p->mode == MODE_PRIV && agg->numGroups > p->gcap)
 	{
-		p->mode = MODE_TR;
+		p->mode = p->prog.nullable ? MODE_TRN : MODE_TR;
+		rc = scanagg_configure(p);
+	}
+	if (rc == GG_OK && p->mode != MODE_HASH && agg->numGroups > p->gcap)
+	{
+		/* the planner expects more groups than a block holds on chip: the HBM hash table from the start */
+		p->mode = MODE_HASH;
 		rc = scanagg_configure(p);
 	}
 	if (rc) { delete p; return rc; }
@@ -466,6 +588,7 @@ static int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 	GG_CUDA(cudaMalloc((void **) &p->d_nout, sizeof(int)));
 	GG_CUDA(cudaMalloc((void **) &p->d_err, sizeof(uint32_t)));
 	GG_CUDA(cudaMalloc((void **) &p->d_counters, 2 * sizeof(unsigned long long)));
+	GG_CUDA(cudaMalloc((void **) &p->d_nout64, sizeof(unsigned long long)));
 	*out = p;
 	return gg_scanagg_reset(p);
 }
@@ -502,6 +625,13 @@ int gg_scanagg_reset(gg_scanagg *p)
 	GG_CUDA(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), st));
 	p->has_state = false;
 	p->kev_used = 0;
+	if (p->mode == MODE_HASH)
+	{
+		/* planner's estimate (Agg.numGroups) x 2, at least 64 K slots; a full table is rebuilt larger by fetch */
+		uint64_t cap = p->ha_cap ? p->ha_cap : 65536;
+		while (cap < 2 * (uint64_t) (p->agg.numGroups > 0 ? p->agg.numGroups : 0)) cap <<= 1;
+		return hashagg_alloc(p, cap);
+	}
 	return GG_OK;
 }
 
@@ -656,6 +786,66 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	GG_CUDA(cudaMemcpy(&flags, p->d_err, sizeof flags, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(counters, p->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
 	GG_CUDA(cudaMemcpy(&n, p->d_nout, sizeof n, cudaMemcpyDeviceToHost));
+	if (p->mode == MODE_HASH || ((flags & GGP_EF_GROUP_OVERFLOW) && p->mode != MODE_PRIV))
+	{
+		/* the general HashAggregate.  Reached directly (planner expected many groups), or because a block-table
+		 * variant overflowed, or because this table filled up: then the fed inputs are replayed into a larger one. */
+		const bool grow = p->mode == MODE_HASH && (flags & GGP_EF_TABLE_FULL);
+		if (p->mode != MODE_HASH || grow)
+		{
+			std::vector<gg_scanagg::Fed> replay = p->fed;
+			uint64_t cap = grow ? p->ha_cap * 8 : (p->ha_cap ? p->ha_cap : 1u << 20);
+			if (cap > (1ull << 31)) { gg_set_error("more groups than the device hash aggregate can hold"); return GG_ERR_NOMEM; }
+			p->mode = MODE_HASH;
+			int rc2 = scanagg_configure(p);
+			if (rc2) return rc2;
+			p->ha_cap = cap;
+			if (p->ha_mem) { GG_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(p->ha_mem); p->ha_mem = nullptr; }
+			rc2 = gg_scanagg_reset(p);
+			if (rc2) return rc2;
+			for (const auto &f : replay)
+			{
+				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows) : scanagg_stream_host(p, f.host, f.nblocks);
+				if (rc2) return rc2;
+			}
+			p->fed = replay;
+			return gg_scanagg_fetch(p, out, outcap, nout, rows_scanned, rows_passed);
+		}
+		if (rows_scanned) *rows_scanned = counters[0];
+		if (rows_passed) *rows_passed = counters[1];
+		unsigned long long n64 = 0;
+		const unsigned long long ecap = (unsigned long long) (outcap > 0 ? outcap : 1);
+		ggp_grec *d_recs = nullptr;
+		std::vector<ggp_grec> recs;
+		if (p->has_state)
+		{
+			GG_CUDA(cudaMalloc((void **) &d_recs, sizeof(ggp_grec) * ecap));
+			cudaError_t ce = cudaMemsetAsync(p->d_nout64, 0, sizeof n64, e->stream);
+			if (ce == cudaSuccess)
+			{
+				gg_hashagg_emit_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>(p->ha, d_recs, ecap, p->d_nout64, p->d_err);
+				ce = cudaGetLastError();
+				e->launches++;
+			}
+			if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n64, p->d_nout64, sizeof n64, cudaMemcpyDeviceToHost, e->stream);
+			if (ce == cudaSuccess) ce = cudaMemcpyAsync(&flags, p->d_err, sizeof flags, cudaMemcpyDeviceToHost, e->stream);
+			if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+			if (ce == cudaSuccess && n64 <= ecap && n64 > 0)
+			{
+				recs.resize((size_t) n64);
+				ce = cudaMemcpy(recs.data(), d_recs, sizeof(ggp_grec) * (size_t) n64, cudaMemcpyDeviceToHost);
+			}
+			cudaFree(d_recs);
+			if (ce != cudaSuccess) return gg_cuda_fail(ce, "gg_scanagg_fetch(hash)");
+		}
+		int rc3 = gg_errflags_to_code(flags & ~(uint32_t) GGP_EF_GROUP_OVERFLOW);
+		if (rc3) return rc3;
+		if (n64 > ecap) { gg_set_error("output capacity %d < %llu groups", outcap, n64); return GG_ERR_NOMEM; }
+		if (n64 == 0 && p->agg.numCols == 0) { recs.resize(1); memset(&recs[0], 0, sizeof(ggp_grec)); n64 = 1; }
+		finalize_rows(&p->agg, p->aggmap, &p->prog, 0, recs.data(), (int) n64, out);
+		*nout = (int) n64;
+		return GG_OK;
+	}
 	if ((flags & (GGP_EF_GROUP_OVERFLOW | GGP_EF_RECHECK)) && p->mode == MODE_PRIV)
 	{
 		/* Either more groups than the private-accumulator variant holds (the planner's numGroups was low or
@@ -722,7 +912,7 @@ void gg_scanagg_free(gg_scanagg *p)
 	cudaSetDevice(p->eng->device);
 	cudaStreamSynchronize(p->eng->stream);
 	cudaFree(p->recs); cudaFree(p->merged); cudaFree(p->vidx); cudaFree(p->vmap);
-	cudaFree(p->d_nout); cudaFree(p->d_err); cudaFree(p->d_counters);
+	cudaFree(p->d_nout); cudaFree(p->d_err); cudaFree(p->d_counters); cudaFree(p->d_nout64); cudaFree(p->ha_mem);
 	for (int b = 0; b < 2; b++)
 	{
 		if (p->stage[b]) cudaFree(p->stage[b]);

@@ -37,7 +37,28 @@ namespace ggd {
 
 enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2,
        MODE_BUILD = 3,     /* Hash node: scan the inner relation into the join hash table (no aggregation) */
-       MODE_PART = 4 };    /* sending Motion: route every row by cdbhash and write it into its destination's region */
+       MODE_PART = 4,      /* sending Motion: route every row by cdbhash and write it into its destination's region */
+       MODE_HASH = 5 };    /* HashAggregate with any number of groups: one hash table in HBM, atomics */
+
+/* The general HashAggregate (execHHashagg.c:456 lookup_agg_hash_entry, nodeAgg.c:545 advance_aggregates) for group
+ * counts beyond what a block holds on chip: open addressing in HBM, structure of arrays, capacity a power of two.
+ *   hdr[cap]            0 empty | 1 being written | bit 63 ready, bits 32..35 key-NULL mask, bits 0..31 hash tag
+ *   keys[cap][4]        normalised grouping keys
+ *   cnt[cap]            rows of the group
+ *   acc[nacc][cap]      F8SUM/I8SUM: running sum; MIN/MAX: current extreme (bits)      -> atomicAdd / CAS / atomicMin,Max
+ *   accn[nacc][cap]     non-NULL inputs
+ *   sq[nacc][cap]       float8_accum's sumX2 where the plan ships it
+ * Float sums are accumulated with atomicAdd in arrival order: exact to the last few ulps, not run-to-run identical
+ * (the reference's hash aggregate adds in scan order, also not an order the SQL result depends on). */
+struct HashAggTable {
+	unsigned long long *hdr, *keys, *cnt, *accn;
+	double *acc, *sq;
+	uint64_t cap;                          /* slots; also the stride of the per-column arrays */
+	uint8_t sqcol[GGP_MAX_SLOTS];          /* value slot -> accumulator column whose sum of squares it is (slots >= nacc) */
+	uint8_t acckind[GGP_MAX_ACCS];
+	int nacc, nkeys;
+};
+#define GG_HA_LOCKED 1ull
 
 /* Redistribute Motion, sending side (nodeMotion.c:1481-1687 + cdbhash.c:173-287): output = nsegs regions of
  * `cap` datum rows (GG_FMT_DATUMROWS) each; cursor[d] counts the rows claimed for destination d. */
@@ -87,6 +108,7 @@ struct ScanAggParams {
 	uint32_t cnt_off, acc_off;            /* MODE_PRIV: per-thread row counts [gcap][NT] u32, sums [gcap][nslots][NT] f64 */
 	JoinTable jt;                         /* joins only */
 	MotionOut mo;                         /* MODE_PART only */
+	HashAggTable ha;                      /* MODE_HASH only */
 	uint64_t nrows;                       /* datum-row input: total rows (pages/nblocks then describe 32 KB chunks of rows) */
 };
 
@@ -351,7 +373,105 @@ struct PartSink {
 		else row[1 + slot] = (unsigned long long) __double_as_longlong(v);
 	}
 };
+/* general HashAggregate: KEY = grouping key, GROUP = find or insert the group's slot, OUT = advance one transition value */
+struct HashSink {
+	HashAggTable ha;
+	uint32_t keytypes;
+	uint64_t k0, k1, k2, k3;
+	uint32_t knull;
+	long long e;                 /* slot of this row's group, -1 = none */
+	unsigned long long npassed;
+	uint32_t *err;
+	bool nonfinite, jq, nullext, suppress;
+	int gid, lane;
+	uint32_t vnull;
+	__device__ __forceinline__ void begin_row() { k0 = k1 = k2 = k3 = 0; knull = 0; e = -1; }
+	__device__ __forceinline__ bool filter(bool pass) { return pass; }
+	__device__ __forceinline__ bool filter_match(bool pass)
+	{
+		if (nullext) return true;
+		jq = pass;
+		return pass && !suppress;
+	}
+	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
+	{
+		if (isnull) { knull |= 1u << kc; return; }
+		v = normalize_key(v, (int) ((keytypes >> (2 * kc)) & 3));
+		if (kc == 0) k0 = v; else if (kc == 1) k1 = v; else if (kc == 2) k2 = v; else k3 = v;
+	}
+	__device__ __forceinline__ bool group(bool live)
+	{
+		if (suppress) live = false;
+		if (!live) return false;
+		npassed++;
+		uint64_t h = join_hash(k0 ^ (k2 * 0xD6E8FEB86659FD93ull), k1 ^ (k3 * 0xA0761D6478BD642Full) ^ ((uint64_t) knull << 56));
+		const unsigned long long ready = 0x8000000000000000ull | ((unsigned long long) knull << 32) | (uint32_t) h;
+		uint64_t slot = (h >> 32) & (ha.cap - 1);
+		/* a probe sequence this long means the table is overloaded: report it full so that the host rebuilds it larger */
+		const uint64_t maxtries = ha.cap < 256 ? ha.cap : 256;
+		for (uint64_t tries = 0; tries < maxtries; )
+		{
+			volatile unsigned long long *hp = ha.hdr + slot;
+			unsigned long long cur = *hp;
+			if (cur == 0)
+			{
+				if (atomicCAS(ha.hdr + slot, 0ull, GG_HA_LOCKED) == 0ull)
+				{
+					unsigned long long *kp = ha.keys + slot * GG_MAX_KEYS;
+					kp[0] = k0; kp[1] = k1; kp[2] = k2; kp[3] = k3;
+					__threadfence();
+					*hp = ready;
+					e = (long long) slot;
+					break;
+				}
+				continue;                           /* somebody else took it: look again */
+			}
+			if (cur == GG_HA_LOCKED) continue;        /* being written: look again */
+			if (cur == ready)
+			{
+				const unsigned long long *kp = ha.keys + slot * GG_MAX_KEYS;
+				if (kp[0] == k0 && kp[1] == k1 && kp[2] == k2 && kp[3] == k3) { e = (long long) slot; break; }
+			}
+			slot = (slot + 1) & (ha.cap - 1);
+			tries++;
+		}
+		if (e < 0) { *err |= GGP_EF_TABLE_FULL; return false; }
+		atomicAdd(ha.cnt + e, 1ull);
+		return true;
+	}
+	__device__ __forceinline__ void out(int slot, double v, bool isnull)
+	{
+		if (e < 0 || isnull) return;
+		if (slot >= ha.nacc)
+		{
+			atomicAdd(ha.sq + (uint64_t) ha.sqcol[slot] * ha.cap + (uint64_t) e, v);
+			return;
+		}
+		const uint64_t at = (uint64_t) slot * ha.cap + (uint64_t) e;
+		const int kind = ha.acckind[slot];
+		atomicAdd(ha.accn + at, 1ull);
+		if (kind == GGP_ACC_F8SUM) { if (!f8_finite(v)) nonfinite = true; atomicAdd(ha.acc + at, v); }
+		else if (kind == GGP_ACC_I8SUM) atomicAdd((unsigned long long *) (ha.acc + at), (unsigned long long) __double_as_longlong(v));
+		else if (kind == GGP_ACC_I8MIN) atomicMin((long long *) (ha.acc + at), __double_as_longlong(v));
+		else if (kind == GGP_ACC_I8MAX) atomicMax((long long *) (ha.acc + at), __double_as_longlong(v));
+		else if (kind == GGP_ACC_F8MIN || kind == GGP_ACC_F8MAX)
+		{
+			/* float8smaller / float8larger under float8_cmp_internal's order (NaN largest), float.c:964 */
+			unsigned long long *ap = (unsigned long long *) (ha.acc + at);
+			unsigned long long old = *ap;
+			for (;;)
+			{
+				const int c = f8_cmp(v, __longlong_as_double((long long) old));
+				if (kind == GGP_ACC_F8MIN ? c >= 0 : c <= 0) break;
+				const unsigned long long seen = atomicCAS(ap, old, (unsigned long long) __double_as_longlong(v));
+				if (seen == old) break;
+				old = seen;
+			}
+		}
+	}
+};
 template <int MODE, bool JOIN> struct SinkSel { typedef RowSink<MODE, JOIN> type; };
+template <bool JOIN> struct SinkSel<MODE_HASH, JOIN> { typedef HashSink type; };
 template <bool JOIN> struct SinkSel<MODE_PART, JOIN> { typedef PartSink type; };
 template <bool JOIN> struct SinkSel<MODE_BUILD, JOIN> { typedef BuildSink type; };
 
@@ -388,7 +508,7 @@ struct DynPlan {
 template <int MODE, class PL, bool JOIN = false>
 __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAggParams &prm)
 {
-	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD || MODE == MODE_PART);
+	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD || MODE == MODE_PART || MODE == MODE_HASH);
 	constexpr bool TRMODE = (MODE == MODE_TR || MODE == MODE_TRN);
 	extern __shared__ __align__(128) uint8_t smem[];
 	const int nstage = prm.nstage;
@@ -503,6 +623,11 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		else if constexpr (MODE == MODE_PART)
 		{
 			sink.mo = prm.mo; sink.lane = lane;
+		}
+		else if constexpr (MODE == MODE_HASH)
+		{
+			sink.ha = prm.ha; sink.keytypes = PL::keytypes(P); sink.lane = lane;
+			sink.jq = false; sink.nullext = false; sink.suppress = false;
 		}
 		else
 		{
@@ -768,7 +893,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			if (err) atomicOr(prm.errflags, err);
 		}
 	}
-	if constexpr (MODE == MODE_PART) return;
+	if constexpr (MODE == MODE_PART || MODE == MODE_HASH) return;
 	if constexpr (MODE == MODE_BUILD)
 	{
 		/* n_passed was folded across the warp above */

@@ -81,6 +81,33 @@ def test_lineitem_orders_synth_vs_oracle(eng, kind, jointype):
     assert_aggrows_match(got_h, want, agg)
 
 
+def test_join_with_a_high_cardinality_aggregate(eng):
+    """HashJoin feeding the general HashAggregate: GROUP BY l_orderkey above the join."""
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import JoinAgg, Relation
+    li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 150_000, seed=2, norders=30_000))
+    od, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 24_000, seed=2))
+    c, oc = tpch.LI_NARROW_COLS, tpch.ORDERS_COLS
+    p = ExprPool()
+    lkey, okey = p.var(c["orderkey"], capi.INT8OID, 0), p.var(oc["orderkey"], capi.INT8OID, 1)
+    outer = capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW), -1)
+    inner = capi.make_scan(capi.synth_tupdesc(capi.TAB_ORDERS), -1)
+    hj = capi.make_hashjoin(capi.JOIN_LEFT, [lkey], [okey])
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [lkey], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(c["extendedprice"], capi.FLOAT8OID, 0)),
+                                                      (capi.AGG_MIN_DATE, p.var(oc["orderdate"], capi.DATEOID, 1))], num_groups=30_000)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, p.pool, li, od, cap=100_000)
+    ja = JoinAgg(eng, outer, inner, hj, agg, p.pool)
+    lrel, orel = Relation(eng, host_pages=li), Relation(eng, host_pages=od)
+    try:
+        ja.build(orel)
+        ja.probe(lrel)
+        got, nj = ja.fetch(cap=100_000)
+        assert nj == nj_want and len(got) == len(want) > 20_000
+        assert_aggrows_match(got, want, agg)
+    finally:
+        ja.free(); lrel.free(); orel.free()
+
+
 def test_empty_sides(eng):
     li, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 5000, seed=4))
     od, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 1250, seed=4))

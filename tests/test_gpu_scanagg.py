@@ -235,14 +235,89 @@ def test_more_groups_than_private_accumulators_hold(eng):
     assert_aggrows_match(rows, want, agg)
 
 
-def test_too_many_groups_is_refused_not_wrong(eng):
-    pages, nb, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 50000, seed=5))
-    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
+def _many_groups_plan(table, num_groups):
+    cols = tpch.LI_NARROW_COLS
+    desc = capi.synth_tupdesc(table)
     p = ExprPool()
-    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(3, capi.INT4OID)], [(capi.AGG_COUNT_STAR, -1)])      # l_suppkey: 100 groups
-    with pytest.raises(capi.GGError) as e:
-        gpu_scanagg(eng, capi.make_scan(desc, -1), agg, p.pool, pages)
-    assert e.value.code == -6
+    price = p.var(cols["extendedprice"], capi.FLOAT8OID)
+    agg = capi.make_agg(capi.AGGSTAGE_PARTIAL, [p.var(cols["orderkey"], capi.INT8OID)],
+                        [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, price), (capi.AGG_AVG_FLOAT8, p.var(cols["quantity"], capi.FLOAT8OID)),
+                         (capi.AGG_MIN_DATE, p.var(cols["shipdate"], capi.DATEOID)), (capi.AGG_MAX_FLOAT8, price)], num_groups=num_groups)
+    return capi.make_scan(desc, -1), agg, p
+
+
+@pytest.mark.parametrize("hint", [0, 60_000])
+def test_group_by_with_tens_of_thousands_of_groups(eng, hint):
+    """GROUP BY l_orderkey: the general HashAggregate (HBM hash table).  Without a planner estimate the on-chip
+    variants overflow first and the input is replayed; with one the table is used from the start."""
+    from greengage_b200.engine import Relation, ScanAgg
+    pages, nb, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 200_000, seed=5))
+    scan, agg, p = _many_groups_plan(capi.TAB_LINEITEM_NARROW, hint)
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages, cap=100_000)
+    assert len(want) > 40_000
+    rel = Relation(eng, host_pages=pages)
+    sa = ScanAgg(eng, scan, agg, p.pool)
+    try:
+        half = rel.nblocks // 2
+        sa.run(rel, 0, half)                          # two runs accumulate into the same table
+        sa.run(rel, half, rel.nblocks - half)
+        got, gsc, gps = sa.fetch(cap=100_000)
+        assert sa.variant() == 5
+        assert (gsc, gps) == (sc, ps)
+        assert_aggrows_match(got, want, agg)
+        with pytest.raises(capi.GGError) as e:        # the caller's buffer is too small: said so, not truncated
+            sa.fetch(cap=1000)
+        assert e.value.code == -8
+    finally:
+        sa.free()
+        rel.free()
+
+
+def test_group_table_grows_when_the_estimate_was_low(eng):
+    from greengage_b200.engine import Relation, ScanAgg
+    pages, nb, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 600_000, seed=9, norders=400_000))
+    scan, agg, p = _many_groups_plan(capi.TAB_LINEITEM_NARROW, 100)          # the planner said 100 groups; there are ~300 k
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages, cap=500_000)
+    assert len(want) > 65_536
+    with env(GGB200_SCAN_MODE="5"):
+        sa = ScanAgg(eng, scan, agg, p.pool)
+    rel = Relation(eng, host_pages=pages)
+    try:
+        sa.run(rel)
+        got, gsc, gps = sa.fetch(cap=500_000)
+        assert (gsc, gps) == (sc, ps)
+        assert_aggrows_match(got, want, agg)
+    finally:
+        sa.free()
+        rel.free()
+
+
+def test_nullable_keys_and_int_aggregates_in_the_general_hashagg(eng):
+    rng = np.random.default_rng(3)
+    desc = make_desc([(capi.INT4OID, 4, "i", 1), (capi.BPCHAROID, -1, "i", 0), (capi.FLOAT8OID, 8, "d", 1), (capi.INT4OID, 4, "i", 1)])
+    rows, nulls = [], []
+    for i in range(20_000):
+        rows.append([int(rng.integers(0, 300)), bytes([65 + int(rng.integers(0, 6))]), float(rng.normal()) * 10, int(rng.integers(-9, 9))])
+        nulls.append([rng.random() < 0.05, rng.random() < 0.05, rng.random() < 0.1, rng.random() < 0.1])
+    pages = po.build_pages(desc, rows, nulls)
+    p = ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(1, capi.INT4OID), p.var(2, capi.BPCHAROID)],
+                        [(capi.AGG_COUNT_STAR, -1), (capi.AGG_COUNT_ANY, p.var(3, capi.FLOAT8OID)), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID)),
+                         (capi.AGG_MIN_FLOAT8, p.var(3, capi.FLOAT8OID)), (capi.AGG_SUM_INT4, p.var(4, capi.INT4OID)),
+                         (capi.AGG_MAX_INT4, p.var(4, capi.INT4OID)), (capi.AGG_AVG_FLOAT8, p.var(3, capi.FLOAT8OID))], num_groups=2000)
+    scan = capi.make_scan(desc, -1)
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages, cap=10_000)
+    from greengage_b200.engine import Relation, ScanAgg
+    rel = Relation(eng, host_pages=pages)
+    sa = ScanAgg(eng, scan, agg, p.pool)
+    try:
+        sa.run(rel)
+        got, gsc, gps = sa.fetch(cap=10_000)
+        assert sa.variant() == 5 and len(got) == len(want) > 1500
+        assert_aggrows_match(got, want, agg)
+    finally:
+        sa.free()
+        rel.free()
 
 
 def _f8_relation(values):
