@@ -282,3 +282,19 @@ extern "C" int gg_debug_jit_source(const gg_scan *scan, const gg_agg *agg, const
 	snprintf(buf, (size_t) cap, "%s", s.c_str());
 	return (int) s.size();
 }
+
+/* debugging aid: the plan-specialised sources of a join pipeline (which: 0 build kernel, 1 probe kernel) */
+extern "C" int gg_debug_jit_source_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
+                                        const gg_exprpool *pool, int which, int mode, char *buf, int cap)
+{
+	static ggp_joinprog jp;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	char msg[256];
+	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &jp, aggmap, msg, sizeof msg);
+	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
+	std::string s = which == 0 ? gg_jit_scanagg_source(&jp.build, 3 /* MODE_BUILD */, 256, "_dbg")
+	                           : gg_jit_scanagg_source(&jp.probe, mode, 256, "_dbg", jp.probe_pc);
+	snprintf(buf, (size_t) cap, "%s", s.c_str());
+	return (int) s.size();
+}
+

@@ -321,6 +321,7 @@ struct gg_scanagg {
 	uint64_t ha_cap = 0;
 	unsigned long long *d_nout64 = nullptr;
 	JoinTable jt = {};
+	int join_probe_pc = -1;
 	size_t smem = 0;
 	/* device state */
 	ggp_grec *recs = nullptr;       /* [GG_MERGE_CAP (previous merged)] ++ [grid * GGP_FAST_GROUPS (block records)] */
@@ -404,16 +405,21 @@ static int scanagg_configure(gg_scanagg *p)
 		if (p->smem < 32 * 1024) p->smem = 32 * 1024;             /* the epilogue reuses the ring as reduction scratch */
 	}
 	p->grid = e->sm_count * p->ctas_per_sm;
+	if (p->mode == MODE_HASH || p->is_join)
+	{
+		char jmsg[512];
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, p->is_join ? p->join_probe_pc : -1);
+		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
+		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	}
 	if (p->mode == MODE_HASH)
 	{
-		p->jit = nullptr;
 		if (p->is_join) GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 		else GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 		return GG_OK;
 	}
 	if (p->is_join)
 	{
-		p->jit = nullptr;
 		if (p->mode == MODE_TR)
 			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 		else
@@ -500,7 +506,12 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	if (p->is_join && !p->jt.ent) { gg_set_error("probe before build"); return GG_ERR_ARG; }
 	if (p->mode == MODE_HASH)
 	{
-		if (p->is_join) gg_hashagg_kernel<true><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		if (p->jit)
+		{
+			void *args[] = { (void *) &p->prog, (void *) &prm };
+			GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
+		}
+		else if (p->is_join) gg_hashagg_kernel<true><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 		else gg_hashagg_kernel<false><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 		GG_CUDA(cudaGetLastError());
 		GG_CUDA(cudaEventRecord(p->kev[p->kev_used].second, st));
@@ -509,7 +520,7 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 		p->has_state = true;
 		return GG_OK;
 	}
-	if (p->is_join)
+	if (p->is_join && !p->jit)
 	{
 		if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 		else gg_joinprobe_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
@@ -1070,6 +1081,7 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &j->jp, p->aggmap, msg, sizeof msg);
 	if (rc != GG_OK) { gg_set_error("%s", msg); delete p; delete j; return rc; }
 	p->prog = j->jp.probe;
+	p->join_probe_pc = j->jp.probe_pc;
 	p->prog.nullable = p->prog.nullable || j->jp.build.nullable;     /* a NULL payload column shows up on the probe side */
 	rc = scanagg_finish_create(p, &j->probe);
 	if (rc) { delete j; return rc; }
@@ -1138,7 +1150,18 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	prm.jt = jt;
 	prm.nrows = inner->nrows;
 	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
-	gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
+	{
+		char jmsg[512];
+		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, 256, e->device, jmsg, sizeof jmsg);
+		if (jk)
+		{
+			void *args[] = { (void *) &j->jp.build, (void *) &prm };
+			GG_CUDA(cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st));
+		}
+		else
+			gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
+	}
 	GG_CUDA(cudaGetLastError());
 	e->launches++;
 	GG_CUDA(cudaEventRecord(j->ev1, st));
@@ -1230,8 +1253,19 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_start, st);
 	if (ce == cudaSuccess)
 	{
-		gg_motion_part_kernel<<<e->sm_count * 2, 256, smem, st>>>(prog, prm);
-		ce = cudaGetLastError();
+		char jmsg[512];
+		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, 256, e->device, jmsg, sizeof jmsg);
+		if (jk)
+		{
+			void *args[] = { (void *) &prog, (void *) &prm };
+			ce = cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+			if (ce == cudaSuccess) ce = cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st);
+		}
+		else
+		{
+			gg_motion_part_kernel<<<e->sm_count * 2, 256, smem, st>>>(prog, prm);
+			ce = cudaGetLastError();
+		}
 		e->launches++;
 	}
 	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_stop, st);
