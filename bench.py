@@ -220,9 +220,9 @@ def main():
         """everything above the partial aggregate: Redistribute -> FINAL Agg -> Gather (N > 1)"""
         if world == 1:
             return rows
-        mine = motion.redistribute_aggrows(rows, key_typids, device=torch.device("cuda", local_rank))
+        mine = motion.redistribute_small(rows, key_typids, device=torch.device("cuda", local_rank))
         final_rows = agg_final(eng, fin, mine) if mine else []
-        return motion.gather_aggrows(final_rows, 0, device=torch.device("cuda", local_rank))
+        return motion.gather_small(final_rows, 0, device=torch.device("cuda", local_rank))
 
     scan_ms_tot, scan_launches = 0.0, 0
 

@@ -103,6 +103,7 @@ void gg_engine_free(gg_engine *e)
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
 	cudaStreamSynchronize(e->copy_stream);
+	cudaFree(e->final_scratch);
 	cudaEventDestroy(e->ev_start);
 	cudaEventDestroy(e->ev_stop);
 	cudaStreamDestroy(e->stream);

@@ -18,6 +18,8 @@ struct gg_engine {
 	cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      /* gg_engine_timer_start/stop */
 	bool timed = false;
 	uint64_t launches = 0;
+	void *final_scratch = nullptr;       /* gg_agg_final: device scratch kept across calls, grown on demand */
+	size_t final_cap = 0;                /* records it holds */
 };
 
 struct gg_relation {

@@ -346,7 +346,7 @@ static int scanagg_configure(gg_scanagg *p)
 	gg_engine *e = p->eng;
 	const int nslots = p->prog.nslots;
 	const int V = nslots > 0 ? nslots : 1;
-	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
+	int scr = (p->prog.outer.ncols * 64 * (p->mode == MODE_PRIV ? 2 : 1) + 15) & ~15;   /* column offsets [ncols][32] u16, per row of the lane */
 	if (p->mode == MODE_TR || p->mode == MODE_TRN) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
 	p->scratch_per_warp = (scr + 15) & ~15;
 	p->nstage = 3;
@@ -1012,18 +1012,24 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 			}
 		}
 	}
-	ggp_grec *d_recs = nullptr, *d_out = nullptr;
-	int *d_vidx = nullptr, *d_vmap = nullptr, *d_n = nullptr;
-	uint32_t *d_err = nullptr;
 	int n = 0;
 	uint32_t flags = 0;
 	const int cap = nin > 0 ? nin : 1;
-	GG_CUDA(cudaMalloc((void **) &d_recs, sizeof(ggp_grec) * cap));
-	GG_CUDA(cudaMalloc((void **) &d_out, sizeof(ggp_grec) * cap));
-	GG_CUDA(cudaMalloc((void **) &d_vidx, sizeof(int) * cap));
-	GG_CUDA(cudaMalloc((void **) &d_vmap, sizeof(int) * cap));
-	GG_CUDA(cudaMalloc((void **) &d_n, sizeof(int)));
-	GG_CUDA(cudaMalloc((void **) &d_err, sizeof(uint32_t)));
+	/* one scratch allocation kept in the engine: [recs cap][out cap][vidx cap][vmap cap][n][err] */
+	if (e->final_cap < (size_t) cap)
+	{
+		size_t want = (size_t) cap < 256 ? 256 : (size_t) cap;
+		cudaFree(e->final_scratch);
+		e->final_scratch = nullptr; e->final_cap = 0;
+		GG_CUDA(cudaMalloc(&e->final_scratch, want * (2 * sizeof(ggp_grec) + 2 * sizeof(int)) + 64));
+		e->final_cap = want;
+	}
+	ggp_grec *d_recs = (ggp_grec *) e->final_scratch;
+	ggp_grec *d_out = d_recs + e->final_cap;
+	int *d_vidx = (int *) (d_out + e->final_cap);
+	int *d_vmap = d_vidx + e->final_cap;
+	int *d_n = d_vmap + e->final_cap;
+	uint32_t *d_err = (uint32_t *) (d_n + 1);
 	GG_CUDA(cudaMemcpyAsync(d_recs, recs.data(), sizeof(ggp_grec) * (size_t) nin, cudaMemcpyHostToDevice, e->stream));
 	GG_CUDA(cudaMemcpyAsync(d_err, &hostflags, sizeof hostflags, cudaMemcpyHostToDevice, e->stream));
 	GG_CUDA(cudaMemsetAsync(d_out, 0, sizeof(ggp_grec) * cap, e->stream));
@@ -1036,7 +1042,6 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 	if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
 	std::vector<ggp_grec> merged((size_t) (n > 0 ? n : 1));
 	if (le == cudaSuccess && n > 0) le = cudaMemcpy(merged.data(), d_out, sizeof(ggp_grec) * n, cudaMemcpyDeviceToHost);
-	cudaFree(d_recs); cudaFree(d_out); cudaFree(d_vidx); cudaFree(d_vmap); cudaFree(d_n); cudaFree(d_err);
 	if (le != cudaSuccess) return gg_cuda_fail(le, "gg_agg_final");
 	int rc = gg_errflags_to_code(flags);
 	if (rc) return rc;

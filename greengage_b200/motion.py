@@ -71,6 +71,53 @@ def redistribute_aggrows(rows, key_typids, device=None, group=None):
     return _bytes_to_rows(rt.cpu().numpy())
 
 
+SMALL_MOTION_ROWS = 64      # rows per segment one fixed-size record carries
+
+
+def _allgather_rows(rows, device, group):
+    """One collective: every rank contributes [row count | up to SMALL_MOTION_ROWS rows].  Returns (per-rank row
+    lists, per-rank true counts); a rank with more rows than the record holds contributes its count only."""
+    import torch
+    import torch.distributed as dist
+    nsegs = dist.get_world_size(group)
+    buf = np.zeros(8 + SMALL_MOTION_ROWS * ROW_BYTES, dtype=np.uint8)
+    buf[:8] = np.frombuffer(np.int64(len(rows)).tobytes(), dtype=np.uint8)
+    if len(rows) <= SMALL_MOTION_ROWS:
+        b = _rows_to_bytes(rows)
+        buf[8:8 + b.size] = b
+    t = _tensor(buf, device)
+    out = torch.empty(nsegs * buf.size, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    host = out.cpu().numpy().reshape(nsegs, buf.size)
+    counts = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(nsegs)]
+    per = [_bytes_to_rows(host[r, 8:8 + counts[r] * ROW_BYTES]) if counts[r] <= SMALL_MOTION_ROWS else [] for r in range(nsegs)]
+    return per, counts
+
+
+def redistribute_small(rows, key_typids, device=None, group=None):
+    """Redistribute Motion for the handful of rows a partial aggregate emits: ONE all-gather of fixed-size records,
+    each segment keeps the rows cdbhash routes to it (sender order).  When any segment has more rows than a record
+    holds — every rank sees that in the gathered counts — all ranks take the all-to-all-v path instead."""
+    import torch.distributed as dist
+    nsegs = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per, counts = _allgather_rows(rows, device, group)
+    if max(counts) > SMALL_MOTION_ROWS:
+        return redistribute_aggrows(rows, key_typids, device=device, group=group)
+    return [r for sender in per for r in sender if route_aggrow(r, key_typids, nsegs) == rank]
+
+
+def gather_small(rows, dst=0, device=None, group=None):
+    """Gather Motion for a handful of rows per segment: one all-gather, the receiver keeps everything."""
+    import torch.distributed as dist
+    per, counts = _allgather_rows(rows, device, group)
+    if max(counts) > SMALL_MOTION_ROWS:
+        return gather_aggrows(rows, dst, device=device, group=group)
+    if dist.get_rank(group) != dst:
+        return []
+    return [r for sender in per for r in sender]
+
+
 def gather_aggrows(rows, dst=0, device=None, group=None):
     """Gather Motion (MOTIONTYPE_FIXED to one receiver): rows of all ranks on `dst`, in sender order."""
     import torch

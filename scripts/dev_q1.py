@@ -8,9 +8,10 @@ from greengage_b200.engine import Engine, Relation, ScanAgg
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 5_000_000
 table = capi.TAB_LINEITEM_NARROW if (len(sys.argv) > 2 and sys.argv[2] == "narrow") else capi.TAB_LINEITEM_WIDE
 check = len(sys.argv) > 3 and sys.argv[3] == "check"
+stage = capi.AGGSTAGE_PARTIAL if "partial" in sys.argv[3:] else capi.AGGSTAGE_NORMAL
 spec = tpch.synth_spec(table, n)
 t = time.time(); pages, nb, nr = tpch.synth_generate(spec); print("gen %.2fs blocks=%d rows=%d" % (time.time() - t, nb, nr), flush=True)
-scan, agg, pool = tpch.q1_plan(table)
+scan, agg, pool = tpch.q1_plan(table, stage)
 eng = Engine(0)
 rel = Relation(eng, host_pages=pages)
 sa = ScanAgg(eng, scan, agg, pool)

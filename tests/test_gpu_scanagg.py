@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 VARIANTS = {
     "specialised-priv": {},
     "nvrtc-priv": {"GGB200_PLAN_CACHE": "0"},
+    "nvrtc-priv-1row": {"GGB200_PLAN_CACHE": "0", "GGB200_ROWS_PER_LANE": "1"},      # one row per lane instead of two
     "interp-priv": {"GGB200_JIT": "0"},
     "specialised-tr": {"GGB200_SCAN_MODE": "1"},
     "interp-tr": {"GGB200_JIT": "0", "GGB200_SCAN_MODE": "1"},
@@ -37,7 +38,7 @@ class env:
         self.kw = kw
 
     def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in ("GGB200_JIT", "GGB200_SCAN_MODE", "GGB200_PLAN_CACHE")}
+        self.old = {k: os.environ.get(k) for k in ("GGB200_JIT", "GGB200_SCAN_MODE", "GGB200_PLAN_CACHE", "GGB200_ROWS_PER_LANE")}
         for k in self.old:
             os.environ.pop(k, None)
         os.environ.update(self.kw)
@@ -262,7 +263,7 @@ def test_group_by_with_tens_of_thousands_of_groups(eng, hint):
         sa.run(rel, 0, half)                          # two runs accumulate into the same table
         sa.run(rel, half, rel.nblocks - half)
         got, gsc, gps = sa.fetch(cap=100_000)
-        assert sa.variant() == 5
+        assert sa.variant() % 16 == 5                 # the general HashAggregate (plan-specialised or not)
         assert (gsc, gps) == (sc, ps)
         assert_aggrows_match(got, want, agg)
         with pytest.raises(capi.GGError) as e:        # the caller's buffer is too small: said so, not truncated
@@ -313,7 +314,7 @@ def test_nullable_keys_and_int_aggregates_in_the_general_hashagg(eng):
     try:
         sa.run(rel)
         got, gsc, gps = sa.fetch(cap=10_000)
-        assert sa.variant() == 5 and len(got) == len(want) > 1500
+        assert sa.variant() % 16 == 5 and len(got) == len(want) > 1500
         assert_aggrows_match(got, want, agg)
     finally:
         sa.free()

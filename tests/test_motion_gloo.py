@@ -26,8 +26,16 @@ def _worker(rank, world, port, q):
         mine = motion.redistribute_aggrows(rows, keyt)
         for r in mine:
             assert motion.route_aggrow(r, keyt, world) == rank
+        # the one-collective path for small row counts delivers the same rows in the same order
+        mine2 = motion.redistribute_small(rows, keyt)
+        assert [bytes(r) for r in mine2] == [bytes(r) for r in mine]
+        old = motion.SMALL_MOTION_ROWS
+        motion.SMALL_MOTION_ROWS = 1                  # force the collective fallback decision
+        assert [bytes(r) for r in motion.redistribute_small(rows, keyt)] == [bytes(r) for r in mine]
+        motion.SMALL_MOTION_ROWS = old
         final = po.agg_final(tpch.q1_final_agg(part), mine) if mine else []
         gathered = motion.gather_aggrows(final, 0)
+        assert [bytes(r) for r in motion.gather_small(final, 0)] == [bytes(r) for r in gathered]
         if rank == 0:
             out = [(r.key[0], r.key[1], r.agg[7].i, r.agg[0].f[0], r.agg[4].f[0]) for r in gathered]
             q.put(("ok", sorted(out), nr))
