@@ -25,7 +25,6 @@ struct gg_jit_kernel {
 /* mode: the kernel role (MODE_* of gg_scanagg_kernel.cuh); join_probe_pc >= 0: the probe side of a join pipeline */
 std::string gg_jit_scanagg_source(const ggp_program *prog, int mode, int threads, const char *suffix, int join_probe_pc = -1);
 uint64_t gg_plan_hash(const ggp_program *prog, int mode);
-int gg_jit_rows_per_lane(const ggp_program *prog, int mode, int join_probe_pc);
 /* build-time plan cache (csrc/plans/gg_plan_cache.cu): address of the kernel specialised for this hash, or nullptr */
 const void *gg_plan_cache_lookup(uint64_t hash, int threads);
 /* compile (or fetch from the cache) the specialised scan+agg kernel; returns nullptr and fills err when JIT is

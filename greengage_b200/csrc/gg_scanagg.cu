@@ -315,6 +315,7 @@ struct gg_scanagg {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
 	size_t kev_used = 0;
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
+	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
 	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
 	HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */
 	void *ha_mem = nullptr;
@@ -346,7 +347,7 @@ static int scanagg_configure(gg_scanagg *p)
 	gg_engine *e = p->eng;
 	const int nslots = p->prog.nslots;
 	const int V = nslots > 0 ? nslots : 1;
-	int scr = (p->prog.outer.ncols * 64 * (p->mode == MODE_PRIV ? 2 : 1) + 15) & ~15;   /* column offsets [ncols][32] u16, per row of the lane */
+	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
 	if (p->mode == MODE_TR || p->mode == MODE_TRN) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
 	p->scratch_per_warp = (scr + 15) & ~15;
 	p->nstage = 3;
@@ -355,10 +356,12 @@ static int scanagg_configure(gg_scanagg *p)
 		/* 1 CTA/SM: 14 consumer warps + producer.  What the ring and the scratch leave of the 227 KB goes to
 		 * the per-thread private accumulators; that fixes how many groups this variant holds. */
 		p->ctas_per_sm = 1;
-		/* 16 consumer warps on a 4-page ring measured best on both dense (430 rows/page) and sparse
-		 * (190 rows/page) lineitem pages; fewer warps if the private accumulators of >= 4 groups need the room */
-		int ncons = 16;
-		p->nstage = 4;
+		/* Measured on 10^8-row lineitem (scripts/dev_sweep.sh): sparse pages (190 rows = 6 chunks of 32 line pointers)
+		 * need pages in flight more than warps -> 16 consumer warps on a 4-page ring (4.4 TB/s; 20 warps / 3 pages: 4.0);
+		 * dense pages (430 rows = 14 chunks) keep every warp busy from fewer pages -> 20 warps on a 3-page ring
+		 * (39 G rows/s; 16 warps / 4 pages: 32).  Fewer warps if the private accumulators of >= 4 groups need the room. */
+		int ncons = p->chunks_per_page >= 10 ? 20 : 16;
+		p->nstage = p->chunks_per_page >= 10 ? 3 : 4;
 		for (;;)
 		{
 			size_t need = (size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 48 +
@@ -557,6 +560,30 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 
 extern "C" int gg_scanagg_reset(gg_scanagg *p);
 
+/* First feed of a private-accumulator pipeline: look at one page header to see how densely the relation's pages
+ * are populated and pick the launch configuration for it (see scanagg_configure). */
+static int scanagg_adapt_to_pages(gg_scanagg *p, const uint8_t *dev_page, const void *host_page)
+{
+	if (p->mode != MODE_PRIV || p->has_state || p->chunks_per_page || p->prog.outer.rowwords || getenv("GGB200_PRIV_CONFIG")) return GG_OK;
+	uint32_t hdr[6] = { 0 };
+	if (host_page) memcpy(hdr, host_page, sizeof hdr);
+	else GG_CUDA(cudaMemcpy(hdr, dev_page, sizeof hdr, cudaMemcpyDeviceToHost));
+	const uint32_t pd_lower = hdr[3] & 0xFFFF;
+	int items = pd_lower >= GG_PAGE_HEADER_SIZE && pd_lower <= GG_BLCKSZ ? (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2) : 0;
+	p->chunks_per_page = items > 0 ? (items + 31) / 32 : 1;
+	const int threads0 = p->threads, stages0 = p->nstage;
+	int rc = scanagg_configure(p);
+	if (rc) return rc;
+	if (p->mode == MODE_PRIV && p->agg.numGroups > p->gcap)
+	{
+		/* the denser configuration leaves room for fewer groups than the planner expects: keep the default one */
+		p->chunks_per_page = 1;
+		rc = scanagg_configure(p);
+	}
+	(void) threads0; (void) stages0;
+	return rc;
+}
+
 /* the part of pipeline creation that follows plan compilation (p->prog / p->aggmap are set) */
 static int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 {
@@ -653,8 +680,10 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	gg_engine *e = p->eng;
 	GG_CUDA(cudaSetDevice(e->device));
+	int rc = nblocks ? scanagg_adapt_to_pages(p, r->pages + first_block * GG_BLCKSZ, nullptr) : GG_OK;
+	if (rc) return rc;
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
-	int rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream, r->nrows);
+	rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream, r->nrows);
 	if (rc) return rc;
 	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
@@ -671,7 +700,9 @@ int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 {
 	if (!p || (!host_pages && nblocks)) return GG_ERR_ARG;
 	if (p->prog.outer.rowwords) { gg_set_error("datum rows are device-resident; the streamed path takes heap pages"); return GG_ERR_ARG; }
-	int rc = scanagg_stream_host(p, host_pages, nblocks);
+	int rc = nblocks ? scanagg_adapt_to_pages(p, nullptr, host_pages) : GG_OK;
+	if (rc) return rc;
+	rc = scanagg_stream_host(p, host_pages, nblocks);
 	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0 });
 	return rc;
 }

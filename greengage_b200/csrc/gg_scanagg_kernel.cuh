@@ -542,23 +542,9 @@ struct DynPlan {
 	{
 		walk_tuple(P.outer, tup, tuplen, fast, offs, lane, tv, err);
 	}
-	/* two rows per lane (K == 2) */
-	template <bool NULLABLE, class Sink>
-	__device__ static __forceinline__ void run2(const EvalCtx &X0, const EvalCtx &X1, bool live0, bool live1, uint32_t &err, Sink &s0, Sink &s1)
-	{
-		run_prog<NULLABLE, false>(X0, live0, err, s0);
-		run_prog<NULLABLE, false>(X1, live1, err, s1);
-	}
-	__device__ static __forceinline__ void walk2(const ggp_program &P, uint32_t tup0, uint32_t len0, bool live0, uint32_t tup1, uint32_t len1,
-	                                             bool live1, bool fast, uint32_t offs0, uint32_t offs1, int lane, TupleView &tv0, TupleView &tv1,
-	                                             uint32_t &err)
-	{
-		if (live0) walk_tuple(P.outer, tup0, len0, fast, offs0, lane, tv0, err);
-		if (live1) walk_tuple(P.outer, tup1, len1, fast, offs1, lane, tv1, err);
-	}
 };
 
-template <int MODE, class PL, bool JOIN = false, int K = 1>
+template <int MODE, class PL, bool JOIN = false>
 __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAggParams &prm)
 {
 	constexpr bool NULLABLE = (MODE == MODE_TRN || MODE == MODE_BUILD || MODE == MODE_PART || MODE == MODE_HASH);
@@ -694,11 +680,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			sink.jq = false; sink.nullext = false; sink.suppress = false;
 		}
 
-		EvalCtx X1 = X;                                  /* K == 2: the lane's second row */
-		X1.offs = offs + (uint32_t) ncols * 64;
-		typename SinkSel<MODE, JOIN>::type sink1 = sink;
-
-		/* Chunks (32 * K line pointers) are dealt round-robin over the consumer warps ACROSS pages: chunk c of this page
+		/* Chunks (32 line pointers) are dealt round-robin over the consumer warps ACROSS pages: chunk c of this page
 		 * goes to warp (dealt + c) mod ncons, dealt = chunks of all earlier pages.  Consecutive pages therefore land
 		 * on disjoint warp sets, so the pages in flight in the ring are processed concurrently instead of queueing
 		 * behind the same few warps. */
@@ -728,7 +710,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			else
 				nitems = (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2);
 			const bool all_visible = (pd_flags & GG_PD_ALL_VISIBLE) != 0;     /* heapam.c:391 */
-			const int nchunks = (nitems + 32 * K - 1) / (32 * K);      /* a chunk = 32 * K line pointers: K rows per lane */
+			const int nchunks = (nitems + 31) >> 5;
 
 			int c0 = warp - dealt;
 			if (c0 < 0) c0 += ncons;
@@ -736,38 +718,6 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			while (dealt >= ncons) dealt -= ncons;          /* nchunks <= 37: a handful of subtractions beats a division */
 			for (int c = c0; c < nchunks; c += ncons)
 			{
-				if constexpr (K == 2)
-				{
-					/* two rows per lane, evaluated side by side: the two dependency chains (address -> load -> op ->
-					 * accumulate) are independent, so the scheduler overlaps their latencies */
-					uint32_t tup0, tup1, len0, len1;
-					bool hn0, hn1;
-					bool live0 = heap_tuple_front(pg, c * 64 + lane, nitems, pd_upper, pd_special, all_visible, tup0, len0, hn0, err);
-					bool live1 = heap_tuple_front(pg, c * 64 + 32 + lane, nitems, pd_upper, pd_special, all_visible, tup1, len1, hn1, err);
-					const bool fast = !__any_sync(GG_FULL_MASK, hn0 || hn1);
-					X.fast = fast; X1.fast = fast;
-					X.tv.tp = pg; X.tv.colnull = 0; X1.tv.tp = pg; X1.tv.colnull = 0;
-					n_scanned += (live0 ? 1 : 0) + (live1 ? 1 : 0);
-					const uint32_t e0 = err;
-					PL::walk2(P, tup0, len0, live0, tup1, len1, live1, fast, offs, offs + (uint32_t) ncols * 64, lane, X.tv, X1.tv, err);
-					if (err != e0 && (err & GGP_EF_BADPAGE)) { live0 = false; live1 = false; }
-					if (!NULLABLE && (X.tv.colnull | X1.tv.colnull)) { err |= GGP_EF_NOTNULL_VIOLATED; live0 = false; live1 = false; }
-					if (!live0)
-					{
-						X.tv.tp = pg;
-						for (int sl = 0; sl < ncols; sl++) sts16(offs + (uint32_t) (sl * 32 + lane) * 2, 0);
-					}
-					if (!live1)
-					{
-						X1.tv.tp = pg;
-						for (int sl = 0; sl < ncols; sl++) sts16(offs + (uint32_t) ncols * 64 + (uint32_t) (sl * 32 + lane) * 2, 0);
-					}
-					if (!(live0 && live1)) { X.fast = X.fast && live0; X1.fast = X1.fast && live1; }
-					sink.begin_row();
-					sink1.begin_row();
-					PL::template run2<NULLABLE>(X, X1, live0, live1, err, sink, sink1);
-					continue;
-				}
 				const int idx = c * 32 + lane;
 				bool live = false;
 				uint32_t tup = pg, tuplen = 64;
@@ -931,8 +881,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
 			if (++s == nstage) { s = 0; ph ^= 1; }
 		}
-		n_passed = sink.npassed + (K == 2 ? sink1.npassed : 0);
-		if (sink.nonfinite || (K == 2 && sink1.nonfinite)) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
+		n_passed = sink.npassed;
+		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
 	}
 
 	/* ===== epilogue: threads -> block records, all in fixed order ===== */

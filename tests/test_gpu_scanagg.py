@@ -18,7 +18,6 @@ pytestmark = pytest.mark.gpu
 VARIANTS = {
     "specialised-priv": {},
     "nvrtc-priv": {"GGB200_PLAN_CACHE": "0"},
-    "nvrtc-priv-1row": {"GGB200_PLAN_CACHE": "0", "GGB200_ROWS_PER_LANE": "1"},      # one row per lane instead of two
     "interp-priv": {"GGB200_JIT": "0"},
     "specialised-tr": {"GGB200_SCAN_MODE": "1"},
     "interp-tr": {"GGB200_JIT": "0", "GGB200_SCAN_MODE": "1"},
@@ -38,7 +37,7 @@ class env:
         self.kw = kw
 
     def __enter__(self):
-        self.old = {k: os.environ.get(k) for k in ("GGB200_JIT", "GGB200_SCAN_MODE", "GGB200_PLAN_CACHE", "GGB200_ROWS_PER_LANE")}
+        self.old = {k: os.environ.get(k) for k in ("GGB200_JIT", "GGB200_SCAN_MODE", "GGB200_PLAN_CACHE")}
         for k in self.old:
             os.environ.pop(k, None)
         os.environ.update(self.kw)
