@@ -360,14 +360,24 @@ static int scanagg_configure(gg_scanagg *p)
 		 * need pages in flight more than warps -> 16 consumer warps on a 4-page ring (4.4 TB/s; 20 warps / 3 pages: 4.0);
 		 * dense pages (430 rows = 14 chunks) keep every warp busy from fewer pages -> 20 warps on a 3-page ring
 		 * (39 G rows/s; 16 warps / 4 pages: 32).  Fewer warps if the private accumulators of >= 4 groups need the room. */
-		int ncons = p->chunks_per_page >= 10 ? 20 : 16;
-		p->nstage = p->chunks_per_page >= 10 ? 3 : 4;
-		for (;;)
+		auto fit = [&](int stages, int want) {           /* most consumer warps (<= want) whose accumulators of 4 groups fit */
+			int w = want;
+			for (; w > 4; w--)
+			{
+				size_t need = (size_t) stages * GG_BLCKSZ + (size_t) stages * 16 + sizeof(BlockTable) + 48 +
+				              (size_t) w * p->scratch_per_warp + (size_t) w * 32 * (8 * nslots + 4) * 4;
+				if (need <= e->smem_optin) break;
+			}
+			return w;
+		};
+		int ncons;
+		if (p->chunks_per_page >= 10) { p->nstage = 3; ncons = fit(3, 20); }
+		else
 		{
-			size_t need = (size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 48 +
-			              (size_t) ncons * p->scratch_per_warp + (size_t) ncons * 32 * (8 * nslots + 4) * 4;   /* >= 4 groups */
-			if (need <= e->smem_optin || ncons <= 4) break;
-			ncons--;
+			/* plans with many value slots (a PARTIAL-stage Q1 carries 8): when 4 stages leave room for fewer than 15
+			 * warps, a 3-page ring with more warps measured faster (13 warps / 3 pages: 3.4 TB/s; 9 / 4: 2.8) */
+			p->nstage = 4; ncons = fit(4, 16);
+			if (ncons < 15) { int w3 = fit(3, 16); if (w3 >= ncons + 3) { p->nstage = 3; ncons = w3; } }
 		}
 		{
 			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages" for experiments */

@@ -849,11 +849,14 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 						{
 							for (;;)
 							{
+								/* header and keys are fetched together (one round trip to HBM per probe step, not two) */
 								e = jt.ent + (size_t) slot * jt.stride;
 								hdr = __ldg(e);
+								const unsigned long long ek0 = __ldg(e + 1);
+								const unsigned long long ek1 = jt.nkeys > 1 ? __ldg(e + 2) : 0ull;
 								slot = (slot + 1) & jt.mask;
 								if (hdr == 0) { probing = false; break; }
-								if ((uint32_t) hdr == (uint32_t) h && __ldg(e + 1) == jk0 && (jt.nkeys < 2 || __ldg(e + 2) == jk1)) { have = true; break; }
+								if ((uint32_t) hdr == (uint32_t) h && ek0 == jk0 && (jt.nkeys < 2 || ek1 == jk1)) { have = true; break; }
 							}
 						}
 						bool nullext = false;

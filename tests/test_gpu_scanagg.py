@@ -51,23 +51,24 @@ class env:
 
 def gpu_scanagg(eng, scan, agg, pool, pages, variant=None, ranges=None, host=False):
     from greengage_b200.engine import Relation, ScanAgg
+    # the variant's environment stays in force for the whole pipeline life: the kernel is (re)chosen at the first run too
     with env(**(VARIANTS[variant] if variant else {})):
         sa = ScanAgg(eng, scan, agg, pool)
-    rel = Relation(eng, host_pages=pages) if pages.size else Relation(eng, nblocks=0)
-    nb = pages.size // capi.GG_BLCKSZ
-    try:
-        if host:
-            sa.run_host(pages.ctypes.data, nb)
-        elif ranges:
-            for a, b in ranges:
-                sa.run(rel, a, b - a)
-        else:
-            sa.run(rel)
-        rows, sc, ps = sa.fetch()
-        return rows, sc, ps, sa.variant()
-    finally:
-        sa.free()
-        rel.free()
+        rel = Relation(eng, host_pages=pages) if pages.size else Relation(eng, nblocks=0)
+        nb = pages.size // capi.GG_BLCKSZ
+        try:
+            if host:
+                sa.run_host(pages.ctypes.data, nb)
+            elif ranges:
+                for a, b in ranges:
+                    sa.run(rel, a, b - a)
+            else:
+                sa.run(rel)
+            rows, sc, ps = sa.fetch()
+            return rows, sc, ps, sa.variant()
+        finally:
+            sa.free()
+            rel.free()
 
 
 # ---------------------------------------------------------------------------------------------
