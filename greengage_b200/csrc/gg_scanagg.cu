@@ -22,7 +22,7 @@ gg_scanagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm
 /* HashJoin probe side: the same scan front end; every outer row probes the join hash table and each
  * match runs the per-match piece of the program (join qual, grouping keys, aggregate arguments) */
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
 gg_joinprobe_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
 	scanagg_body<MODE, DynPlan, true>(P, prm);
@@ -433,7 +433,9 @@ static int scanagg_configure(gg_scanagg *p)
 	}
 	if (p->is_join)
 	{
-		if (p->mode == MODE_TR)
+		if (p->mode == MODE_PRIV)
+			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_PRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+		else if (p->mode == MODE_TR)
 			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 		else
 			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
@@ -535,7 +537,8 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	}
 	if (p->is_join && !p->jit)
 	{
-		if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		if (p->mode == MODE_PRIV) gg_joinprobe_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		else if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 		else gg_joinprobe_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	}
 	else if (p->jit)
@@ -603,7 +606,7 @@ static int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 	/* kernel variant: private accumulators when the plan allows it (NOT NULL float8 sums); the planner's
 	 * group estimate decides whether they can hold the groups */
 	p->mode = p->prog.nullable ? MODE_TRN : MODE_TR;
-	if (p->prog.priv_ok && !p->is_join) p->mode = MODE_PRIV;
+	if (p->prog.priv_ok) p->mode = MODE_PRIV;
 	if (!p->is_join)
 	{
 		const char *force = getenv("GGB200_SCAN_MODE");       /* experiments: 0 PRIV, 1 TR, 2 TRN */
@@ -1129,6 +1132,7 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 	p->prog = j->jp.probe;
 	p->join_probe_pc = j->jp.probe_pc;
 	p->prog.nullable = p->prog.nullable || j->jp.build.nullable;     /* a NULL payload column shows up on the probe side */
+	if (p->prog.nullable) p->prog.priv_ok = 0;
 	rc = scanagg_finish_create(p, &j->probe);
 	if (rc) { delete j; return rc; }
 	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 2 * sizeof(unsigned long long)));

@@ -61,3 +61,64 @@ def test_deep_expression_uses_temporaries():
     ops = [ln.split()[1] for ln in lines]
     # a plain aggregate opens with the (key-less) GROUP action
     assert ops == ["NOP", "LD_C8", "MUL_C", "LD_C8", "DIV_C", "RSUB_T", "END"] and "GROUP" in lines[0] and "ST t0" in lines[2]
+
+
+# ---- join pipelines and datum-row input -------------------------------------------------------------------------
+
+L.gg_debug_disasm_join.argtypes = [C.POINTER(capi.gg_scan), C.POINTER(capi.gg_scan), C.POINTER(capi.gg_hashjoin), C.POINTER(capi.gg_agg),
+                                   C.POINTER(capi.gg_exprpool), C.c_char_p, C.c_int]
+
+
+def disasm_join(outer, inner, hj, agg, pool):
+    buf = C.create_string_buffer(1 << 16)
+    n = L.gg_debug_disasm_join(C.byref(outer), C.byref(inner), C.byref(hj), C.byref(agg), C.byref(pool), buf, 1 << 16)
+    if n < 0:
+        raise capi.GGError(n, L.gg_last_error().decode())
+    text = buf.value.decode()
+    build, probe = text.split("-- probe")
+    return build.splitlines()[1:], probe.splitlines()[1:], text
+
+
+def test_join_programs_shape():
+    build, probe, text = disasm_join(*tpch.join_plan(kind="q3ish", jointype=capi.JOIN_INNER))
+    assert "payload 2" in text
+    # build: inner qual, then the join key claims the slot, then the payload columns in slot order
+    assert "FILTER" in build[1] and "KEY0 GROUP" in build[2] and "OUT0" in build[3] and "OUT1" in build[4]
+    # probe: the outer key completes the first piece; the per-match piece reads inner columns (idx >= 128) from the payload
+    assert "KEY0 PROBE" in probe[0] and "per-match segment from pc 1" in text
+    assert any("idx=128" in ln and "FILTER" in ln for ln in probe)           # the join qual l_shipdate > o_orderdate
+    assert any("idx=129" in ln and "GROUP" in ln for ln in probe)            # GROUP BY o_orderstatus
+    assert not any("off=" in ln and "idx=12" in ln and "off=-1" not in ln for ln in probe)   # no tuple offsets for payload reads
+
+
+def test_join_shapes_outside_the_subset_are_refused():
+    outer, inner, hj, agg, pool = tpch.join_plan(kind="count")
+    hj.jointype = 2                                                          # FULL
+    with pytest.raises(capi.GGError) as e:
+        disasm_join(outer, inner, hj, agg, pool)
+    assert e.value.code == -6
+    outer, inner, hj, agg, pool = tpch.join_plan(kind="count")
+    hj.nkeys = 3
+    with pytest.raises(capi.GGError) as e:
+        disasm_join(outer, inner, hj, agg, pool)
+    assert e.value.code == -6
+    # mismatched key classes (int8 = float8) have no common hash function
+    p = ExprPool()
+    li, od = capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW), capi.synth_tupdesc(capi.TAB_ORDERS)
+    hj = capi.make_hashjoin(capi.JOIN_INNER, [p.var(1, capi.INT8OID, 0)], [p.var(4, capi.FLOAT8OID, 1)])
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(capi.AGG_COUNT_STAR, -1)])
+    with pytest.raises(capi.GGError) as e:
+        disasm_join(capi.make_scan(li, -1), capi.make_scan(od, -1), hj, agg, p.pool)
+    assert e.value.code == -6 and "join key" in str(e.value)
+
+
+def test_datum_row_input_uses_constant_word_offsets():
+    types = [capi.INT8OID, capi.FLOAT8OID, capi.BPCHAROID, capi.DATEOID]
+    desc = capi.rows_tupdesc(types, notnull=[1, 1, 0, 1])
+    p = ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(3, capi.BPCHAROID)], [(capi.AGG_SUM_FLOAT8, p.var(2, capi.FLOAT8OID)), (capi.AGG_MIN_DATE, p.var(4, capi.DATEOID))])
+    lines = disasm(capi.make_scan(desc, -1), agg, p.pool)
+    # every column is a 64-bit word: strings and dates are already in loaded form, offsets are 8 * attno
+    assert "LD_C8" in lines[0] and "off=16" in lines[0] and "KEY0" in lines[0]
+    assert "LD_C8" in lines[1] and "off=8" in lines[1]
+    assert "LD_C8" in lines[2] and "off=24" in lines[2]
