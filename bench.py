@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
     cores = host_cores()
     table = capi.TAB_LINEITEM_NARROW if args.table == "narrow" else capi.TAB_LINEITEM_WIDE
     # bounded sample: ~3 s of CPU work per step at ~3 M rows/s/core
-    rows = int(min(args.rows * max(world, 1), 8_000_000 * cores))
+    rows = int(min(args.rows * min(max(world, 1), 2), 8_000_000 * cores, 200_000_000))      # <= 34 GB of pages, a few seconds per step
     t0 = time.time()
     total_secs = 0.0
     nr = 0

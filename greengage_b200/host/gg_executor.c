@@ -309,18 +309,24 @@ static int run_node(GgPlanState *s)
 		{
 			int cap = 4096, n = 0, c;
 			int32_t keytypes[GG_MAX_KEYS] = { 0 };
-			gg_aggrow *rows = malloc(sizeof(gg_aggrow) * (size_t) cap);
-			if (!rows) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+			gg_aggrow *rows = NULL;
 			if (s->kind == K_SCANAGG)
-			{
 				rc = gg_scanagg_run(s->sa, s->rel, 0, gg_relation_nblocks(s->rel));
-				if (rc == GG_OK) rc = gg_scanagg_fetch(s->sa, rows, cap, &n, NULL, NULL);
-			}
 			else
 			{
 				rc = gg_joinagg_build(s->ja, s->inner_rel, 0, gg_relation_nblocks(s->inner_rel));
 				if (rc == GG_OK) rc = gg_joinagg_probe(s->ja, s->rel, 0, gg_relation_nblocks(s->rel));
-				if (rc == GG_OK) rc = gg_joinagg_fetch(s->ja, rows, cap, &n, NULL);
+			}
+			/* the result stays on the device until fetched: grow the row buffer until every group fits */
+			while (rc == GG_OK)
+			{
+				free(rows);
+				rows = malloc(sizeof(gg_aggrow) * (size_t) cap);
+				if (!rows) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+				rc = s->kind == K_SCANAGG ? gg_scanagg_fetch(s->sa, rows, cap, &n, NULL, NULL) : gg_joinagg_fetch(s->ja, rows, cap, &n, NULL);
+				if (rc != GG_ERR_NOMEM || cap >= (1 << 24)) break;
+				cap *= 16;
+				rc = GG_OK;
 			}
 			if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(rows); return -1; }
 			for (c = 0; c < s->agg.numCols; c++) keytypes[c] = expr_type(es->pool, s->agg.grpCol[c]);
@@ -504,3 +510,31 @@ void GgExecEndNode(GgPlanState *s)
 	GgExecEndNode(s->child);
 	free_state(s);
 }
+
+/* ---- per-node entry points (executor/node*.h names) ---- */
+static GgPlanState *init_tagged(GgPlan *plan, GgNodeTag tag, GgEState *estate, int eflags)
+{
+	if (!plan || plan->type != tag) return exec_fail(GG_ERR_ARG, "node tag %d where %d was expected", plan ? (int) plan->type : 0, (int) tag);
+	return GgExecInitNode(plan, estate, eflags);
+}
+
+GgPlanState *GgExecInitAgg(GgAgg *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgAgg, estate, eflags); }
+GgTupleTableSlot *GgExecAgg(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndAgg(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanAgg(GgPlanState *node) { return GgExecReScan(node); }
+void GgExecSquelchAgg(GgPlanState *node) { GgExecSquelchNode(node); }
+
+GgPlanState *GgExecInitSort(GgSort *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgSort, estate, eflags); }
+GgTupleTableSlot *GgExecSort(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndSort(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanSort(GgPlanState *node) { return GgExecReScan(node); }
+void GgExecSquelchSort(GgPlanState *node) { GgExecSquelchNode(node); }
+
+GgPlanState *GgExecInitMotion(GgMotion *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgMotion, estate, eflags); }
+GgTupleTableSlot *GgExecMotion(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndMotion(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanMotion(GgPlanState *node) { return GgExecReScan(node); }
+void GgExecSquelchMotion(GgPlanState *node) { GgExecSquelchNode(node); }
+
+GgPlanState *GgExecInitHashJoin(GgHashJoin *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgHashJoin, estate, eflags); }
+GgPlanState *GgExecInitSeqScan(GgSeqScan *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgSeqScan, estate, eflags); }

@@ -141,6 +141,31 @@ int  GgExecLastErrorCode(void);                /* GG_ERR_* of the failure, GG_OK
 /* introspection: which device pipeline a state node was fused into ("scanagg", "joinagg", "sort", "motion") */
 const char *GgExecNodeKind(GgPlanState *node);
 
+/* The per-node entry points of src/include/executor/node*.h, for a build that replaces the node files
+ * at link time instead of going through ExecProcNode's switch.  Each checks the node tag and delegates to the
+ * functions above; the state they return is the state of the fused pipeline rooted at that node.
+ *     nodeAgg.h:22-25,231   nodeSort.h:19-25   nodeMotion.h:20-27   nodeHashjoin.h:20-28   nodeSeqscan.h:19-24
+ * A HashJoin or SeqScan is only accelerated underneath an Agg (the join is never materialised), so GgExecInitHashJoin /
+ * GgExecInitSeqScan on a bare node return NULL with GG_ERR_UNSUPPORTED, and the Hash node has no state of its own
+ * (MultiExecHash is the build kernel the Agg's pipeline launches). */
+GgPlanState *GgExecInitAgg(GgAgg *node, GgEState *estate, int eflags);
+GgTupleTableSlot *GgExecAgg(GgPlanState *node);
+void GgExecEndAgg(GgPlanState *node);
+int  GgExecReScanAgg(GgPlanState *node);
+void GgExecSquelchAgg(GgPlanState *node);
+GgPlanState *GgExecInitSort(GgSort *node, GgEState *estate, int eflags);
+GgTupleTableSlot *GgExecSort(GgPlanState *node);
+void GgExecEndSort(GgPlanState *node);
+int  GgExecReScanSort(GgPlanState *node);
+void GgExecSquelchSort(GgPlanState *node);
+GgPlanState *GgExecInitMotion(GgMotion *node, GgEState *estate, int eflags);
+GgTupleTableSlot *GgExecMotion(GgPlanState *node);
+void GgExecEndMotion(GgPlanState *node);
+int  GgExecReScanMotion(GgPlanState *node);
+void GgExecSquelchMotion(GgPlanState *node);
+GgPlanState *GgExecInitHashJoin(GgHashJoin *node, GgEState *estate, int eflags);
+GgPlanState *GgExecInitSeqScan(GgSeqScan *node, GgEState *estate, int eflags);
+
 #ifdef __cplusplus
 }
 #endif
