@@ -174,7 +174,7 @@ def main():
         run_reference(args, rank, world)
         return
 
-    from greengage_b200.engine import Engine, Relation, ScanAgg, agg_final, host_alloc, host_free
+    from greengage_b200.engine import Engine, Relation, ScanAgg, agg_final_raw, host_alloc, host_free
 
     dist = None
     torch = None
@@ -216,31 +216,35 @@ def main():
     key_typids = [capi.BPCHAROID, capi.BPCHAROID]
     from greengage_b200 import motion
 
-    def finish(rows):
-        """everything above the partial aggregate: Redistribute -> FINAL Agg -> Gather (N > 1)"""
+    def finish(buf, n):
+        """everything above the partial aggregate: Redistribute -> FINAL Agg -> Gather (N > 1); raw row buffers"""
         if world == 1:
-            return rows
-        mine = motion.redistribute_small(rows, key_typids, device=torch.device("cuda", local_rank))
-        final_rows = agg_final(eng, fin, mine) if mine else []
-        return motion.gather_small(final_rows, 0, device=torch.device("cuda", local_rank))
+            return n
+        dev = torch.device("cuda", local_rank)
+        mine, nm = motion.redistribute_small_raw(buf, n, key_typids, device=dev)
+        fbuf, nf = agg_final_raw(eng, fin, mine, nm, cap=256) if nm else (mine, 0)
+        gbuf, ng = motion.gather_small_raw(fbuf, nf, 0, device=dev)
+        return ng
 
     scan_ms_tot, scan_launches = 0.0, 0
+    fetched = [0]                 # result rows the last step copied device -> host on this rank
 
     def step_resident():
         nonlocal scan_ms_tot, scan_launches
         sa.reset()
         sa.run(rel)
-        rows, scanned, passed = sa.fetch()
-        ms, n = sa.scan_kernel_ms()
+        buf, n, scanned, passed = sa.fetch_raw(256)
+        fetched[0] = n
+        ms, k = sa.scan_kernel_ms()
         scan_ms_tot += ms
-        scan_launches += n
-        return finish(rows), scanned
+        scan_launches += k
+        return finish(buf, n), scanned
 
     def step_e2e():
         sa.reset()
         sa.run_host(haddr, nb)
-        rows, scanned, passed = sa.fetch()
-        return finish(rows), scanned
+        buf, n, scanned, passed = sa.fetch_raw(256)
+        return finish(buf, n), scanned
 
     def barrier():
         if dist is not None:
@@ -294,7 +298,7 @@ def main():
         ems = max_over_ranks(eng.timer_stop())
         barrier()
         e2e = {"value": total_rows * args.e2e_steps / (ems / 1000.0), "unit": UNIT,
-               "h2d_bytes_per_step": int(nbytes * world), "d2h_bytes_per_step": int(len(result_e or result) * C.sizeof(capi.gg_aggrow) * max(world, 1) + 24),
+               "h2d_bytes_per_step": int(nbytes * world), "d2h_bytes_per_step": int((fetched[0] * C.sizeof(capi.gg_aggrow) + 28) * max(world, 1)),
                "steps": args.e2e_steps, "ms_per_step": ems / args.e2e_steps,
                "host_memory": "pinned" if pinned else "pageable"}
 

@@ -130,6 +130,8 @@ def host_lib():
         L.gg_synth_orderkey.restype = C.c_int64
         L.gg_cdbhash_route.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.c_int, C.c_int]
+        L.gg_cdbhash_route_aggrows.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p]
+        L.gg_cdbhash_route_aggrows.restype = None
         L.gg_hash_any.argtypes = [C.c_char_p, C.c_int]
         L.gg_hash_any.restype = C.c_uint32
         _host = L

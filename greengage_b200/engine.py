@@ -147,6 +147,17 @@ class ScanAgg:
         check(dev_lib().gg_scanagg_fetch(self.h, out, cap, C.byref(n), C.byref(sc), C.byref(ps)))
         return [out[i] for i in range(n.value)], sc.value, ps.value
 
+    def fetch_raw(self, cap=4096):
+        """fetch() without building Python row objects: (numpy uint8 view of the gg_aggrow array, n, scanned, passed)"""
+        if getattr(self, "_raw_cap", 0) < cap:
+            self._raw = (capi.gg_aggrow * cap)()
+            self._raw_cap = cap
+        n = C.c_int(0)
+        sc, ps = C.c_uint64(0), C.c_uint64(0)
+        check(dev_lib().gg_scanagg_fetch(self.h, self._raw, cap, C.byref(n), C.byref(sc), C.byref(ps)))
+        buf = np.frombuffer(self._raw, dtype=np.uint8, count=n.value * C.sizeof(capi.gg_aggrow))
+        return buf, n.value, sc.value, ps.value
+
     def scan_kernel_ms(self):
         ms, n = C.c_float(0), C.c_int(0)
         check(dev_lib().gg_scanagg_scan_kernel_ms(self.h, C.byref(ms), C.byref(n)))
@@ -215,6 +226,16 @@ def sort_rows(eng, keys, rows, nulls=None):
     check(dev_lib().gg_sort_rows(eng.h, ka, len(keys), ncols, rows.ctypes.data,
                                  nulls.ctypes.data if nulls is not None else None, n, perm.ctypes.data))
     return perm
+
+
+def agg_final_raw(eng, agg, buf, n, cap=4096):
+    """gg_agg_final on a raw gg_aggrow buffer (numpy uint8); returns (buffer, n)"""
+    out = np.zeros(cap * C.sizeof(capi.gg_aggrow), dtype=np.uint8)
+    m = C.c_int(0)
+    src = np.ascontiguousarray(buf)
+    check(dev_lib().gg_agg_final(eng.h, C.byref(agg), C.cast(src.ctypes.data, C.POINTER(capi.gg_aggrow)), n,
+                                 C.cast(out.ctypes.data, C.POINTER(capi.gg_aggrow)), cap, C.byref(m)))
+    return out[:m.value * C.sizeof(capi.gg_aggrow)], m.value
 
 
 def agg_final(eng, agg, rows, cap=4096):

@@ -93,3 +93,13 @@ int32_t gg_cdbhash_route(const int32_t *typids, const int64_t *vals, const int32
 	}
 	return ggh_jump_consistent_hash((uint64_t) h, nsegs);
 }
+
+/* the same routing for an array of aggregate rows keyed by their group columns: dest[i] = receiving segment of rows[i]
+ * (what evalHashKey does per tuple in the sending Motion's loop, nodeMotion.c:1481) */
+void gg_cdbhash_route_aggrows(const gg_aggrow *rows, int n, const int32_t *typids, int nkeys, int nsegs, int32_t *dest)
+{
+	int r;
+	for (r = 0; r < n; r++)
+		dest[r] = gg_cdbhash_route(typids, rows[r].key, rows[r].keylen, rows[r].keyisnull, nkeys, nsegs);
+}
+

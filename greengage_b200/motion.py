@@ -118,6 +118,61 @@ def gather_small(rows, dst=0, device=None, group=None):
     return [r for sender in per for r in sender]
 
 
+# ---- the same two Motions on raw row buffers (numpy uint8 views of gg_aggrow arrays): no per-row Python objects ----
+
+def route_rows_raw(buf, n, key_typids, nsegs):
+    """dest[i] for the n gg_aggrow records in buf (one C call)"""
+    dest = np.empty(n, dtype=np.int32)
+    if n:
+        t = (C.c_int32 * len(key_typids))(*key_typids)
+        capi.host_lib().gg_cdbhash_route_aggrows(buf.ctypes.data, n, t, len(key_typids), nsegs, dest.ctypes.data)
+    return dest
+
+
+def _allgather_raw(buf, n, device, group):
+    import torch
+    import torch.distributed as dist
+    nsegs = dist.get_world_size(group)
+    rec = np.zeros(8 + SMALL_MOTION_ROWS * ROW_BYTES, dtype=np.uint8)
+    rec[:8].view(np.int64)[0] = n
+    if n <= SMALL_MOTION_ROWS:
+        rec[8:8 + n * ROW_BYTES] = buf[:n * ROW_BYTES]
+    t = _tensor(rec, device)
+    out = torch.empty(nsegs * rec.size, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    host = out.cpu().numpy().reshape(nsegs, rec.size)
+    counts = host[:, :8].copy().view(np.int64).reshape(nsegs)
+    return host, counts
+
+
+def redistribute_small_raw(buf, n, key_typids, device=None, group=None):
+    """redistribute_small on a raw buffer; returns (buffer of the rows routed here, their number)"""
+    import torch.distributed as dist
+    nsegs, rank = dist.get_world_size(group), dist.get_rank(group)
+    host, counts = _allgather_raw(buf, n, device, group)
+    if counts.max() > SMALL_MOTION_ROWS:
+        rows = redistribute_aggrows(_bytes_to_rows(buf[:n * ROW_BYTES]), key_typids, device=device, group=group)
+        return _rows_to_bytes(rows), len(rows)
+    allrows = np.concatenate([host[r, 8:8 + int(counts[r]) * ROW_BYTES] for r in range(nsegs)])
+    tot = int(counts.sum())
+    dest = route_rows_raw(allrows, tot, key_typids, nsegs)
+    keep = np.nonzero(dest == rank)[0]
+    mine = allrows.reshape(tot, ROW_BYTES)[keep].reshape(-1) if tot else allrows
+    return np.ascontiguousarray(mine), len(keep)
+
+
+def gather_small_raw(buf, n, dst=0, device=None, group=None):
+    import torch.distributed as dist
+    nsegs, rank = dist.get_world_size(group), dist.get_rank(group)
+    host, counts = _allgather_raw(buf, n, device, group)
+    if counts.max() > SMALL_MOTION_ROWS:
+        rows = gather_aggrows(_bytes_to_rows(buf[:n * ROW_BYTES]), dst, device=device, group=group)
+        return _rows_to_bytes(rows), len(rows)
+    if rank != dst:
+        return np.zeros(0, dtype=np.uint8), 0
+    return np.concatenate([host[r, 8:8 + int(counts[r]) * ROW_BYTES] for r in range(nsegs)]), int(counts.sum())
+
+
 def gather_aggrows(rows, dst=0, device=None, group=None):
     """Gather Motion (MOTIONTYPE_FIXED to one receiver): rows of all ranks on `dst`, in sender order."""
     import torch

@@ -35,6 +35,13 @@ def _worker(rank, world, port, q):
         motion.SMALL_MOTION_ROWS = old
         final = po.agg_final(tpch.q1_final_agg(part), mine) if mine else []
         gathered = motion.gather_aggrows(final, 0)
+        # the raw-buffer variants bench.py uses: same rows, same order
+        raw = motion._rows_to_bytes(rows)
+        mbuf, nm = motion.redistribute_small_raw(raw, len(rows), keyt)
+        assert nm == len(mine) and mbuf.tobytes() == b"".join(bytes(r) for r in mine)
+        fraw = motion._rows_to_bytes(final)
+        gbuf, ng = motion.gather_small_raw(fraw, len(final), 0)
+        assert ng == len(gathered) and gbuf.tobytes() == b"".join(bytes(r) for r in gathered)
         assert [bytes(r) for r in motion.gather_small(final, 0)] == [bytes(r) for r in gathered]
         if rank == 0:
             out = [(r.key[0], r.key[1], r.agg[7].i, r.agg[0].f[0], r.agg[4].f[0]) for r in gathered]
