@@ -1,0 +1,245 @@
+/*
+ * gg_join.cu — Hash / HashJoin (+ the Agg above): build and probe kernels (interpreter path) and the host pipeline
+ * behind gg_joinagg_* (include/ggb200.h).  The probe side IS a gg_scanagg pipeline (gg_pipeline.h) whose row program
+ * has a per-match piece; everything after the probe (merge, fetch, escalation to the general HashAggregate) is shared.
+ */
+#include "gg_pipeline.h"
+
+using namespace ggd;
+
+/* HashJoin probe side: the same scan front end; every outer row probes the join hash table and each
+ * match runs the per-match piece of the program (join qual, grouping keys, aggregate arguments) */
+template <int MODE>
+__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
+gg_joinprobe_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
+{
+	scanagg_body<MODE, DynPlan, true>(P, prm);
+}
+
+/* Hash node: scan the inner relation into the join hash table */
+__global__ void __launch_bounds__(256, 2)
+gg_joinbuild_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
+{
+	scanagg_body<MODE_BUILD, DynPlan>(P, prm);
+}
+
+/* probe feeding the general HashAggregate (any number of groups) */
+__global__ void __launch_bounds__(256, 2)
+gg_joinhash_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
+{
+	scanagg_body<MODE_HASH, DynPlan, true>(P, prm);
+}
+
+/* upper bound on the inner rows = line pointers of the pages (exact for a freshly loaded relation) */
+__global__ void gg_count_lp_kernel(const uint8_t *pages, uint64_t nblocks, unsigned long long *out)
+{
+	unsigned long long n = 0;
+	for (uint64_t b = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; b < nblocks; b += (uint64_t) gridDim.x * blockDim.x)
+	{
+		const uint32_t w3 = *(const uint32_t *) (pages + b * GG_BLCKSZ + 12);
+		const uint32_t pd_lower = w3 & 0xFFFF;
+		if (pd_lower >= GG_PAGE_HEADER_SIZE && pd_lower <= GG_BLCKSZ) n += (pd_lower - GG_PAGE_HEADER_SIZE) >> 2;
+	}
+	for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(GG_FULL_MASK, n, o);
+	if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
+int gg_probe_kernel_prepare(gg_scanagg *p)
+{
+	if (p->mode == MODE_HASH)
+		GG_CUDA(cudaFuncSetAttribute(gg_joinhash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	else if (p->mode == MODE_PRIV)
+		GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_PRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	else if (p->mode == MODE_TR)
+		GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	else
+		GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+	return GG_OK;
+}
+
+int gg_probe_kernel_launch(gg_scanagg *p, const ScanAggParams &prm, cudaStream_t st)
+{
+	if (p->mode == MODE_HASH) gg_joinhash_kernel<<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else if (p->mode == MODE_PRIV) gg_joinprobe_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else gg_joinprobe_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	GG_CUDA(cudaGetLastError());
+	return GG_OK;
+}
+
+extern "C" {
+
+/* =====================================================================================
+ * HashJoin + Agg (include/ggb200.h gg_joinagg_*)
+ * ===================================================================================== */
+struct gg_joinagg {
+	gg_engine *eng = nullptr;
+	ggp_joinprog jp;
+	gg_scanagg *probe = nullptr;    /* the probe-side pipeline (outer scan -> probe -> Agg) */
+	unsigned long long *ent = nullptr, *d_cnt = nullptr;   /* d_cnt[0] line-pointer count, [1] rows inserted */
+	uint64_t slots = 0;
+	uint64_t rows_built = 0;
+	float build_ms = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
+                      const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out)
+{
+	if (!e || !outer || !inner || !hj || !agg || !pool || !out) return GG_ERR_ARG;
+	*out = nullptr;
+	GG_CUDA(cudaSetDevice(e->device));
+	gg_joinagg *j = new gg_joinagg();
+	j->eng = e;
+	gg_scanagg *p = new gg_scanagg();
+	p->eng = e;
+	p->scan = *outer;
+	p->agg = *agg;
+	p->pool = *pool;
+	p->is_join = true;
+	char msg[256];
+	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &j->jp, p->aggmap, msg, sizeof msg);
+	if (rc != GG_OK) { gg_set_error("%s", msg); delete p; delete j; return rc; }
+	p->prog = j->jp.probe;
+	p->join_probe_pc = j->jp.probe_pc;
+	p->prog.nullable = p->prog.nullable || j->jp.build.nullable;     /* a NULL payload column shows up on the probe side */
+	if (p->prog.nullable) p->prog.priv_ok = 0;
+	rc = scanagg_finish_create(p, &j->probe);
+	if (rc) { delete j; return rc; }
+	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 2 * sizeof(unsigned long long)));
+	GG_CUDA(cudaEventCreate(&j->ev0));
+	GG_CUDA(cudaEventCreate(&j->ev1));
+	GG_CUDA(cudaFuncSetAttribute(gg_joinbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+	*out = j;
+	return GG_OK;
+}
+
+/* MultiExecHash: size the table from the inner relation's line pointers (ExecChooseHashTableSize sizes from the
+ * planner's row estimate, nodeHash.c:463; the pages give a tight bound for free), then one scan inserts. */
+int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, uint64_t nblocks)
+{
+	if (!j || !inner || first_block + nblocks > inner->nblocks) return GG_ERR_ARG;
+	if (inner->rowwords != j->jp.build.outer.rowwords) { gg_set_error("inner relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
+	if (inner->rowwords && (first_block != 0 || nblocks != inner->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
+	gg_engine *e = j->eng;
+	cudaStream_t st = e->stream;
+	GG_CUDA(cudaSetDevice(e->device));
+	if (j->ent) { cudaFree(j->ent); j->ent = nullptr; }
+	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
+	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 2 * sizeof(unsigned long long), st));
+	GG_CUDA(cudaEventRecord(j->ev0, st));
+	unsigned long long nlp = inner->nrows;
+	if (!inner->rowwords)
+	{
+		gg_count_lp_kernel<<<e->sm_count, 256, 0, st>>>(pages, nblocks, j->d_cnt);
+		GG_CUDA(cudaGetLastError());
+		e->launches++;
+		GG_CUDA(cudaMemcpyAsync(&nlp, j->d_cnt, sizeof nlp, cudaMemcpyDeviceToHost, st));
+		GG_CUDA(cudaStreamSynchronize(st));
+	}
+	uint64_t slots = 1024;
+	while (slots < 2 * (uint64_t) nlp) slots <<= 1;
+	if (slots > (1ull << 31)) { gg_set_error("inner relation too large for one hash table (%llu rows)", nlp); return GG_ERR_NOMEM; }
+	JoinTable jt;
+	memset(&jt, 0, sizeof jt);
+	jt.stride = (uint32_t) (1 + j->jp.nkeys + j->jp.npayload);
+	jt.mask = (uint32_t) (slots - 1);
+	jt.nkeys = j->jp.nkeys;
+	jt.npayload = j->jp.npayload;
+	jt.jointype = j->jp.jointype;
+	jt.probe_pc = j->jp.probe_pc;
+	for (int k = 0; k < j->jp.nkeys; k++) jt.keytypes |= (uint32_t) j->jp.keytype[k] << (2 * k);
+	const size_t bytes = (size_t) slots * jt.stride * 8;
+	cudaError_t ce = cudaMalloc((void **) &j->ent, bytes);
+	if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("hash table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
+	GG_CUDA(cudaMemsetAsync(j->ent, 0, bytes, st));
+	jt.ent = j->ent;
+	jt.nbuilt = j->d_cnt + 1;
+	j->slots = slots;
+
+	ScanAggParams prm;
+	memset(&prm, 0, sizeof prm);
+	prm.pages = pages;
+	prm.nblocks = nblocks;
+	prm.errflags = j->probe->d_err;
+	prm.counters = j->probe->d_counters;    /* reset below: the probe's counters describe the outer side */
+	prm.nstage = 2;
+	prm.gcap = 0;
+	const int ncons = 7;
+	prm.scratch_per_warp = ((j->jp.build.outer.ncols * 64 + 15) & ~15) + 16;
+	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
+	prm.jt = jt;
+	prm.nrows = inner->nrows;
+	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
+	{
+		char jmsg[512];
+		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, 256, e->device, jmsg, sizeof jmsg);
+		if (jk)
+		{
+			void *args[] = { (void *) &j->jp.build, (void *) &prm };
+			GG_CUDA(cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st));
+		}
+		else
+			gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
+	}
+	GG_CUDA(cudaGetLastError());
+	e->launches++;
+	GG_CUDA(cudaEventRecord(j->ev1, st));
+	unsigned long long nb = 0;
+	GG_CUDA(cudaMemcpyAsync(&nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaMemsetAsync(j->probe->d_counters, 0, 2 * sizeof(unsigned long long), st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	GG_CUDA(cudaEventElapsedTime(&j->build_ms, j->ev0, j->ev1));
+	j->rows_built = nb;
+	j->probe->jt = jt;
+	return GG_OK;
+}
+
+int gg_joinagg_probe(gg_joinagg *j, gg_relation *outer, uint64_t first_block, uint64_t nblocks)
+{
+	if (!j) return GG_ERR_ARG;
+	return gg_scanagg_run(j->probe, outer, first_block, nblocks);
+}
+
+int gg_joinagg_probe_host(gg_joinagg *j, const void *host_pages, uint64_t nblocks)
+{
+	if (!j) return GG_ERR_ARG;
+	return gg_scanagg_run_host(j->probe, host_pages, nblocks);
+}
+
+int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
+{
+	if (!j) return GG_ERR_ARG;
+	return gg_scanagg_fetch(j->probe, out, outcap, nout, nullptr, rows_joined);
+}
+
+int gg_joinagg_reset(gg_joinagg *j)
+{
+	if (!j) return GG_ERR_ARG;
+	return gg_scanagg_reset(j->probe);
+}
+
+int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms)
+{
+	if (!j) return GG_ERR_ARG;
+	if (rows_built) *rows_built = j->rows_built;
+	if (table_bytes) *table_bytes = j->slots * (uint64_t) (1 + j->jp.nkeys + j->jp.npayload) * 8;
+	if (build_ms) *build_ms = j->build_ms;
+	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
+	return GG_OK;
+}
+
+void gg_joinagg_free(gg_joinagg *j)
+{
+	if (!j) return;
+	cudaSetDevice(j->eng->device);
+	cudaStreamSynchronize(j->eng->stream);
+	if (j->probe) gg_scanagg_free(j->probe);
+	cudaFree(j->ent); cudaFree(j->d_cnt);
+	if (j->ev0) cudaEventDestroy(j->ev0);
+	if (j->ev1) cudaEventDestroy(j->ev1);
+	delete j;
+}
+
+}  /* extern "C" */

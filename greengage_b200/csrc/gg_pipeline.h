@@ -1,0 +1,60 @@
+/*
+ * gg_pipeline.h — the host object behind gg_scanagg (and, as its probe side, gg_joinagg): shared by gg_scanagg.cu and
+ * gg_join.cu.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "gg_scanagg_kernel.cuh"
+#include "gg_engine.h"
+#include "gg_jit.h"
+
+#define GG_MERGE_CAP 1024          /* merged groups the fast path holds per segment */
+#define GG_STREAM_CHUNK_BLOCKS 8192 /* 256 MB staging chunks for gg_scanagg_run_host */
+
+struct gg_scanagg {
+	gg_engine *eng = nullptr;
+	gg_scan scan;
+	gg_agg agg;
+	gg_exprpool pool;
+	ggp_program prog;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	int grid = 0, threads = 0, nstage = 0, scratch_per_warp = 0;
+	int mode = ggd::MODE_PRIV;           /* kernel variant; escalates PRIV -> TR when a run overflows its group capacity */
+	int ctas_per_sm = 2, gcap = 0;
+	uint32_t scratch_off = 0, cnt_off = 0, acc_off = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
+	size_t kev_used = 0;
+	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
+	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
+	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
+	ggd::HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */
+	void *ha_mem = nullptr;
+	uint64_t ha_cap = 0;
+	unsigned long long *d_nout64 = nullptr;
+	ggd::JoinTable jt = {};
+	int join_probe_pc = -1;
+	size_t smem = 0;
+	/* device state */
+	ggp_grec *recs = nullptr;       /* [GG_MERGE_CAP (previous merged)] ++ [grid * GGP_FAST_GROUPS (block records)] */
+	ggp_grec *merged = nullptr;     /* [GG_MERGE_CAP] output of the merge kernel */
+	int *vidx = nullptr, *vmap = nullptr, *d_nout = nullptr;
+	uint32_t *d_err = nullptr;
+	unsigned long long *d_counters = nullptr;
+	int nrecs_total = 0, nrecs_cap = 0;
+	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
+	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; };
+	std::vector<Fed> fed;
+	bool has_state = false;
+	/* host staging for the streamed path */
+	uint8_t *stage[2] = { nullptr, nullptr };
+	cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
+};
+
+/* gg_scanagg.cu */
+int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out);      /* after p->prog / p->aggmap are compiled */
+/* gg_join.cu: the probe-side kernels of a join pipeline (interpreter path) */
+int gg_probe_kernel_prepare(gg_scanagg *p);
+int gg_probe_kernel_launch(gg_scanagg *p, const ggd::ScanAggParams &prm, cudaStream_t st);

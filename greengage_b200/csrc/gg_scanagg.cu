@@ -1,6 +1,7 @@
 /*
  * gg_scanagg.cu — SeqScan -> qual -> Agg: the ahead-of-time kernels (interpreter path), the merge
- * kernel, and the host pipeline behind gg_scanagg_* / gg_agg_final (include/ggb200.h).
+ * kernel, and the host pipeline behind gg_scanagg_* / gg_agg_final (include/ggb200.h).  The same pipeline
+ * object is the probe side of a join (gg_join.cu).
  * The kernel body lives in gg_scanagg_kernel.cuh so that gg_jit.cpp can instantiate it again,
  * specialised for one plan.
  */
@@ -19,28 +20,11 @@ gg_scanagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm
 	scanagg_body<MODE, DynPlan>(P, prm);
 }
 
-/* HashJoin probe side: the same scan front end; every outer row probes the join hash table and each
- * match runs the per-match piece of the program (join qual, grouping keys, aggregate arguments) */
-template <int MODE>
-__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
-gg_joinprobe_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
-{
-	scanagg_body<MODE, DynPlan, true>(P, prm);
-}
-
-/* Hash node: scan the inner relation into the join hash table */
-__global__ void __launch_bounds__(256, 2)
-gg_joinbuild_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
-{
-	scanagg_body<MODE_BUILD, DynPlan>(P, prm);
-}
-
 /* general HashAggregate (any number of groups): scan + probe side variants */
-template <bool JOIN>
 __global__ void __launch_bounds__(256, 2)
 gg_hashagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
-	scanagg_body<MODE_HASH, DynPlan, JOIN>(P, prm);
+	scanagg_body<MODE_HASH, DynPlan>(P, prm);
 }
 
 /* MIN/MAX start from the identity of their comparison; everything else from zero (the table is memset first) */
@@ -87,27 +71,6 @@ __global__ void gg_hashagg_emit_kernel(HashAggTable ha, ggp_grec *out, unsigned 
 		}
 		out[at] = r;
 	}
-}
-
-/* sending Motion: route every qualifying row and write it into its destination's region */
-__global__ void __launch_bounds__(256, 2)
-gg_motion_part_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
-{
-	scanagg_body<MODE_PART, DynPlan>(P, prm);
-}
-
-/* upper bound on the inner rows = line pointers of the pages (exact for a freshly loaded relation) */
-__global__ void gg_count_lp_kernel(const uint8_t *pages, uint64_t nblocks, unsigned long long *out)
-{
-	unsigned long long n = 0;
-	for (uint64_t b = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; b < nblocks; b += (uint64_t) gridDim.x * blockDim.x)
-	{
-		const uint32_t w3 = *(const uint32_t *) (pages + b * GG_BLCKSZ + 12);
-		const uint32_t pd_lower = w3 & 0xFFFF;
-		if (pd_lower >= GG_PAGE_HEADER_SIZE && pd_lower <= GG_BLCKSZ) n += (pd_lower - GG_PAGE_HEADER_SIZE) >> 2;
-	}
-	for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(GG_FULL_MASK, n, o);
-	if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
 }
 
 /* ---- merge kernel: fold group records with equal keys, in record order (deterministic) ----
@@ -298,47 +261,7 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 #include <cstring>
 #include <vector>
 
-#define GG_MERGE_CAP 1024          /* merged groups the fast path holds per segment */
-#define GG_STREAM_CHUNK_BLOCKS 8192 /* 256 MB staging chunks for gg_scanagg_run_host */
-
-struct gg_scanagg {
-	gg_engine *eng = nullptr;
-	gg_scan scan;
-	gg_agg agg;
-	gg_exprpool pool;
-	ggp_program prog;
-	ggp_aggmap aggmap[GG_MAX_AGGS];
-	int grid = 0, threads = 0, nstage = 0, scratch_per_warp = 0;
-	int mode = MODE_PRIV;           /* kernel variant; escalates PRIV -> TR when a run overflows its group capacity */
-	int ctas_per_sm = 2, gcap = 0;
-	uint32_t scratch_off = 0, cnt_off = 0, acc_off = 0;
-	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
-	size_t kev_used = 0;
-	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
-	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
-	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
-	HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */
-	void *ha_mem = nullptr;
-	uint64_t ha_cap = 0;
-	unsigned long long *d_nout64 = nullptr;
-	JoinTable jt = {};
-	int join_probe_pc = -1;
-	size_t smem = 0;
-	/* device state */
-	ggp_grec *recs = nullptr;       /* [GG_MERGE_CAP (previous merged)] ++ [grid * GGP_FAST_GROUPS (block records)] */
-	ggp_grec *merged = nullptr;     /* [GG_MERGE_CAP] output of the merge kernel */
-	int *vidx = nullptr, *vmap = nullptr, *d_nout = nullptr;
-	uint32_t *d_err = nullptr;
-	unsigned long long *d_counters = nullptr;
-	int nrecs_total = 0, nrecs_cap = 0;
-	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
-	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; };
-	std::vector<Fed> fed;
-	bool has_state = false;
-	/* host staging for the streamed path */
-	uint8_t *stage[2] = { nullptr, nullptr };
-	cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
-};
+#include "gg_pipeline.h"
 
 /* launch configuration and shared-memory layout for the current kernel variant:
  *   ring[nstage][32 KB] | full/empty mbarriers | BlockTable | per-warp scratch | (PRIV) counts | (PRIV) sums */
@@ -425,20 +348,10 @@ static int scanagg_configure(gg_scanagg *p)
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
 		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 	}
+	if (p->is_join) return gg_probe_kernel_prepare(p);
 	if (p->mode == MODE_HASH)
 	{
-		if (p->is_join) GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
-		else GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
-		return GG_OK;
-	}
-	if (p->is_join)
-	{
-		if (p->mode == MODE_PRIV)
-			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_PRIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
-		else if (p->mode == MODE_TR)
-			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
-		else
-			GG_CUDA(cudaFuncSetAttribute(gg_joinprobe_kernel<MODE_TRN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+		GG_CUDA(cudaFuncSetAttribute(gg_hashagg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 		return GG_OK;
 	}
 	{
@@ -519,15 +432,28 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	}
 	GG_CUDA(cudaEventRecord(p->kev[p->kev_used].first, st));
 	if (p->is_join && !p->jt.ent) { gg_set_error("probe before build"); return GG_ERR_ARG; }
+	if (p->jit)
+	{
+		/* plan-specialised kernel (any role) */
+		void *args[] = { (void *) &p->prog, (void *) &prm };
+		GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
+	}
+	else if (p->is_join)
+	{
+		int rcj = gg_probe_kernel_launch(p, prm, st);            /* gg_join.cu */
+		if (rcj) return rcj;
+	}
+	else if (p->mode == MODE_HASH)
+		gg_hashagg_kernel<<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else if (p->mode == MODE_PRIV)
+		gg_scanagg_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else if (p->mode == MODE_TR)
+		gg_scanagg_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+	else
+		gg_scanagg_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	if (p->mode == MODE_HASH)
 	{
-		if (p->jit)
-		{
-			void *args[] = { (void *) &p->prog, (void *) &prm };
-			GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
-		}
-		else if (p->is_join) gg_hashagg_kernel<true><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-		else gg_hashagg_kernel<false><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
+		/* the group table lives in HBM across launches: nothing to fold */
 		GG_CUDA(cudaGetLastError());
 		GG_CUDA(cudaEventRecord(p->kev[p->kev_used].second, st));
 		p->kev_used++;
@@ -535,23 +461,6 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 		p->has_state = true;
 		return GG_OK;
 	}
-	if (p->is_join && !p->jit)
-	{
-		if (p->mode == MODE_PRIV) gg_joinprobe_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-		else if (p->mode == MODE_TR) gg_joinprobe_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-		else gg_joinprobe_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-	}
-	else if (p->jit)
-	{
-		void *args[] = { (void *) &p->prog, (void *) &prm };
-		GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
-	}
-	else if (p->mode == MODE_PRIV)
-		gg_scanagg_kernel<MODE_PRIV><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-	else if (p->mode == MODE_TR)
-		gg_scanagg_kernel<MODE_TR><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
-	else
-		gg_scanagg_kernel<MODE_TRN><<<p->grid, p->threads, p->smem, st>>>(p->prog, prm);
 	GG_CUDA(cudaGetLastError());
 	GG_CUDA(cudaEventRecord(p->kev[p->kev_used].second, st));
 	p->kev_used++;
@@ -598,7 +507,7 @@ static int scanagg_adapt_to_pages(gg_scanagg *p, const uint8_t *dev_page, const 
 }
 
 /* the part of pipeline creation that follows plan compilation (p->prog / p->aggmap are set) */
-static int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
+int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 {
 	gg_engine *e = p->eng;
 	const gg_agg *agg = &p->agg;
@@ -1096,261 +1005,6 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 	finalize_rows(&fin, aggmap, &prog, 1, merged.data(), n, out);
 	*nout = n;
 	return GG_OK;
-}
-
-/* =====================================================================================
- * HashJoin + Agg (include/ggb200.h gg_joinagg_*)
- * ===================================================================================== */
-struct gg_joinagg {
-	gg_engine *eng = nullptr;
-	ggp_joinprog jp;
-	gg_scanagg *probe = nullptr;    /* the probe-side pipeline (outer scan -> probe -> Agg) */
-	unsigned long long *ent = nullptr, *d_cnt = nullptr;   /* d_cnt[0] line-pointer count, [1] rows inserted */
-	uint64_t slots = 0;
-	uint64_t rows_built = 0;
-	float build_ms = 0;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
-
-int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
-                      const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out)
-{
-	if (!e || !outer || !inner || !hj || !agg || !pool || !out) return GG_ERR_ARG;
-	*out = nullptr;
-	GG_CUDA(cudaSetDevice(e->device));
-	gg_joinagg *j = new gg_joinagg();
-	j->eng = e;
-	gg_scanagg *p = new gg_scanagg();
-	p->eng = e;
-	p->scan = *outer;
-	p->agg = *agg;
-	p->pool = *pool;
-	p->is_join = true;
-	char msg[256];
-	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &j->jp, p->aggmap, msg, sizeof msg);
-	if (rc != GG_OK) { gg_set_error("%s", msg); delete p; delete j; return rc; }
-	p->prog = j->jp.probe;
-	p->join_probe_pc = j->jp.probe_pc;
-	p->prog.nullable = p->prog.nullable || j->jp.build.nullable;     /* a NULL payload column shows up on the probe side */
-	if (p->prog.nullable) p->prog.priv_ok = 0;
-	rc = scanagg_finish_create(p, &j->probe);
-	if (rc) { delete j; return rc; }
-	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 2 * sizeof(unsigned long long)));
-	GG_CUDA(cudaEventCreate(&j->ev0));
-	GG_CUDA(cudaEventCreate(&j->ev1));
-	GG_CUDA(cudaFuncSetAttribute(gg_joinbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-	*out = j;
-	return GG_OK;
-}
-
-/* MultiExecHash: size the table from the inner relation's line pointers (ExecChooseHashTableSize sizes from the
- * planner's row estimate, nodeHash.c:463; the pages give a tight bound for free), then one scan inserts. */
-int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, uint64_t nblocks)
-{
-	if (!j || !inner || first_block + nblocks > inner->nblocks) return GG_ERR_ARG;
-	if (inner->rowwords != j->jp.build.outer.rowwords) { gg_set_error("inner relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
-	if (inner->rowwords && (first_block != 0 || nblocks != inner->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
-	gg_engine *e = j->eng;
-	cudaStream_t st = e->stream;
-	GG_CUDA(cudaSetDevice(e->device));
-	if (j->ent) { cudaFree(j->ent); j->ent = nullptr; }
-	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
-	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 2 * sizeof(unsigned long long), st));
-	GG_CUDA(cudaEventRecord(j->ev0, st));
-	unsigned long long nlp = inner->nrows;
-	if (!inner->rowwords)
-	{
-		gg_count_lp_kernel<<<e->sm_count, 256, 0, st>>>(pages, nblocks, j->d_cnt);
-		GG_CUDA(cudaGetLastError());
-		e->launches++;
-		GG_CUDA(cudaMemcpyAsync(&nlp, j->d_cnt, sizeof nlp, cudaMemcpyDeviceToHost, st));
-		GG_CUDA(cudaStreamSynchronize(st));
-	}
-	uint64_t slots = 1024;
-	while (slots < 2 * (uint64_t) nlp) slots <<= 1;
-	if (slots > (1ull << 31)) { gg_set_error("inner relation too large for one hash table (%llu rows)", nlp); return GG_ERR_NOMEM; }
-	JoinTable jt;
-	memset(&jt, 0, sizeof jt);
-	jt.stride = (uint32_t) (1 + j->jp.nkeys + j->jp.npayload);
-	jt.mask = (uint32_t) (slots - 1);
-	jt.nkeys = j->jp.nkeys;
-	jt.npayload = j->jp.npayload;
-	jt.jointype = j->jp.jointype;
-	jt.probe_pc = j->jp.probe_pc;
-	for (int k = 0; k < j->jp.nkeys; k++) jt.keytypes |= (uint32_t) j->jp.keytype[k] << (2 * k);
-	const size_t bytes = (size_t) slots * jt.stride * 8;
-	cudaError_t ce = cudaMalloc((void **) &j->ent, bytes);
-	if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("hash table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
-	GG_CUDA(cudaMemsetAsync(j->ent, 0, bytes, st));
-	jt.ent = j->ent;
-	jt.nbuilt = j->d_cnt + 1;
-	j->slots = slots;
-
-	ScanAggParams prm;
-	memset(&prm, 0, sizeof prm);
-	prm.pages = pages;
-	prm.nblocks = nblocks;
-	prm.errflags = j->probe->d_err;
-	prm.counters = j->probe->d_counters;    /* reset below: the probe's counters describe the outer side */
-	prm.nstage = 2;
-	prm.gcap = 0;
-	const int ncons = 7;
-	prm.scratch_per_warp = ((j->jp.build.outer.ncols * 64 + 15) & ~15) + 16;
-	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
-	prm.jt = jt;
-	prm.nrows = inner->nrows;
-	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
-	{
-		char jmsg[512];
-		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, 256, e->device, jmsg, sizeof jmsg);
-		if (jk)
-		{
-			void *args[] = { (void *) &j->jp.build, (void *) &prm };
-			GG_CUDA(cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st));
-		}
-		else
-			gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
-	}
-	GG_CUDA(cudaGetLastError());
-	e->launches++;
-	GG_CUDA(cudaEventRecord(j->ev1, st));
-	unsigned long long nb = 0;
-	GG_CUDA(cudaMemcpyAsync(&nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
-	GG_CUDA(cudaMemsetAsync(j->probe->d_counters, 0, 2 * sizeof(unsigned long long), st));
-	GG_CUDA(cudaStreamSynchronize(st));
-	GG_CUDA(cudaEventElapsedTime(&j->build_ms, j->ev0, j->ev1));
-	j->rows_built = nb;
-	j->probe->jt = jt;
-	return GG_OK;
-}
-
-int gg_joinagg_probe(gg_joinagg *j, gg_relation *outer, uint64_t first_block, uint64_t nblocks)
-{
-	if (!j) return GG_ERR_ARG;
-	return gg_scanagg_run(j->probe, outer, first_block, nblocks);
-}
-
-int gg_joinagg_probe_host(gg_joinagg *j, const void *host_pages, uint64_t nblocks)
-{
-	if (!j) return GG_ERR_ARG;
-	return gg_scanagg_run_host(j->probe, host_pages, nblocks);
-}
-
-int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
-{
-	if (!j) return GG_ERR_ARG;
-	return gg_scanagg_fetch(j->probe, out, outcap, nout, nullptr, rows_joined);
-}
-
-int gg_joinagg_reset(gg_joinagg *j)
-{
-	if (!j) return GG_ERR_ARG;
-	return gg_scanagg_reset(j->probe);
-}
-
-int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms)
-{
-	if (!j) return GG_ERR_ARG;
-	if (rows_built) *rows_built = j->rows_built;
-	if (table_bytes) *table_bytes = j->slots * (uint64_t) (1 + j->jp.nkeys + j->jp.npayload) * 8;
-	if (build_ms) *build_ms = j->build_ms;
-	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
-	return GG_OK;
-}
-
-/* Redistribute Motion, sending side.  out region d = rows [d * cap, d * cap + counts[d]) with cap = out_cap_rows / nsegs. */
-int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
-                        const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
-                        int nsegs, gg_relation *r, uint64_t first_block, uint64_t nblocks,
-                        void *device_out_rows, uint64_t out_cap_rows,
-                        uint64_t *host_counts, uint64_t *host_offsets)
-{
-	if (!e || !scan || !pool || !hashkeys || !payload || !r || !host_counts || nsegs < 1 || nsegs > 1024 ||
-	    first_block + nblocks > r->nblocks || (!device_out_rows && out_cap_rows))
-		return GG_ERR_ARG;
-	GG_CUDA(cudaSetDevice(e->device));
-	static ggp_program prog;              /* 3 KB: kept off the stack */
-	uint8_t hashtype[GG_MAX_KEYS] = { 0 };
-	char msg[256];
-	int rc = ggp_compile_motion(scan, pool, hashkeys, nkeys, payload, npayload, &prog, hashtype, msg, sizeof msg);
-	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
-	if (r->rowwords != prog.outer.rowwords) { gg_set_error("relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
-	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
-	cudaStream_t st = e->stream;
-	unsigned long long *d_state = nullptr;          /* [nsegs] cursors, [1] error flags, [2] counters */
-	GG_CUDA(cudaMalloc((void **) &d_state, (size_t) (nsegs + 4) * 8));
-	cudaError_t ce = cudaMemsetAsync(d_state, 0, (size_t) (nsegs + 4) * 8, st);
-	ScanAggParams prm;
-	memset(&prm, 0, sizeof prm);
-	prm.pages = r->pages + first_block * GG_BLCKSZ;
-	prm.nblocks = nblocks;
-	prm.nrows = r->nrows;
-	prm.errflags = (uint32_t *) (d_state + nsegs);
-	prm.counters = d_state + nsegs + 1;
-	prm.nstage = 2;
-	const int ncons = 7;
-	prm.scratch_per_warp = ((prog.outer.ncols * 64 + 15) & ~15) + 16;
-	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
-	prm.mo.rows = (unsigned long long *) device_out_rows;
-	prm.mo.cursor = d_state;
-	prm.mo.cap = (out_cap_rows / (uint64_t) nsegs) & ~1ull;      /* even: every region starts 16-byte aligned */
-	prm.mo.nsegs = nsegs;
-	prm.mo.rowwords = 1 + npayload;
-	for (int k = 0; k < nkeys; k++) prm.mo.hashtypes |= (uint32_t) hashtype[k] << (4 * k);
-	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
-	if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gg_motion_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_start, st);
-	if (ce == cudaSuccess)
-	{
-		char jmsg[512];
-		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, 256, e->device, jmsg, sizeof jmsg);
-		if (jk)
-		{
-			void *args[] = { (void *) &prog, (void *) &prm };
-			ce = cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-			if (ce == cudaSuccess) ce = cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st);
-		}
-		else
-		{
-			gg_motion_part_kernel<<<e->sm_count * 2, 256, smem, st>>>(prog, prm);
-			ce = cudaGetLastError();
-		}
-		e->launches++;
-	}
-	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_stop, st);
-	e->timed = true;
-	std::vector<unsigned long long> host((size_t) nsegs + 4);
-	if (ce == cudaSuccess) ce = cudaMemcpyAsync(host.data(), d_state, (size_t) (nsegs + 4) * 8, cudaMemcpyDeviceToHost, st);
-	if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-	cudaFree(d_state);
-	if (ce != cudaSuccess) return gg_cuda_fail(ce, "gg_motion_partition");
-	uint32_t flags = (uint32_t) host[(size_t) nsegs];
-	for (int d = 0; d < nsegs; d++)
-	{
-		host_counts[d] = host[(size_t) d] < prm.mo.cap ? host[(size_t) d] : prm.mo.cap;
-		if (host_offsets) host_offsets[d] = (uint64_t) d * prm.mo.cap;
-	}
-	if (flags & GGP_EF_TABLE_FULL)
-	{
-		unsigned long long need = 0;
-		for (int d = 0; d < nsegs; d++) if (host[(size_t) d] > need) need = host[(size_t) d];
-		gg_set_error("motion output region too small: a destination receives %llu rows, capacity %llu", need, (unsigned long long) prm.mo.cap);
-		return GG_ERR_NOMEM;
-	}
-	return gg_errflags_to_code(flags);
-}
-
-void gg_joinagg_free(gg_joinagg *j)
-{
-	if (!j) return;
-	cudaSetDevice(j->eng->device);
-	cudaStreamSynchronize(j->eng->stream);
-	if (j->probe) gg_scanagg_free(j->probe);
-	cudaFree(j->ent); cudaFree(j->d_cnt);
-	if (j->ev0) cudaEventDestroy(j->ev0);
-	if (j->ev1) cudaEventDestroy(j->ev1);
-	delete j;
 }
 
 }  /* extern "C" */
