@@ -37,7 +37,7 @@ AGG_MIN_INT8, AGG_MIN_INT4, AGG_MIN_FLOAT8, AGG_MIN_DATE = 2131, 2132, 2136, 213
 AGG_COUNT_ANY, AGG_COUNT_STAR = 2147, 2803
 
 AGGSTAGE_NORMAL, AGGSTAGE_PARTIAL, AGGSTAGE_FINAL = 0, 1, 3
-JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 4, 5
+JOIN_INNER, JOIN_LEFT, JOIN_FULL, JOIN_RIGHT, JOIN_SEMI, JOIN_ANTI, JOIN_LASJ_NOTIN = 0, 1, 2, 3, 4, 5, 6
 E_VAR, E_CONST, E_FUNC, E_AND, E_OR, E_NOT, E_ISNULL, E_ISNOTNULL = 1, 2, 3, 4, 5, 6, 7, 8
 
 TAB_LINEITEM_WIDE, TAB_LINEITEM_NARROW, TAB_ORDERS = 1, 2, 3

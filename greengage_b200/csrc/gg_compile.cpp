@@ -689,8 +689,17 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	c.pool = pool; c.err = err; c.errlen = errlen;
 	if (err && errlen) err[0] = 0;
 	if (hj->nkeys < 1 || hj->nkeys > 2) { fail(c, "hash join with %d keys not supported (1 or 2)", hj->nkeys); return GG_ERR_UNSUPPORTED; }
-	if (!(hj->jointype == GG_JOIN_INNER || hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_SEMI || hj->jointype == GG_JOIN_ANTI))
-	{ fail(c, "join type %d not supported", hj->jointype); return GG_ERR_UNSUPPORTED; }
+	switch (hj->jointype)
+	{
+		case GG_JOIN_INNER: case GG_JOIN_LEFT: case GG_JOIN_FULL: case GG_JOIN_RIGHT:
+		case GG_JOIN_SEMI: case GG_JOIN_ANTI: case GG_JOIN_LASJ_NOTIN:
+			break;
+		default:
+			fail(c, "join type %d not supported", hj->jointype);
+			return GG_ERR_UNSUPPORTED;
+	}
+	/* a side that can come back null-extended makes every expression above the join nullable */
+	const bool nullext = hj->jointype != GG_JOIN_INNER && hj->jointype != GG_JOIN_SEMI;
 	jp->nkeys = hj->nkeys;
 	jp->jointype = hj->jointype;
 
@@ -728,10 +737,10 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 		ggp_op *o = gen_value(c, hj->joinqual);
 		if (!c.failed) o->flags |= GGP_F_FILTER;
 	}
-	if (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI) jp->probe.nullable = 1;   /* null-extended inner side */
+	if (nullext) jp->probe.nullable = 1;
 	if (!c.failed) compile_agg_part(c, agg, aggmap);
 	jp->npayload = innerside.ncols;
-	if (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI) { jp->probe.nullable = 1; jp->probe.priv_ok = 0; }
+	if (nullext) { jp->probe.nullable = 1; jp->probe.priv_ok = 0; }
 
 	/* ---- build program: inner tuple scanned; keys, then the payload columns in slot order ---- */
 	Ctx b;

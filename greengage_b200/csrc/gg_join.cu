@@ -44,6 +44,13 @@ __global__ void gg_count_lp_kernel(const uint8_t *pages, uint64_t nblocks, unsig
 	if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
 }
 
+/* ExecReScanHashJoin with the table kept: forget which entries matched */
+__global__ void gg_clear_matched_kernel(unsigned long long *ent, uint64_t slots, uint32_t stride)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < slots; i += (uint64_t) gridDim.x * blockDim.x)
+		ent[i * stride] &= ~GG_HT_MATCHED;
+}
+
 int gg_probe_kernel_prepare(gg_scanagg *p)
 {
 	if (p->mode == MODE_HASH)
@@ -78,7 +85,9 @@ struct gg_joinagg {
 	gg_scanagg *probe = nullptr;    /* the probe-side pipeline (outer scan -> probe -> Agg) */
 	unsigned long long *ent = nullptr, *d_cnt = nullptr;   /* d_cnt[0] line-pointer count, [1] rows inserted */
 	uint64_t slots = 0;
-	uint64_t rows_built = 0;
+	uint64_t rows_built = 0, null_keys = 0;
+	bool filled = false;            /* right / full join: the unmatched inner rows have been emitted */
+	bool lasj_empty = false;        /* LASJ_NOTIN met a NULL inner key: the result is empty */
 	float build_ms = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -106,7 +115,7 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 	if (p->prog.nullable) p->prog.priv_ok = 0;
 	rc = scanagg_finish_create(p, &j->probe);
 	if (rc) { delete j; return rc; }
-	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 2 * sizeof(unsigned long long)));
+	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 3 * sizeof(unsigned long long)));
 	GG_CUDA(cudaEventCreate(&j->ev0));
 	GG_CUDA(cudaEventCreate(&j->ev1));
 	GG_CUDA(cudaFuncSetAttribute(gg_joinbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -126,7 +135,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	GG_CUDA(cudaSetDevice(e->device));
 	if (j->ent) { cudaFree(j->ent); j->ent = nullptr; }
 	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
-	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 2 * sizeof(unsigned long long), st));
+	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 3 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaEventRecord(j->ev0, st));
 	unsigned long long nlp = inner->nrows;
 	if (!inner->rowwords)
@@ -148,9 +157,10 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	jt.npayload = j->jp.npayload;
 	jt.jointype = j->jp.jointype;
 	jt.probe_pc = j->jp.probe_pc;
+	jt.keepnull = jt.mark_matched = (j->jp.jointype == GG_JOIN_RIGHT || j->jp.jointype == GG_JOIN_FULL);
 	for (int k = 0; k < j->jp.nkeys; k++) jt.keytypes |= (uint32_t) j->jp.keytype[k] << (2 * k);
 	const size_t bytes = (size_t) slots * jt.stride * 8;
-	cudaError_t ce = cudaMalloc((void **) &j->ent, bytes);
+	cudaError_t ce = cudaMalloc((void **) &j->ent, bytes + 64);      /* slack: the fill-inner pass reads it in 16-byte multiples */
 	if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("hash table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
 	GG_CUDA(cudaMemsetAsync(j->ent, 0, bytes, st));
 	jt.ent = j->ent;
@@ -186,12 +196,16 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	GG_CUDA(cudaGetLastError());
 	e->launches++;
 	GG_CUDA(cudaEventRecord(j->ev1, st));
-	unsigned long long nb = 0;
-	GG_CUDA(cudaMemcpyAsync(&nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
+	unsigned long long nb[2] = { 0, 0 };
+	GG_CUDA(cudaMemcpyAsync(nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
 	GG_CUDA(cudaMemsetAsync(j->probe->d_counters, 0, 2 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaStreamSynchronize(st));
 	GG_CUDA(cudaEventElapsedTime(&j->build_ms, j->ev0, j->ev1));
-	j->rows_built = nb;
+	j->rows_built = nb[0];
+	j->null_keys = nb[1];
+	jt.inner_empty = nb[0] == 0;
+	j->lasj_empty = j->jp.jointype == GG_JOIN_LASJ_NOTIN && nb[1] > 0;      /* nodeHashjoin.c:238 */
+	j->filled = false;
 	j->probe->jt = jt;
 	return GG_OK;
 }
@@ -199,24 +213,50 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 int gg_joinagg_probe(gg_joinagg *j, gg_relation *outer, uint64_t first_block, uint64_t nblocks)
 {
 	if (!j) return GG_ERR_ARG;
+	if (j->filled) { gg_set_error("the unmatched inner rows were already emitted: reset before probing again"); return GG_ERR_ARG; }
+	if (j->lasj_empty) return GG_OK;          /* x NOT IN (.., NULL, ..): no outer row can qualify */
 	return gg_scanagg_run(j->probe, outer, first_block, nblocks);
 }
 
 int gg_joinagg_probe_host(gg_joinagg *j, const void *host_pages, uint64_t nblocks)
 {
 	if (!j) return GG_ERR_ARG;
+	if (j->filled) { gg_set_error("the unmatched inner rows were already emitted: reset before probing again"); return GG_ERR_ARG; }
+	if (j->lasj_empty) return GG_OK;
 	return gg_scanagg_run_host(j->probe, host_pages, nblocks);
 }
 
 int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
 {
 	if (!j) return GG_ERR_ARG;
+	if (j->probe->jt.mark_matched && !j->filled && j->ent)
+	{
+		/* HJ_FILL_INNER_TUPLES: every outer row has been through the probe; what is still unmatched in the table comes
+		 * out with a null-extended outer side.  The table is scanned by the probe kernel itself, as rows of entries. */
+		gg_scanagg *p = j->probe;
+		const JoinTable &jt = p->jt;
+		const uint64_t per_chunk = (GG_BLCKSZ / (8ull * jt.stride)) & ~1ull;
+		const uint64_t chunks = (j->slots + per_chunk - 1) / per_chunk;
+		GG_CUDA(cudaSetDevice(j->eng->device));
+		int rc = scanagg_launch(p, (const uint8_t *) j->ent, chunks, j->eng->stream, j->slots, true);
+		if (rc) return rc;
+		p->fed.push_back({ (const uint8_t *) j->ent, nullptr, chunks, j->slots, true });
+		j->filled = true;
+	}
 	return gg_scanagg_fetch(j->probe, out, outcap, nout, nullptr, rows_joined);
 }
 
 int gg_joinagg_reset(gg_joinagg *j)
 {
 	if (!j) return GG_ERR_ARG;
+	if (j->probe->jt.mark_matched && j->ent)
+	{
+		GG_CUDA(cudaSetDevice(j->eng->device));
+		gg_clear_matched_kernel<<<j->eng->sm_count * 4, 256, 0, j->eng->stream>>>(j->ent, j->slots, j->probe->jt.stride);
+		GG_CUDA(cudaGetLastError());
+		j->eng->launches++;
+	}
+	j->filled = false;
 	return gg_scanagg_reset(j->probe);
 }
 

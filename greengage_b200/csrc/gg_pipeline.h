@@ -45,7 +45,7 @@ struct gg_scanagg {
 	unsigned long long *d_counters = nullptr;
 	int nrecs_total = 0, nrecs_cap = 0;
 	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
-	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; };
+	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; };
 	std::vector<Fed> fed;
 	bool has_state = false;
 	/* host staging for the streamed path */
@@ -55,6 +55,8 @@ struct gg_scanagg {
 
 /* gg_scanagg.cu */
 int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out);      /* after p->prog / p->aggmap are compiled */
+/* one launch of the pipeline's kernel over device pages (fill_inner: the HJ_FILL_INNER_TUPLES pass of a right/full join) */
+int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0, bool fill_inner = false);
 /* gg_join.cu: the probe-side kernels of a join pipeline (interpreter path) */
 int gg_probe_kernel_prepare(gg_scanagg *p);
 int gg_probe_kernel_launch(gg_scanagg *p, const ggd::ScanAggParams &prm, cudaStream_t st);

@@ -404,7 +404,7 @@ static int hashagg_alloc(gg_scanagg *p, uint64_t cap)
 	return GG_OK;
 }
 
-static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0)
+int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows, bool fill_inner)
 {
 	gg_engine *e = p->eng;
 	ScanAggParams prm;
@@ -422,6 +422,7 @@ static int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblo
 	prm.jt = p->jt;
 	memset(&prm.mo, 0, sizeof prm.mo);
 	prm.nrows = nrows;
+	prm.fill_inner = fill_inner ? 1 : 0;
 	prm.ha = p->ha;
 	if (p->kev_used == p->kev.size())
 	{
@@ -607,7 +608,7 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
 	rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream, r->nrows);
 	if (rc) return rc;
-	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows });
+	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows, false });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
@@ -625,7 +626,7 @@ int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 	int rc = nblocks ? scanagg_adapt_to_pages(p, nullptr, host_pages) : GG_OK;
 	if (rc) return rc;
 	rc = scanagg_stream_host(p, host_pages, nblocks);
-	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0 });
+	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0, false });
 	return rc;
 }
 
@@ -769,7 +770,7 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 			if (rc2) return rc2;
 			for (const auto &f : replay)
 			{
-				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows) : scanagg_stream_host(p, f.host, f.nblocks);
+				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
 				if (rc2) return rc2;
 			}
 			p->fed = replay;
@@ -825,7 +826,7 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 		if (rc2) return rc2;
 		for (const auto &f : replay)
 		{
-			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows) : scanagg_stream_host(p, f.host, f.nblocks);
+			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
 			if (rc2) return rc2;
 		}
 		p->fed = replay;

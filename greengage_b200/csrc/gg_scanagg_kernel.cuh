@@ -72,7 +72,9 @@ struct MotionOut {
 
 /* Join hash table (Hash / HashJoin, nodeHash.c:88-176,906-1222): open addressing, linear probing, one
  * slot per inner row (duplicate keys simply occupy successive slots), entries of `stride` 64-bit words:
- *   [0]            bit 63 occupied | bits 32..39 payload-NULL mask | bits 0..31 hash
+ *   [0]            bit 63 occupied | bit 62 NULL join key (kept for right/full joins only: never matches) |
+ *                  bit 61 matched (MemTupleSetMatch, nodeHashjoin.c:386; right/full joins) |
+ *                  bits 32..39 payload-NULL mask | bits 0..31 hash
  *   [1 .. nkeys]   join keys, normalised so that bitwise equality is SQL equality
  *   [1+nkeys ..]   payload = the inner columns referenced above the join, loaded by the build program
  * Sized by the host to >= 2x the inner row count, so a probe always ends at an empty slot. */
@@ -84,9 +86,14 @@ struct JoinTable {
 	int jointype;                         /* gg_jointype */
 	int probe_pc;                         /* probe program: first op of the per-match segment */
 	uint32_t keytypes;                    /* join keys, 2 bits each */
-	unsigned long long *nbuilt;           /* rows inserted */
+	unsigned long long *nbuilt;           /* [0] rows inserted, [1] inner rows with a NULL join key */
+	int keepnull;                         /* right / full join: rows with NULL keys are inserted too (nodeHashjoin.c:209) */
+	int mark_matched;                     /* right / full join: a qualifying match marks the entry */
+	int inner_empty;                      /* LASJ_NOTIN needs to know (nodeHashjoin.c:361) */
 };
 #define GG_HT_OCCUPIED 0x8000000000000000ull
+#define GG_HT_NULLKEY  0x4000000000000000ull
+#define GG_HT_MATCHED  0x2000000000000000ull
 
 __device__ __forceinline__ uint64_t join_hash(uint64_t k0, uint64_t k1)
 {
@@ -110,6 +117,8 @@ struct ScanAggParams {
 	MotionOut mo;                         /* MODE_PART only */
 	HashAggTable ha;                      /* MODE_HASH only */
 	uint64_t nrows;                       /* datum-row input: total rows (pages/nblocks then describe 32 KB chunks of rows) */
+	int fill_inner;                       /* join probe kernels: this launch is HJ_FILL_INNER_TUPLES — the "pages" are the hash
+	                                       * table itself, every unmatched entry is emitted with a null-extended outer side */
 };
 
 struct BlockTable {                       /* per-block group table in shared memory */
@@ -293,9 +302,14 @@ struct BuildSink {
 	}
 	__device__ __forceinline__ bool group(bool live)
 	{
-		if (!live || knull) return false;
+		if (!live) return false;
+		if (knull)
+		{
+			atomicAdd(jt.nbuilt + 1, 1ull);
+			if (!jt.keepnull) return false;
+		}
 		const uint64_t h = join_hash(k0, k1);
-		const unsigned long long hdr = GG_HT_OCCUPIED | (uint32_t) h;
+		const unsigned long long hdr = GG_HT_OCCUPIED | (knull ? GG_HT_NULLKEY : 0ull) | (uint32_t) h;
 		uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
 		for (uint32_t tries = 0; tries <= jt.mask; tries++)
 		{
@@ -593,7 +607,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	__syncthreads();
 
 	/* input format: heap pages, or 32 KB chunks of fixed-width datum rows (what a receiving Motion delivers) */
-	const uint32_t rowwords = (uint32_t) PL::rowwords(P);
+	/* HJ_FILL_INNER_TUPLES of a right / full join: the input of this launch is the hash table itself, scanned as rows
+	 * of `stride` words */
+	const bool fill_inner = JOIN && prm.fill_inner != 0;
+	const uint32_t rowwords = fill_inner ? prm.jt.stride : (uint32_t) PL::rowwords(P);
 	const uint32_t rowbytes = rowwords * 8;
 	const uint32_t rows_per_chunk = rowwords ? ((GG_BLCKSZ / rowbytes) & ~1u) : 0;
 	const uint32_t chunk_bytes = rowwords ? rows_per_chunk * rowbytes : GG_BLCKSZ;
@@ -721,7 +738,19 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				const int idx = c * 32 + lane;
 				bool live = false;
 				uint32_t tup = pg, tuplen = 64;
-				if (rowwords)
+				unsigned long long fill_hdr = 0;
+				if (JOIN && fill_inner)
+				{
+					/* a table entry: emitted iff occupied and never matched; the outer side is all NULL */
+					live = idx < nitems;
+					const uint32_t rp = pg + (live ? (uint32_t) idx * rowbytes : 0);
+					fill_hdr = lds64(rp);
+					live = live && (fill_hdr & GG_HT_OCCUPIED) && !(fill_hdr & GG_HT_MATCHED);
+					X.fast = true;
+					X.tv.tp = pg;
+					X.tv.colnull = 0xFFFFFFFFu;
+				}
+				else if (rowwords)
 				{
 					/* datum row: NULL mask word, then one word per column at constant offsets */
 					live = idx < nitems;
@@ -818,6 +847,23 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					PL::template run<NULLABLE>(X, live, err, sink);
 					if constexpr (TRMODE) tr_accumulate();
 				}
+				else if (fill_inner)
+				{
+					/* ExecScanHashTableForUnmatched (nodeHashjoin.c:460-490): the per-match piece runs once for the entry,
+					 * outer columns NULL, the join qual not applied */
+					const JoinTable &jt = prm.jt;
+					const uint64_t entry = (first + (uint64_t) it * stride) * rows_per_chunk + (uint64_t) (live ? idx : 0);
+					MachState M2;
+					M2.reset(live);
+					M2.tnull = 0xF;                           /* whatever the first piece would have kept in temporaries is NULL */
+					X.ipay = (const uint64_t *) (jt.ent + entry * jt.stride + 1 + jt.nkeys);
+					X.ipaynull = (uint32_t) (fill_hdr >> 32) & 0xFFu;
+					sink.begin_row();
+					sink.jq = false; sink.nullext = true; sink.suppress = false;
+					MatchSink<decltype(sink)> ms = { sink };
+					PL::template run_range<NULLABLE>(X, M2, jt.probe_pc, GGP_MAX_CODE, err, ms);
+					if constexpr (TRMODE) tr_accumulate();
+				}
 				else
 				{
 					/* ExecHashJoin_guts (nodeHashjoin.c:78-509): HJ_NEED_NEW_OUTER = the first program piece (outer
@@ -825,8 +871,10 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					 * qual, grouping keys, aggregate arguments) with the matched entry's payload as inner columns;
 					 * HJ_FILL_OUTER_TUPLE = the null-extended run for LEFT / ANTI */
 					const JoinTable &jt = prm.jt;
-					const bool fill_outer = jt.jointype == GG_JOIN_LEFT || jt.jointype == GG_JOIN_ANTI;
-					const bool single = jt.jointype == GG_JOIN_SEMI || jt.jointype == GG_JOIN_ANTI;
+					const bool lasj = jt.jointype == GG_JOIN_LASJ_NOTIN;
+					const bool anti = jt.jointype == GG_JOIN_ANTI || lasj;
+					const bool fill_outer = jt.jointype == GG_JOIN_LEFT || jt.jointype == GG_JOIN_FULL || anti;
+					const bool single = jt.jointype == GG_JOIN_SEMI || anti;
 					MachState M1;
 					M1.reset(live);
 					const uint32_t gkt = sink.keytypes;
@@ -836,6 +884,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					const uint64_t jk0 = sink.k0, jk1 = sink.k1;
 					const bool jknull = sink.knull != 0;
 					bool pending = M1.live && (fill_outer || !jknull);     /* a NULL key matches nothing (nodeHash.c:1070) */
+					if (lasj && jknull && !jt.inner_empty) pending = false;     /* NULL NOT IN (non-empty set): dropped (nodeHashjoin.c:361) */
 					bool probing = pending && !jknull;
 					bool matched = false;
 					const uint64_t h = join_hash(jk0, jk1);
@@ -856,7 +905,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 								const unsigned long long ek1 = jt.nkeys > 1 ? __ldg(e + 2) : 0ull;
 								slot = (slot + 1) & jt.mask;
 								if (hdr == 0) { probing = false; break; }
-								if ((uint32_t) hdr == (uint32_t) h && ek0 == jk0 && (jt.nkeys < 2 || ek1 == jk1)) { have = true; break; }
+								if ((uint32_t) hdr == (uint32_t) h && !(hdr & GG_HT_NULLKEY) && ek0 == jk0 && (jt.nkeys < 2 || ek1 == jk1)) { have = true; break; }
 							}
 						}
 						bool nullext = false;
@@ -868,12 +917,13 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 						X.ipay = (const uint64_t *) (e + 1 + jt.nkeys);
 						X.ipaynull = nullext ? 0xFFFFFFFFu : (uint32_t) (hdr >> 32) & 0xFFu;
 						sink.begin_row();
-						sink.jq = have; sink.nullext = nullext; sink.suppress = have && jt.jointype == GG_JOIN_ANTI;
+						sink.jq = have; sink.nullext = nullext; sink.suppress = have && anti;
 						MatchSink<decltype(sink)> ms = { sink };
 						PL::template run_range<NULLABLE>(X, M2, jt.probe_pc, GGP_MAX_CODE, err, ms);
 						if (have && sink.jq)
 						{
 							matched = true;
+							if (jt.mark_matched && !(hdr & GG_HT_MATCHED)) atomicOr((unsigned long long *) e, GG_HT_MATCHED);
 							if (single) { probing = false; pending = false; }
 						}
 						if constexpr (TRMODE) tr_accumulate();

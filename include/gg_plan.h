@@ -230,7 +230,8 @@ typedef struct gg_agg {             /* Agg (AGG_HASHED or AGG_PLAIN when numCols
 } gg_agg;
 
 enum gg_jointype {                  /* nodes/nodes.h JoinType */
-	GG_JOIN_INNER = 0, GG_JOIN_LEFT = 1, GG_JOIN_SEMI = 4, GG_JOIN_ANTI = 5
+	GG_JOIN_INNER = 0, GG_JOIN_LEFT = 1, GG_JOIN_FULL = 2, GG_JOIN_RIGHT = 3, GG_JOIN_SEMI = 4, GG_JOIN_ANTI = 5,
+	GG_JOIN_LASJ_NOTIN = 6              /* NOT IN: any NULL inner key empties the result (nodeHashjoin.c:220-239,356-368) */
 };
 
 typedef struct gg_hashjoin {        /* HashJoin + Hash (nodeHashjoin.c, nodeHash.c) */

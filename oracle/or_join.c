@@ -11,7 +11,7 @@
  *   ExecHashJoinOuterGetTuple             src/backend/executor/nodeHashjoin.c:801-897
  *
  * Single batch only: multi-batch spill (nodeHash.c:713, nodeHashjoin.c:906) is
- * out of scope.  Join types: inner, left, semi, anti.
+ * out of scope.  Join types: inner, left, right, full, semi, anti, LASJ_NOTIN.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -25,6 +25,8 @@ typedef struct hj_tuple {				/* HashJoinTupleData {next, hashvalue} + tuple, has
 	uint32_t hashvalue;
 	const uint8_t *tuple;
 	uint64_t tid;
+	int matched;					/* MemTupleSetMatch (HEAP_TUPLE_HAS_MATCH), nodeHashjoin.c:386 */
+	int nullkey;					/* kept only for right/full joins: never matches */
 } hj_tuple;
 
 typedef struct hj_table {
@@ -137,6 +139,11 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 	or_row row, irow;
 	int rc = 0;
 	uint32_t nb;
+	const int fill_inner = (hj->jointype == GG_JOIN_RIGHT || hj->jointype == GG_JOIN_FULL);	/* HJ_FILL_INNER */
+	const int fill_outer = (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_FULL ||
+							hj->jointype == GG_JOIN_ANTI || hj->jointype == GG_JOIN_LASJ_NOTIN);
+	const int lasj = hj->jointype == GG_JOIN_LASJ_NOTIN;
+	int inner_has_nullkey = 0;
 
 	/* ---- HJ_BUILD_HASHTABLE: MultiExecHash drains the inner side ---- */
 	memset(&tab, 0, sizeof tab);
@@ -161,7 +168,13 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 		if ((rc = hash_keys(pool, hj->innerkey, hj->nkeys, &row, 0, 0, &h, &ok)) != 0)
 			goto done;
 		if (!ok)
-			continue;					/* NULL key never matches a strict operator (nodeHash.c:1070-1077) */
+		{
+			/* NULL key never matches a strict operator (nodeHash.c:1070-1077): dropped, unless a right/full
+			 * join must still emit the row (keepNulls, nodeHashjoin.c:209), or LASJ_NOTIN gives up (:223,238) */
+			inner_has_nullkey = 1;
+			if (!fill_inner)
+				continue;
+		}
 		if (tab.ntuples == tab.cap)
 		{
 			tab.cap *= 2;
@@ -170,6 +183,8 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 		tab.arena[tab.ntuples].hashvalue = h;
 		tab.arena[tab.ntuples].tuple = tup;
 		tab.arena[tab.ntuples].tid = tid;
+		tab.arena[tab.ntuples].matched = 0;
+		tab.arena[tab.ntuples].nullkey = !ok;
 		tab.ntuples++;
 	}
 	if (hs->error) { rc = hs->error; goto done; }
@@ -193,13 +208,16 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 		}
 	}
 
+	if (lasj && inner_has_nullkey)
+		goto done;						/* x NOT IN (..., NULL, ...) is never true */
+
 	/* ---- HJ_NEED_NEW_OUTER / HJ_SCAN_BUCKET ---- */
 	or_scan_begin(hs, &outer->desc, outer_pages, outer_nblocks);
 	while ((tup = or_scan_next(hs, &tid)) != NULL)
 	{
 		uint32_t h;
 		int ok, matched = 0;
-		int keep_nulls = (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI);
+		int keep_nulls = fill_outer;
 		hj_tuple *t;
 
 		or_row_store(&row, &outer->desc, tup);
@@ -216,11 +234,27 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 			goto done;
 		if (!ok)
 			continue;
+		if (lasj && tab.ntuples > 0)
+		{
+			/* OPT-3325: a NULL outer key against a non-empty inner side is dropped (nodeHashjoin.c:356-368) */
+			int k, anynull = 0;
+
+			for (k = 0; k < hj->nkeys; k++)
+			{
+				or_datum d;
+
+				if ((rc = or_eval(pool, hj->outerkey[k], &row, NULL, &d)) != 0)
+					goto done;
+				anynull |= d.isnull;
+			}
+			if (anynull)
+				continue;
+		}
 		for (t = tab.buckets[h & (nb - 1)]; t; t = t->next)
 		{
 			int m;
 
-			if (t->hashvalue != h)
+			if (t->hashvalue != h || t->nullkey)
 				continue;
 			or_row_store(&irow, &inner->desc, t->tuple);
 			if ((rc = keys_match(pool, hj, &row, &irow, &m)) != 0)
@@ -237,19 +271,39 @@ run_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, cons
 					continue;
 			}
 			matched = 1;
-			if (hj->jointype == GG_JOIN_ANTI)
+			t->matched = 1;
+			if (hj->jointype == GG_JOIN_ANTI || lasj)
 				break;
 			if ((rc = emit(ctx, &row, tid, &irow, t->tid)) != 0)
 				goto done;
 			if (hj->jointype == GG_JOIN_SEMI)
 				break;
 		}
-		if (!matched && (hj->jointype == GG_JOIN_LEFT || hj->jointype == GG_JOIN_ANTI))
+		if (!matched && fill_outer)
 			if ((rc = emit(ctx, &row, tid, NULL, (uint64_t) -1)) != 0)	/* HJ_FILL_OUTER_TUPLE */
 				goto done;
 	}
 	if (hs->error)
+	{
 		rc = hs->error;
+		goto done;
+	}
+	if (fill_inner)
+	{
+		/* HJ_FILL_INNER_TUPLES: ExecScanHashTableForUnmatched, nodeHashjoin.c:460-490 */
+		uint64_t i;
+
+		for (i = 0; i < tab.ntuples; i++)
+		{
+			hj_tuple *u = &tab.arena[i];
+
+			if (u->matched)
+				continue;
+			or_row_store(&irow, &inner->desc, u->tuple);
+			if ((rc = emit(ctx, NULL, (uint64_t) -1, &irow, u->tid)) != 0)
+				goto done;
+		}
+	}
 done:
 	free(tab.arena);
 	free(tab.buckets);

@@ -93,7 +93,7 @@ def test_join_programs_shape():
 
 def test_join_shapes_outside_the_subset_are_refused():
     outer, inner, hj, agg, pool = tpch.join_plan(kind="count")
-    hj.jointype = 2                                                          # FULL
+    hj.jointype = 7                                                          # JOIN_UNIQUE_OUTER (planner-internal)
     with pytest.raises(capi.GGError) as e:
         disasm_join(outer, inner, hj, agg, pool)
     assert e.value.code == -6

@@ -11,7 +11,8 @@ from test_oracle_join import join_nodes, small_relations
 
 pytestmark = pytest.mark.gpu
 
-JOINTYPES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI]
+JOINTYPES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_RIGHT, capi.JOIN_FULL, capi.JOIN_SEMI, capi.JOIN_ANTI, capi.JOIN_LASJ_NOTIN]
+BOTH_SIDES = (capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_RIGHT, capi.JOIN_FULL)      # join types whose output carries inner columns
 
 
 @pytest.fixture(scope="module")
@@ -52,9 +53,9 @@ def gpu_joinagg(eng, outer, inner, hj, agg, pool, opages, ipages, host=False, tw
 def test_small_relations_duplicates_and_nulls(eng, jointype, nkeys, with_qual):
     odesc, idesc, orows, onulls, irows, inulls, opages, ipages = small_relations()
     p, outer, inner, hj = join_nodes(odesc, idesc, jointype, nkeys, with_qual)
-    grp = [p.var(2, capi.BPCHAROID, 1)] if jointype in (capi.JOIN_INNER, capi.JOIN_LEFT) else [p.var(2, capi.BPCHAROID, 0)]
+    grp = [p.var(2, capi.BPCHAROID, 1)] if jointype in BOTH_SIDES else [p.var(2, capi.BPCHAROID, 0)]
     aggs = [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID, 0))]
-    if jointype in (capi.JOIN_INNER, capi.JOIN_LEFT):
+    if jointype in BOTH_SIDES:
         aggs += [(capi.AGG_SUM_INT4, p.var(3, capi.INT4OID, 1)), (capi.AGG_COUNT_ANY, p.var(1, capi.INT4OID, 1))]
     agg = capi.make_agg(capi.AGGSTAGE_NORMAL, grp, aggs)
     want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, p.pool, opages, ipages)
@@ -77,6 +78,38 @@ def test_lineitem_orders_synth_vs_oracle(eng, kind, jointype):
     assert nj == nj_want and nj > 0
     assert_aggrows_match(got, want, agg)
     got_h, nj_h, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od, host=True)
+    assert nj_h == nj_want
+    assert_aggrows_match(got_h, want, agg)
+
+
+@pytest.mark.parametrize("nkeys", [1, 2])
+def test_lasj_notin_with_a_null_free_inner_side(eng, nkeys):
+    """NOT IN over an inner side without NULL keys: an anti join that also drops outer rows with NULL keys; and
+    against an empty inner side every outer row qualifies."""
+    odesc, idesc, orows, onulls, irows, inulls, opages, ipages = small_relations(seed=12)
+    inulls = [[False, False, n[2]] for n in inulls]
+    ipages = po.build_pages(idesc, irows, inulls)
+    p, outer, inner, hj = join_nodes(odesc, idesc, capi.JOIN_LASJ_NOTIN, nkeys, False)
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(2, capi.BPCHAROID, 0)], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID, 0))])
+    for ip in (ipages, np.zeros(0, dtype=np.uint8)):
+        want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, p.pool, opages, ip)
+        got, nj, _ = gpu_joinagg(eng, outer, inner, hj, agg, p.pool, opages, ip, twice=True)
+        assert nj == nj_want and nj > 0
+        assert_aggrows_match(got, want, agg)
+
+
+@pytest.mark.parametrize("jointype", [capi.JOIN_RIGHT, capi.JOIN_FULL])
+def test_right_and_full_join_synth(eng, jointype):
+    """orders holds keys no lineitem references and lineitem references orders that are missing: both sides have
+    unmatched rows.  Rescan (hash table kept) must forget the match marks."""
+    li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 200_000, seed=4, norders=40_000))
+    od_all, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 60_000, seed=4))
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "q3ish", jointype)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, pool, li, od_all)
+    got, nj, st = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od_all, twice=True)
+    assert nj == nj_want
+    assert_aggrows_match(got, want, agg)
+    got_h, nj_h, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od_all, host=True)
     assert nj_h == nj_want
     assert_aggrows_match(got_h, want, agg)
 
@@ -124,7 +157,7 @@ def test_empty_sides(eng):
 def test_unsupported_join_shapes_are_refused(eng):
     from greengage_b200.engine import JoinAgg
     outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "count")
-    hj.jointype = 2                                   # JOIN_FULL: the CPU node keeps it
+    hj.jointype = 7                                   # JOIN_UNIQUE_OUTER: a planner-internal code, the CPU node keeps it
     with pytest.raises(capi.GGError) as e:
         JoinAgg(eng, outer, inner, hj, agg, pool)
     assert e.value.code == -6

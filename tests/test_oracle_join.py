@@ -35,28 +35,40 @@ def small_relations(seed=5, nouter=400, ninner=150):
 
 
 def brute(orows, onulls, irows, inulls, jointype, nkeys, with_qual):
-    """-> list of (outer index, inner index or -1)"""
+    """-> list of (outer index or -1, inner index or -1)"""
     out = []
+    fill_outer = jointype in (capi.JOIN_LEFT, capi.JOIN_FULL, capi.JOIN_ANTI, capi.JOIN_LASJ_NOTIN)
+    fill_inner = jointype in (capi.JOIN_RIGHT, capi.JOIN_FULL)
+    anti = jointype in (capi.JOIN_ANTI, capi.JOIN_LASJ_NOTIN)
+    inner_keynull = [rn[0] or (nkeys == 2 and rn[1]) for rn in inulls]
+    if jointype == capi.JOIN_LASJ_NOTIN and any(inner_keynull):
+        return []                                                   # x NOT IN (.., NULL, ..) is never true
+    inner_matched = [False] * len(irows)
     for oi, (o, on) in enumerate(zip(orows, onulls)):
         matched = False
         okeynull = on[0] or (nkeys == 2 and on[1])
-        if okeynull and jointype in (capi.JOIN_INNER, capi.JOIN_SEMI):
+        if okeynull and not fill_outer:
             continue
+        if okeynull and jointype == capi.JOIN_LASJ_NOTIN and irows:
+            continue                                                # NULL NOT IN (non-empty set) is not true
         for ii, (r, rn) in enumerate(zip(irows, inulls)):
-            if okeynull or rn[0] or (nkeys == 2 and rn[1]):
+            if okeynull or inner_keynull[ii]:
                 continue
             if o[0] != r[0] or (nkeys == 2 and o[1] != r[1]):
                 continue
             if with_qual and (rn[2] or not (r[2] > 0)):          # join qual: inner.c > 0 (NULL is not true)
                 continue
             matched = True
-            if jointype == capi.JOIN_ANTI:
+            inner_matched[ii] = True
+            if anti:
                 break
             out.append((oi, ii))
             if jointype == capi.JOIN_SEMI:
                 break
-        if not matched and jointype in (capi.JOIN_LEFT, capi.JOIN_ANTI):
+        if not matched and fill_outer:
             out.append((oi, -1))
+    if fill_inner:
+        out += [(-1, ii) for ii in range(len(irows)) if not inner_matched[ii]]
     return out
 
 
@@ -68,7 +80,10 @@ def join_nodes(odesc, idesc, jointype, nkeys, with_qual):
     return p, capi.make_scan(odesc, -1), capi.make_scan(idesc, -1), capi.make_hashjoin(jointype, ok, ik, jq)
 
 
-@pytest.mark.parametrize("jointype", [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI])
+ALL_JOINTYPES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_RIGHT, capi.JOIN_FULL, capi.JOIN_SEMI, capi.JOIN_ANTI, capi.JOIN_LASJ_NOTIN]
+
+
+@pytest.mark.parametrize("jointype", ALL_JOINTYPES)
 @pytest.mark.parametrize("nkeys", [1, 2])
 @pytest.mark.parametrize("with_qual", [False, True])
 def test_join_pairs_match_nested_loop(jointype, nkeys, with_qual):
@@ -77,7 +92,7 @@ def test_join_pairs_match_nested_loop(jointype, nkeys, with_qual):
     pairs = po.hashjoin_tids(outer, inner, hj, p.pool, opages, ipages)
     want = brute(orows, onulls, irows, inulls, jointype, nkeys, with_qual)
     # tids are (block << 16 | offnum); both relations fit one page here, so offnum - 1 = row index
-    got = sorted(((int(a) & 0xFFFF) - 1, ((int(b) & 0xFFFF) - 1) if b >= 0 else -1) for a, b in pairs)
+    got = sorted((((int(a) & 0xFFFF) - 1) if a >= 0 else -1, ((int(b) & 0xFFFF) - 1) if b >= 0 else -1) for a, b in pairs)
     if jointype == capi.JOIN_SEMI:
         # which of several qualifying inner rows a semi join reports is unspecified: compare outer rows only
         assert sorted(a for a, _ in got) == sorted(a for a, _ in want)
@@ -112,3 +127,18 @@ def test_join_agg_counts_match_pairs():
         assert (r.agg[2].isnull == 1) == (g[2] is None)
         if g[2] is not None:
             assert r.agg[2].i == g[2]
+
+
+def test_lasj_notin_without_inner_nulls_is_an_anti_join_that_drops_null_outer_keys():
+    """the interesting half of LASJ_NOTIN: inner side free of NULL keys"""
+    odesc, idesc, orows, onulls, irows, inulls, opages, ipages = small_relations(seed=12)
+    inulls = [[False, False, n[2]] for n in inulls]
+    ipages = po.build_pages(idesc, irows, inulls)
+    for nkeys in (1, 2):
+        p, outer, inner, hj = join_nodes(odesc, idesc, capi.JOIN_LASJ_NOTIN, nkeys, False)
+        pairs = po.hashjoin_tids(outer, inner, hj, p.pool, opages, ipages)
+        want = brute(orows, onulls, irows, inulls, capi.JOIN_LASJ_NOTIN, nkeys, False)
+        assert len(want) > 0 and sorted(((int(a) & 0xFFFF) - 1) for a, b in pairs) == sorted(a for a, _ in want)
+        # and against an EMPTY inner side every outer row comes back, NULL keys included
+        pairs = po.hashjoin_tids(outer, inner, hj, p.pool, opages, np.zeros(0, dtype=np.uint8))
+        assert len(pairs) == len(orows)
