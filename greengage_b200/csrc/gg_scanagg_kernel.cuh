@@ -859,7 +859,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					X.ipay = (const uint64_t *) (jt.ent + entry * jt.stride + 1 + jt.nkeys);
 					X.ipaynull = (uint32_t) (fill_hdr >> 32) & 0xFFu;
 					sink.begin_row();
-					sink.jq = false; sink.nullext = true; sink.suppress = false;
+					sink.jq = false; sink.nullext = live;      /* only the lanes that hold an unmatched entry skip the join qual */
+					sink.suppress = false;
 					MatchSink<decltype(sink)> ms = { sink };
 					PL::template run_range<NULLABLE>(X, M2, jt.probe_pc, GGP_MAX_CODE, err, ms);
 					if constexpr (TRMODE) tr_accumulate();

@@ -6,6 +6,7 @@ than L2, >= 3 warm-up passes.
   python scripts/bench_ops.py join  [--rows 1e8] [--orders 2.5e7] [--kind count|q3ish]      BASELINE config 2
   python scripts/bench_ops.py sort  [--rows 1e8]
   python scripts/bench_ops.py motion [--rows 1e8] [--nsegs 8]                                sending side only
+  python scripts/bench_ops.py groupby [--rows 1e8]                                           general HashAggregate
   torchrun ... scripts/bench_ops.py rjoin [--rows 1e8] [--orders 2.5e7]                       BASELINE config 3 (N GPUs)
 """
 import argparse
@@ -97,6 +98,30 @@ def bench_sort(args):
                       "roofline": {"bound": "hbm", "achieved": algo / (t / 1e3) / 1e9, "peak": peak(), "unit": "GB/s",
                                    "frac": algo / (t / 1e3) / 1e9 / peak(),
                                    "algorithmic_bytes": "16 B/row key build + 32 B/row per executed radix pass"}}), flush=True)
+
+
+def bench_groupby(args):
+    """The general HashAggregate: GROUP BY l_orderkey (2.5 * 10^7 groups at the default size), count(*) + sum(float8)."""
+    from greengage_b200.engine import ScanAgg
+    eng = Engine(0)
+    li, nb, nr = gen(eng, capi.TAB_LINEITEM_NARROW, args.rows)
+    c = tpch.LI_NARROW_COLS
+    p = capi.ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(c["orderkey"], capi.INT8OID)],
+                        [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(c["extendedprice"], capi.FLOAT8OID))], num_groups=int(args.rows // 4))
+    sa = ScanAgg(eng, capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW), -1), agg, p.pool)
+    ms = []
+    for it in range(args.warmup + args.steps):
+        sa.reset()
+        sa.run(li)
+        eng.sync()
+        if it >= args.warmup:
+            ms.append(sa.scan_kernel_ms()[0])
+    t = np.mean(ms)
+    print(json.dumps({"op": "hashagg-general", "workload": "GROUP BY l_orderkey over %d rows (~%d groups), count(*) + sum(float8)" % (nr, args.rows // 4),
+                      "ms": t, "rows_per_s": nr / (t / 1e3), "variant": sa.variant(),
+                      "roofline": {"bound": "hbm", "achieved": nb * 32768 / (t / 1e3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                   "frac": nb * 32768 / (t / 1e3) / 1e9 / peak(), "algorithmic_bytes": "pages read once (+ 4 random table sectors per row)"}}), flush=True)
 
 
 def li_payload():
@@ -229,7 +254,7 @@ def bench_rjoin(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["join", "sort", "motion", "rjoin"])
+    ap.add_argument("op", choices=["join", "sort", "motion", "rjoin", "groupby"])
     ap.add_argument("--rows", type=float, default=1e8)
     ap.add_argument("--orders", type=float, default=2.5e7)
     ap.add_argument("--kind", default="count")
@@ -238,4 +263,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     a.rows, a.orders = int(a.rows), int(a.orders)
-    {"join": bench_join, "sort": bench_sort, "motion": bench_motion, "rjoin": bench_rjoin}[a.op](a)
+    {"join": bench_join, "sort": bench_sort, "motion": bench_motion, "rjoin": bench_rjoin, "groupby": bench_groupby}[a.op](a)
