@@ -104,6 +104,7 @@ void gg_engine_free(gg_engine *e)
 	cudaStreamSynchronize(e->stream);
 	cudaStreamSynchronize(e->copy_stream);
 	cudaFree(e->final_scratch);
+	cudaFree(e->sort_scratch);
 	cudaEventDestroy(e->ev_start);
 	cudaEventDestroy(e->ev_stop);
 	cudaStreamDestroy(e->stream);

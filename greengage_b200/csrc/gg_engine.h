@@ -20,6 +20,8 @@ struct gg_engine {
 	uint64_t launches = 0;
 	void *final_scratch = nullptr;       /* gg_agg_final: device scratch kept across calls, grown on demand */
 	size_t final_cap = 0;                /* records it holds */
+	void *sort_scratch = nullptr;        /* gg_sort_*: key/value ping-pong buffers, histograms; kept across calls */
+	size_t sort_scratch_bytes = 0;
 };
 
 struct gg_relation {

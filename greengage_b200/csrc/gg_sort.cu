@@ -312,15 +312,11 @@ static bool sort_type_ok(int32_t t)
 	return false;
 }
 
-struct SortScratch {
+struct SortScratch {                      /* carved out of one allocation the engine keeps (grown on demand) */
 	uint64_t *k[2] = { nullptr, nullptr };
 	uint32_t *v[2] = { nullptr, nullptr };
 	uint32_t *hist = nullptr, *sums = nullptr;
 	unsigned long long *orand = nullptr;
-	~SortScratch()
-	{
-		cudaFree(k[0]); cudaFree(k[1]); cudaFree(v[0]); cudaFree(v[1]); cudaFree(hist); cudaFree(sums); cudaFree(orand);
-	}
 };
 
 /* sort rows resident on the device; dev_perm receives n uint32 row numbers in sorted order.
@@ -343,12 +339,26 @@ static int sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncol
 	const uint32_t nblk = (uint32_t) ((m + 4095) / 4096);
 	const int grid1d = e->sm_count * 8;
 	SortScratch s;
-	GG_CUDA(cudaMalloc((void **) &s.k[0], n * 8));
-	GG_CUDA(cudaMalloc((void **) &s.k[1], n * 8));
-	GG_CUDA(cudaMalloc((void **) &s.v[1], n * 4));
-	GG_CUDA(cudaMalloc((void **) &s.hist, m * 4));
-	GG_CUDA(cudaMalloc((void **) &s.sums, (size_t) nblk * 4));
-	GG_CUDA(cudaMalloc((void **) &s.orand, 16));
+	{
+		auto up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+		const size_t need = 2 * up(n * 8) + up(n * 4) + up(m * 4) + up((size_t) nblk * 4) + 256;
+		if (e->sort_scratch_bytes < need)
+		{
+			GG_CUDA(cudaStreamSynchronize(st));
+			cudaFree(e->sort_scratch);
+			e->sort_scratch = nullptr; e->sort_scratch_bytes = 0;
+			cudaError_t ce = cudaMalloc(&e->sort_scratch, need);
+			if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("sort scratch of %zu bytes does not fit in device memory", need); return GG_ERR_NOMEM; }
+			e->sort_scratch_bytes = need;
+		}
+		uint8_t *b = (uint8_t *) e->sort_scratch;
+		s.k[0] = (uint64_t *) b; b += up(n * 8);
+		s.k[1] = (uint64_t *) b; b += up(n * 8);
+		s.v[1] = (uint32_t *) b; b += up(n * 4);
+		s.hist = (uint32_t *) b; b += up(m * 4);
+		s.sums = (uint32_t *) b; b += up((size_t) nblk * 4);
+		s.orand = (unsigned long long *) b;
+	}
 	const size_t smem = (size_t) SORT_TILE * 12 + (SORT_WARPS * 256 + 512) * 4;
 	GG_CUDA(cudaFuncSetAttribute(gg_sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 
