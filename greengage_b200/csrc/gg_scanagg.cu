@@ -39,8 +39,8 @@ __global__ void gg_hashagg_init_kernel(HashAggTable ha)
 		else if (kind == GGP_ACC_I8MIN) init = 0x7fffffffffffffffull;
 		else if (kind == GGP_ACC_I8MAX) init = 0x8000000000000000ull;
 		else continue;
-		unsigned long long *a = (unsigned long long *) (ha.acc + (uint64_t) j * ha.cap);
-		for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < ha.cap; i += (uint64_t) gridDim.x * blockDim.x) a[i] = init;
+		for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < ha.cap; i += (uint64_t) gridDim.x * blockDim.x)
+			ha.ent[i * ha.stride + ha.off_acc + j] = init;
 	}
 }
 
@@ -51,21 +51,22 @@ __global__ void gg_hashagg_emit_kernel(HashAggTable ha, ggp_grec *out, unsigned 
 	const bool saw_inf = (*errflags & GGP_EF_SAW_INF) != 0;
 	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < ha.cap; i += (uint64_t) gridDim.x * blockDim.x)
 	{
-		const unsigned long long h = ha.hdr[i];
+		const unsigned long long *ep = ha.ent + i * ha.stride;
+		const unsigned long long h = ep[0];
 		if (!(h >> 63)) continue;
 		const unsigned long long at = atomicAdd(nout, 1ull);
 		if (at >= outcap) continue;
 		ggp_grec r;
 		memset(&r, 0, sizeof r);
-		for (int c = 0; c < GG_MAX_KEYS; c++) r.key[c] = ha.keys[i * GG_MAX_KEYS + c];
+		for (int c = 0; c < ha.nkeys; c++) r.key[c] = ep[1 + c];
 		r.keynull = (uint32_t) (h >> 32) & 0xF;
 		r.valid = 1;
-		r.count = ha.cnt[i];
+		r.count = ep[ha.off_cnt];
 		for (int j = 0; j < ha.nacc; j++)
 		{
-			r.sum[j] = ha.acc[(uint64_t) j * ha.cap + i];
-			r.sumsq[j] = ha.sq ? ha.sq[(uint64_t) j * ha.cap + i] : 0.0;
-			r.n[j] = ha.accn[(uint64_t) j * ha.cap + i];
+			r.sum[j] = __longlong_as_double((long long) ep[ha.off_acc + j]);
+			r.sumsq[j] = ha.off_sq ? __longlong_as_double((long long) ep[ha.off_sq + j]) : 0.0;
+			r.n[j] = ha.off_accn ? ep[ha.off_accn + j] : r.count;          /* no NULLs anywhere: every row counted */
 			/* float8pl's CHECKFLOATVAL (float.c:782): an infinite sum of finite inputs is an overflow */
 			if (ha.acckind[j] == GGP_ACC_F8SUM && !saw_inf && r.n[j] && !f8_finite(r.sum[j])) atomicOr(errflags, GGP_EF_FLOAT_OVERFLOW);
 		}
@@ -376,28 +377,29 @@ static int hashagg_alloc(gg_scanagg *p, uint64_t cap)
 	const ggp_program &P = p->prog;
 	bool anysq = false;
 	for (int j = 0; j < P.nacc; j++) anysq = anysq || P.accsq[j] >= 0;
-	if (p->ha_mem && p->ha_cap != cap) { GG_CUDA(cudaStreamSynchronize(st)); cudaFree(p->ha_mem); p->ha_mem = nullptr; }
-	const size_t words = (size_t) cap * (1 + GG_MAX_KEYS + 1 + (size_t) P.nacc * (2 + (anysq ? 1 : 0)));
-	if (!p->ha_mem)
-	{
-		cudaError_t ce = cudaMalloc(&p->ha_mem, words * 8);
-		if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("group table of %zu bytes does not fit in device memory", words * 8); return GG_ERR_NOMEM; }
-	}
-	p->ha_cap = cap;
-	unsigned long long *w = (unsigned long long *) p->ha_mem;
-	HashAggTable &ha = p->ha;
+	HashAggTable ha;
 	memset(&ha, 0, sizeof ha);
 	ha.cap = cap;
-	ha.hdr = w; w += cap;
-	ha.keys = w; w += cap * GG_MAX_KEYS;
-	ha.cnt = w; w += cap;
-	ha.acc = (double *) w; w += cap * (size_t) P.nacc;
-	ha.accn = w; w += cap * (size_t) P.nacc;
-	ha.sq = anysq ? (double *) w : nullptr;
 	ha.nacc = P.nacc; ha.nkeys = P.nkeys;
+	uint32_t w = 1 + (uint32_t) P.nkeys;
+	ha.off_cnt = w++;
+	ha.off_acc = w; w += (uint32_t) P.nacc;
+	if (P.nullable && P.nacc) { ha.off_accn = w; w += (uint32_t) P.nacc; }      /* NOT NULL inputs: n == row count */
+	if (anysq) { ha.off_sq = w; w += (uint32_t) P.nacc; }
+	ha.stride = (w + 3) & ~3u;                                                    /* entries start on 32-byte sectors */
 	memcpy(ha.acckind, P.acckind, sizeof ha.acckind);
 	for (int j = 0; j < P.nacc; j++) if (P.accsq[j] >= 0 && P.accsq[j] < GGP_MAX_SLOTS) ha.sqcol[P.accsq[j]] = (uint8_t) j;
-	GG_CUDA(cudaMemsetAsync(p->ha_mem, 0, words * 8, st));
+	const size_t bytes = (size_t) cap * ha.stride * 8;
+	if (p->ha_mem && p->ha_cap != cap) { GG_CUDA(cudaStreamSynchronize(st)); cudaFree(p->ha_mem); p->ha_mem = nullptr; }
+	if (!p->ha_mem)
+	{
+		cudaError_t ce = cudaMalloc(&p->ha_mem, bytes);
+		if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("group table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
+	}
+	p->ha_cap = cap;
+	ha.ent = (unsigned long long *) p->ha_mem;
+	p->ha = ha;
+	GG_CUDA(cudaMemsetAsync(p->ha_mem, 0, bytes, st));
 	gg_hashagg_init_kernel<<<p->eng->sm_count * 4, 256, 0, st>>>(ha);
 	GG_CUDA(cudaGetLastError());
 	p->eng->launches++;

@@ -41,19 +41,22 @@ enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2,
        MODE_HASH = 5 };    /* HashAggregate with any number of groups: one hash table in HBM, atomics */
 
 /* The general HashAggregate (execHHashagg.c:456 lookup_agg_hash_entry, nodeAgg.c:545 advance_aggregates) for group
- * counts beyond what a block holds on chip: open addressing in HBM, structure of arrays, capacity a power of two.
- *   hdr[cap]            0 empty | 1 being written | bit 63 ready, bits 32..35 key-NULL mask, bits 0..31 hash tag
- *   keys[cap][4]        normalised grouping keys
- *   cnt[cap]            rows of the group
- *   acc[nacc][cap]      F8SUM/I8SUM: running sum; MIN/MAX: current extreme (bits)      -> atomicAdd / CAS / atomicMin,Max
- *   accn[nacc][cap]     non-NULL inputs
- *   sq[nacc][cap]       float8_accum's sumX2 where the plan ships it
+ * counts beyond what a block holds on chip: open addressing in HBM, capacity a power of two, one entry of `stride`
+ * 64-bit words per slot (a multiple of 4 words, so entries start on 32-byte sectors and a row's lookup + transition
+ * touch one or two sectors):
+ *   [0]                    0 empty | 1 being written | bit 63 ready, bits 32..35 key-NULL mask, bits 0..31 hash tag
+ *   [1 .. nkeys]           normalised grouping keys
+ *   [off_cnt]              rows of the group
+ *   [off_acc + j]          F8SUM/I8SUM: running sum; MIN/MAX: current extreme (bits)   -> atomicAdd / CAS / atomicMin,Max
+ *   [off_accn + j]         non-NULL inputs (only when the plan can see NULLs; else it equals the row count)
+ *   [off_sq + j]           float8_accum's sumX2 where the plan ships it
  * Float sums are accumulated with atomicAdd in arrival order: exact to the last few ulps, not run-to-run identical
  * (the reference's hash aggregate adds in scan order, also not an order the SQL result depends on). */
 struct HashAggTable {
-	unsigned long long *hdr, *keys, *cnt, *accn;
-	double *acc, *sq;
-	uint64_t cap;                          /* slots; also the stride of the per-column arrays */
+	unsigned long long *ent;
+	uint64_t cap;                          /* slots */
+	uint32_t stride;                       /* words per entry */
+	uint32_t off_cnt, off_acc, off_accn, off_sq;   /* word offsets inside an entry; off_accn / off_sq = 0: not kept */
 	uint8_t sqcol[GGP_MAX_SLOTS];          /* value slot -> accumulator column whose sum of squares it is (slots >= nacc) */
 	uint8_t acckind[GGP_MAX_ACCS];
 	int nacc, nkeys;
@@ -425,14 +428,17 @@ struct HashSink {
 		const uint64_t maxtries = ha.cap < 256 ? ha.cap : 256;
 		for (uint64_t tries = 0; tries < maxtries; )
 		{
-			volatile unsigned long long *hp = ha.hdr + slot;
+			unsigned long long *ep = ha.ent + slot * ha.stride;
+			volatile unsigned long long *hp = ep;
 			unsigned long long cur = *hp;
 			if (cur == 0)
 			{
-				if (atomicCAS(ha.hdr + slot, 0ull, GG_HA_LOCKED) == 0ull)
+				if (atomicCAS(ep, 0ull, GG_HA_LOCKED) == 0ull)
 				{
-					unsigned long long *kp = ha.keys + slot * GG_MAX_KEYS;
-					kp[0] = k0; kp[1] = k1; kp[2] = k2; kp[3] = k3;
+					ep[1] = k0;
+					if (ha.nkeys > 1) ep[2] = k1;
+					if (ha.nkeys > 2) ep[3] = k2;
+					if (ha.nkeys > 3) ep[4] = k3;
 					__threadfence();
 					*hp = ready;
 					e = (long long) slot;
@@ -443,36 +449,37 @@ struct HashSink {
 			if (cur == GG_HA_LOCKED) continue;        /* being written: look again */
 			if (cur == ready)
 			{
-				const unsigned long long *kp = ha.keys + slot * GG_MAX_KEYS;
-				if (kp[0] == k0 && kp[1] == k1 && kp[2] == k2 && kp[3] == k3) { e = (long long) slot; break; }
+				const volatile unsigned long long *kp = ep + 1;
+				if (kp[0] == k0 && (ha.nkeys < 2 || kp[1] == k1) && (ha.nkeys < 3 || kp[2] == k2) && (ha.nkeys < 4 || kp[3] == k3))
+				{ e = (long long) slot; break; }
 			}
 			slot = (slot + 1) & (ha.cap - 1);
 			tries++;
 		}
 		if (e < 0) { *err |= GGP_EF_TABLE_FULL; return false; }
-		atomicAdd(ha.cnt + e, 1ull);
+		atomicAdd(ha.ent + (uint64_t) e * ha.stride + ha.off_cnt, 1ull);
 		return true;
 	}
 	__device__ __forceinline__ void out(int slot, double v, bool isnull)
 	{
 		if (e < 0 || isnull) return;
+		unsigned long long *ep = ha.ent + (uint64_t) e * ha.stride;
 		if (slot >= ha.nacc)
 		{
-			atomicAdd(ha.sq + (uint64_t) ha.sqcol[slot] * ha.cap + (uint64_t) e, v);
+			atomicAdd((double *) (ep + ha.off_sq + ha.sqcol[slot]), v);
 			return;
 		}
-		const uint64_t at = (uint64_t) slot * ha.cap + (uint64_t) e;
+		unsigned long long *ap = ep + ha.off_acc + slot;
 		const int kind = ha.acckind[slot];
-		atomicAdd(ha.accn + at, 1ull);
-		if (kind == GGP_ACC_F8SUM) { if (!f8_finite(v)) nonfinite = true; atomicAdd(ha.acc + at, v); }
-		else if (kind == GGP_ACC_I8SUM) atomicAdd((unsigned long long *) (ha.acc + at), (unsigned long long) __double_as_longlong(v));
-		else if (kind == GGP_ACC_I8MIN) atomicMin((long long *) (ha.acc + at), __double_as_longlong(v));
-		else if (kind == GGP_ACC_I8MAX) atomicMax((long long *) (ha.acc + at), __double_as_longlong(v));
+		if (ha.off_accn) atomicAdd(ep + ha.off_accn + slot, 1ull);
+		if (kind == GGP_ACC_F8SUM) { if (!f8_finite(v)) nonfinite = true; atomicAdd((double *) ap, v); }
+		else if (kind == GGP_ACC_I8SUM) atomicAdd(ap, (unsigned long long) __double_as_longlong(v));
+		else if (kind == GGP_ACC_I8MIN) atomicMin((long long *) ap, __double_as_longlong(v));
+		else if (kind == GGP_ACC_I8MAX) atomicMax((long long *) ap, __double_as_longlong(v));
 		else if (kind == GGP_ACC_F8MIN || kind == GGP_ACC_F8MAX)
 		{
 			/* float8smaller / float8larger under float8_cmp_internal's order (NaN largest), float.c:964 */
-			unsigned long long *ap = (unsigned long long *) (ha.acc + at);
-			unsigned long long old = *ap;
+			unsigned long long old = *(volatile unsigned long long *) ap;
 			for (;;)
 			{
 				const int c = f8_cmp(v, __longlong_as_double((long long) old));
