@@ -424,3 +424,39 @@ def test_large_relation_properties(eng):
         for i in range(4):
             s = ka[k].agg[i].f[0] + kb[k].agg[i].f[0]
             assert abs(s - r.agg[i].f[0]) <= 1e-9 * abs(r.agg[i].f[0])
+
+
+def test_four_byte_varlena_headers_and_alignment_padding(eng):
+    """Short strings normally carry 1-byte headers; a 4-byte (big-endian, GPDB) header is aligned like an int with zero
+    pad bytes in front — att_align_pointer's peek (tupmacs.h:149) decides per value.  Tuples are crafted byte by byte
+    (header copied from a tuple the oracle formed); both header kinds are mixed on one page and followed by an aligned
+    float8, so every offset after the string depends on the decision."""
+    desc = make_desc([(capi.INT4OID, 4, "i", 1, 1), (capi.BPCHAROID, -1, "i", 0, 1), (capi.FLOAT8OID, 8, "d", 1, 1)])
+    rng = np.random.default_rng(17)
+    L = po.lib()
+    page = np.zeros(capi.GG_BLCKSZ, dtype=np.uint8)
+    L.or_page_init(page.ctypes.data)
+    L.or_page_set_all_visible(page.ctypes.data)
+    n = 0
+    for i in range(500):
+        a = int(rng.integers(0, 1000))
+        s = bytes([65 + int(rng.integers(0, 4))]) + (b"x " if i % 3 == 0 else b"  ")        # char(3), blank padded
+        c = float(rng.integers(1, 100)) / 4
+        t = bytearray(po.form_tuple(desc, [a, s, c]))
+        if i % 2:
+            # same row with a 4-byte header: data = int4 | 00 00 00 07 | 3 bytes | pad to 8 | float8
+            data = a.to_bytes(4, "little", signed=True) + (7).to_bytes(4, "big") + s + b"\0" * 5 + np.float64(c).tobytes()
+            t = t[:24] + data
+        tb = (C.c_uint8 * len(t)).from_buffer_copy(bytes(t))
+        assert L.or_page_add_item(page.ctypes.data, tb, len(t)) > 0
+        n += 1
+    p = ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(2, capi.BPCHAROID)],
+                        [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID)), (capi.AGG_SUM_INT4, p.var(1, capi.INT4OID))])
+    scan = capi.make_scan(desc, -1)
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, page)
+    assert sc == n and len(want) == 8                      # 4 letters x {"Ax", "A"}
+    for variant in ("interp-tr", "specialised-tr"):
+        got, gsc, gps, _ = gpu_scanagg(eng, scan, agg, p.pool, page, variant)
+        assert (gsc, gps) == (sc, ps)
+        assert_aggrows_match(got, want, agg)
