@@ -17,7 +17,7 @@
 #include <stdint.h>
 #include "../../include/gg_plan.h"
 
-#define GGP_MAX_COLS    16     /* distinct referenced columns per side */
+#define GGP_MAX_COLS    32     /* distinct referenced columns per side (= GG_MAX_ATTS) */
 #define GGP_MAX_CONSTS  24
 #define GGP_MAX_CODE    160
 #define GGP_MAX_ACCS    16     /* accumulator columns (deduplicated aggregate arguments) */

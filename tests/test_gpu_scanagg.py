@@ -460,3 +460,49 @@ def test_four_byte_varlena_headers_and_alignment_padding(eng):
         got, gsc, gps, _ = gpu_scanagg(eng, scan, agg, p.pool, page, variant)
         assert (gsc, gps) == (sc, ps)
         assert_aggrows_match(got, want, agg)
+
+
+def test_limits_of_the_accelerated_subset(eng):
+    """The widest plan the subset allows: a 32-attribute relation (GG_MAX_ATTS), 4 grouping keys (GG_MAX_KEYS) of four
+    different types, 16 aggregates (GG_MAX_AGGS) over nullable columns, PARTIAL stage (avg carries its sum of squares)."""
+    rng = np.random.default_rng(23)
+    spec = []
+    for i in range(32):
+        spec.append([(capi.INT4OID, 4, "i", 1), (capi.FLOAT8OID, 8, "d", 1), (capi.BPCHAROID, -1, "i", 0), (capi.INT8OID, 8, "d", 1),
+                     (capi.DATEOID, 4, "i", 1)][i % 5])
+    desc = make_desc(spec)
+    rows, nulls = [], []
+    for r in range(6000):
+        row, nl = [], []
+        for i in range(32):
+            k = i % 5
+            if k == 0: v = int(rng.integers(0, 2)) if i == 0 else int(rng.integers(-1000, 1000))
+            elif k == 1: v = float(rng.integers(-500, 500)) / 8
+            elif k == 2: v = bytes([65 + int(rng.integers(0, 2))]) + b" " * 3
+            elif k == 3: v = int(rng.integers(0, 2)) if i == 3 else int(rng.integers(-10**12, 10**12))
+            else: v = int(rng.integers(7000, 7002)) if i == 4 else int(rng.integers(-3000, 9000))
+            row.append(v)
+            nl.append(bool(rng.random() < 0.07))
+        rows.append(row)
+        nulls.append(nl)
+    pages = po.build_pages(desc, rows, nulls)
+    p = ExprPool()
+    keys = [p.var(1, capi.INT4OID), p.var(3, capi.BPCHAROID), p.var(4, capi.INT8OID), p.var(5, capi.DATEOID)]
+    f = lambda a: p.var(a, capi.FLOAT8OID)
+    aggs = [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, f(2)), (capi.AGG_AVG_FLOAT8, f(7)), (capi.AGG_MIN_FLOAT8, f(12)),
+            (capi.AGG_MAX_FLOAT8, f(17)), (capi.AGG_SUM_INT4, p.var(6, capi.INT4OID)), (capi.AGG_MIN_INT4, p.var(11, capi.INT4OID)),
+            (capi.AGG_MAX_INT4, p.var(16, capi.INT4OID)), (capi.AGG_MIN_INT8, p.var(9, capi.INT8OID)), (capi.AGG_MAX_INT8, p.var(14, capi.INT8OID)),
+            (capi.AGG_MIN_DATE, p.var(10, capi.DATEOID)), (capi.AGG_MAX_DATE, p.var(15, capi.DATEOID)), (capi.AGG_COUNT_ANY, f(22)),
+            (capi.AGG_AVG_FLOAT8, f(27)), (capi.AGG_SUM_FLOAT8, p.func(capi.F_FLOAT8MUL, capi.FLOAT8OID, f(32), f(2))),
+            (capi.AGG_COUNT_ANY, p.var(31, capi.INT4OID))]
+    assert len(aggs) == capi.GG_MAX_AGGS
+    agg = capi.make_agg(capi.AGGSTAGE_PARTIAL, keys, aggs, num_groups=81)
+    scan = capi.make_scan(desc, -1)
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages)
+    assert 30 < len(want) <= 81                              # 3^4 combinations of {value, value, NULL}
+    got, gsc, gps, var = gpu_scanagg(eng, scan, agg, p.pool, pages)
+    assert (gsc, gps) == (sc, ps)
+    assert_aggrows_match(got, want, agg)
+    agg.numGroups = 0                                        # no planner estimate: the on-chip variants overflow, then the HBM table
+    got2, _, _, var2 = gpu_scanagg(eng, scan, agg, p.pool, pages)
+    assert_aggrows_match(got2, want, agg)
