@@ -40,9 +40,16 @@ struct gg_scanagg {
 	/* device state */
 	ggp_grec *recs = nullptr;       /* [GG_MERGE_CAP (previous merged)] ++ [grid * GGP_FAST_GROUPS (block records)] */
 	ggp_grec *merged = nullptr;     /* [GG_MERGE_CAP] output of the merge kernel */
-	int *vidx = nullptr, *vmap = nullptr, *d_nout = nullptr;
-	uint32_t *d_err = nullptr;
-	unsigned long long *d_counters = nullptr;
+	int *vidx = nullptr, *vmap = nullptr;
+	/* status words of the pipeline: one device block, mirrored into pinned host memory by ONE copy per fetch
+	 * (together with the first merged group records) */
+	struct Status { uint32_t err; int nout; unsigned long long counters[2]; };
+	Status *d_status = nullptr;
+	int *d_nout = nullptr;                  /* = &d_status->nout */
+	uint32_t *d_err = nullptr;              /* = &d_status->err */
+	unsigned long long *d_counters = nullptr;   /* = d_status->counters */
+	struct HostMirror { Status st; ggp_grec recs[GGP_FAST_GROUPS]; };
+	HostMirror *h_mirror = nullptr;         /* pinned */
 	int nrecs_total = 0, nrecs_cap = 0;
 	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
 	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; };

@@ -79,19 +79,20 @@ __global__ void gg_hashagg_emit_kernel(HashAggTable ha, ggp_grec *out, unsigned 
  * lock, creates) its merged group.  C: thread (group, column) folds that group's records in record
  * order.  This is also the combine step of a FINAL-stage Agg (float8pl / float8_combine / int8pl,
  * nodeAgg.c:2123-2148) when the records come from other segments. */
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(1024, 1)
 gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_acckinds kinds,
                      ggp_grec *out, int outcap, int *nout, int *vidx /* [nrecs] */, int *vmap /* [nrecs] */,
                      uint32_t *errflags)
 {
 	__shared__ int s_nvalid, s_nout, s_lock;
-	__shared__ int s_warpsum[8];
+	__shared__ int s_warpsum[32];
+	const int nthreads = (int) blockDim.x, nwarps = nthreads >> 5;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) { s_nvalid = 0; s_nout = 0; s_lock = 0; }
 	__syncthreads();
 
-	/* A: ordered compaction (chunks of 256 records, in order) */
-	for (int base = 0; base < nrecs; base += 256)
+	/* A: ordered compaction (chunks of blockDim.x records, in order) */
+	for (int base = 0; base < nrecs; base += nthreads)
 	{
 		int i = base + tid;
 		bool v = i < nrecs && recs[i].valid != 0;
@@ -101,7 +102,7 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 		int pre = 0;
 		for (int w = 0; w < warp; w++) pre += s_warpsum[w];
 		int tot = 0;
-		for (int w = 0; w < 8; w++) tot += s_warpsum[w];
+		for (int w = 0; w < nwarps; w++) tot += s_warpsum[w];
 		int pos = s_nvalid + pre + __popc(b & ((1u << lane) - 1));
 		if (v) vidx[pos] = i;
 		__syncthreads();
@@ -111,7 +112,7 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 	const int nvalid = s_nvalid;
 
 	/* B: group assignment */
-	for (int base = 0; base < nvalid; base += 256)
+	for (int base = 0; base < nvalid; base += nthreads)
 	{
 		int k = base + tid;
 		bool need = k < nvalid;
@@ -199,7 +200,10 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 		for (int slot = 0; slot < GGP_FAST_GROUPS; slot++)
 		{
 			const int i = set * GGP_FAST_GROUPS + slot;
-			if (i >= nrecs || !recs[i].valid || vmap[i] != mg) continue;
+			/* within a set the valid records are a prefix (a block fills slots 0..G-1; merged / FINAL-stage input is
+			 * dense), so the first invalid slot ends the set */
+			if (i >= nrecs || !recs[i].valid) break;
+			if (vmap[i] != mg) continue;
 			const ggp_grec &x = recs[i];
 			cnt += x.count;
 			if (nacc > 0 && x.n[j])
@@ -471,7 +475,7 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	/* fold the block records (and the previously merged groups) */
 	ggp_acckinds kinds;
 	memcpy(kinds.k, p->prog.acckind, sizeof kinds.k);
-	gg_merge_recs_kernel<<<1, 256, 0, st>>>(p->recs, p->nrecs_total, p->prog.nkeys, p->prog.nacc, kinds,
+	gg_merge_recs_kernel<<<1, 1024, 0, st>>>(p->recs, p->nrecs_total, p->prog.nkeys, p->prog.nacc, kinds,
 	                                        p->merged, GG_MERGE_CAP, p->d_nout, p->vidx, p->vmap, p->d_err);
 	GG_CUDA(cudaGetLastError());
 	e->launches++;
@@ -548,9 +552,11 @@ int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out)
 	GG_CUDA(cudaMalloc((void **) &p->merged, sizeof(ggp_grec) * GG_MERGE_CAP));
 	GG_CUDA(cudaMalloc((void **) &p->vidx, sizeof(int) * p->nrecs_cap));
 	GG_CUDA(cudaMalloc((void **) &p->vmap, sizeof(int) * p->nrecs_cap));
-	GG_CUDA(cudaMalloc((void **) &p->d_nout, sizeof(int)));
-	GG_CUDA(cudaMalloc((void **) &p->d_err, sizeof(uint32_t)));
-	GG_CUDA(cudaMalloc((void **) &p->d_counters, 2 * sizeof(unsigned long long)));
+	GG_CUDA(cudaMalloc((void **) &p->d_status, sizeof(gg_scanagg::Status)));
+	p->d_nout = &p->d_status->nout;
+	p->d_err = &p->d_status->err;
+	p->d_counters = p->d_status->counters;
+	GG_CUDA(cudaHostAlloc((void **) &p->h_mirror, sizeof(gg_scanagg::HostMirror), cudaHostAllocDefault));
 	GG_CUDA(cudaMalloc((void **) &p->d_nout64, sizeof(unsigned long long)));
 	*out = p;
 	return gg_scanagg_reset(p);
@@ -583,9 +589,7 @@ int gg_scanagg_reset(gg_scanagg *p)
 	GG_CUDA(cudaMemsetAsync(p->recs, 0, sizeof(ggp_grec) * p->nrecs_cap, st));
 	p->fed.clear();
 	GG_CUDA(cudaMemsetAsync(p->merged, 0, sizeof(ggp_grec) * GG_MERGE_CAP, st));
-	GG_CUDA(cudaMemsetAsync(p->d_nout, 0, sizeof(int), st));
-	GG_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(uint32_t), st));
-	GG_CUDA(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), st));
+	GG_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(gg_scanagg::Status), st));
 	p->has_state = false;
 	p->kev_used = 0;
 	if (p->mode == MODE_HASH)
@@ -746,13 +750,13 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	gg_engine *e = p->eng;
 	GG_CUDA(cudaSetDevice(e->device));
 	GG_CUDA(cudaStreamSynchronize(e->copy_stream));
+	/* one round trip: status words and (speculatively) the first merged group records, behind everything queued */
+	GG_CUDA(cudaMemcpyAsync(&p->h_mirror->st, p->d_status, sizeof(gg_scanagg::Status), cudaMemcpyDeviceToHost, e->stream));
+	GG_CUDA(cudaMemcpyAsync(p->h_mirror->recs, p->recs, sizeof p->h_mirror->recs, cudaMemcpyDeviceToHost, e->stream));
 	GG_CUDA(cudaStreamSynchronize(e->stream));
-	uint32_t flags = 0;
-	unsigned long long counters[2] = { 0, 0 };
-	int n = 0;
-	GG_CUDA(cudaMemcpy(&flags, p->d_err, sizeof flags, cudaMemcpyDeviceToHost));
-	GG_CUDA(cudaMemcpy(counters, p->d_counters, sizeof counters, cudaMemcpyDeviceToHost));
-	GG_CUDA(cudaMemcpy(&n, p->d_nout, sizeof n, cudaMemcpyDeviceToHost));
+	uint32_t flags = p->h_mirror->st.err;
+	unsigned long long counters[2] = { p->h_mirror->st.counters[0], p->h_mirror->st.counters[1] };
+	int n = p->h_mirror->st.nout;
 	if (p->mode == MODE_HASH || ((flags & GGP_EF_GROUP_OVERFLOW) && p->mode != MODE_PRIV))
 	{
 		/* the general HashAggregate.  Reached directly (planner expected many groups), or because a block-table
@@ -841,7 +845,8 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 	if (!p->has_state) n = 0;
 	/* plain aggregation over zero rows still yields one row (nodeAgg.c:1247-1400) */
 	std::vector<ggp_grec> recs((size_t) (n > 0 ? n : 1));
-	if (n > 0) GG_CUDA(cudaMemcpy(recs.data(), p->recs, sizeof(ggp_grec) * n, cudaMemcpyDeviceToHost));
+	if (n > 0 && n <= GGP_FAST_GROUPS) memcpy(recs.data(), p->h_mirror->recs, sizeof(ggp_grec) * (size_t) n);     /* already here */
+	else if (n > 0) GG_CUDA(cudaMemcpy(recs.data(), p->recs, sizeof(ggp_grec) * n, cudaMemcpyDeviceToHost));
 	if (n == 0 && p->agg.numCols == 0) { memset(&recs[0], 0, sizeof(ggp_grec)); n = 1; }
 	if (n > outcap) { gg_set_error("output capacity %d < %d groups", outcap, n); return GG_ERR_NOMEM; }
 	finalize_rows(&p->agg, p->aggmap, &p->prog, 0, recs.data(), n, out);
@@ -879,7 +884,7 @@ void gg_scanagg_free(gg_scanagg *p)
 	cudaSetDevice(p->eng->device);
 	cudaStreamSynchronize(p->eng->stream);
 	cudaFree(p->recs); cudaFree(p->merged); cudaFree(p->vidx); cudaFree(p->vmap);
-	cudaFree(p->d_nout); cudaFree(p->d_err); cudaFree(p->d_counters); cudaFree(p->d_nout64); cudaFree(p->ha_mem);
+	cudaFree(p->d_status); cudaFreeHost(p->h_mirror); cudaFree(p->d_nout64); cudaFree(p->ha_mem);
 	for (int b = 0; b < 2; b++)
 	{
 		if (p->stage[b]) cudaFree(p->stage[b]);
@@ -989,7 +994,7 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 	GG_CUDA(cudaMemcpyAsync(d_recs, recs.data(), sizeof(ggp_grec) * (size_t) nin, cudaMemcpyHostToDevice, e->stream));
 	GG_CUDA(cudaMemcpyAsync(d_err, &hostflags, sizeof hostflags, cudaMemcpyHostToDevice, e->stream));
 	GG_CUDA(cudaMemsetAsync(d_out, 0, sizeof(ggp_grec) * cap, e->stream));
-	gg_merge_recs_kernel<<<1, 256, 0, e->stream>>>(d_recs, nin, agg->numCols, agg->numAggs, kinds,
+	gg_merge_recs_kernel<<<1, 1024, 0, e->stream>>>(d_recs, nin, agg->numCols, agg->numAggs, kinds,
 	                                               d_out, cap, d_n, d_vidx, d_vmap, d_err);
 	cudaError_t le = cudaGetLastError();
 	e->launches++;
