@@ -48,7 +48,8 @@ class GgSort(C.Structure):
 
 class GgMotion(C.Structure):
     _fields_ = [("plan", GgPlan), ("motionType", C.c_int32), ("numHashCols", C.c_int32),
-                ("hashCol", C.c_int32 * capi.GG_MAX_KEYS), ("motionID", C.c_int32)]
+                ("hashCol", C.c_int32 * capi.GG_MAX_KEYS), ("motionID", C.c_int32),
+                ("numSortCols", C.c_int32), ("sortKeys", capi.gg_sortkey * GG_MAX_SORTKEYS)]
 
 
 class GgTupleTableSlot(C.Structure):
@@ -151,12 +152,15 @@ class PlanBuilder:
             n.keys[i] = k
         return n
 
-    def motion(self, child, motion_type, hash_cols=(), motion_id=1):
+    def motion(self, child, motion_type, hash_cols=(), motion_id=1, merge_keys=()):
         n = self._keep(GgMotion())
         n.plan.type, n.plan.qual, n.plan.lefttree = T_Motion, -1, _as_plan(child)
         n.motionType, n.numHashCols, n.motionID = motion_type, len(hash_cols), motion_id
         for i, c in enumerate(hash_cols):
             n.hashCol[i] = c
+        n.numSortCols = len(merge_keys)                 # sendSorted: the receiver merges on these keys
+        for i, k in enumerate(merge_keys):
+            n.sortKeys[i] = k
         return n
 
 

@@ -448,6 +448,35 @@ static int run_node(GgPlanState *s)
 				free(recv.values); free(recv.isnull);
 			}
 			memcpy(s->typid, ch->typid, sizeof s->typid);
+			if (mo->numSortCols > 0 && s->nrows > 1)
+			{
+				/* sorted receive: the merged order of sorted streams is the sorted order of their union; the comparator is
+				 * the Sort node's (tuplesort_mk.c:2816), ties in unspecified order as in the reference's merge */
+				gg_sortkey keys[GG_MAX_SORTKEYS];
+				uint64_t *perm = malloc(8 * (size_t) s->nrows);
+				int64_t *v2 = malloc(8 * (size_t) s->nrows * s->ncols);
+				uint8_t *n2 = malloc((size_t) s->nrows * s->ncols);
+				int32_t *l2 = malloc(4 * (size_t) s->nrows * s->ncols);
+				int k;
+				if (mo->numSortCols > GG_MAX_SORTKEYS) { exec_fail(GG_ERR_UNSUPPORTED, "Motion with %d merge keys", mo->numSortCols); free(perm); free(v2); free(n2); free(l2); return -1; }
+				if (!perm || !v2 || !n2 || !l2) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+				for (k = 0; k < mo->numSortCols; k++)
+				{
+					keys[k] = mo->sortKeys[k];
+					if (keys[k].col < 0 || keys[k].col >= s->ncols) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_ARG, "Motion merge key column %d out of range", keys[k].col); return -1; }
+					if (!keys[k].typid) keys[k].typid = s->typid[keys[k].col];
+				}
+				rc = gg_sort_rows(es->engine, keys, mo->numSortCols, s->ncols, s->values, s->isnull, (uint64_t) s->nrows, perm);
+				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(perm); free(v2); free(n2); free(l2); return -1; }
+				for (r = 0; r < s->nrows; r++)
+				{
+					memcpy(v2 + (size_t) r * s->ncols, s->values + (size_t) perm[r] * s->ncols, 8 * (size_t) s->ncols);
+					memcpy(n2 + (size_t) r * s->ncols, s->isnull + (size_t) perm[r] * s->ncols, (size_t) s->ncols);
+					memcpy(l2 + (size_t) r * s->ncols, s->lens + (size_t) perm[r] * s->ncols, 4 * (size_t) s->ncols);
+				}
+				free(s->values); free(s->isnull); free(s->lens); free(perm);
+				s->values = v2; s->isnull = n2; s->lens = l2;
+			}
 			break;
 		}
 		default:

@@ -87,6 +87,11 @@ typedef struct GgMotion {
 	int32_t numHashCols;
 	int32_t hashCol[GG_MAX_KEYS];   /* Redistribute: 0-based output columns of the child that are hashed */
 	int32_t motionID;
+	/* sendSorted (plannodes.h Motion.sendSorted + sort keys): every sender's stream is sorted on these keys and the
+	 * receiver returns the merged order (execMotionSortedReceiver_mk, nodeMotion.c:636) — Q1's final
+	 * "Gather Motion, Merge Key: l_returnflag, l_linestatus".  0 = arrival order. */
+	int32_t numSortCols;
+	gg_sortkey sortKeys[GG_MAX_SORTKEYS];
 } GgMotion;
 
 /* TupleTableSlot holding a virtual tuple (tuptable.h:117-175): Datums + null flags */

@@ -4,7 +4,7 @@ answer (ORDER BY included) and the oracle."""
 import numpy as np
 import pytest
 
-from _util import assert_aggrows_match, golden, lineitem_fixture_pages
+from _util import golden, lineitem_fixture_pages
 from greengage_b200 import capi, executor as ex, tpch
 from oracle import pyoracle as po
 
@@ -32,7 +32,8 @@ def q1_sorted_plan(b, scan, agg, two_stage):
     part.aggstage = capi.AGGSTAGE_PARTIAL
     fin = tpch.q1_final_agg(part)
     # Gather Motion <- Sort <- Agg(FINAL) <- Redistribute Motion <- Agg(PARTIAL) <- SeqScan   (tpch500GB.out:1771-1782)
-    return b.motion(b.sort(b.agg(b.motion(b.agg(ss, part), ex.MOTION_HASH, [0, 1], 1), fin), keys), ex.MOTION_GATHER, [], 2)
+    return b.motion(b.sort(b.agg(b.motion(b.agg(ss, part), ex.MOTION_HASH, [0, 1], 1), fin), keys), ex.MOTION_GATHER, [], 2,
+                    merge_keys=keys)          # Gather Motion with Merge Key: l_returnflag, l_linestatus
 
 
 @pytest.mark.parametrize("two_stage", [False, True])

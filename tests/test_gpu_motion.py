@@ -162,7 +162,7 @@ def test_q1_over_redistributed_rows(eng):
 def test_join_over_redistributed_rows(eng, jointype):
     """Redistribute both sides on the join key, then HashJoin -> Agg over what arrived (BASELINE config 3 on one
     segment): every destination joins its share; the shares' partial results combine to the heap-page answer."""
-    from greengage_b200.engine import JoinAgg, RowRelation, agg_final
+    from greengage_b200.engine import JoinAgg, RowRelation
     li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 200_000, seed=8, norders=40_000))
     od, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 30_000, seed=8))
     nsegs = 3

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from _util import assert_aggrows_match, f2b, golden, lineitem_fixture_pages, make_desc
+from _util import assert_aggrows_match, golden, lineitem_fixture_pages, make_desc
 from greengage_b200 import capi, tpch
 from greengage_b200.capi import ExprPool
 from oracle import pyoracle as po
