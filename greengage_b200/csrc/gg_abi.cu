@@ -272,15 +272,16 @@ extern "C" int gg_debug_disasm_join(const gg_scan *outer, const gg_scan *inner, 
 /* debugging aid: the plan-specialised source gg_jit.cpp would compile for this plan and kernel variant */
 #include "gg_jit.h"
 extern "C" int gg_debug_jit_source(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, int mode, int threads,
-                                   const char *suffix, unsigned long long *hash, char *buf, int cap)
+                                   const char *suffix, unsigned long long *hash, char *buf, int cap, int regslots_or_rule)
 {
 	ggp_program prog;
 	ggp_aggmap aggmap[GG_MAX_AGGS];
 	char msg[256];
 	int rc = ggp_compile_scanagg(scan, agg, pool, &prog, aggmap, msg, sizeof msg);
 	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
-	std::string s = gg_jit_scanagg_source(&prog, mode, threads, suffix);
-	if (hash) *hash = gg_plan_hash(&prog, mode);
+	const int regslots = regslots_or_rule >= 0 ? regslots_or_rule : gg_priv_regslots(&prog, mode, agg->numGroups, -1);
+	std::string s = gg_jit_scanagg_source(&prog, mode, threads, suffix, -1, regslots);
+	if (hash) *hash = gg_plan_hash(&prog, mode) ^ (0x9E3779B97F4A7C15ULL * (uint64_t) regslots);
 	snprintf(buf, (size_t) cap, "%s", s.c_str());
 	return (int) s.size();
 }

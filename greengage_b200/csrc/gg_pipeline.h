@@ -28,6 +28,7 @@ struct gg_scanagg {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
 	size_t kev_used = 0;
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
+	int regslots = -1;              /* private-accumulator variant: trailing value slots kept in registers (-1: not decided) */
 	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
 	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
 	ggd::HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */

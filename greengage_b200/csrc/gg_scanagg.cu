@@ -273,8 +273,19 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 static int scanagg_configure(gg_scanagg *p)
 {
 	gg_engine *e = p->eng;
-	const int nslots = p->prog.nslots;
-	const int V = nslots > 0 ? nslots : 1;
+	const int V = p->prog.nslots > 0 ? p->prog.nslots : 1;
+	/* value slots that need shared memory: the private-accumulator variant keeps the last few in registers when a
+	 * plan-specialised kernel is available and the planner expects no more groups than the registers hold */
+	if (p->mode != MODE_PRIV) p->regslots = 0;
+	else if (p->regslots < 0)
+	{
+		/* Measured (scripts/dev_regs.sh, 10^8-row lineitem-wide): register slots cost a few predicated adds per row
+		 * but free shared memory — Q1 one-stage: 20 warps instead of 16 on the 4-page ring, 4.56 -> 4.74 TB/s; Q1
+		 * PARTIAL stage (8 value slots): 16 warps / 4 pages instead of 13 / 3, 3.43 -> 4.15 TB/s.  Dense pages run
+		 * on a 3-page ring where everything fits anyway, and there the plain layout is faster (38.7 vs 37.7 G rows/s). */
+		p->regslots = p->chunks_per_page >= 10 ? 0 : gg_priv_regslots(&p->prog, p->mode, p->agg.numGroups, p->is_join ? p->join_probe_pc : -1);
+	}
+	const int nslots = p->prog.nslots - p->regslots;
 	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
 	if (p->mode == MODE_TR || p->mode == MODE_TRN) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
 	p->scratch_per_warp = (scr + 15) & ~15;
@@ -304,7 +315,7 @@ static int scanagg_configure(gg_scanagg *p)
 		{
 			/* plans with many value slots (a PARTIAL-stage Q1 carries 8): when 4 stages leave room for fewer than 15
 			 * warps, a 3-page ring with more warps measured faster (13 warps / 3 pages: 3.4 TB/s; 9 / 4: 2.8) */
-			p->nstage = 4; ncons = fit(4, 16);
+			p->nstage = 4; ncons = fit(4, p->regslots > 0 ? 20 : 16);
 			if (ncons < 15) { int w3 = fit(3, 16); if (w3 >= ncons + 3) { p->nstage = 3; ncons = w3; } }
 		}
 		{
@@ -319,6 +330,7 @@ static int scanagg_configure(gg_scanagg *p)
 		if (fixed + (size_t) NT * (8 * nslots + 4) > e->smem_optin) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
 		int gcap = (int) ((e->smem_optin - fixed) / ((size_t) NT * (8 * nslots + 4)));
 		if (gcap > GGP_FAST_GROUPS) gcap = GGP_FAST_GROUPS;
+		if (p->regslots > 0 && gcap > GG_REG_GROUPS) gcap = GG_REG_GROUPS;
 		p->gcap = gcap;
 		p->scratch_off = (uint32_t) (((size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 		p->cnt_off = p->scratch_off + (uint32_t) ncons * p->scratch_per_warp;
@@ -361,8 +373,14 @@ static int scanagg_configure(gg_scanagg *p)
 	}
 	{
 		char jmsg[512];
-		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg);
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, -1, p->regslots);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
+		if (!p->jit && p->regslots > 0)
+		{
+			/* the interpreter kernel addresses value slots dynamically: everything in shared memory */
+			p->regslots = 0;
+			return scanagg_configure(p);
+		}
 		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 	}
 	if (p->mode == MODE_PRIV)
@@ -500,6 +518,7 @@ static int scanagg_adapt_to_pages(gg_scanagg *p, const uint8_t *dev_page, const 
 	const uint32_t pd_lower = hdr[3] & 0xFFFF;
 	int items = pd_lower >= GG_PAGE_HEADER_SIZE && pd_lower <= GG_BLCKSZ ? (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2) : 0;
 	p->chunks_per_page = items > 0 ? (items + 31) / 32 : 1;
+	p->regslots = -1;                          /* decided again for this page density */
 	const int threads0 = p->threads, stages0 = p->nstage;
 	int rc = scanagg_configure(p);
 	if (rc) return rc;

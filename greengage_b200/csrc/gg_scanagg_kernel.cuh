@@ -34,6 +34,27 @@
 namespace ggd {
 
 #define GG_NROUNDS (GGP_MAX_PAIRS / 32)
+#define GG_REG_GROUPS 4        /* register-resident accumulators: groups ... */
+#define GG_REG_SLOTS  3        /* ... x trailing value slots */
+/* the 12 accumulators are separate scalars (arrays inside the sink end up in local memory): X(group, slot) */
+#define GG_RQ_FOREACH(X) X(0, 0) X(0, 1) X(0, 2) X(1, 0) X(1, 1) X(1, 2) X(2, 0) X(2, 1) X(2, 2) X(3, 0) X(3, 1) X(3, 2)
+struct RegAcc {
+#define GG_RQ_DECL(G, J) double r##G##J;
+	GG_RQ_FOREACH(GG_RQ_DECL)
+#undef GG_RQ_DECL
+	__device__ __forceinline__ void zero()
+	{
+#define GG_RQ_ZERO(G, J) r##G##J = 0.0;
+		GG_RQ_FOREACH(GG_RQ_ZERO)
+#undef GG_RQ_ZERO
+	}
+	__device__ __forceinline__ void add(int g, int j, double v)
+	{
+#define GG_RQ_ADD(G, J) if (j == J && g == G) r##G##J = __dadd_rn(r##G##J, v);
+		GG_RQ_FOREACH(GG_RQ_ADD)
+#undef GG_RQ_ADD
+	}
+};
 
 enum { MODE_PRIV = 0, MODE_TR = 1, MODE_TRN = 2,
        MODE_BUILD = 3,     /* Hash node: scan the inner relation into the join hash table (no aggregation) */
@@ -210,6 +231,11 @@ struct RowSink {
 	uint32_t acc_thread;         /* shared address of this thread's slot-0/group-0 accumulator */
 	uint32_t cnt_thread;
 	uint32_t gstride, sstride, cstride;
+	/* MODE_PRIV, plan-specialised kernels with at most GG_REG_GROUPS groups: the last `nreg` value slots are not kept in
+	 * shared memory but in registers (rq[group][slot - nsl]) — predicated adds with compile-time indices.  Frees
+	 * shared memory for more warps / ring stages; folded through the ring's memory in the epilogue. */
+	int nsl, nreg;
+	RegAcc rq;
 	/* MODE_TR */
 	uint32_t sv;                 /* shared address of the warp's transposed values [slot][33] f64 */
 	uint32_t vnull;
@@ -257,7 +283,11 @@ struct RowSink {
 	{
 		if (MODE == MODE_PRIV)
 		{
-			if (gid >= 0)
+			if (slot >= nsl)
+			{
+				rq.add(gid, slot - nsl, v);
+			}
+			else if (gid >= 0)
 			{
 				uint32_t a = acc_thread + (uint32_t) gid * gstride + (uint32_t) slot * sstride;
 				stsf64(a, __dadd_rn(ldsf64(a), v));
@@ -544,6 +574,7 @@ struct DynPlan {
 	__device__ static __forceinline__ int nacc(const ggp_program &P) { return P.nacc; }
 	__device__ static __forceinline__ int ncols(const ggp_program &P) { return P.outer.ncols; }
 	__device__ static __forceinline__ int rowwords(const ggp_program &P) { return P.outer.rowwords; }
+	__device__ static __forceinline__ int regslots(const ggp_program &) { return 0; }       /* interpreter: dynamic slot numbers */
 	__device__ static __forceinline__ uint32_t keytypes(const ggp_program &P)
 	{
 		return (uint32_t) P.keytype[0] | ((uint32_t) P.keytype[1] << 2) | ((uint32_t) P.keytype[2] << 4) | ((uint32_t) P.keytype[3] << 6);
@@ -588,6 +619,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	const int ncols = PL::ncols(P);
 	const int V = nslots > 0 ? nslots : 1;
 	const int gcap = prm.gcap;
+	const int nreg = (MODE == MODE_PRIV) ? PL::regslots(P) : 0;      /* trailing value slots kept in registers */
+	const int nsl = nslots - nreg;                                    /* value slots kept in shared memory */
 
 	if (threadIdx.x == 0)
 	{
@@ -607,8 +640,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		for (int g = 0; g < gcap; g++)
 		{
 			sts32(smem_base + prm.cnt_off + (uint32_t) (g * NT + (int) threadIdx.x) * 4, 0);
-			for (int s = 0; s < nslots; s++)
-				sts64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + s) * NT + (int) threadIdx.x) * 8, 0);
+			for (int s = 0; s < nsl; s++)
+				sts64(smem_base + prm.acc_off + (uint32_t) ((g * nsl + s) * NT + (int) threadIdx.x) * 8, 0);
 		}
 	}
 	__syncthreads();
@@ -644,6 +677,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	}
 	uint32_t err = 0;
 	unsigned long long n_scanned = 0, n_passed = 0;
+	RegAcc rq_keep;                                   /* MODE_PRIV: the thread's register-resident accumulators, for the epilogue */
+	rq_keep.zero();
 
 	if (warp == ncons)
 	{
@@ -698,7 +733,9 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			sink.acc_thread = smem_base + prm.acc_off + threadIdx.x * 8;
 			sink.cnt_thread = smem_base + prm.cnt_off + threadIdx.x * 4;
 			sink.sstride = (uint32_t) NT * 8;
-			sink.gstride = (uint32_t) nslots * NT * 8;
+			sink.gstride = (uint32_t) nsl * NT * 8;
+			sink.nsl = nsl; sink.nreg = nreg;
+			sink.rq.zero();
 			sink.cstride = (uint32_t) NT * 4;
 			sink.sv = sv;
 			sink.jq = false; sink.nullext = false; sink.suppress = false;
@@ -944,6 +981,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		}
 		n_passed = sink.npassed;
 		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
+		if constexpr (MODE == MODE_PRIV) rq_keep = sink.rq;
 	}
 
 	/* ===== epilogue: threads -> block records, all in fixed order ===== */
@@ -977,6 +1015,18 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 
 	if (MODE == MODE_PRIV)
 	{
+		/* register-resident accumulators -> the ring's memory, now that no page in it is in use any more */
+		double *reg_stage = (double *) smem;          /* [GG_REG_GROUPS][GG_REG_SLOTS][NT] <= 48 KB, inside the ring */
+		if (nreg > 0)
+		{
+			if (warp < ncons)
+			{
+#define GG_RQ_STAGE(G, J) if (J < nreg) reg_stage[(G * GG_REG_SLOTS + J) * NT + (int) threadIdx.x] = rq_keep.r##G##J;
+				GG_RQ_FOREACH(GG_RQ_STAGE)
+#undef GG_RQ_STAGE
+			}
+			__syncthreads();
+		}
 		/* one warp per (group, slot): lane l folds threads l, l+32, ... in order, then a fixed butterfly */
 		for (int e = warp; e < G * V; e += (int) (blockDim.x >> 5))
 		{
@@ -987,7 +1037,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			{
 				if (nslots > 0)
 				{
-					const double pv = ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nslots + sl) * NT + t) * 8);
+					const double pv = sl < nsl ? ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nsl + sl) * NT + t) * 8)
+					                           : reg_stage[(g * GG_REG_SLOTS + (sl - nsl)) * NT + t];
 					/* a non-finite private sum is either a legitimate +-Inf/NaN input or a float8pl overflow
 					 * (ERROR in the reference, float.c:782): this variant does not track which, so it asks the host
 					 * to decide by replaying the input on the fully checked interpreter kernel */
