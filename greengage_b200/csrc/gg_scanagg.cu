@@ -283,7 +283,15 @@ static int scanagg_configure(gg_scanagg *p)
 		 * but free shared memory — Q1 one-stage: 20 warps instead of 16 on the 4-page ring, 4.56 -> 4.74 TB/s; Q1
 		 * PARTIAL stage (8 value slots): 16 warps / 4 pages instead of 13 / 3, 3.43 -> 4.15 TB/s.  Dense pages run
 		 * on a 3-page ring where everything fits anyway, and there the plain layout is faster (38.7 vs 37.7 G rows/s). */
-		p->regslots = p->chunks_per_page >= 10 ? 0 : gg_priv_regslots(&p->prog, p->mode, p->agg.numGroups, p->is_join ? p->join_probe_pc : -1);
+		const int rule = gg_priv_regslots(&p->prog, p->mode, p->agg.numGroups, p->is_join ? p->join_probe_pc : -1);
+		p->regslots = rule;
+		if (p->chunks_per_page >= 10)
+		{
+			/* dense pages: plain layout whenever it leaves room for (nearly) all 20 warps on the 3-page ring */
+			const size_t per_warp = (size_t) ((p->prog.outer.ncols * 64 + 15) & ~15) + (size_t) 32 * (8 * p->prog.nslots + 4) * 4;
+			const size_t ring = (size_t) 3 * GG_BLCKSZ + 3 * 16 + sizeof(BlockTable) + 48;
+			if (ring + 18 * per_warp <= e->smem_optin) p->regslots = 0;
+		}
 	}
 	const int nslots = p->prog.nslots - p->regslots;
 	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
@@ -316,6 +324,8 @@ static int scanagg_configure(gg_scanagg *p)
 			/* plans with many value slots (a PARTIAL-stage Q1 carries 8): when 4 stages leave room for fewer than 15
 			 * warps, a 3-page ring with more warps measured faster (13 warps / 3 pages: 3.4 TB/s; 9 / 4: 2.8) */
 			p->nstage = 4; ncons = fit(4, p->regslots > 0 ? 20 : 16);
+			/* a fifth page in flight when it costs no warp (one-stage Q1 with register slots: 4.65 -> 4.84 TB/s) */
+			if (fit(5, ncons) >= ncons) p->nstage = 5;
 			if (ncons < 15) { int w3 = fit(3, 16); if (w3 >= ncons + 3) { p->nstage = 3; ncons = w3; } }
 		}
 		{
