@@ -25,7 +25,7 @@ for f in os.listdir(tmp):
         for ln in txt.splitlines():
             m = re.match(r"\s*\.text\.(\S+):", ln)
             if m:
-                infunc = kname in m.group(1)
+                infunc = m.group(1) == kname or m.group(1).endswith("." + kname)
                 continue
             if ln.startswith("//----") and ".text." in ln:
                 infunc = False
