@@ -1,28 +1,35 @@
 /*
- * gg_scanagg_kernel.cuh — fused heap SeqScan -> qual -> projection -> partial HashAggregate.
+ * gg_scanagg_kernel.cuh — the scan kernel body of the B200 segment engine, in six roles.
  *
- * Replaces, for one segment, the per-tuple loop
+ * Replaces, for one segment, the per-tuple loops
  *   ExecAgg -> agg_hash_initial_pass -> ExecSeqScan -> heap_getnext -> heapgetpage
- *   (nodeAgg.c:1123, execHHashagg.c:905, nodeSeqscan.c:128, heapam.c:312-463,767-1006;
- *    SURVEY §3.3 hot loops B and C)
- * with one persistent, warp-specialised kernel:
+ *   MultiExecHash / ExecHashJoin_guts, the sending half of ExecMotion
+ *   (nodeAgg.c:1123, execHHashagg.c:905, nodeSeqscan.c:128, heapam.c:312-463,767-1006, nodeHash.c:88,
+ *    nodeHashjoin.c:78, nodeMotion.c:270; SURVEY §3.3 hot loops B and C)
+ * with one persistent, warp-specialised kernel body (scanagg_body<MODE, PL, JOIN>):
  *
- *   producer warp    TMA bulk-copies whole 32 KB heap pages HBM -> shared-memory ring
- *                    (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP)
- *   consumer warps   lane = one line pointer: ItemId decode, visibility, attribute walk
- *                    (slot_deform_tuple semantics), then ONE compiled program per row
- *                    (gg_program.h): scan qual -> grouping keys -> group lookup in a per-block
- *                    key table -> aggregate arguments
- *   accumulate       MODE_PRIV: every consumer thread owns a private (group x value-slot) float8
- *                               accumulator array in shared memory, laid out [group][slot][thread]
- *                               so a warp's 32 read-modify-writes hit 32 different banks:
- *                               3 instructions per value, no atomics, no shuffles
- *                    MODE_TR  : "lane owns (group, slot)": the warp's 32 values are transposed
- *                               through shared memory and folded by the owning lane into
- *                               registers (<= 32 groups, <= 128 pairs; min/max/int sums, NULLs)
- *                    Reduction trees are fixed => sums are deterministic run to run.
- *   epilogue         threads -> one record per group and block -> global; a single-block merge
- *                    kernel folds records with equal keys, again in a fixed order.
+ *   producer warp    TMA bulk-copies whole 32 KB heap pages (or 32 KB chunks of datum rows) HBM -> shared-memory
+ *                    ring (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP)
+ *   consumer warps   lane = one line pointer: ItemId decode, visibility, attribute walk (slot_deform_tuple
+ *                    semantics), then ONE compiled program per row (gg_program.h); what the program's
+ *                    post-actions do is the role:
+ *     MODE_PRIV      scan qual -> grouping keys -> group lookup in a per-block key table -> aggregate arguments into
+ *                    per-thread private accumulators: [group][slot][thread] float8 arrays in shared memory (a
+ *                    warp's 32 read-modify-writes hit 32 banks: 3 instructions per value, no atomics, no
+ *                    shuffles) and, in plan-specialised kernels, the last slots in registers (RegAcc)
+ *     MODE_TR/TRN    the same with "lane owns (group, slot)": the warp's 32 values are transposed through shared
+ *                    memory and folded by the owning lane into registers (<= 32 groups, <= 128 pairs; min/max/int
+ *                    sums; TRN tracks NULLs)
+ *     MODE_HASH      the general HashAggregate: groups in one HBM hash table, transition functions as atomics
+ *     MODE_BUILD     Hash node: join keys + payload columns into the join hash table
+ *     JOIN = true    (with PRIV / TR / TRN / HASH) the probe side: every outer row probes the table and each match
+ *                    runs the per-match piece of the program; also the fill-inner pass of right / full joins
+ *     MODE_PART      sending Motion: cdbhash + jump consistent hash, rows packed per destination
+ *   epilogue         PRIV / TR: threads -> one record per group and block -> global; a single-block merge kernel
+ *                    folds records with equal keys.  Every reduction tree is fixed => sums are bit-identical run to
+ *                    run.
+ *   PL               how the kernel reaches the plan: DynPlan interprets the program table; a generated StaticPlan
+ *                    (gg_jit.cpp) carries the same exec_op()/walk_step() calls with literal operands.
  *
  * HBM-bound by construction: algorithmic bytes = nblocks * 32768, each read exactly once.
  */
