@@ -69,6 +69,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def has_sample(self):
+        try:
+            return os.path.getsize(self.path) > 0
+        except OSError:
+            return False
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
@@ -267,12 +273,25 @@ def main():
         return float(t.item())
 
     # ---- resident: W warm-up steps, then exactly K timed steps ----
+    # The clock sampler (nvidia-smi) is started first and the GPU is kept under load, untimed, until its first line is
+    # out: NVML initialisation can stall CUDA calls for hundreds of milliseconds, which must not land in the K steps.
+    # Every sample it takes from then on is under load (pre-steps, warm-up, timed steps).
+    sampler = ClockSampler(device) if rank == 0 else None
+    t_pre = time.time()
+    while True:
+        more = 1 if (rank == 0 and sampler.proc is not None and not sampler.has_sample() and time.time() - t_pre < 8.0) else 0
+        if dist is not None:
+            flag = torch.tensor([more], dtype=torch.int32, device=torch.device("cuda", local_rank))
+            dist.broadcast(flag, 0)
+            more = int(flag.item())
+        if not more:
+            break
+        step_resident()
     for _ in range(args.warmup):
         result, scanned = step_resident()
     assert scanned == nr, (scanned, nr)
     scan_ms_tot, scan_launches = 0.0, 0
     barrier()
-    sampler = ClockSampler(device) if rank == 0 else None
     l0 = eng.launch_count()
     eng.timer_start()
     for _ in range(args.steps):
