@@ -1,5 +1,6 @@
 """Plan compiler (host side, no GPU): expression trees -> accumulator-machine program; eligibility."""
 import ctypes as C
+import os
 
 import pytest
 
@@ -122,3 +123,26 @@ def test_datum_row_input_uses_constant_word_offsets():
     assert "LD_C8" in lines[0] and "off=16" in lines[0] and "KEY0" in lines[0]
     assert "LD_C8" in lines[1] and "off=8" in lines[1]
     assert "LD_C8" in lines[2] and "off=24" in lines[2]
+
+
+def test_generated_kernel_sources_compile_for_sm100a(tmp_path):
+    """The plan-specialised translation units (what NVRTC compiles at run time) must be valid CUDA for every kernel
+    role: checked here with nvcc, without a GPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    L.gg_debug_jit_source_join.argtypes = [C.POINTER(capi.gg_scan), C.POINTER(capi.gg_scan), C.POINTER(capi.gg_hashjoin), C.POINTER(capi.gg_agg),
+                                           C.POINTER(capi.gg_exprpool), C.c_int, C.c_int, C.c_char_p, C.c_int]
+    outer, inner, hj, agg, pool = tpch.join_plan(kind="q3ish", jointype=capi.JOIN_FULL)
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "greengage_b200", "csrc")
+    for which, mode, name in ((0, 3, "build"), (1, 2, "probe_transposed_nulls"), (1, 5, "probe_hashagg")):
+        buf = C.create_string_buffer(1 << 18)
+        n = L.gg_debug_jit_source_join(C.byref(outer), C.byref(inner), C.byref(hj), C.byref(agg), C.byref(pool), which, mode, buf, 1 << 18)
+        assert n > 0, L.gg_last_error()
+        src = tmp_path / (name + ".cu")
+        src.write_text(buf.value.decode())
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", csrc, "-c", str(src), "-o", str(tmp_path / (name + ".o"))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]

@@ -75,3 +75,34 @@ def test_against_reference_objects_when_built():
         ns = rng.choice([1, 2, 3, 5, 8, 13, 64, 999])
         t, vv, ln, nu = (C.c_int32 * 1)(20), (C.c_int64 * 1)(v), (C.c_int32 * 1)(0), (C.c_int32 * 1)(0)
         assert R.ref_cdbhash_route(t, vv, ln, nu, 1, ns) == L.or_route_datums(t, vv, ln, nu, 1, ns)
+
+
+def test_bulk_routing_of_aggregate_rows_matches_the_oracle():
+    """greengage_b200.motion.route_rows_raw (one C call over a gg_aggrow array, what bench.py's Redistribute uses) against
+    the oracle's cdbhash restatement, row by row: int, float8 (incl. -0), packed-string and NULL keys."""
+    import ctypes as C
+    import numpy as np
+    from greengage_b200 import capi, motion
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(31)
+    n = 500
+    rows = (capi.gg_aggrow * n)()
+    typids = [capi.INT8OID, capi.BPCHAROID, capi.FLOAT8OID, capi.INT4OID]
+    for r in rows:
+        r.key[0] = int(rng.integers(-2**40, 2**40))
+        s, ln = capi.pack_str("".join(rng.choice(list("ABCxyz"), int(rng.integers(0, 6)))))
+        r.key[1], r.keylen[1] = s, ln
+        f = float(rng.choice([0.0, -0.0, 1.5, -2.25, 1e300, float(rng.normal())]))
+        r.key[2] = np.float64(f).view(np.int64).item()
+        r.key[3] = int(rng.integers(-1000, 1000))
+        for c in range(4):
+            r.keyisnull[c] = int(rng.random() < 0.15)
+    buf = np.frombuffer(rows, dtype=np.uint8)
+    for nsegs in (1, 2, 3, 8, 64):
+        got = motion.route_rows_raw(buf, n, typids, nsegs)
+        t = (C.c_int32 * 4)(*typids)
+        for i, r in enumerate(rows):
+            v = (C.c_int64 * 4)(*[r.key[c] for c in range(4)])
+            ln = (C.c_int32 * 4)(*[r.keylen[c] for c in range(4)])
+            nn = (C.c_int32 * 4)(*[r.keyisnull[c] for c in range(4)])
+            assert got[i] == po.lib().or_route_datums(t, v, ln, nn, 4, nsegs), (i, nsegs)
