@@ -472,7 +472,7 @@ struct HashSink {
 			{
 				if (atomicCAS(ep, 0ull, GG_HA_LOCKED) == 0ull)
 				{
-					ep[1] = k0;
+					if (ha.nkeys > 0) ep[1] = k0;                /* plain aggregation has no key words: [1] is the row count */
 					if (ha.nkeys > 1) ep[2] = k1;
 					if (ha.nkeys > 2) ep[3] = k2;
 					if (ha.nkeys > 3) ep[4] = k3;
@@ -487,7 +487,7 @@ struct HashSink {
 			if (cur == ready)
 			{
 				const volatile unsigned long long *kp = ep + 1;
-				if (kp[0] == k0 && (ha.nkeys < 2 || kp[1] == k1) && (ha.nkeys < 3 || kp[2] == k2) && (ha.nkeys < 4 || kp[3] == k3))
+				if ((ha.nkeys < 1 || kp[0] == k0) && (ha.nkeys < 2 || kp[1] == k1) && (ha.nkeys < 3 || kp[2] == k2) && (ha.nkeys < 4 || kp[3] == k3))
 				{ e = (long long) slot; break; }
 			}
 			slot = (slot + 1) & (ha.cap - 1);

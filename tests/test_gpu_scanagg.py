@@ -506,3 +506,18 @@ def test_limits_of_the_accelerated_subset(eng):
     agg.numGroups = 0                                        # no planner estimate: the on-chip variants overflow, then the HBM table
     got2, _, _, var2 = gpu_scanagg(eng, scan, agg, p.pool, pages)
     assert_aggrows_match(got2, want, agg)
+
+
+def test_plain_aggregate_on_the_general_hashagg(eng):
+    """numCols == 0 with a planner estimate that sends the plan to the HBM group table: the single group's entry has no
+    key words (found by the randomised join test)."""
+    pages, nb, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 80_000, seed=2))
+    c = tpch.LI_NARROW_COLS
+    p = ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(c["quantity"], capi.FLOAT8OID)),
+                                                   (capi.AGG_MIN_DATE, p.var(c["shipdate"], capi.DATEOID))], num_groups=500)
+    scan = capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW), -1)
+    want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages)
+    got, gsc, gps, var = gpu_scanagg(eng, scan, agg, p.pool, pages)
+    assert var % 16 == 5 and (gsc, gps) == (sc, ps) and len(got) == 1
+    assert_aggrows_match(got, want, agg)
