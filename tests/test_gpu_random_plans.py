@@ -93,7 +93,7 @@ def test_random_plan(eng, relation, seed):
         aggs.append((int(rng.choice([capi.AGG_SUM_INT4, capi.AGG_MIN_INT4, capi.AGG_MAX_INT4])), p.var(int(rng.choice([2, 3])), capi.INT4OID)))
     keys = [[], [p.var(1, capi.INT4OID)], [p.var(1, capi.INT4OID), p.var(6, capi.BPCHAROID)]][int(rng.integers(0, 3))]
     stage = capi.AGGSTAGE_PARTIAL if rng.random() < 0.3 else capi.AGGSTAGE_NORMAL
-    agg = capi.make_agg(stage, keys, aggs, num_groups=int(rng.choice([0, 20, 500]))      # 500: straight to the HBM group table)
+    agg = capi.make_agg(stage, keys, aggs, num_groups=int(rng.choice([0, 20, 500])))      # 500: straight to the HBM group table
     scan = capi.make_scan(desc, qual)
     try:
         want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages)
