@@ -44,6 +44,29 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_quota():
+    """CPUs the container may actually use (cgroup quota), or None: the affinity mask can be far wider than that."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return q / per
+    except Exception:
+        pass
+    return None
+
+
+def cores_note(cores):
+    q = cpu_quota()
+    return "%d threads (affinity mask)%s" % (cores, "" if q is None else ", cgroup CPU quota %.1f" % q)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -150,7 +173,7 @@ def run_reference(args, rank, world):
         "config": {"workload": "Q1 scan+filter+hashagg (no ORDER BY), lineitem-%s, %d rows/GPU" % (args.table, args.rows),
                    "sample_rows": nr, "threads": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of the workload's rows, one oracle thread (= CPU segment) per host core, pages in RAM" % nr},
+                         "sample": "%d of the workload's rows, one oracle thread (= CPU segment) per host core, pages in RAM; %s" % (nr, cores_note(cores))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "setup_s": round(time.time() - t0 - total_secs, 1),
     }
@@ -328,7 +351,7 @@ def main():
         sample = int(min(args.rows, 4_000_000 * cores))
         srows, secs = cpu_baseline_run(table, sample, cores)
         cpu = {"value": srows / secs, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d of the workload's %d rows, one oracle thread (= one CPU segment) per host core, pages in RAM" % (srows, args.rows)}
+               "sample": "%d of the workload's %d rows, one oracle thread (= one CPU segment) per host core, pages in RAM; %s" % (srows, args.rows, cores_note(cores))}
 
     if rank == 0:
         peak, peak_src = measured_peak()
