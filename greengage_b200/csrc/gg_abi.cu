@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "gg_engine.h"
 
 static thread_local char g_err[512] = "";
@@ -257,7 +258,8 @@ extern "C" int gg_debug_disasm_scanagg(const gg_scan *scan, const gg_agg *agg, c
 extern "C" int gg_debug_disasm_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
                                     const gg_exprpool *pool, char *buf, int cap)
 {
-	static ggp_joinprog jp;
+	std::vector<ggp_joinprog> jpbuf(1);     /* ~7 KB: kept off the stack */
+	ggp_joinprog &jp = jpbuf[0];
 	ggp_aggmap aggmap[GG_MAX_AGGS];
 	char msg[256];
 	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &jp, aggmap, msg, sizeof msg);
@@ -290,7 +292,8 @@ extern "C" int gg_debug_jit_source(const gg_scan *scan, const gg_agg *agg, const
 extern "C" int gg_debug_jit_source_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
                                         const gg_exprpool *pool, int which, int mode, char *buf, int cap)
 {
-	static ggp_joinprog jp;
+	std::vector<ggp_joinprog> jpbuf(1);     /* ~7 KB: kept off the stack */
+	ggp_joinprog &jp = jpbuf[0];
 	ggp_aggmap aggmap[GG_MAX_AGGS];
 	char msg[256];
 	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &jp, aggmap, msg, sizeof msg);

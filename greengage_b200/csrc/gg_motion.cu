@@ -27,7 +27,8 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	    first_block + nblocks > r->nblocks || (!device_out_rows && out_cap_rows))
 		return GG_ERR_ARG;
 	GG_CUDA(cudaSetDevice(e->device));
-	static ggp_program prog;              /* 3 KB: kept off the stack */
+	std::vector<ggp_program> progbuf(1);   /* 3 KB: kept off the stack */
+	ggp_program &prog = progbuf[0];
 	uint8_t hashtype[GG_MAX_KEYS] = { 0 };
 	char msg[256];
 	int rc = ggp_compile_motion(scan, pool, hashkeys, nkeys, payload, npayload, &prog, hashtype, msg, sizeof msg);
