@@ -116,3 +116,20 @@ def test_transport_moves_rows_as_routed_over_gloo():
         assert np.array_equal(by[me][5], want) and np.array_equal(by[me][6], wantn)
         assert np.array_equal(by[me][7], np.concatenate([by[0][2][:5], by[1][2][:5]]))     # broadcast: everyone gets everything
     assert np.array_equal(by[0][8], np.concatenate([by[0][2], by[1][2]])) and by[1][8].shape[0] == 0   # gather on segment 0
+
+
+def test_c_example_builds_as_plain_c_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/q1_executor.c drives Q1 through GgExecInitNode / GgExecProcNode in C11 (-pedantic): the headers are a C
+    ABI, not C++.  On a machine without a CUDA device the program must stop at gg_engine_create with the no-fallback
+    message (on the GPU box it prints the Q1 rows)."""
+    exe = tmp_path / "q1_executor"
+    lib = os.path.join(ROOT, "greengage_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "q1_executor.c"), "-L", lib, "-lggexec", "-lggb200", "-lgghost",
+                           "-Wl,-rpath," + lib, "-o", str(exe)])
+    r = subprocess.run([str(exe), "2000"], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "count" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
