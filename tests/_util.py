@@ -98,3 +98,73 @@ def assert_aggrows_match(got, want, agg, rel=1e-6, float_exact=False):
                         assert x == y or (x != x and y != y), (k, i, j, x, y)
                     else:
                         assert abs(x - y) <= rel * abs(y), (k, i, j, x, y)
+
+
+# ---- the reference's regression lineitem / orders as join-shaped relations (tests/golden/*.npz) ----
+
+def tpch_join_fixture():
+    """(li_desc, li_pages, ord_desc, ord_pages, shipmode_code, priority_code): the reference's heap_lineitem / heap_orders
+    regression data, projected to the columns its Q4 and Q12 touch.  Strings longer than 8 bytes become 1-character
+    codes in 1:1 correspondence (l_shipmode -> 'a'.., o_orderpriority -> its first character), so grouping on the code
+    is grouping on the value."""
+    if "join" in _fixture_cache:
+        return _fixture_cache["join"]
+    zl = np.load(os.path.join(GOLD, "lineitem_q1.npz"))
+    li = {k: zl[k] for k in ("orderkey", "shipdate", "commitdate", "receiptdate", "shipmode")}
+    modes = [str(x) for x in zl["shipmode_names"]]
+    zo = np.load(os.path.join(GOLD, "orders_tpch.npz"))
+    od = {k: zo[k] for k in ("orderkey", "orderdate", "orderpriority")}
+    prios = [str(x) for x in zo["orderpriority_names"]]
+    li_desc = make_desc([(capi.INT8OID, 8, "d", 1, 1), (capi.DATEOID, 4, "i", 1, 1), (capi.DATEOID, 4, "i", 1, 1), (capi.DATEOID, 4, "i", 1, 1),
+                         (capi.BPCHAROID, -1, "i", 0, 1)])
+    ord_desc = make_desc([(capi.INT8OID, 8, "d", 1, 1), (capi.DATEOID, 4, "i", 1, 1), (capi.BPCHAROID, -1, "i", 0, 1)])
+    shipmode_code = {m: chr(ord("a") + i) for i, m in enumerate(modes)}
+    priority_code = {p: p[0] for p in prios}
+    li_rows = [[int(li["orderkey"][i]), int(li["shipdate"][i]), int(li["commitdate"][i]), int(li["receiptdate"][i]),
+                shipmode_code[modes[li["shipmode"][i]]].encode()] for i in range(len(li["orderkey"]))]
+    ord_rows = [[int(od["orderkey"][i]), int(od["orderdate"][i]), priority_code[prios[od["orderpriority"][i]]].encode()]
+                for i in range(len(od["orderkey"]))]
+    _fixture_cache["join"] = (li_desc, po.build_pages(li_desc, li_rows), ord_desc, po.build_pages(ord_desc, ord_rows), shipmode_code, priority_code)
+    return _fixture_cache["join"]
+
+
+def tpch_q4_plan(li_desc, ord_desc, exp):
+    """Q4: orders SEMI JOIN lineitem (l_commitdate < l_receiptdate) on the order key, orders filtered on o_orderdate,
+    GROUP BY o_orderpriority, count(*)  (output/rpt_tpch.source, 'mpph4')."""
+    p = capi.ExprPool()
+    okey, odate, oprio = p.var(1, capi.INT8OID, 0), p.var(2, capi.DATEOID, 0), p.var(3, capi.BPCHAROID, 0)
+    lkey, lcommit, lreceipt = p.var(1, capi.INT8OID, 1), p.var(3, capi.DATEOID, 1), p.var(4, capi.DATEOID, 1)
+    oqual = p.boolop(capi.E_AND, p.func(capi.F_DATE_GE, capi.BOOLOID, odate, p.const(capi.DATEOID, exp["orderdate_from"])),
+                     p.func(capi.F_DATE_LT, capi.BOOLOID, odate, p.const(capi.DATEOID, exp["orderdate_to"])))
+    iqual = p.func(capi.F_DATE_LT, capi.BOOLOID, lcommit, lreceipt)
+    outer, inner = capi.make_scan(ord_desc, oqual), capi.make_scan(li_desc, iqual)
+    hj = capi.make_hashjoin(capi.JOIN_SEMI, [okey], [lkey])
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [oprio], [(capi.AGG_COUNT_STAR, -1)])
+    return outer, inner, hj, agg, p.pool
+
+
+def tpch_q12_plan(li_desc, ord_desc, exp, shipmode_code, priority_code, high):
+    """Q12's join: lineitem (its five quals) INNER JOIN orders on the order key, GROUP BY l_shipmode, count(*); the orders
+    side keeps the high-priority orders (high=True: Q12's high_line_count) or the others (low_line_count)."""
+    p = capi.ExprPool()
+    lkey, lship, lcommit, lreceipt, lmode = (p.var(1, capi.INT8OID, 0), p.var(2, capi.DATEOID, 0), p.var(3, capi.DATEOID, 0),
+                                             p.var(4, capi.DATEOID, 0), p.var(5, capi.BPCHAROID, 0))
+    okey, oprio = p.var(1, capi.INT8OID, 1), p.var(3, capi.BPCHAROID, 1)
+    m1, m2 = (shipmode_code[m] for m in exp["shipmodes"])
+    q = p.boolop(capi.E_OR, p.func(capi.F_BPCHAREQ, capi.BOOLOID, lmode, p.const(capi.BPCHAROID, m1)),
+                 p.func(capi.F_BPCHAREQ, capi.BOOLOID, lmode, p.const(capi.BPCHAROID, m2)))
+    for cond in (p.func(capi.F_DATE_LT, capi.BOOLOID, lcommit, lreceipt), p.func(capi.F_DATE_LT, capi.BOOLOID, lship, lcommit),
+                 p.func(capi.F_DATE_GE, capi.BOOLOID, lreceipt, p.const(capi.DATEOID, exp["receipt_from"])),
+                 p.func(capi.F_DATE_LT, capi.BOOLOID, lreceipt, p.const(capi.DATEOID, exp["receipt_to"]))):
+        q = p.boolop(capi.E_AND, q, cond)
+    h1, h2 = (priority_code[x] for x in exp["high_priorities"])
+    if high:
+        iq = p.boolop(capi.E_OR, p.func(capi.F_BPCHAREQ, capi.BOOLOID, oprio, p.const(capi.BPCHAROID, h1)),
+                      p.func(capi.F_BPCHAREQ, capi.BOOLOID, oprio, p.const(capi.BPCHAROID, h2)))
+    else:
+        iq = p.boolop(capi.E_AND, p.func(capi.F_BPCHARNE, capi.BOOLOID, oprio, p.const(capi.BPCHAROID, h1)),
+                      p.func(capi.F_BPCHARNE, capi.BOOLOID, oprio, p.const(capi.BPCHAROID, h2)))
+    outer, inner = capi.make_scan(li_desc, q), capi.make_scan(ord_desc, iq)
+    hj = capi.make_hashjoin(capi.JOIN_INNER, [lkey], [okey])
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [lmode], [(capi.AGG_COUNT_STAR, -1)])
+    return outer, inner, hj, agg, p.pool

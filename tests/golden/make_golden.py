@@ -11,6 +11,8 @@
   lineitem_q1.npz   the reference's own regression data (src/test/regress/data/lineitem_small.csv + lineitem.csv,
                     loaded into heap_lineitem by input/rpt_tpch.source:98-99), columns as arrays
   q1_expected.json  the reference's golden Q1 answer over that data (output/rpt_tpch.source:309-315)
+  orders_tpch.npz   heap_orders of the same suite (order_small.csv + order.csv)
+  tpch_join_expected.json  the reference's golden Q4 (semi join) and Q12 (inner join) answers over heap_orders/heap_lineitem
 """
 import ctypes as C
 import json
@@ -256,9 +258,63 @@ def lineitem_fixture():
     print("lineitem_q1.npz", len(rows), "rows; q1_expected.json", exp[0])
 
 
+def orders_fixture():
+    """heap_orders as the reference loads it (order_small.csv + order.csv, input/rpt_tpch.source:92-93) and the golden
+    answers of the two TPC-H queries of its regression suite that are a lineitem-orders hash join with an aggregate
+    on top: Q4 (semi join, output/rpt_tpch.source 'mpph4') and Q12 (inner join, 'mpph12')."""
+    rows = []
+    for fn in ("order_small.csv", "order.csv"):
+        for ln in open(os.path.join(REF, "src/test/regress/data", fn), encoding="latin1"):
+            f = ln.rstrip("\n").split("|")
+            if len(f) >= 9:
+                rows.append(f[:9])
+    epoch = date(2000, 1, 1)
+
+    def d2i(s):
+        y, m, d = map(int, s.split("-"))
+        return (date(y, m, d) - epoch).days
+
+    prios = sorted({r[5] for r in rows})
+    np.savez_compressed(
+        os.path.join(HERE, "orders_tpch.npz"),
+        orderkey=np.array([int(r[0]) for r in rows], dtype=np.int64), custkey=np.array([int(r[1]) for r in rows], dtype=np.int32),
+        orderstatus=np.array([ord(r[2]) for r in rows], dtype=np.uint8), totalprice=np.array([float(r[3]) for r in rows]),
+        orderdate=np.array([d2i(r[4]) for r in rows], dtype=np.int32),
+        orderpriority=np.array([prios.index(r[5]) for r in rows], dtype=np.uint8), orderpriority_names=np.array(prios),
+        shippriority=np.array([int(r[7]) for r in rows], dtype=np.int32))
+    txt = open(os.path.join(REF, "src/test/regress/output/rpt_tpch.source")).read().splitlines()
+
+    def answer(tag, first_from):
+        """rows of the first result block tagged `tag` whose query reads `first_from` (the heap_ tables)"""
+        out = []
+        for i, ln in enumerate(txt):
+            if ln.strip().startswith("select  '%s'," % tag) and any(first_from in x for x in txt[i:i + 30]):
+                j = i
+                while not txt[j].startswith("----------+"):
+                    j += 1
+                j += 1
+                while txt[j].strip().startswith(tag + " "):
+                    out.append([x.strip() for x in txt[j].split("|")][1:])
+                    j += 1
+                return out
+        raise AssertionError(tag)
+
+    q4 = answer("mpph4", "heap_orders")
+    q12 = answer("mpph12", "heap_orders")
+    json.dump({"source": "src/test/regress/output/rpt_tpch.source (mpph4, mpph12 over heap_orders/heap_lineitem)",
+               "q4": {"orderdate_from": d2i("1994-05-01"), "orderdate_to": d2i("1994-08-01"),
+                      "rows": [{"orderpriority": r[0], "order_count": int(r[1])} for r in q4]},
+               "q12": {"shipmodes": ["RAIL", "MAIL"], "receipt_from": d2i("1993-01-01"), "receipt_to": d2i("1994-01-01"),
+                       "high_priorities": ["1-URGENT", "2-HIGH"],
+                       "rows": [{"shipmode": r[0], "high_line_count": int(r[1]), "low_line_count": int(r[2])} for r in q12]},
+               "norders_loaded": len(rows)}, open(os.path.join(HERE, "tpch_join_expected.json"), "w"), indent=1)
+    print("orders_tpch.npz", len(rows), "rows; q4", q4, "q12", q12)
+
+
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
     hash_kat()
     heap_kat()
     float_kat()
     lineitem_fixture()
+    orders_fixture()
