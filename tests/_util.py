@@ -168,3 +168,24 @@ def tpch_q12_plan(li_desc, ord_desc, exp, shipmode_code, priority_code, high):
     hj = capi.make_hashjoin(capi.JOIN_INNER, [lkey], [okey])
     agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [lmode], [(capi.AGG_COUNT_STAR, -1)])
     return outer, inner, hj, agg, p.pool
+
+
+def tpch_q6_plan(desc):
+    """Q6 over the reference's regression lineitem (output/rpt_tpch.source 'mpph6', golden revenue 740117.7050):
+    sum(l_extendedprice * l_discount) where l_shipdate in 1996, l_discount between 0.03 and 0.05, l_quantity < 24."""
+    from datetime import date
+    p = capi.ExprPool()
+    qty, price, disc, shipdate = p.var(5, capi.FLOAT8OID), p.var(6, capi.FLOAT8OID), p.var(7, capi.FLOAT8OID), p.var(11, capi.DATEOID)
+    d0 = (date(1996, 1, 1) - date(2000, 1, 1)).days
+    d1 = (date(1997, 1, 1) - date(2000, 1, 1)).days
+    q = p.func(capi.F_DATE_GE, capi.BOOLOID, shipdate, p.const(capi.DATEOID, d0))
+    for cond in (p.func(capi.F_DATE_LT, capi.BOOLOID, shipdate, p.const(capi.DATEOID, d1)),
+                 p.func(capi.F_FLOAT8GE, capi.BOOLOID, disc, p.const(capi.FLOAT8OID, 0.03)),
+                 p.func(capi.F_FLOAT8LE, capi.BOOLOID, disc, p.const(capi.FLOAT8OID, 0.05)),
+                 p.func(capi.F_FLOAT8LT, capi.BOOLOID, qty, p.const(capi.FLOAT8OID, 24.0))):
+        q = p.boolop(capi.E_AND, q, cond)
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(capi.AGG_SUM_FLOAT8, p.func(capi.F_FLOAT8MUL, capi.FLOAT8OID, price, disc)), (capi.AGG_COUNT_STAR, -1)])
+    return capi.make_scan(desc, q), agg, p.pool
+
+
+Q6_GOLDEN_REVENUE = 740117.7050          # src/test/regress/output/rpt_tpch.source:531 (numeric; float8 columns here: <= 1e-6 relative)

@@ -146,3 +146,15 @@ def test_generated_kernel_sources_compile_for_sm100a(tmp_path):
         r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-I", csrc, "-c", str(src), "-o", str(tmp_path / (name + ".o"))],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_q6_plan_compiles_to_one_filter_and_one_sum():
+    """The Q6 plan the golden tests run (tests/_util.tpch_q6_plan): the five range predicates are three-valued ANDs feeding
+    one FILTER in front of the single accumulate, and the plan has no group key (private-accumulator kernel)."""
+    from _util import lineitem_fixture_pages, tpch_q6_plan
+    desc, _, _ = lineitem_fixture_pages()
+    lines = disasm(*tpch_q6_plan(desc))
+    assert sum(1 for ln in lines if "FILTER" in ln) == 1 and sum(1 for ln in lines if "AND_T" in ln) == 4
+    assert sum(1 for ln in lines if "CMPF_K" in ln) == 3 and sum(1 for ln in lines if "CMPI_K" in ln) == 2
+    assert sum(1 for ln in lines if "OUT" in ln and "OUTSQ" not in ln) == 1 and not any("KEY" in ln for ln in lines)
+    assert lines[-1].split()[1] == "END"

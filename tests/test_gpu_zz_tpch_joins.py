@@ -36,3 +36,16 @@ def test_q12_inner_join_counts_are_the_references(eng):
         rows, nj, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, li_pages, ord_pages)
         got = {capi.unpack_str(r.key[0], r.keylen[0]): r.agg[0].i for r in rows}
         assert got == {shipmode_code[e["shipmode"]]: e[col] for e in exp["rows"]}, (col, got)
+
+
+def test_q6_revenue_is_the_references(eng):
+    """Q6 ('mpph6'): scan -> five range predicates -> plain aggregate, against the reference's golden revenue and the oracle."""
+    from _util import Q6_GOLDEN_REVENUE, lineitem_fixture_pages, tpch_q6_plan
+    from oracle import pyoracle as po
+    from test_gpu_scanagg import gpu_scanagg
+    desc, pages, n = lineitem_fixture_pages()
+    scan, agg, pool = tpch_q6_plan(desc)
+    want, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
+    got, gsc, gps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
+    assert (gsc, gps) == (sc, ps) and len(got) == 1 and got[0].agg[1].i == want[0].agg[1].i
+    assert abs(got[0].agg[0].f[0] - Q6_GOLDEN_REVENUE) <= 1e-6 * Q6_GOLDEN_REVENUE, got[0].agg[0].f[0]

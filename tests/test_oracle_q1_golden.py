@@ -73,3 +73,15 @@ def test_count_star_two_segment_plumbing():
     ptrs = (C.c_void_p * 2)(*[p.ctypes.data for p, _ in segs])
     nbs = (C.c_uint64 * 2)(*[nb for _, nb in segs])
     assert po.lib().or_count_star_2stage(ptrs, nbs, 2) == 100000
+
+
+def test_q6_revenue_is_the_references():
+    """A second golden answer of the same suite for the scan -> qual -> aggregate path: Q6 ('mpph6', a plain aggregate
+    behind five range predicates)."""
+    from _util import Q6_GOLDEN_REVENUE, lineitem_fixture_pages, tpch_q6_plan
+    from oracle import pyoracle as po
+    desc, pages, n = lineitem_fixture_pages()
+    scan, agg, pool = tpch_q6_plan(desc)
+    rows, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
+    assert sc == n and len(rows) == 1 and 0 < ps < n
+    assert abs(rows[0].agg[0].f[0] - Q6_GOLDEN_REVENUE) <= 1e-6 * Q6_GOLDEN_REVENUE, rows[0].agg[0].f[0]
