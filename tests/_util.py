@@ -189,3 +189,68 @@ def tpch_q6_plan(desc):
 
 
 Q6_GOLDEN_REVENUE = 740117.7050          # src/test/regress/output/rpt_tpch.source:531 (numeric; float8 columns here: <= 1e-6 relative)
+
+
+def j1j2_fixture():
+    """(j1_desc, j1_pages, j2_desc, j2_pages, golden): J1_TBL(i int4, j int4, t text) / J2_TBL(i int4, k int4) of the
+    reference's sql/join.sql:6-38 and its expected/join.out answers (tests/golden/join_j1j2.json)."""
+    if "j1j2" not in _fixture_cache:
+        g = golden("join_j1j2.json")
+        d1 = make_desc([(capi.INT4OID, 4, "i", 1), (capi.INT4OID, 4, "i", 1), (capi.TEXTOID, -1, "i", 0)])
+        d2 = make_desc([(capi.INT4OID, 4, "i", 1), (capi.INT4OID, 4, "i", 1)])
+        r1 = [[r[0] or 0, r[1] or 0, (r[2] or "").encode()] for r in g["j1"]]
+        r2 = [[r[0] or 0, r[1] or 0] for r in g["j2"]]
+        n1 = [[v is None for v in r] for r in g["j1"]]
+        n2 = [[v is None for v in r] for r in g["j2"]]
+        _fixture_cache["j1j2"] = (d1, po.build_pages(d1, r1, n1), d2, po.build_pages(d2, r2, n2), g)
+    return _fixture_cache["j1j2"]
+
+
+J1J2_QUERIES = {"inner": (capi.JOIN_INNER, 1), "inner_i_eq_k": (capi.JOIN_INNER, 2), "left": (capi.JOIN_LEFT, 1),
+                "right": (capi.JOIN_RIGHT, 1), "full": (capi.JOIN_FULL, 1)}      # name -> (jointype, J2 key attno)
+
+
+def j1j2_join(d1, d2, name):
+    """J1_TBL <jointype> JOIN J2_TBL ON J1.i = J2.<i|k> -> (pool, outer scan, inner scan, hashjoin)"""
+    jt, inner_att = J1J2_QUERIES[name]
+    p = capi.ExprPool()
+    hj = capi.make_hashjoin(jt, [p.var(1, capi.INT4OID, 0)], [p.var(inner_att, capi.INT4OID, 1)], -1)
+    return p, capi.make_scan(d1, -1), capi.make_scan(d2, -1), hj
+
+
+def j1j2_golden_rows(g, name):
+    """the golden table as (J1.i-or-coalesced i, j, t, k) tuples; for ON (J1.i = J2.k) the extra J2.i column is kept last"""
+    q = g["queries"][name]
+    return [tuple(r) for r in q["rows"]]
+
+
+def j1j2_agg(p):
+    """GROUP BY J1.i: count(*), sum(J1.j), count(J1.j), sum(J2.k), count(J2.k) — what a join that is never materialised can
+    be held to against the golden table (the row multiset per group, reduced)."""
+    return capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(1, capi.INT4OID, 0)],
+                         [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_INT4, p.var(2, capi.INT4OID, 0)), (capi.AGG_COUNT_ANY, p.var(2, capi.INT4OID, 0)),
+                          (capi.AGG_SUM_INT4, p.var(2, capi.INT4OID, 1)), (capi.AGG_COUNT_ANY, p.var(2, capi.INT4OID, 1))])
+
+
+def j1j2_golden_groups(g, name):
+    """{J1.i or None: [count, sum_j or None, count_j, sum_k or None, count_k]} from the golden table.  J1.i of a row is
+    recovered from its t column (unique per J1 row up to the two 'zero' rows, which differ in i IS NULL <=> j = 0)."""
+    groups = {}
+    for r in j1j2_golden_rows(g, name):
+        i, j, t, k = r[0], r[1], r[2], r[-1]
+        j1_i = None if t is None else next(x[0] for x in g["j1"] if x[2] == t and x[1] == j)
+        a = groups.setdefault(j1_i, [0, None, 0, None, 0])
+        a[0] += 1
+        if j is not None:
+            a[1], a[2] = (a[1] or 0) + j, a[2] + 1
+        if k is not None:
+            a[3], a[4] = (a[3] or 0) + k, a[4] + 1
+    return groups
+
+
+def j1j2_check_groups(rows, want):
+    got = {}
+    for r in rows:
+        key = None if r.keyisnull[0] else int(np.int32(r.key[0] & 0xFFFFFFFF))
+        got[key] = [r.agg[0].i, None if r.agg[1].isnull else r.agg[1].i, r.agg[2].i, None if r.agg[3].isnull else r.agg[3].i, r.agg[4].i]
+    assert got == want, (got, want)

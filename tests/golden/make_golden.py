@@ -13,6 +13,7 @@
   q1_expected.json  the reference's golden Q1 answer over that data (output/rpt_tpch.source:309-315)
   orders_tpch.npz   heap_orders of the same suite (order_small.csv + order.csv)
   tpch_join_expected.json  the reference's golden Q4 (semi join) and Q12 (inner join) answers over heap_orders/heap_lineitem
+  join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
 import ctypes as C
 import json
@@ -311,6 +312,46 @@ def orders_fixture():
     print("orders_tpch.npz", len(rows), "rows; q4", q4, "q12", q12)
 
 
+def join_j1j2_fixture():
+    """J1_TBL / J2_TBL of the reference's join regression test (sql/join.sql:6-38: NULL keys, duplicate keys, keys only one
+    side has) and its golden result tables for the equi-joins of every outer-join type (expected/join.out)."""
+    sql = open(os.path.join(REF, "src/test/regress/sql/join.sql")).read().splitlines()
+
+    def inserts(tab):
+        rows = []
+        for ln in sql:
+            if ln.startswith("INSERT INTO %s VALUES (" % tab):
+                vals = [v.strip() for v in ln[ln.index("(") + 1:ln.rindex(")")].split(",")]
+                rows.append([None if v == "NULL" else (v.strip("'") if v.startswith("'") else int(v)) for v in vals])
+        return rows
+
+    out = open(os.path.join(REF, "src/test/regress/expected/join.out")).read().splitlines()
+
+    def answer(from_clause):
+        i = next(n for n, ln in enumerate(out) if ln.strip().startswith(from_clause))
+        while not out[i].startswith("-----+"):
+            i += 1
+        cols = [c.strip() for c in out[i - 1].split("|")][1:]
+        rows = []
+        i += 1
+        while not out[i].startswith("("):
+            f = [x.strip() for x in out[i].split("|")][1:]
+            rows.append([None if x == "" else (x if c == "t" else int(x)) for c, x in zip(cols, f)])
+            i += 1
+        assert out[i] == "(%d rows)" % len(rows), (from_clause, out[i], len(rows))
+        return {"cols": cols, "rows": rows}
+
+    q = {"inner": answer("FROM J1_TBL INNER JOIN J2_TBL USING (i);"),
+         "inner_i_eq_k": answer("FROM J1_TBL JOIN J2_TBL ON (J1_TBL.i = J2_TBL.k);"),
+         "left": answer("FROM J1_TBL LEFT OUTER JOIN J2_TBL USING (i)"),
+         "right": answer("FROM J1_TBL RIGHT OUTER JOIN J2_TBL USING (i);"),
+         "full": answer("FROM J1_TBL FULL OUTER JOIN J2_TBL USING (i)")}
+    json.dump({"source": "src/test/regress/sql/join.sql:6-38 (tables), expected/join.out (answers)",
+               "j1": inserts("J1_TBL"), "j2": inserts("J2_TBL"), "queries": q},
+              open(os.path.join(HERE, "join_j1j2.json"), "w"), indent=1)
+    print("join_j1j2.json", {k: len(v["rows"]) for k, v in q.items()})
+
+
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
     hash_kat()
@@ -318,3 +359,4 @@ if __name__ == "__main__":
     float_kat()
     lineitem_fixture()
     orders_fixture()
+    join_j1j2_fixture()

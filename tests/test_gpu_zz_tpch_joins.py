@@ -49,3 +49,16 @@ def test_q6_revenue_is_the_references(eng):
     got, gsc, gps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
     assert (gsc, gps) == (sc, ps) and len(got) == 1 and got[0].agg[1].i == want[0].agg[1].i
     assert abs(got[0].agg[0].f[0] - Q6_GOLDEN_REVENUE) <= 1e-6 * Q6_GOLDEN_REVENUE, got[0].agg[0].f[0]
+
+
+@pytest.mark.parametrize("name", ["inner", "inner_i_eq_k", "left", "right", "full"])
+def test_j1j2_joins_reduce_the_references_golden_tables(eng, name):
+    """J1_TBL / J2_TBL of the reference's sql/join.sql and the golden inner / left / right / full tables of expected/join.out
+    (NULL keys on both sides, duplicate inner keys), consumed by GROUP BY J1.i aggregates; tests/test_oracle_join_golden.py
+    holds the oracle to the same tables row by row."""
+    from _util import j1j2_agg, j1j2_check_groups, j1j2_fixture, j1j2_golden_groups, j1j2_join
+    d1, p1, d2, p2, g = j1j2_fixture()
+    p, outer, inner, hj = j1j2_join(d1, d2, name)
+    rows, nj, _ = gpu_joinagg(eng, outer, inner, hj, j1j2_agg(p), p.pool, p1, p2)
+    assert nj == len(g["queries"][name]["rows"])
+    j1j2_check_groups(rows, j1j2_golden_groups(g, name))
