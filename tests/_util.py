@@ -254,3 +254,34 @@ def j1j2_check_groups(rows, want):
         key = None if r.keyisnull[0] else int(np.int32(r.key[0] & 0xFFFFFFFF))
         got[key] = [r.agg[0].i, None if r.agg[1].isnull else r.agg[1].i, r.agg[2].i, None if r.agg[3].isnull else r.agg[3].i, r.agg[4].i]
     assert got == want, (got, want)
+
+
+def sort_golden_cases():
+    """[(name, keys, shuffled input rows [n,1] int64, nulls [n,1], golden rows in order, golden nulls)] from the reference's
+    expected/sort.out (tests/golden/sort_golden.json): input = the golden values in a fixed shuffled order."""
+    g = golden("sort_golden.json")
+    typid = {"int8": capi.INT8OID, "int4": capi.INT4OID, "date": capi.DATEOID, "float8": capi.FLOAT8OID, "bpchar": capi.BPCHAROID}
+
+    def datum(t, v):
+        if v is None:
+            return 0
+        if t == "float8":
+            return f2b(v)
+        if t in ("bpchar", "text"):
+            return capi.pack_str(v)[0]
+        return int(v)
+
+    def case(name, t, oid, want, desc, nulls_first):
+        rng = np.random.default_rng(len(name) * 7 + desc)
+        order = rng.permutation(len(want))
+        w = np.array([[datum(t, v)] for v in want], dtype=np.int64)
+        wn = np.array([[v is None] for v in want], dtype=np.uint8)
+        return (name, [capi.make_sortkey(0, oid, desc, nulls_first)], w[order], wn[order], w, wn)
+
+    cases = []
+    for col, c in g["alltypes"].items():
+        cases.append(case(col + "-asc", c["type"], typid[c["type"]], c["asc"], False, None))
+        cases.append(case(col + "-desc", c["type"], typid[c["type"]], c["desc"], True, None))
+    cases.append(case("colltest-nulls-last", "text", capi.TEXTOID, g["colltest"]["nulls_last"], False, None))
+    cases.append(case("colltest-nulls-first", "text", capi.TEXTOID, g["colltest"]["nulls_first"], False, True))
+    return cases

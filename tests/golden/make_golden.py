@@ -13,6 +13,7 @@
   q1_expected.json  the reference's golden Q1 answer over that data (output/rpt_tpch.source:309-315)
   orders_tpch.npz   heap_orders of the same suite (order_small.csv + order.csv)
   tpch_join_expected.json  the reference's golden Q4 (semi join) and Q12 (inner join) answers over heap_orders/heap_lineitem
+  sort_golden.json  ORDER BY answers of expected/sort.out for the column types the Sort path takes, ASC/DESC, NULLS FIRST/LAST
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
 import ctypes as C
@@ -352,6 +353,39 @@ def join_j1j2_fixture():
     print("join_j1j2.json", {k: len(v["rows"]) for k, v in q.items()})
 
 
+def sort_fixture():
+    """Golden ORDER BY answers of the reference's sort regression test (expected/sort.out): gpsort_alltypes columns of the
+    types the Sort path takes (int8, char, date, float8, int4), ASC and DESC, and colltest's text COLLATE "C" with NULLS
+    LAST / NULLS FIRST through a merging Gather Motion."""
+    out = open(os.path.join(REF, "src/test/regress/expected/sort.out")).read().splitlines()
+    epoch = date(2000, 1, 1)
+
+    def block(query):
+        i = out.index(query)
+        while not out[i].startswith("---"):
+            i += 1
+        rows = []
+        i += 1
+        while not out[i].startswith("("):
+            rows.append(out[i].strip())
+            i += 1
+        assert out[i] == "(%d rows)" % len(rows), (query, out[i])
+        return rows
+
+    conv = {"int8": int, "int4": int, "float8": float, "bpchar": str,
+            "date": lambda x: (date(int(x[6:]), int(x[:2]), int(x[3:5])) - epoch).days}       # regression DateStyle: MM-DD-YYYY
+    cols = {}
+    for col, typ in (("col1", "int8"), ("col6", "bpchar"), ("col10", "date"), ("col12", "float8"), ("col14", "int4")):
+        cols[col] = {"type": typ,
+                     "asc": [conv[typ](x) for x in block("select %s from gpsort_alltypes order by %s asc;" % (col, col))],
+                     "desc": [conv[typ](x) for x in block("select %s from gpsort_alltypes order by %s desc;" % (col, col))]}
+    coll = {"nulls_last": [x or None for x in block('select * from colltest order by t COLLATE "C";')],
+            "nulls_first": [x or None for x in block('select * from colltest order by t COLLATE "C" NULLS FIRST;')]}
+    json.dump({"source": "src/test/regress/expected/sort.out (gpsort_alltypes, colltest)", "alltypes": cols, "colltest": coll},
+              open(os.path.join(HERE, "sort_golden.json"), "w"), indent=1)
+    print("sort_golden.json", {k: v["asc"] for k, v in cols.items()}, coll)
+
+
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
     hash_kat()
@@ -360,3 +394,4 @@ if __name__ == "__main__":
     lineitem_fixture()
     orders_fixture()
     join_j1j2_fixture()
+    sort_fixture()

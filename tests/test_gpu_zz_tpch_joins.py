@@ -62,3 +62,13 @@ def test_j1j2_joins_reduce_the_references_golden_tables(eng, name):
     rows, nj, _ = gpu_joinagg(eng, outer, inner, hj, j1j2_agg(p), p.pool, p1, p2)
     assert nj == len(g["queries"][name]["rows"])
     j1j2_check_groups(rows, j1j2_golden_groups(g, name))
+
+
+def test_order_by_answers_are_the_references(eng):
+    """Golden ORDER BY outputs of the reference's expected/sort.out through the device sort (gg_sort_rows)."""
+    import numpy as np
+    from _util import sort_golden_cases
+    from greengage_b200.engine import sort_rows
+    for name, keys, rows, nulls, want, wantnulls in sort_golden_cases():
+        perm = sort_rows(eng, keys, rows, nulls).astype(np.int64)
+        assert np.array_equal(rows[perm], want) and np.array_equal(nulls[perm], wantnulls), name

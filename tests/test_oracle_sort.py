@@ -71,3 +71,14 @@ def test_sort_perm_is_sorted_under_the_comparator():
     for i in range(n - 1):
         a, b = perm[i], perm[i + 1]
         assert compare(keys, rows[a].tolist(), rows[b].tolist(), nulls[a].tolist(), nulls[b].tolist()) <= 0
+
+
+def test_order_by_answers_are_the_references():
+    """Golden ORDER BY outputs of the reference's sort regression test (expected/sort.out: int8, char, date, float8, int4
+    columns ASC and DESC; text COLLATE "C" with NULLS LAST and NULLS FIRST)."""
+    from _util import sort_golden_cases
+    cases = sort_golden_cases()
+    assert len(cases) == 12
+    for name, keys, rows, nulls, want, wantnulls in cases:
+        perm = po.sort_perm(keys, 1, rows, nulls).astype(np.int64)
+        assert np.array_equal(rows[perm], want) and np.array_equal(nulls[perm], wantnulls), name
