@@ -285,3 +285,32 @@ def sort_golden_cases():
     cases.append(case("colltest-nulls-last", "text", capi.TEXTOID, g["colltest"]["nulls_last"], False, None))
     cases.append(case("colltest-nulls-first", "text", capi.TEXTOID, g["colltest"]["nulls_first"], False, True))
     return cases
+
+
+def onek_fixture():
+    """(desc, pages, expected): the regression suite's onek table (13 int4 columns, 1000 rows) and the golden aggregates of
+    expected/aggregates.out over it (tests/golden/onek.npz, onek_agg_expected.json)."""
+    if "onek" not in _fixture_cache:
+        ints = np.load(os.path.join(GOLD, "onek.npz"))["ints"]
+        desc = make_desc([(capi.INT4OID, 4, "i", 1)] * ints.shape[1])
+        _fixture_cache["onek"] = (desc, po.build_pages(desc, [[int(v) for v in r] for r in ints]), golden("onek_agg_expected.json"))
+    return _fixture_cache["onek"]
+
+
+def onek_plans(desc, exp):
+    """-> (plain, grouped): `sum(four), max(four), count(four)` and `ten, count(*), sum(four) GROUP BY ten`
+    (sql/aggregates.sql:22,27,70,73)"""
+    four, ten = exp["columns"].index("four") + 1, exp["columns"].index("ten") + 1
+    p = capi.ExprPool()
+    plain = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(capi.AGG_SUM_INT4, p.var(four, capi.INT4OID)), (capi.AGG_MAX_INT4, p.var(four, capi.INT4OID)),
+                                                     (capi.AGG_COUNT_ANY, p.var(four, capi.INT4OID))])
+    grouped = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(ten, capi.INT4OID)], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_INT4, p.var(four, capi.INT4OID))])
+    return (capi.make_scan(desc, -1), plain, p.pool), (capi.make_scan(desc, -1), grouped, p.pool)
+
+
+def onek_check(exp, plain_rows, grouped_rows):
+    assert len(plain_rows) == 1
+    a = plain_rows[0].agg
+    assert (a[0].i, a[1].i, a[2].i) == (exp["sum_four"], exp["max_four"], exp["count_four"])
+    got = sorted([int(np.int32(r.key[0] & 0xFFFFFFFF)), r.agg[0].i, r.agg[1].i] for r in grouped_rows)
+    assert got == exp["by_ten"], got

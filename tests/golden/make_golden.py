@@ -13,6 +13,7 @@
   q1_expected.json  the reference's golden Q1 answer over that data (output/rpt_tpch.source:309-315)
   orders_tpch.npz   heap_orders of the same suite (order_small.csv + order.csv)
   tpch_join_expected.json  the reference's golden Q4 (semi join) and Q12 (inner join) answers over heap_orders/heap_lineitem
+  onek.npz + onek_agg_expected.json  the suite's onek table (int4 columns) and the golden plain / hashed aggregates of aggregates.out
   sort_golden.json  ORDER BY answers of expected/sort.out for the column types the Sort path takes, ASC/DESC, NULLS FIRST/LAST
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
@@ -386,6 +387,36 @@ def sort_fixture():
     print("sort_golden.json", {k: v["asc"] for k, v in cols.items()}, coll)
 
 
+def onek_fixture():
+    """onek of the reference's regression suite (data/onek.data, 1000 rows; the 13 int4 columns of sql/create_table.sql:18-34)
+    and the golden aggregates over it in expected/aggregates.out: sum(four), max(four), count(four), and the hashed
+    `select ten, count(*), sum(four) from onek group by ten`."""
+    rows = [[int(x) for x in ln.split("\t")[:13]] for ln in open(os.path.join(REF, "src/test/regress/data/onek.data"))]
+    np.savez_compressed(os.path.join(HERE, "onek.npz"), ints=np.array(rows, dtype=np.int32))
+    out = open(os.path.join(REF, "src/test/regress/expected/aggregates.out")).read().splitlines()
+
+    def block(query):
+        i = out.index(query)
+        while not out[i].startswith("---"):
+            i += 1
+        rows = []
+        i += 1
+        while not out[i].startswith("("):
+            rows.append([int(x) for x in out[i].split("|")])
+            i += 1
+        return rows
+
+    json.dump({"source": "src/test/regress/expected/aggregates.out:30-34,54-58,256-260,268-282",
+               "columns": ["unique1", "unique2", "two", "four", "ten", "twenty", "hundred", "thousand", "twothousand", "fivethous",
+                           "tenthous", "odd", "even"],
+               "sum_four": block("SELECT sum(four) AS sum_1500 FROM onek;")[0][0],
+               "max_four": block("SELECT max(four) AS max_3 FROM onek;")[0][0],
+               "count_four": block("SELECT count(four) AS cnt_1000 FROM onek;")[0][0],
+               "by_ten": block("select ten, count(*), sum(four) from onek")},
+              open(os.path.join(HERE, "onek_agg_expected.json"), "w"), indent=1)
+    print("onek.npz", len(rows), "rows")
+
+
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
     hash_kat()
@@ -395,3 +426,4 @@ if __name__ == "__main__":
     orders_fixture()
     join_j1j2_fixture()
     sort_fixture()
+    onek_fixture()

@@ -1,6 +1,8 @@
-"""GPU HashJoin + Agg against the REFERENCE'S OWN golden answers: TPC-H Q4 (semi join) and Q12 (inner join) of its
-regression suite over its regression data (src/test/regress/output/rpt_tpch.source 'mpph4' / 'mpph12').  The same plans
-and fixtures as tests/test_oracle_tpch_joins.py, which holds the oracle to those answers on every CPU run."""
+"""The GPU path against the REFERENCE'S OWN golden answers (its regression suite's expected outputs over its own data):
+TPC-H Q4 (semi join), Q12 (inner join) and Q6 (range predicates + plain aggregate) of output/rpt_tpch.source; the inner /
+left / right / full join tables of expected/join.out; the ORDER BY answers of expected/sort.out; the integer and hashed
+aggregates of expected/aggregates.out.  Same plans and fixtures as the tests/test_oracle_*golden* tests, which hold the oracle
+to those answers on every CPU run.  (Q1's golden is tests/test_gpu_scanagg.py / test_gpu_executor.py.)"""
 import pytest
 
 from _util import golden, tpch_join_fixture, tpch_q4_plan, tpch_q12_plan
@@ -72,3 +74,12 @@ def test_order_by_answers_are_the_references(eng):
     for name, keys, rows, nulls, want, wantnulls in sort_golden_cases():
         perm = sort_rows(eng, keys, rows, nulls).astype(np.int64)
         assert np.array_equal(rows[perm], want) and np.array_equal(nulls[perm], wantnulls), name
+
+
+def test_onek_aggregates_are_the_references(eng):
+    """expected/aggregates.out over onek: sum/max/count of an int4 column, and `ten, count(*), sum(four) GROUP BY ten`."""
+    from _util import onek_check, onek_fixture, onek_plans
+    from test_gpu_scanagg import gpu_scanagg
+    desc, pages, exp = onek_fixture()
+    plain, grouped = onek_plans(desc, exp)
+    onek_check(exp, gpu_scanagg(eng, *plain, pages)[0], gpu_scanagg(eng, *grouped, pages)[0])

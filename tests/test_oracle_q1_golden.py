@@ -85,3 +85,14 @@ def test_q6_revenue_is_the_references():
     rows, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
     assert sc == n and len(rows) == 1 and 0 < ps < n
     assert abs(rows[0].agg[0].f[0] - Q6_GOLDEN_REVENUE) <= 1e-6 * Q6_GOLDEN_REVENUE, rows[0].agg[0].f[0]
+
+
+def test_onek_aggregates_are_the_references():
+    """Integer aggregates and a hashed GROUP BY on an int4 key, against expected/aggregates.out over the suite's onek table."""
+    from _util import onek_check, onek_fixture, onek_plans
+    from oracle import pyoracle as po
+    from test_compile import disasm
+    desc, pages, exp = onek_fixture()
+    plain, grouped = onek_plans(desc, exp)
+    onek_check(exp, po.seqscan_agg(*plain, pages)[0], po.seqscan_agg(*grouped, pages)[0])
+    assert disasm(*plain) and disasm(*grouped)               # and the device compiler takes both plans
