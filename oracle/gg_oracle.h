@@ -133,6 +133,23 @@ int or_motion_route(const gg_scan *scan, const gg_exprpool *pool, const int32_t 
 int32_t or_route_datums(const int32_t *typids, const int64_t *vals, const int32_t *lens,
                         const int32_t *isnull, int nkeys, int nsegs);
 
+/* ---------------- column-oriented append-only (AOCS) column files, compresstype=none (or_aocs.c) ----------------
+ * SURVEY §8f rank 1.  Storage blocks: cdbappendonlystorage_int.h:18-150, cdbappendonlystorageformat.c:26-321,1202-1417;
+ * block content: datumstreamblock.h:68-81, datumstreamblock.c:150-330,1486-1748,3644-3710. */
+uint32_t or_aocs_crc32c(const uint8_t *p, int64_t n);         /* port/pg_crc32c_sb8.c, not inverted at the end */
+/* values[]: by-value Datums, or (attlen -1) pointers to payload bytes of lens[] bytes.  Returns the file length, <0 OR_ERR_* */
+int64_t or_aocs_write_column(const gg_attr *att, const int64_t *values, const int32_t *lens, const uint8_t *nulls,
+                             int64_t nrows, int blocksize, int checksum, int64_t first_rownum, uint8_t *out, int64_t outcap);
+/* values[]: by-value Datums zero-extended from attlen bytes, or (attlen -1) byte offsets of the stored varlena in `file`.
+ * firstrows/rowcounts: one entry per storage block.  Returns the row count, <0 OR_ERR_* (bad checksum, unknown block kind) */
+int64_t or_aocs_read_column(const gg_attr *att, const uint8_t *file, int64_t nbytes, int checksum,
+                            int64_t *values, uint8_t *nulls, int64_t cap,
+                            int64_t *firstrows, int32_t *rowcounts, int blockcap, int *nblocks);
+/* SeqScan (aocs_getnext, aocsam.c:700-800) -> qual -> Agg; colfiles[i] NULL = column not projected */
+int or_aocs_seqscan_agg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
+                        const uint8_t *const *colfiles, const int64_t *colbytes, int checksum, int64_t nrows_hint,
+                        gg_aggrow *out, int outcap, int *nout, uint64_t *rows_scanned, uint64_t *rows_passed);
+
 /* count(*) plumbing of BASELINE config 0: per-segment partial int8inc, Gather, final int8pl */
 int64_t or_count_star_2stage(const uint8_t *const *seg_pages, const uint64_t *seg_nblocks, int nsegs);
 

@@ -83,6 +83,15 @@ def lib():
                                         C.POINTER(capi.gg_aggrow), i32, C.POINTER(i32),
                                         C.POINTER(C.c_double), C.POINTER(u64)]
         L.or_eval.argtypes = [C.POINTER(capi.gg_exprpool), i32, vp, vp, C.POINTER(or_datum)]
+        L.or_aocs_crc32c.restype = u32
+        L.or_aocs_crc32c.argtypes = [vp, i64]
+        L.or_aocs_write_column.restype = i64
+        L.or_aocs_write_column.argtypes = [C.POINTER(capi.gg_attr), vp, vp, vp, i64, i32, i32, i64, vp, i64]
+        L.or_aocs_read_column.restype = i64
+        L.or_aocs_read_column.argtypes = [C.POINTER(capi.gg_attr), vp, i64, i32, vp, vp, i64, vp, vp, i32, C.POINTER(i32)]
+        L.or_aocs_seqscan_agg.argtypes = [C.POINTER(capi.gg_scan), C.POINTER(capi.gg_agg), C.POINTER(capi.gg_exprpool),
+                                          C.POINTER(vp), C.POINTER(i64), i32, i64, C.POINTER(capi.gg_aggrow), i32,
+                                          C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)]
         L.or_bctruelen.argtypes = [C.c_char_p, i32]
         L.or_strerror.restype = C.c_char_p
         L.or_strerror.argtypes = [i32]
@@ -128,6 +137,14 @@ def ref_lib():
         R.ref_int8pl.argtypes = [i64, i64, C.POINTER(i32)]
         R.ref_int8pl.restype = i64
         R.ref_date_cmp_timestamp.argtypes = [i32, i32, i64, C.POINTER(i32)]
+        if hasattr(R, "ref_aocs_write_column"):
+            vp = C.c_void_p
+            R.ref_aocs_write_column.restype = i64
+            R.ref_aocs_write_column.argtypes = [i32, i32, i32, C.c_char, vp, vp, vp, i64, i32, i32, i64, vp, i64, C.POINTER(i32)]
+            R.ref_aocs_read_column.restype = i64
+            R.ref_aocs_read_column.argtypes = [i32, i32, i32, C.c_char, vp, i64, i32, vp, vp, i64, vp, vp, i32, C.POINTER(i32), C.POINTER(i32)]
+            R.ref_aocs_crc32c.restype = u32
+            R.ref_aocs_crc32c.argtypes = [vp, i64]
         _ref = R
     return _ref
 
@@ -308,3 +325,83 @@ def deform_page(desc, pages, blk):
                 row.append(int(vals[a]))
         out.append(row)
     return out
+
+
+# ---- column-oriented append-only (AOCS) column files (or_aocs.c) ----
+
+def _aocs_inputs(att, values, nulls):
+    """python values -> (int64 value array, int32 lens or None, uint8 nulls or None, keepalive)"""
+    n = len(values)
+    vals = np.zeros(n, dtype=np.int64)
+    lens = np.zeros(n, dtype=np.int32) if att.attlen == -1 else None
+    keep = []
+    for i, v in enumerate(values):
+        if nulls is not None and nulls[i]:
+            continue
+        if att.attlen == -1:
+            b = v.encode() if isinstance(v, str) else bytes(v)
+            buf = C.create_string_buffer(b, len(b))
+            keep.append(buf)
+            vals[i] = C.addressof(buf)
+            lens[i] = len(b)
+        elif att.atttypid == capi.FLOAT8OID:
+            vals[i] = C.c_int64.from_buffer_copy(C.c_double(float(v))).value
+        else:
+            vals[i] = int(v)
+    nl = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.uint8)
+    return vals, lens, nl, keep
+
+
+def aocs_write_column(att, values, nulls=None, blocksize=32768, checksum=True, first_rownum=1, ref=False):
+    """One column of an AOCS segment file as a uint8 array; ref=True has the REFERENCE'S OWN objects write it."""
+    vals, lens, nl, keep = _aocs_inputs(att, values, nulls)
+    n = len(values)
+    out = np.zeros((n // 1000 + 2) * blocksize + (int(lens.sum()) if lens is not None else 8 * n) * 2, dtype=np.uint8)
+    args = (_ptr(vals), _ptr(lens) if lens is not None else None, _ptr(nl) if nl is not None else None, n, blocksize,
+            int(checksum), first_rownum, _ptr(out), out.size)
+    if ref:
+        err = C.c_int32(0)
+        sz = ref_lib().ref_aocs_write_column(att.atttypid, att.attlen, att.attbyval, bytes([att.attalign]), *args, C.byref(err))
+        if err.value:
+            raise OracleError(-6)
+    else:
+        sz = lib().or_aocs_write_column(C.byref(att), *args)
+        if sz < 0:
+            raise OracleError(int(sz))
+    return out[:sz].copy()
+
+
+def aocs_read_column(att, file, nrows_cap, checksum=True, ref=False):
+    """-> (values int64[n], nulls uint8[n], firstrows, rowcounts); varlena values are byte offsets into `file`."""
+    vals = np.zeros(nrows_cap, dtype=np.int64)
+    nl = np.zeros(nrows_cap, dtype=np.uint8)
+    bcap = file.size // 24 + 1
+    fr = np.zeros(bcap, dtype=np.int64)
+    rc = np.zeros(bcap, dtype=np.int32)
+    nb = C.c_int32(0)
+    if ref:
+        err = C.c_int32(0)
+        n = ref_lib().ref_aocs_read_column(att.atttypid, att.attlen, att.attbyval, bytes([att.attalign]), _ptr(file), file.size,
+                                           int(checksum), _ptr(vals), _ptr(nl), nrows_cap, _ptr(fr), _ptr(rc), bcap,
+                                           C.byref(nb), C.byref(err))
+        if err.value or n < 0:
+            raise OracleError(-6)
+    else:
+        n = lib().or_aocs_read_column(C.byref(att), _ptr(file), file.size, int(checksum), _ptr(vals), _ptr(nl), nrows_cap,
+                                      _ptr(fr), _ptr(rc), bcap, C.byref(nb))
+        if n < 0:
+            raise OracleError(int(n))
+    return vals[:n], nl[:n], fr[:nb.value], rc[:nb.value]
+
+
+def aocs_seqscan_agg(scan, agg, pool, colfiles, nrows, checksum=True, cap=4096):
+    """colfiles: one uint8 array per attribute of scan.desc, None for columns the plan does not read"""
+    natts = scan.desc.natts
+    ptrs = (C.c_void_p * natts)(*[None if f is None else f.ctypes.data for f in colfiles])
+    sizes = (C.c_int64 * natts)(*[0 if f is None else f.size for f in colfiles])
+    out = (capi.gg_aggrow * cap)()
+    n = C.c_int32(0)
+    sc, ps = C.c_uint64(0), C.c_uint64(0)
+    _chk(lib().or_aocs_seqscan_agg(C.byref(scan), C.byref(agg), C.byref(pool), ptrs, sizes, int(checksum), nrows, out, cap,
+                                   C.byref(n), C.byref(sc), C.byref(ps)))
+    return [out[i] for i in range(n.value)], sc.value, ps.value

@@ -47,6 +47,9 @@ int errcode(int c) { (void) c; return 0; }
 int errmsg(const char *fmt, ...)
 { va_list ap; va_start(ap, fmt); vsnprintf(ref_err_msg, sizeof ref_err_msg, fmt, ap); va_end(ap); return 0; }
 int errhint(const char *fmt, ...) { (void) fmt; return 0; }
+int errdetail(const char *fmt, ...) { (void) fmt; return 0; }
+int errdetail_internal(const char *fmt, ...) { (void) fmt; return 0; }
+int errprintstack(int on) { (void) on; return 0; }
 void elog_start(const char *f, int l, const char *fn) { (void) f; (void) l; (void) fn; }
 void elog_finish(int elevel, const char *fmt, ...)
 { va_list ap; va_start(ap, fmt); vsnprintf(ref_err_msg, sizeof ref_err_msg, fmt, ap); va_end(ap); cur_elevel = elevel; raise(); }

@@ -14,6 +14,8 @@
   orders_tpch.npz   heap_orders of the same suite (order_small.csv + order.csv)
   tpch_join_expected.json  the reference's golden Q4 (semi join) and Q12 (inner join) answers over heap_orders/heap_lineitem
   onek.npz + onek_agg_expected.json  the suite's onek table (int4 columns) and the golden plain / hashed aggregates of aggregates.out
+  aocs_kat.npz      append-only column-oriented (AOCS) column files written by the reference's datumstreamblock.o +
+                    cdbappendonlystorageformat.o, what its reader returns for them, and CRC-32C known answers
   sort_golden.json  ORDER BY answers of expected/sort.out for the column types the Sort path takes, ASC/DESC, NULLS FIRST/LAST
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
@@ -417,6 +419,63 @@ def onek_fixture():
     print("onek.npz", len(rows), "rows")
 
 
+AOCS_TYPES = [("int8", capi.INT8OID, 8, "d", 1), ("int4", capi.INT4OID, 4, "i", 1), ("float8", capi.FLOAT8OID, 8, "d", 1),
+              ("date", capi.DATEOID, 4, "i", 1), ("bpchar1", capi.BPCHAROID, -1, "i", 0), ("text", capi.TEXTOID, -1, "i", 0)]
+
+
+def aocs_attr(typid, attlen, align, byval):
+    a = capi.gg_attr()
+    a.atttypid, a.atttypmod, a.attlen, a.attalign, a.attbyval, a.attnotnull = typid, -1, attlen, ord(align), byval, 0
+    return a
+
+
+def aocs_kat():
+    """Column files of an append-only column-oriented relation (compresstype=none) WRITTEN BY THE REFERENCE'S OWN
+    datumstreamblock.o + cdbappendonlystorageformat.o (oracle/ref_build/refwrap_aocs.c), and what its block reader returns
+    for them: per type x {no NULLs, 20 % NULLs} x {checksum on, off}, 8 KB blocks so every file has several."""
+    g = np.random.default_rng(20260923)
+    out = {"crc_inputs": g.integers(0, 256, 4096).astype(np.uint8)}
+    lens_for_crc = [0, 1, 3, 8, 12, 13, 64, 1000, 4096]
+    out["crc_lens"] = np.array(lens_for_crc, dtype=np.int32)
+    out["crc_values"] = np.array([R.ref_aocs_crc32c(out["crc_inputs"].ctypes.data, ln) for ln in lens_for_crc], dtype=np.uint32)
+    names = []
+    for name, typid, attlen, align, byval in AOCS_TYPES:
+        att = aocs_attr(typid, attlen, align, byval)
+        n = {"bpchar1": 6000, "text": 1200}.get(name, 2500)
+        if name == "float8":
+            vals = [float(x) for x in np.concatenate([g.normal(size=n - 6) * 1e3, [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324]])]
+        elif name == "bpchar1":
+            vals = [bytes([65 + int(x)]) for x in g.integers(0, 26, n)]
+        elif name == "text":
+            vals = [bytes(g.integers(97, 123, int(ln)).astype(np.uint8)) for ln in g.choice([0, 1, 5, 30, 125, 126, 127, 128, 300], n)]
+        elif name == "int8":
+            vals = [int(x) for x in g.integers(-2**62, 2**62, n)]
+        else:
+            vals = [int(x) for x in g.integers(-2**31, 2**31, n)]
+        for nullfrac in (0.0, 0.2):
+            nulls = (g.random(n) < nullfrac).astype(np.uint8) if nullfrac else None
+            for cs in (1, 0):
+                key = "%s_n%d_c%d" % (name, int(nullfrac * 10), cs)
+                f = po.aocs_write_column(att, vals, nulls, blocksize=8192, checksum=bool(cs), first_rownum=1, ref=True)
+                v, nl, fr, rc = po.aocs_read_column(att, f, n, checksum=bool(cs), ref=True)
+                assert len(v) == n and len(rc) > 1
+                names.append(key)
+                out[key + "_file"], out[key + "_vals"], out[key + "_nulls"] = f, v, nl
+                out[key + "_firstrows"], out[key + "_rowcounts"] = fr, rc
+                if nulls is not None:
+                    out[key + "_innulls"] = nulls
+        if attlen == -1:
+            out[name + "_inlens"] = np.array([len(b) for b in vals], dtype=np.int32)
+            out[name + "_inbytes"] = np.frombuffer(b"".join(vals), dtype=np.uint8)
+        elif name == "float8":
+            out[name + "_in"] = np.array(vals, dtype=np.float64).view(np.int64)
+        else:
+            out[name + "_in"] = np.array(vals, dtype=np.int64)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "aocs_kat.npz"), **out)
+    print("aocs_kat.npz", len(names), "column files")
+
+
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
     hash_kat()
@@ -427,3 +486,4 @@ if __name__ == "__main__":
     join_j1j2_fixture()
     sort_fixture()
     onek_fixture()
+    aocs_kat()
