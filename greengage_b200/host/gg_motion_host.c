@@ -69,11 +69,11 @@ static uint32_t hash_datum(int32_t typid, int64_t v, int32_t len)
 		}
 		case GG_BPCHAROID:
 		{
-			/* packed strings are already blank-stripped (bcTruelen) */
-			return gg_hash_any((const unsigned char *) &v, len);
+			/* packed strings are already blank-stripped (bcTruelen); a packed Datum holds at most 8 bytes */
+			return gg_hash_any((const unsigned char *) &v, len < 0 ? 0 : (len > 8 ? 8 : len));
 		}
 		case GG_VARCHAROID: case GG_TEXTOID:
-			return gg_hash_any((const unsigned char *) &v, len);
+			return gg_hash_any((const unsigned char *) &v, len < 0 ? 0 : (len > 8 ? 8 : len));
 		case GG_BOOLOID:
 			return ggh_hash_uint32((uint32_t) (int32_t) (int8_t) v);
 	}

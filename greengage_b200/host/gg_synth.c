@@ -369,6 +369,7 @@ static int run_all(const gg_synth_spec *spec, int nthreads, uint8_t *pages, uint
 	j.nextents = next;
 	j.ext_blocks = calloc(next + 1, sizeof(uint64_t));
 	j.ext_rows = calloc(next + 1, sizeof(uint64_t));
+	if (j.ext_blocks == NULL || j.ext_rows == NULL) { free(j.ext_blocks); free(j.ext_rows); return -3; }
 	j.pages = NULL;
 	j.next = &counter;
 	for (t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, worker, &j);

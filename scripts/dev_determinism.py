@@ -1,7 +1,6 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-import numpy as np
 from greengage_b200 import capi, tpch
 from greengage_b200.engine import Engine, Relation, ScanAgg
 from _util import f2b

@@ -1,7 +1,6 @@
 """Development driver: Q1 on synthetic lineitem through the C-ABI, timed with CUDA events."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from greengage_b200 import capi, tpch
 from greengage_b200.engine import Engine, Relation, ScanAgg
 

@@ -2,7 +2,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 from greengage_b200 import capi, tpch, motion
 from greengage_b200.engine import Engine, Relation, ScanAgg, agg_final_raw
 torch.cuda.set_device(0)

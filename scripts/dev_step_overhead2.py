@@ -1,7 +1,7 @@
 """dev_step_overhead with TWO processes (gloo, both on cuda:0): is the N > 1 step slow because of the Motion path?"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 from greengage_b200 import capi, tpch, motion
 from greengage_b200.engine import Engine, Relation, ScanAgg, agg_final_raw
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])

@@ -5,7 +5,6 @@ single-segment answer.  The per-segment partial aggregates come from the oracle 
 import os
 import sys
 
-import pytest
 
 
 def _worker(rank, world, port, q):

@@ -1,7 +1,6 @@
 """float8 / int8 / date semantics of the oracle against the reference's own float.o, int8.o, date.o
 (golden float_kat.json): CHECKFLOATVAL overflow/underflow ERRORs, division by zero, NaN ordering,
 float8_accum / float8_combine / float8_avg, int8pl overflow, date vs timestamp promotion."""
-import ctypes as C
 
 import pytest
 
