@@ -1,0 +1,110 @@
+"""Host side of the append-only column-oriented (AOCS) scan: ctypes mirror of include/gg_aocs.h (libgghost.so, no GPU
+needed) — the loader's block directory, the column-file writer and the synthetic relations as column files.
+SURVEY §8f rank 1; DESIGN.md §8.1.  The device kernel that consumes the directory is round-2 work."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+DEFAULT_BLOCKSIZE = 32768
+MAX_BLOCK_ROWS = 16382
+
+# gg_aocs_block (32 bytes)
+BLOCK_DTYPE = np.dtype([("first_row", np.int64), ("data_off", np.int64), ("null_off", np.int64), ("nrows", np.int32),
+                        ("data_len", np.int32)])
+
+
+def _check(rc):
+    if rc != 0:
+        raise capi.GGError(rc, "gg_aocs: error %d" % rc)
+
+
+def crc32c(buf):
+    a = np.ascontiguousarray(buf, dtype=np.uint8)
+    return capi.host_lib().gg_aocs_crc32c(a.ctypes.data, a.size)
+
+
+def index_column(att, file, checksum=True):
+    """Validate a column file and return its block directory (structured array of BLOCK_DTYPE) and the row count."""
+    L = capi.host_lib()
+    f = np.ascontiguousarray(file, dtype=np.uint8)
+    nb, nr = C.c_int64(0), C.c_int64(0)
+    _check(L.gg_aocs_index_column(C.byref(att), f.ctypes.data, f.size, int(checksum), None, 0, C.byref(nb), C.byref(nr)))
+    d = np.zeros(nb.value, dtype=BLOCK_DTYPE)
+    _check(L.gg_aocs_index_column(C.byref(att), f.ctypes.data, f.size, int(checksum), d.ctypes.data, d.size, C.byref(nb), C.byref(nr)))
+    return d, nr.value
+
+
+def write_column(att, values, nulls=None, blocksize=DEFAULT_BLOCKSIZE, checksum=True, first_rownum=1):
+    """One column file from python values (bytes for varlena attributes); returns a uint8 array."""
+    L = capi.host_lib()
+    n = len(values)
+    maxlen = max([len(v) for i, v in enumerate(values) if att.attlen == -1 and not (nulls is not None and nulls[i])] or [0])
+    out = np.zeros(L.gg_aocs_file_bound(C.byref(att), n, maxlen, blocksize, int(checksum)), dtype=np.uint8)
+    w = C.c_void_p()
+    _check(L.gg_aocs_writer_create(C.byref(att), blocksize, int(checksum), first_rownum, out.ctypes.data, out.size, C.byref(w)))
+    rc = 0
+    for i, v in enumerate(values):
+        if nulls is not None and nulls[i]:
+            rc = L.gg_aocs_writer_put(w, 0, 0, 1)
+        elif att.attlen == -1:
+            b = v.encode() if isinstance(v, str) else bytes(v)
+            buf = C.create_string_buffer(b, len(b))
+            rc = L.gg_aocs_writer_put(w, C.addressof(buf), len(b), 0)
+        elif att.atttypid == capi.FLOAT8OID:
+            rc = L.gg_aocs_writer_put(w, C.c_int64.from_buffer_copy(C.c_double(float(v))).value, 0, 0)
+        else:
+            rc = L.gg_aocs_writer_put(w, int(v), 0, 0)
+        if rc:
+            break
+    nbytes = C.c_int64(0)
+    rc2 = L.gg_aocs_writer_finish(w, C.byref(nbytes))
+    _check(rc or rc2)
+    return out[:nbytes.value].copy()
+
+
+def synth_columns(spec, cols, nrows_bound, blocksize=DEFAULT_BLOCKSIZE, checksum=True, nthreads=None):
+    """The synthetic relation of `spec` (greengage_b200.tpch.synth_spec) as AOCS column files for the 0-based attribute
+    numbers in `cols`; returns ({col: uint8 array}, nrows).  nrows_bound: an upper bound of this segment's rows
+    (tpch.synth_measure gives the exact count)."""
+    L = capi.host_lib()
+    desc = capi.synth_tupdesc(spec.table)
+    k = len(cols)
+    bufs, caps = [], (C.c_int64 * k)()
+    for i, c in enumerate(cols):
+        cap = L.gg_aocs_file_bound(C.byref(desc.attrs[c]), nrows_bound, 80, blocksize, int(checksum))
+        bufs.append(np.zeros(cap, dtype=np.uint8))
+        caps[i] = cap
+    ptrs = (C.c_void_p * k)(*[b.ctypes.data for b in bufs])
+    outb = (C.c_int64 * k)()
+    nrows = C.c_uint64(0)
+    rc = L.gg_synth_aocs_generate(C.byref(spec), nthreads or min(k, os.cpu_count() or 1), (C.c_int32 * k)(*cols), k, ptrs, caps,
+                                  blocksize, int(checksum), outb, C.byref(nrows))
+    _check(rc)
+    return {c: bufs[i][:outb[i]] for i, c in enumerate(cols)}, nrows.value
+
+
+def fixed_column_values(att, file, directory):
+    """Decode a fixed-width column through the directory alone — what the device kernel's addressing amounts to:
+    value of the j-th non-NULL row of block b = file[data_off + j * attlen ...].  Returns (values int64, nulls uint8)."""
+    assert att.attlen > 0
+    f = np.ascontiguousarray(file, dtype=np.uint8)
+    vals, nulls = [], []
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[att.attlen]
+    for b in directory:
+        n = int(b["nrows"])
+        if b["null_off"] >= 0:
+            bits = np.unpackbits(f[b["null_off"]:b["null_off"] + (n + 7) // 8], bitorder="little")[:n]
+        else:
+            bits = np.zeros(n, dtype=np.uint8)
+        stored = f[b["data_off"]:b["data_off"] + b["data_len"]].view(dt).astype(np.uint64).view(np.int64)
+        assert len(stored) == n - int(bits.sum())
+        v = np.zeros(n, dtype=np.int64)
+        v[bits == 0] = stored
+        vals.append(v)
+        nulls.append(bits)
+    if not vals:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.uint8)
+    return np.concatenate(vals), np.concatenate(nulls)

@@ -126,6 +126,17 @@ def host_lib():
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gg_synth_row.argtypes = [C.POINTER(gg_synth_spec), C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                    C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        L.gg_synth_aocs_generate.argtypes = [C.POINTER(gg_synth_spec), C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+        L.gg_aocs_crc32c.restype = C.c_uint32
+        L.gg_aocs_crc32c.argtypes = [C.c_void_p, C.c_int64]
+        L.gg_aocs_index_column.argtypes = [C.POINTER(gg_attr), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.gg_aocs_writer_create.argtypes = [C.POINTER(gg_attr), C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.gg_aocs_writer_put.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int]
+        L.gg_aocs_writer_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.gg_aocs_file_bound.restype = C.c_int64
+        L.gg_aocs_file_bound.argtypes = [C.POINTER(gg_attr), C.c_int64, C.c_int32, C.c_int, C.c_int]
         L.gg_synth_orderkey.argtypes = [C.c_uint64]
         L.gg_synth_orderkey.restype = C.c_int64
         L.gg_cdbhash_route.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../include/gg_synth.h"
+#include "../../include/gg_aocs.h"
 #include "gg_hostutil.h"
 
 #define D_1992_01_02 (-2921)
@@ -405,4 +406,84 @@ int gg_synth_generate(const gg_synth_spec *spec, int nthreads, uint8_t *pages, u
                       uint64_t *nblocks, uint64_t *nrows)
 {
 	return run_all(spec, nthreads, pages, cap_blocks, nblocks, nrows);
+}
+
+/* ---- the same relation as AOCS column files ---- */
+
+typedef struct aocs_job {
+	const gg_synth_spec *spec;
+	gg_tupdesc desc;
+	const int32_t *cols;
+	int ncols;
+	uint8_t *const *out;
+	const int64_t *outcap;
+	int blocksize, checksum;
+	int64_t *outbytes;
+	uint64_t *colrows;
+	int *rc;
+	volatile uint64_t *next;
+} aocs_job;
+
+static void *aocs_worker(void *p)
+{
+	aocs_job *j = p;
+	const gg_synth_spec *s = j->spec;
+
+	for (;;)
+	{
+		uint64_t k = __sync_fetch_and_add(j->next, 1), c, rows = 0;
+		gg_aocs_writer *w;
+		int64_t v[GG_MAX_ATTS];
+		int32_t len[GG_MAX_ATTS];
+		char sb[256];
+		int col, rc;
+
+		if (k >= (uint64_t) j->ncols) break;
+		col = j->cols[k];
+		rc = gg_aocs_writer_create(&j->desc.attrs[col], j->blocksize, j->checksum, 1, j->out[k], j->outcap[k], &w);
+		for (c = 0; rc == GG_OK && c < s->ncand; c++)
+		{
+			int mine;
+			if (s->nsegs > 1 && s->policy == GG_DIST_RANDOM && (int) (c % (uint64_t) s->nsegs) != s->seg) continue;
+			gg_synth_row(s, c, v, len, sb, sizeof sb, &mine);
+			if (!mine) continue;
+			rc = gg_aocs_writer_put(w, v[col], len[col], 0);
+			rows++;
+		}
+		if (rc == GG_OK)
+			rc = gg_aocs_writer_finish(w, &j->outbytes[k]);
+		else if (w != NULL)
+			(void) gg_aocs_writer_finish(w, NULL);
+		j->colrows[k] = rows;
+		j->rc[k] = rc;
+	}
+	return NULL;
+}
+
+int gg_synth_aocs_generate(const gg_synth_spec *spec, int nthreads, const int32_t *cols, int ncols,
+                           uint8_t *const *out, const int64_t *outcap, int blocksize, int checksum,
+                           int64_t *outbytes, uint64_t *nrows)
+{
+	aocs_job j;
+	pthread_t th[GG_MAX_ATTS];
+	uint64_t colrows[GG_MAX_ATTS];
+	int rcs[GG_MAX_ATTS], t, i, rc = 0;
+	volatile uint64_t counter = 0;
+
+	if (spec == NULL || cols == NULL || out == NULL || outcap == NULL || outbytes == NULL || ncols < 1 || ncols > GG_MAX_ATTS)
+		return -1;
+	if (gg_synth_tupdesc(spec->table, &j.desc)) return -1;
+	for (i = 0; i < ncols; i++)
+		if (cols[i] < 0 || cols[i] >= j.desc.natts) return -1;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > ncols) nthreads = ncols;
+	j.spec = spec; j.cols = cols; j.ncols = ncols; j.out = out; j.outcap = outcap;
+	j.blocksize = blocksize; j.checksum = checksum; j.outbytes = outbytes; j.colrows = colrows; j.rc = rcs;
+	j.next = &counter;
+	for (t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, aocs_worker, &j);
+	for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+	for (i = 0; i < ncols; i++)
+		if (rcs[i]) rc = rcs[i];
+	if (nrows) *nrows = colrows[0];
+	return rc;
 }

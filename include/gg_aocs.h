@@ -1,0 +1,74 @@
+/*
+ * gg_aocs.h — host side of the append-only column-oriented (AOCS) scan: what the loader does with a segment's column
+ * files before they go to the device (libgghost.so, host C, no GPU needed).  SURVEY §8f rank 1; DESIGN.md §8.1.
+ * The device kernel that consumes the directory is round-2 work; nothing here computes query results.
+ *
+ * On-disk format handled (compresstype=none):
+ *   storage blocks   AOSmallContentHeader + optional CRC-32C checksums + first row number
+ *                    src/include/cdb/cdbappendonlystorage_int.h:18-150, src/backend/cdb/cdbappendonlystorageformat.c:26-321,1202-1417
+ *   block content    DatumStreamBlock_Orig: 16-byte header, NULL bitmap, packed non-NULL values
+ *                    src/include/utils/datumstreamblock.h:68-81, src/backend/utils/datumstream/datumstreamblock.c:150-330,1486-1748,3644-3710
+ * Anything else (bulk compression, RLE_TYPE / delta "Dense" blocks, large-object blocks) is GG_ERR_UNSUPPORTED: the
+ * caller keeps the CPU scan for that relation.
+ */
+#ifndef GG_AOCS_H
+#define GG_AOCS_H
+
+#include <stdint.h>
+#include "gg_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef GG_OK
+#define GG_OK               0
+#define GG_ERR_UNSUPPORTED (-6)
+#define GG_ERR_NOMEM       (-8)
+#define GG_ERR_BADPAGE     (-9)
+#define GG_ERR_ARG         (-10)
+#endif
+
+#define GG_AOCS_DEFAULT_BLOCKSIZE 32768     /* DEFAULT_APPENDONLY_BLOCK_SIZE (cdb/cdbappendonlyam.h) */
+#define GG_AOCS_MAX_BLOCK_ROWS    16382     /* a small-content block takes rows while nth + 1 < 0x3FFF (datumstreamblock.c:1497) */
+
+/* One storage block of a column file, as the device scan addresses it: datapath(row) = data_off + index of the row among
+ * the block's non-NULL rows * attlen (fixed-width types), NULL-ness = bit (row - first_row) of the bitmap at null_off. */
+typedef struct gg_aocs_block {
+	int64_t first_row;      /* firstRowNum: row number of the block's first row within the segment file (1-based) */
+	int64_t data_off;       /* byte offset in the column file of the first stored value */
+	int64_t null_off;       /* byte offset of the NULL bitmap (one bit per row, LSB first, 1 = NULL); -1: no NULLs */
+	int32_t nrows;          /* logical rows of the block, NULLs included */
+	int32_t data_len;       /* bytes of stored values */
+} gg_aocs_block;            /* 32 bytes */
+
+/* CRC-32C the way the append-only storage layer computes it (port/pg_crc32c_sb8.c; initial value 0xFFFFFFFF and, "by
+ * historical accident", no final inversion — cdbappendonlystorageformat.c:38-47).  Uses the SSE4.2 instruction when the
+ * CPU has it. */
+uint32_t gg_aocs_crc32c(const uint8_t *p, int64_t n);
+
+/* Walk a column file: validate every storage-block header (and both checksums when the relation has checksum=true),
+ * validate the datum-stream block header inside, and fill the block directory.  AppendOnlyStorageRead's header walk
+ * (cdbappendonlystorageread.c) + DatumStreamBlockRead_GetReadyOrig (datumstreamblock.c:150-330).
+ * dir may be NULL (count only).  GG_ERR_BADPAGE: checksum or structure error; GG_ERR_UNSUPPORTED: a block kind outside the
+ * format above; GG_ERR_NOMEM: more than cap blocks. */
+int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes, int checksum,
+                         gg_aocs_block *dir, int64_t cap, int64_t *nblocks, int64_t *nrows);
+
+/* Streaming writer of one column file (what an INSERT / COPY into the relation appends: aocs_insert_values,
+ * aocsam.c:964-1016 -> datumstreamwrite_put / datumstreamwrite_block_orig -> AppendOnlyStorageWrite_FinishBuffer).
+ * Used by the synthetic loader and the tests; byte-identical to what the reference writes for the same values. */
+typedef struct gg_aocs_writer gg_aocs_writer;
+int gg_aocs_writer_create(const gg_attr *att, int blocksize, int checksum, int64_t first_rownum,
+                          uint8_t *out, int64_t outcap, gg_aocs_writer **w);
+/* value: the Datum of a by-value type, or a pointer to attlen bytes (fixed by-reference) / to len payload bytes (varlena) */
+int gg_aocs_writer_put(gg_aocs_writer *w, int64_t value, int32_t len, int isnull);
+/* flush the open block, report the file length, free the writer */
+int gg_aocs_writer_finish(gg_aocs_writer *w, int64_t *nbytes);
+/* a safe output-buffer size for nrows values of at most maxlen payload bytes each */
+int64_t gg_aocs_file_bound(const gg_attr *att, int64_t nrows, int32_t maxlen, int blocksize, int checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_AOCS_H */

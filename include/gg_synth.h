@@ -53,6 +53,13 @@ int      gg_synth_generate(const gg_synth_spec *spec, int nthreads, uint8_t *pag
  * belongs to this segment — for verification */
 int      gg_synth_row(const gg_synth_spec *spec, uint64_t cand, int64_t *vals, int32_t *lens,
                       char *strbuf, int strcap, int *mine);
+/* The same relation (same rows, same order) stored append-only column-oriented: one column file per requested
+ * attribute (0-based attribute numbers in cols[]), written by include/gg_aocs.h's writer the way an INSERT into a table
+ * `WITH (appendonly=true, orientation=column)` would.  out[i] / outcap[i]: buffer of column cols[i]
+ * (gg_aocs_file_bound() sizes it); outbytes[i] receives the file length.  One thread per column, at most nthreads. */
+int      gg_synth_aocs_generate(const gg_synth_spec *spec, int nthreads, const int32_t *cols, int ncols,
+                                uint8_t *const *out, const int64_t *outcap, int blocksize, int checksum,
+                                int64_t *outbytes, uint64_t *nrows);
 /* the dbgen-style sparse order key of order index o: 8 keys per 32 */
 int64_t  gg_synth_orderkey(uint64_t o);
 
