@@ -16,6 +16,10 @@ BLOCK_DTYPE = np.dtype([("first_row", np.int64), ("data_off", np.int64), ("null_
                         ("data_len", np.int32)])
 
 
+# gg_aocs_tile (16 bytes)
+TILE_DTYPE = np.dtype([("block", np.int32), ("row_in_block", np.int32), ("nulls_before", np.int32), ("pad", np.int32)])
+
+
 def _check(rc):
     if rc != 0:
         raise capi.GGError(rc, "gg_aocs: error %d" % rc)
@@ -35,6 +39,44 @@ def index_column(att, file, checksum=True):
     d = np.zeros(nb.value, dtype=BLOCK_DTYPE)
     _check(L.gg_aocs_index_column(C.byref(att), f.ctypes.data, f.size, int(checksum), d.ctypes.data, d.size, C.byref(nb), C.byref(nr)))
     return d, nr.value
+
+
+def plan_tiles(directory, file, tile_rows):
+    """Per-tile starting points of one column (structured array of TILE_DTYPE): see gg_aocs_plan_tiles."""
+    f = np.ascontiguousarray(file, dtype=np.uint8)
+    d = np.ascontiguousarray(directory)
+    total = int(d["nrows"].sum())
+    tiles = np.zeros((total + tile_rows - 1) // tile_rows, dtype=TILE_DTYPE)
+    _check(capi.host_lib().gg_aocs_plan_tiles(d.ctypes.data, d.size, f.ctypes.data, tile_rows, tiles.ctypes.data, tiles.size))
+    return tiles
+
+
+def tile_values(att, file, directory, tiles, tile_rows, t):
+    """What ONE tile's threads compute, written the way the device kernel will address the column: start at the tile's
+    block, walk forward, NULL prefix by popcount.  Returns (values int64[rows of the tile], nulls uint8) for a
+    fixed-width column — the emulation the CPU tests hold against the oracle."""
+    assert att.attlen > 0
+    f = np.ascontiguousarray(file, dtype=np.uint8)
+    total = int(directory["nrows"].sum())
+    n = min(tile_rows, total - t * tile_rows)
+    b, j, skipped = int(tiles[t]["block"]), int(tiles[t]["row_in_block"]), int(tiles[t]["nulls_before"])
+    vals, nulls = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.uint8)
+    for lane in range(n):
+        while j >= int(directory[b]["nrows"]):                   # next storage block of this column
+            b, j, skipped = b + 1, 0, 0
+        blk = directory[b]
+        isnull = 0
+        if blk["null_off"] >= 0:
+            isnull = (int(f[blk["null_off"] + (j >> 3)]) >> (j & 7)) & 1
+        if isnull:
+            nulls[lane] = 1
+            skipped += 1
+        else:
+            at = int(blk["data_off"]) + (j - skipped) * att.attlen
+            x = int.from_bytes(f[at:at + att.attlen].tobytes(), "little")        # zero-extended, like the block reader
+            vals[lane] = x - (1 << 64) if x >= 1 << 63 else x
+        j += 1
+    return vals, nulls
 
 
 def write_column(att, values, nulls=None, blocksize=DEFAULT_BLOCKSIZE, checksum=True, first_rownum=1):

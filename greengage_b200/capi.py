@@ -132,6 +132,7 @@ def host_lib():
         L.gg_aocs_crc32c.argtypes = [C.c_void_p, C.c_int64]
         L.gg_aocs_index_column.argtypes = [C.POINTER(gg_attr), C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.gg_aocs_plan_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
         L.gg_aocs_writer_create.argtypes = [C.POINTER(gg_attr), C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
         L.gg_aocs_writer_put.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int]
         L.gg_aocs_writer_finish.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]

@@ -216,6 +216,57 @@ int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes
 	return GG_OK;
 }
 
+/* ------------------------------------------------ tile plan ------------------------------------------------ */
+
+static int32_t count_null_bits(const uint8_t *bitmap, int32_t nbits)
+{
+	int32_t n = 0, i = 0;
+
+	for (; i + 64 <= nbits; i += 64)
+	{
+		uint64_t w;
+		memcpy(&w, bitmap + (i >> 3), 8);
+		n += __builtin_popcountll(w);
+	}
+	for (; i < nbits; i++)
+		n += (bitmap[i >> 3] >> (i & 7)) & 1;
+	return n;
+}
+
+int gg_aocs_plan_tiles(const gg_aocs_block *dir, int64_t nblocks, const uint8_t *file, int32_t tile_rows,
+                       gg_aocs_tile *tiles, int64_t ntiles)
+{
+	int64_t b = 0, pos = 0, t;		/* pos: file position (row ordinal) of block b's first row */
+	int64_t total = 0, i;
+
+	if (dir == NULL || tiles == NULL || tile_rows <= 0 || nblocks < 0 || ntiles < 0)
+		return GG_ERR_ARG;
+	for (i = 0; i < nblocks; i++)
+		total += dir[i].nrows;
+	if (ntiles != (total + tile_rows - 1) / tile_rows)
+		return GG_ERR_ARG;
+	for (t = 0; t < ntiles; t++)
+	{
+		int64_t r = t * (int64_t) tile_rows;
+
+		while (b < nblocks && r >= pos + dir[b].nrows)
+			pos += dir[b++].nrows;
+		if (b >= nblocks)
+			return GG_ERR_BADPAGE;
+		tiles[t].block = (int32_t) b;
+		tiles[t].row_in_block = (int32_t) (r - pos);
+		tiles[t].nulls_before = 0;
+		tiles[t].pad = 0;
+		if (dir[b].null_off >= 0 && r > pos)
+		{
+			if (file == NULL)
+				return GG_ERR_ARG;
+			tiles[t].nulls_before = count_null_bits(file + dir[b].null_off, (int32_t) (r - pos));
+		}
+	}
+	return GG_OK;
+}
+
 /* ------------------------------------------------ writer ------------------------------------------------ */
 
 struct gg_aocs_writer {

@@ -55,6 +55,26 @@ uint32_t gg_aocs_crc32c(const uint8_t *p, int64_t n);
 int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes, int checksum,
                          gg_aocs_block *dir, int64_t cap, int64_t *nblocks, int64_t *nrows);
 
+/* The scan's unit of work is a TILE of tile_rows consecutive rows (the same rows of every projected column; the columns'
+ * storage blocks end at different rows because their widths differ).  For one column, per tile: the storage block that
+ * holds the tile's first row and how many of that block's rows before it are NULL — so that a thread handling row r of
+ * the tile finds its value without searching:
+ *     j = row_in_block + (r - tile's first row);  while j >= nrows of the block: j -= nrows, next block;
+ *     value index in the block = j - (NULLs among the block's rows [0, j)), of which `nulls_before` are already counted
+ *     for the tile's first block (the rest is a popcount over at most tile_rows bitmap bits).
+ * Rows are addressed by POSITION in the file (0-based, counting every row of every block in order), which is what
+ * aocs_getnext returns them in; first_row numbers may have gaps between blocks and are not used for addressing. */
+typedef struct gg_aocs_tile {
+	int32_t block;          /* index in the directory of the block holding the tile's first row */
+	int32_t row_in_block;   /* position of the tile's first row inside that block */
+	int32_t nulls_before;   /* NULL rows among the block's rows [0, row_in_block) */
+	int32_t pad;
+} gg_aocs_tile;             /* 16 bytes */
+
+/* ntiles must be ceil(nrows / tile_rows) for the directory's row total; file is needed to count NULL bits. */
+int gg_aocs_plan_tiles(const gg_aocs_block *dir, int64_t nblocks, const uint8_t *file, int32_t tile_rows,
+                       gg_aocs_tile *tiles, int64_t ntiles);
+
 /* Streaming writer of one column file (what an INSERT / COPY into the relation appends: aocs_insert_values,
  * aocsam.c:964-1016 -> datumstreamwrite_put / datumstreamwrite_block_orig -> AppendOnlyStorageWrite_FinishBuffer).
  * Used by the synthetic loader and the tests; byte-identical to what the reference writes for the same values. */

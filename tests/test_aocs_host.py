@@ -25,7 +25,7 @@ def kat():
 def test_host_library_exports_every_declared_symbol():
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "gg_aocs.h")).read(), flags=re.S)
     decl = sorted(set(re.findall(r"\b(gg_aocs_[a-z0-9_]+)\s*\(", txt)))
-    assert len(decl) == 6, decl
+    assert len(decl) == 7, decl
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "greengage_b200", "libgghost.so")]).decode()
     exp = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert [s for s in decl if s not in exp] == []
@@ -65,6 +65,30 @@ def test_directory_of_reference_written_files(kat):
                 if len(live):
                     assert vals[row + live[0]] == b["data_off"]
                 row += b["nrows"]
+
+
+@pytest.mark.parametrize("tile_rows", [64, 1000, 4096])
+def test_tile_plan_addresses_every_row(kat, tile_rows):
+    """the per-tile starting points (gg_aocs_plan_tiles) + the forward walk a thread does from them reach exactly the values
+    the reference's reader returned, for every row of the reference-written fixed-width files (NULL-bearing ones too)"""
+    for key in kat["cases"]:
+        name, cs = str(key).split("_")[0], str(key).endswith("c1")
+        if TYPES[name][1] < 0 or not cs:
+            continue
+        a, f = attr(name), kat[key + "_file"]
+        d, nrows = aocs.index_column(a, f)
+        tiles = aocs.plan_tiles(d, f, tile_rows)
+        assert len(tiles) == (nrows + tile_rows - 1) // tile_rows
+        got = [aocs.tile_values(a, f, d, tiles, tile_rows, t) for t in range(len(tiles))]
+        v, nl = np.concatenate([g[0] for g in got]), np.concatenate([g[1] for g in got])
+        assert np.array_equal(nl, kat[key + "_nulls"]), key
+        assert np.array_equal(v, kat[key + "_vals"]), key
+        # tiles that start inside a block carry the NULL count of the rows before them
+        pos = np.concatenate([[0], np.cumsum(d["nrows"])])
+        for t in range(len(tiles)):
+            b = int(tiles[t]["block"])
+            assert pos[b] <= t * tile_rows < pos[b + 1] and tiles[t]["row_in_block"] == t * tile_rows - pos[b]
+            assert tiles[t]["nulls_before"] == int(kat[key + "_nulls"][pos[b]:t * tile_rows].sum())
 
 
 def test_writer_reproduces_the_references_files_byte_for_byte(kat):
