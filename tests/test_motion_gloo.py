@@ -1,10 +1,11 @@
-"""Motion host plumbing over a 2-rank gloo group on CPU (the N > 1 path of bench.py without GPUs):
+"""Motion host plumbing over 2- and 4-rank gloo groups on CPU (the N > 1 path of bench.py without GPUs):
 Redistribute on the group keys routes every partial row to the segment the reference's cdbhash picks,
 the FINAL stage combines there, Gather brings the result to rank 0 — and the answer equals the
 single-segment answer.  The per-segment partial aggregates come from the oracle (this is a test)."""
 import os
 import sys
 
+import pytest
 
 
 def _worker(rank, world, port, q):
@@ -54,12 +55,13 @@ def _worker(rank, world, port, q):
         q.put(("err", traceback.format_exc(), 0))
 
 
-def test_two_segment_q1_through_motion():
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_segment_q1_through_motion(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 1000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
