@@ -83,3 +83,14 @@ def test_onek_aggregates_are_the_references(eng):
     desc, pages, exp = onek_fixture()
     plain, grouped = onek_plans(desc, exp)
     onek_check(exp, gpu_scanagg(eng, *plain, pages)[0], gpu_scanagg(eng, *grouped, pages)[0])
+
+
+@pytest.mark.xfail(reason="known deviation (DESIGN.md §8): AND/OR evaluate both arms on the device, so a division by zero in "
+                          "the arm ExecEvalAnd/ExecEvalOr would have skipped fails the query", strict=False)
+def test_and_or_skip_the_arm_that_would_raise(eng):
+    from test_gpu_scanagg import gpu_scanagg
+    from test_oracle_float import short_circuit_case
+    desc, pages, plans = short_circuit_case()
+    for scan, agg, pool, want in plans:
+        rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
+        assert (sc, ps, rows[0].agg[0].i) == (5, want, want)

@@ -127,3 +127,33 @@ def test_date_vs_timestamp():
             assert rc != 0
         else:
             assert rc == 0 and int(v) == r, (op, d, ts)
+
+
+def short_circuit_case():
+    """`b <> 0 AND a / b > 1` and `b = 0 OR a / b > 1` over rows where b = 0: ExecEvalAnd / ExecEvalOr (execQual.c:3455,3385)
+    never evaluate the division for those rows.  -> (desc, pages, [(scan, agg, pool, expected count)])"""
+    from _util import make_desc
+    desc = make_desc([(capi.FLOAT8OID, 8, 'd', 1, 1), (capi.FLOAT8OID, 8, 'd', 1, 1)])
+    pages = po.build_pages(desc, [[4.0, 2.0], [1.0, 0.0], [9.0, 3.0], [5.0, 0.0], [1.0, 4.0]])
+    plans = []
+    for kind, first, want in ((capi.E_AND, capi.F_FLOAT8NE, 2), (capi.E_OR, capi.F_FLOAT8EQ, 4)):
+        p = capi.ExprPool()
+        a, b = p.var(1, capi.FLOAT8OID), p.var(2, capi.FLOAT8OID)
+        guard = p.func(first, capi.BOOLOID, b, p.const(capi.FLOAT8OID, 0.0))
+        ratio = p.func(capi.F_FLOAT8GT, capi.BOOLOID, p.func(capi.F_FLOAT8DIV, capi.FLOAT8OID, a, b), p.const(capi.FLOAT8OID, 1.0))
+        plans.append((capi.make_scan(desc, p.boolop(kind, guard, ratio)), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool, want))
+    return desc, pages, plans
+
+
+def test_and_or_skip_the_arm_that_would_raise():
+    desc, pages, plans = short_circuit_case()
+    for scan, agg, pool, want in plans:
+        rows, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
+        assert (sc, ps, rows[0].agg[0].i) == (5, want, want)
+    # with the arms swapped the division runs first and the ERROR is the reference's too
+    p = capi.ExprPool()
+    a, b = p.var(1, capi.FLOAT8OID), p.var(2, capi.FLOAT8OID)
+    ratio = p.func(capi.F_FLOAT8GT, capi.BOOLOID, p.func(capi.F_FLOAT8DIV, capi.FLOAT8OID, a, b), p.const(capi.FLOAT8OID, 1.0))
+    guard = p.func(capi.F_FLOAT8NE, capi.BOOLOID, b, p.const(capi.FLOAT8OID, 0.0))
+    with pytest.raises(po.OracleError):
+        po.seqscan_agg(capi.make_scan(desc, p.boolop(capi.E_AND, ratio, guard)), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool, pages)
