@@ -11,9 +11,9 @@ from . import capi
 DEFAULT_BLOCKSIZE = 32768
 MAX_BLOCK_ROWS = 16382
 
-# gg_aocs_block (32 bytes)
+# gg_aocs_block (40 bytes)
 BLOCK_DTYPE = np.dtype([("first_row", np.int64), ("data_off", np.int64), ("null_off", np.int64), ("nrows", np.int32),
-                        ("data_len", np.int32)])
+                        ("data_len", np.int32), ("stride", np.int32), ("pad", np.int32)])
 
 
 # gg_aocs_tile (16 bytes)
@@ -150,3 +150,88 @@ def fixed_column_values(att, file, directory):
     if not vals:
         return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.uint8)
     return np.concatenate(vals), np.concatenate(nulls)
+
+
+# ---- device side: column files in HBM -> datum rows (gg_aocs_decode_rows, csrc/gg_aocs.cu) ----
+
+K_W8, K_I4, K_I2, K_B1, K_BPCHAR, K_TEXT = range(6)
+KIND_OF_TYPE = {capi.INT8OID: K_W8, capi.FLOAT8OID: K_W8, capi.TIMESTAMPOID: K_W8, capi.INT4OID: K_I4, capi.DATEOID: K_I4,
+                capi.BOOLOID: K_B1, capi.BPCHAROID: K_BPCHAR, capi.VARCHAROID: K_TEXT, capi.TEXTOID: K_TEXT}
+
+
+class gg_aocs_devcol(C.Structure):
+    _fields_ = [("file", C.c_void_p), ("dir", C.c_void_p), ("tiles", C.c_void_p), ("nblocks", C.c_int64),
+                ("kind", C.c_int32), ("pad", C.c_int32)]
+
+
+def _pad16(n):
+    return (n + 15) & ~15
+
+
+class DeviceColumns:
+    """The projected column files of one segment file resident in HBM with their block directories and tile plans, and
+    their decoding into GG_FMT_DATUMROWS rows every operator scans.
+
+    desc: the table's descriptor; cols: 0-based attribute numbers to project (the row's columns, in this order);
+    files: {attribute number: uint8 array}.  The loader work (checksums, directory, tile plan) runs on the host
+    (libgghost.so); the decoding on the device (gg_aocs_decode_rows).  Fails loudly without a GPU like everything else."""
+
+    def __init__(self, eng, desc, cols, files, checksum=True, tile_rows=1024):
+        from .engine import Relation
+        self.eng, self.cols, self.tile_rows = eng, list(cols), tile_rows
+        self.typids = [desc.attrs[c].atttypid for c in self.cols]
+        parts, layout, off, self.nrows = [], [], 0, None
+        for c in self.cols:
+            att = desc.attrs[c]
+            if att.atttypid not in KIND_OF_TYPE:
+                raise capi.GGError(-6, "AOCS column %d: type %d is not decodable on the device" % (c, att.atttypid))
+            f = np.ascontiguousarray(files[c], dtype=np.uint8)
+            d, nrows = index_column(att, f, checksum)
+            if self.nrows is not None and nrows != self.nrows:
+                raise capi.GGError(-9, "AOCS column files of one segment file disagree on the row count")
+            self.nrows = nrows
+            t = plan_tiles(d, f, tile_rows)
+            entry = {"kind": KIND_OF_TYPE[att.atttypid], "nblocks": len(d)}
+            for name, arr in (("file", f), ("dir", d.view(np.uint8).reshape(-1)), ("tiles", t.view(np.uint8).reshape(-1))):
+                entry[name] = off
+                parts.append((off, arr))
+                off += _pad16(arr.size + 16)              # 16 bytes of slack: 8-byte loads at the tail of a bitmap / value area
+            layout.append(entry)
+        self.bytes_in = sum(np.ascontiguousarray(files[c]).size for c in self.cols)
+        nb = (off + capi.GG_BLCKSZ - 1) // capi.GG_BLCKSZ
+        arena = np.zeros(nb * capi.GG_BLCKSZ, dtype=np.uint8)
+        for o, arr in parts:
+            arena[o:o + arr.size] = arr
+        self.arena = Relation(eng, host_pages=arena)
+        base = self.arena.device_ptr()
+        self.devcols = (gg_aocs_devcol * len(self.cols))()
+        for i, e in enumerate(layout):
+            self.devcols[i].file, self.devcols[i].dir, self.devcols[i].tiles = base + e["file"], base + e["dir"], base + e["tiles"]
+            self.devcols[i].nblocks, self.devcols[i].kind = e["nblocks"], e["kind"]
+        self.rows = None
+
+    def rows_tupdesc(self, notnull=None):
+        return capi.rows_tupdesc(self.typids, notnull)
+
+    def decode(self):
+        """-> engine.RowRelation over the decoded rows (kept until free())"""
+        from .engine import Relation, RowRelation, dev_lib
+        W = 1 + len(self.cols)
+        nb = (self.nrows * W * 8 + 64 + capi.GG_BLCKSZ - 1) // capi.GG_BLCKSZ
+        self.rows = Relation(self.eng, nblocks=max(nb, 1))
+        L = dev_lib()
+        L.gg_aocs_decode_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int32, C.c_void_p]
+        capi.check(L.gg_aocs_decode_rows(self.eng.h, self.devcols, len(self.cols), self.nrows, self.tile_rows,
+                                         C.c_void_p(self.rows.device_ptr())))
+        return RowRelation(self.eng, self.rows.device_ptr(), self.nrows, len(self.cols))
+
+    def read_rows(self):
+        """the decoded rows back on the host as an int64 array [nrows, 1 + ncols] (tests)"""
+        W = 1 + len(self.cols)
+        return self.rows.read().view(np.int64)[:self.nrows * W].reshape(self.nrows, W)
+
+    def free(self):
+        for r in (self.rows, self.arena):
+            if r is not None:
+                r.free()
+        self.rows = self.arena = None

@@ -113,6 +113,30 @@ static int attr_ok(const gg_attr *att)
 
 /* ------------------------------------------------ index (loader) ------------------------------------------------ */
 
+/* Stored size shared by every value of a varlena block, or 0.  Only 1-byte-header values qualify (first byte 0x80 | size,
+ * postgres.h VARATT_IS_1B in this tree): a zero byte is alignment padding in front of a 4-byte header. */
+static int32_t uniform_varlena_size(const uint8_t *d, int64_t len)
+{
+	int64_t at = 0;
+	int32_t size = 0;
+
+	if (len == 0)
+		return 1;							/* a block of NULLs only: nothing is ever addressed */
+	while (at < len)
+	{
+		int32_t sz;
+
+		if (!(d[at] & 0x80))
+			return 0;
+		sz = d[at] & 0x7F;
+		if (sz < 1 || (size != 0 && sz != size))
+			return 0;
+		size = sz;
+		at += sz;
+	}
+	return at == len ? size : 0;
+}
+
 int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes, int checksum,
                          gg_aocs_block *dir, int64_t cap, int64_t *nblocks, int64_t *nrows)
 {
@@ -206,6 +230,9 @@ int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes
 			dir[nb].data_off = at + hdr + up8(STREAM_HDR + (int64_t) nullbytes);
 			dir[nb].nrows = nrow;
 			dir[nb].data_len = (int32_t) datalen;
+			dir[nb].stride = att->attlen > 0 ? att->attlen
+				: uniform_varlena_size(b + hdr + up8(STREAM_HDR + (int64_t) nullbytes), (int64_t) datalen);
+			dir[nb].pad = 0;
 		}
 		nb++;
 		rows += nrow;

@@ -40,7 +40,11 @@ typedef struct gg_aocs_block {
 	int64_t null_off;       /* byte offset of the NULL bitmap (one bit per row, LSB first, 1 = NULL); -1: no NULLs */
 	int32_t nrows;          /* logical rows of the block, NULLs included */
 	int32_t data_len;       /* bytes of stored values */
-} gg_aocs_block;            /* 32 bytes */
+	int32_t stride;         /* bytes from one stored value to the next: attlen for fixed-width types; for a varlena column the
+	                         * common stored size when every value of the block is a 1-byte-header varlena of the same length
+	                         * (bpchar(n), n <= 126 — the loader walks the block to make sure), else 0 = irregular */
+	int32_t pad;
+} gg_aocs_block;            /* 40 bytes */
 
 /* CRC-32C the way the append-only storage layer computes it (port/pg_crc32c_sb8.c; initial value 0xFFFFFFFF and, "by
  * historical accident", no final inversion — cdbappendonlystorageformat.c:38-47).  Uses the SSE4.2 instruction when the
@@ -74,6 +78,31 @@ typedef struct gg_aocs_tile {
 /* ntiles must be ceil(nrows / tile_rows) for the directory's row total; file is needed to count NULL bits. */
 int gg_aocs_plan_tiles(const gg_aocs_block *dir, int64_t nblocks, const uint8_t *file, int32_t tile_rows,
                        gg_aocs_tile *tiles, int64_t ntiles);
+
+/* ---- what the device side takes (libggb200.so: gg_aocs_decode_rows in ggb200.h; kernel in csrc/gg_aocs.cu) ---- */
+
+/* how a stored value becomes the 64-bit Datum word of a GG_FMT_DATUMROWS row (gg_plan.h) */
+enum gg_aocs_kind {
+	GG_AOCS_K_W8 = 0,       /* 8-byte by-value types (int8, float8, timestamp): the bits */
+	GG_AOCS_K_I4 = 1,       /* int4, date: sign-extended like DatumGetInt32 */
+	GG_AOCS_K_I2 = 2,       /* int2: sign-extended */
+	GG_AOCS_K_B1 = 3,       /* bool / "char": the byte */
+	GG_AOCS_K_BPCHAR = 4,   /* 1-byte-header varlena of <= 8 payload bytes, trailing blanks stripped (bcTruelen), packed LSB first */
+	GG_AOCS_K_TEXT = 5      /* the same without stripping (varchar, text) */
+};
+
+#define GG_AOCS_E_RANGE     1u      /* the walk ran off the directory: plan and directory disagree */
+#define GG_AOCS_E_IRREGULAR 2u      /* a block whose values have no common stride (stride 0) or a string too long to pack */
+
+/* one projected column as the kernel sees it (device pointers) */
+typedef struct gg_aocs_devcol {
+	const uint8_t *file;
+	const gg_aocs_block *dir;
+	const gg_aocs_tile *tiles;
+	int64_t nblocks;
+	int32_t kind;           /* enum gg_aocs_kind */
+	int32_t pad;
+} gg_aocs_devcol;           /* 40 bytes */
 
 /* Streaming writer of one column file (what an INSERT / COPY into the relation appends: aocs_insert_values,
  * aocsam.c:964-1016 -> datumstreamwrite_put / datumstreamwrite_block_orig -> AppendOnlyStorageWrite_FinishBuffer).

@@ -131,6 +131,18 @@ int  gg_joinagg_reset(gg_joinagg *p);      /* ExecReScanHashJoin with the hash t
 int  gg_joinagg_stats(gg_joinagg *p, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms);
 void gg_joinagg_free(gg_joinagg *p);
 
+/* ---- Append-only column-oriented (AOCS) relations ----
+ * Decode the projected columns of a segment file, resident in device memory together with the loader's block directories
+ * and tile plans (include/gg_aocs.h), into GG_FMT_DATUMROWS rows: device_rows receives nrows rows of 1 + ncols 64-bit
+ * words (NULL mask, then the columns in the order given) and is then scanned like any relation through
+ * gg_relation_attach_rows.  What aocs_getnext does per row (src/backend/access/aocs/aocsam.c:700-800).  The pointers inside
+ * cols[] are DEVICE pointers; cols itself is host memory.  device_rows: 16-byte aligned, 16 bytes of slack after the last
+ * row.  GG_ERR_UNSUPPORTED: a projected column whose values have no common stride (strings longer than 8 bytes or of
+ * mixed length); GG_ERR_BADPAGE: plan and directory disagree. */
+struct gg_aocs_devcol;
+int  gg_aocs_decode_rows(gg_engine *e, const struct gg_aocs_devcol *cols, int ncols, uint64_t nrows, int32_t tile_rows,
+                         void *device_rows);
+
 /* ---- Sort ----
  * Replaces tuplesort_begin_heap_mk/puttupleslot/performsort/gettupleslot
  * (tuplesort_mk.c:771,1154,1378,1668) for fixed-width rows: rows is n x ncols

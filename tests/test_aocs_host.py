@@ -29,7 +29,7 @@ def test_host_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "greengage_b200", "libgghost.so")]).decode()
     exp = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert [s for s in decl if s not in exp] == []
-    assert aocs.BLOCK_DTYPE.itemsize == 32
+    assert aocs.BLOCK_DTYPE.itemsize == 40 and aocs.TILE_DTYPE.itemsize == 16
 
 
 def test_crc32c_known_answers(kat):
@@ -51,6 +51,8 @@ def test_directory_of_reference_written_files(kat):
         assert nrows == len(kat[key + "_vals"])
         assert np.array_equal(d["first_row"], kat[key + "_firstrows"]) and np.array_equal(d["nrows"], kat[key + "_rowcounts"])
         assert np.all(d["data_off"] % 8 == 0)
+        # stride: attlen for fixed-width columns, 2 for char(1) (header byte + character), 0 for the mixed-length text column
+        assert np.all(d["stride"] == {"bpchar1": 2, "text": 0}.get(name, TYPES[name][1]))
         has_nulls = kat[key + "_nulls"].any()
         assert np.all((d["null_off"] >= 0) == has_nulls) or has_nulls     # a block of a NULL-bearing column may have none
         if TYPES[name][1] > 0:

