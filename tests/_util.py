@@ -314,3 +314,23 @@ def onek_check(exp, plain_rows, grouped_rows):
     assert (a[0].i, a[1].i, a[2].i) == (exp["sum_four"], exp["max_four"], exp["count_four"])
     got = sorted([int(np.int32(r.key[0] & 0xFFFFFFFF)), r.agg[0].i, r.agg[1].i] for r in grouped_rows)
     assert got == exp["by_ten"], got
+
+
+def gp_hashagg_case():
+    """MPP-2614 of the reference's sql/gp_hashagg.sql:4-28 (hashed aggregate with a text key behind a three-clause qual;
+    golden answer expected/gp_hashagg.out:17-22: hi 9, there 6).  -> (desc, pages, scan, agg, pool, expected {grp: sum})"""
+    from datetime import date
+    d = lambda m, dd: (date(2006, m, dd) - date(2000, 1, 1)).days
+    desc = make_desc([(capi.INT4OID, 4, "i", 1), (capi.INT4OID, 4, "i", 1), (capi.DATEOID, 4, "i", 1), (capi.TEXTOID, -1, "i", 0),
+                      (capi.INT4OID, 4, "i", 1)])
+    rows = [[1, 1, d(1, 1), b"there", 1], [1, 1, d(1, 2), b"there", 2], [1, 1, d(1, 3), b"there", 3],
+            [1, 1, d(1, 1), b"hi", 2], [1, 1, d(1, 2), b"hi", 3], [1, 1, d(1, 3), b"hi", 4]]        # the six INSERTs
+    p = capi.ExprPool()
+    id1, id2, day, grp, v = (p.var(i + 1, desc.attrs[i].atttypid) for i in range(5))
+    q = p.func(capi.F_INT4EQ, capi.BOOLOID, id1, p.const(capi.INT4OID, 1))
+    for cond in (p.func(capi.F_INT4EQ, capi.BOOLOID, id2, p.const(capi.INT4OID, 1)),
+                 p.func(capi.F_DATE_GE, capi.BOOLOID, day, p.const(capi.DATEOID, d(1, 1))),
+                 p.func(capi.F_DATE_LE, capi.BOOLOID, day, p.const(capi.DATEOID, d(1, 31)))):
+        q = p.boolop(capi.E_AND, q, cond)
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [grp], [(capi.AGG_SUM_INT4, v)])
+    return desc, po.build_pages(desc, rows), capi.make_scan(desc, q), agg, p.pool, {"hi": 9, "there": 6}

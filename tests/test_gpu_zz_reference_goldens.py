@@ -85,6 +85,16 @@ def test_onek_aggregates_are_the_references(eng):
     onek_check(exp, gpu_scanagg(eng, *plain, pages)[0], gpu_scanagg(eng, *grouped, pages)[0])
 
 
+def test_gp_hashagg_text_key_answer_is_the_references(eng):
+    """sql/gp_hashagg.sql MPP-2614: hashed aggregate with a text key behind a three-clause qual (expected/gp_hashagg.out:17-22)"""
+    from _util import gp_hashagg_case
+    from test_gpu_scanagg import gpu_scanagg
+    desc, pages, scan, agg, pool, want = gp_hashagg_case()
+    rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
+    assert (sc, ps) == (6, 6)
+    assert {capi.unpack_str(r.key[0], r.keylen[0]): r.agg[0].i for r in rows} == want
+
+
 @pytest.mark.xfail(reason="known deviation (DESIGN.md §8): AND/OR evaluate both arms on the device, so a division by zero in "
                           "the arm ExecEvalAnd/ExecEvalOr would have skipped fails the query", strict=False)
 def test_and_or_skip_the_arm_that_would_raise(eng):

@@ -96,3 +96,14 @@ def test_onek_aggregates_are_the_references():
     plain, grouped = onek_plans(desc, exp)
     onek_check(exp, po.seqscan_agg(*plain, pages)[0], po.seqscan_agg(*grouped, pages)[0])
     assert disasm(*plain) and disasm(*grouped)               # and the device compiler takes both plans
+
+
+def test_gp_hashagg_text_key_answer_is_the_references():
+    from _util import gp_hashagg_case
+    from oracle import pyoracle as po
+    from test_compile import disasm
+    desc, pages, scan, agg, pool, want = gp_hashagg_case()
+    rows, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
+    assert (sc, ps) == (6, 6)
+    assert {capi.unpack_str(r.key[0], r.keylen[0]): r.agg[0].i for r in rows} == want
+    assert disasm(scan, agg, pool)
