@@ -7,6 +7,7 @@ than L2, >= 3 warm-up passes.
   python scripts/bench_ops.py sort  [--rows 1e8]
   python scripts/bench_ops.py motion [--rows 1e8] [--nsegs 8]                                sending side only
   python scripts/bench_ops.py groupby [--rows 1e8]                                           general HashAggregate
+  python scripts/bench_ops.py aocs  [--rows 1e8]                                             Q1 over AOCS column files (decode + scan)
   torchrun ... scripts/bench_ops.py rjoin [--rows 1e8] [--orders 2.5e7]                       BASELINE config 3 (N GPUs)
 """
 import argparse
@@ -121,6 +122,52 @@ def bench_groupby(args):
                       "ms": t, "rows_per_s": nr / (t / 1e3), "variant": sa.variant(),
                       "roofline": {"bound": "hbm", "achieved": nb * 32768 / (t / 1e3) / 1e9, "peak": peak(), "unit": "GB/s",
                                    "frac": nb * 32768 / (t / 1e3) / 1e9 / peak(), "algorithmic_bytes": "pages read once (+ 4 random table sectors per row)"}}), flush=True)
+
+
+def bench_aocs(args):
+    """Q1 over the LI-wide segment stored append-only column-oriented: the seven projected column files are loaded
+    (host index + tile plan, one H2D of the files), decoded to datum rows on the device (gg_aocs_decode_rows) and scanned.
+    Reports the decode kernel, the scan over the decoded rows, and the load (host loader + H2D) beside them."""
+    import time
+    from greengage_b200 import aocs
+    from greengage_b200.engine import ScanAgg
+    eng = Engine(0)
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, args.rows)
+    nb, nr = tpch.synth_measure(spec)
+    cols = [4, 5, 6, 7, 8, 9, 10]
+    t0 = time.time()
+    files, nrows = aocs.synth_columns(spec, cols, nr)
+    gen_s = time.time() - t0
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
+    t0 = time.time()
+    dc = aocs.DeviceColumns(eng, desc, cols, files)
+    load_s = time.time() - t0
+    names = dict(quantity=1, extendedprice=2, discount=3, tax=4, returnflag=5, linestatus=6, shipdate=7)
+    scan, agg, pool = tpch.q1_plan(stage=capi.AGGSTAGE_NORMAL, desc=dc.rows_tupdesc([1] * len(cols)), cols=names)
+    sa = ScanAgg(eng, scan, agg, pool)
+    dec_ms, scan_ms = [], []
+    rel = None
+    for it in range(args.warmup + args.steps):
+        if rel is not None:
+            rel.free()
+            dc.rows.free()
+        rel = dc.decode()
+        d = eng.last_kernel_ms()
+        sa.reset()
+        sa.run(rel)
+        rows, sc, ps = sa.fetch()
+        if it >= args.warmup:
+            dec_ms.append(d); scan_ms.append(sa.scan_kernel_ms()[0])
+    d, t = float(np.mean(dec_ms)), float(np.mean(scan_ms))
+    rowbytes = 8 * (1 + len(cols))
+    dec_bytes = dc.bytes_in + nr * rowbytes
+    print(json.dumps({"op": "aocs-q1", "workload": "Q1 over %d rows of LI-wide stored as AOCS column files, 7 projected columns" % nr,
+                      "column_bytes": dc.bytes_in, "bytes_per_row": dc.bytes_in / nr, "heap_bytes_per_row": 172,
+                      "decode_ms": d, "scan_ms": t, "rows_per_s": nr / ((d + t) / 1e3), "groups": len(rows),
+                      "host_generate_s": gen_s, "host_index_plan_and_h2d_s": load_s,
+                      "roofline": {"bound": "hbm", "kernel": "gg_aocs_rows_kernel", "achieved": dec_bytes / (d / 1e3) / 1e9, "peak": peak(),
+                                   "unit": "GB/s", "frac": dec_bytes / (d / 1e3) / 1e9 / peak(),
+                                   "algorithmic_bytes": "column files read once + %d B/row of datum rows written" % rowbytes}}), flush=True)
 
 
 def li_payload():
@@ -253,7 +300,7 @@ def bench_rjoin(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("op", choices=["join", "sort", "motion", "rjoin", "groupby"])
+    ap.add_argument("op", choices=["join", "sort", "motion", "rjoin", "groupby", "aocs"])
     ap.add_argument("--rows", type=float, default=1e8)
     ap.add_argument("--orders", type=float, default=2.5e7)
     ap.add_argument("--kind", default="count")
@@ -262,4 +309,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     a.rows, a.orders = int(a.rows), int(a.orders)
-    {"join": bench_join, "sort": bench_sort, "motion": bench_motion, "rjoin": bench_rjoin, "groupby": bench_groupby}[a.op](a)
+    {"join": bench_join, "sort": bench_sort, "motion": bench_motion, "rjoin": bench_rjoin, "groupby": bench_groupby, "aocs": bench_aocs}[a.op](a)
