@@ -86,22 +86,26 @@ def exec_lib():
         if not os.path.exists(path):
             raise ImportError("greengage_b200/libggexec.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
         capi.dev_lib()
-        L = C.CDLL(path)
-        L.GgExecInitNode.restype = C.c_void_p
-        L.GgExecInitNode.argtypes = [C.POINTER(GgPlan), C.POINTER(GgEState), C.c_int]
-        L.GgExecProcNode.restype = C.POINTER(GgTupleTableSlot)
-        L.GgExecProcNode.argtypes = [C.c_void_p]
-        L.GgExecEndNode.restype = None
-        L.GgExecEndNode.argtypes = [C.c_void_p]
-        L.GgExecReScan.argtypes = [C.c_void_p]
-        L.GgExecSquelchNode.restype = None
-        L.GgExecSquelchNode.argtypes = [C.c_void_p]
-        L.GgExecLastError.restype = C.c_char_p
-        L.GgExecLastErrorCode.restype = C.c_int
-        L.GgExecNodeKind.restype = C.c_char_p
-        L.GgExecNodeKind.argtypes = [C.c_void_p]
-        _lib = L
+        _lib = bind(C.CDLL(path))
     return _lib
+
+
+def bind(L):
+    """ctypes signatures of include/gg_executor.h on a loaded library"""
+    L.GgExecInitNode.restype = C.c_void_p
+    L.GgExecInitNode.argtypes = [C.POINTER(GgPlan), C.POINTER(GgEState), C.c_int]
+    L.GgExecProcNode.restype = C.POINTER(GgTupleTableSlot)
+    L.GgExecProcNode.argtypes = [C.c_void_p]
+    L.GgExecEndNode.restype = None
+    L.GgExecEndNode.argtypes = [C.c_void_p]
+    L.GgExecReScan.argtypes = [C.c_void_p]
+    L.GgExecSquelchNode.restype = None
+    L.GgExecSquelchNode.argtypes = [C.c_void_p]
+    L.GgExecLastError.restype = C.c_char_p
+    L.GgExecLastErrorCode.restype = C.c_int
+    L.GgExecNodeKind.restype = C.c_char_p
+    L.GgExecNodeKind.argtypes = [C.c_void_p]
+    return L
 
 
 class ExecError(capi.GGError):

@@ -1,0 +1,109 @@
+/*
+ * ggb200_mock.c — TEST INFRASTRUCTURE: a stand-in for libggb200.so that answers the C-ABI calls of the executor-node
+ * surface (greengage_b200/host/gg_executor.c) with the ORACLE, so the host logic above the device engine — pipeline
+ * fusion, slot formation, ReScan / Squelch, and above all the N > 1 path through Motion (routing, transport, FINAL stage on
+ * the receiving segments, merging Gather) — can run on a CPU-only box with several gloo ranks.
+ * Built by tests/test_executor_multiseg.py into a temporary directory together with the product's gg_executor.c and
+ * gg_motion_host.c; never shipped, never loaded by the product.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/ggb200.h"
+#include "../../oracle/gg_oracle.h"
+
+struct gg_engine { int unused; };
+struct gg_relation { const uint8_t *pages; uint64_t nblocks; };
+struct gg_scanagg { gg_scan scan; gg_agg agg; gg_exprpool pool; const uint8_t *pages; uint64_t nblocks; int fed; };
+struct gg_joinagg { gg_scan outer, inner; gg_hashjoin hj; gg_agg agg; gg_exprpool pool;
+                    const uint8_t *opages, *ipages; uint64_t onb, inb; };
+
+static char last_error[256] = "";
+const char *gg_last_error(void) { return last_error; }
+
+static int fail(int rc, const char *what)
+{
+	if (rc) { strncpy(last_error, what, sizeof last_error - 1); }
+	return rc == 0 ? GG_OK : (rc == OR_ERR_NOMEM ? GG_ERR_NOMEM : rc);      /* OR_ERR_* use the GG_ERR_* numbers */
+}
+
+/* test-only constructors */
+gg_engine *mock_engine(void) { static gg_engine e; return &e; }
+gg_relation *mock_relation(const uint8_t *pages, uint64_t nblocks)
+{
+	gg_relation *r = calloc(1, sizeof *r);
+	r->pages = pages; r->nblocks = nblocks;
+	return r;
+}
+
+uint64_t gg_relation_nblocks(gg_relation *r) { return r->nblocks; }
+
+int gg_scanagg_create(gg_engine *e, const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, gg_scanagg **out)
+{
+	gg_scanagg *p = calloc(1, sizeof *p);
+	(void) e;
+	p->scan = *scan; p->agg = *agg; p->pool = *pool;
+	*out = p;
+	return GG_OK;
+}
+
+int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t nblocks)
+{
+	if (p->fed) return fail(GG_ERR_ARG, "mock: one run per accumulation");
+	p->pages = r->pages + first_block * (uint64_t) GG_BLCKSZ;
+	p->nblocks = nblocks;
+	p->fed = 1;
+	return GG_OK;
+}
+
+int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_scanned, uint64_t *rows_passed)
+{
+	return fail(or_seqscan_agg(&p->scan, &p->agg, &p->pool, p->pages, p->nblocks, out, outcap, nout, rows_scanned, rows_passed),
+	            "mock: or_seqscan_agg failed");
+}
+
+int gg_scanagg_reset(gg_scanagg *p) { p->fed = 0; p->pages = NULL; p->nblocks = 0; return GG_OK; }
+void gg_scanagg_free(gg_scanagg *p) { free(p); }
+
+int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin, gg_aggrow *out, int outcap, int *nout)
+{
+	(void) e;
+	return fail(or_agg_final(agg, in, nin, out, outcap, nout), "mock: or_agg_final failed");
+}
+
+int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
+                      const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out)
+{
+	gg_joinagg *p = calloc(1, sizeof *p);
+	(void) e;
+	p->outer = *outer; p->inner = *inner; p->hj = *hj; p->agg = *agg; p->pool = *pool;
+	*out = p;
+	return GG_OK;
+}
+
+int gg_joinagg_build(gg_joinagg *p, gg_relation *inner, uint64_t first_block, uint64_t nblocks)
+{
+	p->ipages = inner->pages + first_block * (uint64_t) GG_BLCKSZ; p->inb = nblocks;
+	return GG_OK;
+}
+
+int gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, uint64_t nblocks)
+{
+	p->opages = outer->pages + first_block * (uint64_t) GG_BLCKSZ; p->onb = nblocks;
+	return GG_OK;
+}
+
+int gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
+{
+	return fail(or_hashjoin_agg(&p->outer, &p->inner, &p->hj, &p->agg, &p->pool, p->opages, p->onb, p->ipages, p->inb,
+	                            out, outcap, nout, rows_joined), "mock: or_hashjoin_agg failed");
+}
+
+int gg_joinagg_reset(gg_joinagg *p) { p->opages = NULL; p->onb = 0; return GG_OK; }
+void gg_joinagg_free(gg_joinagg *p) { free(p); }
+
+int gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const int64_t *host_rows, const uint8_t *host_nulls,
+                 uint64_t n, uint64_t *host_perm)
+{
+	(void) e;
+	return fail(or_sort_perm(keys, nkeys, ncols, host_rows, host_nulls, n, host_perm), "mock: or_sort_perm failed");
+}
