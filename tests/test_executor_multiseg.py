@@ -34,10 +34,12 @@ class MockRel:
 
 def _worker(rank, world, port, mock, case, q):
     try:
-        os.environ["MASTER_ADDR"] = "127.0.0.1"
-        os.environ["MASTER_PORT"] = str(port)
-        import torch.distributed as dist
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist = None
+        if world > 1:
+            os.environ["MASTER_ADDR"] = "127.0.0.1"
+            os.environ["MASTER_PORT"] = str(port)
+            import torch.distributed as dist
+            dist.init_process_group("gloo", rank=rank, world_size=world)
         sys.path.insert(0, ROOT)
         sys.path.insert(0, HERE)
         from greengage_b200 import capi, executor as ex, tpch
@@ -47,8 +49,11 @@ def _worker(rank, world, port, mock, case, q):
         L.mock_relation.argtypes = [C.c_void_p, C.c_uint64]
         ex._lib = L                                                   # the Executor class now drives the mock-linked host code
         eng = L.mock_engine()
-        tr = ex.TorchTransport()
+        tr = ex.TorchTransport() if world > 1 else None
         b = ex.PlanBuilder()
+        if case == "single":
+            q.put(("ok", rank, "single", single_segment_checks(L, eng, ex), None, 0))
+            return
         if case == "q1":
             from test_gpu_executor import q1_sorted_plan
             spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 60000, nsegs=world, seg=rank)
@@ -76,10 +81,65 @@ def _worker(rank, world, port, mock, case, q):
             again = x.rows()
         x.end()
         q.put(("ok", rank, kind, rows, again, nr))
-        dist.destroy_process_group()
+        if dist is not None:
+            dist.destroy_process_group()
     except Exception:  # pragma: no cover
         import traceback
         q.put(("err", rank, traceback.format_exc(), None, None, 0))
+
+
+def single_segment_checks(L, eng, ex):
+    """what tests/test_gpu_executor.py checks on the device, with the oracle behind the C-ABI: node-surface control flow"""
+    from _util import golden, lineitem_fixture_pages
+    from greengage_b200 import capi, tpch
+    from oracle import pyoracle as po
+    from test_gpu_executor import b2f, q1_sorted_plan
+    done = []
+    desc, pages, n = lineitem_fixture_pages()
+    exp = golden("q1_expected.json")
+    scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL, interval_days=exp["interval_days"], desc=desc)
+    for two_stage in (False, True):
+        x = ex.Executor(eng, pool, [MockRel(L, pages)], q1_sorted_plan(ex.PlanBuilder(), scan, agg, two_stage))
+        assert x.kind() == ("motion" if two_stage else "sort")
+        rows = x.rows()
+        assert len(rows) == len(exp["rows"])
+        for (v, nl, ty, ln), w in zip(rows, exp["rows"]):              # ORDER BY l_returnflag, l_linestatus
+            assert capi.unpack_str(v[0], ln[0]) == w["returnflag"] and capi.unpack_str(v[1], ln[1]) == w["linestatus"]
+            assert v[9] == w["count_order"]
+            for col, name in ((2, "sum_qty"), (3, "sum_base_price"), (4, "sum_disc_price"), (5, "sum_charge"),
+                              (6, "avg_qty"), (7, "avg_price"), (8, "avg_disc")):
+                assert abs(b2f(v[col]) - float(w[name])) <= 1e-6 * abs(float(w[name]))
+        assert x.rows() == []                                           # end of stream stays end of stream
+        x.rescan()
+        assert len(x.rows()) == len(rows)                               # ExecReScan runs the slice again
+        x.rescan()
+        assert len(x.rows(limit=2)) == 2 and x.rows() == []              # squelched after LIMIT
+        x.end()
+        done.append("q1-two-stage" if two_stage else "q1-one-stage")
+    li, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 30_000, seed=6, norders=6_000))
+    od, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 5_000, seed=6))
+    outer, inner, hj, jagg, jpool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "q3ish", capi.JOIN_INNER)
+    want, _ = po.hashjoin_agg(outer, inner, hj, jagg, jpool, li, od)
+    b = ex.PlanBuilder()
+    plan = b.sort(b.agg(b.hashjoin(b.seqscan(0, outer.desc, outer.qual), b.hash(b.seqscan(1, inner.desc, inner.qual)), hj), jagg),
+                  [capi.make_sortkey(0, capi.BPCHAROID, desc=True)])
+    x = ex.Executor(eng, jpool, [MockRel(L, li), MockRel(L, od)], plan)
+    rows = x.rows()
+    keys = [capi.unpack_str(v[0], ln[0]) for v, nl, ty, ln in rows]
+    assert keys == sorted(keys, reverse=True) and len(rows) == len(want)
+    byk = {r.key[0]: r for r in want}
+    for v, nl, ty, ln in rows:
+        assert v[1] == byk[v[0]].agg[0].i and v[3] == byk[v[0]].agg[2].i
+    x.end()
+    done.append("join-sort-desc")
+    # a Motion over several segments without a transport is refused at init, not at run time
+    try:
+        ex.Executor(eng, pool, [MockRel(L, pages)], q1_sorted_plan(ex.PlanBuilder(), scan, agg, True), nsegs=2, segindex=0)
+        raise AssertionError("accepted")
+    except ex.ExecError as e:
+        assert e.code == -10
+    done.append("motion-needs-transport")
+    return done
 
 
 def run(world, case, tmp_path):
@@ -150,3 +210,10 @@ def test_colocated_join_under_a_gather(tmp_path):
         g = got[w.key[0]]
         assert g[0] == w.agg[0].i and g[2] == w.agg[2].i
         assert abs(g[1] - w.agg[1].f[0]) <= 1e-9 * abs(w.agg[1].f[0])
+
+
+def test_node_surface_control_flow_on_one_segment(tmp_path):
+    """ReScan, end of stream, Squelch after a LIMIT, Sort DESC above a join pipeline, the loopback Motions of the two-stage
+    plan — tests/test_gpu_executor.py's checks with the oracle behind the C-ABI, in a child process"""
+    by = run(1, "single", tmp_path)
+    assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "motion-needs-transport"]
