@@ -371,8 +371,10 @@ int alloc_temp(Ctx &c)
 /* temp[t] = acc, as a post-action of the op that produced acc */
 void store_temp(Ctx &c, int t)
 {
+	if (c.failed) return;
+	if (c.prog->ncode == 0 || (c.prog->code[c.prog->ncode - 1].flags & GGP_F_ST)) emit(c, GGP_NOP);
+	if (c.prog->ncode == 0) return;
 	ggp_op *o = &c.prog->code[c.prog->ncode - 1];
-	if (c.prog->ncode == 0 || (o->flags & GGP_F_ST)) { emit(c, GGP_NOP); o = &c.prog->code[c.prog->ncode - 1]; }
 	o->flags |= GGP_F_ST;
 	o->aux = (uint8_t) ((o->aux & ~0x30) | (t << 4));
 }
@@ -624,6 +626,80 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 }
 
 
+/* ---- structural validation of what crosses the C-ABI ----
+ * Nothing below indexes the pool, a descriptor or the aggregate list with a value that was not checked here: a malformed
+ * plan is GG_ERR_ARG with a message, never a crash of the backend that loaded the library.  A pool lists children before
+ * their parents (gg_plan.h), which is also what rules out cycles; only the nodes reachable from the plan's roots are looked
+ * at (a pool may hold the expressions of other pipelines of the same plan tree). */
+struct Roots {
+	int n = 0;
+	int r[4 + 2 * GG_MAX_KEYS + GG_MAX_AGGS + GGP_MAX_ACCS];
+	bool ok = true;
+	void add(Ctx &c, const gg_exprpool *pool, int root, bool optional, const char *what)
+	{
+		if (optional && root == -1) return;
+		if (root < 0 || root >= pool->nnodes) { fail(c, "%s: node %d is not in the pool (%d nodes)", what, root, pool->nnodes); ok = false; return; }
+		if (n < (int) (sizeof r / sizeof r[0])) r[n++] = root;
+	}
+};
+
+static bool valid_nodes(Ctx &c, const gg_exprpool *pool, const gg_tupdesc *odesc, const gg_tupdesc *idesc, const Roots &roots)
+{
+	bool used[GG_MAX_EXPR_NODES];
+	memset(used, 0, sizeof used);
+	for (int i = 0; i < roots.n; i++) used[roots.r[i]] = true;
+	for (int i = pool->nnodes - 1; i >= 0; i--)        /* children have smaller indices: one descending sweep reaches everything */
+	{
+		if (!used[i]) continue;
+		const gg_expr &e = pool->nodes[i];
+		int need = 0;
+		switch (e.kind)
+		{
+			case GG_E_VAR:
+			{
+				const gg_tupdesc *d = e.varno == 0 ? odesc : (e.varno == 1 ? idesc : nullptr);
+				if (!d) { fail(c, "node %d: Var of relation %d, which this plan does not have", i, e.varno); return false; }
+				if (e.varattno < 1 || e.varattno > d->natts) { fail(c, "node %d: Var attribute %d out of range (1..%d)", i, e.varattno, d->natts); return false; }
+				break;
+			}
+			case GG_E_CONST: break;
+			case GG_E_FUNC:
+			{
+				BinInfo b; int un;
+				need = (func_info(e.funcid, &b, &un) && b.isbin) ? 2 : 1;     /* an unknown function is refused where it is compiled */
+				break;
+			}
+			case GG_E_AND: case GG_E_OR: need = 2; break;
+			case GG_E_NOT: case GG_E_ISNULL: case GG_E_ISNOTNULL: need = 1; break;
+			default: fail(c, "node %d: expression kind %d not supported", i, e.kind); return false;
+		}
+		if (need && (e.nargs < need || e.nargs > 2)) { fail(c, "node %d: %d arguments where %d are needed", i, e.nargs, need); return false; }
+		for (int k = 0; k < need; k++)
+		{
+			if (e.args[k] < 0 || e.args[k] >= i) { fail(c, "node %d: argument %d is node %d (children come before their parents)", i, k, e.args[k]); return false; }
+			used[e.args[k]] = true;
+		}
+	}
+	return true;
+}
+
+static bool valid_header(Ctx &c, const gg_exprpool *pool, const gg_tupdesc *odesc, const gg_tupdesc *idesc)
+{
+	if (pool->nnodes < 0 || pool->nnodes > GG_MAX_EXPR_NODES) { fail(c, "expression pool with %d nodes (0..%d)", pool->nnodes, GG_MAX_EXPR_NODES); return false; }
+	if (odesc->natts < 0 || odesc->natts > GG_MAX_ATTS || (idesc && (idesc->natts < 0 || idesc->natts > GG_MAX_ATTS))) { fail(c, "descriptor with too many attributes"); return false; }
+	return true;
+}
+
+static bool add_agg_roots(Ctx &c, const gg_agg *agg, const gg_exprpool *pool, Roots &roots)
+{
+	if (agg->numCols < 0 || agg->numCols > GG_MAX_KEYS) { fail(c, "%d grouping columns (0..%d)", agg->numCols, GG_MAX_KEYS); return false; }
+	if (agg->numAggs < 0 || agg->numAggs > GG_MAX_AGGS) { fail(c, "%d aggregates (0..%d)", agg->numAggs, GG_MAX_AGGS); return false; }
+	if (agg->aggstage == GG_AGGSTAGE_FINAL) return true;            /* grpCol carries type OIDs there; refused by compile_agg_part */
+	for (int i = 0; i < agg->numCols; i++) roots.add(c, pool, agg->grpCol[i], false, "grouping column");
+	for (int i = 0; i < agg->numAggs; i++) roots.add(c, pool, agg->aggs[i].arg, true, "aggregate argument");
+	return roots.ok;
+}
+
 int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
                         ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen)
 {
@@ -633,6 +709,12 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 	c.pool = pool; c.prog = prog; c.outer = &prog->outer; c.inner = nullptr;
 	c.odesc = &scan->desc; c.idesc = nullptr; c.err = err; c.errlen = errlen;
 	if (err && errlen) err[0] = 0;
+	{
+		Roots roots;
+		if (!valid_header(c, pool, &scan->desc, nullptr)) return GG_ERR_ARG;
+		roots.add(c, pool, scan->qual, true, "scan qual");
+		if (!add_agg_roots(c, agg, pool, roots) || !roots.ok || !valid_nodes(c, pool, &scan->desc, nullptr, roots)) return GG_ERR_ARG;
+	}
 
 	if (scan->desc.natts < 0 || scan->desc.natts > GG_MAX_ATTS) { fail(c, "too many attributes"); return GG_ERR_UNSUPPORTED; }
 	for (int i = 0; i < scan->desc.natts; i++)
@@ -689,6 +771,19 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	c.pool = pool; c.err = err; c.errlen = errlen;
 	if (err && errlen) err[0] = 0;
 	if (hj->nkeys < 1 || hj->nkeys > 2) { fail(c, "hash join with %d keys not supported (1 or 2)", hj->nkeys); return GG_ERR_UNSUPPORTED; }
+	{
+		Roots roots;
+		if (!valid_header(c, pool, &outer->desc, &inner->desc)) return GG_ERR_ARG;
+		roots.add(c, pool, outer->qual, true, "outer scan qual");
+		roots.add(c, pool, inner->qual, true, "inner scan qual");
+		roots.add(c, pool, hj->joinqual, true, "join qual");
+		for (int k = 0; k < hj->nkeys; k++)
+		{
+			roots.add(c, pool, hj->outerkey[k], false, "outer join key");
+			roots.add(c, pool, hj->innerkey[k], false, "inner join key");
+		}
+		if (!add_agg_roots(c, agg, pool, roots) || !roots.ok || !valid_nodes(c, pool, &outer->desc, &inner->desc, roots)) return GG_ERR_ARG;
+	}
 	switch (hj->jointype)
 	{
 		case GG_JOIN_INNER: case GG_JOIN_LEFT: case GG_JOIN_FULL: case GG_JOIN_RIGHT:
@@ -799,6 +894,14 @@ int ggp_compile_motion(const gg_scan *scan, const gg_exprpool *pool, const int32
 	if (err && errlen) err[0] = 0;
 	if (nkeys < 1 || nkeys > GG_MAX_KEYS) { fail(c, "motion with %d hash keys not supported", nkeys); return GG_ERR_UNSUPPORTED; }
 	if (npayload < 1 || npayload > GGP_MAX_ACCS) { fail(c, "motion with %d output columns not supported (1..%d)", npayload, GGP_MAX_ACCS); return GG_ERR_UNSUPPORTED; }
+	{
+		Roots roots;
+		if (!valid_header(c, pool, &scan->desc, nullptr)) return GG_ERR_ARG;
+		roots.add(c, pool, scan->qual, true, "scan qual");
+		for (int k = 0; k < nkeys; k++) roots.add(c, pool, hashkeys[k], false, "hash key");
+		for (int k = 0; k < npayload; k++) roots.add(c, pool, payload[k], false, "output column");
+		if (!roots.ok || !valid_nodes(c, pool, &scan->desc, nullptr, roots)) return GG_ERR_ARG;
+	}
 	if (!check_desc(c, &scan->desc)) return GG_ERR_UNSUPPORTED;
 	init_side(&prog->outer, &scan->desc);
 	if (scan->qual >= 0)

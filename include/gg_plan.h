@@ -147,7 +147,10 @@ typedef struct gg_tupdesc {
 	gg_attr attrs[GG_MAX_ATTS];
 } gg_tupdesc;
 
-/* ---- expressions: flat pool, children by index ---- */
+/* ---- expressions: flat pool, children by index ----
+ * A node's arguments have SMALLER indices than the node itself (children are appended before their parents, the way a
+ * post-order walk of the Expr tree emits them); the plan compiler checks this, which is also what rules out cycles.
+ * A malformed pool (index out of range, attribute number outside the descriptor, ...) is GG_ERR_ARG, never a crash. */
 enum gg_expr_kind {
 	GG_E_VAR = 1,      /* varno (0 = outer/scan, 1 = inner), varattno 1-based */
 	GG_E_CONST = 2,    /* constvalue = Datum bits; strings: <=8 blank-stripped bytes packed LSB-first, constlen */

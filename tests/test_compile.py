@@ -158,3 +158,62 @@ def test_q6_plan_compiles_to_one_filter_and_one_sum():
     assert sum(1 for ln in lines if "CMPF_K" in ln) == 3 and sum(1 for ln in lines if "CMPI_K" in ln) == 2
     assert sum(1 for ln in lines if "OUT" in ln and "OUTSQ" not in ln) == 1 and not any("KEY" in ln for ln in lines)
     assert lines[-1].split()[1] == "END"
+
+
+def test_malformed_plans_are_error_codes_not_crashes():
+    """What crosses the C-ABI is validated before anything indexes with it (gg_compile.cpp: valid_nodes): a plan whose
+    expression indices, attribute numbers or counts are out of range comes back as GG_ERR_ARG with a message.  Found by
+    fuzzing the plan compiler under AddressSanitizer (a child index past the pool used to be dereferenced)."""
+    def refused(scan, agg, pool, code=-10):
+        with pytest.raises(capi.GGError) as e:
+            disasm(scan, agg, pool)
+        assert e.value.code == code, (e.value.code, str(e.value))
+        return str(e.value)
+
+    def fresh():
+        scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE)
+        return (type(scan).from_buffer_copy(bytes(scan)), type(agg).from_buffer_copy(bytes(agg)), type(pool).from_buffer_copy(bytes(pool)))
+
+    scan, agg, pool = fresh()
+    assert disasm(scan, agg, pool)                                     # the copy compiles
+    func = next(i for i in range(pool.nnodes) if pool.nodes[i].kind == 3)      # GG_E_FUNC
+    for bad in (2 ** 31 - 1, -7, 4000, func):                          # child index: far out, negative, past the pool, itself (a cycle)
+        scan, agg, pool = fresh()
+        pool.nodes[func].args[0] = bad
+        assert "children come before their parents" in refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    pool.nnodes = 10 ** 6
+    assert "expression pool" in refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    var = next(i for i in range(pool.nnodes) if pool.nodes[i].kind == 1)
+    pool.nodes[var].varattno = 99
+    assert "attribute 99" in refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    pool.nodes[var].varno = 1                                          # an inner Var in a plan without an inner side
+    assert "relation 1" in refused(scan, agg, pool)
+    for field, bad in (("numCols", 77), ("numAggs", -3), ("numAggs", 10 ** 6)):
+        scan, agg, pool = fresh()
+        setattr(agg, field, bad)
+        refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    agg.aggs[0].arg = 12345
+    assert "aggregate argument" in refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    scan.qual = 500
+    assert "scan qual" in refused(scan, agg, pool)
+    scan, agg, pool = fresh()
+    scan.desc.natts = 1000
+    refused(scan, agg, pool)
+    # nodes no root reaches are not looked at: a pool may hold other pipelines' expressions
+    scan, agg, pool = fresh()
+    n = pool.nnodes
+    pool.nodes[n].kind, pool.nodes[n].varno, pool.nodes[n].varattno = 1, 1, 3
+    pool.nnodes = n + 1
+    assert disasm(scan, agg, pool)
+    # the same validation guards the join compiler
+    outer, inner, hj, jagg, jpool = tpch.join_plan(kind="q3ish", jointype=capi.JOIN_INNER)
+    hj = type(hj).from_buffer_copy(bytes(hj))
+    hj.innerkey[0] = -5
+    with pytest.raises(capi.GGError) as e:
+        disasm_join(outer, inner, hj, jagg, jpool)
+    assert e.value.code == -10 and "inner join key" in str(e.value)
