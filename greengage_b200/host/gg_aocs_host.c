@@ -113,6 +113,8 @@ static int attr_ok(const gg_attr *att)
 
 /* ------------------------------------------------ index (loader) ------------------------------------------------ */
 
+static int32_t count_null_bits(const uint8_t *bitmap, int32_t nbits);
+
 /* Stored size shared by every value of a varlena block, or 0.  Only 1-byte-header values qualify (first byte 0x80 | size,
  * postgres.h VARATT_IS_1B in this tree): a zero byte is alignment padding in front of a 4-byte header. */
 static int32_t uniform_varlena_size(const uint8_t *d, int64_t len)
@@ -150,7 +152,7 @@ int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes
 		const uint8_t *b = file + at, *s;
 		uint32_t w0, w1, kind, contentlen, flags, nullbytes, datalen;
 		int64_t hdr, blocklen, firstrow = -1;
-		int nrow, ndatum;
+		int nrow, ndatum, nvalues;
 
 		if (nbytes - at < fixed)
 			return GG_ERR_BADPAGE;
@@ -212,7 +214,10 @@ int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes
 			return GG_ERR_BADPAGE;
 		if (att->attlen > 0 && datalen % (uint32_t) att->attlen != 0)
 			return GG_ERR_BADPAGE;
-		if (att->attlen > 0 && !(flags & FLAG_NULLMAP) && datalen != (uint32_t) nrow * (uint32_t) att->attlen)
+		/* the value area holds exactly the non-NULL rows: the device addresses value i at data_off + i * stride without
+		 * looking at data_len again, so a block that claims more values than it stores must not get into the directory */
+		nvalues = nrow - ((flags & FLAG_NULLMAP) ? count_null_bits(s + STREAM_HDR, nrow) : 0);
+		if (att->attlen > 0 && (int64_t) datalen != (int64_t) nvalues * att->attlen)
 			return GG_ERR_BADPAGE;
 		/* row numbers of consecutive blocks of one segment file are contiguous unless rows were appended by separate
 		 * inserts with gaps in the fast sequence (allowed): they must at least never go backwards */
@@ -232,6 +237,8 @@ int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes
 			dir[nb].data_len = (int32_t) datalen;
 			dir[nb].stride = att->attlen > 0 ? att->attlen
 				: uniform_varlena_size(b + hdr + up8(STREAM_HDR + (int64_t) nullbytes), (int64_t) datalen);
+			if (att->attlen < 0 && dir[nb].stride > 0 && nvalues > 0 && (int64_t) dir[nb].stride * nvalues != (int64_t) datalen)
+				dir[nb].stride = 0;						/* fewer values than rows claim: irregular, the device refuses the block */
 			dir[nb].pad = 0;
 		}
 		nb++;
