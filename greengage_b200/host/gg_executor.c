@@ -195,13 +195,23 @@ static gg_relation *relation_of(GgEState *es, const GgSeqScan *scan)
 
 static int32_t expr_type(const gg_exprpool *pool, int32_t root) { return pool->nodes[root].rettype; }
 
+#define GG_MAX_PLAN_DEPTH 32        /* the deepest accelerated slice is Motion <- Sort <- Agg <- Motion <- Agg <- HashJoin <- Hash <- SeqScan */
+
+static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int depth);
+
 GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
+{
+	g_err[0] = 0; g_errcode = GG_OK;
+	return init_node(node, estate, eflags, 0);
+}
+
+static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int depth)
 {
 	GgPlanState *s;
 	(void) eflags;
-	g_err[0] = 0; g_errcode = GG_OK;
 	if (!node) return NULL;                                   /* ExecInitNode(NULL) is NULL, execProcnode.c:268 */
 	if (!estate || !estate->engine || !estate->pool) return exec_fail(GG_ERR_ARG, "EState without engine or expression pool");
+	if (depth > GG_MAX_PLAN_DEPTH) return exec_fail(GG_ERR_ARG, "plan tree deeper than %d nodes (a cycle?)", GG_MAX_PLAN_DEPTH);
 	s = calloc(1, sizeof *s);
 	if (!s) return exec_fail(GG_ERR_NOMEM, "out of memory");
 	s->plan = node; s->estate = estate;
@@ -213,11 +223,17 @@ GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
 			GgPlan *below = node->lefttree;
 			int rc;
 			s->agg = an->agg;
+			if (an->agg.numCols < 0 || an->agg.numCols > GG_MAX_KEYS || an->agg.numAggs < 0 || an->agg.numAggs > GG_MAX_AGGS)
+			{
+				exec_fail(GG_ERR_ARG, "Agg with %d grouping columns and %d aggregates", an->agg.numCols, an->agg.numAggs);
+				free_state(s);
+				return NULL;
+			}
 			if (an->agg.aggstage == GG_AGGSTAGE_FINAL)
 			{
 				/* the receiving half of a two-stage aggregate: combine what the Motion below delivers */
 				s->kind = K_AGGFINAL;
-				s->child = GgExecInitNode(below, estate, eflags);
+				s->child = init_node(below, estate, eflags, depth + 1);
 				if (!s->child) { free_state(s); return NULL; }
 				return s;
 			}
@@ -263,7 +279,7 @@ GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
 			GgSort *so = (GgSort *) node;
 			if (so->numCols < 1 || so->numCols > GG_MAX_SORTKEYS) { exec_fail(GG_ERR_UNSUPPORTED, "Sort with %d keys", so->numCols); free_state(s); return NULL; }
 			s->kind = K_SORT;
-			s->child = GgExecInitNode(node->lefttree, estate, eflags);
+			s->child = init_node(node->lefttree, estate, eflags, depth + 1);
 			if (!s->child) { free_state(s); return NULL; }
 			return s;
 		}
@@ -274,7 +290,7 @@ GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
 			if (mo->motionType == GG_MOTIONTYPE_HASH && (mo->numHashCols < 1 || mo->numHashCols > GG_MAX_KEYS))
 			{ exec_fail(GG_ERR_UNSUPPORTED, "Redistribute Motion with %d hash columns", mo->numHashCols); free_state(s); return NULL; }
 			s->kind = K_MOTION;
-			s->child = GgExecInitNode(node->lefttree, estate, eflags);
+			s->child = init_node(node->lefttree, estate, eflags, depth + 1);
 			if (!s->child) { free_state(s); return NULL; }
 			return s;
 		}
@@ -342,6 +358,12 @@ static int run_node(GgPlanState *s)
 			gg_agg part = s->agg;
 			if (run_child(s)) return -1;
 			part.aggstage = GG_AGGSTAGE_PARTIAL;      /* layout of the incoming rows */
+			{
+				int want = part.numCols, i;
+				for (i = 0; i < part.numAggs; i++) want += agg_ncols_of(&part, i);
+				if (want != s->child->ncols && s->child->nrows > 0)
+				{ exec_fail(GG_ERR_ARG, "FINAL Agg expects %d columns of partial state, the node below delivers %d", want, s->child->ncols); return -1; }
+			}
 			in = aggrows_from_rows(s->child, &part);
 			cap = s->child->nrows > 0 ? (int) s->child->nrows : 1;
 			out = malloc(sizeof(gg_aggrow) * (size_t) cap);
@@ -402,7 +424,12 @@ static int run_node(GgPlanState *s)
 			else
 			{
 				GgRowBatch send, recv;
-				int32_t *dest = malloc(4 * (size_t) (ch->nrows > 0 ? ch->nrows : 1));
+				int32_t *dest;
+				if (mo->motionType == GG_MOTIONTYPE_HASH)
+					for (c = 0; c < mo->numHashCols; c++)
+						if (mo->hashCol[c] < 0 || mo->hashCol[c] >= ch->ncols)
+						{ exec_fail(GG_ERR_ARG, "Motion hash column %d out of range (the node below has %d columns)", mo->hashCol[c], ch->ncols); return -1; }
+				dest = malloc(4 * (size_t) (ch->nrows > 0 ? ch->nrows : 1));
 				if (!dest) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
 				for (r = 0; r < ch->nrows; r++)
 				{

@@ -6,9 +6,10 @@
 set -e
 cd "$(dirname "$0")/.."
 OUT=$(mktemp -d)
-gcc -O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -std=gnu11 -shared -o "$OUT/libggexec_mock_asan.so" \
-    greengage_b200/host/gg_executor.c greengage_b200/host/gg_motion_host.c tests/mock/ggb200_mock.c \
-    -L oracle -lggoracle -Wl,-rpath,"$PWD/oracle" -lm
+SAN="-O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer"
+for f in greengage_b200/host/gg_executor.c greengage_b200/host/gg_motion_host.c tests/mock/ggb200_mock.c; do gcc $SAN -std=gnu11 -c $f -o "$OUT/$(basename $f).o"; done
+for f in tests/mock/compile_glue.cpp greengage_b200/csrc/gg_compile.cpp; do g++ $SAN -std=c++17 -c $f -o "$OUT/$(basename $f).o"; done
+g++ -shared -fsanitize=address,undefined -o "$OUT/libggexec_mock_asan.so" "$OUT"/*.o -L oracle -lggoracle -Wl,-rpath,"$PWD/oracle" -lm
 cat > "$OUT/worker.py" <<PY
 import ctypes as C, sys
 sys.path.insert(0, "$PWD"); sys.path.insert(0, "$PWD/tests")

@@ -20,6 +20,15 @@ struct gg_joinagg { gg_scan outer, inner; gg_hashjoin hj; gg_agg agg; gg_exprpoo
 static char last_error[256] = "";
 const char *gg_last_error(void) { return last_error; }
 
+/* The product's own plan compiler (greengage_b200/csrc/gg_compile.cpp, host C++, linked in) decides what *_create accepts,
+ * exactly as in libggb200.so: a plan it refuses never reaches the oracle. */
+#include <stdarg.h>
+#include <stdio.h>
+void gg_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(last_error, sizeof last_error, fmt, ap); va_end(ap); }
+int mock_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, char *err, int errlen);
+int mock_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg, const gg_exprpool *pool,
+                      char *err, int errlen);
+
 static int fail(int rc, const char *what)
 {
 	if (rc) { strncpy(last_error, what, sizeof last_error - 1); }
@@ -39,8 +48,11 @@ uint64_t gg_relation_nblocks(gg_relation *r) { return r->nblocks; }
 
 int gg_scanagg_create(gg_engine *e, const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, gg_scanagg **out)
 {
-	gg_scanagg *p = calloc(1, sizeof *p);
+	gg_scanagg *p;
+	int rc = mock_compile_scanagg(scan, agg, pool, last_error, sizeof last_error);
 	(void) e;
+	if (rc != GG_OK) return rc;
+	p = calloc(1, sizeof *p);
 	p->scan = *scan; p->agg = *agg; p->pool = *pool;
 	*out = p;
 	return GG_OK;
@@ -73,8 +85,11 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin, 
 int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
                       const gg_agg *agg, const gg_exprpool *pool, gg_joinagg **out)
 {
-	gg_joinagg *p = calloc(1, sizeof *p);
+	gg_joinagg *p;
+	int rc = mock_compile_join(outer, inner, hj, agg, pool, last_error, sizeof last_error);
 	(void) e;
+	if (rc != GG_OK) return rc;
+	p = calloc(1, sizeof *p);
 	p->outer = *outer; p->inner = *inner; p->hj = *hj; p->agg = *agg; p->pool = *pool;
 	*out = p;
 	return GG_OK;

@@ -19,10 +19,16 @@ ROOT = os.path.dirname(HERE)
 def build_mock(outdir):
     so = os.path.join(outdir, "libggexec_mock.so")
     host = os.path.join(ROOT, "greengage_b200", "host")
-    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-Wall", "-Wextra", "-std=gnu11", "-shared", "-o", so,
-                           os.path.join(host, "gg_executor.c"), os.path.join(host, "gg_motion_host.c"),
-                           os.path.join(HERE, "mock", "ggb200_mock.c"), "-L", os.path.join(ROOT, "oracle"), "-lggoracle",
-                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-Wl,-z,defs", "-lm"])
+    objs = []
+    for src, cc, std in ((os.path.join(host, "gg_executor.c"), "gcc", "-std=gnu11"), (os.path.join(host, "gg_motion_host.c"), "gcc", "-std=gnu11"),
+                         (os.path.join(HERE, "mock", "ggb200_mock.c"), "gcc", "-std=gnu11"),
+                         (os.path.join(HERE, "mock", "compile_glue.cpp"), "g++", "-std=c++17"),
+                         (os.path.join(ROOT, "greengage_b200", "csrc", "gg_compile.cpp"), "g++", "-std=c++17")):   # the product's plan compiler
+        obj = os.path.join(outdir, os.path.basename(src) + ".o")
+        subprocess.check_call([cc, "-O1", "-g", "-fPIC", "-Wall", "-Wextra", std, "-c", src, "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-L", os.path.join(ROOT, "oracle"), "-lggoracle",
+                                                                 "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-Wl,-z,defs", "-lm"])
     return so
 
 
@@ -139,6 +145,34 @@ def single_segment_checks(L, eng, ex):
     except ex.ExecError as e:
         assert e.code == -10
     done.append("motion-needs-transport")
+    # malformed plan trees are error codes, never crashes (scripts/fuzz/run_executor_fuzz.sh found these under ASan)
+    b = ex.PlanBuilder()
+    plan = q1_sorted_plan(b, scan, agg, True)
+    sort = next(n for n in b.nodes if isinstance(n, ex.GgSort))
+    sort.plan.lefttree = ex._as_plan(plan)                               # a cycle: Sort's child is the top Motion again
+    try:
+        ex.Executor(eng, pool, [MockRel(L, pages)], plan)
+        raise AssertionError("accepted a cyclic plan")
+    except ex.ExecError as e:
+        assert e.code == -10 and "deeper" in str(e)
+    b = ex.PlanBuilder()
+    plan = q1_sorted_plan(b, scan, agg, True)
+    fin = next(n for n in b.nodes if isinstance(n, ex.GgAgg) and n.agg.aggstage == capi.AGGSTAGE_FINAL)
+    fin.agg.numAggs = 12                                                 # a FINAL stage that expects more state columns than arrive
+    x = ex.Executor(eng, pool, [MockRel(L, pages)], plan)
+    try:
+        x.rows()
+        raise AssertionError("ran a FINAL Agg over too few columns")
+    except ex.ExecError as e:
+        assert e.code == -10 and "FINAL Agg expects" in str(e)
+    x.end()
+    fin.agg.numAggs = 10 ** 6
+    try:
+        ex.Executor(eng, pool, [MockRel(L, pages)], plan)
+        raise AssertionError("accepted")
+    except ex.ExecError as e:
+        assert e.code == -10
+    done.append("malformed-trees-refused")
     return done
 
 
@@ -216,4 +250,4 @@ def test_node_surface_control_flow_on_one_segment(tmp_path):
     """ReScan, end of stream, Squelch after a LIMIT, Sort DESC above a join pipeline, the loopback Motions of the two-stage
     plan — tests/test_gpu_executor.py's checks with the oracle behind the C-ABI, in a child process"""
     by = run(1, "single", tmp_path)
-    assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "motion-needs-transport"]
+    assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "motion-needs-transport", "malformed-trees-refused"]
