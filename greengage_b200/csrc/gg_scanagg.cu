@@ -930,6 +930,8 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
                  gg_aggrow *out, int outcap, int *nout)
 {
 	if (!e || !agg || !nout || (nin && !in)) return GG_ERR_ARG;
+	if (agg->numCols < 0 || agg->numCols > GG_MAX_KEYS || agg->numAggs < 0 || nin < 0 || outcap < 0 || (outcap && !out))
+	{ gg_set_error("gg_agg_final: %d grouping columns, %d aggregates, %d rows in, room for %d", agg->numCols, agg->numAggs, nin, outcap); return GG_ERR_ARG; }
 	if (agg->numAggs > GGP_MAX_ACCS) { gg_set_error("too many aggregates"); return GG_ERR_UNSUPPORTED; }
 	GG_CUDA(cudaSetDevice(e->device));
 	ggp_program prog;
