@@ -205,7 +205,7 @@ int gg_relation_attach_rows(gg_engine *e, void *device_rows, uint64_t nrows, int
 
 int gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks)
 {
-	if (!r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	if (!r || nblocks > r->nblocks || first_block > r->nblocks - nblocks) return GG_ERR_ARG;
 	GG_CUDA(cudaSetDevice(r->eng->device));
 	GG_CUDA(cudaMemcpyAsync(r->pages + first_block * GG_BLCKSZ, host_pages, (size_t) nblocks * GG_BLCKSZ,
 	                        cudaMemcpyHostToDevice, r->eng->stream));
@@ -214,7 +214,7 @@ int gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_page
 
 int gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uint64_t nblocks)
 {
-	if (!r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	if (!r || nblocks > r->nblocks || first_block > r->nblocks - nblocks) return GG_ERR_ARG;
 	GG_CUDA(cudaSetDevice(r->eng->device));
 	GG_CUDA(cudaMemcpyAsync(host_pages, r->pages + first_block * GG_BLCKSZ, (size_t) nblocks * GG_BLCKSZ,
 	                        cudaMemcpyDeviceToHost, r->eng->stream));

@@ -127,7 +127,7 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
  * planner's row estimate, nodeHash.c:463; the pages give a tight bound for free), then one scan inserts. */
 int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, uint64_t nblocks)
 {
-	if (!j || !inner || first_block + nblocks > inner->nblocks) return GG_ERR_ARG;
+	if (!j || !inner || nblocks > inner->nblocks || first_block > inner->nblocks - nblocks) return GG_ERR_ARG;
 	if (inner->rowwords != j->jp.build.outer.rowwords) { gg_set_error("inner relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
 	if (inner->rowwords && (first_block != 0 || nblocks != inner->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	gg_engine *e = j->eng;

@@ -24,7 +24,7 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
                         uint64_t *host_counts, uint64_t *host_offsets)
 {
 	if (!e || !scan || !pool || !hashkeys || !payload || !r || !host_counts || nsegs < 1 || nsegs > 1024 ||
-	    first_block + nblocks > r->nblocks || (!device_out_rows && out_cap_rows))
+	    nblocks > r->nblocks || first_block > r->nblocks - nblocks || (!device_out_rows && out_cap_rows))
 		return GG_ERR_ARG;
 	GG_CUDA(cudaSetDevice(e->device));
 	std::vector<ggp_program> progbuf(1);   /* 3 KB: kept off the stack */

@@ -633,7 +633,7 @@ int gg_scanagg_reset(gg_scanagg *p)
 
 int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t nblocks)
 {
-	if (!p || !r || first_block + nblocks > r->nblocks) return GG_ERR_ARG;
+	if (!p || !r || nblocks > r->nblocks || first_block > r->nblocks - nblocks) return GG_ERR_ARG;
 	if (r->rowwords != p->prog.outer.rowwords) { gg_set_error("relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
 	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	gg_engine *e = p->eng;
