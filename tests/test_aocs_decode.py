@@ -105,3 +105,21 @@ def test_q1_columns_of_the_synthetic_relation(harness):
         want = [np.float64(h[4]).view(np.uint64), np.float64(h[5]).view(np.uint64), np.float64(h[6]).view(np.uint64),
                 np.float64(h[7]).view(np.uint64), h[8][0], h[9][0], np.int64(h[10]).view(np.uint64)]
         assert [int(x) for x in rows[i, 1:]] == [int(x) for x in want], i
+
+
+def test_null_mask_of_a_multi_column_row(harness, kat):
+    """columns with independent NULLs and different block boundaries: word 0 of every row carries one bit per projected column"""
+    keys = ["int8_n2_c1", "date_n2_c1", "float8_n0_c1", "int4_n2_c0"]
+    names = [k.split("_")[0] for k in keys]
+    # the golden files of one type share their values but every file drew its own NULLs; all hold 2500 rows
+    out = []
+    for cs in (True, False):
+        sel = [i for i, k in enumerate(keys) if k.endswith("c1") == cs]
+        rows, err = host_decode(harness, [attr(names[i]) for i in sel], [kat[keys[i] + "_file"] for i in sel], 777, cs)
+        assert err == 0 and len(rows) == 2500
+        want_mask = np.zeros(2500, dtype=np.uint64)
+        for bit, i in enumerate(sel):
+            want_mask |= kat[keys[i] + "_nulls"].astype(np.uint64) << np.uint64(bit)
+        assert np.array_equal(rows[:, 0], want_mask)
+        out.append(rows)
+    assert out[0][:, 0].max() >= 3 and (out[0][:, 0] == 0).any()      # rows with both NULL bits, rows with none
