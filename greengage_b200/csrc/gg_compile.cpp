@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
+#include <cstdlib>
 #include "gg_program.h"
 #include "../../include/ggb200.h"
 
@@ -42,6 +43,14 @@ void fail(Ctx &c, const char *fmt, ...)
 	va_start(ap, fmt);
 	vsnprintf(c.err, (size_t) c.errlen, fmt, ap);
 	va_end(ap);
+}
+
+/* switches for measurements that are not validated yet: off unless the variable is set to something
+ * other than "0"; with every switch off the compiler's output is what round 1 validated on the GPU */
+static bool experiment(const char *name)
+{
+	const char *v = getenv(name);
+	return v && v[0] && !(v[0] == '0' && !v[1]);
 }
 
 int loadtype_of(int32_t typid)
@@ -549,7 +558,7 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			case GG_AGG_SUM_FLOAT8: kind = GGP_ACC_F8SUM; break;
 			/* float8_accum also maintains sumX2, which float8_avg ignores (float.c:1982): only a PARTIAL stage,
 			 * whose transition state {N, sumX, sumX2} is shipped to another process, has to produce it */
-			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = (agg->aggstage == GG_AGGSTAGE_PARTIAL); break;
+			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = (agg->aggstage == GG_AGGSTAGE_PARTIAL) && !experiment("GGB200_PARTIAL_NO_SUMSQ"); break;
 			case GG_AGG_MIN_FLOAT8: kind = GGP_ACC_F8MIN; break;
 			case GG_AGG_MAX_FLOAT8: kind = GGP_ACC_F8MAX; break;
 			case GG_AGG_SUM_INT4: kind = GGP_ACC_I8SUM; break;
@@ -726,7 +735,29 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 	init_side(&prog->outer, &scan->desc);
 
 	/* ---- scan qual ---- */
-	if (scan->qual >= 0)
+	if (scan->qual >= 0 && experiment("GGB200_FLATTEN_QUAL"))
+	{
+		/* an implicit-AND qual is a list of clauses ExecQual walks until one is not true (execQual.c:6260-6310): one FILTER
+		 * per clause instead of three-valued ANDs feeding one FILTER, so lanes that already failed skip nothing they need
+		 * and a clause the reference would not have reached cannot raise */
+		int stack[GG_MAX_EXPR_NODES], sp = 0, clauses[GG_MAX_EXPR_NODES], nc = 0;
+		stack[sp++] = scan->qual;
+		while (sp > 0)
+		{
+			const int r = stack[--sp];
+			const gg_expr &e = pool->nodes[r];
+			if (e.kind == GG_E_AND && sp + 2 <= GG_MAX_EXPR_NODES) { stack[sp++] = e.args[1]; stack[sp++] = e.args[0]; }   /* left clause first */
+			else clauses[nc++] = r;
+		}
+		for (int k = 0; k < nc && !c.failed; k++)
+		{
+			ggp_op *o = gen_value(c, clauses[k]);
+			if (c.failed) break;
+			if (o->flags & GGP_F_FILTER) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+			o->flags |= GGP_F_FILTER;
+		}
+	}
+	else if (scan->qual >= 0)
 	{
 		ggp_op *o = gen_value(c, scan->qual);
 		if (!c.failed) o->flags |= GGP_F_FILTER;

@@ -1,6 +1,7 @@
 /* Test/fuzz harness: the plan compiler's entry points without the CUDA library (scripts/fuzz/run_compiler_fuzz.sh). */
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 #include <vector>
 #include "../../greengage_b200/csrc/gg_program.h"
 #include "../../include/ggb200.h"
@@ -29,4 +30,25 @@ extern "C" int fz_motion(const gg_scan *scan, const gg_exprpool *pool, const int
 	int rc = ggp_compile_motion(scan, pool, hk, nkeys, pl, npl, &prog, ht, msg, sizeof msg);
 	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
 	return ggp_disasm(&prog, buf, cap);
+}
+/* the whole compiled program and aggregate map as bytes (comparing two builds of the compiler) */
+extern "C" int fz_scanagg_raw(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, unsigned char *out, int cap)
+{
+	ggp_program prog; ggp_aggmap aggmap[GG_MAX_AGGS]; char msg[256];
+	memset(aggmap, 0, sizeof aggmap);
+	int rc = ggp_compile_scanagg(scan, agg, pool, &prog, aggmap, msg, sizeof msg);
+	if (rc != GG_OK) return rc;
+	if ((int) (sizeof prog + sizeof aggmap) > cap) return -8;
+	memcpy(out, &prog, sizeof prog); memcpy(out + sizeof prog, aggmap, sizeof aggmap);
+	return (int) (sizeof prog + sizeof aggmap);
+}
+extern "C" int fz_join_raw(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg, const gg_exprpool *pool, unsigned char *out, int cap)
+{
+	std::vector<ggp_joinprog> jpbuf(1); ggp_aggmap aggmap[GG_MAX_AGGS]; char msg[256];
+	memset(aggmap, 0, sizeof aggmap);
+	int rc = ggp_compile_join(outer, inner, hj, agg, pool, &jpbuf[0], aggmap, msg, sizeof msg);
+	if (rc != GG_OK) return rc;
+	if ((int) (sizeof(ggp_joinprog) + sizeof aggmap) > cap) return -8;
+	memcpy(out, &jpbuf[0], sizeof(ggp_joinprog)); memcpy(out + sizeof(ggp_joinprog), aggmap, sizeof aggmap);
+	return (int) (sizeof(ggp_joinprog) + sizeof aggmap);
 }

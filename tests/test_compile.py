@@ -217,3 +217,25 @@ def test_malformed_plans_are_error_codes_not_crashes():
     with pytest.raises(capi.GGError) as e:
         disasm_join(outer, inner, hj, jagg, jpool)
     assert e.value.code == -10 and "inner join key" in str(e.value)
+
+
+def test_experiment_switches_change_only_what_they_say(monkeypatch):
+    """Two measurements queued for the next round sit behind environment switches that are off by default
+    (scripts/fuzz/compiler_compare.py shows the default output byte-identical to the compiler round 1 validated on the GPU):
+    one FILTER per clause of an implicit-AND qual, and a PARTIAL stage without avg's sumX2 columns."""
+    from _util import lineitem_fixture_pages, tpch_q6_plan
+    desc, _, _ = lineitem_fixture_pages()
+    base = disasm(*tpch_q6_plan(desc))
+    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
+    flat = disasm(*tpch_q6_plan(desc))
+    assert sum(1 for ln in flat if "FILTER" in ln) == 5 and not any("AND_T" in ln for ln in flat)
+    assert len(flat) < len(base)
+    assert [ln.split()[1] for ln in flat if "OUT" in ln] == [ln.split()[1] for ln in base if "OUT" in ln]
+    assert disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE)) is not None          # a single-clause qual is unchanged in shape
+    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "0")
+    assert disasm(*tpch_q6_plan(desc)) == base
+    part = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
+    monkeypatch.setenv("GGB200_PARTIAL_NO_SUMSQ", "1")
+    nosq = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
+    assert sum(1 for ln in part if "OUTSQ" in ln) == 3 and not any("OUTSQ" in ln for ln in nosq)
+    assert nosq == disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL))   # the program is then the one-stage plan's
