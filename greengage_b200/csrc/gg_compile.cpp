@@ -740,12 +740,14 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 		/* an implicit-AND qual is a list of clauses ExecQual walks until one is not true (execQual.c:6260-6310): one FILTER
 		 * per clause instead of three-valued ANDs feeding one FILTER, so lanes that already failed skip nothing they need
 		 * and a clause the reference would not have reached cannot raise */
-		int stack[GG_MAX_EXPR_NODES], sp = 0, clauses[GG_MAX_EXPR_NODES], nc = 0;
+		int stack[GG_MAX_EXPR_NODES], sp = 0, clauses[GG_MAX_EXPR_NODES], nc = 0, steps = 0;
 		stack[sp++] = scan->qual;
-		while (sp > 0)
+		while (sp > 0 && !c.failed)
 		{
 			const int r = stack[--sp];
 			const gg_expr &e = pool->nodes[r];
+			/* a pool is a DAG: AND nodes sharing children could be walked exponentially often — bounded, then refused */
+			if (++steps > 4 * GG_MAX_EXPR_NODES || nc >= GG_MAX_EXPR_NODES) { fail(c, "qual with too many clauses"); break; }
 			if (e.kind == GG_E_AND && sp + 2 <= GG_MAX_EXPR_NODES) { stack[sp++] = e.args[1]; stack[sp++] = e.args[0]; }   /* left clause first */
 			else clauses[nc++] = r;
 		}

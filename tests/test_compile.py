@@ -239,3 +239,16 @@ def test_experiment_switches_change_only_what_they_say(monkeypatch):
     nosq = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
     assert sum(1 for ln in part if "OUTSQ" in ln) == 3 and not any("OUTSQ" in ln for ln in nosq)
     assert nosq == disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL))   # the program is then the one-stage plan's
+
+
+def test_flattening_a_shared_and_chain_is_bounded(monkeypatch):
+    """a pool is a DAG: and(x, x) nested 60 deep would be 2^60 clauses if walked as a tree"""
+    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
+    desc = make_desc([(capi.INT4OID, 4, 'i', 1)])
+    p = ExprPool()
+    q = p.func(capi.F_INT4GT, capi.BOOLOID, p.var(1, capi.INT4OID), p.const(capi.INT4OID, 0))
+    for _ in range(60):
+        q = p.boolop(capi.E_AND, q, q)
+    with pytest.raises(capi.GGError) as e:
+        disasm(capi.make_scan(desc, q), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool)
+    assert e.value.code == -6 and "too many clauses" in str(e.value)
