@@ -10,7 +10,14 @@
  *     cdbhash.c:191-287,549-560)
  */
 #pragma once
+#ifdef GG_HOST_EMU
+/* tests/emu/gg_host_emu.h: host stand-ins for the shared-memory accessors and the few intrinsics used below, so that the
+ * tuple walk and the interpreter of THIS file can be compiled by g++ and run on a CPU against the oracle
+ * (tests/test_device_emu.py).  Never defined in a product build. */
+#include "gg_host_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "gg_program.h"
 
@@ -18,6 +25,7 @@
 
 namespace ggd {
 
+#ifndef GG_HOST_EMU
 /* ---------------- PTX wrappers ---------------- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -73,6 +81,7 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void sts64(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v)); }
 __device__ __forceinline__ void stsf64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+#endif /* !GG_HOST_EMU */
 
 /* ---------------- hashing: bit-exact with hashfunc.c ---------------- */
 __device__ __forceinline__ uint32_t rot32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }

@@ -1,0 +1,158 @@
+/*
+ * device_emu.cpp — TEST INFRASTRUCTURE.  The product's plan compiler (gg_compile.cpp) and the product's device
+ * interpreter (gg_device.cuh: walk_tuple + run_prog, compiled for the host through gg_host_emu.h) driven over heap pages by
+ * a plain loop, one tuple at a time; a host sink folds what the program emits the way the kernels' sinks and the merge
+ * kernel do (per accumulator kind).  tests/test_device_emu.py compares the result with the oracle for random plans: a
+ * differential test of compiler + interpreter semantics that needs no GPU.  What it does NOT cover is everything
+ * parallel — warps, the TMA ring, shared-memory accumulators, the merge kernel, atomics: that is the GPU tests' job.
+ */
+#define GG_HOST_EMU
+#include "gg_host_emu.h"
+#include "../../greengage_b200/csrc/gg_device.cuh"
+#include "../../include/ggb200.h"
+#include <map>
+#include <vector>
+#include <array>
+
+uint8_t gg_emu_smem[GG_EMU_SMEM_BYTES];
+void gg_set_error(const char *, ...) {}
+
+using namespace ggd;
+
+struct EmuGroup {
+	uint64_t key[GG_MAX_KEYS];
+	uint32_t keynull;
+	uint32_t pad;
+	uint64_t count;
+	double   sum[GGP_MAX_ACCS];      /* by accumulator column; I8* kinds keep int64 bits */
+	double   sumsq[GGP_MAX_ACCS];
+	uint64_t n[GGP_MAX_ACCS];
+};
+
+struct HostSink {
+	const ggp_program *P;
+	std::map<std::array<uint64_t, GG_MAX_KEYS + 1>, EmuGroup> groups;
+	uint64_t k[GG_MAX_KEYS];
+	uint32_t knull;
+	EmuGroup *cur;
+	unsigned long long npassed;
+
+	void begin_row() { memset(k, 0, sizeof k); knull = 0; cur = nullptr; }
+	bool filter(bool pass) { return pass; }
+	void key(int kc, uint64_t v, bool isnull)
+	{
+		if (isnull) { knull |= 1u << kc; return; }
+		k[kc] = normalize_key(v, P->keytype[kc]);
+	}
+	bool group(bool live)
+	{
+		if (!live) { cur = nullptr; return false; }
+		std::array<uint64_t, GG_MAX_KEYS + 1> id;
+		for (int i = 0; i < GG_MAX_KEYS; i++) id[i] = (i < P->nkeys && !((knull >> i) & 1)) ? k[i] : 0;
+		id[GG_MAX_KEYS] = knull;
+		auto it = groups.find(id);
+		if (it == groups.end())
+		{
+			EmuGroup g;
+			memset(&g, 0, sizeof g);
+			for (int i = 0; i < GG_MAX_KEYS; i++) g.key[i] = id[i];
+			g.keynull = knull;
+			it = groups.emplace(id, g).first;
+		}
+		cur = &it->second;
+		cur->count++;
+		npassed++;
+		return true;
+	}
+	/* slot j < nacc is accumulator column j; a slot >= nacc is the sum of squares of the column whose accsq names it */
+	void out(int slot, double v, bool isnull)
+	{
+		if (!cur || isnull) return;
+		if (slot >= P->nacc)
+		{
+			for (int j = 0; j < P->nacc; j++)
+				if (P->accsq[j] == slot) cur->sumsq[j] = cur->sumsq[j] + v;
+			return;
+		}
+		const int kind = P->acckind[slot];
+		double &s = cur->sum[slot];
+		uint64_t &nn = cur->n[slot];
+		const long long vi = __double_as_longlong(v), si = __double_as_longlong(s);
+		switch (kind)
+		{
+			case GGP_ACC_F8SUM: s = s + v; break;
+			case GGP_ACC_I8SUM: s = __longlong_as_double(si + vi); break;
+			case GGP_ACC_F8MIN: if (nn == 0 || f8_cmp(v, s) < 0) s = v; break;
+			case GGP_ACC_F8MAX: if (nn == 0 || f8_cmp(v, s) > 0) s = v; break;
+			case GGP_ACC_I8MIN: if (nn == 0 || vi < si) s = v; break;
+			case GGP_ACC_I8MAX: if (nn == 0 || vi > si) s = v; break;
+			default: break;                              /* GGP_ACC_COUNT: only n */
+		}
+		nn++;
+	}
+};
+
+template <bool NULLABLE>
+static void run_pages(const ggp_program &P, const uint8_t *pages, uint64_t nblocks, HostSink &sink, uint32_t &err, uint64_t &scanned)
+{
+	const uint32_t PG = 0, OFFS = GG_BLCKSZ + 1024;         /* page at 0, the per-lane offset scratch after it */
+	for (uint64_t b = 0; b < nblocks; b++)
+	{
+		memcpy(gg_emu_smem + PG, pages + b * (uint64_t) GG_BLCKSZ, GG_BLCKSZ);
+		const uint32_t pd_lower = lds16(PG + 12);
+		const int nitems = pd_lower >= GG_PAGE_HEADER_SIZE ? (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2) : 0;
+		for (int i = 0; i < nitems; i++)
+		{
+			const uint32_t lp = lds32(PG + GG_PAGE_HEADER_SIZE + 4 * (uint32_t) i);
+			const uint32_t off = lp & 0x7FFF, flags = (lp >> 15) & 3, len = lp >> 17;
+			if (flags != 1) continue;                       /* LP_NORMAL */
+			const uint32_t tup = PG + off;
+			const bool hasnulls = (lds16(tup + 20) & GG_HEAP_HASNULL) != 0;
+			EvalCtx X;
+			memset(&X, 0, sizeof X);
+			X.P = &P; X.offs = OFFS; X.lane = 0; X.fast = !hasnulls;
+			uint32_t e0 = err;
+			walk_tuple(P.outer, tup, len, X.fast, OFFS, 0, X.tv, err);
+			scanned++;
+			bool live = !(err != e0 && (err & GGP_EF_BADPAGE));
+			if (!NULLABLE && X.tv.colnull) { err |= GGP_EF_NOTNULL_VIOLATED; live = false; }
+			sink.begin_row();
+			run_prog<NULLABLE, false>(X, live, err, sink);
+		}
+	}
+}
+
+/* compile with the product's compiler, run with the product's interpreter; groups come back as EmuGroup records */
+extern "C" int emu_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, const uint8_t *pages, uint64_t nblocks,
+                           EmuGroup *out, int cap, int *nout, int32_t *aggcol /* [GG_MAX_AGGS] */, int32_t *accsq /* [GGP_MAX_ACCS] */,
+                           uint64_t *scanned, uint64_t *passed, uint32_t *errflags, char *msg, int msglen)
+{
+	static ggp_program P;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	int rc = ggp_compile_scanagg(scan, agg, pool, &P, aggmap, msg, msglen);
+	if (rc != GG_OK) return rc;
+	HostSink sink;
+	sink.P = &P; sink.npassed = 0; sink.cur = nullptr;
+	uint32_t err = 0;
+	uint64_t nscan = 0;
+	if (P.nullable) run_pages<true>(P, pages, nblocks, sink, err, nscan);
+	else run_pages<false>(P, pages, nblocks, sink, err, nscan);
+	if (P.nkeys == 0 && sink.groups.empty())               /* plain aggregate over no rows: the one group exists (count 0) */
+	{
+		sink.begin_row();
+		std::array<uint64_t, GG_MAX_KEYS + 1> id{};
+		EmuGroup g; memset(&g, 0, sizeof g);
+		sink.groups.emplace(id, g);
+	}
+	int n = 0;
+	for (auto &kv : sink.groups)
+	{
+		if (n >= cap) return GG_ERR_NOMEM;
+		out[n++] = kv.second;
+	}
+	*nout = n;
+	for (int i = 0; i < agg->numAggs; i++) aggcol[i] = aggmap[i].col;
+	for (int j = 0; j < GGP_MAX_ACCS; j++) accsq[j] = P.accsq[j];
+	*scanned = nscan; *passed = sink.npassed; *errflags = err;
+	return GG_OK;
+}

@@ -1,0 +1,171 @@
+"""Differential test of the plan compiler + the device interpreter on the CPU: tests/emu/device_emu.cpp compiles
+greengage_b200/csrc/gg_device.cuh for the host (-DGG_HOST_EMU: shared memory becomes a byte array, nothing else changes) and
+runs walk_tuple + run_prog tuple by tuple over heap pages for plans built by the same random generator the GPU tests use;
+the groups must equal the oracle's.  Sequential on both sides, so float8 sums are compared bit for bit.  Covers what a
+program MEANS (operand decoding, NULL tracking, three-valued logic, comparisons, casts, key normalisation, error flags);
+the parallel machinery around it is the GPU tests' job."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from _util import make_desc
+from greengage_b200 import capi
+from greengage_b200.capi import ExprPool
+from oracle import pyoracle as po
+import test_gpu_random_plans as rp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ARITH = 0x01 | 0x02 | 0x04 | 0x80 | 0x200            # GGP_EF_FLOAT_OVERFLOW | UNDERFLOW | DIV_ZERO | DATE_RANGE | INT_OVERFLOW
+
+
+class EmuGroup(C.Structure):
+    _fields_ = [("key", C.c_uint64 * capi.GG_MAX_KEYS), ("keynull", C.c_uint32), ("pad", C.c_uint32), ("count", C.c_uint64),
+                ("sum", C.c_double * 16), ("sumsq", C.c_double * 16), ("n", C.c_uint64 * 16)]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libemu.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-I", os.path.join(HERE, "emu"), "-shared", "-o", so,
+                           os.path.join(HERE, "emu", "device_emu.cpp"), os.path.join(ROOT, "greengage_b200", "csrc", "gg_compile.cpp")])
+    L = C.CDLL(so)
+    L.emu_scanagg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                              C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_char_p, C.c_int]
+    return L
+
+
+@pytest.fixture(scope="module")
+def relation():
+    rng = np.random.default_rng(77)
+    desc = make_desc([(capi.INT4OID, 4, "i", 1, 1), (capi.INT4OID, 4, "i", 1, 1), (capi.INT4OID, 4, "i", 1, 0), (capi.FLOAT8OID, 8, "d", 1, 1),
+                      (capi.FLOAT8OID, 8, "d", 1, 0), (capi.BPCHAROID, -1, "i", 0, 0), (capi.DATEOID, 4, "i", 1, 1), (capi.INT8OID, 8, "d", 1, 1)])
+    rows, nulls = [], []
+    for _ in range(4000):
+        rows.append([int(rng.integers(0, 5)), int(rng.integers(-20, 20)), int(rng.integers(-5, 5)), float(rng.integers(-40, 40)) / 4,
+                     float(rng.choice([0.0, -0.0, 0.5, -1.25, 3.0, 1e-3, float(rng.integers(-9, 9))])), bytes([65 + int(rng.integers(0, 3))]) + b" ",
+                     int(rng.integers(-400, 400)), int(rng.integers(-10**9, 10**9))])
+        nulls.append([False, False, rng.random() < 0.15, False, rng.random() < 0.15, rng.random() < 0.1, False, False])
+    return desc, po.build_pages(desc, rows, nulls)
+
+
+def run_emu(L, scan, agg, pool, pages, cap=4096):
+    out = (EmuGroup * cap)()
+    n, sc, ps, err = C.c_int(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    aggcol, accsq = (C.c_int32 * capi.GG_MAX_AGGS)(), (C.c_int32 * 16)()
+    msg = C.create_string_buffer(256)
+    rc = L.emu_scanagg(C.byref(scan), C.byref(agg), C.byref(pool), pages.ctypes.data, pages.size // capi.GG_BLCKSZ, out, cap, C.byref(n),
+                       aggcol, accsq, C.byref(sc), C.byref(ps), C.byref(err), msg, 256)
+    assert rc == 0, (rc, msg.value)
+    return [out[i] for i in range(n.value)], list(aggcol), sc.value, ps.value, err.value
+
+
+def check(groups, aggcol, want, agg):
+    by = {}
+    for g in groups:
+        by[tuple((None if (g.keynull >> c) & 1 else int(np.uint64(g.key[c]).astype(np.int64))) for c in range(agg.numCols))] = g
+    assert len(by) == len(want)
+    partial = agg.aggstage == capi.AGGSTAGE_PARTIAL
+    for r in want:
+        g = by[tuple(None if r.keyisnull[c] else r.key[c] for c in range(agg.numCols))]
+        for i in range(agg.numAggs):
+            fn, col, v = agg.aggs[i].aggfnoid, aggcol[i], r.agg[i]
+            if col < 0:
+                assert v.i == g.count
+                continue
+            nn, s = g.n[col], g.sum[col]
+            ibits = int(np.float64(s).view(np.int64))
+            if fn == capi.AGG_COUNT_ANY:
+                assert v.i == nn
+            elif fn == capi.AGG_AVG_FLOAT8:
+                if partial:
+                    assert (v.f[0], v.f[1]) == (float(nn), s) and v.f[2] == g.sumsq[col], (v.f[2], g.sumsq[col])
+                elif nn == 0:
+                    assert v.isnull
+                else:
+                    assert v.f[0] == s / nn
+            elif fn in (capi.AGG_SUM_FLOAT8, capi.AGG_MIN_FLOAT8, capi.AGG_MAX_FLOAT8):
+                assert bool(v.isnull) == (nn == 0)
+                if nn:
+                    assert v.f[0] == s or (v.f[0] != v.f[0] and s != s), (fn, v.f[0], s)
+            else:
+                assert bool(v.isnull) == (nn == 0)
+                if nn:
+                    assert v.i == ibits, (fn, v.i, ibits)
+
+
+def random_plan(desc, seed, depth=2):
+    rng = np.random.default_rng(1000 + seed)
+    p = ExprPool()
+    g = rp.Gen(rng, p)
+    qual = g.boolean(depth) if rng.random() < 0.8 else -1
+    aggs = [(capi.AGG_COUNT_STAR, -1)]
+    for _ in range(int(rng.integers(1, 5))):
+        fn = int(rng.choice([capi.AGG_SUM_FLOAT8, capi.AGG_AVG_FLOAT8, capi.AGG_MIN_FLOAT8, capi.AGG_MAX_FLOAT8, capi.AGG_COUNT_ANY]))
+        aggs.append((fn, g.f8(depth)))
+    if rng.random() < 0.5:
+        aggs.append((int(rng.choice([capi.AGG_SUM_INT4, capi.AGG_MIN_INT4, capi.AGG_MAX_INT4])), p.var(int(rng.choice([2, 3])), capi.INT4OID)))
+    keys = [[], [p.var(1, capi.INT4OID)], [p.var(1, capi.INT4OID), p.var(6, capi.BPCHAROID)]][int(rng.integers(0, 3))]
+    stage = capi.AGGSTAGE_PARTIAL if rng.random() < 0.3 else capi.AGGSTAGE_NORMAL
+    return capi.make_scan(desc, qual), capi.make_agg(stage, keys, aggs, num_groups=int(rng.choice([0, 20, 500]))), p
+
+
+def differential(emu, relation, seeds, stats):
+    desc, pages = relation
+    for seed in seeds:
+        scan, agg, p = random_plan(desc, seed)
+        try:
+            want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages)
+            oracle_error = None
+        except po.OracleError as e:
+            oracle_error = e
+        groups, aggcol, gsc, gps, err = run_emu(emu, scan, agg, p.pool, pages)
+        if oracle_error is not None:
+            assert err & ARITH, (seed, str(oracle_error), hex(err))
+            stats["errors"] += 1
+        elif err & ARITH:
+            stats["skipped_arm_raised"] += 1          # AND/OR evaluate both arms on the device: known deviation
+        else:
+            assert err == 0 or not (err & ~0x800), (seed, hex(err))
+            assert (gsc, gps) == (sc, ps), seed
+            check(groups, aggcol, want, agg)
+            stats["equal"] += 1
+
+
+def test_random_plans_mean_what_the_oracle_computes(emu, relation):
+    stats = {"equal": 0, "errors": 0, "skipped_arm_raised": 0}
+    differential(emu, relation, range(300), stats)
+    assert stats["equal"] > 200 and stats["errors"] > 0, stats
+    assert stats["skipped_arm_raised"] <= 0.1 * 300, stats
+
+
+def test_the_experiment_switches_keep_the_meaning(emu, relation, monkeypatch):
+    """one FILTER per qual clause / a PARTIAL stage without sumX2 against the same oracle answers"""
+    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
+    stats = {"equal": 0, "errors": 0, "skipped_arm_raised": 0}
+    differential(emu, relation, range(150), stats)
+    assert stats["equal"] > 100, stats
+    monkeypatch.delenv("GGB200_FLATTEN_QUAL")
+    monkeypatch.setenv("GGB200_PARTIAL_NO_SUMSQ", "1")
+    desc, pages = relation
+    for seed in range(60):
+        scan, agg, p = random_plan(desc, seed)
+        if agg.aggstage != capi.AGGSTAGE_PARTIAL:
+            continue
+        try:
+            want, sc, ps = po.seqscan_agg(scan, agg, p.pool, pages)
+        except po.OracleError:
+            continue
+        groups, aggcol, gsc, gps, err = run_emu(emu, scan, agg, p.pool, pages)
+        if err & ARITH:
+            continue
+        for g in groups:
+            assert not any(g.sumsq[j] for j in range(16))
+        for r in want:                                   # everything but sumX2 is unchanged
+            for i in range(agg.numAggs):
+                if agg.aggs[i].aggfnoid == capi.AGG_AVG_FLOAT8:
+                    r.agg[i].f[2] = 0.0
+        check(groups, aggcol, want, agg)
