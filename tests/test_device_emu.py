@@ -169,3 +169,36 @@ def test_the_experiment_switches_keep_the_meaning(emu, relation, monkeypatch):
                 if agg.aggs[i].aggfnoid == capi.AGG_AVG_FLOAT8:
                     r.agg[i].f[2] = 0.0
         check(groups, aggcol, want, agg)
+
+
+def test_reference_golden_plans_through_the_device_interpreter(emu):
+    """the scan/aggregate plans of the reference-golden GPU tests (Q1, Q6, onek, gp_hashagg), compiled by the product and run
+    by the product's interpreter on the CPU: the reference's own answers"""
+    from _util import Q6_GOLDEN_REVENUE, golden, gp_hashagg_case, lineitem_fixture_pages, onek_fixture, onek_plans, tpch_q6_plan
+    from greengage_b200 import tpch
+    desc, pages, n = lineitem_fixture_pages()
+    scan, agg, pool = tpch_q6_plan(desc)
+    groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, pool, pages)
+    assert err == 0 and sc == n and len(groups) == 1
+    assert abs(groups[0].sum[aggcol[0]] - Q6_GOLDEN_REVENUE) <= 1e-6 * Q6_GOLDEN_REVENUE and groups[0].count == ps
+    exp = golden("q1_expected.json")
+    scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL, interval_days=exp["interval_days"], desc=desc)
+    groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, pool, pages)
+    by = {(chr(g.key[0] & 0xFF), chr(g.key[1] & 0xFF)): g for g in groups}
+    assert err == 0 and len(by) == 4
+    for e in exp["rows"]:
+        g = by[(e["returnflag"], e["linestatus"])]
+        assert g.count == e["count_order"]
+        for i, name in enumerate(("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge")):
+            assert abs(g.sum[aggcol[i]] - float(e[name])) <= 1e-6 * float(e[name])
+        assert abs(g.sum[aggcol[4]] / g.n[aggcol[4]] - float(e["avg_qty"])) <= 1e-6 * float(e["avg_qty"])
+    d, pg, oexp = onek_fixture()
+    plain, grouped = onek_plans(d, oexp)
+    groups, aggcol, sc, ps, err = run_emu(emu, *plain, pg)
+    f8i = lambda x: int(np.float64(x).view(np.int64))
+    assert err == 0 and (f8i(groups[0].sum[aggcol[0]]), f8i(groups[0].sum[aggcol[1]]), groups[0].n[aggcol[2]]) == (oexp["sum_four"], oexp["max_four"], oexp["count_four"])
+    groups, aggcol, sc, ps, err = run_emu(emu, *grouped, pg)
+    assert err == 0 and sorted([int(np.int32(g.key[0] & 0xFFFFFFFF)), g.count, f8i(g.sum[aggcol[1]])] for g in groups) == oexp["by_ten"]
+    d, pg, scan, agg, pool, want = gp_hashagg_case()
+    groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, pool, pg)
+    assert err == 0 and {capi.unpack_str(g.key[0], 8).rstrip("\0"): f8i(g.sum[aggcol[0]]) for g in groups} == want
