@@ -122,6 +122,31 @@ static void run_pages(const ggp_program &P, const uint8_t *pages, uint64_t nbloc
 	}
 }
 
+/* GG_FMT_DATUMROWS input (what a receiving Motion delivers and what gg_aocs_decode_rows produces): the datum-row front end of
+ * scanagg_body — NULL mask word, then one 64-bit word per column at constant offsets (gg_scanagg_kernel.cuh) */
+template <bool NULLABLE>
+static void run_rows(const ggp_program &P, const uint64_t *rows, uint64_t nrows, HostSink &sink, uint32_t &err, uint64_t &scanned)
+{
+	const uint32_t RP = 0, rowwords = (uint32_t) P.outer.rowwords;
+	for (uint64_t r = 0; r < nrows; r++)
+	{
+		memcpy(gg_emu_smem + RP, rows + r * rowwords, (size_t) rowwords * 8);
+		EvalCtx X;
+		memset(&X, 0, sizeof X);
+		X.P = &P; X.offs = 65536; X.lane = 0; X.fast = true;
+		X.tv.tp = RP + 8;
+		uint32_t cn = 0;
+		const uint64_t mask = lds64(RP);
+		for (int sl = 0; sl < P.outer.ncols; sl++) cn |= (uint32_t) ((mask >> P.outer.colatt[sl]) & 1) << sl;
+		X.tv.colnull = cn;
+		bool live = true;
+		scanned++;
+		if (!NULLABLE && cn) { err |= GGP_EF_NOTNULL_VIOLATED; live = false; }
+		sink.begin_row();
+		run_prog<NULLABLE, false>(X, live, err, sink);
+	}
+}
+
 /* compile with the product's compiler, run with the product's interpreter; groups come back as EmuGroup records */
 extern "C" int emu_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, const uint8_t *pages, uint64_t nblocks,
                            EmuGroup *out, int cap, int *nout, int32_t *aggcol /* [GG_MAX_AGGS] */, int32_t *accsq /* [GGP_MAX_ACCS] */,
@@ -135,7 +160,13 @@ extern "C" int emu_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_expr
 	sink.P = &P; sink.npassed = 0; sink.cur = nullptr;
 	uint32_t err = 0;
 	uint64_t nscan = 0;
-	if (P.nullable) run_pages<true>(P, pages, nblocks, sink, err, nscan);
+	if (P.outer.rowwords > 0)
+	{
+		/* datum rows: `pages` is the row array, `nblocks` the row count */
+		if (P.nullable) run_rows<true>(P, (const uint64_t *) pages, nblocks, sink, err, nscan);
+		else run_rows<false>(P, (const uint64_t *) pages, nblocks, sink, err, nscan);
+	}
+	else if (P.nullable) run_pages<true>(P, pages, nblocks, sink, err, nscan);
 	else run_pages<false>(P, pages, nblocks, sink, err, nscan);
 	if (P.nkeys == 0 && sink.groups.empty())               /* plain aggregate over no rows: the one group exists (count 0) */
 	{

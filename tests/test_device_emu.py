@@ -52,12 +52,13 @@ def relation():
     return desc, po.build_pages(desc, rows, nulls)
 
 
-def run_emu(L, scan, agg, pool, pages, cap=4096):
+def run_emu(L, scan, agg, pool, pages, cap=4096, nrows=None):
+    """pages: heap pages (uint8), or with nrows the datum rows (uint64 [nrows, 1 + ncols]) of a GG_FMT_DATUMROWS descriptor"""
     out = (EmuGroup * cap)()
     n, sc, ps, err = C.c_int(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
     aggcol, accsq = (C.c_int32 * capi.GG_MAX_AGGS)(), (C.c_int32 * 16)()
     msg = C.create_string_buffer(256)
-    rc = L.emu_scanagg(C.byref(scan), C.byref(agg), C.byref(pool), pages.ctypes.data, pages.size // capi.GG_BLCKSZ, out, cap, C.byref(n),
+    rc = L.emu_scanagg(C.byref(scan), C.byref(agg), C.byref(pool), pages.ctypes.data, pages.size // capi.GG_BLCKSZ if nrows is None else nrows, out, cap, C.byref(n),
                        aggcol, accsq, C.byref(sc), C.byref(ps), C.byref(err), msg, 256)
     assert rc == 0, (rc, msg.value)
     return [out[i] for i in range(n.value)], list(aggcol), sc.value, ps.value, err.value
@@ -202,3 +203,37 @@ def test_reference_golden_plans_through_the_device_interpreter(emu):
     d, pg, scan, agg, pool, want = gp_hashagg_case()
     groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, pool, pg)
     assert err == 0 and {capi.unpack_str(g.key[0], 8).rstrip("\0"): f8i(g.sum[aggcol[0]]) for g in groups} == want
+
+
+def test_aocs_column_files_to_q1_with_product_source_only(emu):
+    """The whole AOCS path as far as a CPU can run it with the product's own source: column files (host loader: directory, tile
+    plan) -> the decode kernel's device function (tests/aocs_decode_harness.c) -> datum rows -> the product's compiler and
+    interpreter on the row descriptor.  Same groups, bit for bit, as the interpreter over the heap pages of the same rows."""
+    import test_aocs_decode as ad
+    from greengage_b200 import aocs, tpch
+    so = os.path.join(os.path.dirname(emu._name), "harness.so")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "aocs_decode_harness.c")])
+    H = C.CDLL(so)
+    H.harness_decode_rows.restype = C.c_uint32
+    H.harness_decode_rows.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int32, C.c_void_p]
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 40000, nsegs=2, seg=0)
+    pages, nb, nr = tpch.synth_generate(spec)
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
+    cols = [4, 5, 6, 7, 8, 9, 10]
+    files, nrows = aocs.synth_columns(spec, cols, nr)
+    rows, err = ad.host_decode(H, [desc.attrs[c] for c in cols], [files[c] for c in cols], 1024)
+    assert err == 0 and rows.shape == (nr, 8)
+    rdesc = capi.rows_tupdesc([desc.attrs[c].atttypid for c in cols], notnull=[1] * len(cols))
+    names = dict(quantity=1, extendedprice=2, discount=3, tax=4, returnflag=5, linestatus=6, shipdate=7)
+    scan_r, agg_r, pool_r = tpch.q1_plan(stage=capi.AGGSTAGE_NORMAL, desc=rdesc, cols=names)
+    got, aggcol_r, sc, ps, e1 = run_emu(emu, scan_r, agg_r, pool_r, np.ascontiguousarray(rows), nrows=nr)
+    scan_h, agg_h, pool_h = tpch.q1_plan(capi.TAB_LINEITEM_WIDE)
+    want, aggcol_h, hsc, hps, e2 = run_emu(emu, scan_h, agg_h, pool_h, pages)
+    assert e1 == 0 and e2 == 0 and (sc, ps) == (hsc, hps) == (nr, ps) and aggcol_r == aggcol_h
+    key = lambda g: (g.key[0], g.key[1])
+    for a, b in zip(sorted(got, key=key), sorted(want, key=key)):
+        assert key(a) == key(b) and a.count == b.count
+        assert [a.sum[j] for j in range(8)] == [b.sum[j] for j in range(8)] and [a.n[j] for j in range(8)] == [b.n[j] for j in range(8)]
+    # and that answer is the oracle's
+    owant, osc, ops = po.seqscan_agg(scan_h, agg_h, pool_h, pages)
+    check(want, aggcol_h, owant, agg_h)
