@@ -187,3 +187,26 @@ extern "C" int emu_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_expr
 	*scanned = nscan; *passed = sink.npassed; *errflags = err;
 	return GG_OK;
 }
+
+/* the device hashing and routing functions (gg_device.cuh), for the golden vectors the reference's own objects produced */
+extern "C" uint32_t emu_hash_uint32(uint32_t k) { return hash_uint32(k); }
+extern "C" uint32_t emu_hashint8(int64_t v) { return hashint8(v); }
+extern "C" uint32_t emu_hashfloat8(uint64_t bits) { return hashfloat8(bits); }
+extern "C" uint32_t emu_hash_any_le8(uint64_t v, int len) { return hash_any_le8(v, len); }
+extern "C" int32_t emu_route(const int32_t *typids, const int64_t *vals, const int32_t *lens, const int32_t *isnull, int nkeys, int nsegs)
+{
+	uint32_t h = 0;
+	for (int i = 0; i < nkeys; i++)
+	{
+		uint32_t hk = 0;
+		switch (typids[i])
+		{
+			case GG_INT4OID: case GG_DATEOID: hk = hash_uint32((uint32_t) (int32_t) vals[i]); break;
+			case GG_INT8OID: case GG_TIMESTAMPOID: hk = hashint8(vals[i]); break;
+			case GG_FLOAT8OID: hk = hashfloat8((uint64_t) vals[i]); break;
+			default: hk = hash_any_le8((uint64_t) vals[i], lens[i]); break;       /* packed, blank-stripped strings */
+		}
+		h = cdbhash_add(h, hk, isnull[i] != 0);
+	}
+	return jump_consistent_hash((uint64_t) h, nsegs);
+}

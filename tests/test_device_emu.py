@@ -237,3 +237,48 @@ def test_aocs_column_files_to_q1_with_product_source_only(emu):
     # and that answer is the oracle's
     owant, osc, ops = po.seqscan_agg(scan_h, agg_h, pool_h, pages)
     check(want, aggcol_h, owant, agg_h)
+
+
+def test_device_hash_and_routing_functions_equal_the_references(emu):
+    """hash_uint32 / hashint8 / hashfloat8 / hash_any (<= 8 bytes) / cdbhash + jump_consistent_hash as written for the device
+    (gg_device.cuh), against tests/golden/hash_kat.json — computed by the reference's own hashfunc.o, varchar.o and cdbhash.o"""
+    from _util import golden
+    K = golden("hash_kat.json")
+    emu.emu_hash_uint32.restype = emu.emu_hashint8.restype = emu.emu_hashfloat8.restype = emu.emu_hash_any_le8.restype = C.c_uint32
+    emu.emu_hash_uint32.argtypes = [C.c_uint32]
+    emu.emu_hashint8.argtypes = [C.c_int64]
+    emu.emu_hashfloat8.argtypes = [C.c_uint64]
+    emu.emu_hash_any_le8.argtypes = [C.c_uint64, C.c_int]
+    emu.emu_route.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int]
+    for v, want in K["hash_uint32"]:
+        assert emu.emu_hash_uint32(v) == want
+    for v, want in K["hashint4"]:
+        assert emu.emu_hash_uint32(v & 0xFFFFFFFF) == want             # hashint4 = hash_uint32 of the value (hashfunc.c:46)
+    for v, want in K["hashint8"]:
+        assert emu.emu_hashint8(int(v)) == want
+    for bits, want in K["hashfloat8"]:
+        assert emu.emu_hashfloat8(int(bits) & 0xFFFFFFFFFFFFFFFF) == want
+    short = 0
+    for hexs, want in K["hash_any"]:
+        b = bytes.fromhex(hexs)
+        if len(b) <= 8:
+            assert emu.emu_hash_any_le8(int.from_bytes(b.ljust(8, b"\0"), "little"), len(b)) == want
+            short += 1
+    for hexs, want in K["hashbpchar"]:
+        b = bytes.fromhex(hexs).rstrip(b" ")                             # bcTruelen: the packed form is already stripped
+        if len(b) <= 8:
+            assert emu.emu_hash_any_le8(int.from_bytes(b.ljust(8, b"\0"), "little"), len(b)) == want
+            short += 1
+    assert short > 100
+    routed = 0
+    for r in K["route"]:
+        n = len(r["typ"])
+        if any(t in (capi.BPCHAROID, capi.VARCHAROID, capi.TEXTOID) and ln > 8 for t, ln in zip(r["typ"], r["len"])):
+            continue
+        t = (C.c_int32 * n)(*r["typ"])
+        v = (C.c_int64 * n)(*[int(x) for x in r["val"]])
+        ln = (C.c_int32 * n)(*r["len"])
+        nn = (C.c_int32 * n)(*r["null"])
+        assert emu.emu_route(t, v, ln, nn, n, r["nsegs"]) == r["seg"], r
+        routed += 1
+    assert routed > 1000
