@@ -210,3 +210,54 @@ extern "C" int32_t emu_route(const int32_t *typids, const int64_t *vals, const i
 	}
 	return jump_consistent_hash((uint64_t) h, nsegs);
 }
+
+/* The device's attribute walk over ONE tuple (walk_tuple, slot_deform_tuple's restatement for the GPU): every attribute of
+ * the descriptor is referenced through a count(col) plan so that the compiled side description covers them all.
+ * values[a]: the Datum of a fixed-width attribute as the interpreter's loads read it (LD_C8 / LD_C4), or for a varlena the
+ * offset of its header byte from the tuple start — the convention of tests/golden/heap_kat.json. */
+extern "C" int emu_walk(const gg_tupdesc *desc, const uint8_t *tuple, int len, int force_slow, int64_t *values, uint8_t *nulls, uint32_t *errflags)
+{
+	static gg_scan scan; static gg_agg agg; static gg_exprpool pool; static ggp_program P;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	char msg[256];
+	if (desc->natts < 1 || desc->natts > GG_MAX_AGGS) return GG_ERR_ARG;
+	memset(&scan, 0, sizeof scan); memset(&agg, 0, sizeof agg); memset(&pool, 0, sizeof pool);
+	scan.desc = *desc; scan.qual = -1;
+	for (int a = 0; a < desc->natts; a++)
+	{
+		gg_expr &e = pool.nodes[pool.nnodes];
+		e.kind = GG_E_VAR; e.varno = 0; e.varattno = (int16_t) (a + 1); e.rettype = desc->attrs[a].atttypid;
+		agg.aggs[a].aggfnoid = GG_AGG_COUNT_ANY; agg.aggs[a].arg = pool.nnodes++;
+	}
+	agg.numAggs = desc->natts;
+	int rc = ggp_compile_scanagg(&scan, &agg, &pool, &P, aggmap, msg, sizeof msg);
+	if (rc != GG_OK) return rc;
+	const uint32_t TUP = 64, OFFS = 40000;
+	memset(gg_emu_smem, 0xEE, 65536);
+	memcpy(gg_emu_smem + TUP, tuple, (size_t) len);
+	const bool hasnulls = (lds16(TUP + 20) & GG_HEAP_HASNULL) != 0;
+	const bool fast = !hasnulls && !force_slow;
+	TupleView tv;
+	uint32_t err = 0;
+	walk_tuple(P.outer, TUP, (uint32_t) len, fast, OFFS, 0, tv, err);
+	*errflags = err;
+	for (int a = 0; a < desc->natts; a++) { nulls[a] = 2; values[a] = 0; }       /* 2 = not referenced (cannot happen here) */
+	for (int s = 0; s < P.outer.ncols; s++)
+	{
+		const int a = P.outer.colatt[s];
+		nulls[a] = (uint8_t) ((tv.colnull >> s) & 1);
+		if (nulls[a]) continue;
+		const int cacheoff = P.outer.att[a].cacheoff;
+		const uint32_t off = (fast && cacheoff >= 0) ? (uint32_t) cacheoff : lds16(OFFS + (uint32_t) (s * 32) * 2);
+		const uint32_t addr = tv.tp + off;
+		switch (desc->attrs[a].attlen)
+		{
+			case 8: values[a] = (int64_t) lds64(addr); break;
+			case 4: values[a] = (int64_t) (int32_t) lds32(addr); break;
+			case 2: values[a] = (int64_t) (int16_t) lds16(addr); break;
+			case 1: values[a] = (int64_t) (int8_t) lds8(addr); break;
+			default: values[a] = (int64_t) (addr - TUP); break;
+		}
+	}
+	return GG_OK;
+}
