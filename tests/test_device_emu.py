@@ -314,3 +314,74 @@ def test_device_tuple_walk_equals_the_references_deform(emu):
                     assert int(v[i]) == want, (case["desc"], i, force_slow)
             checked += 1
     assert checked >= 300, checked
+
+
+def test_device_arithmetic_and_comparisons_equal_the_references(emu):
+    """float8pl / mi / mul / div with their overflow / underflow / division-by-zero ERRORs, float8 comparisons (NaN ordering,
+    signed zeros) and date-vs-timestamp comparisons with "date out of range", as the device interpreter computes them,
+    against tests/golden/float_kat.json — answers of the reference's own float.o / date.o.  Column-column, column-constant
+    and constant-column operand forms of every case (different op codes of the accumulator machine)."""
+    from _util import golden
+    K = golden("float_kat.json")
+    FN = {"pl": capi.F_FLOAT8PL, "mi": capi.F_FLOAT8MI, "mul": capi.F_FLOAT8MUL, "div": capi.F_FLOAT8DIV}
+    ERR = {0x01, 0x02, 0x04}
+    b2f = lambda x: float(np.int64(int(x)).view(np.float64))
+    f2b = lambda x: int(np.float64(x).view(np.int64))
+    d2 = make_desc([(capi.FLOAT8OID, 8, 'd', 1, 1), (capi.FLOAT8OID, 8, 'd', 1, 1)])
+
+    def operands(p, form, a, b):
+        x, y = p.var(1, capi.FLOAT8OID), p.var(2, capi.FLOAT8OID)
+        if form == 1:
+            y = p.const(capi.FLOAT8OID, 0.0); p.pool.nodes[y].constvalue = int(b)
+        elif form == 2:
+            x = p.const(capi.FLOAT8OID, 0.0); p.pool.nodes[x].constvalue = int(a)
+        return x, y
+
+    pages_cache = {}
+
+    def pages_of(a, b):
+        key = (a, b)
+        if key not in pages_cache:
+            pages_cache[key] = po.build_pages(d2, [[b2f(a), b2f(b)]])
+        return pages_cache[key]
+
+    n = 0
+    for fn, a, b, err, r, _msg in K["arith"][::4]:
+        for form in (0, 1, 2):
+            p = ExprPool()
+            x, y = operands(p, form, a, b)
+            agg = capi.make_agg(0, [], [(capi.AGG_MIN_FLOAT8, p.func(FN[fn], capi.FLOAT8OID, x, y))])
+            groups, aggcol, sc, ps, e = run_emu(emu, capi.make_scan(d2, -1), agg, p.pool, pages_of(a, b))
+            if err:
+                assert e & 0x07, (fn, b2f(a), b2f(b), form, hex(e))
+            else:
+                assert not (e & 0x07), (fn, b2f(a), b2f(b), form, hex(e))
+                got, want = groups[0].sum[aggcol[0]], b2f(r)
+                assert f2b(got) == int(r) or (got != got and want != want), (fn, b2f(a), b2f(b), form, got, want)
+            n += 1
+    for a, b, eq, lt, le, cmp3 in K["cmp"][::2]:
+        for fid, want in ((capi.F_FLOAT8EQ, eq), (capi.F_FLOAT8LT, lt), (capi.F_FLOAT8LE, le), (capi.F_FLOAT8NE, 1 - eq),
+                          (capi.F_FLOAT8GT, 1 - le), (capi.F_FLOAT8GE, 1 - lt)):
+            for form in (0, 1, 2):
+                p = ExprPool()
+                x, y = operands(p, form, a, b)
+                agg = capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)])
+                groups, aggcol, sc, ps, e = run_emu(emu, capi.make_scan(d2, p.func(fid, capi.BOOLOID, x, y)), agg, p.pool, pages_of(a, b))
+                assert e == 0 and ps == want, (fid, b2f(a), b2f(b), form, ps, want)
+                n += 1
+    dd = make_desc([(capi.DATEOID, 4, 'i', 1, 1)])
+    FD = [capi.F_DATE_LT_TIMESTAMP, capi.F_DATE_LE_TIMESTAMP, capi.F_DATE_EQ_TIMESTAMP, capi.F_DATE_GT_TIMESTAMP, capi.F_DATE_GE_TIMESTAMP,
+          capi.F_DATE_NE_TIMESTAMP]
+    dpages = {}
+    for op, d, ts, err, res in K["date_ts"][::3]:
+        if d not in dpages:
+            dpages[d] = po.build_pages(dd, [[d]])
+        p = ExprPool()
+        q = p.func(FD[op], capi.BOOLOID, p.var(1, capi.DATEOID), p.const(capi.TIMESTAMPOID, int(ts)))
+        groups, aggcol, sc, ps, e = run_emu(emu, capi.make_scan(dd, q), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool, dpages[d])
+        if err:
+            assert e & 0x80, (op, d, ts)
+        else:
+            assert e == 0 and ps == res, (op, d, ts, ps, res)
+        n += 1
+    assert n > 2500, n
