@@ -385,3 +385,52 @@ def test_device_arithmetic_and_comparisons_equal_the_references(emu):
             assert e == 0 and ps == res, (op, d, ts, ps, res)
         n += 1
     assert n > 2500, n
+
+
+def test_random_plans_over_datum_rows(emu):
+    """the same random plans compiled for the GG_FMT_DATUMROWS descriptor (what a receiving Motion and the AOCS decode
+    deliver: NULL-mask word + one 64-bit Datum per column, constant offsets) and run over the same rows in that format"""
+    rng = np.random.default_rng(78)
+    types = [capi.INT4OID, capi.INT4OID, capi.INT4OID, capi.FLOAT8OID, capi.FLOAT8OID, capi.BPCHAROID, capi.DATEOID, capi.INT8OID]
+    notnull = [1, 1, 0, 1, 0, 0, 1, 1]
+    hdesc = make_desc([(capi.INT4OID, 4, "i", 1, 1), (capi.INT4OID, 4, "i", 1, 1), (capi.INT4OID, 4, "i", 1, 0), (capi.FLOAT8OID, 8, "d", 1, 1),
+                       (capi.FLOAT8OID, 8, "d", 1, 0), (capi.BPCHAROID, -1, "i", 0, 0), (capi.DATEOID, 4, "i", 1, 1), (capi.INT8OID, 8, "d", 1, 1)])
+    rows, nulls = [], []
+    for _ in range(2500):
+        rows.append([int(rng.integers(0, 5)), int(rng.integers(-20, 20)), int(rng.integers(-5, 5)), float(rng.integers(-40, 40)) / 4,
+                     float(rng.choice([0.0, -0.0, 0.5, -1.25, 3.0, 1e-3, float(rng.integers(-9, 9))])), bytes([65 + int(rng.integers(0, 3))]) + b" ",
+                     int(rng.integers(-400, 400)), int(rng.integers(-10**9, 10**9))])
+        nulls.append([False, False, rng.random() < 0.15, False, rng.random() < 0.15, rng.random() < 0.1, False, False])
+    pages = po.build_pages(hdesc, rows, nulls)
+    dr = np.zeros((len(rows), 9), dtype=np.int64)
+    for i, (r, nl) in enumerate(zip(rows, nulls)):
+        mask = 0
+        for c, (v, isn) in enumerate(zip(r, nl)):
+            if isn:
+                mask |= 1 << c
+            elif types[c] == capi.FLOAT8OID:
+                dr[i, 1 + c] = np.float64(v).view(np.int64)
+            elif types[c] == capi.BPCHAROID:
+                dr[i, 1 + c] = capi.pack_str(v)[0]
+            else:
+                dr[i, 1 + c] = v
+        dr[i, 0] = mask
+    rdesc = capi.rows_tupdesc(types, notnull=notnull)
+    stats = {"equal": 0, "errors": 0}
+    for seed in range(200):
+        scan_h, agg, p = random_plan(hdesc, seed)
+        scan_r = capi.make_scan(rdesc, scan_h.qual)
+        try:
+            want, sc, ps = po.seqscan_agg(scan_h, agg, p.pool, pages)
+        except po.OracleError:
+            groups, aggcol, gsc, gps, err = run_emu(emu, scan_r, agg, p.pool, dr, nrows=len(rows))
+            assert err & ARITH
+            stats["errors"] += 1
+            continue
+        groups, aggcol, gsc, gps, err = run_emu(emu, scan_r, agg, p.pool, dr, nrows=len(rows))
+        if err & ARITH:
+            continue
+        assert (gsc, gps) == (sc, ps), seed
+        check(groups, aggcol, want, agg)
+        stats["equal"] += 1
+    assert stats["equal"] > 120 and stats["errors"] > 10, stats
