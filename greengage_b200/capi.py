@@ -84,7 +84,7 @@ class gg_scan(C.Structure):
 
 class gg_agg(C.Structure):
     _fields_ = [("aggstage", C.c_int32), ("numCols", C.c_int32), ("grpCol", C.c_int32 * GG_MAX_KEYS),
-                ("numAggs", C.c_int32), ("pad", C.c_int32), ("aggs", gg_aggref * GG_MAX_AGGS),
+                ("numAggs", C.c_int32), ("flags", C.c_int32), ("aggs", gg_aggref * GG_MAX_AGGS),
                 ("numGroups", C.c_int64)]
 
 
@@ -298,9 +298,13 @@ def make_scan(desc, qual=-1):
     return s
 
 
-def make_agg(stage, grpcols, aggs, num_groups=0):
+AGGF_DEVICE_FINAL = 1      # gg_plan.h GG_AGGF_DEVICE_FINAL
+
+
+def make_agg(stage, grpcols, aggs, num_groups=0, flags=0):
     a = gg_agg()
     a.aggstage = stage
+    a.flags = flags
     a.numGroups = num_groups
     a.numCols = len(grpcols)
     for i, g in enumerate(grpcols):

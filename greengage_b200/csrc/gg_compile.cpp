@@ -45,14 +45,6 @@ void fail(Ctx &c, const char *fmt, ...)
 	va_end(ap);
 }
 
-/* switches for measurements that are not validated yet: off unless the variable is set to something
- * other than "0"; with every switch off the compiler's output is what round 1 validated on the GPU */
-static bool experiment(const char *name)
-{
-	const char *v = getenv(name);
-	return v && v[0] && !(v[0] == '0' && !v[1]);
-}
-
 int loadtype_of(int32_t typid)
 {
 	switch (typid)
@@ -419,7 +411,11 @@ void gen_binary(Ctx &c, int lroot, int rroot, int k, int cc)
 		gen(c, lroot);
 		int t = alloc_temp(c);
 		store_temp(c, t);
+		/* ExecEvalAnd / ExecEvalOr (execQual.c:3321-3450) do not evaluate the second arm once the first has decided the
+		 * result: lanes where it has are not live while the arm runs, so what it would have raised is not raised */
+		if (logical) emit(c, k == K_AND ? GGP_GUARD_AND : GGP_GUARD_OR, t);
 		gen(c, rroot);
+		if (logical) emit(c, GGP_UNGUARD);
 		Operand to = { OPD_T, t };
 		emit_binop(c, k, cc, to, !commut);
 		c.temps_busy &= ~(1 << t);
@@ -508,6 +504,35 @@ ggp_op *gen_value(Ctx &c, int root)
 	return last_op(c, start);
 }
 
+/* A plan qual is an implicit-AND list of clauses that ExecQual walks until one is not true (execQual.c:6260-6310; the
+ * planner flattens every top-level AND, make_ands_implicit): one FILTER per clause.  A row that failed a clause is not
+ * live for the clauses behind it, so they raise nothing for it — what the reference does by never reaching them — and a
+ * specialised kernel lets such lanes skip nothing they need. */
+void gen_qual(Ctx &c, int qual)
+{
+	if (qual < 0) return;
+	const gg_exprpool *pool = c.pool;
+	ggp_program *prog = c.prog;
+	int stack[GG_MAX_EXPR_NODES], sp = 0, clauses[GG_MAX_EXPR_NODES], nc = 0, steps = 0;
+	stack[sp++] = qual;
+	while (sp > 0 && !c.failed)
+	{
+		const int r = stack[--sp];
+		const gg_expr &e = pool->nodes[r];
+		/* a pool is a DAG: AND nodes sharing children could be walked exponentially often — bounded, then refused */
+		if (++steps > 4 * GG_MAX_EXPR_NODES || nc >= GG_MAX_EXPR_NODES) { fail(c, "qual with too many clauses"); break; }
+		if (e.kind == GG_E_AND && sp + 2 <= GG_MAX_EXPR_NODES) { stack[sp++] = e.args[1]; stack[sp++] = e.args[0]; }   /* left clause first */
+		else clauses[nc++] = r;
+	}
+	for (int k = 0; k < nc && !c.failed; k++)
+	{
+		ggp_op *o = gen_value(c, clauses[k]);
+		if (c.failed) break;
+		if (o->flags & GGP_F_FILTER) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
+		o->flags |= GGP_F_FILTER;
+	}
+}
+
 }  // namespace
 
 /* grouping keys, GROUP and the aggregate arguments: the part of the row program that is the same for a
@@ -558,7 +583,7 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			case GG_AGG_SUM_FLOAT8: kind = GGP_ACC_F8SUM; break;
 			/* float8_accum also maintains sumX2, which float8_avg ignores (float.c:1982): only a PARTIAL stage,
 			 * whose transition state {N, sumX, sumX2} is shipped to another process, has to produce it */
-			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = (agg->aggstage == GG_AGGSTAGE_PARTIAL) && !experiment("GGB200_PARTIAL_NO_SUMSQ"); break;
+			case GG_AGG_AVG_FLOAT8: kind = GGP_ACC_F8SUM; sq = (agg->aggstage == GG_AGGSTAGE_PARTIAL) && !(agg->flags & GG_AGGF_DEVICE_FINAL); break;
 			case GG_AGG_MIN_FLOAT8: kind = GGP_ACC_F8MIN; break;
 			case GG_AGG_MAX_FLOAT8: kind = GGP_ACC_F8MAX; break;
 			case GG_AGG_SUM_INT4: kind = GGP_ACC_I8SUM; break;
@@ -735,35 +760,7 @@ int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpoo
 	init_side(&prog->outer, &scan->desc);
 
 	/* ---- scan qual ---- */
-	if (scan->qual >= 0 && experiment("GGB200_FLATTEN_QUAL"))
-	{
-		/* an implicit-AND qual is a list of clauses ExecQual walks until one is not true (execQual.c:6260-6310): one FILTER
-		 * per clause instead of three-valued ANDs feeding one FILTER, so lanes that already failed skip nothing they need
-		 * and a clause the reference would not have reached cannot raise */
-		int stack[GG_MAX_EXPR_NODES], sp = 0, clauses[GG_MAX_EXPR_NODES], nc = 0, steps = 0;
-		stack[sp++] = scan->qual;
-		while (sp > 0 && !c.failed)
-		{
-			const int r = stack[--sp];
-			const gg_expr &e = pool->nodes[r];
-			/* a pool is a DAG: AND nodes sharing children could be walked exponentially often — bounded, then refused */
-			if (++steps > 4 * GG_MAX_EXPR_NODES || nc >= GG_MAX_EXPR_NODES) { fail(c, "qual with too many clauses"); break; }
-			if (e.kind == GG_E_AND && sp + 2 <= GG_MAX_EXPR_NODES) { stack[sp++] = e.args[1]; stack[sp++] = e.args[0]; }   /* left clause first */
-			else clauses[nc++] = r;
-		}
-		for (int k = 0; k < nc && !c.failed; k++)
-		{
-			ggp_op *o = gen_value(c, clauses[k]);
-			if (c.failed) break;
-			if (o->flags & GGP_F_FILTER) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
-			o->flags |= GGP_F_FILTER;
-		}
-	}
-	else if (scan->qual >= 0)
-	{
-		ggp_op *o = gen_value(c, scan->qual);
-		if (!c.failed) o->flags |= GGP_F_FILTER;
-	}
+	gen_qual(c, scan->qual);
 	compile_agg_part(c, agg, aggmap);
 	if (c.failed) return GG_ERR_UNSUPPORTED;
 	return GG_OK;
@@ -841,11 +838,7 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	if (!check_desc(c, &outer->desc) || !check_desc(c, &inner->desc)) return GG_ERR_UNSUPPORTED;
 	init_side(&jp->probe.outer, &outer->desc);
 	init_side(&innerside, &inner->desc);
-	if (outer->qual >= 0)
-	{
-		ggp_op *o = gen_value(c, outer->qual);
-		if (!c.failed) o->flags |= GGP_F_FILTER;
-	}
+	gen_qual(c, outer->qual);
 	for (int k = 0; k < hj->nkeys && !c.failed; k++)
 	{
 		int kt = join_keytype(pool->nodes[hj->outerkey[k]].rettype);
@@ -862,6 +855,8 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	jp->probe_pc = jp->probe.ncode;
 	if (hj->joinqual >= 0 && !c.failed)
 	{
+		/* one FILTER for the whole join qual: an ANTI join evaluates it on a match without emitting (the sink takes the
+		 * lane out after the FILTER), so clauses cannot be separate FILTERs here; AND arms are guarded all the same */
 		ggp_op *o = gen_value(c, hj->joinqual);
 		if (!c.failed) o->flags |= GGP_F_FILTER;
 	}
@@ -882,11 +877,7 @@ int ggp_compile_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjo
 	b.idesc = nullptr;
 	b.inner_as_outer = true;
 	init_side(&jp->build.outer, &inner->desc);
-	if (inner->qual >= 0 && !b.failed)
-	{
-		ggp_op *o = gen_value(b, inner->qual);
-		if (!b.failed) o->flags |= GGP_F_FILTER;
-	}
+	if (!b.failed) gen_qual(b, inner->qual);
 	for (int k = 0; k < hj->nkeys && !b.failed; k++)
 	{
 		ggp_op *o = gen_value(b, hj->innerkey[k]);
@@ -937,11 +928,7 @@ int ggp_compile_motion(const gg_scan *scan, const gg_exprpool *pool, const int32
 	}
 	if (!check_desc(c, &scan->desc)) return GG_ERR_UNSUPPORTED;
 	init_side(&prog->outer, &scan->desc);
-	if (scan->qual >= 0)
-	{
-		ggp_op *o = gen_value(c, scan->qual);
-		if (!c.failed) o->flags |= GGP_F_FILTER;
-	}
+	gen_qual(c, scan->qual);
 	for (int k = 0; k < nkeys && !c.failed; k++)
 	{
 		switch (pool->nodes[hashkeys[k]].rettype)
@@ -984,7 +971,7 @@ int ggp_disasm(const ggp_program *p, char *buf, int cap)
 		"ADD_C", "ADD_K", "ADD_T", "SUB_C", "SUB_K", "SUB_T", "RSUB_C", "RSUB_K", "RSUB_T", "MUL_C", "MUL_K", "MUL_T",
 		"DIV_C", "DIV_K", "DIV_T", "RDIV_C", "RDIV_K", "RDIV_T", "CMPF_C", "CMPF_K", "CMPF_T",
 		"CMPI_C4", "CMPI_C8", "CMPI_K", "CMPI_T", "CMPS_K", "CMPS_T", "DATE2TS", "I2F8", "AND_T", "OR_T",
-		"NOT", "ISNULL", "ISNOTNULL", "NOP" };
+		"NOT", "ISNULL", "ISNOTNULL", "NOP", "GUARD_AND", "GUARD_OR", "UNGUARD" };
 	int n = 0;
 	for (int i = 0; i < p->ncode && n < cap - 96; i++)
 	{

@@ -353,10 +353,11 @@ struct EvalCtx {
 struct MachState {
 	uint64_t acc, t0, t1, t2, t3;
 	uint32_t tnull;
+	uint32_t livestk;       /* `live` of the enclosing AND / OR arms (GGP_GUARD_*), innermost in bit 0 */
 	bool accnull;
 	bool live;              /* this lane carries a row that still counts; dead lanes keep executing (the op
 	                         * stream is warp-uniform) but raise no errors and produce no effects */
-	__device__ __forceinline__ void reset(bool l) { acc = t0 = t1 = t2 = t3 = 0; tnull = 0; accnull = false; live = l; }
+	__device__ __forceinline__ void reset(bool l) { acc = t0 = t1 = t2 = t3 = 0; tnull = 0; livestk = 0; accnull = false; live = l; }
 };
 
 /* One op of the accumulator machine, including its post-actions.  `o` is passed by value: on the
@@ -481,6 +482,16 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 			}
 			break;
 		}
+		case GGP_GUARD_AND:
+		case GGP_GUARD_OR:
+		{
+			/* the arm that follows is reached only if temp[idx] has not decided the result (execQual.c:3385,3455) */
+			const bool decided = !GG_TNULL(o.idx) && ((GG_TEMP(o.idx) != 0) == (op == GGP_GUARD_OR));
+			M.livestk = (M.livestk << 1) | (M.live ? 1u : 0u);
+			M.live = M.live && !decided;
+			break;
+		}
+		case GGP_UNGUARD: M.live = (M.livestk & 1u) != 0; M.livestk >>= 1; break;
 		case GGP_NOT: M.acc = (M.acc == 0); break;
 		case GGP_ISNULL: M.acc = M.accnull; M.accnull = false; break;
 		case GGP_ISNOTNULL: M.acc = !M.accnull; M.accnull = false; break;

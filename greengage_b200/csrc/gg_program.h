@@ -54,6 +54,12 @@ enum ggp_opcode {
 	GGP_AND_T, GGP_OR_T,                        /* 3-valued (execQual.c:3404,3455) */
 	GGP_NOT, GGP_ISNULL, GGP_ISNOTNULL,
 	GGP_NOP,                                    /* carries post-actions only */
+	/* short-circuit evaluation (ExecEvalAnd / ExecEvalOr, execQual.c:3321-3450): the second arm of AND / OR is not
+	 * evaluated when the first decides the result, so it cannot raise.  The op stream stays warp-uniform: the arm still
+	 * runs, but on lanes where the reference would have skipped it the lane is not `live`, and dead lanes raise nothing.
+	 * GUARD pushes `live` and clears it where temp[idx] already decides (AND: non-NULL FALSE; OR: non-NULL TRUE);
+	 * UNGUARD pops. */
+	GGP_GUARD_AND, GGP_GUARD_OR, GGP_UNGUARD,
 	GGP_NOPS
 };
 

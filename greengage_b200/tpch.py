@@ -21,7 +21,7 @@ LI_WIDE_COLS = dict(orderkey=1, quantity=5, extendedprice=6, discount=7, tax=8, 
 LI_NARROW_COLS = dict(orderkey=1, quantity=2, extendedprice=3, discount=4, tax=5, returnflag=6, linestatus=7, shipdate=8)
 
 
-def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_days=90, desc=None, cols=None):
+def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_days=90, desc=None, cols=None, flags=0):
     """Q1: scan + filter + group by (l_returnflag, l_linestatus) + 4 sums, 3 avgs, count(*).
     `desc` / `cols` override the relation layout (e.g. datum rows a Motion delivered)."""
     cols = cols or (LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS)
@@ -43,7 +43,7 @@ def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_d
     scan = capi.make_scan(desc, qual)
     agg = capi.make_agg(stage, [flag, status], [
         (AGG_SUM_FLOAT8, qty), (AGG_SUM_FLOAT8, price), (AGG_SUM_FLOAT8, disc_price), (AGG_SUM_FLOAT8, charge),
-        (AGG_AVG_FLOAT8, qty), (AGG_AVG_FLOAT8, price), (AGG_AVG_FLOAT8, disc), (AGG_COUNT_STAR, -1)])
+        (AGG_AVG_FLOAT8, qty), (AGG_AVG_FLOAT8, price), (AGG_AVG_FLOAT8, disc), (AGG_COUNT_STAR, -1)], flags=flags)
     return scan, agg, p.pool
 
 

@@ -221,12 +221,18 @@ typedef struct gg_scan {            /* SeqScan + its qual (nodeSeqscan.c, execSc
 	int32_t    pad;
 } gg_scan;
 
+/* gg_agg.flags.  DEVICE_FINAL (PARTIAL stage only): the rows of this stage are combined by this engine's own FINAL stage
+ * (gg_agg_final / the device-resident Motion), which like float8_avg never reads avg's sumX2 (float.c:1982-1996): the
+ * stage then does not compute it and ships 0.  Leave it clear when a CPU FINAL stage consumes the rows — the reference's
+ * float8_combine adds the sumX2 fields and its CHECKFLOATVAL sees them (float.c:1842-1876). */
+#define GG_AGGF_DEVICE_FINAL 1
+
 typedef struct gg_agg {             /* Agg (AGG_HASHED or AGG_PLAIN when numCols==0), nodeAgg.c */
 	int32_t   aggstage;
 	int32_t   numCols;
 	int32_t   grpCol[GG_MAX_KEYS];      /* expr roots of the grouping columns (Vars of the input) */
 	int32_t   numAggs;
-	int32_t   pad;
+	int32_t   flags;                    /* GG_AGGF_* */
 	gg_aggref aggs[GG_MAX_AGGS];
 	int64_t   numGroups;                /* planner's estimate (Agg.numGroups, plannodes.h); 0 = unknown.
 	                                     * Sizes the hash table as in create_agg_hash_table (execHHashagg.c:810) */

@@ -148,13 +148,13 @@ def test_generated_kernel_sources_compile_for_sm100a(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
 
 
-def test_q6_plan_compiles_to_one_filter_and_one_sum():
-    """The Q6 plan the golden tests run (tests/_util.tpch_q6_plan): the five range predicates are three-valued ANDs feeding
-    one FILTER in front of the single accumulate, and the plan has no group key (private-accumulator kernel)."""
+def test_q6_plan_compiles_to_five_filters_and_one_sum():
+    """The Q6 plan the golden tests run (tests/_util.tpch_q6_plan): the five range predicates are the clauses of an
+    implicit-AND qual, one FILTER each, in front of the single accumulate; no group key (private-accumulator kernel)."""
     from _util import lineitem_fixture_pages, tpch_q6_plan
     desc, _, _ = lineitem_fixture_pages()
     lines = disasm(*tpch_q6_plan(desc))
-    assert sum(1 for ln in lines if "FILTER" in ln) == 1 and sum(1 for ln in lines if "AND_T" in ln) == 4
+    assert sum(1 for ln in lines if "FILTER" in ln) == 5 and sum(1 for ln in lines if "AND_T" in ln) == 0
     assert sum(1 for ln in lines if "CMPF_K" in ln) == 3 and sum(1 for ln in lines if "CMPI_K" in ln) == 2
     assert sum(1 for ln in lines if "OUT" in ln and "OUTSQ" not in ln) == 1 and not any("KEY" in ln for ln in lines)
     assert lines[-1].split()[1] == "END"
@@ -219,31 +219,38 @@ def test_malformed_plans_are_error_codes_not_crashes():
     assert e.value.code == -10 and "inner join key" in str(e.value)
 
 
-def test_experiment_switches_change_only_what_they_say(monkeypatch):
-    """Two measurements queued for the next round sit behind environment switches that are off by default
-    (scripts/fuzz/compiler_compare.py shows the default output byte-identical to the compiler round 1 validated on the GPU):
-    one FILTER per clause of an implicit-AND qual, and a PARTIAL stage without avg's sumX2 columns."""
+def test_qual_clauses_are_separate_filters_and_and_or_arms_are_guarded():
+    """An implicit-AND qual compiles to one FILTER per clause (ExecQual's list walk, execQual.c:6260-6310); a nested AND / OR
+    keeps its three-valued combinator but the second arm runs under a GUARD (ExecEvalAnd / ExecEvalOr stop at the deciding
+    arm, execQual.c:3385,3455)."""
     from _util import lineitem_fixture_pages, tpch_q6_plan
     desc, _, _ = lineitem_fixture_pages()
-    base = disasm(*tpch_q6_plan(desc))
-    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
     flat = disasm(*tpch_q6_plan(desc))
-    assert sum(1 for ln in flat if "FILTER" in ln) == 5 and not any("AND_T" in ln for ln in flat)
-    assert len(flat) < len(base)
-    assert [ln.split()[1] for ln in flat if "OUT" in ln] == [ln.split()[1] for ln in base if "OUT" in ln]
-    assert disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE)) is not None          # a single-clause qual is unchanged in shape
-    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "0")
-    assert disasm(*tpch_q6_plan(desc)) == base
+    assert sum(1 for ln in flat if "FILTER" in ln) == 5 and not any("AND_T" in ln or "GUARD" in ln for ln in flat)
+    assert sum(1 for ln in disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE)) if "FILTER" in ln) == 1
+    d = make_desc([(capi.FLOAT8OID, 8, 'd', 1), (capi.FLOAT8OID, 8, 'd', 1)])
+    p = ExprPool()
+    a, b = p.var(1, capi.FLOAT8OID), p.var(2, capi.FLOAT8OID)
+    nz = p.func(capi.F_FLOAT8NE, capi.BOOLOID, b, p.const(capi.FLOAT8OID, 0.0))
+    gt = p.func(capi.F_FLOAT8GT, capi.BOOLOID, p.func(capi.F_FLOAT8DIV, capi.FLOAT8OID, a, b), p.const(capi.FLOAT8OID, 1.0))
+    inner = p.boolop(capi.E_OR, p.boolop(capi.E_NOT, nz), gt)            # NOT (b <> 0) OR a / b > 1
+    lines = disasm(capi.make_scan(d, inner), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool)
+    ops = [ln.split()[1] for ln in lines]
+    assert ops.count("GUARD_OR") == 1 and ops.count("UNGUARD") == 1 and ops.count("OR_T") == 1
+    assert ops.index("GUARD_OR") < ops.index("DIV_C") < ops.index("UNGUARD") < ops.index("OR_T")
+
+
+def test_partial_stage_ships_sumsq_unless_this_engine_combines_it():
+    """avg's transition state is {N, sumX, sumX2} (float8_accum, float.c:1878); float8_avg never reads sumX2, so a PARTIAL
+    stage whose rows go to this engine's own FINAL stage (GG_AGGF_DEVICE_FINAL) is the one-stage program"""
     part = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
-    monkeypatch.setenv("GGB200_PARTIAL_NO_SUMSQ", "1")
-    nosq = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL))
+    nosq = disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL, flags=capi.AGGF_DEVICE_FINAL))
     assert sum(1 for ln in part if "OUTSQ" in ln) == 3 and not any("OUTSQ" in ln for ln in nosq)
-    assert nosq == disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL))   # the program is then the one-stage plan's
+    assert nosq == disasm(*tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_NORMAL))
 
 
-def test_flattening_a_shared_and_chain_is_bounded(monkeypatch):
+def test_flattening_a_shared_and_chain_is_bounded():
     """a pool is a DAG: and(x, x) nested 60 deep would be 2^60 clauses if walked as a tree"""
-    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
     desc = make_desc([(capi.INT4OID, 4, 'i', 1)])
     p = ExprPool()
     q = p.func(capi.F_INT4GT, capi.BOOLOID, p.var(1, capi.INT4OID), p.const(capi.INT4OID, 0))

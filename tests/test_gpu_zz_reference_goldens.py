@@ -95,26 +95,22 @@ def test_gp_hashagg_text_key_answer_is_the_references(eng):
     assert {capi.unpack_str(r.key[0], r.keylen[0]): r.agg[0].i for r in rows} == want
 
 
-@pytest.mark.xfail(reason="known deviation (DESIGN.md §8): AND/OR evaluate both arms on the device, so a division by zero in "
-                          "the arm ExecEvalAnd/ExecEvalOr would have skipped fails the query", strict=False)
 def test_and_or_skip_the_arm_that_would_raise(eng):
+    """ExecEvalAnd / ExecEvalOr stop at the deciding arm (execQual.c:3385,3455): a division by zero in the arm they skip is
+    not an error; every kernel variant (specialised, interpreter private / transposed)"""
     from test_gpu_scanagg import gpu_scanagg
     from test_oracle_float import short_circuit_case
     desc, pages, plans = short_circuit_case()
     for scan, agg, pool, want in plans:
-        rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pages)
-        assert (sc, ps, rows[0].agg[0].i) == (5, want, want)
+        for variant in (None, "interp-priv", "interp-tr"):
+            rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pages, variant)
+            assert (sc, ps, rows[0].agg[0].i) == (5, want, want)
 
 
-# ---- AOCS column files -> datum rows on the device (csrc/gg_aocs.cu).  The kernel was written after round 1's last GPU
-# minute: its device function is checked on the CPU (tests/test_aocs_decode.py runs the same source through gcc against the
-# reference-written files), its first run on hardware is the round-end run of this file.  Non-strict xfail keeps an
-# unvalidated launch path from turning the validated suite red; an XPASS here is the expected outcome.
-AOCS_UNVALIDATED = pytest.mark.xfail(reason="gg_aocs_decode_rows has not run on hardware yet (CPU build of the device "
-                                            "function is green in tests/test_aocs_decode.py)", strict=False)
+# ---- AOCS column files -> datum rows on the device (csrc/gg_aocs.cu); the same device function runs through gcc against the
+# reference-written files in tests/test_aocs_decode.py
 
 
-@AOCS_UNVALIDATED
 def test_aocs_columns_decode_to_the_rows_the_oracle_reads(eng):
     import numpy as np
     from greengage_b200 import aocs, tpch
@@ -144,7 +140,6 @@ def test_aocs_columns_decode_to_the_rows_the_oracle_reads(eng):
         assert np.array_equal(rows[:, 1 + i], want), c
 
 
-@AOCS_UNVALIDATED
 def test_aocs_q1_equals_the_heap_answer_and_the_references_golden(eng):
     from _util import assert_aggrows_match, golden, lineitem_fixture_pages
     from greengage_b200 import aocs, tpch
@@ -187,17 +182,10 @@ def test_aocs_q1_equals_the_heap_answer_and_the_references_golden(eng):
     _check_against_golden(got)
 
 
-# ---- the two compiler switches queued for measurement, off by default; same non-strict xfail rule as above
-SWITCH_UNVALIDATED = pytest.mark.xfail(reason="experiment switch (off by default) that has not run on hardware yet; CPU side: "
-                                              "tests/test_compile.py::test_experiment_switches_change_only_what_they_say", strict=False)
-
-
-@SWITCH_UNVALIDATED
-def test_flattened_qual_gives_the_references_q6_revenue(eng, monkeypatch):
+def test_flattened_qual_gives_the_references_q6_revenue(eng):
     from _util import Q6_GOLDEN_REVENUE, lineitem_fixture_pages, tpch_q6_plan
     from oracle import pyoracle as po
     from test_gpu_scanagg import gpu_scanagg
-    monkeypatch.setenv("GGB200_FLATTEN_QUAL", "1")
     desc, pages, n = lineitem_fixture_pages()
     scan, agg, pool = tpch_q6_plan(desc)
     want, sc, ps = po.seqscan_agg(scan, agg, pool, pages)
@@ -213,17 +201,16 @@ def test_flattened_qual_gives_the_references_q6_revenue(eng, monkeypatch):
     assert (sc2, ps2, rows[0].agg[0].i) == (5, want2, want2)
 
 
-@SWITCH_UNVALIDATED
-def test_partial_stage_without_sumsq_gives_the_references_q1(eng, monkeypatch):
+def test_partial_stage_without_sumsq_gives_the_references_q1(eng):
     from _util import golden, lineitem_fixture_pages
     from greengage_b200 import tpch
     from greengage_b200.engine import agg_final
     from test_gpu_scanagg import gpu_scanagg
     from test_oracle_q1_golden import _check_against_golden
-    monkeypatch.setenv("GGB200_PARTIAL_NO_SUMSQ", "1")
     desc, pages, n = lineitem_fixture_pages()
     exp = golden("q1_expected.json")
-    scan, part, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL, interval_days=exp["interval_days"], desc=desc)
+    scan, part, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL, interval_days=exp["interval_days"], desc=desc,
+                                    flags=capi.AGGF_DEVICE_FINAL)
     nb = pages.size // capi.GG_BLCKSZ
     parts = []
     for lo, hi in ((0, nb // 2), (nb // 2, nb)):              # two "segments"
