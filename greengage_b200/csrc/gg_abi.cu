@@ -64,6 +64,7 @@ const char *gg_strerror(int code)
 		case GG_ERR_BADPAGE: return "corrupted page";
 		case GG_ERR_ARG: return "bad argument";
 		case GG_ERR_DATE_RANGE: return "date out of range for timestamp";
+		case GG_ERR_PEER: return "another segment reported an error";
 	}
 	return "unknown error";
 }
@@ -106,6 +107,8 @@ void gg_engine_free(gg_engine *e)
 	cudaStreamSynchronize(e->copy_stream);
 	cudaFree(e->final_scratch);
 	cudaFree(e->sort_scratch);
+	for (void *m : e->groups_pool) cudaFree(m);
+	cudaFreeHost(e->groups_mirror);
 	cudaEventDestroy(e->ev_start);
 	cudaEventDestroy(e->ev_stop);
 	cudaStreamDestroy(e->stream);

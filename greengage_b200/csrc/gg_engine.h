@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "gg_program.h"
 #include "../../include/ggb200.h"
 
@@ -22,6 +23,8 @@ struct gg_engine {
 	size_t final_cap = 0;                /* records it holds */
 	void *sort_scratch = nullptr;        /* gg_sort_*: key/value ping-pong buffers, histograms; kept across calls */
 	size_t sort_scratch_bytes = 0;
+	std::vector<void *> groups_pool;     /* gg_groups buffers of the common size, recycled (gg_scanagg.cu) */
+	void *groups_mirror = nullptr;       /* pinned: status + records of one gg_groups_fetch */
 };
 
 struct gg_relation {

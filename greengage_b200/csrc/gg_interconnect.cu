@@ -1,0 +1,518 @@
+/*
+ * gg_interconnect.cu — the Motion layer of the B200 segment engine in C over NCCL (include/ggb200.h gg_ic_*).
+ *
+ * Replaces, for GPU segments, the UDP interconnect under ExecMotion:
+ *     SetupInterconnect / TeardownInterconnect            cdb/motion/ic_common.c:522,560
+ *     ChunkTransportState vtable (SendChunk, RecvTupleChunkFrom[Any], doSendStopMessage, SendEos)
+ *                                                          cdb/cdbinterconnect.h:500-533
+ *     SendTuple / RecvTupleFrom / SendEndOfStream          cdb/motion/cdbmotion.c:434,559,532
+ *     ic_udpifc.c (reliable datagram streams, acks, retransmission)   — nothing of it remains
+ * One communicator per query, NCCL rank = contentid (segment), peers over NVLink / NVSwitch.  What moves is not tuple
+ * chunks but whole device-resident batches:
+ *     group records   the handful of partial-aggregate states a slice emits (ggp_grec): ONE all-gather of fixed-size
+ *                     blocks; every receiver keeps the records cdbhash routes to it (Redistribute), the root keeps all
+ *                     (Gather), everybody keeps all (Broadcast).  Every block carries its sender's status word, so an
+ *                     ERROR on one segment reaches all of them with the data — the reference's error / stop propagation
+ *                     (cdbmotion.c:342 SendStopMessage, ic_udpifc.c:5798) — and no rank can be left waiting in a
+ *                     collective another rank never enters.
+ *     datum rows      what gg_motion_partition wrote per destination: a count exchange (all-gather of the counts) and
+ *                     grouped ncclSend / ncclRecv straight out of the sender's regions into the receiver's row buffer.
+ *     host rows       the executor's generic row batches (GgRowBatch), staged through device buffers.
+ * End of stream is the completion of the collective.  NCCL is dlopen'ed (libnccl.so.2): no link-time dependency.
+ */
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "gg_pipeline.h"
+#include "gg_groups.h"
+
+using namespace ggd;
+
+/* ---------------- NCCL through dlopen ---------------- */
+namespace {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0, ncclInProgress_ = 7 };
+enum { ncclUint8_ = 1, ncclUint64_ = 5 };
+
+struct Nccl {
+	void *h = nullptr;
+	int (*GetVersion)(int *) = nullptr;
+	int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*CommAbort)(ncclComm_t) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)(void) = nullptr;
+	int (*GroupEnd)(void) = nullptr;
+	bool ok = false;
+	char why[256] = "";
+};
+
+Nccl &nccl()
+{
+	static Nccl n;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char *env = getenv("GGB200_NCCL_LIB");
+		const char *names[] = { env, "libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2" };
+		for (const char *nm : names)
+			if (nm && nm[0] && (n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+		if (!n.h) { snprintf(n.why, sizeof n.why, "libnccl.so.2 not found (%s)", dlerror()); return; }
+#define LOADSYM(F) *(void **) (&n.F) = dlsym(n.h, "nccl" #F); if (!n.F) { snprintf(n.why, sizeof n.why, "nccl" #F " missing"); return; }
+		LOADSYM(GetVersion) LOADSYM(GetUniqueId) LOADSYM(CommInitRank) LOADSYM(CommDestroy) LOADSYM(CommAbort)
+		LOADSYM(GetErrorString) LOADSYM(AllGather) LOADSYM(Send) LOADSYM(Recv) LOADSYM(GroupStart) LOADSYM(GroupEnd)
+#undef LOADSYM
+		n.ok = true;
+	});
+	return n;
+}
+
+int nccl_fail(int rc, const char *what)
+{
+	gg_set_error("NCCL error %d (%s) in %s", rc, nccl().GetErrorString ? nccl().GetErrorString(rc) : "?", what);
+	return GG_ERR_CUDA;
+}
+#define GG_NCCL(call) do { int _r = (call); if (_r != ncclSuccess_) return nccl_fail(_r, #call); } while (0)
+
+}  // namespace
+
+/* what one segment contributes to a Motion of group records */
+struct GroupBlock {
+	uint32_t n;                 /* records this segment sends (may exceed GG_IC_GROUP_CAP: then none travel and every receiver sees it) */
+	uint32_t err;               /* GGP_EF_* of the sending pipeline */
+	unsigned long long counters[2];
+	ggp_grec recs[GG_IC_GROUP_CAP];
+};
+
+struct gg_interconnect {
+	gg_engine *eng = nullptr;
+	ncclComm_t comm = nullptr;       /* nullptr: one segment, loopback */
+	int nsegs = 1, seg = 0;
+	GroupBlock *d_send = nullptr;    /* [1] */
+	GroupBlock *d_all = nullptr;     /* [nsegs] */
+	unsigned long long *d_counts = nullptr;   /* [nsegs] mine, [nsegs * nsegs] everybody's */
+	unsigned long long *h_counts = nullptr;   /* pinned mirror of the matrix */
+	void *stage = nullptr;           /* host-row exchange: device staging, grown on demand */
+	size_t stage_bytes = 0;
+	uint64_t ncollectives = 0;
+};
+
+/* ---------------- kernels ---------------- */
+
+/* pipeline result -> the block that travels */
+__global__ void gg_ic_pack_groups_kernel(const ggp_grec *recs, const int *d_n, const gg_groupstatus *st, int sparse, int cap, GroupBlock *dst)
+{
+	__shared__ int s_n;
+	if (threadIdx.x == 0)
+	{
+		int n = 0;
+		if (sparse) { for (int i = 0; i < cap; i++) n += recs[i].valid ? 1 : 0; }
+		else n = *d_n;
+		s_n = n;
+		dst->n = (uint32_t) n;
+		dst->err = st->err | (n > GG_IC_GROUP_CAP ? GGP_EF_GROUP_OVERFLOW : 0u);
+		dst->counters[0] = st->counters[0];
+		dst->counters[1] = st->counters[1];
+	}
+	__syncthreads();
+	if (s_n > GG_IC_GROUP_CAP) return;
+	/* copy word-wise; a sparse source is compacted in slot order (deterministic) */
+	const int W = (int) (sizeof(ggp_grec) / 8);
+	if (!sparse)
+	{
+		for (int i = threadIdx.x; i < s_n * W; i += blockDim.x)
+			((unsigned long long *) dst->recs)[i] = ((const unsigned long long *) recs)[i];
+	}
+	else if (threadIdx.x < 32)
+	{
+		int at = 0;
+		for (int i = 0; i < cap; i++)
+		{
+			if (!recs[i].valid) continue;
+			for (int w = threadIdx.x; w < W; w += 32)
+				((unsigned long long *) &dst->recs[at])[w] = ((const unsigned long long *) &recs[i])[w];
+			at++;
+		}
+	}
+}
+
+/* evalHashKey + cdbhash + cdbhashreduce over a group record's keys (nodeMotion.c:1481, cdbhash.c:191-287) */
+__device__ __forceinline__ int route_group(const ggp_grec &r, int nhash, const int *hashcol, const int *hashtype, int nsegs)
+{
+	uint32_t h = 0;
+	for (int k = 0; k < nhash; k++)
+	{
+		const int c = hashcol[k];
+		const bool isnull = (r.keynull >> c) & 1;
+		const uint64_t v = r.key[c];
+		uint32_t hk = 0;
+		if (!isnull)
+		{
+			const int t = hashtype[k];
+			if (t == GGP_HT_INT4) hk = hash_uint32((uint32_t) v);
+			else if (t == GGP_HT_INT8) hk = hashint8((int64_t) v);
+			else if (t == GGP_HT_FLOAT8) hk = hashfloat8(v);
+			else if (t == GGP_HT_BOOL) hk = hash_uint32((uint32_t) (int32_t) (int8_t) v);
+			else
+			{
+				int len = 0;
+				while (len < 8 && ((v >> (8 * len)) & 0xff)) len++;
+				hk = hash_any_le8(v, len);
+			}
+		}
+		h = cdbhash_add(h, hk, isnull);
+	}
+	return jump_consistent_hash((uint64_t) h, nsegs);
+}
+
+struct RouteSpec { int nhash; int hashcol[GG_MAX_KEYS]; int hashtype[GG_MAX_KEYS]; };
+
+/* receiving side: out = [nsegs][GG_IC_GROUP_CAP] records, valid where this segment keeps the record */
+__global__ void gg_ic_route_groups_kernel(const GroupBlock *all, int nsegs, int myseg, int motion, int root, RouteSpec spec,
+                                          ggp_grec *out, gg_groupstatus *st)
+{
+	const int W = (int) (sizeof(ggp_grec) / 8);
+	if (threadIdx.x == 0)
+	{
+		/* every sender's ERROR flags reach every receiver; the row counters travel once: a Gather adds them up at the root,
+		 * any other Motion passes this segment's own through */
+		uint32_t e = 0;
+		unsigned long long c0 = 0, c1 = 0;
+		for (int r = 0; r < nsegs; r++)
+		{
+			e |= all[r].err;
+			if (motion == GG_IC_MOTION_GATHER ? myseg == root : r == myseg) { c0 += all[r].counters[0]; c1 += all[r].counters[1]; }
+		}
+		st->err = e; st->counters[0] = c0; st->counters[1] = c1; st->n = 0;
+	}
+	for (int i = threadIdx.x; i < nsegs * GG_IC_GROUP_CAP; i += blockDim.x)
+	{
+		const int r = i / GG_IC_GROUP_CAP, j = i % GG_IC_GROUP_CAP;
+		bool keep = (uint32_t) j < all[r].n && all[r].n <= GG_IC_GROUP_CAP;
+		if (keep)
+		{
+			if (motion == GG_IC_MOTION_HASH) keep = route_group(all[r].recs[j], spec.nhash, spec.hashcol, spec.hashtype, nsegs) == myseg;
+			else if (motion == GG_IC_MOTION_GATHER) keep = myseg == root;
+		}
+		if (keep)
+		{
+			for (int w = 0; w < W; w++) ((unsigned long long *) &out[i])[w] = ((const unsigned long long *) &all[r].recs[j])[w];
+			out[i].valid = 1;
+		}
+		else
+			out[i].valid = 0;
+	}
+}
+
+/* host rows <-> packed records: [ncols datums][null bytes padded to 8] per row, grouped by destination */
+static inline size_t hostrow_words(int ncols) { return (size_t) ncols + (size_t) ((ncols + 7) / 8); }
+
+extern "C" {
+
+int gg_ic_available(void)
+{
+	return nccl().ok ? 1 : 0;
+}
+
+int gg_ic_unique_id(void *out, int len)
+{
+	if (!out || len < GG_IC_UNIQUE_ID_BYTES) return GG_ERR_ARG;
+	Nccl &n = nccl();
+	if (!n.ok) { gg_set_error("NCCL not available: %s", n.why); return GG_ERR_UNSUPPORTED; }
+	ncclUniqueId id;
+	GG_NCCL(n.GetUniqueId(&id));
+	memcpy(out, &id, sizeof id);
+	return GG_OK;
+}
+
+/* SetupInterconnect (ic_common.c:522): join the query's communicator as segment `segindex` of `nsegs` */
+int gg_ic_create(gg_engine *e, const void *unique_id, int nsegs, int segindex, gg_interconnect **out)
+{
+	if (!e || !out || nsegs < 1 || segindex < 0 || segindex >= nsegs || (nsegs > 1 && !unique_id)) return GG_ERR_ARG;
+	*out = nullptr;
+	GG_CUDA(cudaSetDevice(e->device));
+	gg_interconnect *ic = new gg_interconnect();
+	ic->eng = e; ic->nsegs = nsegs; ic->seg = segindex;
+	if (nsegs > 1)
+	{
+		Nccl &n = nccl();
+		if (!n.ok) { gg_set_error("NCCL not available: %s", n.why); delete ic; return GG_ERR_UNSUPPORTED; }
+		ncclUniqueId id;
+		memcpy(&id, unique_id, sizeof id);
+		int rc = n.CommInitRank(&ic->comm, nsegs, id, segindex);
+		if (rc != ncclSuccess_) { delete ic; return nccl_fail(rc, "ncclCommInitRank"); }
+	}
+	cudaError_t ce = cudaMalloc((void **) &ic->d_send, sizeof(GroupBlock));
+	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_all, sizeof(GroupBlock) * (size_t) nsegs);
+	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_counts, 8 * (size_t) (nsegs + nsegs * nsegs));
+	if (ce == cudaSuccess) ce = cudaHostAlloc((void **) &ic->h_counts, 8 * (size_t) (nsegs * nsegs), cudaHostAllocDefault);
+	if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
+	*out = ic;
+	return GG_OK;
+}
+
+/* TeardownInterconnect (ic_common.c:560).  has_errors: the query is being aborted — do not wait for peers */
+void gg_ic_teardown(gg_interconnect *ic, int has_errors)
+{
+	if (!ic) return;
+	cudaSetDevice(ic->eng->device);
+	if (ic->comm)
+	{
+		if (has_errors) nccl().CommAbort(ic->comm);
+		else { cudaStreamSynchronize(ic->eng->stream); nccl().CommDestroy(ic->comm); }
+		ic->comm = nullptr;
+	}
+	cudaFree(ic->d_send); cudaFree(ic->d_all); cudaFree(ic->d_counts); cudaFreeHost(ic->h_counts); cudaFree(ic->stage);
+	delete ic;
+}
+
+void gg_ic_free(gg_interconnect *ic) { gg_ic_teardown(ic, 0); }
+
+int gg_ic_nsegs(gg_interconnect *ic) { return ic ? ic->nsegs : 0; }
+int gg_ic_segindex(gg_interconnect *ic) { return ic ? ic->seg : -1; }
+uint64_t gg_ic_collective_count(gg_interconnect *ic) { return ic ? ic->ncollectives : 0; }
+
+/* all-gather of `bytes` per segment on the engine's stream (loopback: a copy) */
+static int ic_allgather(gg_interconnect *ic, const void *send, void *recv, size_t bytes)
+{
+	cudaStream_t st = ic->eng->stream;
+	if (!ic->comm)
+	{
+		GG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
+		return GG_OK;
+	}
+	GG_NCCL(nccl().AllGather(send, recv, bytes, ncclUint8_, ic->comm, st));
+	ic->ncollectives++;
+	return GG_OK;
+}
+
+/* A barrier that is also useful: every segment learns every segment's 64-bit word (bench: max-over-ranks timing) */
+int gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all /* [nsegs] */)
+{
+	if (!ic || !all) return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(ic->eng->device));
+	cudaStream_t st = ic->eng->stream;
+	GG_CUDA(cudaMemcpyAsync(ic->d_counts, &mine, 8, cudaMemcpyHostToDevice, st));
+	int rc = ic_allgather(ic, ic->d_counts, ic->d_counts + ic->nsegs, 8);
+	if (rc) return rc;
+	GG_CUDA(cudaMemcpyAsync(ic->h_counts, ic->d_counts + ic->nsegs, 8 * (size_t) ic->nsegs, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	memcpy(all, ic->h_counts, 8 * (size_t) ic->nsegs);
+	return GG_OK;
+}
+
+/* Motion of group records, device to device: the sending half (execMotionSender, nodeMotion.c:270-374) packs the
+ * pipeline's result into this segment's block, the all-gather is the interconnect, the receiving half
+ * (execMotionUnsortedReceiver, :378) keeps what is routed here. */
+int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhash, const int32_t *hashcol,
+                        const int32_t *hashtypid, gg_groups *in, gg_groups **out)
+{
+	if (!ic || !in || !out || nhash < 0 || nhash > GG_MAX_KEYS || (nhash && (!hashcol || !hashtypid))) return GG_ERR_ARG;
+	if (motion_type != GG_IC_MOTION_HASH && motion_type != GG_IC_MOTION_GATHER && motion_type != GG_IC_MOTION_BROADCAST) return GG_ERR_ARG;
+	if (motion_type == GG_IC_MOTION_HASH && nhash < 1) return GG_ERR_ARG;
+	if (root < 0 || root >= ic->nsegs) return GG_ERR_ARG;
+	*out = nullptr;
+	gg_engine *e = ic->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	cudaStream_t st = e->stream;
+	RouteSpec spec;
+	memset(&spec, 0, sizeof spec);
+	spec.nhash = nhash;
+	for (int k = 0; k < nhash; k++)
+	{
+		if (hashcol[k] < 0 || hashcol[k] >= in->nkeys)
+		{ gg_set_error("Motion hash column %d is not a grouping column of the rows below", hashcol[k]); return GG_ERR_UNSUPPORTED; }
+		spec.hashcol[k] = hashcol[k];
+		switch (hashtypid[k])
+		{
+			case GG_INT4OID: case GG_DATEOID: spec.hashtype[k] = GGP_HT_INT4; break;
+			case GG_INT8OID: case GG_TIMESTAMPOID: spec.hashtype[k] = GGP_HT_INT8; break;
+			case GG_FLOAT8OID: spec.hashtype[k] = GGP_HT_FLOAT8; break;
+			case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID: spec.hashtype[k] = GGP_HT_STR; break;
+			case GG_BOOLOID: spec.hashtype[k] = GGP_HT_BOOL; break;
+			default: gg_set_error("hash column type %d has no device hash function", hashtypid[k]); return GG_ERR_UNSUPPORTED;
+		}
+	}
+	gg_groups *g = gg_groups_alloc(e, in, ic->nsegs * GG_IC_GROUP_CAP, /*sparse*/ true);
+	if (!g) return GG_ERR_NOMEM;
+	gg_ic_pack_groups_kernel<<<1, 256, 0, st>>>(in->recs, in->d_n, in->d_status, in->sparse ? 1 : 0, in->cap, ic->d_send);
+	cudaError_t ce = cudaGetLastError();
+	e->launches++;
+	int rc = ce == cudaSuccess ? ic_allgather(ic, ic->d_send, ic->d_all, sizeof(GroupBlock)) : gg_cuda_fail(ce, "gg_ic_motion_groups");
+	if (rc) { gg_groups_free(g); return rc; }
+	gg_ic_route_groups_kernel<<<1, 256, 0, st>>>(ic->d_all, ic->nsegs, ic->seg, motion_type, root, spec, g->recs, g->d_status);
+	ce = cudaGetLastError();
+	e->launches++;
+	if (ce != cudaSuccess) { gg_groups_free(g); return gg_cuda_fail(ce, "gg_ic_motion_groups"); }
+	*out = g;
+	return GG_OK;
+}
+
+/* Redistribute Motion of datum rows: send_rows = nsegs regions of region_cap rows of `rowwords` words (what
+ * gg_motion_partition wrote), counts[d] rows valid in region d.  Receives into recv_rows (capacity recv_cap rows),
+ * senders in segment order; *nrecv = rows received.  The count exchange is the only host synchronisation. */
+int gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64_t *counts, uint64_t region_cap, int rowwords,
+                        void *recv_rows, uint64_t recv_cap, uint64_t *nrecv)
+{
+	if (!ic || !send_rows || !counts || !recv_rows || !nrecv || rowwords < 1) return GG_ERR_ARG;
+	gg_engine *e = ic->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	cudaStream_t st = e->stream;
+	const int N = ic->nsegs;
+	const size_t rb = (size_t) rowwords * 8;
+	if (!ic->comm)
+	{
+		if (counts[0] > recv_cap) { gg_set_error("Motion receive buffer too small: %llu rows, capacity %llu", (unsigned long long) counts[0], (unsigned long long) recv_cap); return GG_ERR_NOMEM; }
+		GG_CUDA(cudaMemcpyAsync(recv_rows, send_rows, counts[0] * rb, cudaMemcpyDeviceToDevice, st));
+		*nrecv = counts[0];
+		return GG_OK;
+	}
+	/* count exchange: row d of the matrix = what segment d sends to everybody */
+	GG_CUDA(cudaMemcpyAsync(ic->d_counts, counts, 8 * (size_t) N, cudaMemcpyHostToDevice, st));
+	int rc = ic_allgather(ic, ic->d_counts, ic->d_counts + N, 8 * (size_t) N);
+	if (rc) return rc;
+	GG_CUDA(cudaMemcpyAsync(ic->h_counts, ic->d_counts + N, 8 * (size_t) N * N, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	uint64_t total = 0;
+	for (int s = 0; s < N; s++) total += ic->h_counts[(size_t) s * N + ic->seg];
+	*nrecv = total;
+	/* every segment computes every segment's total, so an overflow anywhere makes everybody skip the exchange */
+	int overflow = 0;
+	for (int d = 0; d < N; d++)
+	{
+		uint64_t t = 0;
+		for (int s = 0; s < N; s++) t += ic->h_counts[(size_t) s * N + d];
+		if (d == ic->seg ? t > recv_cap : false) overflow = 1;
+	}
+	/* capacities are local knowledge: agree on the outcome with one more (tiny) exchange */
+	{
+		uint64_t all[1024];
+		if (N > 1024) return GG_ERR_UNSUPPORTED;
+		rc = gg_ic_allgather_u64(ic, (uint64_t) overflow, all);
+		if (rc) return rc;
+		for (int s = 0; s < N; s++) if (all[s]) overflow = 2;
+	}
+	if (overflow)
+	{
+		gg_set_error("Motion receive buffer too small on some segment (this one receives %llu rows, capacity %llu)",
+		             (unsigned long long) total, (unsigned long long) recv_cap);
+		return GG_ERR_NOMEM;
+	}
+	Nccl &n = nccl();
+	GG_NCCL(n.GroupStart());
+	uint64_t at = 0;
+	for (int s = 0; s < N; s++)
+	{
+		const uint64_t sendn = counts[s], recvn = ic->h_counts[(size_t) s * N + ic->seg];
+		if (sendn) GG_NCCL(n.Send((const uint8_t *) send_rows + (size_t) s * region_cap * rb, sendn * rb, ncclUint8_, s, ic->comm, st));
+		if (recvn) GG_NCCL(n.Recv((uint8_t *) recv_rows + at * rb, recvn * rb, ncclUint8_, s, ic->comm, st));
+		at += recvn;
+	}
+	GG_NCCL(n.GroupEnd());
+	ic->ncollectives++;
+	return GG_OK;
+}
+
+/* The executor's generic Motion of host rows (GgRowBatch): values [nrows][ncols] Datums, isnull [nrows][ncols], dest[i] =
+ * receiving segment or -1 for all.  Staged through device memory; out arrays are malloc'd, the caller frees them. */
+int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *values, const uint8_t *isnull,
+                        const int32_t *dest, int my_error, int64_t *out_nrows, int64_t **out_values, uint8_t **out_isnull)
+{
+	if (my_error) nrows = 0;
+	if (!ic || ncols < 1 || nrows < 0 || (nrows && (!values || !isnull || !dest)) || !out_nrows || !out_values || !out_isnull) return GG_ERR_ARG;
+	gg_engine *e = ic->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	const int N = ic->nsegs;
+	const size_t W = hostrow_words(ncols);
+	if (N + 1 > 1024) return GG_ERR_UNSUPPORTED;
+	std::vector<uint64_t> counts((size_t) N, 0), offs((size_t) N + 1, 0), fill((size_t) N, 0);
+	{
+		/* the sender's status travels ahead of the rows: a segment whose slice failed still enters the exchange, with no
+		 * rows, and every segment learns of it here (the reference: SendStopMessage / error propagation, cdbmotion.c:342) */
+		uint64_t all[1024];
+		int rcs = gg_ic_allgather_u64(ic, (uint64_t) (my_error != 0), all);
+		if (rcs) return rcs;
+		for (int s = 0; s < N; s++)
+			if (all[s]) { gg_set_error("segment %d reported an error in its slice below the Motion", s); return GG_ERR_PEER; }
+	}
+	for (int64_t r = 0; r < nrows; r++)
+	{
+		if (dest[r] < -1 || dest[r] >= N) { gg_set_error("Motion destination %d out of range", dest[r]); return GG_ERR_ARG; }
+		if (dest[r] < 0) for (int d = 0; d < N; d++) counts[(size_t) d]++;
+		else counts[(size_t) dest[r]]++;
+	}
+	for (int d = 0; d < N; d++) offs[(size_t) d + 1] = offs[(size_t) d] + counts[(size_t) d];
+	const uint64_t nsend = offs[(size_t) N];
+	std::vector<uint64_t> packed((size_t) (nsend ? nsend : 1) * W, 0);
+	auto put = [&](int d, int64_t r) {
+		uint64_t *p = packed.data() + (offs[(size_t) d] + fill[(size_t) d]++) * W;
+		memcpy(p, values + (size_t) r * ncols, 8 * (size_t) ncols);
+		memcpy(p + ncols, isnull + (size_t) r * ncols, (size_t) ncols);
+	};
+	for (int64_t r = 0; r < nrows; r++)
+	{
+		if (dest[r] < 0) for (int d = 0; d < N; d++) put(d, r);
+		else put(dest[r], r);
+	}
+	/* count exchange first: it sizes the staging */
+	cudaStream_t st = e->stream;
+	GG_CUDA(cudaMemcpyAsync(ic->d_counts, counts.data(), 8 * (size_t) N, cudaMemcpyHostToDevice, st));
+	int rc = ic_allgather(ic, ic->d_counts, ic->d_counts + N, 8 * (size_t) N);
+	if (rc) return rc;
+	GG_CUDA(cudaMemcpyAsync(ic->h_counts, ic->d_counts + N, 8 * (size_t) N * N, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	uint64_t nrecv = 0;
+	for (int s = 0; s < N; s++) nrecv += ic->h_counts[(size_t) s * N + ic->seg];
+	const size_t need = (size_t) (nsend + nrecv + 2) * W * 8;
+	if (ic->stage_bytes < need)
+	{
+		cudaFree(ic->stage);
+		ic->stage = nullptr; ic->stage_bytes = 0;
+		GG_CUDA(cudaMalloc(&ic->stage, need));
+		ic->stage_bytes = need;
+	}
+	uint64_t *d_send = (uint64_t *) ic->stage, *d_recv = d_send + (size_t) (nsend + 1) * W;
+	if (nsend) GG_CUDA(cudaMemcpyAsync(d_send, packed.data(), (size_t) nsend * W * 8, cudaMemcpyHostToDevice, st));
+	if (!ic->comm)
+	{
+		if (nsend) GG_CUDA(cudaMemcpyAsync(d_recv, d_send, (size_t) nsend * W * 8, cudaMemcpyDeviceToDevice, st));
+	}
+	else
+	{
+		Nccl &n = nccl();
+		GG_NCCL(n.GroupStart());
+		uint64_t at = 0;
+		for (int s = 0; s < N; s++)
+		{
+			const uint64_t sendn = counts[(size_t) s], recvn = ic->h_counts[(size_t) s * N + ic->seg];
+			if (sendn) GG_NCCL(n.Send(d_send + offs[(size_t) s] * W, sendn * W * 8, ncclUint8_, s, ic->comm, st));
+			if (recvn) GG_NCCL(n.Recv(d_recv + at * W, recvn * W * 8, ncclUint8_, s, ic->comm, st));
+			at += recvn;
+		}
+		GG_NCCL(n.GroupEnd());
+		ic->ncollectives++;
+	}
+	std::vector<uint64_t> got((size_t) (nrecv ? nrecv : 1) * W);
+	if (nrecv) GG_CUDA(cudaMemcpyAsync(got.data(), d_recv, (size_t) nrecv * W * 8, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	int64_t *ov = (int64_t *) malloc(8 * (size_t) (nrecv ? nrecv : 1) * ncols);
+	uint8_t *on = (uint8_t *) malloc((size_t) (nrecv ? nrecv : 1) * ncols);
+	if (!ov || !on) { free(ov); free(on); gg_set_error("out of memory"); return GG_ERR_NOMEM; }
+	for (uint64_t r = 0; r < nrecv; r++)
+	{
+		memcpy(ov + r * ncols, got.data() + r * W, 8 * (size_t) ncols);
+		memcpy(on + r * ncols, got.data() + r * W + ncols, (size_t) ncols);
+	}
+	*out_nrows = (int64_t) nrecv; *out_values = ov; *out_isnull = on;
+	return GG_OK;
+}
+
+}  /* extern "C" */

@@ -4,6 +4,7 @@
  * has a per-match piece; everything after the probe (merge, fetch, escalation to the general HashAggregate) is shared.
  */
 #include "gg_pipeline.h"
+#include "gg_groups.h"
 
 using namespace ggd;
 
@@ -244,6 +245,14 @@ int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint6
 		j->filled = true;
 	}
 	return gg_scanagg_fetch(j->probe, out, outcap, nout, nullptr, rows_joined);
+}
+
+/* the joined-and-aggregated result as device-resident group records (after gg_joinagg_fetch ran the last pass) */
+int gg_scanagg_groups(gg_scanagg *p, gg_groups **out);
+int gg_joinagg_groups(gg_joinagg *j, gg_groups **out)
+{
+	if (!j) return GG_ERR_ARG;
+	return gg_scanagg_groups(j->probe, out);
 }
 
 int gg_joinagg_reset(gg_joinagg *j)

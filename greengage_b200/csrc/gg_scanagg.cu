@@ -82,7 +82,7 @@ __global__ void gg_hashagg_emit_kernel(HashAggTable ha, ggp_grec *out, unsigned 
 __global__ void __launch_bounds__(1024, 1)
 gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_acckinds kinds,
                      ggp_grec *out, int outcap, int *nout, int *vidx /* [nrecs] */, int *vmap /* [nrecs] */,
-                     uint32_t *errflags)
+                     uint32_t *errflags, int prefix_sets /* 1: the valid records of a set are a prefix of it */)
 {
 	__shared__ int s_nvalid, s_nout, s_lock;
 	__shared__ int s_warpsum[32];
@@ -202,7 +202,8 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 			const int i = set * GGP_FAST_GROUPS + slot;
 			/* within a set the valid records are a prefix (a block fills slots 0..G-1; merged / FINAL-stage input is
 			 * dense), so the first invalid slot ends the set */
-			if (i >= nrecs || !recs[i].valid) break;
+			if (i >= nrecs) break;
+			if (!recs[i].valid) { if (prefix_sets) break; else continue; }
 			if (vmap[i] != mg) continue;
 			const ggp_grec &x = recs[i];
 			cnt += x.count;
@@ -267,6 +268,7 @@ gg_merge_recs_kernel(const ggp_grec *recs, int nrecs, int nkeys, int nacc, ggp_a
 #include <vector>
 
 #include "gg_pipeline.h"
+#include "gg_groups.h"
 
 /* launch configuration and shared-memory layout for the current kernel variant:
  *   ring[nstage][32 KB] | full/empty mbarriers | BlockTable | per-warp scratch | (PRIV) counts | (PRIV) sums */
@@ -504,7 +506,7 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	ggp_acckinds kinds;
 	memcpy(kinds.k, p->prog.acckind, sizeof kinds.k);
 	gg_merge_recs_kernel<<<1, 1024, 0, st>>>(p->recs, p->nrecs_total, p->prog.nkeys, p->prog.nacc, kinds,
-	                                        p->merged, GG_MERGE_CAP, p->d_nout, p->vidx, p->vmap, p->d_err);
+	                                        p->merged, GG_MERGE_CAP, p->d_nout, p->vidx, p->vmap, p->d_err, 1);
 	GG_CUDA(cudaGetLastError());
 	e->launches++;
 	/* merged -> first GG_MERGE_CAP slots of recs (input of the next fold); slots beyond nout are invalidated
@@ -1026,7 +1028,7 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 	GG_CUDA(cudaMemcpyAsync(d_err, &hostflags, sizeof hostflags, cudaMemcpyHostToDevice, e->stream));
 	GG_CUDA(cudaMemsetAsync(d_out, 0, sizeof(ggp_grec) * cap, e->stream));
 	gg_merge_recs_kernel<<<1, 1024, 0, e->stream>>>(d_recs, nin, agg->numCols, agg->numAggs, kinds,
-	                                               d_out, cap, d_n, d_vidx, d_vmap, d_err);
+	                                               d_out, cap, d_n, d_vidx, d_vmap, d_err, 1);
 	cudaError_t le = cudaGetLastError();
 	e->launches++;
 	if (le == cudaSuccess) le = cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, e->stream);
@@ -1046,4 +1048,165 @@ int gg_agg_final(gg_engine *e, const gg_agg *agg, const gg_aggrow *in, int nin,
 	return GG_OK;
 }
 
+
+/* ---------------- device-resident group records (gg_groups.h) ---------------- */
+
+}  /* extern "C" */
+
+/* buffers of the common size are recycled through the engine: a Motion per step must not cost a cudaMalloc */
+#define GG_GROUPS_POOL_CAP 256
+static size_t groups_bytes(int cap) { return sizeof(ggp_grec) * (size_t) cap + sizeof(gg_groupstatus) + 16 + 2 * sizeof(int) * (size_t) cap; }
+
+gg_groups *gg_groups_alloc(gg_engine *e, const gg_groups *like, int cap, bool sparse)
+{
+	gg_groups *g = new gg_groups();
+	if (like) *g = *like;
+	g->eng = e; g->cap = cap; g->sparse = sparse; g->owned = true;
+	const int alloc_cap = cap <= GG_GROUPS_POOL_CAP ? GG_GROUPS_POOL_CAP : cap;
+	void *mem = nullptr;
+	if (alloc_cap == GG_GROUPS_POOL_CAP && !e->groups_pool.empty()) { mem = e->groups_pool.back(); e->groups_pool.pop_back(); }
+	else if (cudaMalloc(&mem, groups_bytes(alloc_cap)) != cudaSuccess) { cudaGetLastError(); gg_set_error("out of device memory for %d group records", cap); delete g; return nullptr; }
+	g->recs = (ggp_grec *) mem;
+	g->d_status = (gg_groupstatus *) (g->recs + alloc_cap);
+	g->d_n = &g->d_status->n;
+	g->scratch = (int *) ((uint8_t *) g->d_status + sizeof(gg_groupstatus) + 8);
+	g->alloc_cap = alloc_cap;
+	return g;
+}
+
+extern "C" {
+
+void gg_groups_free(gg_groups *g)
+{
+	if (!g) return;
+	if (g->owned && g->recs)
+	{
+		/* stream-ordered reuse: whoever takes the buffer next works on the same stream */
+		if (g->alloc_cap == GG_GROUPS_POOL_CAP && g->eng->groups_pool.size() < 16) g->eng->groups_pool.push_back(g->recs);
+		else { cudaStreamSynchronize(g->eng->stream); cudaFree(g->recs); }
+	}
+	delete g;
+}
+
+static void groups_meta_from_pipeline(gg_groups *g, const gg_scanagg *p)
+{
+	g->agg = p->agg;
+	memcpy(g->aggmap, p->aggmap, sizeof g->aggmap);
+	g->nkeys = p->prog.nkeys; g->nacc = p->prog.nacc;
+	memcpy(g->keytype, p->prog.keytype, sizeof g->keytype);
+	memcpy(g->acckind, p->prog.acckind, sizeof g->acckind);
+	for (int c = 0; c < GG_MAX_KEYS; c++)
+		g->keytypid[c] = (c < p->agg.numCols && p->agg.grpCol[c] >= 0 && p->agg.grpCol[c] < p->pool.nnodes) ? p->pool.nodes[p->agg.grpCol[c]].rettype : 0;
+}
+
+/* the result of a pipeline, left where it is: a view into the pipeline's merged records (valid until its next reset).
+ * The general HashAggregate keeps its groups in the HBM table: GG_ERR_UNSUPPORTED, the caller fetches rows instead. */
+int gg_scanagg_groups(gg_scanagg *p, gg_groups **out)
+{
+	if (!p || !out) return GG_ERR_ARG;
+	*out = nullptr;
+	if (p->mode == MODE_HASH) { gg_set_error("the general HashAggregate's groups live in its hash table"); return GG_ERR_UNSUPPORTED; }
+	gg_groups *g = new gg_groups();
+	g->eng = p->eng;
+	g->recs = p->recs; g->cap = GG_MERGE_CAP; g->sparse = false;
+	g->d_status = (gg_groupstatus *) p->d_status;
+	g->d_n = &g->d_status->n;
+	g->owned = false;
+	groups_meta_from_pipeline(g, p);
+	*out = g;
+	return GG_OK;
+}
+
+/* FINAL-stage Agg on the device: combine the records a Motion delivered (float8pl / float8_combine / int8pl,
+ * nodeAgg.c:2123-2148) with the deterministic merge kernel; the result reads like a one-stage aggregate's. */
+int gg_groups_final(gg_engine *e, gg_groups *in, gg_groups **out)
+{
+	if (!e || !in || !out) return GG_ERR_ARG;
+	*out = nullptr;
+	GG_CUDA(cudaSetDevice(e->device));
+	const int cap = in->cap < GG_GROUPS_POOL_CAP ? in->cap : (in->sparse ? in->cap : GG_GROUPS_POOL_CAP);
+	gg_groups *g = gg_groups_alloc(e, in, cap, false);
+	if (!g) return GG_ERR_NOMEM;
+	g->agg.aggstage = GG_AGGSTAGE_NORMAL;          /* combined states finalise like a one-stage aggregate's (float8_avg = sumX / N) */
+	cudaStream_t st = e->stream;
+	ggp_acckinds kinds;
+	memcpy(kinds.k, in->acckind, sizeof kinds.k);
+	cudaError_t ce = cudaMemcpyAsync(g->d_status, in->d_status, sizeof(gg_groupstatus), cudaMemcpyDeviceToDevice, st);
+	if (ce == cudaSuccess) ce = cudaMemsetAsync(g->recs, 0, sizeof(ggp_grec) * (size_t) cap, st);
+	if (ce == cudaSuccess)
+	{
+		const int nrecs = in->sparse ? in->cap : (in->cap < GG_GROUPS_POOL_CAP ? in->cap : GG_GROUPS_POOL_CAP);
+		gg_merge_recs_kernel<<<1, 1024, 0, st>>>(in->recs, nrecs, in->nkeys, in->nacc, kinds, g->recs, cap, g->d_n,
+		                                        g->scratch, g->scratch + g->alloc_cap, &g->d_status->err, in->sparse ? 0 : 1);
+		ce = cudaGetLastError();
+		e->launches++;
+	}
+	if (ce != cudaSuccess) { gg_groups_free(g); return gg_cuda_fail(ce, "gg_groups_final"); }
+	*out = g;
+	return GG_OK;
+}
+
+/* the one host synchronisation of a device-resident slice: records + status -> rows (finalize_aggregate, nodeAgg.c:871) */
+int gg_groups_fetch(gg_groups *g, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_scanned, uint64_t *rows_passed)
+{
+	if (!g || !nout || outcap < 0 || (outcap && !out)) return GG_ERR_ARG;
+	gg_engine *e = g->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	cudaStream_t st = e->stream;
+	if (!e->groups_mirror) GG_CUDA(cudaHostAlloc(&e->groups_mirror, groups_bytes(GG_GROUPS_POOL_CAP), cudaHostAllocDefault));
+	gg_groupstatus *hs = (gg_groupstatus *) e->groups_mirror;
+	ggp_grec *hr = (ggp_grec *) ((uint8_t *) e->groups_mirror + 64);
+	const int first = g->sparse ? (g->cap < GG_GROUPS_POOL_CAP ? g->cap : GG_GROUPS_POOL_CAP) : GGP_FAST_GROUPS;
+	GG_CUDA(cudaMemcpyAsync(hs, g->d_status, sizeof *hs, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaMemcpyAsync(hr, g->recs, sizeof(ggp_grec) * (size_t) first, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaStreamSynchronize(st));
+	if (rows_scanned) *rows_scanned = hs->counters[0];
+	if (rows_passed) *rows_passed = hs->counters[1];
+	const uint32_t flags = hs->err;
+	if (flags & GGP_EF_GROUP_OVERFLOW) { gg_set_error("more group records on one segment than a device Motion block holds (%d)", GG_IC_GROUP_CAP); return GG_ERR_UNSUPPORTED; }
+	int rc = gg_errflags_to_code(flags);
+	if (rc) return rc;
+	std::vector<ggp_grec> recs;
+	if (g->sparse)
+	{
+		std::vector<ggp_grec> all;
+		const ggp_grec *src = hr;
+		if (g->cap > first)
+		{
+			all.resize((size_t) g->cap);
+			GG_CUDA(cudaMemcpy(all.data(), g->recs, sizeof(ggp_grec) * (size_t) g->cap, cudaMemcpyDeviceToHost));
+			src = all.data();
+		}
+		for (int i = 0; i < g->cap; i++) if (src[i].valid) recs.push_back(src[i]);
+	}
+	else
+	{
+		const int n = hs->n;
+		if (n < 0 || n > g->cap) { gg_set_error("group record count %d out of range", n); return GG_ERR_CUDA; }
+		recs.resize((size_t) n);
+		if (n > 0 && n <= first) memcpy(recs.data(), hr, sizeof(ggp_grec) * (size_t) n);
+		else if (n > 0) GG_CUDA(cudaMemcpy(recs.data(), g->recs, sizeof(ggp_grec) * (size_t) n, cudaMemcpyDeviceToHost));
+	}
+	int n = (int) recs.size();
+	/* plain aggregation over zero rows still yields one row (nodeAgg.c:1247-1400) — on the segment that owns the result */
+	if (n == 0 && g->agg.numCols == 0 && !g->empty_is_empty) { recs.resize(1); memset(&recs[0], 0, sizeof(ggp_grec)); n = 1; }
+	if (n > outcap) { gg_set_error("output capacity %d < %d groups", outcap, n); return GG_ERR_NOMEM; }
+	std::vector<ggp_program> pb(1);
+	memset(&pb[0], 0, sizeof(ggp_program));
+	memcpy(pb[0].keytype, g->keytype, sizeof g->keytype);
+	finalize_rows(&g->agg, g->aggmap, &pb[0], 0, recs.data(), n, out);
+	*nout = n;
+	return GG_OK;
+}
+
+int gg_groups_info(gg_groups *g, int *sparse, int *cap)
+{
+	if (!g) return GG_ERR_ARG;
+	if (sparse) *sparse = g->sparse ? 1 : 0;
+	if (cap) *cap = g->cap;
+	return GG_OK;
+}
+
+/* a non-receiving segment of a Gather holds no rows: not even the empty-input row of a plain aggregate */
+void gg_groups_set_nonreceiver(gg_groups *g) { if (g) g->empty_is_empty = true; }
 }  /* extern "C" */

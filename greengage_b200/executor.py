@@ -27,7 +27,8 @@ GgPlan._fields_ = [("type", C.c_int), ("lefttree", C.POINTER(GgPlan)), ("righttr
 
 
 class GgSeqScan(C.Structure):
-    _fields_ = [("plan", GgPlan), ("scanrelid", C.c_int32), ("desc", capi.gg_tupdesc)]
+    _fields_ = [("plan", GgPlan), ("scanrelid", C.c_int32), ("desc", capi.gg_tupdesc),
+                ("numTargets", C.c_int32), ("targets", C.c_int32 * GG_MAX_OUTCOLS)]
 
 
 class GgAgg(C.Structure):
@@ -72,7 +73,8 @@ class GgMotionTransport(C.Structure):
 class GgEState(C.Structure):
     _fields_ = [("engine", C.c_void_p), ("pool", C.POINTER(capi.gg_exprpool)), ("relations", C.c_void_p * GG_MAX_RELATIONS),
                 ("nsegs", C.c_int32), ("segindex", C.c_int32), ("transport", C.POINTER(GgMotionTransport)),
-                ("es_processed", C.c_uint64)]
+                ("es_processed", C.c_uint64), ("interconnect", C.c_void_p),
+                ("host_pages", C.c_void_p * GG_MAX_RELATIONS), ("host_nblocks", C.c_uint64 * GG_MAX_RELATIONS)]
 
 
 _lib = None
@@ -126,10 +128,14 @@ class PlanBuilder:
         self.nodes.append(n)
         return n
 
-    def seqscan(self, scanrelid, desc, qual=-1):
+    def seqscan(self, scanrelid, desc, qual=-1, targets=()):
+        """targets: expression roots the scan projects (rows stay on the device for the node above); () = fused"""
         n = self._keep(GgSeqScan())
         n.plan.type, n.plan.qual, n.scanrelid = T_SeqScan, qual, scanrelid
         C.memmove(C.byref(n.desc), C.byref(desc), C.sizeof(capi.gg_tupdesc))
+        n.numTargets = len(targets)
+        for i, t in enumerate(targets):
+            n.targets[i] = t
         return n
 
     def agg(self, child, agg):
@@ -171,14 +177,20 @@ class PlanBuilder:
 class Executor:
     """One slice on one segment: ExecInitNode at construction, rows() drives ExecProcNode to end of stream."""
 
-    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None):
+    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None, interconnect=None):
+        """relations[i]: a device-resident Relation, or (host address, nblocks) for pages in host memory, or None"""
         L = exec_lib()
         self.es = GgEState()
         self.es.engine = eng.h if hasattr(eng, "h") else eng
         self._pool = pool
         self.es.pool = C.pointer(pool)
         for i, r in enumerate(relations):
-            self.es.relations[i] = r.h if r is not None else None
+            if isinstance(r, tuple):
+                self.es.host_pages[i], self.es.host_nblocks[i] = r
+            else:
+                self.es.relations[i] = r.h if r is not None else None
+        if interconnect is not None:
+            self.es.interconnect = interconnect.h if hasattr(interconnect, "h") else interconnect
         self.es.nsegs, self.es.segindex = nsegs, segindex
         self._transport = transport
         if transport is not None:
@@ -275,6 +287,15 @@ class TorchTransport:
         try:
             s = send.contents
             n, ncols = int(s.nrows), int(s.ncols)
+            import torch
+            import torch.distributed as dist
+            # every segment says whether its slice below the Motion failed (nrows = -1) before any row moves: a failed
+            # segment takes part with no rows and every segment comes back with GG_ERR_PEER
+            flag = torch.tensor([1 if n < 0 else 0], dtype=torch.int32)
+            flag = flag.to(self.device) if self.device is not None else flag
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            if int(flag.item()):
+                return -12
             if n:
                 values = np.ctypeslib.as_array(s.values, shape=(n, ncols)).copy()
                 isnull = np.ctypeslib.as_array(s.isnull, shape=(n, ncols)).copy()

@@ -7,6 +7,14 @@
  * every call hands out one row of the result as a virtual tuple — the contract the node above sees is the
  * reference's (one TupleTableSlot per call, NULL at end of stream, ExecReScan restarts, ExecSquelchNode stops
  * early; nodeAgg.c:1123, nodeHashjoin.c:78, nodeSort.c:48, nodeMotion.c:180).
+ *
+ * Results stay on the device between the nodes of a slice:
+ *     aggregate rows   as group records (gg_groups): Agg -> Motion -> FINAL Agg -> Gather move and combine them there
+ *                      (gg_ic_motion_groups, gg_groups_final); the node at the top fetches once
+ *     scanned rows     as datum rows (GG_FMT_DATUMROWS): SeqScan with a target list -> Redistribute Motion ->
+ *                      Hash / HashJoin / Agg scan them with the same kernels (gg_motion_partition, gg_ic_exchange_rows)
+ * Host arrays of Datums appear only where a node has to hand tuples to its caller, or on the generic path (Sort, a
+ * Motion over a transport callback).
  */
 #include <stdarg.h>
 #include <stdio.h>
@@ -17,23 +25,39 @@
 int32_t gg_cdbhash_route(const int32_t *typids, const int64_t *vals, const int32_t *lens, const int32_t *isnull,
                          int nkeys, int nsegs);      /* gg_motion_host.c */
 
-enum { K_SCANAGG = 1, K_JOINAGG, K_AGGFINAL, K_SORT, K_MOTION };
+enum { K_SCANAGG = 1, K_JOINAGG, K_AGGFINAL, K_SORT, K_MOTION, K_SCANROWS, K_HASH };
 
 struct GgPlanState {
 	int kind;
 	GgPlan *plan;
 	GgEState *estate;
-	struct GgPlanState *child;          /* Sort / Motion / final Agg: the pipeline below */
+	struct GgPlanState *child;          /* Sort / Motion / final Agg / Agg over rows: the pipeline below */
+	struct GgPlanState *inner;          /* join: the rows node under the Hash (NULL: the inner SeqScan is fused) */
 	/* device pipelines */
 	gg_scanagg *sa;
 	gg_joinagg *ja;
-	gg_relation *rel, *inner_rel;
+	gg_relation *rel, *inner_rel;       /* base relations (not owned) */
+	const void *host_pages;             /* K_SCANAGG over a relation in host memory */
+	uint64_t host_nblocks;
 	gg_agg agg;
-	/* result set: filled by the first ExecProcNode, then handed out row by row */
+	/* device-resident results */
+	gg_groups *groups;                  /* aggregate rows */
+	gg_relation *rows_rel;              /* datum rows (K_SCANROWS, K_MOTION over a scan): wraps rows_recv / rows_send */
+	gg_relation *rows_send, *rows_recv; /* raw device buffers (gg_relation_create) */
+	uint64_t rows_cap;                  /* rows the send buffer holds over all destinations */
+	uint64_t rows_n;
+	int32_t rows_ncols;
+	int32_t rows_targets[GG_MAX_OUTCOLS];
+	gg_tupdesc rows_desc;               /* GG_FMT_DATUMROWS descriptor of what this node delivers */
+	GgSeqScan *rows_scan;               /* the SeqScan the rows come from */
+	int32_t rows_nsegs;                 /* destinations the rows are partitioned for (1: plain projection) */
+	/* result set: filled on demand, then handed out row by row */
 	int done;                           /* pipeline has run */
+	int rows_ready;                     /* host arrays below are filled */
 	int squelched;
+	int nonreceiver;                    /* above a Gather, on a segment that is not its receiver: no rows at all */
 	int32_t ncols;
-	int64_t nrows, next;
+	int64_t nrows, next, markpos;
 	int64_t *values;
 	uint8_t *isnull;
 	int32_t typid[GG_MAX_OUTCOLS];
@@ -67,6 +91,8 @@ const char *GgExecNodeKind(GgPlanState *s)
 		case K_AGGFINAL: return "aggfinal";
 		case K_SORT: return "sort";
 		case K_MOTION: return "motion";
+		case K_SCANROWS: return "scanrows";
+		case K_HASH: return "hash";
 	}
 	return "";
 }
@@ -91,31 +117,44 @@ static int32_t agg_result_type(int32_t fn)
 
 static int64_t f8bits(double d) { int64_t v; memcpy(&v, &d, 8); return v; }
 static double bitsf8(int64_t v) { double d; memcpy(&d, &v, 8); return d; }
+static int is_string_type(int32_t t) { return t == GG_BPCHAROID || t == GG_VARCHAROID || t == GG_TEXTOID; }
 
 static int alloc_result(GgPlanState *s, int64_t nrows, int32_t ncols)
 {
 	free(s->values); free(s->isnull); free(s->lens);
-	s->nrows = nrows; s->ncols = ncols; s->next = 0;
+	s->nrows = nrows; s->ncols = ncols; s->next = 0; s->markpos = 0;
 	s->values = calloc((size_t) (nrows > 0 ? nrows : 1) * (size_t) ncols, 8);
 	s->isnull = calloc((size_t) (nrows > 0 ? nrows : 1) * (size_t) ncols, 1);
 	s->lens = calloc((size_t) (nrows > 0 ? nrows : 1) * (size_t) ncols, 4);
 	return (s->values && s->isnull && s->lens) ? 0 : -1;
 }
 
-/* gg_aggrow[] -> result columns */
-static int rows_from_aggrows(GgPlanState *s, const gg_agg *agg, const int32_t *keytypes, const gg_aggrow *rows, int n)
+/* column count and types of an Agg node's output rows */
+static int set_layout_types(GgPlanState *s, const gg_agg *agg, const int32_t *keytypes)
 {
-	int ncols = agg->numCols, i, c, r;
+	int ncols = agg->numCols, i, c;
+	int32_t kt[GG_MAX_KEYS];
+	for (c = 0; c < agg->numCols && c < GG_MAX_KEYS; c++) kt[c] = keytypes[c];      /* keytypes may alias s->typid */
 	for (i = 0; i < agg->numAggs; i++) ncols += agg_ncols_of(agg, i);
 	if (ncols > GG_MAX_OUTCOLS) { exec_fail(GG_ERR_UNSUPPORTED, "too many output columns"); return -1; }
-	if (alloc_result(s, n, ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-	for (c = 0; c < agg->numCols; c++) s->typid[c] = keytypes[c];
+	for (c = 0; c < agg->numCols; c++) s->typid[c] = kt[c];
 	for (i = 0, c = agg->numCols; i < agg->numAggs; i++)
 	{
 		int w = agg_ncols_of(agg, i), k;
 		for (k = 0; k < w; k++) s->typid[c + k] = (w == 3) ? GG_FLOAT8OID : agg_result_type(agg->aggs[i].aggfnoid);
 		c += w;
 	}
+	s->ncols = ncols;
+	return 0;
+}
+
+/* gg_aggrow[] -> result columns */
+static int rows_from_aggrows(GgPlanState *s, const gg_agg *agg, const int32_t *keytypes, const gg_aggrow *rows, int n)
+{
+	int ncols, i, c, r;
+	if (set_layout_types(s, agg, keytypes)) return -1;
+	ncols = s->ncols;
+	if (alloc_result(s, n, ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
 	for (r = 0; r < n; r++)
 	{
 		int64_t *v = s->values + (size_t) r * ncols;
@@ -138,6 +177,7 @@ static int rows_from_aggrows(GgPlanState *s, const gg_agg *agg, const int32_t *k
 			c += w;
 		}
 	}
+	s->rows_ready = 1;
 	return 0;
 }
 
@@ -177,25 +217,35 @@ static gg_aggrow *aggrows_from_rows(const GgPlanState *child, const gg_agg *agg)
 	return out;
 }
 
+static void drop_device_results(GgPlanState *s)
+{
+	if (s->groups) { gg_groups_free(s->groups); s->groups = NULL; }
+	if (s->rows_rel) { gg_relation_free(s->rows_rel); s->rows_rel = NULL; }
+}
+
 static void free_state(GgPlanState *s)
 {
 	if (!s) return;
+	drop_device_results(s);
+	if (s->rows_send) gg_relation_free(s->rows_send);
+	if (s->rows_recv) gg_relation_free(s->rows_recv);
 	if (s->sa) gg_scanagg_free(s->sa);
 	if (s->ja) gg_joinagg_free(s->ja);
 	free(s->values); free(s->isnull); free(s->lens);
 	free(s);
 }
 
-static gg_relation *relation_of(GgEState *es, const GgSeqScan *scan)
+static void end_tree(GgPlanState *s)
 {
-	if (scan->scanrelid < 0 || scan->scanrelid >= GG_MAX_RELATIONS || !es->relations[scan->scanrelid])
-		return exec_fail(GG_ERR_ARG, "SeqScan: relation %d is not resident on the device", scan->scanrelid);
-	return es->relations[scan->scanrelid];
+	if (!s) return;
+	end_tree(s->child);
+	end_tree(s->inner);
+	free_state(s);
 }
 
 static int32_t expr_type(const gg_exprpool *pool, int32_t root) { return pool->nodes[root].rettype; }
 
-#define GG_MAX_PLAN_DEPTH 32        /* the deepest accelerated slice is Motion <- Sort <- Agg <- Motion <- Agg <- HashJoin <- Hash <- SeqScan */
+#define GG_MAX_PLAN_DEPTH 32        /* the deepest accelerated slice is Motion <- Sort <- Agg <- Motion <- Agg <- HashJoin <- Hash <- Motion <- SeqScan */
 
 static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int depth);
 
@@ -205,10 +255,85 @@ GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
 	return init_node(node, estate, eflags, 0);
 }
 
+static int multi_segment(const GgEState *es) { return es->nsegs > 1; }
+
+/* a node that delivers device-resident datum rows: a SeqScan with a target list, or a Motion over one */
+static int yields_rows(const GgPlan *p)
+{
+	if (!p) return 0;
+	if (p->type == T_GgSeqScan) return ((const GgSeqScan *) p)->numTargets > 0;
+	if (p->type == T_GgMotion) return p->lefttree && p->lefttree->type == T_GgSeqScan && ((const GgSeqScan *) p->lefttree)->numTargets > 0;
+	return 0;
+}
+
+/* the relation a SeqScan reads: resident on the device, or pages in host memory */
+static int bind_relation(GgEState *es, const GgSeqScan *scan, gg_relation **rel, const void **host_pages, uint64_t *host_nblocks)
+{
+	*rel = NULL; *host_pages = NULL; *host_nblocks = 0;
+	if (scan->scanrelid < 0 || scan->scanrelid >= GG_MAX_RELATIONS)
+	{ exec_fail(GG_ERR_ARG, "SeqScan: relation %d out of range", scan->scanrelid); return -1; }
+	if (es->relations[scan->scanrelid]) { *rel = es->relations[scan->scanrelid]; return 0; }
+	if (es->host_pages[scan->scanrelid]) { *host_pages = es->host_pages[scan->scanrelid]; *host_nblocks = es->host_nblocks[scan->scanrelid]; return 0; }
+	exec_fail(GG_ERR_ARG, "SeqScan: relation %d is neither resident on the device nor given as host pages", scan->scanrelid);
+	return -1;
+}
+
+/* state of a rows-producing node (SeqScan with targets, optionally under a Redistribute Motion) */
+static GgPlanState *init_rows_node(GgPlan *node, GgEState *estate, GgPlanState *s)
+{
+	GgSeqScan *sc = (GgSeqScan *) (node->type == T_GgMotion ? node->lefttree : node);
+	const void *hp; uint64_t hn;
+	int i;
+	if (sc->numTargets < 1 || sc->numTargets > GG_MAX_OUTCOLS || sc->numTargets > 16)
+	{ exec_fail(GG_ERR_UNSUPPORTED, "SeqScan projecting %d columns (1..16 travel as datum rows)", sc->numTargets); free_state(s); return NULL; }
+	if (bind_relation(estate, sc, &s->rel, &hp, &hn)) { free_state(s); return NULL; }
+	if (!s->rel) { exec_fail(GG_ERR_UNSUPPORTED, "a row-producing SeqScan needs its relation resident on the device"); free_state(s); return NULL; }
+	s->rows_scan = sc;
+	s->rows_ncols = sc->numTargets;
+	memset(&s->rows_desc, 0, sizeof s->rows_desc);
+	s->rows_desc.natts = sc->numTargets;
+	s->rows_desc.format = GG_FMT_DATUMROWS;
+	for (i = 0; i < sc->numTargets; i++)
+	{
+		const int32_t root = sc->targets[i];
+		const gg_expr *e;
+		gg_attr *a = &s->rows_desc.attrs[i];
+		if (root < 0 || root >= estate->pool->nnodes) { exec_fail(GG_ERR_ARG, "SeqScan target %d: node %d is not in the pool", i, root); free_state(s); return NULL; }
+		e = &estate->pool->nodes[root];
+		s->rows_targets[i] = root;
+		s->typid[i] = e->rettype;
+		a->atttypid = e->rettype; a->atttypmod = -1; a->attlen = 8; a->attalign = 'd'; a->attbyval = 1;
+		/* a plain Var of a NOT NULL column stays NOT NULL: lets the consumers run their NULL-free kernel variants */
+		a->attnotnull = (e->kind == 1 /* GG_E_VAR */ && e->varattno >= 1 && e->varattno <= sc->desc.natts) ? sc->desc.attrs[e->varattno - 1].attnotnull : 0;
+	}
+	s->ncols = sc->numTargets;
+	if (node->type == T_GgMotion)
+	{
+		GgMotion *mo = (GgMotion *) node;
+		int c;
+		if (mo->motionType != GG_MOTIONTYPE_HASH)
+		{ exec_fail(GG_ERR_UNSUPPORTED, "only a Redistribute Motion moves scanned rows on the device"); free_state(s); return NULL; }
+		if (mo->numHashCols < 1 || mo->numHashCols > GG_MAX_KEYS)
+		{ exec_fail(GG_ERR_UNSUPPORTED, "Redistribute Motion with %d hash columns", mo->numHashCols); free_state(s); return NULL; }
+		for (c = 0; c < mo->numHashCols; c++)
+			if (mo->hashCol[c] < 0 || mo->hashCol[c] >= sc->numTargets)
+			{ exec_fail(GG_ERR_ARG, "Motion hash column %d out of range (the scan projects %d columns)", mo->hashCol[c], sc->numTargets); free_state(s); return NULL; }
+		if (multi_segment(estate) && !estate->interconnect)
+		{ exec_fail(GG_ERR_ARG, "Motion over a scan: %d segments but no device interconnect", estate->nsegs); free_state(s); return NULL; }
+		s->kind = K_MOTION;
+		s->rows_nsegs = estate->nsegs > 0 ? estate->nsegs : 1;
+	}
+	else
+	{
+		s->kind = K_SCANROWS;
+		s->rows_nsegs = 1;
+	}
+	return s;
+}
+
 static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int depth)
 {
 	GgPlanState *s;
-	(void) eflags;
 	if (!node) return NULL;                                   /* ExecInitNode(NULL) is NULL, execProcnode.c:268 */
 	if (!estate || !estate->engine || !estate->pool) return exec_fail(GG_ERR_ARG, "EState without engine or expression pool");
 	if (depth > GG_MAX_PLAN_DEPTH) return exec_fail(GG_ERR_ARG, "plan tree deeper than %d nodes (a cycle?)", GG_MAX_PLAN_DEPTH);
@@ -237,16 +362,26 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 				if (!s->child) { free_state(s); return NULL; }
 				return s;
 			}
-			if (below && below->type == T_GgSeqScan)
+			if (below && (below->type == T_GgSeqScan || yields_rows(below)))
 			{
-				GgSeqScan *sc = (GgSeqScan *) below;
 				gg_scan scan;
 				memset(&scan, 0, sizeof scan);
-				scan.desc = sc->desc; scan.qual = below->qual;
-				if (!(s->rel = relation_of(estate, sc))) { free_state(s); return NULL; }
 				s->kind = K_SCANAGG;
+				if (yields_rows(below))
+				{
+					/* Agg over redistributed / projected rows: the same scan+aggregate kernel over datum rows */
+					s->child = init_node(below, estate, eflags, depth + 1);
+					if (!s->child) { free_state(s); return NULL; }
+					scan.desc = s->child->rows_desc; scan.qual = -1;
+				}
+				else
+				{
+					GgSeqScan *sc = (GgSeqScan *) below;
+					scan.desc = sc->desc; scan.qual = below->qual;
+					if (bind_relation(estate, sc, &s->rel, &s->host_pages, &s->host_nblocks)) { free_state(s); return NULL; }
+				}
 				rc = gg_scanagg_create(estate->engine, &scan, &an->agg, estate->pool, &s->sa);
-				if (rc != GG_OK) { exec_fail(rc, "Agg <- SeqScan: %s", gg_last_error()); free_state(s); return NULL; }
+				if (rc != GG_OK) { exec_fail(rc, "Agg <- SeqScan: %s", gg_last_error()); end_tree(s->child); s->child = NULL; free_state(s); return NULL; }
 				return s;
 			}
 			if (below && below->type == T_GgHashJoin)
@@ -254,20 +389,51 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 				GgHashJoin *hj = (GgHashJoin *) below;
 				GgPlan *outer = below->lefttree, *hash = below->righttree, *inner = hash ? hash->lefttree : NULL;
 				gg_scan oscan, iscan;
-				if (!outer || outer->type != T_GgSeqScan || !hash || hash->type != T_GgHash || !inner || inner->type != T_GgSeqScan)
+				const void *hp; uint64_t hn;
+				if (!outer || !hash || hash->type != T_GgHash || !inner ||
+				    !(outer->type == T_GgSeqScan || yields_rows(outer)) || !(inner->type == T_GgSeqScan || yields_rows(inner)))
 				{
-					exec_fail(GG_ERR_UNSUPPORTED, "HashJoin: only SeqScan ⋈ Hash(SeqScan) is fused on the device");
+					exec_fail(GG_ERR_UNSUPPORTED, "HashJoin: both inputs must be a SeqScan or a Redistribute Motion over one (Hash on the inner side)");
 					free_state(s);
 					return NULL;
 				}
 				memset(&oscan, 0, sizeof oscan); memset(&iscan, 0, sizeof iscan);
-				oscan.desc = ((GgSeqScan *) outer)->desc; oscan.qual = outer->qual;
-				iscan.desc = ((GgSeqScan *) inner)->desc; iscan.qual = inner->qual;
-				if (!(s->rel = relation_of(estate, (GgSeqScan *) outer)) || !(s->inner_rel = relation_of(estate, (GgSeqScan *) inner)))
-				{ free_state(s); return NULL; }
 				s->kind = K_JOINAGG;
+				if (yields_rows(outer))
+				{
+					s->child = init_node(outer, estate, eflags, depth + 1);
+					if (!s->child) { free_state(s); return NULL; }
+					oscan.desc = s->child->rows_desc; oscan.qual = -1;
+				}
+				else
+				{
+					oscan.desc = ((GgSeqScan *) outer)->desc; oscan.qual = outer->qual;
+					if (bind_relation(estate, (GgSeqScan *) outer, &s->rel, &hp, &hn)) { free_state(s); return NULL; }
+					if (!s->rel) { exec_fail(GG_ERR_UNSUPPORTED, "HashJoin: the outer relation must be resident on the device"); free_state(s); return NULL; }
+				}
+				if (yields_rows(inner))
+				{
+					s->inner = init_node(inner, estate, eflags, depth + 2);
+					if (!s->inner) { end_tree(s->child); s->child = NULL; free_state(s); return NULL; }
+					iscan.desc = s->inner->rows_desc; iscan.qual = -1;
+				}
+				else
+				{
+					iscan.desc = ((GgSeqScan *) inner)->desc; iscan.qual = inner->qual;
+					if (bind_relation(estate, (GgSeqScan *) inner, &s->inner_rel, &hp, &hn) || !s->inner_rel)
+					{
+						if (!s->inner_rel && !g_errcode) exec_fail(GG_ERR_UNSUPPORTED, "HashJoin: the inner relation must be resident on the device");
+						end_tree(s->child); s->child = NULL; free_state(s); return NULL;
+					}
+				}
 				rc = gg_joinagg_create(estate->engine, &oscan, &iscan, &hj->hj, &an->agg, estate->pool, &s->ja);
-				if (rc != GG_OK) { exec_fail(rc, "Agg <- HashJoin: %s", gg_last_error()); free_state(s); return NULL; }
+				if (rc != GG_OK)
+				{
+					exec_fail(rc, "Agg <- HashJoin: %s", gg_last_error());
+					end_tree(s->child); end_tree(s->inner); s->child = s->inner = NULL;
+					free_state(s);
+					return NULL;
+				}
 				return s;
 			}
 			exec_fail(GG_ERR_UNSUPPORTED, "Agg: child node type %d is not on the accelerated path", below ? (int) below->type : 0);
@@ -286,7 +452,9 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 		case T_GgMotion:
 		{
 			GgMotion *mo = (GgMotion *) node;
-			if (!estate->transport && estate->nsegs > 1) { exec_fail(GG_ERR_ARG, "Motion: %d segments but no transport", estate->nsegs); free_state(s); return NULL; }
+			if (yields_rows(node)) return init_rows_node(node, estate, s);
+			if (!estate->transport && !estate->interconnect && multi_segment(estate))
+			{ exec_fail(GG_ERR_ARG, "Motion: %d segments but neither an interconnect nor a transport", estate->nsegs); free_state(s); return NULL; }
 			if (mo->motionType == GG_MOTIONTYPE_HASH && (mo->numHashCols < 1 || mo->numHashCols > GG_MAX_KEYS))
 			{ exec_fail(GG_ERR_UNSUPPORTED, "Redistribute Motion with %d hash columns", mo->numHashCols); free_state(s); return NULL; }
 			s->kind = K_MOTION;
@@ -294,25 +462,193 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 			if (!s->child) { free_state(s); return NULL; }
 			return s;
 		}
-		case T_GgSeqScan: case T_GgHashJoin: case T_GgHash:
-			/* bare scans / joins return whole tuples to a CPU parent: nothing to accelerate without an Agg on top */
-			exec_fail(GG_ERR_UNSUPPORTED, "node type %d is only accelerated underneath an Agg", (int) node->type);
+		case T_GgSeqScan:
+			if (((GgSeqScan *) node)->numTargets > 0) return init_rows_node(node, estate, s);
+			exec_fail(GG_ERR_UNSUPPORTED, "a SeqScan without a target list is only accelerated underneath an Agg or a HashJoin");
 			free_state(s);
 			return NULL;
+		case T_GgHashJoin:
+			/* a join that has to return its rows to a CPU parent: not materialised on the device */
+			exec_fail(GG_ERR_UNSUPPORTED, "a HashJoin is only accelerated underneath an Agg (the join is never materialised)");
+			free_state(s);
+			return NULL;
+		case T_GgHash:
+			s->kind = K_HASH;          /* marker: the build is part of the join's pipeline */
+			return s;
 	}
 	exec_fail(GG_ERR_UNSUPPORTED, "unknown node type %d", (int) node->type);
 	free_state(s);
 	return NULL;
 }
 
-/* drain a child pipeline (what tuplesort_puttupleslot / the Motion sender loop do, nodeSort.c:139, nodeMotion.c:340) */
 static int run_node(GgPlanState *s);
 
 static int run_child(GgPlanState *s)
 {
-	if (!s->child->done && run_node(s->child)) return -1;
+	if (s->child && !s->child->done && run_node(s->child)) return -1;
 	return 0;
 }
+
+/* ---- datum rows on the device: SeqScan projection, optionally partitioned for a Redistribute Motion ---- */
+static int run_rows_node(GgPlanState *s)
+{
+	GgEState *es = s->estate;
+	GgSeqScan *sc = s->rows_scan;
+	const int N = s->rows_nsegs;
+	const int W = 1 + s->rows_ncols;
+	const uint64_t nblocks = gg_relation_nblocks(s->rel);
+	gg_scan scan;
+	int32_t hashkeys[GG_MAX_KEYS];
+	int nkeys = 0, c, rc, attempt;
+	uint64_t counts[1024], offs[1024];
+	if (N > 1024) { exec_fail(GG_ERR_UNSUPPORTED, "more than 1024 segments"); return -1; }
+	memset(&scan, 0, sizeof scan);
+	scan.desc = sc->desc; scan.qual = sc->plan.qual;
+	if (s->kind == K_MOTION)
+	{
+		GgMotion *mo = (GgMotion *) s->plan;
+		for (c = 0; c < mo->numHashCols; c++) hashkeys[nkeys++] = s->rows_targets[mo->hashCol[c]];
+	}
+	else
+		hashkeys[nkeys++] = s->rows_targets[0];          /* one destination: the key only feeds jump_consistent_hash(h, 1) = 0 */
+	drop_device_results(s);
+	for (attempt = 0; ; attempt++)
+	{
+		if (!s->rows_send)
+		{
+			/* first guess: no more rows than 48-byte tuples fit the pages (exact sizes are in the pages' line pointers; a region
+			 * that turns out too small is reported with the size it needs) */
+			uint64_t words;
+			if (!s->rows_cap) s->rows_cap = ((nblocks * (uint64_t) GG_BLCKSZ / 48) / (uint64_t) N + 1024) * (uint64_t) N;
+			words = s->rows_cap * (uint64_t) W + 8;
+			rc = gg_relation_create(es->engine, (words * 8 + GG_BLCKSZ - 1) / GG_BLCKSZ, &s->rows_send);
+			if (rc != GG_OK) { exec_fail(rc, "Motion send buffer: %s", gg_last_error()); return -1; }
+		}
+		rc = gg_motion_partition(es->engine, &scan, es->pool, hashkeys, nkeys, s->rows_targets, s->rows_ncols, N, s->rel, 0, nblocks,
+		                         gg_relation_device_ptr(s->rows_send), s->rows_cap, counts, offs);
+		if (rc != GG_ERR_NOMEM || attempt >= 2) break;
+		gg_relation_free(s->rows_send); s->rows_send = NULL;
+		s->rows_cap *= 2;
+	}
+	if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+	if (N == 1)
+	{
+		s->rows_n = counts[0];
+		rc = gg_relation_attach_rows(es->engine, gg_relation_device_ptr(s->rows_send), s->rows_n, s->rows_ncols, &s->rows_rel);
+		if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+		return 0;
+	}
+	for (attempt = 0; ; attempt++)
+	{
+		const uint64_t region_cap = (s->rows_cap / (uint64_t) N) & ~1ull;
+		uint64_t recv_cap;
+		if (!s->rows_recv)
+		{
+			rc = gg_relation_create(es->engine, ((s->rows_cap * (uint64_t) W + 8) * 8 + GG_BLCKSZ - 1) / GG_BLCKSZ, &s->rows_recv);
+			if (rc != GG_OK) { exec_fail(rc, "Motion receive buffer: %s", gg_last_error()); return -1; }
+		}
+		recv_cap = gg_relation_nblocks(s->rows_recv) * (uint64_t) GG_BLCKSZ / 8 / (uint64_t) W - 2;
+		rc = gg_ic_exchange_rows(es->interconnect, gg_relation_device_ptr(s->rows_send), counts, region_cap, W,
+		                         gg_relation_device_ptr(s->rows_recv), recv_cap, &s->rows_n);
+		if (rc != GG_ERR_NOMEM || attempt >= 1) break;
+		/* every segment saw the overflow: all of them come back with a receive buffer twice the size */
+		{
+			const uint64_t nb = gg_relation_nblocks(s->rows_recv) * 2;
+			gg_relation_free(s->rows_recv); s->rows_recv = NULL;
+			rc = gg_relation_create(es->engine, nb, &s->rows_recv);
+			if (rc != GG_OK) { exec_fail(rc, "Motion receive buffer: %s", gg_last_error()); return -1; }
+		}
+	}
+	if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+	rc = gg_relation_attach_rows(es->engine, gg_relation_device_ptr(s->rows_recv), s->rows_n, s->rows_ncols, &s->rows_rel);
+	if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+	return 0;
+}
+
+/* device rows -> host result arrays (only when a rows node sits at the top of what the caller drives) */
+static int rows_to_host(GgPlanState *s)
+{
+	const int W = 1 + s->rows_ncols;
+	const uint64_t n = s->rows_n;
+	const uint64_t bytes = n * (uint64_t) W * 8;
+	const uint64_t nb = (bytes + GG_BLCKSZ - 1) / GG_BLCKSZ;
+	uint64_t *buf, r;
+	int c, rc;
+	if (alloc_result(s, (int64_t) n, s->rows_ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+	if (n)
+	{
+		buf = malloc((size_t) nb * GG_BLCKSZ);
+		if (!buf) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		rc = gg_relation_read(s->rows_recv && s->rows_nsegs > 1 ? s->rows_recv : s->rows_send, 0, buf, nb);
+		if (rc != GG_OK) { free(buf); exec_fail(rc, "%s", gg_last_error()); return -1; }
+		for (r = 0; r < n; r++)
+			for (c = 0; c < s->rows_ncols; c++)
+			{
+				const uint64_t v = buf[r * W + 1 + c];
+				s->values[r * s->rows_ncols + c] = (int64_t) v;
+				s->isnull[r * s->rows_ncols + c] = (uint8_t) ((buf[r * W] >> c) & 1);
+				if (is_string_type(s->typid[c]))
+				{
+					int l = 0;
+					while (l < 8 && ((v >> (8 * l)) & 0xff)) l++;
+					s->lens[r * s->rows_ncols + c] = l;
+				}
+			}
+		free(buf);
+	}
+	s->rows_ready = 1;
+	return 0;
+}
+
+/* device group records -> host result arrays: the one synchronisation of a device-resident slice */
+static int groups_to_host(GgPlanState *s)
+{
+	int cap = 1024, n = 0, rc, c;
+	gg_aggrow *rows = NULL;
+	gg_agg layout;
+	int32_t keytypes[GG_MAX_KEYS] = { 0 };
+	for (;;)
+	{
+		free(rows);
+		rows = malloc(sizeof(gg_aggrow) * (size_t) cap);
+		if (!rows) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		rc = gg_groups_fetch(s->groups, rows, cap, &n, NULL, NULL);
+		if (rc != GG_ERR_NOMEM || cap >= (1 << 20)) break;
+		cap *= 16;
+	}
+	if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(rows); return -1; }
+	/* rows read as the node's own Agg says: a Motion passes its child's layout through */
+	layout = s->agg;
+	if (s->kind == K_AGGFINAL)
+	{
+		layout.aggstage = GG_AGGSTAGE_FINAL;
+		for (c = 0; c < layout.numCols; c++) keytypes[c] = s->agg.grpCol[c];
+	}
+	else
+		for (c = 0; c < layout.numCols; c++) keytypes[c] = s->typid[c];
+	rc = rows_from_aggrows(s, &layout, keytypes, rows, n);
+	free(rows);
+	return rc;
+}
+
+static int ensure_rows(GgPlanState *s)
+{
+	if (s->rows_ready) return 0;
+	if (s->groups) return groups_to_host(s);
+	if (s->rows_rel || s->kind == K_SCANROWS || (s->kind == K_MOTION && s->rows_scan)) return rows_to_host(s);
+	exec_fail(GG_ERR_ARG, "node has no result");
+	return -1;
+}
+
+/* the Agg description and key types of the rows a node hands up (for the nodes that pass rows through) */
+static void inherit_layout(GgPlanState *s, const GgPlanState *ch)
+{
+	s->agg = ch->agg;
+	s->ncols = ch->ncols;
+	memcpy(s->typid, ch->typid, sizeof s->typid);
+}
+
+static int motion_host_path(GgPlanState *s, int child_failed);
 
 static int run_node(GgPlanState *s)
 {
@@ -320,20 +656,33 @@ static int run_node(GgPlanState *s)
 	int rc;
 	switch (s->kind)
 	{
+		case K_SCANROWS:
+			if (run_rows_node(s)) return -1;
+			break;
 		case K_SCANAGG:
 		case K_JOINAGG:
 		{
 			int cap = 4096, n = 0, c;
 			int32_t keytypes[GG_MAX_KEYS] = { 0 };
 			gg_aggrow *rows = NULL;
+			drop_device_results(s);
+			if (s->child && !s->child->done && run_node(s->child)) return -1;
+			if (s->inner && !s->inner->done && run_node(s->inner)) return -1;
 			if (s->kind == K_SCANAGG)
-				rc = gg_scanagg_run(s->sa, s->rel, 0, gg_relation_nblocks(s->rel));
+			{
+				if (s->child) rc = gg_scanagg_run(s->sa, s->child->rows_rel, 0, gg_relation_nblocks(s->child->rows_rel));
+				else if (s->rel) rc = gg_scanagg_run(s->sa, s->rel, 0, gg_relation_nblocks(s->rel));
+				else rc = gg_scanagg_run_host(s->sa, s->host_pages, s->host_nblocks);
+			}
 			else
 			{
-				rc = gg_joinagg_build(s->ja, s->inner_rel, 0, gg_relation_nblocks(s->inner_rel));
-				if (rc == GG_OK) rc = gg_joinagg_probe(s->ja, s->rel, 0, gg_relation_nblocks(s->rel));
+				gg_relation *irel = s->inner ? s->inner->rows_rel : s->inner_rel;
+				gg_relation *orel = s->child ? s->child->rows_rel : s->rel;
+				rc = gg_joinagg_build(s->ja, irel, 0, gg_relation_nblocks(irel));
+				if (rc == GG_OK) rc = gg_joinagg_probe(s->ja, orel, 0, gg_relation_nblocks(orel));
 			}
-			/* the result stays on the device until fetched: grow the row buffer until every group fits */
+			/* fetch decides whether the pipeline has to be replayed on a wider kernel variant (more groups than expected, a
+			 * non-finite sum to attribute), so it runs before anything above consumes the records on the device */
 			while (rc == GG_OK)
 			{
 				free(rows);
@@ -349,26 +698,54 @@ static int run_node(GgPlanState *s)
 			rc = rows_from_aggrows(s, &s->agg, keytypes, rows, n);
 			free(rows);
 			if (rc) return -1;
+			/* and the same rows as device-resident records, for a Motion / FINAL Agg above (not available from the general
+			 * HashAggregate, whose groups live in its hash table: the nodes above then take the host rows) */
+			if (s->kind == K_SCANAGG) rc = gg_scanagg_groups(s->sa, &s->groups);
+			else rc = gg_joinagg_groups(s->ja, &s->groups);
+			if (rc != GG_OK) s->groups = NULL;
 			break;
 		}
 		case K_AGGFINAL:
 		{
 			gg_aggrow *in, *out;
-			int n = 0, cap;
+			int n = 0, cap, i, same;
 			gg_agg part = s->agg;
+			GgPlanState *ch = s->child;
+			drop_device_results(s);
 			if (run_child(s)) return -1;
+			s->nonreceiver = ch->nonreceiver;
+			/* device path: the child delivered group records of a PARTIAL stage with these very aggregates */
+			same = ch->groups != NULL && ch->agg.aggstage == GG_AGGSTAGE_PARTIAL && ch->agg.numAggs == s->agg.numAggs && ch->agg.numCols == s->agg.numCols;
+			for (i = 0; same && i < s->agg.numAggs; i++) same = ch->agg.aggs[i].aggfnoid == s->agg.aggs[i].aggfnoid;
+			if (same)
+			{
+				rc = gg_groups_final(es->engine, ch->groups, &s->groups);
+				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+				if (set_layout_types(s, &s->agg, s->agg.grpCol)) return -1;
+				s->rows_ready = 0;
+				break;
+			}
+			if (ensure_rows(ch)) return -1;
+			if (s->nonreceiver)
+			{
+				/* the slice above a Gather exists only on the receiving segment (the QD in the reference): no rows here, not
+				 * even the empty-input row of a plain aggregate */
+				if (alloc_result(s, 0, ch->ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+				s->rows_ready = 1;
+				break;
+			}
 			part.aggstage = GG_AGGSTAGE_PARTIAL;      /* layout of the incoming rows */
 			{
-				int want = part.numCols, i;
+				int want = part.numCols;
 				for (i = 0; i < part.numAggs; i++) want += agg_ncols_of(&part, i);
-				if (want != s->child->ncols && s->child->nrows > 0)
-				{ exec_fail(GG_ERR_ARG, "FINAL Agg expects %d columns of partial state, the node below delivers %d", want, s->child->ncols); return -1; }
+				if (want != ch->ncols && ch->nrows > 0)
+				{ exec_fail(GG_ERR_ARG, "FINAL Agg expects %d columns of partial state, the node below delivers %d", want, ch->ncols); return -1; }
 			}
-			in = aggrows_from_rows(s->child, &part);
-			cap = s->child->nrows > 0 ? (int) s->child->nrows : 1;
+			in = aggrows_from_rows(ch, &part);
+			cap = ch->nrows > 0 ? (int) ch->nrows : 1;
 			out = malloc(sizeof(gg_aggrow) * (size_t) cap);
 			if (!in || !out) { free(in); free(out); exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-			rc = gg_agg_final(es->engine, &s->agg, in, (int) s->child->nrows, out, cap, &n);
+			rc = gg_agg_final(es->engine, &s->agg, in, (int) ch->nrows, out, cap, &n);
 			free(in);
 			if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(out); return -1; }
 			rc = rows_from_aggrows(s, &s->agg, s->agg.grpCol /* key type OIDs at the FINAL stage */, out, n);
@@ -384,7 +761,8 @@ static int run_node(GgPlanState *s)
 			gg_sortkey keys[GG_MAX_SORTKEYS];
 			int64_t r;
 			int k;
-			if (run_child(s)) return -1;
+			if (run_child(s) || ensure_rows(ch)) return -1;
+			s->nonreceiver = ch->nonreceiver;
 			for (k = 0; k < so->numCols; k++)
 			{
 				keys[k] = so->keys[k];
@@ -404,106 +782,50 @@ static int run_node(GgPlanState *s)
 				memcpy(s->lens + (size_t) r * ch->ncols, ch->lens + (size_t) perm[r] * ch->ncols, 4 * (size_t) ch->ncols);
 			}
 			free(perm);
+			s->rows_ready = 1;
 			break;
 		}
 		case K_MOTION:
 		{
 			GgMotion *mo = (GgMotion *) s->plan;
 			GgPlanState *ch = s->child;
-			int64_t r;
-			int c;
-			if (run_child(s)) return -1;
-			if (!es->transport)
+			int child_failed = 0, c;
+			if (s->rows_scan)
 			{
-				/* one segment: sender and receiver are the same process */
-				if (alloc_result(s, ch->nrows, ch->ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-				memcpy(s->values, ch->values, 8 * (size_t) ch->nrows * ch->ncols);
-				memcpy(s->isnull, ch->isnull, (size_t) ch->nrows * ch->ncols);
-				memcpy(s->lens, ch->lens, 4 * (size_t) ch->nrows * ch->ncols);
+				if (run_rows_node(s)) return -1;
+				break;
 			}
-			else
+			drop_device_results(s);
+			if (run_child(s))
 			{
-				GgRowBatch send, recv;
-				int32_t *dest;
-				if (mo->motionType == GG_MOTIONTYPE_HASH)
-					for (c = 0; c < mo->numHashCols; c++)
-						if (mo->hashCol[c] < 0 || mo->hashCol[c] >= ch->ncols)
-						{ exec_fail(GG_ERR_ARG, "Motion hash column %d out of range (the node below has %d columns)", mo->hashCol[c], ch->ncols); return -1; }
-				dest = malloc(4 * (size_t) (ch->nrows > 0 ? ch->nrows : 1));
-				if (!dest) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-				for (r = 0; r < ch->nrows; r++)
-				{
-					if (mo->motionType == GG_MOTIONTYPE_HASH)
-					{
-						/* evalHashKey (nodeMotion.c:1481): cdbhash over the hash columns, reduced to a segment */
-						int32_t t[GG_MAX_KEYS], ln[GG_MAX_KEYS], nn[GG_MAX_KEYS];
-						int64_t v[GG_MAX_KEYS];
-						for (c = 0; c < mo->numHashCols; c++)
-						{
-							int col = mo->hashCol[c];
-							t[c] = ch->typid[col];
-							v[c] = ch->values[(size_t) r * ch->ncols + col];
-							ln[c] = ch->lens[(size_t) r * ch->ncols + col];
-							nn[c] = ch->isnull[(size_t) r * ch->ncols + col];
-						}
-						dest[r] = gg_cdbhash_route(t, v, ln, nn, mo->numHashCols, es->nsegs);
-					}
-					else
-						dest[r] = mo->motionType == GG_MOTIONTYPE_BROADCAST ? -1 : 0;
-				}
-				send.ncols = ch->ncols; send.nrows = ch->nrows; send.values = ch->values; send.isnull = ch->isnull;
-				memset(&recv, 0, sizeof recv);
-				rc = es->transport->exchange(es->transport->ctx, mo->motionID, mo->motionType, &send, dest, &recv);
-				free(dest);
-				if (rc) { exec_fail(GG_ERR_CUDA, "Motion %d: transport failed (%d)", mo->motionID, rc); return -1; }
-				if (alloc_result(s, recv.nrows, ch->ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-				if (recv.nrows)
-				{
-					memcpy(s->values, recv.values, 8 * (size_t) recv.nrows * ch->ncols);
-					memcpy(s->isnull, recv.isnull, (size_t) recv.nrows * ch->ncols);
-				}
-				/* string lengths do not travel: recompute from the packed bytes */
-				for (r = 0; r < recv.nrows; r++)
-					for (c = 0; c < ch->ncols; c++)
-						if (ch->typid[c] == GG_BPCHAROID || ch->typid[c] == GG_VARCHAROID || ch->typid[c] == GG_TEXTOID)
-						{
-							uint64_t u = (uint64_t) s->values[(size_t) r * ch->ncols + c];
-							int l = 0;
-							while (l < 8 && ((u >> (8 * l)) & 0xff)) l++;
-							s->lens[(size_t) r * ch->ncols + c] = l;
-						}
-				free(recv.values); free(recv.isnull);
+				/* this segment's slice failed: it still takes part in the exchange (with no rows) so that no peer waits for
+				 * it, and every segment comes back with an error (nodeMotion.c / cdbmotion.c:342 stop + error propagation) */
+				if (!multi_segment(es) || (!es->interconnect && !es->transport)) return -1;
+				child_failed = 1;
 			}
-			memcpy(s->typid, ch->typid, sizeof s->typid);
-			if (mo->numSortCols > 0 && s->nrows > 1)
+			s->nonreceiver = (mo->motionType == GG_MOTIONTYPE_GATHER && multi_segment(es) && es->segindex != 0) || (!child_failed && ch->nonreceiver);
+			if (!child_failed) inherit_layout(s, ch);
+			/* device path: aggregate rows move as group records, segment to segment, without touching the host */
+			if (!child_failed && es->interconnect && ch->groups && !(mo->numSortCols > 0))
 			{
-				/* sorted receive: the merged order of sorted streams is the sorted order of their union; the comparator is
-				 * the Sort node's (tuplesort_mk.c:2816), ties in unspecified order as in the reference's merge */
-				gg_sortkey keys[GG_MAX_SORTKEYS];
-				uint64_t *perm = malloc(8 * (size_t) s->nrows);
-				int64_t *v2 = malloc(8 * (size_t) s->nrows * s->ncols);
-				uint8_t *n2 = malloc((size_t) s->nrows * s->ncols);
-				int32_t *l2 = malloc(4 * (size_t) s->nrows * s->ncols);
-				int k;
-				if (mo->numSortCols > GG_MAX_SORTKEYS) { exec_fail(GG_ERR_UNSUPPORTED, "Motion with %d merge keys", mo->numSortCols); free(perm); free(v2); free(n2); free(l2); return -1; }
-				if (!perm || !v2 || !n2 || !l2) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-				for (k = 0; k < mo->numSortCols; k++)
+				int32_t hashtyp[GG_MAX_KEYS];
+				int ok = 1;
+				for (c = 0; c < mo->numHashCols && mo->motionType == GG_MOTIONTYPE_HASH; c++)
 				{
-					keys[k] = mo->sortKeys[k];
-					if (keys[k].col < 0 || keys[k].col >= s->ncols) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_ARG, "Motion merge key column %d out of range", keys[k].col); return -1; }
-					if (!keys[k].typid) keys[k].typid = s->typid[keys[k].col];
+					if (mo->hashCol[c] < 0 || mo->hashCol[c] >= ch->agg.numCols) { ok = 0; break; }      /* hashing an aggregate value: host path */
+					hashtyp[c] = ch->typid[mo->hashCol[c]];
 				}
-				rc = gg_sort_rows(es->engine, keys, mo->numSortCols, s->ncols, s->values, s->isnull, (uint64_t) s->nrows, perm);
-				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(perm); free(v2); free(n2); free(l2); return -1; }
-				for (r = 0; r < s->nrows; r++)
+				if (ok)
 				{
-					memcpy(v2 + (size_t) r * s->ncols, s->values + (size_t) perm[r] * s->ncols, 8 * (size_t) s->ncols);
-					memcpy(n2 + (size_t) r * s->ncols, s->isnull + (size_t) perm[r] * s->ncols, (size_t) s->ncols);
-					memcpy(l2 + (size_t) r * s->ncols, s->lens + (size_t) perm[r] * s->ncols, 4 * (size_t) s->ncols);
+					rc = gg_ic_motion_groups(es->interconnect, mo->motionType, 0, mo->motionType == GG_MOTIONTYPE_HASH ? mo->numHashCols : 0,
+					                         mo->hashCol, hashtyp, ch->groups, &s->groups);
+					if (rc != GG_OK) { exec_fail(rc, "Motion %d: %s", mo->motionID, gg_last_error()); return -1; }
+					if (s->nonreceiver) gg_groups_set_nonreceiver(s->groups);
+					s->rows_ready = 0;
+					break;
 				}
-				free(s->values); free(s->isnull); free(s->lens); free(perm);
-				s->values = v2; s->isnull = n2; s->lens = l2;
 			}
+			if (motion_host_path(s, child_failed)) return -1;
 			break;
 		}
 		default:
@@ -515,14 +837,143 @@ static int run_node(GgPlanState *s)
 	return 0;
 }
 
+/* Motion of host rows: loopback, the C interconnect's staged exchange, or the transport callback */
+static int motion_host_path(GgPlanState *s, int child_failed)
+{
+	GgEState *es = s->estate;
+	GgMotion *mo = (GgMotion *) s->plan;
+	GgPlanState *ch = s->child;
+	int64_t r;
+	int c, rc;
+	if (!child_failed && ensure_rows(ch)) return -1;
+	if (!multi_segment(es) || (!es->transport && !es->interconnect))
+	{
+		/* one segment: sender and receiver are the same process */
+		if (alloc_result(s, ch->nrows, ch->ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		memcpy(s->values, ch->values, 8 * (size_t) ch->nrows * ch->ncols);
+		memcpy(s->isnull, ch->isnull, (size_t) ch->nrows * ch->ncols);
+		memcpy(s->lens, ch->lens, 4 * (size_t) ch->nrows * ch->ncols);
+	}
+	else
+	{
+		GgRowBatch send, recv;
+		int32_t *dest;
+		const int64_t nsend = child_failed ? 0 : ch->nrows;
+		const int32_t ncols = child_failed ? 1 : ch->ncols;
+		char child_err[sizeof g_err];
+		int child_code = g_errcode;
+		memcpy(child_err, g_err, sizeof child_err);
+		if (!child_failed && mo->motionType == GG_MOTIONTYPE_HASH)
+			for (c = 0; c < mo->numHashCols; c++)
+				if (mo->hashCol[c] < 0 || mo->hashCol[c] >= ch->ncols)
+				{ exec_fail(GG_ERR_ARG, "Motion hash column %d out of range (the node below has %d columns)", mo->hashCol[c], ch->ncols); return -1; }
+		dest = malloc(4 * (size_t) (nsend > 0 ? nsend : 1));
+		if (!dest) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		for (r = 0; r < nsend; r++)
+		{
+			if (mo->motionType == GG_MOTIONTYPE_HASH)
+			{
+				/* evalHashKey (nodeMotion.c:1481): cdbhash over the hash columns, reduced to a segment */
+				int32_t t[GG_MAX_KEYS], ln[GG_MAX_KEYS], nn[GG_MAX_KEYS];
+				int64_t v[GG_MAX_KEYS];
+				for (c = 0; c < mo->numHashCols; c++)
+				{
+					int col = mo->hashCol[c];
+					t[c] = ch->typid[col];
+					v[c] = ch->values[(size_t) r * ch->ncols + col];
+					ln[c] = ch->lens[(size_t) r * ch->ncols + col];
+					nn[c] = ch->isnull[(size_t) r * ch->ncols + col];
+				}
+				dest[r] = gg_cdbhash_route(t, v, ln, nn, mo->numHashCols, es->nsegs);
+			}
+			else
+				dest[r] = mo->motionType == GG_MOTIONTYPE_BROADCAST ? -1 : 0;
+		}
+		memset(&recv, 0, sizeof recv);
+		if (es->interconnect)
+		{
+			rc = gg_ic_exchange_host(es->interconnect, ncols, nsend, child_failed ? NULL : ch->values, child_failed ? NULL : ch->isnull, dest,
+			                         child_failed, &recv.nrows, &recv.values, &recv.isnull);
+			free(dest);
+			if (child_failed) { exec_fail(child_code, "%s", child_err); return -1; }        /* our own error is the better message */
+			if (rc != GG_OK) { exec_fail(rc, "Motion %d: %s", mo->motionID, gg_last_error()); return -1; }
+		}
+		else
+		{
+			/* transport callback: nrows = -1 tells the peers that this segment failed */
+			send.ncols = ncols; send.nrows = child_failed ? -1 : nsend;
+			send.values = child_failed ? NULL : ch->values; send.isnull = child_failed ? NULL : ch->isnull;
+			rc = es->transport->exchange(es->transport->ctx, mo->motionID, mo->motionType, &send, dest, &recv);
+			free(dest);
+			if (child_failed) { free(recv.values); free(recv.isnull); exec_fail(child_code, "%s", child_err); return -1; }
+			if (rc) { exec_fail(rc == GG_ERR_PEER ? GG_ERR_PEER : GG_ERR_CUDA, "Motion %d: %s (%d)", mo->motionID, rc == GG_ERR_PEER ? "another segment reported an error" : "transport failed", rc); return -1; }
+		}
+		if (alloc_result(s, recv.nrows, ch->ncols)) { free(recv.values); free(recv.isnull); exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		if (recv.nrows)
+		{
+			memcpy(s->values, recv.values, 8 * (size_t) recv.nrows * ch->ncols);
+			memcpy(s->isnull, recv.isnull, (size_t) recv.nrows * ch->ncols);
+		}
+		/* string lengths do not travel: recompute from the packed bytes */
+		for (r = 0; r < recv.nrows; r++)
+			for (c = 0; c < ch->ncols; c++)
+				if (is_string_type(ch->typid[c]))
+				{
+					uint64_t u = (uint64_t) s->values[(size_t) r * ch->ncols + c];
+					int l = 0;
+					while (l < 8 && ((u >> (8 * l)) & 0xff)) l++;
+					s->lens[(size_t) r * ch->ncols + c] = l;
+				}
+		free(recv.values); free(recv.isnull);
+	}
+	memcpy(s->typid, ch->typid, sizeof s->typid);
+	if (mo->numSortCols > 0 && s->nrows > 1)
+	{
+		/* sorted receive: the merged order of sorted streams is the sorted order of their union; the comparator is
+		 * the Sort node's (tuplesort_mk.c:2816), ties in unspecified order as in the reference's merge */
+		gg_sortkey keys[GG_MAX_SORTKEYS];
+		uint64_t *perm = malloc(8 * (size_t) s->nrows);
+		int64_t *v2 = malloc(8 * (size_t) s->nrows * s->ncols);
+		uint8_t *n2 = malloc((size_t) s->nrows * s->ncols);
+		int32_t *l2 = malloc(4 * (size_t) s->nrows * s->ncols);
+		int k;
+		if (mo->numSortCols > GG_MAX_SORTKEYS) { exec_fail(GG_ERR_UNSUPPORTED, "Motion with %d merge keys", mo->numSortCols); free(perm); free(v2); free(n2); free(l2); return -1; }
+		if (!perm || !v2 || !n2 || !l2) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
+		for (k = 0; k < mo->numSortCols; k++)
+		{
+			keys[k] = mo->sortKeys[k];
+			if (keys[k].col < 0 || keys[k].col >= s->ncols) { free(perm); free(v2); free(n2); free(l2); exec_fail(GG_ERR_ARG, "Motion merge key column %d out of range", keys[k].col); return -1; }
+			if (!keys[k].typid) keys[k].typid = s->typid[keys[k].col];
+		}
+		rc = gg_sort_rows(es->engine, keys, mo->numSortCols, s->ncols, s->values, s->isnull, (uint64_t) s->nrows, perm);
+		if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(perm); free(v2); free(n2); free(l2); return -1; }
+		for (r = 0; r < s->nrows; r++)
+		{
+			memcpy(v2 + (size_t) r * s->ncols, s->values + (size_t) perm[r] * s->ncols, 8 * (size_t) s->ncols);
+			memcpy(n2 + (size_t) r * s->ncols, s->isnull + (size_t) perm[r] * s->ncols, (size_t) s->ncols);
+			memcpy(l2 + (size_t) r * s->ncols, s->lens + (size_t) perm[r] * s->ncols, 4 * (size_t) s->ncols);
+		}
+		free(s->values); free(s->isnull); free(s->lens); free(perm);
+		s->values = v2; s->isnull = n2; s->lens = l2;
+	}
+	s->rows_ready = 1;
+	return 0;
+}
+
 GgTupleTableSlot *GgExecProcNode(GgPlanState *s)
 {
 	int c;
 	if (!s || s->squelched) return NULL;
+	if (s->kind == K_HASH) { exec_fail(GG_ERR_ARG, "Hash node does not return tuples via ExecProcNode()"); return NULL; }     /* nodeHash.c:73 ExecHash */
 	if (!s->done)
 	{
 		g_err[0] = 0; g_errcode = GG_OK;
 		if (run_node(s)) return NULL;                 /* the C wrapper on the Postgres side turns this into ereport(ERROR) */
+	}
+	if (!s->rows_ready)
+	{
+		g_err[0] = 0; g_errcode = GG_OK;
+		if (ensure_rows(s)) return NULL;
 	}
 	if (s->next >= s->nrows)
 	{
@@ -543,28 +994,43 @@ GgTupleTableSlot *GgExecProcNode(GgPlanState *s)
 	return &s->slot;
 }
 
+void *GgMultiExecProcNode(GgPlanState *s)
+{
+	/* execProcnode.c:1217: MultiExecHash is the only multi-exec node on this path, and its work — the build kernel — belongs
+	 * to the join's pipeline (gg_joinagg_build), launched when the Agg above the join first runs */
+	if (!s || s->kind != K_HASH) exec_fail(GG_ERR_ARG, "MultiExecProcNode on a node that is not a Hash");
+	return NULL;
+}
+
 int GgExecReScan(GgPlanState *s)
 {
 	int rc = GG_OK;
 	if (!s) return GG_ERR_ARG;
 	if (s->child && (rc = GgExecReScan(s->child)) != GG_OK) return rc;
+	if (s->inner && (rc = GgExecReScan(s->inner)) != GG_OK) return rc;
+	drop_device_results(s);
 	if (s->sa) rc = gg_scanagg_reset(s->sa);
 	if (s->ja && rc == GG_OK) rc = gg_joinagg_reset(s->ja);
-	s->done = 0; s->squelched = 0; s->next = 0; s->nrows = 0;
+	s->done = 0; s->squelched = 0; s->next = 0; s->nrows = 0; s->rows_ready = 0; s->markpos = 0;
 	return rc;
 }
 
 void GgExecSquelchNode(GgPlanState *s)
 {
-	/* the node above needs no more rows (LIMIT satisfied, nodeLimit.c): stop handing them out */
-	for (; s; s = s->child) s->squelched = 1;
+	/* the node above needs no more rows (LIMIT satisfied, nodeLimit.c): stop handing them out.  A Motion between several
+	 * segments that has not run yet still has to: its peers are (or will be) in the exchange, and a collective has no
+	 * Stop message to send them (ExecSquelchMotion -> SendStopMessage, nodeMotion.c:1730) */
+	for (; s; s = s->child)
+	{
+		if (s->kind == K_MOTION && !s->done && multi_segment(s->estate) && (s->estate->interconnect || s->estate->transport))
+			(void) run_node(s);
+		s->squelched = 1;
+	}
 }
 
 void GgExecEndNode(GgPlanState *s)
 {
-	if (!s) return;
-	GgExecEndNode(s->child);
-	free_state(s);
+	end_tree(s);
 }
 
 /* ---- per-node entry points (executor/node*.h names) ---- */
@@ -585,6 +1051,9 @@ GgTupleTableSlot *GgExecSort(GgPlanState *node) { return GgExecProcNode(node); }
 void GgExecEndSort(GgPlanState *node) { GgExecEndNode(node); }
 int GgExecReScanSort(GgPlanState *node) { return GgExecReScan(node); }
 void GgExecSquelchSort(GgPlanState *node) { GgExecSquelchNode(node); }
+/* ExecSortMarkPos / ExecSortRestrPos (nodeSort.c:444,462): the sorted result is materialised, so a position is an index */
+void GgExecSortMarkPos(GgPlanState *node) { if (node && node->done) node->markpos = node->next; }
+void GgExecSortRestrPos(GgPlanState *node) { if (node && node->done) node->next = node->markpos; }
 
 GgPlanState *GgExecInitMotion(GgMotion *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgMotion, estate, eflags); }
 GgTupleTableSlot *GgExecMotion(GgPlanState *node) { return GgExecProcNode(node); }
@@ -593,4 +1062,48 @@ int GgExecReScanMotion(GgPlanState *node) { return GgExecReScan(node); }
 void GgExecSquelchMotion(GgPlanState *node) { GgExecSquelchNode(node); }
 
 GgPlanState *GgExecInitHashJoin(GgHashJoin *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgHashJoin, estate, eflags); }
+GgTupleTableSlot *GgExecHashJoin(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndHashJoin(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanHashJoin(GgPlanState *node) { return GgExecReScan(node); }
+void GgExecSquelchHashJoin(GgPlanState *node) { GgExecSquelchNode(node); }
+
 GgPlanState *GgExecInitSeqScan(GgSeqScan *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgSeqScan, estate, eflags); }
+GgPlanState *GgExecInitSeqScanForPartition(GgSeqScan *node, GgEState *estate, int eflags, gg_relation *part)
+{
+	/* nodeSeqscan.c:221: the same scan over one partition's relation instead of the one the plan names */
+	GgPlanState *s;
+	gg_relation *saved;
+	if (!node || !estate || node->scanrelid < 0 || node->scanrelid >= GG_MAX_RELATIONS || !part) return exec_fail(GG_ERR_ARG, "bad partition scan");
+	saved = estate->relations[node->scanrelid];
+	estate->relations[node->scanrelid] = part;
+	s = init_tagged(&node->plan, T_GgSeqScan, estate, eflags);
+	estate->relations[node->scanrelid] = saved;
+	return s;
+}
+GgTupleTableSlot *GgExecSeqScan(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndSeqScan(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanSeqScan(GgPlanState *node) { return GgExecReScan(node); }
+
+GgPlanState *GgExecInitHash(GgHash *node, GgEState *estate, int eflags) { return init_tagged(&node->plan, T_GgHash, estate, eflags); }
+void *GgMultiExecHash(GgPlanState *node) { return GgMultiExecProcNode(node); }
+GgTupleTableSlot *GgExecHash(GgPlanState *node) { return GgExecProcNode(node); }
+void GgExecEndHash(GgPlanState *node) { GgExecEndNode(node); }
+int GgExecReScanHash(GgPlanState *node) { return node ? GG_OK : GG_ERR_ARG; }
+
+/* ---- the interconnect entry of the reference's per-type table (cdbinterconnect.h:500-533) ---- */
+static int nccl_setup(GgEState *estate, const void *unique_id)
+{
+	if (!estate || estate->interconnect) return GG_ERR_ARG;
+	return gg_ic_create(estate->engine, unique_id, estate->nsegs > 0 ? estate->nsegs : 1, estate->segindex, &estate->interconnect);
+}
+
+static void nccl_teardown(GgEState *estate, int hasErrors)
+{
+	if (!estate || !estate->interconnect) return;
+	gg_ic_teardown(estate->interconnect, hasErrors);
+	estate->interconnect = NULL;
+}
+
+const GgInterconnectOps GgInterconnectNCCL = {
+	nccl_setup, nccl_teardown, gg_ic_motion_groups, gg_ic_exchange_rows, gg_ic_exchange_host
+};

@@ -44,9 +44,6 @@ typedef enum GgMotionType {         /* plannodes.h MotionType */
 	GG_MOTIONTYPE_BROADCAST = 2
 } GgMotionType;
 
-#define GG_MAX_SORTKEYS 4
-#define GG_MAX_OUTCOLS (GG_MAX_KEYS + 3 * GG_MAX_AGGS)
-
 /* Plan nodes (plannodes.h Plan and friends) */
 typedef struct GgPlan {
 	GgNodeTag type;
@@ -55,10 +52,19 @@ typedef struct GgPlan {
 	int32_t qual;                   /* implicit-AND qual folded into one expression root, -1 = none */
 } GgPlan;
 
+#define GG_MAX_SORTKEYS 4
+#define GG_MAX_OUTCOLS (GG_MAX_KEYS + 3 * GG_MAX_AGGS)
+
 typedef struct GgSeqScan {
 	GgPlan plan;
 	int32_t scanrelid;              /* index into GgEState.relations */
 	gg_tupdesc desc;
+	/* plan.targetlist (plannodes.h Plan): the expressions the scan projects (ExecProject, execScan.c:194), roots in the pool.
+	 * 0 = the node above reads the relation's attributes directly (Agg <- SeqScan, HashJoin <- SeqScan: fused, nothing is
+	 * projected).  > 0: the scan (or the Motion above it) produces rows of these columns — device-resident datum rows — and
+	 * Vars of the nodes above refer to them by position. */
+	int32_t numTargets;
+	int32_t targets[GG_MAX_OUTCOLS];
 } GgSeqScan;
 
 typedef struct GgAgg {
@@ -130,14 +136,22 @@ typedef struct GgEState {
 	const gg_exprpool *pool;
 	gg_relation *relations[GG_MAX_RELATIONS];   /* scanrelid -> heap pages resident on the device */
 	int32_t nsegs, segindex;                    /* GpIdentity.numsegments / segindex */
-	GgMotionTransport *transport;               /* NULL: loopback (nsegs must be 1) */
+	GgMotionTransport *transport;               /* host-row transport callback (tests over gloo); NULL: none */
 	uint64_t es_processed;                      /* rows the top node has returned */
+	/* the interconnect of this query (es_interconnect_is_setup / interconnect_context, execnodes.h:420): Motion nodes move
+	 * device-resident batches through it (gg_ic_*, NCCL); with neither this nor `transport`, nsegs must be 1 */
+	gg_interconnect *interconnect;
+	/* a relation whose pages are in HOST memory (the segment's shared buffers): relations[i] == NULL and host_pages[i] set —
+	 * the scan streams them to the device (gg_scanagg_run_host), H2D overlapped with the kernel */
+	const void *host_pages[GG_MAX_RELATIONS];
+	uint64_t host_nblocks[GG_MAX_RELATIONS];
 } GgEState;
 
 typedef struct GgPlanState GgPlanState;        /* execnodes.h PlanState */
 
 GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags);
 GgTupleTableSlot *GgExecProcNode(GgPlanState *node);
+void *GgMultiExecProcNode(GgPlanState *node);     /* execProcnode.c:1217: only a Hash node answers (with NULL: the table lives in the join's pipeline) */
 void GgExecEndNode(GgPlanState *node);
 int  GgExecReScan(GgPlanState *node);
 void GgExecSquelchNode(GgPlanState *node);
@@ -168,8 +182,42 @@ GgTupleTableSlot *GgExecMotion(GgPlanState *node);
 void GgExecEndMotion(GgPlanState *node);
 int  GgExecReScanMotion(GgPlanState *node);
 void GgExecSquelchMotion(GgPlanState *node);
+void GgExecSortMarkPos(GgPlanState *node);      /* nodeSort.c:444 ExecSortMarkPos */
+void GgExecSortRestrPos(GgPlanState *node);     /* nodeSort.c:462 ExecSortRestrPos */
 GgPlanState *GgExecInitHashJoin(GgHashJoin *node, GgEState *estate, int eflags);
+GgTupleTableSlot *GgExecHashJoin(GgPlanState *node);
+void GgExecEndHashJoin(GgPlanState *node);
+int  GgExecReScanHashJoin(GgPlanState *node);
+void GgExecSquelchHashJoin(GgPlanState *node);
+/* nodeSeqscan.h:19-24.  A SeqScan with a target list produces device-resident rows; returned as slots at the top of a slice */
 GgPlanState *GgExecInitSeqScan(GgSeqScan *node, GgEState *estate, int eflags);
+GgPlanState *GgExecInitSeqScanForPartition(GgSeqScan *node, GgEState *estate, int eflags, gg_relation *part);   /* nodeSeqscan.c:221 */
+GgTupleTableSlot *GgExecSeqScan(GgPlanState *node);
+void GgExecEndSeqScan(GgPlanState *node);
+int  GgExecReScanSeqScan(GgPlanState *node);
+/* nodeHash.h:23-27.  The Hash node has no pipeline of its own — MultiExecHash is the build kernel the join's pipeline
+ * launches — so its state is a marker whose entry points say so the way the reference's do (ExecHash always ERRORs). */
+GgPlanState *GgExecInitHash(GgHash *node, GgEState *estate, int eflags);
+void *GgMultiExecHash(GgPlanState *node);
+GgTupleTableSlot *GgExecHash(GgPlanState *node);
+void GgExecEndHash(GgPlanState *node);
+int  GgExecReScanHash(GgPlanState *node);
+
+/* The interconnect as the reference selects it: a table of entry points per GpVars_Interconnect_Type
+ * (cdbinterconnect.h:500-533, ic_common.c:522-575; UDPIFC / TCP / proxy there).  This is the NCCL entry: a 4th value of
+ * that enum would install it. */
+typedef struct GgInterconnectOps {
+	int  (*SetupInterconnect)(GgEState *estate, const void *unique_id);       /* ic_common.c:522 */
+	void (*TeardownInterconnect)(GgEState *estate, int hasErrors);            /* ic_common.c:560 */
+	/* SendChunk + SendEos of a whole batch (cdbinterconnect.h:525,529): group records / datum rows / host rows */
+	int  (*SendRecvGroups)(gg_interconnect *ic, int motionType, int root, int nhash, const int32_t *hashcol, const int32_t *hashtypid,
+	                       gg_groups *in, gg_groups **out);
+	int  (*SendRecvRows)(gg_interconnect *ic, const void *send_rows, const uint64_t *counts, uint64_t region_cap, int rowwords,
+	                     void *recv_rows, uint64_t recv_cap, uint64_t *nrecv);
+	int  (*SendRecvHostRows)(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *values, const uint8_t *isnull,
+	                         const int32_t *dest, int my_error, int64_t *out_nrows, int64_t **out_values, uint8_t **out_isnull);
+} GgInterconnectOps;
+extern const GgInterconnectOps GgInterconnectNCCL;
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ extern "C" {
 #define GG_ERR_BADPAGE         (-9)    /* page header fails the PageAddItem sanity rules (bufpage.c:196-204) */
 #define GG_ERR_ARG             (-10)
 #define GG_ERR_DATE_RANGE      (-11)   /* "date out of range for timestamp", date.c:471 */
+#define GG_ERR_PEER            (-12)   /* another segment of the Motion reported an ERROR (the QD cancels the query) */
 
 typedef struct gg_engine   gg_engine;     /* one GPU segment: device, streams, scratch */
 typedef struct gg_relation gg_relation;   /* heap pages resident in HBM (replaces bufmgr/smgr for the scan) */
@@ -167,6 +168,57 @@ int  gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *p
                          int nsegs, gg_relation *r, uint64_t first_block, uint64_t nblocks,
                          void *device_out_rows, uint64_t out_cap_rows,
                          uint64_t *host_counts, uint64_t *host_offsets);
+
+/* ---- device-resident aggregate rows ----
+ * The rows an Agg pipeline produced, left on the device as group records so that the nodes above it in the slice
+ * (Motion, FINAL Agg) consume them there; only the top of the slice fetches.  A gg_groups
+ * obtained from a pipeline is a view: valid until that pipeline is reset or freed. */
+typedef struct gg_groups gg_groups;
+int  gg_scanagg_groups(gg_scanagg *p, gg_groups **out);      /* GG_ERR_UNSUPPORTED for the general HashAggregate: fetch rows */
+int  gg_joinagg_groups(gg_joinagg *p, gg_groups **out);
+/* FINAL-stage Agg over records a Motion delivered: the combine functions (nodeAgg.c:2123-2148) on the device */
+int  gg_groups_final(gg_engine *e, gg_groups *in, gg_groups **out);
+/* records + status -> rows: the one host synchronisation of a device-resident slice.  Rows read as the producing Agg's
+ * stage says (PARTIAL: transition states; otherwise finalised values). */
+int  gg_groups_fetch(gg_groups *g, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_scanned, uint64_t *rows_passed);
+int  gg_groups_info(gg_groups *g, int *sparse, int *cap);
+void gg_groups_set_nonreceiver(gg_groups *g);
+void gg_groups_free(gg_groups *g);
+
+/* ---- Interconnect: the Motion layer over NCCL ----
+ * Replaces SetupInterconnect / TeardownInterconnect and the ChunkTransportState vtable of the UDP interconnect
+ * (cdb/cdbinterconnect.h:500-533, cdb/motion/ic_common.c:522,560, cdbmotion.c:434,559) for GPU segments: one NCCL
+ * communicator per query, rank = contentid, whole device-resident batches instead of tuple chunks.  The unique id is
+ * what the dispatcher would ship in the slice table next to the listener addresses (cdbgang.h:121-137). */
+typedef struct gg_interconnect gg_interconnect;
+#define GG_IC_UNIQUE_ID_BYTES 128
+#define GG_IC_MOTION_GATHER    0          /* = GgMotionType */
+#define GG_IC_MOTION_HASH      1
+#define GG_IC_MOTION_BROADCAST 2
+int  gg_ic_available(void);                                   /* libnccl could be loaded */
+int  gg_ic_unique_id(void *out, int len);                     /* on one segment (the QD's choice); len >= GG_IC_UNIQUE_ID_BYTES */
+int  gg_ic_create(gg_engine *e, const void *unique_id, int nsegs, int segindex, gg_interconnect **out);   /* nsegs == 1: loopback, no NCCL */
+void gg_ic_teardown(gg_interconnect *ic, int has_errors);     /* has_errors: ncclCommAbort instead of waiting for peers */
+void gg_ic_free(gg_interconnect *ic);
+int  gg_ic_nsegs(gg_interconnect *ic);
+int  gg_ic_segindex(gg_interconnect *ic);
+uint64_t gg_ic_collective_count(gg_interconnect *ic);
+/* every segment contributes one word and learns everybody's (also a barrier on the engine's stream) */
+int  gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all);
+/* Motion of aggregate rows, device to device.  hashcol[] index the grouping columns of the rows, hashtypid[] their type
+ * OIDs; routing is cdbhash + jump consistent hash, bit-exact with cdbhash.c:191-287.  The status (ERROR flags) of every
+ * sender reaches every receiver with the data. */
+int  gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhash, const int32_t *hashcol,
+                         const int32_t *hashtypid, gg_groups *in, gg_groups **out);
+/* Redistribute of datum rows: the all-to-all-v behind gg_motion_partition (send_rows = its regions, counts = its host_counts,
+ * region_cap = out_cap_rows / nsegs rounded down to even).  recv_rows: device buffer of recv_cap rows (16-byte aligned,
+ * 16 bytes of slack for gg_relation_attach_rows).  GG_ERR_NOMEM (on every segment) if any receive buffer is too small. */
+int  gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64_t *counts, uint64_t region_cap, int rowwords,
+                         void *recv_rows, uint64_t recv_cap, uint64_t *nrecv);
+/* Motion of host rows (the executor's generic path): dest[i] = receiving segment, -1 = all.  out_* are malloc'd.
+ * my_error != 0: this segment's slice failed — it takes part with no rows and EVERY segment returns GG_ERR_PEER. */
+int  gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *values, const uint8_t *isnull,
+                         const int32_t *dest, int my_error, int64_t *out_nrows, int64_t **out_values, uint8_t **out_isnull);
 
 #ifdef __cplusplus
 }

@@ -6,10 +6,11 @@ import csv, io, os, re, subprocess, sys, tempfile, collections
 
 rep, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kname, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
+rows = rows[:hdr_i + 1] + [r for r in rows[hdr_i + 1:] if r and r[0] != "Address"]
 ci = hdr.index("Instructions Executed")
 si = hdr.index("# Samples") if "# Samples" in hdr else None
 sass_counts = [(r[1].strip(), int(r[ci] or 0), int(r[si] or 0) if si is not None else 0) for r in rows[hdr_i + 1:] if len(r) > ci]

@@ -122,3 +122,37 @@ int gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, con
 	(void) e;
 	return fail(or_sort_perm(keys, nkeys, ncols, host_rows, host_nulls, n, host_perm), "mock: or_sort_perm failed");
 }
+
+/* device-resident results and the NCCL interconnect have no stand-in: the executor falls back to host rows and to the
+ * transport callback, which is what these tests exercise */
+static int unsupported(void) { return fail(GG_ERR_UNSUPPORTED, "mock: no device-resident results"); }
+int gg_scanagg_groups(gg_scanagg *p, gg_groups **out) { (void) p; *out = NULL; return unsupported(); }
+int gg_joinagg_groups(gg_joinagg *p, gg_groups **out) { (void) p; *out = NULL; return unsupported(); }
+int gg_groups_final(gg_engine *e, gg_groups *in, gg_groups **out) { (void) e; (void) in; *out = NULL; return unsupported(); }
+int gg_groups_fetch(gg_groups *g, gg_aggrow *out, int outcap, int *nout, uint64_t *a, uint64_t *b)
+{ (void) g; (void) out; (void) outcap; (void) nout; (void) a; (void) b; return unsupported(); }
+void gg_groups_set_nonreceiver(gg_groups *g) { (void) g; }
+void gg_groups_free(gg_groups *g) { (void) g; }
+int gg_ic_create(gg_engine *e, const void *id, int nsegs, int seg, gg_interconnect **out) { (void) e; (void) id; (void) nsegs; (void) seg; *out = NULL; return unsupported(); }
+void gg_ic_teardown(gg_interconnect *ic, int has_errors) { (void) ic; (void) has_errors; }
+int gg_ic_motion_groups(gg_interconnect *ic, int t, int root, int nhash, const int32_t *hc, const int32_t *ht, gg_groups *in, gg_groups **out)
+{ (void) ic; (void) t; (void) root; (void) nhash; (void) hc; (void) ht; (void) in; *out = NULL; return unsupported(); }
+int gg_ic_exchange_rows(gg_interconnect *ic, const void *s, const uint64_t *c, uint64_t rc, int w, void *r, uint64_t cap, uint64_t *n)
+{ (void) ic; (void) s; (void) c; (void) rc; (void) w; (void) r; (void) cap; (void) n; return unsupported(); }
+int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *v, const uint8_t *nl, const int32_t *d, int err,
+                        int64_t *on, int64_t **ov, uint8_t **onl)
+{ (void) ic; (void) ncols; (void) nrows; (void) v; (void) nl; (void) d; (void) err; (void) on; (void) ov; (void) onl; return unsupported(); }
+int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
+{
+	if (p->fed) return fail(GG_ERR_ARG, "mock: one run per accumulation");
+	p->pages = host_pages; p->nblocks = nblocks; p->fed = 1;
+	return GG_OK;
+}
+int gg_relation_create(gg_engine *e, uint64_t nblocks, gg_relation **out) { (void) e; (void) nblocks; *out = NULL; return unsupported(); }
+int gg_relation_attach_rows(gg_engine *e, void *rows, uint64_t nrows, int ncols, gg_relation **out) { (void) e; (void) rows; (void) nrows; (void) ncols; *out = NULL; return unsupported(); }
+int gg_relation_read(gg_relation *r, uint64_t first, void *host, uint64_t n) { (void) r; (void) first; (void) host; (void) n; return unsupported(); }
+void *gg_relation_device_ptr(gg_relation *r) { (void) r; return NULL; }
+void gg_relation_free(gg_relation *r) { free(r); }
+int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool, const int32_t *hk, int nk, const int32_t *pl, int np,
+                        int nsegs, gg_relation *r, uint64_t fb, uint64_t nb, void *out, uint64_t cap, uint64_t *hc, uint64_t *ho)
+{ (void) e; (void) scan; (void) pool; (void) hk; (void) nk; (void) pl; (void) np; (void) nsegs; (void) r; (void) fb; (void) nb; (void) out; (void) cap; (void) hc; (void) ho; return unsupported(); }

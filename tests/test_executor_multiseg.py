@@ -60,6 +60,33 @@ def _worker(rank, world, port, mock, case, q):
         if case == "single":
             q.put(("ok", rank, "single", single_segment_checks(L, eng, ex), None, 0))
             return
+        if case in ("fail", "squelch", "plainfinal"):
+            # one segment's slice fails / one segment stops before its first row / a plain FINAL aggregate above a Gather
+            spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 20000, nsegs=world, seg=rank)
+            pages, nb, nr = tpch.synth_generate(spec, nthreads=1)
+            if case == "fail" and rank == 1:
+                pages = pages.copy()
+                pages[12:16] = 0xFF                                   # pd_lower / pd_upper of the first page: PageAddItem's sanity rules fail
+            if case == "plainfinal":
+                scan, agg, pool = tpch.count_star_plan(capi.TAB_LINEITEM_WIDE, capi.AGGSTAGE_PARTIAL)
+                fin = capi.gg_agg.from_buffer_copy(bytes(agg))
+                fin.aggstage = capi.AGGSTAGE_FINAL
+                plan = b.agg(b.motion(b.agg(b.seqscan(0, scan.desc, scan.qual), agg), ex.MOTION_GATHER, [], 1), fin)
+            else:
+                from test_gpu_executor import q1_sorted_plan
+                scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_WIDE)
+                plan = q1_sorted_plan(b, scan, agg, True)
+            x = ex.Executor(eng, pool, [MockRel(L, pages)], plan, nsegs=world, segindex=rank, transport=tr)
+            try:
+                rows = x.rows(limit=0) if (case == "squelch" and rank == 0) else x.rows()
+                outcome = ("rows", len(rows), [r[0] for r in rows])
+            except ex.ExecError as e:
+                outcome = ("error", e.code, str(e))
+            x.end()
+            q.put(("ok", rank, "ctl", outcome, None, nr))
+            if dist is not None:
+                dist.destroy_process_group()
+            return
         if case == "q1":
             from test_gpu_executor import q1_sorted_plan
             spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 60000, nsegs=world, seg=rank)
@@ -251,3 +278,27 @@ def test_node_surface_control_flow_on_one_segment(tmp_path):
     plan — tests/test_gpu_executor.py's checks with the oracle behind the C-ABI, in a child process"""
     by = run(1, "single", tmp_path)
     assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "motion-needs-transport", "malformed-trees-refused"]
+
+
+def test_a_failing_segment_does_not_leave_its_peers_in_the_exchange(tmp_path):
+    """One segment's scan hits a corrupted page.  It still enters the Motion (with no rows and its status), so the other
+    segment is not left waiting in a collective, and BOTH come back with an error: the failing one with its own, the peer
+    with GG_ERR_PEER (the reference: error propagation + SendStopMessage, cdbmotion.c:342, nodeMotion.c:1730)."""
+    by = run(2, "fail", tmp_path)
+    assert by[1][3][0] == "error" and by[1][3][1] not in (0, -12)          # its own error, not the peer notice
+    assert by[0][3][0] == "error" and by[0][3][1] == -12
+
+
+def test_a_segment_squelched_before_its_first_row_still_takes_part(tmp_path):
+    """LIMIT 0 on segment 0: ExecSquelchNode reaches a Motion that has not run — it runs (the peers are in the exchange) and
+    then hands out nothing; segment 1 finishes normally"""
+    by = run(2, "squelch", tmp_path)
+    assert by[0][3] == ("rows", 0, []) and by[1][3][0] == "rows"
+
+
+def test_plain_final_aggregate_above_a_gather_yields_its_row_on_the_receiver_only(tmp_path):
+    """Agg(FINAL, no keys) <- Gather <- Agg(PARTIAL): the slice above a Gather exists on the receiving segment only
+    (nodeMotion.c:1036-1053); a non-receiving segment must not synthesise the empty-input row count = 0"""
+    by = run(2, "plainfinal", tmp_path)
+    assert by[0][3][0] == "rows" and by[0][3][1] == 1 and by[0][3][2][0][0] == by[0][5] + by[1][5]
+    assert by[1][3] == ("rows", 0, [])
