@@ -180,6 +180,7 @@ def dev_lib():
         L.gg_relation_attach.argtypes = [vp, vp, u64, C.POINTER(vp)]
         L.gg_relation_load.argtypes = [vp, u64, vp, u64]
         L.gg_relation_read.argtypes = [vp, u64, vp, u64]
+        L.gg_relation_count_rows.argtypes = [vp, C.POINTER(u64)]
         L.gg_relation_nblocks.argtypes = [vp]
         L.gg_relation_nblocks.restype = u64
         L.gg_relation_device_ptr.argtypes = [vp]
@@ -210,6 +211,30 @@ def dev_lib():
         L.gg_sort_rows.argtypes = [vp, C.POINTER(gg_sortkey), i32, i32, vp, vp, u64, vp]
         L.gg_sort_device.argtypes = [vp, C.POINTER(gg_sortkey), i32, i32, vp, vp, u64, vp, C.POINTER(i32)]
         L.gg_relation_attach_rows.argtypes = [vp, vp, u64, i32, C.POINTER(vp)]
+        # device-resident aggregate rows and the NCCL interconnect
+        L.gg_scanagg_groups.argtypes = [vp, C.POINTER(vp)]
+        L.gg_joinagg_groups.argtypes = [vp, C.POINTER(vp)]
+        L.gg_groups_final.argtypes = [vp, vp, C.POINTER(vp)]
+        L.gg_groups_fetch.argtypes = [vp, C.POINTER(gg_aggrow), i32, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)]
+        L.gg_groups_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.gg_groups_set_nonreceiver.argtypes = [vp]
+        L.gg_groups_set_nonreceiver.restype = None
+        L.gg_groups_free.argtypes = [vp]
+        L.gg_groups_free.restype = None
+        L.gg_ic_unique_id.argtypes = [vp, i32]
+        L.gg_ic_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+        L.gg_ic_teardown.argtypes = [vp, i32]
+        L.gg_ic_teardown.restype = None
+        L.gg_ic_free.argtypes = [vp]
+        L.gg_ic_free.restype = None
+        L.gg_ic_nsegs.argtypes = [vp]
+        L.gg_ic_segindex.argtypes = [vp]
+        L.gg_ic_collective_count.argtypes = [vp]
+        L.gg_ic_collective_count.restype = u64
+        L.gg_ic_allgather_u64.argtypes = [vp, u64, C.POINTER(u64)]
+        L.gg_ic_motion_groups.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, i32, C.POINTER(vp)]
+        L.gg_ic_exchange_rows.argtypes = [vp, vp, C.POINTER(u64), u64, i32, vp, u64, C.POINTER(u64)]
+        L.gg_ic_exchange_host.argtypes = [vp, i32, C.c_int64, vp, vp, vp, i32, C.POINTER(C.c_int64), C.POINTER(vp), C.POINTER(vp)]
         L.gg_motion_partition.argtypes = [vp, C.POINTER(gg_scan), C.POINTER(gg_exprpool), C.POINTER(C.c_int32), i32,
                                           C.POINTER(C.c_int32), i32, i32, vp, u64, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         _dev = L

@@ -38,6 +38,8 @@ int gg_errflags_to_code(uint32_t f)
 	if (f & GGP_EF_INT_OVERFLOW) { gg_set_error("bigint out of range"); return GG_ERR_INT_OVERFLOW; }
 	if (f & GGP_EF_DATE_RANGE) { gg_set_error("date out of range for timestamp"); return GG_ERR_DATE_RANGE; }
 	if (f & GGP_EF_STRING_TOO_LONG) { gg_set_error("string value longer than 8 bytes (or toasted) in a GPU expression"); return GG_ERR_UNSUPPORTED; }
+	if (f & GGP_EF_PEER_FAILED) { gg_set_error("another segment reported an error in its slice below the Motion"); return GG_ERR_PEER; }
+	if (f & GGP_EF_HOSTPATH) { gg_set_error("a segment could not keep its aggregate rows on the device: run the slice with host-row Motions"); return GG_ERR_RETRY_HOST; }
 	if (f & GGP_EF_GROUP_OVERFLOW) { gg_set_error("more groups than the GPU aggregate holds"); return GG_ERR_UNSUPPORTED; }
 	if (f & GGP_EF_TABLE_FULL) { gg_set_error("hash table full"); return GG_ERR_NOMEM; }
 	gg_set_error("device error flags 0x%x", f);
@@ -65,6 +67,7 @@ const char *gg_strerror(int code)
 		case GG_ERR_ARG: return "bad argument";
 		case GG_ERR_DATE_RANGE: return "date out of range for timestamp";
 		case GG_ERR_PEER: return "another segment reported an error";
+		case GG_ERR_RETRY_HOST: return "run the slice again with host-row Motions";
 	}
 	return "unknown error";
 }

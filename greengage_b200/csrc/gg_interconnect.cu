@@ -108,22 +108,26 @@ struct gg_interconnect {
 /* ---------------- kernels ---------------- */
 
 /* pipeline result -> the block that travels */
-__global__ void gg_ic_pack_groups_kernel(const ggp_grec *recs, const int *d_n, const gg_groupstatus *st, int sparse, int cap, GroupBlock *dst)
+__global__ void gg_ic_pack_groups_kernel(const ggp_grec *recs, const int *d_n, const gg_groupstatus *st, int sparse, int cap,
+                                         uint32_t local_flags, GroupBlock *dst)
 {
 	__shared__ int s_n;
 	if (threadIdx.x == 0)
 	{
 		int n = 0;
-		if (sparse) { for (int i = 0; i < cap; i++) n += recs[i].valid ? 1 : 0; }
+		if (!recs) n = 0;                                   /* nothing to send: the status is the message */
+		else if (sparse) { for (int i = 0; i < cap; i++) n += recs[i].valid ? 1 : 0; }
 		else n = *d_n;
-		s_n = n;
-		dst->n = (uint32_t) n;
-		dst->err = st->err | (n > GG_IC_GROUP_CAP ? GGP_EF_GROUP_OVERFLOW : 0u);
-		dst->counters[0] = st->counters[0];
-		dst->counters[1] = st->counters[1];
+		/* more records than a block carries: none travel, and everybody learns that this Motion has to take the host path */
+		const bool over = n > GG_IC_GROUP_CAP;
+		s_n = over ? GG_IC_GROUP_CAP + 1 : n;
+		dst->n = over ? 0u : (uint32_t) n;
+		dst->err = (st ? st->err : 0u) | local_flags | (over ? GGP_EF_HOSTPATH : 0u);
+		dst->counters[0] = st ? st->counters[0] : 0ull;
+		dst->counters[1] = st ? st->counters[1] : 0ull;
 	}
 	__syncthreads();
-	if (s_n > GG_IC_GROUP_CAP) return;
+	if (!recs || s_n > GG_IC_GROUP_CAP) return;
 	/* copy word-wise; a sparse source is compacted in slot order (deterministic) */
 	const int W = (int) (sizeof(ggp_grec) / 8);
 	if (!sparse)
@@ -312,10 +316,27 @@ int gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all /* [ns
 /* Motion of group records, device to device: the sending half (execMotionSender, nodeMotion.c:270-374) packs the
  * pipeline's result into this segment's block, the all-gather is the interconnect, the receiving half
  * (execMotionUnsortedReceiver, :378) keeps what is routed here. */
-int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhash, const int32_t *hashcol,
-                        const int32_t *hashtypid, gg_groups *in, gg_groups **out)
+static uint32_t errflag_of_code(int code)
 {
-	if (!ic || !in || !out || nhash < 0 || nhash > GG_MAX_KEYS || (nhash && (!hashcol || !hashtypid))) return GG_ERR_ARG;
+	switch (code)
+	{
+		case GG_OK: return 0;
+		case GG_ERR_FLOAT_OVERFLOW: return GGP_EF_FLOAT_OVERFLOW;
+		case GG_ERR_FLOAT_UNDERFLOW: return GGP_EF_FLOAT_UNDERFLOW;
+		case GG_ERR_DIV_ZERO: return GGP_EF_DIV_ZERO;
+		case GG_ERR_INT_OVERFLOW: return GGP_EF_INT_OVERFLOW;
+		case GG_ERR_VISIBILITY: return GGP_EF_VISIBILITY;
+		case GG_ERR_BADPAGE: return GGP_EF_BADPAGE;
+		case GG_ERR_DATE_RANGE: return GGP_EF_DATE_RANGE;
+		case GG_ERR_RETRY_HOST: return GGP_EF_HOSTPATH;
+	}
+	return GGP_EF_PEER_FAILED;
+}
+
+int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhash, const int32_t *hashcol,
+                        const int32_t *hashtypid, gg_groups *in, int local_error, gg_groups **out)
+{
+	if (!ic || !out || nhash < 0 || nhash > GG_MAX_KEYS || (nhash && (!hashcol || !hashtypid))) return GG_ERR_ARG;
 	if (motion_type != GG_IC_MOTION_HASH && motion_type != GG_IC_MOTION_GATHER && motion_type != GG_IC_MOTION_BROADCAST) return GG_ERR_ARG;
 	if (motion_type == GG_IC_MOTION_HASH && nhash < 1) return GG_ERR_ARG;
 	if (root < 0 || root >= ic->nsegs) return GG_ERR_ARG;
@@ -328,7 +349,7 @@ int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhas
 	spec.nhash = nhash;
 	for (int k = 0; k < nhash; k++)
 	{
-		if (hashcol[k] < 0 || hashcol[k] >= in->nkeys)
+		if (hashcol[k] < 0 || (in && hashcol[k] >= in->nkeys))
 		{ gg_set_error("Motion hash column %d is not a grouping column of the rows below", hashcol[k]); return GG_ERR_UNSUPPORTED; }
 		spec.hashcol[k] = hashcol[k];
 		switch (hashtypid[k])
@@ -343,7 +364,9 @@ int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhas
 	}
 	gg_groups *g = gg_groups_alloc(e, in, ic->nsegs * GG_IC_GROUP_CAP, /*sparse*/ true);
 	if (!g) return GG_ERR_NOMEM;
-	gg_ic_pack_groups_kernel<<<1, 256, 0, st>>>(in->recs, in->d_n, in->d_status, in->sparse ? 1 : 0, in->cap, ic->d_send);
+	const uint32_t local_flags = in ? errflag_of_code(local_error) : (local_error != GG_OK ? errflag_of_code(local_error) : GGP_EF_HOSTPATH);
+	if (in) gg_ic_pack_groups_kernel<<<1, 256, 0, st>>>(in->recs, in->d_n, in->d_status, in->sparse ? 1 : 0, in->cap, local_flags, ic->d_send);
+	else gg_ic_pack_groups_kernel<<<1, 256, 0, st>>>(nullptr, nullptr, nullptr, 0, 0, local_flags, ic->d_send);
 	cudaError_t ce = cudaGetLastError();
 	e->launches++;
 	int rc = ce == cudaSuccess ? ic_allgather(ic, ic->d_send, ic->d_all, sizeof(GroupBlock)) : gg_cuda_fail(ce, "gg_ic_motion_groups");

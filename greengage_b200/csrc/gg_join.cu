@@ -77,6 +77,32 @@ int gg_probe_kernel_launch(gg_scanagg *p, const ScanAggParams &prm, cudaStream_t
 
 extern "C" {
 
+/* how many tuples a relation holds at most: line pointers of its heap pages (exact for a loaded relation without dead
+ * items), or the row count of datum rows.  Sizes Motion buffers and hash tables (ExecChooseHashTableSize sizes from the
+ * planner's estimate, nodeHash.c:463; the pages give a tight bound for one pass over their headers). */
+int gg_relation_count_rows(gg_relation *r, uint64_t *nrows)
+{
+	if (!r || !nrows) return GG_ERR_ARG;
+	if (r->rowwords) { *nrows = r->nrows; return GG_OK; }
+	gg_engine *e = r->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	unsigned long long *d = nullptr, n = 0;
+	GG_CUDA(cudaMalloc((void **) &d, sizeof n));
+	cudaError_t ce = cudaMemsetAsync(d, 0, sizeof n, e->stream);
+	if (ce == cudaSuccess)
+	{
+		gg_count_lp_kernel<<<e->sm_count, 256, 0, e->stream>>>(r->pages, r->nblocks, d);
+		ce = cudaGetLastError();
+		e->launches++;
+	}
+	if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n, d, sizeof n, cudaMemcpyDeviceToHost, e->stream);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+	cudaFree(d);
+	if (ce != cudaSuccess) return gg_cuda_fail(ce, "gg_relation_count_rows");
+	*nrows = n;
+	return GG_OK;
+}
+
 /* =====================================================================================
  * HashJoin + Agg (include/ggb200.h gg_joinagg_*)
  * ===================================================================================== */
@@ -278,6 +304,8 @@ int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes,
 	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
 	return GG_OK;
 }
+
+int gg_joinagg_variant(gg_joinagg *j) { return j ? gg_scanagg_variant(j->probe) : -1; }
 
 void gg_joinagg_free(gg_joinagg *j)
 {

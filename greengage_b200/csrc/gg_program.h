@@ -173,6 +173,10 @@ typedef struct ggp_grec {
 #define GGP_EF_TABLE_FULL       0x400
 #define GGP_EF_SAW_INF          0x800   /* informational: an aggregate input was +-Inf/NaN */
 #define GGP_EF_RECHECK          0x1000  /* a fast variant saw a non-finite sum: replay on the checked variant */
+#define GGP_EF_PEER_FAILED      0x2000  /* a segment's slice below a Motion failed with an error that has no flag of its own */
+#define GGP_EF_HOSTPATH         0x4000  /* a segment could not contribute device-resident records to a Motion (its aggregate
+                                         * spilled to the general hash table, or holds more groups than a block carries): every
+                                         * segment sees it and the slice is run again with host-row Motions */
 #define GGP_EF_INFO_MASK        (GGP_EF_SAW_INF | GGP_EF_RECHECK)
 
 /* how a Motion hash key is hashed (cdbhash.c:215-287: the type's default hash opclass function) */

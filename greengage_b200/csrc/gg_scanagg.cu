@@ -1163,7 +1163,6 @@ int gg_groups_fetch(gg_groups *g, gg_aggrow *out, int outcap, int *nout, uint64_
 	if (rows_scanned) *rows_scanned = hs->counters[0];
 	if (rows_passed) *rows_passed = hs->counters[1];
 	const uint32_t flags = hs->err;
-	if (flags & GGP_EF_GROUP_OVERFLOW) { gg_set_error("more group records on one segment than a device Motion block holds (%d)", GG_IC_GROUP_CAP); return GG_ERR_UNSUPPORTED; }
 	int rc = gg_errflags_to_code(flags);
 	if (rc) return rc;
 	std::vector<ggp_grec> recs;

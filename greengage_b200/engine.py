@@ -246,3 +246,78 @@ def agg_final(eng, agg, rows, cap=4096):
     n = C.c_int(0)
     check(dev_lib().gg_agg_final(eng.h, C.byref(agg), arr, len(rows), out, cap, C.byref(n)))
     return [out[i] for i in range(n.value)]
+
+
+class Groups:
+    """Aggregate rows left on the device as group records (gg_groups)."""
+
+    def __init__(self, eng, h):
+        self.eng, self.h = eng, h
+
+    @classmethod
+    def of(cls, pipeline):
+        h = C.c_void_p()
+        fn = dev_lib().gg_joinagg_groups if isinstance(pipeline, JoinAgg) else dev_lib().gg_scanagg_groups
+        check(fn(pipeline.h, C.byref(h)))
+        return cls(pipeline.eng, h)
+
+    def final(self):
+        """FINAL-stage combine on the device (gg_groups_final)"""
+        h = C.c_void_p()
+        check(dev_lib().gg_groups_final(self.eng.h, self.h, C.byref(h)))
+        return Groups(self.eng, h)
+
+    def fetch(self, cap=4096):
+        out = (capi.gg_aggrow * cap)()
+        n = C.c_int(0)
+        sc, ps = C.c_uint64(0), C.c_uint64(0)
+        check(dev_lib().gg_groups_fetch(self.h, out, cap, C.byref(n), C.byref(sc), C.byref(ps)))
+        return [out[i] for i in range(n.value)], sc.value, ps.value
+
+    def free(self):
+        if self.h:
+            dev_lib().gg_groups_free(self.h)
+            self.h = C.c_void_p()
+
+
+class Interconnect:
+    """The Motion layer over NCCL (gg_interconnect): one communicator per query, rank = segment.  `unique_id` is the
+    128 bytes one segment obtained from Interconnect.unique_id() and handed to the others (the dispatcher's job)."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        check(dev_lib().gg_ic_unique_id(buf, 128))
+        return buf.raw
+
+    def __init__(self, eng, nsegs=1, segindex=0, unique_id=None):
+        self.eng, self.nsegs, self.segindex = eng, nsegs, segindex
+        self.h = C.c_void_p()
+        uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(dev_lib().gg_ic_create(eng.h, uid, nsegs, segindex, C.byref(self.h)))
+
+    def allgather_u64(self, mine):
+        out = (C.c_uint64 * self.nsegs)()
+        check(dev_lib().gg_ic_allgather_u64(self.h, int(mine), out))
+        return list(out)
+
+    def collective_count(self):
+        return dev_lib().gg_ic_collective_count(self.h)
+
+    def motion_groups(self, groups, motion_type, hashcols=(), hashtypids=(), root=0):
+        h = C.c_void_p()
+        hc = (C.c_int32 * max(len(hashcols), 1))(*hashcols)
+        ht = (C.c_int32 * max(len(hashtypids), 1))(*hashtypids)
+        check(dev_lib().gg_ic_motion_groups(self.h, motion_type, root, len(hashcols), hc, ht, groups.h if groups is not None else None, 0, C.byref(h)))
+        return Groups(self.eng, h)
+
+    def exchange_rows(self, send_ptr, counts, region_cap, rowwords, recv_ptr, recv_cap):
+        n = C.c_uint64(0)
+        ca = (C.c_uint64 * len(counts))(*counts)
+        check(dev_lib().gg_ic_exchange_rows(self.h, C.c_void_p(send_ptr), ca, region_cap, rowwords, C.c_void_p(recv_ptr), recv_cap, C.byref(n)))
+        return n.value
+
+    def close(self, has_errors=False):
+        if self.h:
+            dev_lib().gg_ic_teardown(self.h, 1 if has_errors else 0)
+            self.h = C.c_void_p()

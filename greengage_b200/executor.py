@@ -74,7 +74,8 @@ class GgEState(C.Structure):
     _fields_ = [("engine", C.c_void_p), ("pool", C.POINTER(capi.gg_exprpool)), ("relations", C.c_void_p * GG_MAX_RELATIONS),
                 ("nsegs", C.c_int32), ("segindex", C.c_int32), ("transport", C.POINTER(GgMotionTransport)),
                 ("es_processed", C.c_uint64), ("interconnect", C.c_void_p),
-                ("host_pages", C.c_void_p * GG_MAX_RELATIONS), ("host_nblocks", C.c_uint64 * GG_MAX_RELATIONS)]
+                ("host_pages", C.c_void_p * GG_MAX_RELATIONS), ("host_nblocks", C.c_uint64 * GG_MAX_RELATIONS),
+                ("motion_on_host", C.c_int32), ("pad", C.c_int32)]
 
 
 _lib = None
@@ -107,6 +108,13 @@ def bind(L):
     L.GgExecLastErrorCode.restype = C.c_int
     L.GgExecNodeKind.restype = C.c_char_p
     L.GgExecNodeKind.argtypes = [C.c_void_p]
+    L.GgExecNodeResultLocation.restype = C.c_char_p
+    L.GgExecNodeResultLocation.argtypes = [C.c_void_p]
+    L.GgExecPipelineKernelMs.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    L.GgExecOuterPlanState.restype = C.c_void_p
+    L.GgExecOuterPlanState.argtypes = [C.c_void_p]
+    L.GgExecInnerPlanState.restype = C.c_void_p
+    L.GgExecInnerPlanState.argtypes = [C.c_void_p]
     return L
 
 
@@ -202,6 +210,32 @@ class Executor:
 
     def kind(self):
         return exec_lib().GgExecNodeKind(self.state).decode()
+
+    def locations(self):
+        """[(node kind, where its result lives)] from the top node down the outer children"""
+        L = exec_lib()
+        out, st = [], self.state
+        while st:
+            out.append((L.GgExecNodeKind(st).decode(), L.GgExecNodeResultLocation(st).decode()))
+            st = L.GgExecOuterPlanState(st)
+        return out
+
+    def kernel_ms(self):
+        """(scan/probe kernel ms since the last rescan, launches, kernel variant, join build ms) of the slice's pipeline"""
+        ms, n, v, b = C.c_float(0), C.c_int(0), C.c_int(0), C.c_float(0)
+        capi.check(exec_lib().GgExecPipelineKernelMs(self.state, C.byref(ms), C.byref(n), C.byref(v), C.byref(b)))
+        return ms.value, n.value, v.value, b.value
+
+    def drain(self):
+        """ExecProcNode to end of stream without building Python rows; returns the row count (benchmarks)"""
+        L = exec_lib()
+        n = 0
+        while L.GgExecProcNode(self.state):
+            n += 1
+        code = L.GgExecLastErrorCode()
+        if code:
+            raise ExecError(code, L.GgExecLastError().decode("utf-8", "replace"))
+        return n
 
     def rows(self, limit=None):
         """[(values, isnull, typids, lens)] one per ExecProcNode call"""

@@ -56,6 +56,8 @@ struct GgPlanState {
 	int rows_ready;                     /* host arrays below are filled */
 	int squelched;
 	int nonreceiver;                    /* above a Gather, on a segment that is not its receiver: no rows at all */
+	int dev_groups;                     /* decided at init, from the plan alone (so every segment decides alike): this node hands
+	                                     * its aggregate rows up as device-resident group records */
 	int32_t ncols;
 	int64_t nrows, next, markpos;
 	int64_t *values;
@@ -67,6 +69,10 @@ struct GgPlanState {
 
 static _Thread_local char g_err[512];
 static _Thread_local int g_errcode;
+/* the first failure of THIS segment's own slice while it kept taking part in device Motions (so that its peers are never
+ * left alone in a collective): what it reports in the end, rather than the flag that came back through the interconnect */
+static _Thread_local char g_local_err[512];
+static _Thread_local int g_local_code;
 
 static void *exec_fail(int code, const char *fmt, ...)
 {
@@ -96,6 +102,44 @@ const char *GgExecNodeKind(GgPlanState *s)
 	}
 	return "";
 }
+
+/* where a node that has run keeps its result: "device-groups", "device-rows" or "host" (tests and EXPLAIN-style output) */
+const char *GgExecNodeResultLocation(GgPlanState *s)
+{
+	if (!s || !s->done) return "";
+	if (s->groups && !s->rows_ready) return "device-groups";
+	if (s->rows_rel && !s->rows_ready) return "device-rows";
+	return "host";
+}
+
+/* benchmarks: summed CUDA-event time of the scan / probe kernel launches of the pipeline at or below `s` since its last
+ * rescan, their count, the kernel variant (gg_scanagg_variant), and for a join the build time */
+int GgExecPipelineKernelMs(GgPlanState *s, float *ms, int *launches, int *variant, float *build_ms)
+{
+	for (; s; s = s->child)
+	{
+		if (s->sa)
+		{
+			if (variant) *variant = gg_scanagg_variant(s->sa);
+			if (build_ms) *build_ms = 0;
+			return gg_scanagg_scan_kernel_ms(s->sa, ms, launches);
+		}
+		if (s->ja)
+		{
+			uint64_t rb, tb;
+			float b = 0;
+			int rc = gg_joinagg_stats(s->ja, &rb, &tb, &b, ms);
+			if (variant) *variant = gg_joinagg_variant(s->ja);
+			if (build_ms) *build_ms = b;
+			if (launches) *launches = 1;
+			return rc;
+		}
+	}
+	return GG_ERR_ARG;
+}
+
+GgPlanState *GgExecOuterPlanState(GgPlanState *s) { return s ? s->child : NULL; }
+GgPlanState *GgExecInnerPlanState(GgPlanState *s) { return s ? s->inner : NULL; }
 
 /* ---- output layout of an Agg node: group keys, then aggregates (a PARTIAL avg is its float8[3] state) ---- */
 static int agg_ncols_of(const gg_agg *agg, int i)
@@ -252,6 +296,7 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 GgPlanState *GgExecInitNode(GgPlan *node, GgEState *estate, int eflags)
 {
 	g_err[0] = 0; g_errcode = GG_OK;
+	g_local_code = 0; g_local_err[0] = 0;
 	return init_node(node, estate, eflags, 0);
 }
 
@@ -360,6 +405,13 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 				s->kind = K_AGGFINAL;
 				s->child = init_node(below, estate, eflags, depth + 1);
 				if (!s->child) { free_state(s); return NULL; }
+				{
+					/* device path: the child delivers group records of a PARTIAL stage with these very aggregates */
+					const GgPlanState *ch = s->child;
+					int i, same = ch->dev_groups && ch->agg.aggstage == GG_AGGSTAGE_PARTIAL && ch->agg.numAggs == an->agg.numAggs && ch->agg.numCols == an->agg.numCols;
+					for (i = 0; same && i < an->agg.numAggs; i++) same = ch->agg.aggs[i].aggfnoid == an->agg.aggs[i].aggfnoid;
+					s->dev_groups = same;
+				}
 				return s;
 			}
 			if (below && (below->type == T_GgSeqScan || yields_rows(below)))
@@ -382,6 +434,7 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 				}
 				rc = gg_scanagg_create(estate->engine, &scan, &an->agg, estate->pool, &s->sa);
 				if (rc != GG_OK) { exec_fail(rc, "Agg <- SeqScan: %s", gg_last_error()); end_tree(s->child); s->child = NULL; free_state(s); return NULL; }
+				s->dev_groups = 1;
 				return s;
 			}
 			if (below && below->type == T_GgHashJoin)
@@ -434,6 +487,7 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 					free_state(s);
 					return NULL;
 				}
+				s->dev_groups = 1;
 				return s;
 			}
 			exec_fail(GG_ERR_UNSUPPORTED, "Agg: child node type %d is not on the accelerated path", below ? (int) below->type : 0);
@@ -460,6 +514,15 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 			s->kind = K_MOTION;
 			s->child = init_node(node->lefttree, estate, eflags, depth + 1);
 			if (!s->child) { free_state(s); return NULL; }
+			s->agg = s->child->agg;
+			{
+				/* aggregate rows move as device-resident group records when the rows below are such records, the hash columns
+				 * are grouping columns, and the receiver does not merge sorted streams */
+				int c, ok = estate->interconnect != NULL && s->child->dev_groups && mo->numSortCols == 0;
+				for (c = 0; ok && mo->motionType == GG_MOTIONTYPE_HASH && c < mo->numHashCols; c++)
+					ok = mo->hashCol[c] >= 0 && mo->hashCol[c] < s->child->agg.numCols;
+				s->dev_groups = ok;
+			}
 			return s;
 		}
 		case T_GgSeqScan:
@@ -516,10 +579,15 @@ static int run_rows_node(GgPlanState *s)
 	{
 		if (!s->rows_send)
 		{
-			/* first guess: no more rows than 48-byte tuples fit the pages (exact sizes are in the pages' line pointers; a region
-			 * that turns out too small is reported with the size it needs) */
 			uint64_t words;
-			if (!s->rows_cap) s->rows_cap = ((nblocks * (uint64_t) GG_BLCKSZ / 48) / (uint64_t) N + 1024) * (uint64_t) N;
+			if (!s->rows_cap)
+			{
+				/* the line pointers bound the rows; a hash spreads them evenly over the destinations (10 % + 8192 slack each) */
+				uint64_t nlp = 0;
+				rc = gg_relation_count_rows(s->rel, &nlp);
+				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+				s->rows_cap = N == 1 ? nlp + 2 : (nlp / (uint64_t) N + nlp / (uint64_t) (10 * N) + 8192) * (uint64_t) N;
+			}
 			words = s->rows_cap * (uint64_t) W + 8;
 			rc = gg_relation_create(es->engine, (words * 8 + GG_BLCKSZ - 1) / GG_BLCKSZ, &s->rows_send);
 			if (rc != GG_OK) { exec_fail(rc, "Motion send buffer: %s", gg_last_error()); return -1; }
@@ -616,7 +684,13 @@ static int groups_to_host(GgPlanState *s)
 		if (rc != GG_ERR_NOMEM || cap >= (1 << 20)) break;
 		cap *= 16;
 	}
-	if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(rows); return -1; }
+	if (rc != GG_OK)
+	{
+		if (g_local_code && rc != GG_ERR_RETRY_HOST) exec_fail(g_local_code, "%s", g_local_err);      /* this segment's own failure */
+		else exec_fail(rc, "%s", gg_last_error());
+		free(rows);
+		return -1;
+	}
 	/* rows read as the node's own Agg says: a Motion passes its child's layout through */
 	layout = s->agg;
 	if (s->kind == K_AGGFINAL)
@@ -708,16 +782,13 @@ static int run_node(GgPlanState *s)
 		case K_AGGFINAL:
 		{
 			gg_aggrow *in, *out;
-			int n = 0, cap, i, same;
+			int n = 0, cap, i;
 			gg_agg part = s->agg;
 			GgPlanState *ch = s->child;
 			drop_device_results(s);
 			if (run_child(s)) return -1;
 			s->nonreceiver = ch->nonreceiver;
-			/* device path: the child delivered group records of a PARTIAL stage with these very aggregates */
-			same = ch->groups != NULL && ch->agg.aggstage == GG_AGGSTAGE_PARTIAL && ch->agg.numAggs == s->agg.numAggs && ch->agg.numCols == s->agg.numCols;
-			for (i = 0; same && i < s->agg.numAggs; i++) same = ch->agg.aggs[i].aggfnoid == s->agg.aggs[i].aggfnoid;
-			if (same)
+			if (s->dev_groups && !es->motion_on_host && ch->groups)
 			{
 				rc = gg_groups_final(es->engine, ch->groups, &s->groups);
 				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
@@ -802,28 +873,33 @@ static int run_node(GgPlanState *s)
 				 * it, and every segment comes back with an error (nodeMotion.c / cdbmotion.c:342 stop + error propagation) */
 				if (!multi_segment(es) || (!es->interconnect && !es->transport)) return -1;
 				child_failed = 1;
+				if (!g_local_code) { g_local_code = g_errcode; memcpy(g_local_err, g_err, sizeof g_local_err); }
 			}
 			s->nonreceiver = (mo->motionType == GG_MOTIONTYPE_GATHER && multi_segment(es) && es->segindex != 0) || (!child_failed && ch->nonreceiver);
 			if (!child_failed) inherit_layout(s, ch);
-			/* device path: aggregate rows move as group records, segment to segment, without touching the host */
-			if (!child_failed && es->interconnect && ch->groups && !(mo->numSortCols > 0))
+			/* device path: aggregate rows move as group records, segment to segment, without touching the host.  Whether a
+			 * Motion takes it was decided from the plan (every segment alike); a segment that cannot contribute records —
+			 * its slice failed, or its aggregate keeps its groups in the general hash table — sends its status instead, and
+			 * the flag reaches every segment's fetch with the data (an ERROR, or "run the slice again with host-row Motions"). */
+			if (s->dev_groups && !es->motion_on_host)
 			{
-				int32_t hashtyp[GG_MAX_KEYS];
-				int ok = 1;
+				int32_t hashtyp[GG_MAX_KEYS] = { 0 };
+				gg_groups *in = child_failed ? NULL : ch->groups;
 				for (c = 0; c < mo->numHashCols && mo->motionType == GG_MOTIONTYPE_HASH; c++)
+					hashtyp[c] = s->agg.aggstage == GG_AGGSTAGE_FINAL ? s->agg.grpCol[mo->hashCol[c]] : expr_type(es->pool, s->agg.grpCol[mo->hashCol[c]]);
+				rc = gg_ic_motion_groups(es->interconnect, mo->motionType, 0, mo->motionType == GG_MOTIONTYPE_HASH ? mo->numHashCols : 0,
+				                         mo->hashCol, hashtyp, in, child_failed ? g_errcode : GG_OK, &s->groups);
+				if (rc != GG_OK) { exec_fail(rc, "Motion %d: %s", mo->motionID, gg_last_error()); return -1; }
+				if (s->nonreceiver) gg_groups_set_nonreceiver(s->groups);
+				if (child_failed)
 				{
-					if (mo->hashCol[c] < 0 || mo->hashCol[c] >= ch->agg.numCols) { ok = 0; break; }      /* hashing an aggregate value: host path */
-					hashtyp[c] = ch->typid[mo->hashCol[c]];
+					/* layout of the rows this node would have handed up: taken from the plan */
+					int32_t kt[GG_MAX_KEYS] = { 0 };
+					for (c = 0; c < s->agg.numCols; c++) kt[c] = s->agg.aggstage == GG_AGGSTAGE_FINAL ? s->agg.grpCol[c] : expr_type(es->pool, s->agg.grpCol[c]);
+					if (set_layout_types(s, &s->agg, kt)) return -1;
 				}
-				if (ok)
-				{
-					rc = gg_ic_motion_groups(es->interconnect, mo->motionType, 0, mo->motionType == GG_MOTIONTYPE_HASH ? mo->numHashCols : 0,
-					                         mo->hashCol, hashtyp, ch->groups, &s->groups);
-					if (rc != GG_OK) { exec_fail(rc, "Motion %d: %s", mo->motionID, gg_last_error()); return -1; }
-					if (s->nonreceiver) gg_groups_set_nonreceiver(s->groups);
-					s->rows_ready = 0;
-					break;
-				}
+				s->rows_ready = 0;
+				break;
 			}
 			if (motion_host_path(s, child_failed)) return -1;
 			break;
@@ -965,15 +1041,29 @@ GgTupleTableSlot *GgExecProcNode(GgPlanState *s)
 	int c;
 	if (!s || s->squelched) return NULL;
 	if (s->kind == K_HASH) { exec_fail(GG_ERR_ARG, "Hash node does not return tuples via ExecProcNode()"); return NULL; }     /* nodeHash.c:73 ExecHash */
-	if (!s->done)
+	for (;;)
 	{
-		g_err[0] = 0; g_errcode = GG_OK;
-		if (run_node(s)) return NULL;                 /* the C wrapper on the Postgres side turns this into ereport(ERROR) */
-	}
-	if (!s->rows_ready)
-	{
-		g_err[0] = 0; g_errcode = GG_OK;
-		if (ensure_rows(s)) return NULL;
+		int failed = 0;
+		if (!s->done)
+		{
+			g_err[0] = 0; g_errcode = GG_OK;
+			failed = run_node(s);                     /* the C wrapper on the Postgres side turns a failure into ereport(ERROR) */
+		}
+		if (!failed && !s->rows_ready)
+		{
+			g_err[0] = 0; g_errcode = GG_OK;
+			failed = ensure_rows(s);
+		}
+		if (!failed) break;
+		if (g_errcode == GG_ERR_RETRY_HOST && !s->estate->motion_on_host)
+		{
+			/* some segment could not keep its aggregate rows on the device; every segment learned it at its fetch, so all
+			 * of them run the slice again, with the Motions moving host rows */
+			s->estate->motion_on_host = 1;
+			if (GgExecReScan(s) != GG_OK) return NULL;
+			continue;
+		}
+		return NULL;
 	}
 	if (s->next >= s->nrows)
 	{
@@ -1006,6 +1096,7 @@ int GgExecReScan(GgPlanState *s)
 {
 	int rc = GG_OK;
 	if (!s) return GG_ERR_ARG;
+	g_local_code = 0; g_local_err[0] = 0;
 	if (s->child && (rc = GgExecReScan(s->child)) != GG_OK) return rc;
 	if (s->inner && (rc = GgExecReScan(s->inner)) != GG_OK) return rc;
 	drop_device_results(s);

@@ -91,6 +91,16 @@ def join_plan(table=capi.TAB_LINEITEM_NARROW, kind="count", jointype=capi.JOIN_I
         hj = capi.make_hashjoin(jointype, [lkey], [okey])
         agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(AGG_COUNT_STAR, -1)])
         return outer, inner, hj, agg, p.pool
+    if kind == "survey":
+        # SELECT count(*), sum(o_custkey), sum(l_extendedprice) — count and the integer sum are the bit-exact
+        # checks, the float8 sum the 1e-6 one
+        custkey = p.var(ocols["custkey"], capi.INT4OID, varno=1)
+        price = p.var(cols["extendedprice"], FLOAT8OID, varno=0)
+        outer = capi.make_scan(li_desc, -1)
+        inner = capi.make_scan(ord_desc, -1)
+        hj = capi.make_hashjoin(jointype, [lkey], [okey])
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(AGG_COUNT_STAR, -1), (capi.AGG_SUM_INT4, custkey), (AGG_SUM_FLOAT8, price)])
+        return outer, inner, hj, agg, p.pool
     odate = p.var(ocols["orderdate"], DATEOID, varno=1)
     ostatus = p.var(ocols["orderstatus"], BPCHAROID, varno=1)
     price = p.var(cols["extendedprice"], FLOAT8OID, varno=0)
@@ -136,3 +146,71 @@ def synth_generate(spec, out=None, nthreads=None):
     rc = capi.host_lib().gg_synth_generate(C.byref(spec), nthreads, ptr, nb, C.byref(nb2), C.byref(nr2))
     assert rc == 0 and nb2.value == nb
     return out, nb, nr
+
+
+def final_agg_of(agg, key_typids):
+    """The FINAL-stage Agg above a Motion: same aggregates, grpCol carries the key type OIDs."""
+    fin = capi.gg_agg()
+    C.memmove(C.byref(fin), C.byref(agg), C.sizeof(capi.gg_agg))
+    fin.aggstage = capi.AGGSTAGE_FINAL
+    for i, t in enumerate(key_typids):
+        fin.grpCol[i] = t
+    return fin
+
+
+def q1_exec_plan(b, table=capi.TAB_LINEITEM_WIDE, two_stage=False, interval_days=90, desc=None):
+    """The executor plan tree of the headline benchmark (scan + filter + hash aggregate, no ORDER BY):
+       one segment     Agg(NORMAL) <- SeqScan
+       several         Gather Motion <- Agg(FINAL) <- Redistribute Motion(l_returnflag, l_linestatus) <- Agg(PARTIAL) <- SeqScan
+    (expected/tpch500GB.out:1771-1782 without the Sort).  Returns (plan, pool)."""
+    from . import executor as ex
+    if not two_stage:
+        scan, agg, pool = q1_plan(table, capi.AGGSTAGE_NORMAL, interval_days, desc)
+        return b.agg(b.seqscan(0, scan.desc, scan.qual), agg), pool
+    # this engine's own FINAL stage combines the partial rows: float8_avg never reads sumX2 (float.c:1982-1996)
+    scan, part, pool = q1_plan(table, capi.AGGSTAGE_PARTIAL, interval_days, desc, flags=capi.AGGF_DEVICE_FINAL)
+    fin = final_agg_of(part, [BPCHAROID, BPCHAROID])
+    return b.motion(b.agg(b.motion(b.agg(b.seqscan(0, scan.desc, scan.qual), part), ex.MOTION_HASH, [0, 1], 1), fin), ex.MOTION_GATHER, [], 2), pool
+
+
+def rjoin_exec_plan(b, kind="q3ish", table=capi.TAB_LINEITEM_NARROW, redistribute=True):
+    """BASELINE config 3: lineitem JOIN orders with both sides redistributed on the join key, aggregated in two stages:
+         Agg(FINAL) <- Gather Motion <- Agg(PARTIAL) <- HashJoin( Redistribute Motion <- SeqScan(lineitem),
+                                                                  Hash <- Redistribute Motion <- SeqScan(orders) )
+    (nodeMotion.c:1481-1687, nodeHashjoin.c:78-509).  The scans project the columns the join needs (targets), so only those
+    travel.  relations: [lineitem, orders].  redistribute=False: the same join over the base relations (co-located data).
+    Returns (plan, pool, lineitem_targets, orders_targets)."""
+    from . import executor as ex
+    ldesc, odesc = capi.synth_tupdesc(table), capi.synth_tupdesc(capi.TAB_ORDERS)
+    lc = LI_WIDE_COLS if table == capi.TAB_LINEITEM_WIDE else LI_NARROW_COLS
+    if kind == "survey":
+        lnames, ltypes = ["orderkey", "extendedprice"], [capi.INT8OID, FLOAT8OID]
+        onames, otypes = ["orderkey", "custkey"], [capi.INT8OID, capi.INT4OID]
+    else:
+        lnames, ltypes = ["orderkey", "extendedprice", "discount", "shipdate"], [capi.INT8OID, FLOAT8OID, FLOAT8OID, DATEOID]
+        onames, otypes = ["orderkey", "orderdate", "orderstatus"], [capi.INT8OID, DATEOID, BPCHAROID]
+    if not redistribute:
+        outer, inner, hj, agg, pool = join_plan(table, kind)
+        part = capi.gg_agg.from_buffer_copy(bytes(agg))
+        part.aggstage, part.flags = capi.AGGSTAGE_PARTIAL, capi.AGGF_DEVICE_FINAL
+        fin = final_agg_of(part, [BPCHAROID] if part.numCols else [])
+        join = b.hashjoin(b.seqscan(0, outer.desc, outer.qual), b.hash(b.seqscan(1, inner.desc, inner.qual)), hj)
+        return b.agg(b.motion(b.agg(join, part), ex.MOTION_GATHER, [], 3), fin), pool, [], []
+    lrd = capi.rows_tupdesc(ltypes, notnull=[1] * len(ltypes))
+    ord_ = capi.rows_tupdesc(otypes, notnull=[1] * len(otypes))
+    outer, inner, hj, agg, pool = join_plan(table, kind, li_desc=lrd, ord_desc=ord_,
+                                            li_cols={n: i + 1 for i, n in enumerate(lnames)}, ord_cols={n: i + 1 for i, n in enumerate(onames)})
+    ep = ExprPool()
+    ep.pool = pool                                    # the plan's one expression pool: the scans' target lists go into it too
+    lt = [ep.var(lc[n], t) for n, t in zip(lnames, ltypes)]
+    ot = [ep.var(ORDERS_COLS[n], t) for n, t in zip(onames, otypes)]
+    oqual = -1
+    if kind == "q3ish":                               # the inner scan qual sits on the base SeqScan, below the Motion
+        oqual = ep.func(capi.F_DATE_LT, BOOLOID, ep.var(ORDERS_COLS["orderdate"], DATEOID), ep.const(DATEOID, D_1995_03_15))
+    part = capi.gg_agg.from_buffer_copy(bytes(agg))
+    part.aggstage, part.flags = capi.AGGSTAGE_PARTIAL, capi.AGGF_DEVICE_FINAL
+    fin = final_agg_of(part, [BPCHAROID] if part.numCols else [])
+    lside = b.motion(b.seqscan(0, ldesc, -1, targets=lt), ex.MOTION_HASH, [0], 1)
+    oside = b.motion(b.seqscan(1, odesc, oqual, targets=ot), ex.MOTION_HASH, [0], 2)
+    join = b.hashjoin(lside, b.hash(oside), hj)
+    return b.agg(b.motion(b.agg(join, part), ex.MOTION_GATHER, [], 3), fin), pool, lt, ot

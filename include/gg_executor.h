@@ -145,6 +145,10 @@ typedef struct GgEState {
 	 * the scan streams them to the device (gg_scanagg_run_host), H2D overlapped with the kernel */
 	const void *host_pages[GG_MAX_RELATIONS];
 	uint64_t host_nblocks[GG_MAX_RELATIONS];
+	/* set by the executor when a slice had to be run again with its Motions moving host rows (some segment's aggregate did
+	 * not fit the device-resident path); 0 at query start */
+	int32_t motion_on_host;
+	int32_t pad;
 } GgEState;
 
 typedef struct GgPlanState GgPlanState;        /* execnodes.h PlanState */
@@ -159,6 +163,13 @@ const char *GgExecLastError(void);
 int  GgExecLastErrorCode(void);                /* GG_ERR_* of the failure, GG_OK if none */
 /* introspection: which device pipeline a state node was fused into ("scanagg", "joinagg", "sort", "motion") */
 const char *GgExecNodeKind(GgPlanState *node);
+/* where a node that has run keeps its result: "device-groups" (aggregate rows as group records), "device-rows" (datum rows)
+ * or "host" (Datum arrays); "" before it has run */
+const char *GgExecNodeResultLocation(GgPlanState *node);
+/* the state of a node's outer / inner child (outerPlanState / innerPlanState, execnodes.h:1441), NULL if fused away */
+int GgExecPipelineKernelMs(GgPlanState *node, float *ms, int *launches, int *variant, float *build_ms);   /* benchmarks */
+GgPlanState *GgExecOuterPlanState(GgPlanState *node);
+GgPlanState *GgExecInnerPlanState(GgPlanState *node);
 
 /* The per-node entry points of src/include/executor/node*.h, for a build that replaces the node files
  * at link time instead of going through ExecProcNode's switch.  Each checks the node tag and delegates to the
@@ -211,7 +222,7 @@ typedef struct GgInterconnectOps {
 	void (*TeardownInterconnect)(GgEState *estate, int hasErrors);            /* ic_common.c:560 */
 	/* SendChunk + SendEos of a whole batch (cdbinterconnect.h:525,529): group records / datum rows / host rows */
 	int  (*SendRecvGroups)(gg_interconnect *ic, int motionType, int root, int nhash, const int32_t *hashcol, const int32_t *hashtypid,
-	                       gg_groups *in, gg_groups **out);
+	                       gg_groups *in, int local_error, gg_groups **out);
 	int  (*SendRecvRows)(gg_interconnect *ic, const void *send_rows, const uint64_t *counts, uint64_t region_cap, int rowwords,
 	                     void *recv_rows, uint64_t recv_cap, uint64_t *nrecv);
 	int  (*SendRecvHostRows)(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *values, const uint8_t *isnull,

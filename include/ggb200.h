@@ -43,6 +43,8 @@ extern "C" {
 #define GG_ERR_ARG             (-10)
 #define GG_ERR_DATE_RANGE      (-11)   /* "date out of range for timestamp", date.c:471 */
 #define GG_ERR_PEER            (-12)   /* another segment of the Motion reported an ERROR (the QD cancels the query) */
+#define GG_ERR_RETRY_HOST      (-13)   /* not an error of the query: some segment could not keep its aggregate rows on the device
+                                        * (every segment gets this at its fetch): run the slice again with host-row Motions */
 
 typedef struct gg_engine   gg_engine;     /* one GPU segment: device, streams, scratch */
 typedef struct gg_relation gg_relation;   /* heap pages resident in HBM (replaces bufmgr/smgr for the scan) */
@@ -83,6 +85,8 @@ int  gg_relation_attach_rows(gg_engine *e, void *device_rows, uint64_t nrows, in
 int  gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks);
 int  gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uint64_t nblocks);
 uint64_t gg_relation_nblocks(gg_relation *r);
+/* upper bound on the tuples of the relation: its line pointers (one pass over the page headers), or the row count of datum rows */
+int  gg_relation_count_rows(gg_relation *r, uint64_t *nrows);
 void *gg_relation_device_ptr(gg_relation *r);
 void gg_relation_free(gg_relation *r);
 
@@ -130,6 +134,7 @@ int  gg_joinagg_probe_host(gg_joinagg *p, const void *host_pages, uint64_t nbloc
 int  gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined);
 int  gg_joinagg_reset(gg_joinagg *p);      /* ExecReScanHashJoin with the hash table kept (nodeHashjoin.c:1015-1050) */
 int  gg_joinagg_stats(gg_joinagg *p, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms);
+int  gg_joinagg_variant(gg_joinagg *p);       /* kernel variant of the probe side, as gg_scanagg_variant */
 void gg_joinagg_free(gg_joinagg *p);
 
 /* ---- Append-only column-oriented (AOCS) relations ----
@@ -209,7 +214,11 @@ int  gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all);
  * OIDs; routing is cdbhash + jump consistent hash, bit-exact with cdbhash.c:191-287.  The status (ERROR flags) of every
  * sender reaches every receiver with the data. */
 int  gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhash, const int32_t *hashcol,
-                         const int32_t *hashtypid, gg_groups *in, gg_groups **out);
+                         const int32_t *hashtypid, gg_groups *in, int local_error, gg_groups **out);
+/* `in` == NULL: this segment has no device-resident records to send — its slice failed (local_error = the GG_ERR_* code) or
+ * its aggregate keeps its groups elsewhere (local_error = GG_OK).  It still takes part, with an empty block whose status says
+ * so; the flags travel with the data and every segment meets them at its fetch (an ERROR, or GG_ERR_RETRY_HOST).  A segment
+ * never leaves its peers alone in a collective. */
 /* Redistribute of datum rows: the all-to-all-v behind gg_motion_partition (send_rows = its regions, counts = its host_counts,
  * region_cap = out_cap_rows / nsegs rounded down to even).  recv_rows: device buffer of recv_cap rows (16-byte aligned,
  * 16 bytes of slack for gg_relation_attach_rows).  GG_ERR_NOMEM (on every segment) if any receive buffer is too small. */

@@ -135,8 +135,8 @@ void gg_groups_set_nonreceiver(gg_groups *g) { (void) g; }
 void gg_groups_free(gg_groups *g) { (void) g; }
 int gg_ic_create(gg_engine *e, const void *id, int nsegs, int seg, gg_interconnect **out) { (void) e; (void) id; (void) nsegs; (void) seg; *out = NULL; return unsupported(); }
 void gg_ic_teardown(gg_interconnect *ic, int has_errors) { (void) ic; (void) has_errors; }
-int gg_ic_motion_groups(gg_interconnect *ic, int t, int root, int nhash, const int32_t *hc, const int32_t *ht, gg_groups *in, gg_groups **out)
-{ (void) ic; (void) t; (void) root; (void) nhash; (void) hc; (void) ht; (void) in; *out = NULL; return unsupported(); }
+int gg_ic_motion_groups(gg_interconnect *ic, int t, int root, int nhash, const int32_t *hc, const int32_t *ht, gg_groups *in, int lerr, gg_groups **out)
+{ (void) ic; (void) t; (void) root; (void) nhash; (void) hc; (void) ht; (void) in; (void) lerr; *out = NULL; return unsupported(); }
 int gg_ic_exchange_rows(gg_interconnect *ic, const void *s, const uint64_t *c, uint64_t rc, int w, void *r, uint64_t cap, uint64_t *n)
 { (void) ic; (void) s; (void) c; (void) rc; (void) w; (void) r; (void) cap; (void) n; return unsupported(); }
 int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int64_t *v, const uint8_t *nl, const int32_t *d, int err,
@@ -156,3 +156,8 @@ void gg_relation_free(gg_relation *r) { free(r); }
 int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool, const int32_t *hk, int nk, const int32_t *pl, int np,
                         int nsegs, gg_relation *r, uint64_t fb, uint64_t nb, void *out, uint64_t cap, uint64_t *hc, uint64_t *ho)
 { (void) e; (void) scan; (void) pool; (void) hk; (void) nk; (void) pl; (void) np; (void) nsegs; (void) r; (void) fb; (void) nb; (void) out; (void) cap; (void) hc; (void) ho; return unsupported(); }
+int gg_relation_count_rows(gg_relation *r, uint64_t *n) { (void) r; (void) n; return unsupported(); }
+int gg_scanagg_scan_kernel_ms(gg_scanagg *p, float *ms, int *launches) { (void) p; if (ms) *ms = 0; if (launches) *launches = 0; return GG_OK; }
+int gg_scanagg_variant(gg_scanagg *p) { (void) p; return -1; }
+int gg_joinagg_variant(gg_joinagg *p) { (void) p; return -1; }
+int gg_joinagg_stats(gg_joinagg *p, uint64_t *a, uint64_t *b, float *c, float *d) { (void) p; (void) a; (void) b; (void) c; (void) d; return unsupported(); }

@@ -110,3 +110,131 @@ def test_device_errors_surface_through_exec_proc_node(eng):
     finally:
         x.end()
         rel.free()
+
+
+# ---- results that stay on the device between the nodes of a slice (gg_groups / datum rows) and the C interconnect ----
+
+def _check_q1_rows(rows, exp):
+    by = {(capi.unpack_str(v[0], ln[0]), capi.unpack_str(v[1], ln[1])): v for v, nl, ty, ln in rows}
+    assert len(by) == len(rows) == len(exp["rows"])
+    for w in exp["rows"]:
+        v = by[(w["returnflag"], w["linestatus"])]
+        assert v[9] == w["count_order"]
+        for col, name in ((2, "sum_qty"), (3, "sum_base_price"), (4, "sum_disc_price"), (5, "sum_charge"),
+                          (6, "avg_qty"), (7, "avg_price"), (8, "avg_disc")):
+            assert abs(b2f(v[col]) - float(w[name])) <= 1e-6 * abs(float(w[name])), (name, b2f(v[col]), w[name])
+
+
+def test_two_stage_q1_stays_on_the_device_through_the_interconnect(eng):
+    """Gather <- Agg(FINAL) <- Redistribute <- Agg(PARTIAL) <- SeqScan with the C interconnect (one segment: loopback, the
+    same pack / route / combine kernels as over NCCL): the partial rows never leave the device until the top node is asked
+    for tuples, and the answer is the reference's golden Q1."""
+    from greengage_b200.engine import Interconnect, Relation
+    desc, pages, n = lineitem_fixture_pages()
+    exp = golden("q1_expected.json")
+    rel = Relation(eng, host_pages=pages)
+    ic = Interconnect(eng, 1, 0)
+    b = ex.PlanBuilder()
+    plan, pool = tpch.q1_exec_plan(b, two_stage=True, interval_days=exp["interval_days"], desc=desc)
+    x = ex.Executor(eng, pool, [rel], plan, interconnect=ic)
+    try:
+        rows = x.rows()
+        _check_q1_rows(rows, exp)
+        loc = x.locations()
+        assert [k for k, _ in loc] == ["motion", "aggfinal", "motion", "scanagg"]
+        assert loc[1][1] == "device-groups" and loc[2][1] == "device-groups"      # FINAL Agg and Redistribute: no host rows
+        x.rescan()
+        _check_q1_rows(x.rows(), exp)
+    finally:
+        x.end()
+        ic.close()
+        rel.free()
+
+
+def test_scan_of_a_relation_in_host_memory(eng):
+    """GgEState.host_pages: the SeqScan's pages are in (pinned) host memory and are streamed to the device inside the
+    pipeline — the end-to-end path bench.py times"""
+    from greengage_b200.engine import host_alloc, host_free
+    desc, pages, n = lineitem_fixture_pages()
+    exp = golden("q1_expected.json")
+    addr, view = host_alloc(pages.size)
+    view[:] = pages
+    b = ex.PlanBuilder()
+    plan, pool = tpch.q1_exec_plan(b, two_stage=False, interval_days=exp["interval_days"], desc=desc)
+    x = ex.Executor(eng, pool, [(addr, pages.size // capi.GG_BLCKSZ)], plan)
+    try:
+        _check_q1_rows(x.rows(), exp)
+    finally:
+        x.end()
+        host_free(addr)
+
+
+@pytest.mark.parametrize("kind", ["q3ish", "survey"])
+@pytest.mark.parametrize("redistribute", [True, False])
+def test_redistribute_hashjoin_plan(eng, kind, redistribute):
+    """BASELINE config 3's plan through the node surface on one segment: both sides projected by their scans, partitioned on
+    the join key (device Motion), joined over the delivered datum rows, aggregated in two stages — equal to the oracle's join
+    over the heap pages."""
+    from greengage_b200.engine import Interconnect, Relation
+    li, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 120_000, seed=9, norders=30_000))
+    od, _, _ = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 25_000, seed=9))
+    outer, inner, hj, agg, pool0 = tpch.join_plan(capi.TAB_LINEITEM_NARROW, kind, capi.JOIN_INNER)
+    want, nj = po.hashjoin_agg(outer, inner, hj, agg, pool0, li, od)
+    lrel, orel = Relation(eng, host_pages=li), Relation(eng, host_pages=od)
+    ic = Interconnect(eng, 1, 0)
+    b = ex.PlanBuilder()
+    plan, pool, _, _ = tpch.rjoin_exec_plan(b, kind, redistribute=redistribute)
+    x = ex.Executor(eng, pool, [lrel, orel], plan, interconnect=ic)
+    try:
+        rows = x.rows()
+        assert len(rows) == len(want)
+        if kind == "survey":
+            v = rows[0][0]
+            w = want[0]
+            assert v[0] == w.agg[0].i == nj and v[1] == w.agg[1].i               # count(*), sum(o_custkey): bit-exact
+            assert abs(b2f(v[2]) - w.agg[2].f[0]) <= 1e-6 * abs(w.agg[2].f[0])
+        else:
+            by = {r.key[0]: r for r in want}
+            for v, nl, ty, ln in rows:
+                w = by[v[0]]
+                assert v[1] == w.agg[0].i and v[3] == w.agg[2].i
+                assert abs(b2f(v[2]) - w.agg[1].f[0]) <= 1e-6 * abs(w.agg[1].f[0])
+        if redistribute:
+            L = ex.exec_lib()
+            join_state = L.GgExecOuterPlanState(L.GgExecOuterPlanState(x.state))      # Agg(FINAL) -> Gather -> Agg over the join
+            assert L.GgExecNodeKind(join_state) == b"joinagg"
+            assert L.GgExecNodeResultLocation(L.GgExecOuterPlanState(join_state)) == b"device-rows"
+            assert L.GgExecNodeResultLocation(L.GgExecInnerPlanState(join_state)) == b"device-rows"
+    finally:
+        x.end()
+        ic.close()
+        lrel.free()
+        orel.free()
+
+
+def test_bare_seqscan_with_a_target_list_returns_its_rows(eng):
+    """ExecSeqScan proper (nodeSeqscan.c:128): qual + projection, tuples handed to the caller one slot at a time"""
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import Relation
+    li, _, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 20_000, seed=3))
+    c = tpch.LI_NARROW_COLS
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW)
+    p = ExprPool()
+    key, price, flag = p.var(c["orderkey"], capi.INT8OID), p.var(c["extendedprice"], capi.FLOAT8OID), p.var(c["returnflag"], capi.BPCHAROID)
+    qual = p.func(capi.F_FLOAT8GT, capi.BOOLOID, p.var(c["quantity"], capi.FLOAT8OID), p.const(capi.FLOAT8OID, 25.0))
+    agg = capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, price), (capi.AGG_SUM_FLOAT8, p.func(capi.F_I8TOD, capi.FLOAT8OID, key))])
+    want, sc, ps = po.seqscan_agg(capi.make_scan(desc, qual), agg, p.pool, li)
+    rel = Relation(eng, host_pages=li)
+    b = ex.PlanBuilder()
+    x = ex.Executor(eng, p.pool, [rel], b.seqscan(0, desc, qual, targets=[key, price, flag]))
+    try:
+        assert x.kind() == "scanrows"
+        rows = x.rows()
+        assert len(rows) == ps == want[0].agg[0].i
+        assert rows[0][2] == [capi.INT8OID, capi.FLOAT8OID, capi.BPCHAROID]
+        assert sorted(capi.unpack_str(v[2], ln[2]) for v, nl, ty, ln in rows[:200]) <= ["R"] * 200
+        assert abs(sum(b2f(v[1]) for v, nl, ty, ln in rows) - want[0].agg[1].f[0]) <= 1e-9 * want[0].agg[1].f[0]
+        assert sum(v[0] for v, nl, ty, ln in rows) == int(want[0].agg[2].f[0])
+    finally:
+        x.end()
+        rel.free()
