@@ -180,6 +180,7 @@ def dev_lib():
         L.gg_relation_attach.argtypes = [vp, vp, u64, C.POINTER(vp)]
         L.gg_relation_load.argtypes = [vp, u64, vp, u64]
         L.gg_relation_read.argtypes = [vp, u64, vp, u64]
+        L.gg_relation_copy.argtypes = [vp, u64, vp, u64, u64]
         L.gg_relation_count_rows.argtypes = [vp, C.POINTER(u64)]
         L.gg_relation_nblocks.argtypes = [vp]
         L.gg_relation_nblocks.restype = u64

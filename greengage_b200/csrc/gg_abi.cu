@@ -228,6 +228,16 @@ int gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uin
 	return GG_OK;
 }
 
+int gg_relation_copy(gg_relation *dst, uint64_t dst_first, gg_relation *src, uint64_t src_first, uint64_t nblocks)
+{
+	if (!dst || !src || nblocks > dst->nblocks || dst_first > dst->nblocks - nblocks || nblocks > src->nblocks || src_first > src->nblocks - nblocks)
+		return GG_ERR_ARG;
+	GG_CUDA(cudaSetDevice(dst->eng->device));
+	GG_CUDA(cudaMemcpyAsync(dst->pages + dst_first * GG_BLCKSZ, src->pages + src_first * GG_BLCKSZ, (size_t) nblocks * GG_BLCKSZ,
+	                        cudaMemcpyDeviceToDevice, dst->eng->stream));
+	return GG_OK;
+}
+
 uint64_t gg_relation_nblocks(gg_relation *r) { return r ? r->nblocks : 0; }
 void *gg_relation_device_ptr(gg_relation *r) { return r ? r->pages : nullptr; }
 

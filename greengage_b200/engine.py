@@ -87,6 +87,11 @@ class Relation:
     def device_ptr(self):
         return dev_lib().gg_relation_device_ptr(self.h)
 
+    def copy_from(self, src, dst_first=0, src_first=0, nblocks=None):
+        """device -> device copy of pages (gg_relation_copy)"""
+        nblocks = src.nblocks - src_first if nblocks is None else nblocks
+        check(dev_lib().gg_relation_copy(self.h, dst_first, src.h, src_first, nblocks))
+
     def free(self):
         if self.h:
             dev_lib().gg_relation_free(self.h)

@@ -133,10 +133,11 @@ def synth_measure(spec, nthreads=None):
     return nb.value, nr.value
 
 
-def synth_generate(spec, out=None, nthreads=None):
-    """Generate this segment's pages into a numpy uint8 array (or a caller-provided buffer address)."""
+def synth_generate(spec, out=None, nthreads=None, measured=None):
+    """Generate this segment's pages into a numpy uint8 array (or a caller-provided buffer address).
+    measured: (nblocks, nrows) from an earlier synth_measure of the same spec (saves one pass over the candidates)."""
     nthreads = nthreads or min(os.cpu_count() or 1, 64)
-    nb, nr = synth_measure(spec, nthreads)
+    nb, nr = measured if measured is not None else synth_measure(spec, nthreads)
     if out is None:
         out = np.empty(nb * capi.GG_BLCKSZ, dtype=np.uint8)
         ptr = out.ctypes.data_as(C.c_void_p)

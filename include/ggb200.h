@@ -84,6 +84,9 @@ int  gg_relation_attach_rows(gg_engine *e, void *device_rows, uint64_t nrows, in
  * when host_pages is pinned; gg_engine_sync or the next *_run orders it) */
 int  gg_relation_load(gg_relation *r, uint64_t first_block, const void *host_pages, uint64_t nblocks);
 int  gg_relation_read(gg_relation *r, uint64_t first_block, void *host_pages, uint64_t nblocks);
+/* device -> device copy of nblocks pages between two relations of one engine (async on the engine's stream): a partition
+ * attached to its parent, a relation extended by pages another scan produced */
+int  gg_relation_copy(gg_relation *dst, uint64_t dst_first, gg_relation *src, uint64_t src_first, uint64_t nblocks);
 uint64_t gg_relation_nblocks(gg_relation *r);
 /* upper bound on the tuples of the relation: its line pointers (one pass over the page headers), or the row count of datum rows */
 int  gg_relation_count_rows(gg_relation *r, uint64_t *nrows);
