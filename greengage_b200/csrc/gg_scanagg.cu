@@ -331,9 +331,10 @@ static int scanagg_configure(gg_scanagg *p)
 			if (ncons < 15) { int w3 = fit(3, 16); if (w3 >= ncons + 3) { p->nstage = 3; ncons = w3; } }
 		}
 		{
-			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages" for experiments */
-			int a, b;
-			if (cfg && sscanf(cfg, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 20 && b >= 2 && b <= 6) { ncons = a; p->nstage = b; }
+			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages[,team]" for experiments */
+			int a, b, c = 0;
+			p->team = 0;
+			if (cfg && sscanf(cfg, "%d,%d,%d", &a, &b, &c) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && c >= 0 && c <= a) { ncons = a; p->nstage = b; p->team = c; }
 		}
 		p->threads = (ncons + 1) * 32;
 		const int NT = ncons * 32;
@@ -459,6 +460,7 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	memset(&prm.mo, 0, sizeof prm.mo);
 	prm.nrows = nrows;
 	prm.fill_inner = fill_inner ? 1 : 0;
+	prm.team = p->team;
 	prm.ha = p->ha;
 	if (p->kev_used == p->kev.size())
 	{

@@ -150,6 +150,9 @@ struct ScanAggParams {
 	uint64_t nrows;                       /* datum-row input: total rows (pages/nblocks then describe 32 KB chunks of rows) */
 	int fill_inner;                       /* join probe kernels: this launch is HJ_FILL_INNER_TUPLES — the "pages" are the hash
 	                                       * table itself, every unmatched entry is emitted with a null-extended outer side */
+	int team;                             /* > 0: consumer warps work in teams of this many warps, one page per team at a time (a
+	                                       * warp only visits its team's pages); 0: every warp visits every page and the chunks
+	                                       * are dealt round-robin across pages */
 };
 
 struct BlockTable {                       /* per-block group table in shared memory */
@@ -269,10 +272,45 @@ struct RowSink {
 		v = normalize_key(v, (int) ((keytypes >> (2 * kc)) & 3));
 		if (kc == 0) k0 = v; else if (kc == 1) k1 = v; else if (kc == 2) k2 = v; else k3 = v;
 	}
+	/* the first groups of the block's table, cached in registers: with a handful of groups (Q1 has four) a row finds its group
+	 * by comparing against registers, and the shared-memory table (and its lock) is only visited for a key no lane of the warp
+	 * has cached yet.  Entries mirror table slots 0 .. cn-1 exactly (slot = group id); a slot with a NULL key ends the cache. */
+	int cn;
+	uint64_t c00, c01, c10, c11, c20, c21, c30, c31;
+	__device__ __forceinline__ void cache_refresh()
+	{
+		const volatile BlockTable *V = T;          /* keys of slots below n are final (written before n moved, fenced) */
+		const int n = V->n;
+		cn = 0;
+		if (n > 0 && V->keynull[0] == 0) { c00 = V->key[0][0]; c01 = V->key[0][1]; cn = 1; }
+		if (cn == 1 && n > 1 && V->keynull[1] == 0) { c10 = V->key[1][0]; c11 = V->key[1][1]; cn = 2; }
+		if (cn == 2 && n > 2 && V->keynull[2] == 0) { c20 = V->key[2][0]; c21 = V->key[2][1]; cn = 3; }
+		if (cn == 3 && n > 3 && V->keynull[3] == 0) { c30 = V->key[3][0]; c31 = V->key[3][1]; cn = 4; }
+	}
 	__device__ __forceinline__ bool group(bool live)
 	{
 		if (JOIN && suppress) live = false;
 		if (nkeys == 0) gid = live ? 0 : -1;
+		else if (nkeys <= 2)
+		{
+			int g = -1;
+			if (knull == 0)
+			{
+				if (cn > 0 && k0 == c00 && k1 == c01) g = 0;
+				else if (cn > 1 && k0 == c10 && k1 == c11) g = 1;
+				else if (cn > 2 && k0 == c20 && k1 == c21) g = 2;
+				else if (cn > 3 && k0 == c30 && k1 == c31) g = 3;
+			}
+			const bool need = live && g < 0;
+			if (__any_sync(GG_FULL_MASK, need))
+			{
+				uint64_t k[GG_MAX_KEYS] = { k0, k1, k2, k3 };
+				const int g2 = find_or_insert(T, k, knull, nkeys, gcap, need, lane, *err);
+				if (need) g = g2;
+				cache_refresh();
+			}
+			gid = live ? g : -1;
+		}
 		else
 		{
 			uint64_t k[GG_MAX_KEYS] = { k0, k1, k2, k3 };
@@ -634,7 +672,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		for (int s = 0; s < nstage; s++)
 		{
 			mbar_init(full_bar + s * 8, 1);
-			mbar_init(empty_bar + s * 8, ncons);
+			mbar_init(empty_bar + s * 8, prm.team > 0 ? prm.team : ncons);
 		}
 		T->n = (nkeys == 0) ? 1 : 0;               /* plain aggregation: the single group always exists */
 		T->lock = 0;
@@ -744,17 +782,26 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			sink.nsl = nsl; sink.nreg = nreg;
 			sink.rq.zero();
 			sink.cstride = (uint32_t) NT * 4;
+			sink.cn = 0; sink.c00 = sink.c01 = sink.c10 = sink.c11 = sink.c20 = sink.c21 = sink.c30 = sink.c31 = 0;
 			sink.sv = sv;
 			sink.jq = false; sink.nullext = false; sink.suppress = false;
 		}
 
-		/* Chunks (32 line pointers) are dealt round-robin over the consumer warps ACROSS pages: chunk c of this page
-		 * goes to warp (dealt + c) mod ncons, dealt = chunks of all earlier pages.  Consecutive pages therefore land
-		 * on disjoint warp sets, so the pages in flight in the ring are processed concurrently instead of queueing
-		 * behind the same few warps. */
-		int s = 0, dealt = 0;
+		/* Which warp works on which chunk (32 line pointers) of which page:
+		 *   teams (prm.team = TS > 0)  the consumer warps form ncons / TS teams; page `it` of this block belongs to team
+		 *       it mod nteams, whose warp j takes chunks j, j + TS, ...  A warp visits only its team's pages (header decode,
+		 *       barrier wait and release cost nothing on the others), and the teams work on different pages of the ring
+		 *       concurrently.  The host picks TS from the page density (6 chunks per page -> teams of 6).
+		 *   dealt (prm.team = 0)  every warp visits every page; chunk c of a page goes to warp (dealt + c) mod ncons, dealt =
+		 *       chunks of all earlier pages, so consecutive pages land on disjoint warp sets. */
+		const int TS = prm.team > 0 ? prm.team : ncons;
+		const int nteams = prm.team > 0 ? ncons / TS : 1;
+		const int team = prm.team > 0 ? warp / TS : 0;
+		const int tw = prm.team > 0 ? warp - team * TS : warp;
+		int s = team, dealt = 0;
 		uint32_t ph = 0;
-		for (uint32_t it = 0; it < npages; it++)
+		while (s >= nstage) { s -= nstage; ph ^= 1; }
+		for (uint32_t it = (uint32_t) team; it < npages && team < nteams; it += (uint32_t) nteams)
 		{
 			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
 			__syncwarp();
@@ -780,11 +827,15 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			const bool all_visible = (pd_flags & GG_PD_ALL_VISIBLE) != 0;     /* heapam.c:391 */
 			const int nchunks = (nitems + 31) >> 5;
 
-			int c0 = warp - dealt;
-			if (c0 < 0) c0 += ncons;
-			dealt += nchunks;
-			while (dealt >= ncons) dealt -= ncons;          /* nchunks <= 37: a handful of subtractions beats a division */
-			for (int c = c0; c < nchunks; c += ncons)
+			int c0 = tw;
+			if (prm.team == 0)
+			{
+				c0 = warp - dealt;
+				if (c0 < 0) c0 += ncons;
+				dealt += nchunks;
+				while (dealt >= ncons) dealt -= ncons;          /* nchunks <= 37: a handful of subtractions beats a division */
+			}
+			for (int c = c0; c < nchunks; c += TS)
 			{
 				const int idx = c * 32 + lane;
 				bool live = false;
@@ -984,7 +1035,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
-			if (++s == nstage) { s = 0; ph ^= 1; }
+			s += nteams;
+			while (s >= nstage) { s -= nstage; ph ^= 1; }
 		}
 		n_passed = sink.npassed;
 		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */
