@@ -112,6 +112,8 @@ struct gg_joinagg {
 	gg_scanagg *probe = nullptr;    /* the probe-side pipeline (outer scan -> probe -> Agg) */
 	unsigned long long *ent = nullptr, *d_cnt = nullptr;   /* d_cnt[0] line-pointer count, [1] rows inserted */
 	uint64_t slots = 0;
+	uint32_t stride = 0;            /* 64-bit words per table entry */
+	size_t ent_bytes = 0;           /* size of the allocation behind ent (kept across builds of the same size) */
 	uint64_t rows_built = 0, null_keys = 0;
 	bool filled = false;            /* right / full join: the unmatched inner rows have been emitted */
 	bool lasj_empty = false;        /* LASJ_NOTIN met a NULL inner key: the result is empty */
@@ -160,7 +162,6 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	gg_engine *e = j->eng;
 	cudaStream_t st = e->stream;
 	GG_CUDA(cudaSetDevice(e->device));
-	if (j->ent) { cudaFree(j->ent); j->ent = nullptr; }
 	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
 	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 3 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaEventRecord(j->ev0, st));
@@ -178,7 +179,10 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	if (slots > (1ull << 31)) { gg_set_error("inner relation too large for one hash table (%llu rows)", nlp); return GG_ERR_NOMEM; }
 	JoinTable jt;
 	memset(&jt, 0, sizeof jt);
+	/* header | keys | payload, padded to a whole 32-byte sector when that costs one word: an entry of 3 (7) words becomes 4
+	 * (8), so a probe step — header, keys and payload — touches exactly one (two) sectors instead of straddling */
 	jt.stride = (uint32_t) (1 + j->jp.nkeys + j->jp.npayload);
+	if ((jt.stride & 3) == 3) jt.stride++;
 	jt.mask = (uint32_t) (slots - 1);
 	jt.nkeys = j->jp.nkeys;
 	jt.npayload = j->jp.npayload;
@@ -187,12 +191,18 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	jt.keepnull = jt.mark_matched = (j->jp.jointype == GG_JOIN_RIGHT || j->jp.jointype == GG_JOIN_FULL);
 	for (int k = 0; k < j->jp.nkeys; k++) jt.keytypes |= (uint32_t) j->jp.keytype[k] << (2 * k);
 	const size_t bytes = (size_t) slots * jt.stride * 8;
-	cudaError_t ce = cudaMalloc((void **) &j->ent, bytes + 64);      /* slack: the fill-inner pass reads it in 16-byte multiples */
-	if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("hash table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
+	if (j->ent && j->ent_bytes != bytes) { cudaFree(j->ent); j->ent = nullptr; }      /* a rescan of the same inner side keeps the allocation */
+	if (!j->ent)
+	{
+		cudaError_t ce = cudaMalloc((void **) &j->ent, bytes + 64);      /* slack: the fill-inner pass reads it in 16-byte multiples */
+		if (ce != cudaSuccess) { cudaGetLastError(); j->ent = nullptr; gg_set_error("hash table of %zu bytes does not fit in device memory", bytes); return GG_ERR_NOMEM; }
+		j->ent_bytes = bytes;
+	}
 	GG_CUDA(cudaMemsetAsync(j->ent, 0, bytes, st));
 	jt.ent = j->ent;
 	jt.nbuilt = j->d_cnt + 1;
 	j->slots = slots;
+	j->stride = jt.stride;
 
 	ScanAggParams prm;
 	memset(&prm, 0, sizeof prm);
@@ -299,7 +309,7 @@ int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes,
 {
 	if (!j) return GG_ERR_ARG;
 	if (rows_built) *rows_built = j->rows_built;
-	if (table_bytes) *table_bytes = j->slots * (uint64_t) (1 + j->jp.nkeys + j->jp.npayload) * 8;
+	if (table_bytes) *table_bytes = j->slots * (uint64_t) j->stride * 8;
 	if (build_ms) *build_ms = j->build_ms;
 	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
 	return GG_OK;

@@ -1003,8 +1003,14 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 							{
 								/* header and keys are fetched together (one round trip to HBM per probe step, not two) */
 								e = jt.ent + (size_t) slot * jt.stride;
-								hdr = __ldg(e);
-								const unsigned long long ek0 = __ldg(e + 1);
+								unsigned long long ek0;
+								if ((jt.stride & 1) == 0)
+								{
+									/* entries of an even number of words start 16-byte aligned: header and first key in one request */
+									const ulonglong2 hk = __ldg((const ulonglong2 *) e);
+									hdr = hk.x; ek0 = hk.y;
+								}
+								else { hdr = __ldg(e); ek0 = __ldg(e + 1); }
 								const unsigned long long ek1 = jt.nkeys > 1 ? __ldg(e + 2) : 0ull;
 								slot = (slot + 1) & jt.mask;
 								if (hdr == 0) { probing = false; break; }
