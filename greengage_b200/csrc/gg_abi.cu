@@ -110,6 +110,7 @@ void gg_engine_free(gg_engine *e)
 	cudaStreamSynchronize(e->copy_stream);
 	cudaFree(e->final_scratch);
 	cudaFree(e->sort_scratch);
+	cudaFree(e->motion_state);
 	for (void *m : e->groups_pool) cudaFree(m);
 	cudaFreeHost(e->groups_mirror);
 	cudaEventDestroy(e->ev_start);

@@ -25,6 +25,7 @@ struct gg_engine {
 	size_t sort_scratch_bytes = 0;
 	std::vector<void *> groups_pool;     /* gg_groups buffers of the common size, recycled (gg_scanagg.cu) */
 	void *groups_mirror = nullptr;       /* pinned: status + records of one gg_groups_fetch */
+	void *motion_state = nullptr;        /* gg_motion_partition: region cursors, error flags, counters (device) */
 };
 
 struct gg_relation {

@@ -2,6 +2,7 @@
  * gg_motion.cu — the sending side of a Redistribute Motion on the device (include/ggb200.h gg_motion_partition):
  * the scan kernel body in its MODE_PART role (interpreter path) and the host call around it.
  */
+#include <cstdlib>
 #include <vector>
 #include "gg_pipeline.h"
 
@@ -36,8 +37,9 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	if (r->rowwords != prog.outer.rowwords) { gg_set_error("relation format does not match the plan's tuple descriptor"); return GG_ERR_ARG; }
 	if (r->rowwords && (first_block != 0 || nblocks != r->nblocks)) { gg_set_error("datum-row relations are scanned whole"); return GG_ERR_ARG; }
 	cudaStream_t st = e->stream;
-	unsigned long long *d_state = nullptr;          /* [nsegs] cursors, [1] error flags, [2] counters */
-	GG_CUDA(cudaMalloc((void **) &d_state, (size_t) (nsegs + 4) * 8));
+	/* [nsegs] cursors, [1] error flags, [2] counters: one small block per engine, kept across calls */
+	if (!e->motion_state) GG_CUDA(cudaMalloc(&e->motion_state, (size_t) (1024 + 4) * 8));
+	unsigned long long *d_state = (unsigned long long *) e->motion_state;
 	cudaError_t ce = cudaMemsetAsync(d_state, 0, (size_t) (nsegs + 4) * 8, st);
 	ScanAggParams prm;
 	memset(&prm, 0, sizeof prm);
@@ -48,7 +50,7 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	prm.counters = d_state + nsegs + 1;
 	prm.nstage = 2;
 	const int ncons = 7;
-	prm.scratch_per_warp = ((prog.outer.ncols * 64 + 15) & ~15) + 16;
+	prm.scratch_per_warp = ((prog.outer.ncols * 64 + 15) & ~15) + 512 + 16;     /* column offsets + the warp's claim windows */
 	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 	prm.mo.rows = (unsigned long long *) device_out_rows;
 	prm.mo.cursor = d_state;
@@ -56,6 +58,16 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	prm.mo.nsegs = nsegs;
 	prm.mo.rowwords = 1 + npayload;
 	for (int k = 0; k < nkeys; k++) prm.mo.hashtypes |= (uint32_t) hashtype[k] << (4 * k);
+	{
+		/* claim windows (MotionOut.window): as large as keeps the unused tails of all warps below 1/8 of a region */
+		const uint64_t warps = (uint64_t) e->sm_count * 2 * ncons;
+		const uint64_t w = prm.mo.cap / (warps * 8);
+		uint32_t window = 0;
+		if (nsegs <= 32 && w >= 32) { window = 32; while (window * 2 <= w && window < 1024) window *= 2; }
+		const char *env = getenv("GGB200_MOTION_WINDOW");            /* experiments: 0 = exact claims */
+		if (env && nsegs <= 32) { int v = atoi(env); if (v == 0 || (v >= 32 && v <= 4096)) window = (uint32_t) v; }
+		prm.mo.window = window;
+	}
 	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
 	if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gg_motion_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_start, st);
@@ -81,7 +93,6 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	std::vector<unsigned long long> host((size_t) nsegs + 4);
 	if (ce == cudaSuccess) ce = cudaMemcpyAsync(host.data(), d_state, (size_t) (nsegs + 4) * 8, cudaMemcpyDeviceToHost, st);
 	if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-	cudaFree(d_state);
 	if (ce != cudaSuccess) return gg_cuda_fail(ce, "gg_motion_partition");
 	uint32_t flags = (uint32_t) host[(size_t) nsegs];
 	for (int d = 0; d < nsegs; d++)

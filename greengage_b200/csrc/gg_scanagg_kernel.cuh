@@ -99,7 +99,14 @@ struct MotionOut {
 	uint64_t cap;
 	int nsegs, rowwords;
 	uint32_t hashtypes;                   /* 4 bits per hash key: ggp_hashtype */
+	/* > 0: a warp claims rows of a destination's region `window` at a time and hands them out from shared memory, so the
+	 * region cursors (a handful of addresses every warp of the grid would otherwise hit once per 32 rows) see 1 / window of
+	 * the atomics.  What a warp has claimed and not used when the kernel ends is marked dead (GG_ROW_DEAD in the row's mask
+	 * word): the region stays one contiguous run of rows, a few of which no consumer sees.  0: exact claims, no dead rows
+	 * (small inputs, more than 32 destinations). */
+	uint32_t window;
 };
+#define GG_ROW_DEAD 0x8000000000000000ull  /* datum rows: mask word bit 63 = not a row (skipped by every consumer) */
 
 /* Join hash table (Hash / HashJoin, nodeHash.c:88-176,906-1222): open addressing, linear probing, one
  * slot per inner row (duplicate keys simply occupy successive slots), entries of `stride` 64-bit words:
@@ -420,6 +427,7 @@ struct PartSink {
 	bool nonfinite;
 	int gid, lane;
 	uint32_t vnull;
+	uint32_t win;                /* shared address of this warp's claim windows: [32] x { next free row, end } u64 */
 	__device__ __forceinline__ void begin_row() { h = 0; row = nullptr; nullmask = 0; }
 	__device__ __forceinline__ bool filter(bool pass) { return pass; }
 	__device__ __forceinline__ void key(int kc, uint64_t v, bool isnull)
@@ -447,11 +455,33 @@ struct PartSink {
 		/* one atomic per destination present in the warp */
 		const uint32_t peers = __match_any_sync(GG_FULL_MASK, live ? (uint32_t) dest : 0x80000000u + (uint32_t) lane);
 		const int leader = __ffs(peers) - 1;
-		unsigned long long base = 0;
-		if (live && lane == leader) base = atomicAdd(&mo.cursor[dest], (unsigned long long) __popc(peers));
+		const int cnt = __popc(peers);
+		unsigned long long base = 0, base2 = 0;
+		int split = cnt;                      /* rows [0, split) of the group go to base, the rest to base2 (a fresh window) */
+		if (live && lane == leader)
+		{
+			if (mo.window == 0) base = atomicAdd(&mo.cursor[dest], (unsigned long long) cnt);
+			else
+			{
+				const uint32_t wa = win + (uint32_t) dest * 16;
+				const unsigned long long b = lds64(wa), e = lds64(wa + 8);
+				base = b;
+				if (b + (unsigned long long) cnt <= e) sts64(wa, b + (unsigned long long) cnt);
+				else
+				{
+					split = (int) (e - b);
+					base2 = atomicAdd(&mo.cursor[dest], (unsigned long long) mo.window);
+					sts64(wa, base2 + (unsigned long long) (cnt - split));
+					sts64(wa + 8, base2 + mo.window);
+				}
+			}
+		}
 		base = __shfl_sync(GG_FULL_MASK, base, leader);
+		base2 = __shfl_sync(GG_FULL_MASK, base2, leader);
+		split = __shfl_sync(GG_FULL_MASK, split, leader);
 		if (!live) return false;
-		const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+		const int rank = __popc(peers & ((1u << lane) - 1));
+		const unsigned long long pos = rank < split ? base + (unsigned long long) rank : base2 + (unsigned long long) (rank - split);
 		if (pos >= mo.cap) { *err |= GGP_EF_TABLE_FULL; return false; }
 		row = mo.rows + ((uint64_t) dest * mo.cap + pos) * (uint64_t) mo.rowwords;
 		row[0] = 0;
@@ -766,6 +796,9 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		else if constexpr (MODE == MODE_PART)
 		{
 			sink.mo = prm.mo; sink.lane = lane;
+			sink.win = sv;                       /* the per-warp scratch behind the column offsets */
+			sts64(sv + (uint32_t) lane * 16, 0); sts64(sv + (uint32_t) lane * 16 + 8, 0);
+			__syncwarp();
 		}
 		else if constexpr (MODE == MODE_HASH)
 		{
@@ -860,11 +893,12 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					X.fast = true;
 					X.tv.tp = rp + 8;
 					X.tv.colnull = 0;
+					const uint64_t mask = live ? lds64(rp) : 0;
+					if (mask & GG_ROW_DEAD) live = false;      /* claimed by a sending Motion and never filled */
 					if (live)
 					{
 						n_scanned++;
 						uint32_t cn = 0;
-						const uint64_t mask = lds64(rp);
 						for (int sl = 0; sl < ncols; sl++) cn |= (uint32_t) ((mask >> P.outer.colatt[sl]) & 1) << sl;
 						X.tv.colnull = cn;
 						if (!NULLABLE && cn) { err |= GGP_EF_NOTNULL_VIOLATED; live = false; }
@@ -1043,6 +1077,19 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
 			s += nteams;
 			while (s >= nstage) { s -= nstage; ph ^= 1; }
+		}
+		if constexpr (MODE == MODE_PART)
+		{
+			/* what this warp claimed of each region and did not fill is marked dead */
+			__syncwarp();
+			if (prm.mo.window > 0 && lane < prm.mo.nsegs)
+			{
+				const unsigned long long b = lds64(sink.win + (uint32_t) lane * 16);
+				unsigned long long e = lds64(sink.win + (uint32_t) lane * 16 + 8);
+				if (e > prm.mo.cap) e = prm.mo.cap;
+				for (unsigned long long r = b; r < e; r++)
+					prm.mo.rows[((uint64_t) lane * prm.mo.cap + r) * (uint64_t) prm.mo.rowwords] = GG_ROW_DEAD;
+			}
 		}
 		n_passed = sink.npassed;
 		if (sink.nonfinite) err |= GGP_EF_SAW_INF;     /* an infinite/NaN input legitimises an infinite sum */

@@ -586,7 +586,8 @@ static int run_rows_node(GgPlanState *s)
 				uint64_t nlp = 0;
 				rc = gg_relation_count_rows(s->rel, &nlp);
 				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
-				s->rows_cap = N == 1 ? nlp + 2 : (nlp / (uint64_t) N + nlp / (uint64_t) (10 * N) + 8192) * (uint64_t) N;
+				/* + 1/4: a hash does not spread perfectly, and the sending kernel leaves up to 1/8 of a region as dead slots */
+				s->rows_cap = (nlp / (uint64_t) N + nlp / (uint64_t) (4 * N) + 8192) * (uint64_t) N;
 			}
 			words = s->rows_cap * (uint64_t) W + 8;
 			rc = gg_relation_create(es->engine, (words * 8 + GG_BLCKSZ - 1) / GG_BLCKSZ, &s->rows_send);
@@ -645,23 +646,29 @@ static int rows_to_host(GgPlanState *s)
 	if (alloc_result(s, (int64_t) n, s->rows_ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
 	if (n)
 	{
+		uint64_t live = 0;
 		buf = malloc((size_t) nb * GG_BLCKSZ);
 		if (!buf) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
 		rc = gg_relation_read(s->rows_recv && s->rows_nsegs > 1 ? s->rows_recv : s->rows_send, 0, buf, nb);
 		if (rc != GG_OK) { free(buf); exec_fail(rc, "%s", gg_last_error()); return -1; }
 		for (r = 0; r < n; r++)
+		{
+			if (buf[r * W] & GG_DATUMROW_DEAD) continue;          /* a slot the sending kernel claimed and did not fill */
 			for (c = 0; c < s->rows_ncols; c++)
 			{
 				const uint64_t v = buf[r * W + 1 + c];
-				s->values[r * s->rows_ncols + c] = (int64_t) v;
-				s->isnull[r * s->rows_ncols + c] = (uint8_t) ((buf[r * W] >> c) & 1);
+				s->values[live * s->rows_ncols + c] = (int64_t) v;
+				s->isnull[live * s->rows_ncols + c] = (uint8_t) ((buf[r * W] >> c) & 1);
 				if (is_string_type(s->typid[c]))
 				{
 					int l = 0;
 					while (l < 8 && ((v >> (8 * l)) & 0xff)) l++;
-					s->lens[r * s->rows_ncols + c] = l;
+					s->lens[live * s->rows_ncols + c] = l;
 				}
 			}
+			live++;
+		}
+		s->nrows = (int64_t) live;
 		free(buf);
 	}
 	s->rows_ready = 1;

@@ -137,9 +137,12 @@ typedef struct gg_attr {
  *                     column i as a Datum in loaded form (int4/date sign-extended, float8 bits, short strings
  *                     packed LSB-first, bpchar blank-stripped).  This is what a receiving Motion hands to the
  *                     node above it — the device analogue of the MinimalTuples tupser.c serialises
- *                     (cdbmotion.c:378-470): every operator that scans heap pages also scans these rows. */
+ *                     (cdbmotion.c:378-470): every operator that scans heap pages also scans these rows.
+ *                     Bit 63 of the mask word marks a slot that holds no row (a sending Motion claimed it and did not
+ *                     fill it): consumers skip it. */
 #define GG_FMT_HEAP      0
 #define GG_FMT_DATUMROWS 1
+#define GG_DATUMROW_DEAD 0x8000000000000000ull
 
 typedef struct gg_tupdesc {
 	int32_t natts;

@@ -168,7 +168,10 @@ int  gg_sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, 
  * scan qual, the hash-key expressions and the expressions that travel for every tuple, computes the destination
  * segment bit-exactly (cdbhash + jump consistent hash), and writes GG_FMT_DATUMROWS rows of 1 + npayload words into
  * the destination's region of device_out_rows: region d = rows [d * cap, d * cap + host_counts[d]) with
- * cap = (out_cap_rows / nsegs) rounded down to even; host_offsets[d] = d * cap.  GG_ERR_NOMEM if a region overflows
+ * cap = (out_cap_rows / nsegs) rounded down to even; host_offsets[d] = d * cap.  On large inputs the warps claim rows of a
+ * region in windows; the few rows a warp claimed and did not fill are marked dead (bit 63 of the row's mask word) and are
+ * skipped by every consumer, so host_counts[d] is the length of the region's run of rows, dead ones included: size
+ * out_cap_rows with 1/8 of slack per region.  GG_ERR_NOMEM if a region overflows
  * (gg_last_error says how many rows the fullest destination receives).  The exchange itself is an all-to-all of the
  * regions over NCCL (greengage_b200/motion.py); the receiver wraps what it got with gg_relation_attach_rows. */
 int  gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
