@@ -210,9 +210,11 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	prm.nblocks = nblocks;
 	prm.errflags = j->probe->d_err;
 	prm.counters = j->probe->d_counters;    /* reset below: the probe's counters describe the outer side */
-	prm.nstage = 2;
+	const gg_npconfig nc = gg_np_config(7, 2);
+	prm.nstage = nc.nstage;
+	prm.team = nc.team;
 	prm.gcap = 0;
-	const int ncons = 7;
+	const int ncons = nc.ncons;
 	prm.scratch_per_warp = ((j->jp.build.outer.ncols * 64 + 15) & ~15) + 16;
 	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 	prm.jt = jt;
@@ -220,13 +222,15 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	const size_t smem = prm.scratch_off + (size_t) ncons * prm.scratch_per_warp;
 	{
 		char jmsg[512];
-		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, 256, e->device, jmsg, sizeof jmsg);
+		const int threads = (ncons + 1) * 32;
+		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0);
 		if (jk)
 		{
 			void *args[] = { (void *) &j->jp.build, (void *) &prm };
 			GG_CUDA(cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st));
+			GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * nc.ctas), dim3(threads), args, smem, st));
 		}
+		else if (threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		else
 			gg_joinbuild_kernel<<<e->sm_count * 2, 256, smem, st>>>(j->jp.build, prm);
 	}

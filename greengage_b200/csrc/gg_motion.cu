@@ -48,8 +48,11 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	prm.nrows = r->nrows;
 	prm.errflags = (uint32_t *) (d_state + nsegs);
 	prm.counters = d_state + nsegs + 1;
-	prm.nstage = 2;
-	const int ncons = 7;
+	const gg_npconfig nc = gg_np_config(7, 2);
+	prm.nstage = nc.nstage;
+	prm.team = nc.team;
+	const int ncons = nc.ncons;
+	const int threads = (ncons + 1) * 32;
 	prm.scratch_per_warp = ((prog.outer.ncols * 64 + 15) & ~15) + 512 + 16;     /* column offsets + the warp's claim windows */
 	prm.scratch_off = (uint32_t) (((size_t) prm.nstage * GG_BLCKSZ + (size_t) prm.nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 	prm.mo.rows = (unsigned long long *) device_out_rows;
@@ -60,7 +63,7 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	for (int k = 0; k < nkeys; k++) prm.mo.hashtypes |= (uint32_t) hashtype[k] << (4 * k);
 	{
 		/* claim windows (MotionOut.window): as large as keeps the unused tails of all warps below 1/8 of a region */
-		const uint64_t warps = (uint64_t) e->sm_count * 2 * ncons;
+		const uint64_t warps = (uint64_t) e->sm_count * nc.ctas * ncons;
 		const uint64_t w = prm.mo.cap / (warps * 8);
 		uint32_t window = 0;
 		if (nsegs <= 32 && w >= 32) { window = 32; while (window * 2 <= w && window < 1024) window *= 2; }
@@ -74,13 +77,14 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	if (ce == cudaSuccess)
 	{
 		char jmsg[512];
-		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, 256, e->device, jmsg, sizeof jmsg);
+		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0);
 		if (jk)
 		{
 			void *args[] = { (void *) &prog, (void *) &prm };
 			ce = cudaFuncSetAttribute((const void *) jk->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-			if (ce == cudaSuccess) ce = cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * 2), dim3(256), args, smem, st);
+			if (ce == cudaSuccess) ce = cudaLaunchKernel((const void *) jk->kernel, dim3(e->sm_count * nc.ctas), dim3(threads), args, smem, st);
 		}
+		else if (threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		else
 		{
 			gg_motion_part_kernel<<<e->sm_count * 2, 256, smem, st>>>(prog, prm);

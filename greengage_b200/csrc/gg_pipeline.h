@@ -5,11 +5,27 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "gg_scanagg_kernel.cuh"
 #include "gg_engine.h"
 #include "gg_jit.h"
+
+/* Launch configuration of the kernels that run two small blocks per SM by default (hash build, Motion send, general
+ * HashAggregate, the transposed / nullable scan and probe variants): consumer warps per block, ring stages, team size
+ * (ScanAggParams.team) and blocks per SM.  GGB200_NP_CONFIG="ncons,stages,team,ctas" overrides it for experiments; block
+ * sizes other than the default need the run-time specialised kernel (the interpreter kernels are built for 256 threads). */
+struct gg_npconfig { int ncons, nstage, team, ctas; bool forced; };
+static inline gg_npconfig gg_np_config(int ncons, int nstage)
+{
+	gg_npconfig c = { ncons, nstage, 0, 2, false };
+	const char *env = getenv("GGB200_NP_CONFIG");
+	int a, b, t = 0, k = 2;
+	if (env && sscanf(env, "%d,%d,%d,%d", &a, &b, &t, &k) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && t >= 0 && t <= a && k >= 1 && k <= 4)
+	{ c.ncons = a; c.nstage = b; c.team = t; c.ctas = k; c.forced = true; }
+	return c;
+}
 
 #define GG_MERGE_CAP 1024          /* merged groups the fast path holds per segment */
 #define GG_STREAM_CHUNK_BLOCKS 8192 /* 256 MB staging chunks for gg_scanagg_run_host */
@@ -31,6 +47,7 @@ struct gg_scanagg {
 	int regslots = -1;              /* private-accumulator variant: trailing value slots kept in registers (-1: not decided) */
 	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
 	int team = 0;                   /* consumer warps per team (ScanAggParams.team); 0: chunks dealt across all warps */
+	bool np_forced = false;         /* launch configuration came from GGB200_NP_CONFIG */
 	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */
 	ggd::HashAggTable ha = {};           /* MODE_HASH: the group table in HBM */
 	void *ha_mem = nullptr;

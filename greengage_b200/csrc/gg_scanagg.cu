@@ -352,30 +352,37 @@ static int scanagg_configure(gg_scanagg *p)
 	}
 	else
 	{
-		/* 2 CTAs/SM x (7 consumer warps + producer = 8 warps) */
-		p->ctas_per_sm = 2;
-		p->threads = 8 * 32;
-		const int ncons = 7;
+		/* 2 CTAs/SM x (7 consumer warps + producer = 8 warps) unless configured otherwise */
+		const gg_npconfig nc = gg_np_config(7, 3);
+		p->ctas_per_sm = nc.ctas;
+		p->threads = (nc.ncons + 1) * 32;
+		p->nstage = nc.nstage;
+		p->team = nc.team;
+		p->np_forced = nc.forced;
+		const int ncons = nc.ncons;
 		p->gcap = GGP_MAX_PAIRS / V < GGP_FAST_GROUPS ? GGP_MAX_PAIRS / V : GGP_FAST_GROUPS;
 		p->scratch_off = (uint32_t) (((size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 		p->cnt_off = p->acc_off = 0;
-		const size_t per_cta_2 = (e->smem_optin + 1024) / 2 - 1024;   /* 1 KB reserved per CTA */
+		const size_t per_cta = (e->smem_optin + 1024) / (size_t) nc.ctas - 1024;   /* 1 KB reserved per CTA */
 		p->smem = p->scratch_off + (size_t) ncons * p->scratch_per_warp;
-		if (p->smem > per_cta_2)
+		if (p->smem > per_cta && !nc.forced)
 		{
 			p->nstage = 2;
 			p->scratch_off = (uint32_t) (((size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 15) & ~(size_t) 15);
 			p->smem = p->scratch_off + (size_t) ncons * p->scratch_per_warp;
 		}
-		if (p->smem > per_cta_2) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
+		if (p->smem > per_cta) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
 		if (p->smem < 32 * 1024) p->smem = 32 * 1024;             /* the epilogue reuses the ring as reduction scratch */
+		if ((size_t) ncons * GGP_MAX_PAIRS * 24 > p->smem) p->smem = (size_t) ncons * GGP_MAX_PAIRS * 24;    /* Red[ncons][GGP_MAX_PAIRS] */
 	}
 	p->grid = e->sm_count * p->ctas_per_sm;
 	if (p->mode == MODE_HASH || p->is_join)
 	{
 		char jmsg[512];
-		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, p->is_join ? p->join_probe_pc : -1);
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, p->is_join ? p->join_probe_pc : -1, 0,
+		                        p->mode != MODE_PRIV && p->np_forced ? p->ctas_per_sm : 0);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
+		if (!p->jit && p->mode != MODE_PRIV && p->threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
 	}
 	if (p->is_join) return gg_probe_kernel_prepare(p);
@@ -386,8 +393,10 @@ static int scanagg_configure(gg_scanagg *p)
 	}
 	{
 		char jmsg[512];
-		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, -1, p->regslots);
+		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, -1, p->regslots,
+		                        p->mode != MODE_PRIV && p->np_forced ? p->ctas_per_sm : 0);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
+		if (!p->jit && p->mode != MODE_PRIV && p->threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		if (!p->jit && p->regslots > 0)
 		{
 			/* the interpreter kernel addresses value slots dynamically: everything in shared memory */
