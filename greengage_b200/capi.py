@@ -206,6 +206,9 @@ def dev_lib():
         L.gg_joinagg_probe_host.argtypes = [vp, vp, u64]
         L.gg_joinagg_fetch.argtypes = [vp, C.POINTER(gg_aggrow), i32, C.POINTER(i32), C.POINTER(u64)]
         L.gg_joinagg_reset.argtypes = [vp]
+        L.gg_joinagg_set_work_mem.argtypes = [vp, u64]
+        L.gg_joinagg_run.argtypes = [vp, vp, vp]
+        L.gg_joinagg_nbatch.argtypes = [vp]
         L.gg_joinagg_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.gg_joinagg_free.argtypes = [vp]
         L.gg_joinagg_free.restype = None

@@ -119,6 +119,24 @@ struct gg_joinagg {
 	bool lasj_empty = false;        /* LASJ_NOTIN met a NULL inner key: the result is empty */
 	float build_ms = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	unsigned long long *d_buildcnt = nullptr;   /* rows scanned / passed by the build kernel (kept apart from the probe's counters) */
+	/* hybrid hash join (nodeHash.c:713,1132; gg_joinagg_set_work_mem / gg_joinagg_run): the plan as given, and what a
+	 * batched run builds from it */
+	gg_scan outer_scan, inner_scan;
+	gg_hashjoin hj;
+	gg_agg agg;
+	gg_exprpool pool;
+	uint64_t work_mem = 0;
+	int nbatch = 1;                 /* batches of the last run */
+	int log2_nbuckets = 0;
+	gg_joinagg *bj = nullptr;       /* the join of one batch pair: the same plan over the partitions' datum rows */
+	gg_exprpool *ipool = nullptr;   /* `pool` with the inner side's Vars as varno 0: what partitions the inner relation */
+	int32_t otargets[GGP_MAX_ACCS], itargets[GGP_MAX_ACCS];   /* expression roots that travel, per side: join keys first */
+	int notargets = 0, nitargets = 0;
+	gg_relation *obuf = nullptr, *ibuf = nullptr;            /* the partitions: nbatch regions of datum rows each */
+	uint64_t ocap = 0, icap = 0;                             /* rows per region */
+	std::vector<uint64_t> ocounts, icounts;
+	float part_ms = 0;
 };
 
 int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj,
@@ -144,7 +162,9 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 	if (p->prog.nullable) p->prog.priv_ok = 0;
 	rc = scanagg_finish_create(p, &j->probe);
 	if (rc) { delete j; return rc; }
+	j->outer_scan = *outer; j->inner_scan = *inner; j->hj = *hj; j->agg = *agg; j->pool = *pool;
 	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 3 * sizeof(unsigned long long)));
+	GG_CUDA(cudaMalloc((void **) &j->d_buildcnt, 2 * sizeof(unsigned long long)));
 	GG_CUDA(cudaEventCreate(&j->ev0));
 	GG_CUDA(cudaEventCreate(&j->ev1));
 	GG_CUDA(cudaFuncSetAttribute(gg_joinbuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -209,7 +229,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	prm.pages = pages;
 	prm.nblocks = nblocks;
 	prm.errflags = j->probe->d_err;
-	prm.counters = j->probe->d_counters;    /* reset below: the probe's counters describe the outer side */
+	prm.counters = j->d_buildcnt;           /* the probe's counters describe the outer side only */
 	const gg_npconfig nc = gg_np_config(7, 2);
 	prm.nstage = nc.nstage;
 	prm.team = nc.team;
@@ -239,7 +259,6 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	GG_CUDA(cudaEventRecord(j->ev1, st));
 	unsigned long long nb[2] = { 0, 0 };
 	GG_CUDA(cudaMemcpyAsync(nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
-	GG_CUDA(cudaMemsetAsync(j->probe->d_counters, 0, 2 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaStreamSynchronize(st));
 	GG_CUDA(cudaEventElapsedTime(&j->build_ms, j->ev0, j->ev1));
 	j->rows_built = nb[0];
@@ -267,9 +286,9 @@ int gg_joinagg_probe_host(gg_joinagg *j, const void *host_pages, uint64_t nblock
 	return gg_scanagg_run_host(j->probe, host_pages, nblocks);
 }
 
-int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
+/* HJ_FILL_INNER_TUPLES of a right / full join, for the table as it stands (nodeHashjoin.c:460-490) */
+static int joinagg_fill_inner(gg_joinagg *j)
 {
-	if (!j) return GG_ERR_ARG;
 	if (j->probe->jt.mark_matched && !j->filled && j->ent)
 	{
 		/* HJ_FILL_INNER_TUPLES: every outer row has been through the probe; what is still unmatched in the table comes
@@ -284,7 +303,213 @@ int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint6
 		p->fed.push_back({ (const uint8_t *) j->ent, nullptr, chunks, j->slots, true });
 		j->filled = true;
 	}
+	return GG_OK;
+}
+
+int gg_joinagg_fetch(gg_joinagg *j, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
+{
+	if (!j) return GG_ERR_ARG;
+	if (j->bj && j->nbatch > 1) return gg_scanagg_fetch(j->bj->probe, out, outcap, nout, nullptr, rows_joined);   /* every batch was filled as it went */
+	int rc = joinagg_fill_inner(j);
+	if (rc) return rc;
 	return gg_scanagg_fetch(j->probe, out, outcap, nout, nullptr, rows_joined);
+}
+
+/* ---- hybrid hash join: batches (nodeHash.c:713 ExecHashIncreaseNumBatches, :1132 ExecHashGetBucketAndBatch) ----
+ * When the hash table of the whole inner side would not fit the operator's memory, both inputs are split by the batch bits
+ * of the join's hash value — the reference's hash function (per key: rotate left one bit, xor the key type's hash function,
+ * nodeHash.c:1044-1085) and its bit usage (batchno = (hashvalue >> log2_nbuckets) & (nbatch - 1)) — with the kernel that
+ * also sends Motions, into nbatch regions of datum rows each (the columns the join and the aggregate above it need; the
+ * scan quals are applied on the way), and the batches are joined pair by pair into ONE aggregate state.  Where the reference
+ * writes batch files (nodeHashjoin.c:906,1083), the partitions stay in device memory: the budget bounds the hash table. */
+static void collect_vars(const gg_exprpool &pool, int32_t root, int varno, std::vector<int32_t> &nodes)
+{
+	if (root < 0 || root >= pool.nnodes) return;
+	const gg_expr &x = pool.nodes[root];
+	if (x.kind == GG_E_VAR)
+	{
+		if (x.varno != varno) return;
+		for (int32_t n : nodes) if (pool.nodes[n].varattno == x.varattno) return;
+		nodes.push_back(root);
+		return;
+	}
+	for (int a = 0; a < x.nargs && a < 2; a++) collect_vars(pool, x.args[a], varno, nodes);
+}
+
+/* compile the batch-pair join: the plan with every Var above the join renumbered to its column in the partition rows */
+static int joinagg_prepare_batches(gg_joinagg *j)
+{
+	if (j->bj) return GG_OK;
+	const gg_exprpool &pool = j->pool;
+	std::vector<int32_t> ov, iv;
+	const int32_t above[] = { j->hj.joinqual };
+	for (int32_t r : above) { collect_vars(pool, r, 0, ov); collect_vars(pool, r, 1, iv); }
+	for (int c = 0; c < j->agg.numCols; c++) { collect_vars(pool, j->agg.grpCol[c], 0, ov); collect_vars(pool, j->agg.grpCol[c], 1, iv); }
+	for (int a = 0; a < j->agg.numAggs; a++) { collect_vars(pool, j->agg.aggs[a].arg, 0, ov); collect_vars(pool, j->agg.aggs[a].arg, 1, iv); }
+	const int nk = j->hj.nkeys;
+	if (nk + (int) ov.size() > GGP_MAX_ACCS || nk + (int) iv.size() > GGP_MAX_ACCS || pool.nnodes + 2 * nk > GG_MAX_EXPR_NODES)
+	{ gg_set_error("batched hash join: too many columns travel (%zu outer, %zu inner)", ov.size() + nk, iv.size() + nk); return GG_ERR_UNSUPPORTED; }
+	j->notargets = j->nitargets = 0;
+	for (int k = 0; k < nk; k++) { j->otargets[j->notargets++] = j->hj.outerkey[k]; j->itargets[j->nitargets++] = j->hj.innerkey[k]; }
+	for (int32_t n : ov) j->otargets[j->notargets++] = n;
+	for (int32_t n : iv) j->itargets[j->nitargets++] = n;
+	/* the batch join's pool: Vars above the join -> their column of the partition rows; the join keys -> new Vars */
+	std::vector<gg_exprpool> pb(1);
+	gg_exprpool &bp = pb[0];
+	bp = pool;
+	for (int n = 0; n < bp.nnodes; n++)
+	{
+		gg_expr &x = bp.nodes[n];
+		if (x.kind != GG_E_VAR) continue;
+		const std::vector<int32_t> &side = x.varno == 0 ? ov : iv;
+		for (size_t i = 0; i < side.size(); i++)
+			if (pool.nodes[side[i]].varattno == x.varattno) { x.varattno = (int16_t) (nk + (int) i + 1); break; }
+	}
+	gg_hashjoin hj2 = j->hj;
+	for (int k = 0; k < nk; k++)
+		for (int sidei = 0; sidei < 2; sidei++)
+		{
+			gg_expr v;
+			memset(&v, 0, sizeof v);
+			v.kind = GG_E_VAR; v.varno = (int16_t) sidei; v.varattno = (int16_t) (k + 1);
+			v.rettype = pool.nodes[sidei == 0 ? j->hj.outerkey[k] : j->hj.innerkey[k]].rettype;
+			bp.nodes[bp.nnodes] = v;
+			if (sidei == 0) hj2.outerkey[k] = bp.nnodes; else hj2.innerkey[k] = bp.nnodes;
+			bp.nnodes++;
+		}
+	/* the partitions' descriptors: one 8-byte Datum per travelling expression; a plain Var of a NOT NULL column stays so */
+	gg_scan os, is;
+	memset(&os, 0, sizeof os); memset(&is, 0, sizeof is);
+	os.qual = is.qual = -1;
+	for (int sidei = 0; sidei < 2; sidei++)
+	{
+		gg_scan &sc = sidei == 0 ? os : is;
+		const gg_scan &base = sidei == 0 ? j->outer_scan : j->inner_scan;
+		const int nt = sidei == 0 ? j->notargets : j->nitargets;
+		const int32_t *t = sidei == 0 ? j->otargets : j->itargets;
+		sc.desc.natts = nt;
+		sc.desc.format = GG_FMT_DATUMROWS;
+		for (int i = 0; i < nt; i++)
+		{
+			const gg_expr &x = pool.nodes[t[i]];
+			gg_attr &a = sc.desc.attrs[i];
+			a.atttypid = x.rettype; a.atttypmod = -1; a.attlen = 8; a.attalign = 'd'; a.attbyval = 1;
+			a.attnotnull = (x.kind == GG_E_VAR && x.varattno >= 1 && x.varattno <= base.desc.natts) ? base.desc.attrs[x.varattno - 1].attnotnull : 0;
+		}
+	}
+	int rc = gg_joinagg_create(j->eng, &os, &is, &hj2, &j->agg, &bp, &j->bj);
+	if (rc) return rc;
+	/* the inner relation is partitioned by a program that sees it as "the scan": its Vars as varno 0 */
+	j->ipool = new gg_exprpool(pool);
+	for (int n = 0; n < j->ipool->nnodes; n++)
+		if (j->ipool->nodes[n].kind == GG_E_VAR) j->ipool->nodes[n].varno = j->ipool->nodes[n].varno == 1 ? 0 : 1;
+	return GG_OK;
+}
+
+/* one pass over the batches: build batch b's table, probe with batch b, fill unmatched inner rows; everything accumulates
+ * in the batch join's aggregate state */
+static int joinagg_run_batches(gg_joinagg *j)
+{
+	gg_joinagg *b = j->bj;
+	const int Wo = 1 + j->notargets, Wi = 1 + j->nitargets;
+	j->build_ms = 0; j->rows_built = 0; j->null_keys = 0;
+	for (int k = 0; k < j->nbatch; k++)
+	{
+		gg_relation *irel = nullptr, *orel = nullptr;
+		int rc = gg_relation_attach_rows(j->eng, j->ibuf->pages + (uint64_t) k * j->icap * Wi * 8, j->icounts[(size_t) k], j->nitargets, &irel);
+		if (rc == GG_OK) rc = gg_relation_attach_rows(j->eng, j->obuf->pages + (uint64_t) k * j->ocap * Wo * 8, j->ocounts[(size_t) k], j->notargets, &orel);
+		if (rc == GG_OK) rc = gg_joinagg_build(b, irel, 0, irel->nblocks);
+		if (rc == GG_OK) { j->build_ms += b->build_ms; j->rows_built += b->rows_built; j->null_keys += b->null_keys; }
+		if (rc == GG_OK && !b->lasj_empty) rc = gg_scanagg_run(b->probe, orel, 0, orel->nblocks);
+		if (rc == GG_OK) rc = joinagg_fill_inner(b);
+		gg_relation_free(irel);
+		gg_relation_free(orel);
+		if (rc) return rc;
+	}
+	return GG_OK;
+}
+
+int gg_joinagg_set_work_mem(gg_joinagg *j, uint64_t bytes)
+{
+	if (!j) return GG_ERR_ARG;
+	j->work_mem = bytes;
+	return GG_OK;
+}
+
+int gg_joinagg_nbatch(gg_joinagg *j) { return j ? j->nbatch : 0; }
+
+int gg_joinagg_run(gg_joinagg *j, gg_relation *inner, gg_relation *outer)
+{
+	if (!j || !inner || !outer) return GG_ERR_ARG;
+	gg_engine *e = j->eng;
+	uint64_t nlp = 0;
+	int rc = gg_relation_count_rows(inner, &nlp);
+	if (rc) return rc;
+	uint64_t slots = 1024;
+	while (slots < 2 * nlp) slots <<= 1;
+	uint32_t stride = (uint32_t) (1 + j->jp.nkeys + j->jp.npayload);
+	if ((stride & 3) == 3) stride++;
+	const uint64_t bytes = slots * stride * 8;
+	j->nbatch = 1;
+	/* NOT IN needs to know about a NULL inner key anywhere before any outer row is judged (nodeHashjoin.c:220-239): one batch */
+	if (!j->work_mem || bytes <= j->work_mem || j->jp.jointype == GG_JOIN_LASJ_NOTIN)
+	{
+		rc = gg_joinagg_build(j, inner, 0, inner->nblocks);
+		if (rc == GG_OK) rc = gg_joinagg_probe(j, outer, 0, outer->nblocks);
+		return rc;
+	}
+	int nbatch = 2;
+	while ((uint64_t) nbatch * j->work_mem < 2 * bytes && nbatch < 1024) nbatch <<= 1;     /* x2: tables are sized in powers of two */
+	rc = joinagg_prepare_batches(j);
+	if (rc) return rc;
+	j->nbatch = nbatch;
+	/* ExecChooseHashTableSize (nodeHash.c:450-659): nbuckets = a power of two near tuples per batch / gp_hashjoin_tuples_per_bucket */
+	{
+		uint64_t per = nlp / (uint64_t) nbatch / 5 + 1, nb = 1024;
+		int l2 = 10;
+		while (nb < per && l2 < 30) { nb <<= 1; l2++; }
+		j->log2_nbuckets = l2;
+	}
+	uint64_t nouter = 0;
+	rc = gg_relation_count_rows(outer, &nouter);
+	if (rc) return rc;
+	GG_CUDA(cudaEventRecord(j->ev0, e->stream));
+	for (int side = 0; side < 2; side++)
+	{
+		gg_relation *rel = side == 0 ? outer : inner;
+		gg_relation *&buf = side == 0 ? j->obuf : j->ibuf;
+		uint64_t &cap = side == 0 ? j->ocap : j->icap;
+		std::vector<uint64_t> &counts = side == 0 ? j->ocounts : j->icounts;
+		const int nt = side == 0 ? j->notargets : j->nitargets;
+		const uint64_t rows = side == 0 ? nouter : nlp;
+		const int W = 1 + nt;
+		uint64_t want = (rows / (uint64_t) nbatch + rows / (uint64_t) (4 * nbatch) + 8192) & ~1ull;
+		for (int attempt = 0; ; attempt++)
+		{
+			if (buf && (cap < want || buf->nblocks * (uint64_t) GG_BLCKSZ < (want * nbatch * W + 8) * 8)) { gg_relation_free(buf); buf = nullptr; }
+			if (!buf)
+			{
+				rc = gg_relation_create(e, ((want * nbatch * W + 8) * 8 + GG_BLCKSZ - 1) / GG_BLCKSZ, &buf);
+				if (rc) return rc;
+				cap = want;
+			}
+			counts.assign((size_t) nbatch, 0);
+			std::vector<uint64_t> offs((size_t) nbatch);
+			rc = gg_partition_rows(e, side == 0 ? &j->outer_scan : &j->inner_scan, side == 0 ? &j->pool : j->ipool,
+			                       side == 0 ? j->hj.outerkey : j->hj.innerkey, j->hj.nkeys, side == 0 ? j->otargets : j->itargets, nt,
+			                       nbatch, 1, j->log2_nbuckets, rel, 0, rel->nblocks, buf->pages, cap * (uint64_t) nbatch, counts.data(), offs.data());
+			if (rc != GG_ERR_NOMEM || attempt >= 3) break;
+			want *= 2;                      /* a skewed key: one batch got more than its share */
+		}
+		if (rc) return rc;
+	}
+	GG_CUDA(cudaEventRecord(j->ev1, e->stream));
+	GG_CUDA(cudaEventSynchronize(j->ev1));
+	GG_CUDA(cudaEventElapsedTime(&j->part_ms, j->ev0, j->ev1));
+	rc = gg_scanagg_reset(j->bj->probe);
+	if (rc) return rc;
+	j->bj->probe->replay_hook = [j]() { return joinagg_run_batches(j); };
+	return joinagg_run_batches(j);
 }
 
 /* the joined-and-aggregated result as device-resident group records (after gg_joinagg_fetch ran the last pass) */
@@ -292,7 +517,7 @@ int gg_scanagg_groups(gg_scanagg *p, gg_groups **out);
 int gg_joinagg_groups(gg_joinagg *j, gg_groups **out)
 {
 	if (!j) return GG_ERR_ARG;
-	return gg_scanagg_groups(j->probe, out);
+	return gg_scanagg_groups(j->bj && j->nbatch > 1 ? j->bj->probe : j->probe, out);
 }
 
 int gg_joinagg_reset(gg_joinagg *j)
@@ -306,6 +531,7 @@ int gg_joinagg_reset(gg_joinagg *j)
 		j->eng->launches++;
 	}
 	j->filled = false;
+	if (j->bj) { int rc = gg_joinagg_reset(j->bj); if (rc) return rc; }
 	return gg_scanagg_reset(j->probe);
 }
 
@@ -315,19 +541,23 @@ int gg_joinagg_stats(gg_joinagg *j, uint64_t *rows_built, uint64_t *table_bytes,
 	if (rows_built) *rows_built = j->rows_built;
 	if (table_bytes) *table_bytes = j->slots * (uint64_t) j->stride * 8;
 	if (build_ms) *build_ms = j->build_ms;
-	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->probe, probe_ms, nullptr);
+	if (probe_ms) return gg_scanagg_scan_kernel_ms(j->bj && j->nbatch > 1 ? j->bj->probe : j->probe, probe_ms, nullptr);
 	return GG_OK;
 }
 
-int gg_joinagg_variant(gg_joinagg *j) { return j ? gg_scanagg_variant(j->probe) : -1; }
+int gg_joinagg_variant(gg_joinagg *j) { return j ? gg_scanagg_variant(j->bj && j->nbatch > 1 ? j->bj->probe : j->probe) : -1; }
 
 void gg_joinagg_free(gg_joinagg *j)
 {
 	if (!j) return;
 	cudaSetDevice(j->eng->device);
 	cudaStreamSynchronize(j->eng->stream);
+	if (j->bj) gg_joinagg_free(j->bj);
+	delete j->ipool;
+	if (j->obuf) gg_relation_free(j->obuf);
+	if (j->ibuf) gg_relation_free(j->ibuf);
 	if (j->probe) gg_scanagg_free(j->probe);
-	cudaFree(j->ent); cudaFree(j->d_cnt);
+	cudaFree(j->ent); cudaFree(j->d_cnt); cudaFree(j->d_buildcnt);
 	if (j->ev0) cudaEventDestroy(j->ev0);
 	if (j->ev1) cudaEventDestroy(j->ev1);
 	delete j;

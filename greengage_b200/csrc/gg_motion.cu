@@ -24,6 +24,19 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
                         void *device_out_rows, uint64_t out_cap_rows,
                         uint64_t *host_counts, uint64_t *host_offsets)
 {
+	return gg_partition_rows(e, scan, pool, hashkeys, nkeys, payload, npayload, nsegs, 0, 0, r, first_block, nblocks,
+	                         device_out_rows, out_cap_rows, host_counts, host_offsets);
+}
+
+}  /* extern "C" */
+
+/* the same kernel with either routing rule (MotionOut.route): segments of a Motion, or batches of a hybrid hash join */
+int gg_partition_rows(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
+                      const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
+                      int nsegs, int route, int shift, gg_relation *r, uint64_t first_block, uint64_t nblocks,
+                      void *device_out_rows, uint64_t out_cap_rows,
+                      uint64_t *host_counts, uint64_t *host_offsets)
+{
 	if (!e || !scan || !pool || !hashkeys || !payload || !r || !host_counts || nsegs < 1 || nsegs > 1024 ||
 	    nblocks > r->nblocks || first_block > r->nblocks - nblocks || (!device_out_rows && out_cap_rows))
 		return GG_ERR_ARG;
@@ -60,6 +73,9 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	prm.mo.cap = (out_cap_rows / (uint64_t) nsegs) & ~1ull;      /* even: every region starts 16-byte aligned */
 	prm.mo.nsegs = nsegs;
 	prm.mo.rowwords = 1 + npayload;
+	prm.mo.route = (uint32_t) route;
+	prm.mo.shift = (uint32_t) shift;
+	if (route && (nsegs & (nsegs - 1))) { gg_set_error("batch routing needs a power-of-two batch count"); return GG_ERR_ARG; }
 	for (int k = 0; k < nkeys; k++) prm.mo.hashtypes |= (uint32_t) hashtype[k] << (4 * k);
 	{
 		/* claim windows (MotionOut.window): as large as keeps the unused tails of all warps below 1/8 of a region */
@@ -113,5 +129,3 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 	}
 	return gg_errflags_to_code(flags);
 }
-
-}  /* extern "C" */

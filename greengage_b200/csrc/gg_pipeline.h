@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <vector>
 #include "gg_scanagg_kernel.cuh"
 #include "gg_engine.h"
@@ -74,6 +75,9 @@ struct gg_scanagg {
 	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; };
 	std::vector<Fed> fed;
 	bool has_state = false;
+	/* set by a batched join: how to feed the inputs again (its batches, each with its own hash table) when fetch has to
+	 * replay them on a wider kernel variant; empty: replay `fed` */
+	std::function<int()> replay_hook;
 	/* host staging for the streamed path */
 	uint8_t *stage[2] = { nullptr, nullptr };
 	cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
@@ -83,6 +87,13 @@ struct gg_scanagg {
 int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out);      /* after p->prog / p->aggmap are compiled */
 /* one launch of the pipeline's kernel over device pages (fill_inner: the HJ_FILL_INNER_TUPLES pass of a right/full join) */
 int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0, bool fill_inner = false);
+/* gg_motion.cu: the partitioning kernel behind gg_motion_partition, with the routing rule as a parameter (route 0: segments by
+ * cdbhash + jump consistent hash; route 1: hash-join batches by the batch bits above `shift`) */
+int gg_partition_rows(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,
+                      const int32_t *hashkeys, int nkeys, const int32_t *payload, int npayload,
+                      int nsegs, int route, int shift, gg_relation *r, uint64_t first_block, uint64_t nblocks,
+                      void *device_out_rows, uint64_t out_cap_rows,
+                      uint64_t *host_counts, uint64_t *host_offsets);
 /* gg_join.cu: the probe-side kernels of a join pipeline (interpreter path) */
 int gg_probe_kernel_prepare(gg_scanagg *p);
 int gg_probe_kernel_launch(gg_scanagg *p, const ggd::ScanAggParams &prm, cudaStream_t st);

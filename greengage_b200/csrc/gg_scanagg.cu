@@ -816,12 +816,16 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 			if (p->ha_mem) { GG_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(p->ha_mem); p->ha_mem = nullptr; }
 			rc2 = gg_scanagg_reset(p);
 			if (rc2) return rc2;
-			for (const auto &f : replay)
+			if (p->replay_hook) { rc2 = p->replay_hook(); if (rc2) return rc2; }
+			else
 			{
-				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
-				if (rc2) return rc2;
+				for (const auto &f : replay)
+				{
+					rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
+					if (rc2) return rc2;
+				}
+				p->fed = replay;
 			}
-			p->fed = replay;
 			return gg_scanagg_fetch(p, out, outcap, nout, rows_scanned, rows_passed);
 		}
 		if (rows_scanned) *rows_scanned = counters[0];
@@ -872,12 +876,16 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 		p->nrecs_total = GG_MERGE_CAP + p->grid * GGP_FAST_GROUPS;
 		rc2 = gg_scanagg_reset(p);
 		if (rc2) return rc2;
-		for (const auto &f : replay)
+		if (p->replay_hook) { rc2 = p->replay_hook(); if (rc2) return rc2; }
+		else
 		{
-			rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
-			if (rc2) return rc2;
+			for (const auto &f : replay)
+			{
+				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
+				if (rc2) return rc2;
+			}
+			p->fed = replay;
 		}
-		p->fed = replay;
 		return gg_scanagg_fetch(p, out, outcap, nout, rows_scanned, rows_passed);
 	}
 	if (rows_scanned) *rows_scanned = counters[0];

@@ -105,6 +105,10 @@ struct MotionOut {
 	 * word): the region stays one contiguous run of rows, a few of which no consumer sees.  0: exact claims, no dead rows
 	 * (small inputs, more than 32 destinations). */
 	uint32_t window;
+	/* how a row's hash value picks its region: 0 = a segment (cdbhashreduce: jump consistent hash, cdbhash.c:255-287);
+	 * 1 = a hash-join batch, the reference's bit usage (ExecHashGetBucketAndBatch, nodeHash.c:1132-1151):
+	 * batchno = (hashvalue >> log2_nbuckets) & (nbatch - 1), nsegs = nbatch a power of two, shift = log2_nbuckets */
+	uint32_t route, shift;
 };
 #define GG_ROW_DEAD 0x8000000000000000ull  /* datum rows: mask word bit 63 = not a row (skipped by every consumer) */
 
@@ -451,7 +455,7 @@ struct PartSink {
 	}
 	__device__ __forceinline__ bool group(bool live)
 	{
-		const int dest = jump_consistent_hash((uint64_t) h, mo.nsegs);
+		const int dest = mo.route ? (int) ((h >> mo.shift) & (uint32_t) (mo.nsegs - 1)) : jump_consistent_hash((uint64_t) h, mo.nsegs);
 		/* one atomic per destination present in the warp */
 		const uint32_t peers = __match_any_sync(GG_FULL_MASK, live ? (uint32_t) dest : 0x80000000u + (uint32_t) lane);
 		const int leader = __ffs(peers) - 1;

@@ -200,6 +200,15 @@ class JoinAgg:
     def reset(self):
         check(dev_lib().gg_joinagg_reset(self.h))
 
+    def set_work_mem(self, nbytes):
+        """the operator's memory: a hash table larger than this makes run() join in batches (0 = no limit)"""
+        check(dev_lib().gg_joinagg_set_work_mem(self.h, int(nbytes)))
+
+    def run(self, inner, outer):
+        """build + probe over whole relations, in batches when the hash table would exceed the work memory"""
+        check(dev_lib().gg_joinagg_run(self.h, inner.h, outer.h))
+        return dev_lib().gg_joinagg_nbatch(self.h)
+
     def fetch(self, cap=4096):
         out = (capi.gg_aggrow * cap)()
         n = C.c_int(0)

@@ -75,7 +75,7 @@ class GgEState(C.Structure):
                 ("nsegs", C.c_int32), ("segindex", C.c_int32), ("transport", C.POINTER(GgMotionTransport)),
                 ("es_processed", C.c_uint64), ("interconnect", C.c_void_p),
                 ("host_pages", C.c_void_p * GG_MAX_RELATIONS), ("host_nblocks", C.c_uint64 * GG_MAX_RELATIONS),
-                ("motion_on_host", C.c_int32), ("pad", C.c_int32)]
+                ("motion_on_host", C.c_int32), ("pad", C.c_int32), ("es_operator_mem", C.c_uint64)]
 
 
 _lib = None
@@ -185,10 +185,11 @@ class PlanBuilder:
 class Executor:
     """One slice on one segment: ExecInitNode at construction, rows() drives ExecProcNode to end of stream."""
 
-    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None, interconnect=None):
+    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None, interconnect=None, operator_mem=0):
         """relations[i]: a device-resident Relation, or (host address, nblocks) for pages in host memory, or None"""
         L = exec_lib()
         self.es = GgEState()
+        self.es.es_operator_mem = int(operator_mem)
         self.es.engine = eng.h if hasattr(eng, "h") else eng
         self._pool = pool
         self.es.pool = C.pointer(pool)

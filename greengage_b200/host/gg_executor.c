@@ -759,8 +759,9 @@ static int run_node(GgPlanState *s)
 			{
 				gg_relation *irel = s->inner ? s->inner->rows_rel : s->inner_rel;
 				gg_relation *orel = s->child ? s->child->rows_rel : s->rel;
-				rc = gg_joinagg_build(s->ja, irel, 0, gg_relation_nblocks(irel));
-				if (rc == GG_OK) rc = gg_joinagg_probe(s->ja, orel, 0, gg_relation_nblocks(orel));
+				/* MultiExecHash + the probe loop; in batches when the table would not fit the operator's memory */
+				rc = gg_joinagg_set_work_mem(s->ja, es->es_operator_mem);
+				if (rc == GG_OK) rc = gg_joinagg_run(s->ja, irel, orel);
 			}
 			/* fetch decides whether the pipeline has to be replayed on a wider kernel variant (more groups than expected, a
 			 * non-finite sum to attribute), so it runs before anything above consumes the records on the device */

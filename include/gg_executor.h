@@ -149,6 +149,9 @@ typedef struct GgEState {
 	 * not fit the device-resident path); 0 at query start */
 	int32_t motion_on_host;
 	int32_t pad;
+	/* the operator's share of statement_mem in bytes (PlanStateOperatorMemKB, execnodes.h:1446): a HashJoin whose table of
+	 * the whole inner side would be larger runs as a hybrid hash join, in batches (gg_joinagg_run); 0 = no limit */
+	uint64_t es_operator_mem;
 } GgEState;
 
 typedef struct GgPlanState GgPlanState;        /* execnodes.h PlanState */

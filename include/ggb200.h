@@ -134,6 +134,14 @@ int  gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner,
 int  gg_joinagg_build(gg_joinagg *p, gg_relation *inner, uint64_t first_block, uint64_t nblocks);
 int  gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, uint64_t nblocks);
 int  gg_joinagg_probe_host(gg_joinagg *p, const void *host_pages, uint64_t nblocks);   /* outer pages in host memory, streamed */
+/* Hybrid hash join (nodeHash.c:713 ExecHashIncreaseNumBatches, :1132 ExecHashGetBucketAndBatch; nodeHashjoin.c:906,1083):
+ * `bytes` is the operator's memory (PlanStateOperatorMemKB, execnodes.h:1446) the hash table has to fit; 0 = no limit.
+ * gg_joinagg_run builds and probes whole relations; when the table of the whole inner side would be larger than that, both
+ * sides are split into nbatch = 2^k partitions by the batch bits of the reference's hash value (the partitions are datum rows
+ * in device memory, not files) and the batches are joined one after the other into the same aggregate. */
+int  gg_joinagg_set_work_mem(gg_joinagg *p, uint64_t bytes);
+int  gg_joinagg_run(gg_joinagg *p, gg_relation *inner, gg_relation *outer);
+int  gg_joinagg_nbatch(gg_joinagg *p);            /* batches of the last gg_joinagg_run (1: one hash table held everything) */
 int  gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined);
 int  gg_joinagg_reset(gg_joinagg *p);      /* ExecReScanHashJoin with the hash table kept (nodeHashjoin.c:1015-1050) */
 int  gg_joinagg_stats(gg_joinagg *p, uint64_t *rows_built, uint64_t *table_bytes, float *build_ms, float *probe_ms);

@@ -107,6 +107,14 @@ int gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, ui
 	return GG_OK;
 }
 
+int gg_joinagg_set_work_mem(gg_joinagg *p, uint64_t bytes) { (void) p; (void) bytes; return GG_OK; }
+int gg_joinagg_run(gg_joinagg *p, gg_relation *inner, gg_relation *outer)
+{
+	p->ipages = inner->pages; p->inb = inner->nblocks;
+	p->opages = outer->pages; p->onb = outer->nblocks;
+	return GG_OK;
+}
+
 int gg_joinagg_fetch(gg_joinagg *p, gg_aggrow *out, int outcap, int *nout, uint64_t *rows_joined)
 {
 	return fail(or_hashjoin_agg(&p->outer, &p->inner, &p->hj, &p->agg, &p->pool, p->opages, p->onb, p->ipages, p->inb,

@@ -161,3 +161,61 @@ def test_unsupported_join_shapes_are_refused(eng):
     with pytest.raises(capi.GGError) as e:
         JoinAgg(eng, outer, inner, hj, agg, pool)
     assert e.value.code == -6
+
+
+def gpu_join_batched(eng, outer, inner, hj, agg, pool, opages, ipages, work_mem):
+    from greengage_b200.engine import JoinAgg, Relation
+    ja = JoinAgg(eng, outer, inner, hj, agg, pool)
+    orel = Relation(eng, host_pages=opages) if opages.size else Relation(eng, nblocks=0)
+    irel = Relation(eng, host_pages=ipages) if ipages.size else Relation(eng, nblocks=0)
+    try:
+        ja.set_work_mem(work_mem)
+        nbatch = ja.run(irel, orel)
+        rows, nj = ja.fetch()
+        ja.reset()                                   # ExecReScanHashJoin: the same answer again, batches and all
+        nbatch2 = ja.run(irel, orel)
+        rows2, nj2 = ja.fetch()
+        assert nbatch2 == nbatch and nj2 == nj and len(rows2) == len(rows)
+        return rows, nj, nbatch, ja.stats()
+    finally:
+        ja.free()
+        orel.free()
+        irel.free()
+
+
+@pytest.mark.parametrize("jointype", [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_RIGHT, capi.JOIN_FULL, capi.JOIN_SEMI, capi.JOIN_ANTI])
+@pytest.mark.parametrize("nkeys", [1, 2])
+def test_hybrid_hash_join_batches_small_relations(eng, jointype, nkeys):
+    """A hash table that does not fit the operator's memory (artificially tiny here): both sides are split by the batch bits of
+    the reference's hash value and joined batch by batch — duplicates, NULL keys, a join qual, every join type that has a
+    probe side; the answer is the one-table oracle's (nodeHash.c:713,1132; nodeHashjoin.c:906)."""
+    odesc, idesc, orows, onulls, irows, inulls, opages, ipages = small_relations()
+    p, outer, inner, hj = join_nodes(odesc, idesc, jointype, nkeys, True)
+    grp = [p.var(2, capi.BPCHAROID, 1)] if jointype in BOTH_SIDES else [p.var(2, capi.BPCHAROID, 0)]
+    aggs = [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(3, capi.FLOAT8OID, 0))]
+    if jointype in BOTH_SIDES:
+        aggs += [(capi.AGG_SUM_INT4, p.var(3, capi.INT4OID, 1)), (capi.AGG_COUNT_ANY, p.var(1, capi.INT4OID, 1))]
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, grp, aggs)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, p.pool, opages, ipages)
+    got, nj, nbatch, st = gpu_join_batched(eng, outer, inner, hj, agg, p.pool, opages, ipages, work_mem=8192)
+    assert nbatch >= 2
+    assert nj == nj_want
+    assert_aggrows_match(got, want, agg)
+
+
+@pytest.mark.parametrize("kind,jointype", [("survey", capi.JOIN_INNER), ("q3ish", capi.JOIN_INNER), ("q3ish", capi.JOIN_LEFT), ("count", capi.JOIN_ANTI)])
+def test_hybrid_hash_join_build_side_larger_than_the_budget(eng, kind, jointype):
+    """lineitem ⋈ orders with the operator's memory at a fraction of the hash table the inner side needs: 4 to 16 batches."""
+    li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 400_000, seed=5, norders=90_000))
+    od, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 70_000, seed=5))
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, kind, jointype)
+    want, nj_want = po.hashjoin_agg(outer, inner, hj, agg, pool, li, od)
+    one, nj_one, _ = gpu_joinagg(eng, outer, inner, hj, agg, pool, li, od)
+    table_bytes = _["table_bytes"]
+    got, nj, nbatch, st = gpu_join_batched(eng, outer, inner, hj, agg, pool, li, od, work_mem=table_bytes // 5)
+    assert 4 <= nbatch <= 16
+    assert nj == nj_want == nj_one and nj > 0
+    assert_aggrows_match(got, want, agg)
+    # and with memory to spare nothing is batched
+    got1, nj1, nbatch1, _ = gpu_join_batched(eng, outer, inner, hj, agg, pool, li, od, work_mem=table_bytes * 2)
+    assert nbatch1 == 1 and nj1 == nj_want
