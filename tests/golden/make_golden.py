@@ -17,6 +17,10 @@
   aocs_kat.npz      append-only column-oriented (AOCS) column files written by the reference's datumstreamblock.o +
                     cdbappendonlystorageformat.o, what its reader returns for them, and CRC-32C known answers
   sort_golden.json  ORDER BY answers of expected/sort.out for the column types the Sort path takes, ASC/DESC, NULLS FIRST/LAST
+  memtuple_kat.json MemTuples formed by the reference's memtuple.o (create_memtuple_binding / memtuple_form_to) for rows with
+                    NULLs, short and long varlenas, > 32 attributes and tuples beyond the 2-byte-offset limit, the bindings
+                    themselves, what memtuple_deform reads back, and the same rows as tuple chunks out of the reference's
+                    tupser.o / tupchunklist.o (SerializeTuple, both the MemTuple and the heap-tuple form, several chunk sizes)
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
 import ctypes as C
@@ -150,6 +154,93 @@ def heap_kat():
         meta[name] = [[desc.attrs[i].atttypid, desc.attrs[i].attlen, chr(desc.attrs[i].attalign), desc.attrs[i].attbyval] for i in range(desc.natts)]
     json.dump({"descs": meta, "cases": out}, open(os.path.join(HERE, "heap_kat.json"), "w"))
     print("heap_kat.json", len(out))
+
+
+def memtuple_kat():
+    """MemTuple + tuple-chunk goldens out of the reference's memtuple.o / tupser.o (oracle/ref_build/refwrap_motion.c)"""
+    rng = random.Random(20260923)          # its own stream: the other fixtures do not change when this one is regenerated
+    TY = {"int8": (20, 8, 'd', 1), "int4": (23, 4, 'i', 1), "int2": (21, 2, 's', 1), "bool": (16, 1, 'c', 1), "float8": (701, 8, 'd', 1),
+          "date": (1082, 4, 'i', 1), "bpchar": (1042, -1, 'i', 0), "varchar": (1043, -1, 'i', 0), "text": (25, -1, 'i', 0), "f8arr": (1022, -1, 'd', 0)}
+    descs = {
+        "q1_partial": ["bpchar", "bpchar", "float8", "float8", "float8", "float8", "f8arr", "f8arr", "f8arr", "int8"],    # what a PARTIAL Q1 ships
+        "ints4": ["int4", "int4", "date", "bpchar"],                                                                       # 4-byte column alignment
+        "mixed": ["int4", "bpchar", "int8", "varchar", "float8", "date", "text", "int2", "bool", "int8", "int2", "bool"],
+        "wide40": ["int4", "int8", "bool", "varchar", "int2"] * 8,                                                         # NULL bitmap beyond the free 4 bytes
+        "strings": ["text", "int2", "text", "bool", "varchar"],
+    }
+    meta, cases = {}, []
+    for name, cols in descs.items():
+        n = len(cols)
+        attrs = (capi.gg_attr * n)()
+        for i, c in enumerate(cols):
+            t, l, al, bv = TY[c]
+            attrs[i].atttypid, attrs[i].attlen, attrs[i].attalign, attrs[i].attbyval, attrs[i].attnotnull, attrs[i].atttypmod = t, l, ord(al), bv, 0, -1
+        meta[name] = {"cols": [list(TY[c]) for c in cols], "bind": {}}
+        for large in (0, 1):
+            o6, info = (C.c_int32 * (6 * n))(), (C.c_int32 * 2)()
+            vs = R.ref_memtuple_binding(n, attrs, large, o6, info)
+            meta[name]["bind"]["large" if large else "small"] = {"var_start": vs, "att": [list(o6[6 * i:6 * i + 6]) for i in range(n)]}
+            meta[name]["column_align"], meta[name]["null_bitmap_extra"] = info[0], info[1]
+        for case in range(40):
+            pnull = rng.choice([0.0, 0.0, 0.15, 0.5, 0.9])
+            big = name == "strings" and case % 8 == 0
+            vals, lens, nulls, pyvals, keep = (C.c_int64 * n)(), (C.c_int32 * n)(), (C.c_uint8 * n)(), [], []
+            for i, c in enumerate(cols):
+                t, l, al, bv = TY[c]
+                if rng.random() < pnull:
+                    nulls[i] = 1
+                    pyvals.append(None)
+                    continue
+                if l == -1:
+                    if c == "f8arr":
+                        pay = struct.pack("<iiIii3d", 1, 0, 701, 3, 1, float(rng.randint(0, 10 ** 6)), rng.uniform(-1e9, 1e9), rng.uniform(0, 1e12))
+                    else:
+                        ln = rng.choice([0, 1, 2, 7, 8, 9, 25, 125, 126, 127, 128, 300]) if not big else rng.choice([40000, 70000])
+                        pay = bytes(rng.choice(b"abcdefg hij") for _ in range(ln))
+                    buf = C.create_string_buffer(pay, max(len(pay), 1))
+                    keep.append(buf)
+                    vals[i], lens[i] = C.addressof(buf), len(pay)
+                    pyvals.append(pay.hex() if len(pay) <= 400 else "x%d:%d" % (len(pay), pay[0]))
+                    if len(pay) > 400:                      # long payloads are regenerated from (length, byte): keep them uniform
+                        pay = bytes([pay[0]]) * len(pay)
+                        buf = C.create_string_buffer(pay, len(pay))
+                        keep.append(buf)
+                        vals[i] = C.addressof(buf)
+                elif c == "float8":
+                    x = rng.choice([0.0, 1.0, -2.5, rng.uniform(-1e5, 1e5)])
+                    vals[i] = f2b(x)
+                    pyvals.append(str(f2b(x)))
+                else:
+                    bits = {8: 64, 4: 32, 2: 16, 1: 1}[l]
+                    x = rng.getrandbits(bits) - (2 ** (bits - 1) if bits > 1 else 0)
+                    vals[i] = x
+                    pyvals.append(str(x))
+            cap = 200000
+            outbuf = (C.c_uint8 * cap)()
+            ln = R.ref_memtuple_form(n, attrs, vals, lens, nulls, outbuf, cap)
+            mt = bytes(outbuf[:ln])
+            dv, dn = (C.c_int64 * n)(), (C.c_uint8 * n)()
+            R.ref_memtuple_deform(n, attrs, (C.c_uint8 * ln).from_buffer_copy(mt), dv, dn)
+            rec = {"desc": name, "values": pyvals, "deform": [str(dv[i]) for i in range(n)], "deform_null": [int(dn[i]) for i in range(n)]}
+            if ln <= 4096:
+                rec["memtuple"] = mt.hex()
+            else:
+                import hashlib
+                rec["memtuple_len"], rec["memtuple_sha1"] = ln, hashlib.sha1(mt).hexdigest()
+            if ln <= 4096:
+                rec["chunks"] = {}
+                for mc in (8124, 64, 16):
+                    nch = C.c_int32(0)
+                    cb = (C.c_uint8 * (4 * ln + 4096))()
+                    t = R.ref_serialize_tuple(n, attrs, vals, lens, nulls, 0, mc, cb, len(cb), C.byref(nch))
+                    rec["chunks"][str(mc)] = [bytes(cb[:t]).hex(), nch.value]
+                nch = C.c_int32(0)
+                cb = (C.c_uint8 * (4 * ln + 4096))()
+                t = R.ref_serialize_tuple(n, attrs, vals, lens, nulls, 1, rng.choice([8124, 48]), cb, len(cb), C.byref(nch))
+                rec["heap_chunks"] = bytes(cb[:t]).hex()
+            cases.append(rec)
+    json.dump({"descs": meta, "cases": cases}, open(os.path.join(HERE, "memtuple_kat.json"), "w"))
+    print("memtuple_kat.json", len(cases))
 
 
 def float_kat():
@@ -478,6 +569,10 @@ def aocs_kat():
 
 if __name__ == "__main__":
     R.ref_last_error.restype = C.c_char_p
+    if len(sys.argv) > 1:                  # only the named fixtures: python make_golden.py memtuple_kat
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     hash_kat()
     heap_kat()
     float_kat()
@@ -487,3 +582,4 @@ if __name__ == "__main__":
     sort_fixture()
     onek_fixture()
     aocs_kat()
+    memtuple_kat()
