@@ -277,8 +277,8 @@ static void chunk_header(uint8_t *p, uint32_t size, uint32_t type) { store_le(p,
 static int64_t chunk_bytes(const uint8_t *data, uint32_t n, int max_chunk, uint8_t *out, uint64_t cap, int32_t *nchunks)
 {
 	/* addByteStringToChunkList (tupser.c:320-370): the byte string fills chunks of at most max_chunk bytes, header included;
-	 * one chunk: TC_WHOLE; several: PARTIAL_START, PARTIAL_MID ..., PARTIAL_END.  Each chunk's data is padded to 4 in the
-	 * packet (ic_common.c:200) */
+	 * one chunk: TC_WHOLE; several: PARTIAL_START, PARTIAL_MID ..., PARTIAL_END.  Each chunk's data is padded to
+	 * TUPLE_CHUNK_ALIGN in the packet (ic_common.c:200): not at all on x86 */
 	const uint32_t room = (uint32_t) max_chunk - GG_TUPLE_CHUNK_HEADER_SIZE;
 	uint32_t done = 0;
 	uint64_t pos = 0;
@@ -412,7 +412,7 @@ int gg_tupser_deserialize(const gg_memtuple_binding *b, const uint8_t *chunks, u
 		if (GG_TUPLE_CHUNK_HEADER_SIZE + (uint64_t) size > nbytes) return GG_ERR_BADPAGE;
 		ser = chunks + GG_TUPLE_CHUNK_HEADER_SIZE;
 		total = size;
-		pos = GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) size + 3) & ~3ull);
+		pos = GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) size + GG_TUPLE_CHUNK_ALIGN - 1) & ~(uint64_t) (GG_TUPLE_CHUNK_ALIGN - 1));
 	}
 	else if (type == GG_TC_PARTIAL_START)
 	{
@@ -427,7 +427,7 @@ int gg_tupser_deserialize(const gg_memtuple_binding *b, const uint8_t *chunks, u
 			if (first ? t != GG_TC_PARTIAL_START : (t != GG_TC_PARTIAL_MID && t != GG_TC_PARTIAL_END)) return GG_ERR_BADPAGE;
 			first = 0;
 			total += s;
-			p += GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) s + 3) & ~3ull);
+			p += GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) s + GG_TUPLE_CHUNK_ALIGN - 1) & ~(uint64_t) (GG_TUPLE_CHUNK_ALIGN - 1));
 			if (t == GG_TC_PARTIAL_END) break;
 		}
 		buf = malloc(total ? total : 1);
@@ -439,7 +439,7 @@ int gg_tupser_deserialize(const gg_memtuple_binding *b, const uint8_t *chunks, u
 				const uint32_t s = (uint32_t) load_le(chunks + q, 2);
 				memcpy(buf + w, chunks + q + GG_TUPLE_CHUNK_HEADER_SIZE, s);
 				w += s;
-				q += GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) s + 3) & ~3ull);
+				q += GG_TUPLE_CHUNK_HEADER_SIZE + (((uint64_t) s + GG_TUPLE_CHUNK_ALIGN - 1) & ~(uint64_t) (GG_TUPLE_CHUNK_ALIGN - 1));
 			}
 		}
 		ser = buf;
@@ -458,7 +458,7 @@ int gg_tupser_deserialize(const gg_memtuple_binding *b, const uint8_t *chunks, u
 		const int tnatts = (int) load_le(ser + 4, 2);
 		const uint32_t infomask = (uint32_t) load_le(ser + 6, 2);
 		const uint32_t nullslen = (infomask & 0x0001) ? (uint32_t) ((tnatts + 7) / 8) : 0;        /* HEAP_HASNULL, BITMAPLEN */
-		const uint32_t hdr = 8 + ((nullslen + 3) & ~3u);
+		const uint32_t hdr = 8 + ((nullslen + GG_TUPLE_CHUNK_ALIGN - 1) & ~(uint32_t) (GG_TUPLE_CHUNK_ALIGN - 1));
 		if (tuplen > total || hdr > tuplen) { free(buf); return GG_ERR_BADPAGE; }
 		rc = deform_heap_data(b, nullslen ? ser + 8 : NULL, tnatts, ser + hdr, tuplen - hdr, values, isnull, lens, ser);
 	}

@@ -6,10 +6,11 @@
  * cluster — has to put its rows on the interconnect exactly as the reference's senders do and read what they send:
  *     MemTuple            src/include/access/memtup.h:52-80, src/backend/access/common/memtuple.c:24-56 (layout),
  *                         :175-417 (create_col_bind), :551 (memtuple_form_to), :917 (memtuple_getattr)
- *     tuple chunks        src/include/cdb/tupchunk.h:21-49 (4-byte header {u16 size, u16 type}), TUPLE_CHUNK_ALIGN 4
- *                         (cdbvars.h:32), src/backend/cdb/motion/tupser.c:400-603 (SerializeTuple: a virtual / MemTuple slot
- *                         travels as its MemTuple; a heap tuple without toasted attributes as TupSerHeader ‖ null bitmap
- *                         (pad 4) ‖ data (pad 4), tupser.c:282-287,497-548), :609 (CvtChunksToTup)
+ *     tuple chunks        src/include/cdb/tupchunk.h:21-49 (4-byte header {u16 size, u16 type}), TUPLE_CHUNK_ALIGN (cdbvars.h:30-34:
+ *                         1, i.e. no padding, on everything but sparc), src/backend/cdb/motion/tupser.c:400-603 (SerializeTuple:
+ *                         a virtual / MemTuple slot travels as its MemTuple; a heap tuple without toasted attributes as
+ *                         TupSerHeader ‖ null bitmap ‖ data, each padded to TUPLE_CHUNK_ALIGN, tupser.c:282-287,497-548),
+ *                         :609 (CvtChunksToTup)
  * Byte-for-byte against the reference's own memtuple.o / tupser.o: tests/golden/memtuple_kat.json, tests/test_tupser.py.
  *
  * Rows cross this API the way the executor's slots hold them: one 64-bit Datum per column + null flags; a varlena column
@@ -65,10 +66,10 @@ uint32_t gg_memtuple_size(const uint8_t *mt);          /* memtuple_get_size */
 /* ---- tuple chunks ---- */
 enum { GG_TC_WHOLE = 0, GG_TC_PARTIAL_START = 1, GG_TC_PARTIAL_MID = 2, GG_TC_PARTIAL_END = 3, GG_TC_END_OF_STREAM = 4, GG_TC_EMPTY = 5 };
 #define GG_TUPLE_CHUNK_HEADER_SIZE 4
-#define GG_TUPLE_CHUNK_ALIGN 4
+#define GG_TUPLE_CHUNK_ALIGN 1          /* cdbvars.h:30-34: 4 on sparc only; everywhere else chunks and their parts are not padded */
 
-/* SerializeTuple for a row that travels as a MemTuple (tupser.c:436-494): the chunks, each {u16 size, u16 type} + data padded
- * to 4 bytes, back to back in out.  max_chunk = Gp_max_tuple_chunk_size (header included), e.g. 8192 - the packet header - 4.
+/* SerializeTuple for a row that travels as a MemTuple (tupser.c:436-494): the chunks, each {u16 size, u16 type} + data,
+ * back to back in out.  max_chunk = Gp_max_tuple_chunk_size (header included), e.g. 8192 - the packet header - 4.
  * Returns the number of bytes written (< 0: GG_ERR_*); *nchunks the chunk count. */
 int64_t gg_tupser_serialize(const gg_memtuple_binding *b, const int64_t *values, const uint8_t *isnull, const int32_t *lens,
                             const void *const *ptrs, int max_chunk, uint8_t *out, uint64_t cap, int32_t *nchunks);
