@@ -78,7 +78,7 @@ def build_device(verbose=False, force=False):
 def build_exec(force=False):
     """libggexec.so: the executor-node surface (host C) above the C-ABI of libggb200.so"""
     out = os.path.join(HERE, "libggexec.so")
-    srcs = [os.path.join(HOST, "gg_executor.c"), os.path.join(HOST, "gg_motion_host.c")]
+    srcs = [os.path.join(HOST, "gg_executor.c"), os.path.join(HOST, "gg_motion_host.c"), os.path.join(HOST, "gg_tupser.c")]
     if force or _newer(out, srcs + _all_headers() + [os.path.join(HERE, "libggb200.so")]):
         subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-Wall", "-Wextra", "-std=gnu11", "-shared", "-o", out + ".tmp"] + srcs +
                               ["-L", HERE, "-lggb200", "-Wl,-rpath,$ORIGIN"])

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../include/gg_executor.h"
+#include "../../include/gg_tupser.h"
 
 int32_t gg_cdbhash_route(const int32_t *typids, const int64_t *vals, const int32_t *lens, const int32_t *isnull,
                          int nkeys, int nsegs);      /* gg_motion_host.c */
@@ -1042,6 +1043,166 @@ static int motion_host_path(GgPlanState *s, int child_failed)
 	}
 	s->rows_ready = 1;
 	return 0;
+}
+
+
+/* ---- rows on the wire: a CPU segment on the other side of a Motion (include/gg_tupser.h) ---- */
+#define GG_FLOAT8ARRAYOID 1022
+
+static void wire_attr(gg_attr *a, int32_t typid)
+{
+	memset(a, 0, sizeof *a);
+	a->atttypid = typid; a->atttypmod = -1;
+	switch (typid)
+	{
+		case GG_BOOLOID: a->attlen = 1; a->attalign = 'c'; a->attbyval = 1; break;
+		case GG_INT4OID: case GG_DATEOID: a->attlen = 4; a->attalign = 'i'; a->attbyval = 1; break;
+		case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID: a->attlen = -1; a->attalign = 'i'; break;
+		case GG_FLOAT8ARRAYOID: a->attlen = -1; a->attalign = 'd'; break;
+		default: a->attlen = 8; a->attalign = 'd'; a->attbyval = 1; break;         /* int8, float8, timestamp */
+	}
+}
+
+/* The tuple descriptor of a node's rows as the reference's nodes see them: one attribute per column, except that the three
+ * columns {N, sumX, sumX2} of a PARTIAL-stage avg(float8) are ONE float8[] attribute — the transition value finalize_aggregate
+ * hands up when there is no final function to run (nodeAgg.c:975-979; SURVEY App. A "two-stage interchange").
+ * map[w] = first result column of wire attribute w; arr[w] = 1 for such an array. */
+static int wire_layout(const GgPlanState *s, gg_attr *attrs, int *map, int *arr)
+{
+	int n = 0, c = 0, i;
+	if (s->agg.aggstage == GG_AGGSTAGE_PARTIAL && (s->agg.numCols + s->agg.numAggs) > 0)
+	{
+		for (c = 0; c < s->agg.numCols; c++, n++) { wire_attr(&attrs[n], s->typid[c]); map[n] = c; arr[n] = 0; }
+		for (i = 0; i < s->agg.numAggs; i++, n++)
+		{
+			const int w = agg_ncols_of(&s->agg, i);
+			wire_attr(&attrs[n], w == 3 ? GG_FLOAT8ARRAYOID : s->typid[c]);
+			map[n] = c; arr[n] = w == 3;
+			c += w;
+		}
+		return c == s->ncols ? n : -1;
+	}
+	for (c = 0; c < s->ncols; c++) { wire_attr(&attrs[c], s->typid[c]); map[c] = c; arr[c] = 0; }
+	return s->ncols;
+}
+
+int64_t GgExecSendTupleChunks(GgPlanState *s, int max_chunk, uint8_t *out, uint64_t cap, int64_t *nrows)
+{
+	gg_attr attrs[GG_MAX_OUTCOLS];
+	int map[GG_MAX_OUTCOLS], arr[GG_MAX_OUTCOLS], natts, w, rc;
+	gg_memtuple_binding *b;
+	uint64_t pos = 0;
+	int64_t r;
+	if (!s || !out) { exec_fail(GG_ERR_ARG, "bad arguments"); return GG_ERR_ARG; }
+	if (!s->done) { g_err[0] = 0; g_errcode = GG_OK; if (run_node(s)) return g_errcode ? g_errcode : GG_ERR_ARG; }
+	if (ensure_rows(s)) return g_errcode ? g_errcode : GG_ERR_ARG;
+	natts = wire_layout(s, attrs, map, arr);
+	if (natts < 0 || natts > GG_MT_MAX_ATTS) { exec_fail(GG_ERR_UNSUPPORTED, "row layout has no wire form"); return GG_ERR_UNSUPPORTED; }
+	b = malloc(sizeof *b);
+	if (!b) { exec_fail(GG_ERR_NOMEM, "out of memory"); return GG_ERR_NOMEM; }
+	rc = gg_memtuple_bind(attrs, natts, b);
+	for (r = 0; rc == GG_OK && r < s->nrows; r++)
+	{
+		int64_t v[GG_MAX_OUTCOLS];
+		uint8_t nl[GG_MAX_OUTCOLS], arrbuf[GG_MAX_OUTCOLS][44];
+		int32_t ln[GG_MAX_OUTCOLS];
+		const void *ptrs[GG_MAX_OUTCOLS];
+		int32_t nch = 0;
+		int64_t got;
+		for (w = 0; w < natts; w++)
+		{
+			const size_t at = (size_t) r * s->ncols + (size_t) map[w];
+			ptrs[w] = NULL; ln[w] = 0;
+			if (arr[w])
+			{
+				gg_float8_array3(bitsf8(s->values[at]), bitsf8(s->values[at + 1]), bitsf8(s->values[at + 2]), arrbuf[w]);
+				v[w] = 0; nl[w] = 0; ptrs[w] = arrbuf[w]; ln[w] = 44;
+			}
+			else { v[w] = s->values[at]; nl[w] = s->isnull[at]; ln[w] = s->lens[at]; }
+		}
+		got = gg_tupser_serialize(b, v, nl, ln, ptrs, max_chunk, out + pos, cap - pos, &nch);
+		if (got < 0) { rc = (int) got; break; }
+		pos += (uint64_t) got;
+	}
+	if (rc == GG_OK)
+	{
+		const int e = gg_tupser_eos(out + pos, cap - pos);          /* SendEndOfStream, cdbmotion.c:532 */
+		if (e < 0) rc = e; else pos += (uint64_t) e;
+	}
+	free(b);
+	if (rc != GG_OK) { exec_fail(rc, "serialising rows: %s", rc == GG_ERR_NOMEM ? "output buffer too small" : "unsupported value"); return rc; }
+	if (nrows) *nrows = s->nrows;
+	return (int64_t) pos;
+}
+
+int GgExecRecvTupleChunks(GgPlanState *s, const uint8_t *chunks, uint64_t nbytes)
+{
+	gg_attr attrs[GG_MAX_OUTCOLS];
+	int map[GG_MAX_OUTCOLS], arr[GG_MAX_OUTCOLS], natts, w, rc = GG_OK, pass;
+	gg_memtuple_binding *b;
+	int64_t nrows = 0;
+	if (!s || s->kind != K_MOTION || !s->child || (!chunks && nbytes)) return (exec_fail(GG_ERR_ARG, "GgExecRecvTupleChunks takes a Motion node"), GG_ERR_ARG);
+	/* the layout of what arrives is the child's: a Motion passes rows through */
+	inherit_layout(s, s->child);
+	if (!s->ncols)
+	{
+		int32_t kt[GG_MAX_KEYS] = { 0 };
+		int c;
+		for (c = 0; c < s->agg.numCols; c++) kt[c] = expr_type(s->estate->pool, s->agg.grpCol[c]);
+		if (set_layout_types(s, &s->agg, kt)) return g_errcode;
+	}
+	natts = wire_layout(s, attrs, map, arr);
+	if (natts < 0 || natts > GG_MT_MAX_ATTS) return (exec_fail(GG_ERR_UNSUPPORTED, "row layout has no wire form"), GG_ERR_UNSUPPORTED);
+	b = malloc(sizeof *b);
+	if (!b) return (exec_fail(GG_ERR_NOMEM, "out of memory"), GG_ERR_NOMEM);
+	rc = gg_memtuple_bind(attrs, natts, b);
+	/* two passes over the chunks: count the tuples, then fill the result */
+	for (pass = 0; rc == GG_OK && pass < 2; pass++)
+	{
+		uint64_t pos = 0;
+		int64_t r = 0;
+		int eos = 0;
+		if (pass == 1 && alloc_result(s, nrows, s->ncols)) { rc = GG_ERR_NOMEM; break; }
+		while (pos < nbytes && !eos)
+		{
+			int64_t v[GG_MAX_OUTCOLS];
+			uint8_t nl[GG_MAX_OUTCOLS], strbuf[4096];
+			int32_t ln[GG_MAX_OUTCOLS];
+			uint64_t used = 0;
+			const int d = gg_tupser_deserialize(b, chunks + pos, nbytes - pos, &used, v, nl, ln, strbuf, sizeof strbuf);
+			if (d == 1) { eos = 1; break; }
+			if (d != GG_OK) { rc = d; break; }
+			pos += used;
+			if (pass == 1)
+				for (w = 0; w < natts; w++)
+				{
+					const size_t at = (size_t) r * s->ncols + (size_t) map[w];
+					if (arr[w])
+					{
+						double st[3] = { 0, 0, 0 };
+						if (nl[w] || gg_float8_array3_read(strbuf + v[w], ln[w], st)) { rc = GG_ERR_ARG; break; }
+						s->values[at] = f8bits(st[0]); s->values[at + 1] = f8bits(st[1]); s->values[at + 2] = f8bits(st[2]);
+					}
+					else if (attrs[w].attlen == -1)
+					{
+						uint64_t packed = 0;
+						int k;
+						if (!nl[w] && ln[w] > 8) { rc = GG_ERR_UNSUPPORTED; break; }      /* strings travel packed in 8 bytes on this path */
+						for (k = 0; !nl[w] && k < ln[w]; k++) packed |= (uint64_t) strbuf[v[w] + k] << (8 * k);
+						s->values[at] = (int64_t) packed; s->isnull[at] = nl[w]; s->lens[at] = nl[w] ? 0 : ln[w];
+					}
+					else { s->values[at] = v[w]; s->isnull[at] = nl[w]; }
+				}
+			r++;
+		}
+		if (rc == GG_OK && !eos) rc = GG_ERR_BADPAGE;              /* a stream ends with its end-of-stream chunk */
+		nrows = r;
+	}
+	free(b);
+	if (rc != GG_OK) return (exec_fail(rc, "reading tuple chunks failed (%d)", rc), rc);
+	drop_device_results(s);
+	s->rows_ready = 1; s->done = 1; s->next = 0;
+	return GG_OK;
 }
 
 GgTupleTableSlot *GgExecProcNode(GgPlanState *s)

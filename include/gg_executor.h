@@ -217,6 +217,17 @@ GgTupleTableSlot *GgExecHash(GgPlanState *node);
 void GgExecEndHash(GgPlanState *node);
 int  GgExecReScanHash(GgPlanState *node);
 
+/* A CPU segment on the other side of a Motion (a CPU FINAL-stage Agg above this engine's PARTIAL stage, a mixed cluster).
+ * GgExecSendTupleChunks: the rows `node` produces, as the reference's senders put them on the interconnect — SendTuple ->
+ * SerializeTuple (cdbmotion.c:434, tupser.c:400): one MemTuple per row in tuple chunks of at most max_chunk bytes, then an
+ * end-of-stream chunk (cdbmotion.c:532).  A PARTIAL-stage avg(float8) state travels as the float8[3] array the reference
+ * ships (nodeAgg.c:975-979).  Returns the bytes written (< 0: GG_ERR_*).  The caller hands them to SendChunk.
+ * GgExecRecvTupleChunks: the reverse for a Motion node's receiving half — what CPU senders produced (RecvTupleFrom ->
+ * CvtChunksToTup, cdbmotion.c:559, tupser.c:609; MemTuple or heap-tuple form), up to and including the end-of-stream chunk,
+ * becomes the node's result as if its exchange had delivered it. */
+int64_t GgExecSendTupleChunks(GgPlanState *node, int max_chunk, uint8_t *out, uint64_t cap, int64_t *nrows);
+int GgExecRecvTupleChunks(GgPlanState *node, const uint8_t *chunks, uint64_t nbytes);
+
 /* The interconnect as the reference selects it: a table of entry points per GpVars_Interconnect_Type
  * (cdbinterconnect.h:500-533, ic_common.c:522-575; UDPIFC / TCP / proxy there).  This is the NCCL entry: a 4th value of
  * that enum would install it. */

@@ -21,6 +21,7 @@ def build_mock(outdir):
     host = os.path.join(ROOT, "greengage_b200", "host")
     objs = []
     for src, cc, std in ((os.path.join(host, "gg_executor.c"), "gcc", "-std=gnu11"), (os.path.join(host, "gg_motion_host.c"), "gcc", "-std=gnu11"),
+                         (os.path.join(host, "gg_tupser.c"), "gcc", "-std=gnu11"),
                          (os.path.join(HERE, "mock", "ggb200_mock.c"), "gcc", "-std=gnu11"),
                          (os.path.join(HERE, "mock", "compile_glue.cpp"), "g++", "-std=c++17"),
                          (os.path.join(ROOT, "greengage_b200", "csrc", "gg_compile.cpp"), "g++", "-std=c++17")):   # the product's plan compiler
