@@ -40,7 +40,8 @@ def _all_headers():
 def embed_sources():
     """The kernel headers as string literals, for run-time plan specialisation (gg_jit.cpp)."""
     files = [("gg_plan_h", os.path.join(ROOT, "include", "gg_plan.h")), ("gg_program_h", os.path.join(CSRC, "gg_program.h")),
-             ("gg_device_cuh", os.path.join(CSRC, "gg_device.cuh")), ("gg_scanagg_kernel_cuh", os.path.join(CSRC, "gg_scanagg_kernel.cuh"))]
+             ("gg_device_cuh", os.path.join(CSRC, "gg_device.cuh")), ("gg_scanagg_kernel_cuh", os.path.join(CSRC, "gg_scanagg_kernel.cuh")),
+             ("gg_aocs_h", os.path.join(ROOT, "include", "gg_aocs.h")), ("gg_aocs_decode_h", os.path.join(CSRC, "gg_aocs_decode.h"))]
     out = os.path.join(BUILD, "gg_jit_sources.inc")
     if not _newer(out, [f for _, f in files]):
         return out

@@ -194,6 +194,7 @@ def dev_lib():
         L.gg_scanagg_create.argtypes = [vp, C.POINTER(gg_scan), C.POINTER(gg_agg), C.POINTER(gg_exprpool), C.POINTER(vp)]
         L.gg_scanagg_run.argtypes = [vp, vp, u64, u64]
         L.gg_scanagg_run_host.argtypes = [vp, vp, u64]
+        L.gg_scanagg_run_aocs.argtypes = [vp, vp, i32, u64, C.c_int32]
         L.gg_scanagg_fetch.argtypes = [vp, C.POINTER(gg_aggrow), i32, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)]
         L.gg_scanagg_reset.argtypes = [vp]
         L.gg_scanagg_free.argtypes = [vp]

@@ -300,7 +300,7 @@ static int joinagg_fill_inner(gg_joinagg *j)
 		GG_CUDA(cudaSetDevice(j->eng->device));
 		int rc = scanagg_launch(p, (const uint8_t *) j->ent, chunks, j->eng->stream, j->slots, true);
 		if (rc) return rc;
-		p->fed.push_back({ (const uint8_t *) j->ent, nullptr, chunks, j->slots, true });
+		p->fed.push_back({ (const uint8_t *) j->ent, nullptr, chunks, j->slots, true, 0 });
 		j->filled = true;
 	}
 	return GG_OK;

@@ -72,7 +72,8 @@ struct gg_scanagg {
 	HostMirror *h_mirror = nullptr;         /* pinned */
 	int nrecs_total = 0, nrecs_cap = 0;
 	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
-	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; };
+	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; int32_t tile_rows; };   /* tile_rows > 0: dev = the column descriptors of an AOCS feed */
+	gg_aocs_devcol *d_aocs = nullptr;       /* device copy of the column descriptors of gg_scanagg_run_aocs */
 	std::vector<Fed> fed;
 	bool has_state = false;
 	/* set by a batched join: how to feed the inputs again (its batches, each with its own hash table) when fetch has to
@@ -86,7 +87,7 @@ struct gg_scanagg {
 /* gg_scanagg.cu */
 int scanagg_finish_create(gg_scanagg *p, gg_scanagg **out);      /* after p->prog / p->aggmap are compiled */
 /* one launch of the pipeline's kernel over device pages (fill_inner: the HJ_FILL_INNER_TUPLES pass of a right/full join) */
-int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0, bool fill_inner = false);
+int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows = 0, bool fill_inner = false, int32_t aocs_tile_rows = 0);
 /* gg_motion.cu: the partitioning kernel behind gg_motion_partition, with the routing rule as a parameter (route 0: segments by
  * cdbhash + jump consistent hash; route 1: hash-join batches by the batch bits above `shift`) */
 int gg_partition_rows(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool,

@@ -298,6 +298,9 @@ static int scanagg_configure(gg_scanagg *p)
 	const int nslots = p->prog.nslots - p->regslots;
 	int scr = (p->prog.outer.ncols * 64 + 15) & ~15;             /* column offsets [ncols][32] u16 */
 	if (p->mode == MODE_TR || p->mode == MODE_TRN) scr += V * 33 * 8 + 128 + 128;      /* + transposed values, group ids, null masks */
+	scr = (scr + 15) & ~15;
+	/* datum-row plans can be fed from column files (gg_scanagg_run_aocs): 32 staged rows per warp at the tail of its scratch */
+	if (p->prog.outer.rowwords) scr += 32 * ((p->prog.outer.rowwords | 1) * 8);
 	p->scratch_per_warp = (scr + 15) & ~15;
 	p->nstage = 3;
 	if (p->mode == MODE_PRIV)
@@ -450,7 +453,7 @@ static int hashagg_alloc(gg_scanagg *p, uint64_t cap)
 	return GG_OK;
 }
 
-int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows, bool fill_inner)
+int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cudaStream_t st, uint64_t nrows, bool fill_inner, int32_t aocs_tile_rows)
 {
 	gg_engine *e = p->eng;
 	ScanAggParams prm;
@@ -470,6 +473,8 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	prm.nrows = nrows;
 	prm.fill_inner = fill_inner ? 1 : 0;
 	prm.team = p->team;
+	prm.aocs = aocs_tile_rows > 0 ? (const gg_aocs_devcol *) dev_pages : nullptr;
+	prm.aocs_tile_rows = aocs_tile_rows;
 	prm.ha = p->ha;
 	if (p->kev_used == p->kev.size())
 	{
@@ -656,7 +661,34 @@ int gg_scanagg_run(gg_scanagg *p, gg_relation *r, uint64_t first_block, uint64_t
 	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
 	rc = scanagg_launch(p, r->pages + first_block * GG_BLCKSZ, nblocks, e->stream, r->nrows);
 	if (rc) return rc;
-	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows, false });
+	p->fed.push_back({ r->pages + first_block * GG_BLCKSZ, nullptr, nblocks, r->nrows, false, 0 });
+	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
+	e->timed = true;
+	return GG_OK;
+}
+
+/* SeqScan over an append-only column-oriented relation, fused with the Agg above it (aocsam.c:661 aocs_getnext + the same
+ * qual / aggregate path as heap pages): the projected column files are resident in device memory with their block directories
+ * and tile plans (include/gg_aocs.h); the plan's scan descriptor is the GG_FMT_DATUMROWS descriptor of those columns. */
+int gg_scanagg_run_aocs(gg_scanagg *p, const struct gg_aocs_devcol *cols, int ncols, uint64_t nrows, int32_t tile_rows)
+{
+	if (!p || !cols || ncols < 1 || ncols > GG_MAX_ATTS || tile_rows < 32 || (tile_rows & 31)) return GG_ERR_ARG;
+	if (!p->prog.outer.rowwords || p->prog.outer.rowwords != 1 + ncols)
+	{ gg_set_error("the plan's scan descriptor must be the datum-row descriptor of the %d projected columns", ncols); return GG_ERR_ARG; }
+	if (p->is_join || p->mode == MODE_BUILD || p->mode == MODE_PART) { gg_set_error("column files feed SeqScan -> Agg pipelines"); return GG_ERR_UNSUPPORTED; }
+	gg_engine *e = p->eng;
+	GG_CUDA(cudaSetDevice(e->device));
+	for (int c = 0; c < ncols; c++)
+		if (!cols[c].file || !cols[c].dir || !cols[c].tiles || cols[c].nblocks < 1 || cols[c].kind < GG_AOCS_K_W8 || cols[c].kind > GG_AOCS_K_TEXT)
+		{ gg_set_error("AOCS column %d: incomplete descriptor", c); return GG_ERR_ARG; }
+	if (!p->d_aocs) GG_CUDA(cudaMalloc((void **) &p->d_aocs, sizeof(gg_aocs_devcol) * GG_MAX_ATTS));
+	GG_CUDA(cudaMemcpyAsync(p->d_aocs, cols, sizeof(gg_aocs_devcol) * (size_t) ncols, cudaMemcpyHostToDevice, e->stream));
+	if (nrows == 0) return GG_OK;
+	const uint64_t ntiles = (nrows + (uint64_t) tile_rows - 1) / (uint64_t) tile_rows;
+	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
+	int rc = scanagg_launch(p, (const uint8_t *) p->d_aocs, ntiles, e->stream, nrows, false, tile_rows);
+	if (rc) return rc;
+	p->fed.push_back({ (const uint8_t *) p->d_aocs, nullptr, ntiles, nrows, false, tile_rows });
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
@@ -674,7 +706,7 @@ int gg_scanagg_run_host(gg_scanagg *p, const void *host_pages, uint64_t nblocks)
 	int rc = nblocks ? scanagg_adapt_to_pages(p, nullptr, host_pages) : GG_OK;
 	if (rc) return rc;
 	rc = scanagg_stream_host(p, host_pages, nblocks);
-	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0, false });
+	if (rc == GG_OK) p->fed.push_back({ nullptr, host_pages, nblocks, 0, false, 0 });
 	return rc;
 }
 
@@ -821,7 +853,7 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 			{
 				for (const auto &f : replay)
 				{
-					rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
+					rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill, f.tile_rows) : scanagg_stream_host(p, f.host, f.nblocks);
 					if (rc2) return rc2;
 				}
 				p->fed = replay;
@@ -881,7 +913,7 @@ int gg_scanagg_fetch(gg_scanagg *p, gg_aggrow *out, int outcap, int *nout,
 		{
 			for (const auto &f : replay)
 			{
-				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill) : scanagg_stream_host(p, f.host, f.nblocks);
+				rc2 = f.dev ? scanagg_launch(p, f.dev, f.nblocks, e->stream, f.nrows, f.fill, f.tile_rows) : scanagg_stream_host(p, f.host, f.nblocks);
 				if (rc2) return rc2;
 			}
 			p->fed = replay;
@@ -934,7 +966,7 @@ void gg_scanagg_free(gg_scanagg *p)
 	cudaSetDevice(p->eng->device);
 	cudaStreamSynchronize(p->eng->stream);
 	cudaFree(p->recs); cudaFree(p->merged); cudaFree(p->vidx); cudaFree(p->vmap);
-	cudaFree(p->d_status); cudaFreeHost(p->h_mirror); cudaFree(p->d_nout64); cudaFree(p->ha_mem);
+	cudaFree(p->d_status); cudaFreeHost(p->h_mirror); cudaFree(p->d_nout64); cudaFree(p->ha_mem); cudaFree(p->d_aocs);
 	for (int b = 0; b < 2; b++)
 	{
 		if (p->stage[b]) cudaFree(p->stage[b]);

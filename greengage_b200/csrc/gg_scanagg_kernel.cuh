@@ -37,6 +37,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gg_device.cuh"
+#include "gg_aocs_decode.h"
 
 namespace ggd {
 
@@ -161,6 +162,12 @@ struct ScanAggParams {
 	uint64_t nrows;                       /* datum-row input: total rows (pages/nblocks then describe 32 KB chunks of rows) */
 	int fill_inner;                       /* join probe kernels: this launch is HJ_FILL_INNER_TUPLES — the "pages" are the hash
 	                                       * table itself, every unmatched entry is emitted with a null-extended outer side */
+	/* Append-only column-oriented input (aocsam.c:661 aocs_getnext): aocs_tile_rows > 0 — there are no pages; unit `it` of a
+	 * block is a TILE of aocs_tile_rows rows (a multiple of 32), a lane loads the referenced columns of its row straight from
+	 * the column files in device memory (aocs[a] = column a of the plan's descriptor; gg_aocs_fetch) into a staged datum row
+	 * in shared memory and the row program runs over that: no attribute walk, no line pointers, only projected bytes read. */
+	const gg_aocs_devcol *aocs;
+	int32_t aocs_tile_rows;
 	int team;                             /* > 0: consumer warps work in teams of this many warps, one page per team at a time (a
 	                                       * warp only visits its team's pages); 0: every warp visits every page and the chunks
 	                                       * are dealt round-robin across pages */
@@ -762,7 +769,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	if (warp == ncons)
 	{
 		/* ===== producer: one elected lane streams pages through the ring ===== */
-		if (lane == 0)
+		if (lane == 0 && prm.aocs_tile_rows == 0)
 		{
 			int s = 0;
 			uint32_t ph = 0;
@@ -840,15 +847,25 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		while (s >= nstage) { s -= nstage; ph ^= 1; }
 		for (uint32_t it = (uint32_t) team; it < npages && team < nteams; it += (uint32_t) nteams)
 		{
-			if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
-			__syncwarp();
+			const bool aocs = prm.aocs_tile_rows > 0;
+			if (!aocs)
+			{
+				if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
+				__syncwarp();
+			}
 			const uint32_t pg = ring + (uint32_t) s * GG_BLCKSZ;
 
 			/* page header, bufpage.h:153-166; sanity rules of PageAddItem (bufpage.c:196-204) */
-			const uint32_t w2 = lds32(pg + 8), w3 = lds32(pg + 12), w4 = lds32(pg + 16);
+			const uint32_t w2 = aocs ? 0 : lds32(pg + 8), w3 = aocs ? 0 : lds32(pg + 12), w4 = aocs ? 0 : lds32(pg + 16);
 			const uint32_t pd_flags = w2 >> 16, pd_lower = w3 & 0xFFFF, pd_upper = w3 >> 16, pd_special = w4 & 0xFFFF;
 			int nitems = 0;
-			if (rowwords)
+			if (aocs)
+			{
+				const uint64_t tile = first + (uint64_t) it * stride;
+				const uint64_t left = prm.nrows - tile * (uint64_t) prm.aocs_tile_rows;
+				nitems = (int) (left < (uint64_t) prm.aocs_tile_rows ? left : (uint64_t) prm.aocs_tile_rows);
+			}
+			else if (rowwords)
 			{
 				const uint64_t chunk = first + (uint64_t) it * stride;
 				const uint64_t left = prm.nrows - chunk * rows_per_chunk;
@@ -893,7 +910,32 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				{
 					/* datum row: NULL mask word, then one word per column at constant offsets */
 					live = idx < nitems;
-					const uint32_t rp = pg + (live ? (uint32_t) idx * rowbytes : 0);
+					uint32_t rp = pg + (live ? (uint32_t) idx * rowbytes : 0);
+					if (aocs)
+					{
+						/* the row is assembled here, from the column files: an odd word stride keeps the lanes on distinct banks */
+						rp = myscr + (uint32_t) prm.scratch_per_warp - (32u - (uint32_t) lane) * ((rowwords | 1u) * 8);      /* the tail of the warp's scratch */
+						uint64_t m = 0;
+						if (live)
+						{
+							const int64_t tile = (int64_t) (first + (uint64_t) it * stride);
+							uint32_t aerr = 0;
+							for (int sl = 0; sl < ncols; sl++)
+							{
+								const int a = P.outer.colatt[sl];
+								uint64_t w = 0;
+								int isn = 0;
+								const uint32_t rc = gg_aocs_fetch(prm.aocs + a, tile, idx, &w, &isn);
+								aerr |= rc;
+								if (rc || isn) { w = 0; m |= 1ull << a; }
+								sts64(rp + 8 + (uint32_t) a * 8, w);
+							}
+							if (aerr & GG_AOCS_E_RANGE) err |= GGP_EF_BADPAGE;
+							if (aerr & GG_AOCS_E_IRREGULAR) err |= GGP_EF_STRING_TOO_LONG;
+							if (aerr) live = false;
+						}
+						sts64(rp, m);
+					}
 					X.fast = true;
 					X.tv.tp = rp + 8;
 					X.tv.colnull = 0;
@@ -1078,7 +1120,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				}
 			}
 			__syncwarp();
-			if (lane == 0) mbar_arrive(empty_bar + s * 8);
+			if (lane == 0 && !aocs) mbar_arrive(empty_bar + s * 8);
 			s += nteams;
 			while (s >= nstage) { s -= nstage; ph ^= 1; }
 		}

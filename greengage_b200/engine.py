@@ -142,6 +142,11 @@ class ScanAgg:
     def run_host(self, host_ptr, nblocks):
         check(dev_lib().gg_scanagg_run_host(self.h, C.c_void_p(host_ptr), nblocks))
 
+    def run_aocs(self, devcols):
+        """fused scan over column files resident on the device (aocs.DeviceColumns); the plan's scan descriptor is
+        devcols.rows_tupdesc()"""
+        check(dev_lib().gg_scanagg_run_aocs(self.h, devcols.devcols, len(devcols.cols), devcols.nrows, devcols.tile_rows))
+
     def reset(self):
         check(dev_lib().gg_scanagg_reset(self.h))
 

@@ -49,6 +49,7 @@ typedef struct gg_aocs_block {
 /* CRC-32C the way the append-only storage layer computes it (port/pg_crc32c_sb8.c; initial value 0xFFFFFFFF and, "by
  * historical accident", no final inversion — cdbappendonlystorageformat.c:38-47).  Uses the SSE4.2 instruction when the
  * CPU has it. */
+#ifndef __CUDACC_RTC__      /* the run-time kernel compiler only needs the types of this header */
 uint32_t gg_aocs_crc32c(const uint8_t *p, int64_t n);
 
 /* Walk a column file: validate every storage-block header (and both checksums when the relation has checksum=true),
@@ -58,6 +59,7 @@ uint32_t gg_aocs_crc32c(const uint8_t *p, int64_t n);
  * format above; GG_ERR_NOMEM: more than cap blocks. */
 int gg_aocs_index_column(const gg_attr *att, const uint8_t *file, int64_t nbytes, int checksum,
                          gg_aocs_block *dir, int64_t cap, int64_t *nblocks, int64_t *nrows);
+#endif
 
 /* The scan's unit of work is a TILE of tile_rows consecutive rows (the same rows of every projected column; the columns'
  * storage blocks end at different rows because their widths differ).  For one column, per tile: the storage block that
@@ -76,8 +78,10 @@ typedef struct gg_aocs_tile {
 } gg_aocs_tile;             /* 16 bytes */
 
 /* ntiles must be ceil(nrows / tile_rows) for the directory's row total; file is needed to count NULL bits. */
+#ifndef __CUDACC_RTC__
 int gg_aocs_plan_tiles(const gg_aocs_block *dir, int64_t nblocks, const uint8_t *file, int32_t tile_rows,
                        gg_aocs_tile *tiles, int64_t ntiles);
+#endif
 
 /* ---- what the device side takes (libggb200.so: gg_aocs_decode_rows in ggb200.h; kernel in csrc/gg_aocs.cu) ---- */
 
@@ -107,6 +111,7 @@ typedef struct gg_aocs_devcol {
 /* Streaming writer of one column file (what an INSERT / COPY into the relation appends: aocs_insert_values,
  * aocsam.c:964-1016 -> datumstreamwrite_put / datumstreamwrite_block_orig -> AppendOnlyStorageWrite_FinishBuffer).
  * Used by the synthetic loader and the tests; byte-identical to what the reference writes for the same values. */
+#ifndef __CUDACC_RTC__
 typedef struct gg_aocs_writer gg_aocs_writer;
 int gg_aocs_writer_create(const gg_attr *att, int blocksize, int checksum, int64_t first_rownum,
                           uint8_t *out, int64_t outcap, gg_aocs_writer **w);
@@ -116,6 +121,7 @@ int gg_aocs_writer_put(gg_aocs_writer *w, int64_t value, int32_t len, int isnull
 int gg_aocs_writer_finish(gg_aocs_writer *w, int64_t *nbytes);
 /* a safe output-buffer size for nrows values of at most maxlen payload bytes each */
 int64_t gg_aocs_file_bound(const gg_attr *att, int64_t nrows, int32_t maxlen, int blocksize, int checksum);
+#endif
 
 #ifdef __cplusplus
 }

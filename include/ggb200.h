@@ -157,6 +157,13 @@ void gg_joinagg_free(gg_joinagg *p);
  * row.  GG_ERR_UNSUPPORTED: a projected column whose values have no common stride (strings longer than 8 bytes or of
  * mixed length); GG_ERR_BADPAGE: plan and directory disagree. */
 struct gg_aocs_devcol;
+/* The fused scan: SeqScan over the column files -> qual -> Agg in ONE kernel (aocs_getnext, aocsam.c:661, feeding the same
+ * row program as heap pages): a lane loads the referenced columns of its row straight from the files, nothing is written
+ * back to device memory, only the projected columns' bytes are read.  The pipeline must have been created over the
+ * GG_FMT_DATUMROWS descriptor of the ncols projected columns (column i of the descriptor = cols[i]); tile_rows = the tile
+ * size the tile plans were made for (a multiple of 32).  Accumulates like gg_scanagg_run; fetch as usual. */
+int  gg_scanagg_run_aocs(gg_scanagg *p, const struct gg_aocs_devcol *cols, int ncols, uint64_t nrows, int32_t tile_rows);
+/* the two-pass form: decode to rows any operator scans (joins, Motions) */
 int  gg_aocs_decode_rows(gg_engine *e, const struct gg_aocs_devcol *cols, int ncols, uint64_t nrows, int32_t tile_rows,
                          void *device_rows);
 

@@ -3,6 +3,7 @@ TPC-H Q4 (semi join), Q12 (inner join) and Q6 (range predicates + plain aggregat
 left / right / full join tables of expected/join.out; the ORDER BY answers of expected/sort.out; the integer and hashed
 aggregates of expected/aggregates.out.  Same plans and fixtures as the tests/test_oracle_*golden* tests, which hold the oracle
 to those answers on every CPU run.  (Q1's golden is tests/test_gpu_scanagg.py / test_gpu_executor.py.)"""
+import numpy as np
 import pytest
 
 from _util import golden, tpch_join_fixture, tpch_q4_plan, tpch_q12_plan
@@ -180,6 +181,93 @@ def test_aocs_q1_equals_the_heap_answer_and_the_references_golden(eng):
     got, sc, ps = run(desc, files, golden("q1_expected.json")["interval_days"])
     assert sc == n
     _check_against_golden(got)
+
+
+@pytest.mark.parametrize("variant", ["specialised", "interpreter"])
+def test_fused_aocs_scan_equals_the_heap_answer_and_the_references_golden(eng, monkeypatch, variant):
+    """SeqScan over column files fused with the Agg (gg_scanagg_run_aocs; aocs_getnext, aocsam.c:661): no rows are written
+    back, a lane loads its row's referenced columns from the files.  Same answers as the heap pages of the same rows
+    (oracle), as the two-pass decode, and as the reference's golden Q1 over co_lineitem (rpt_tpch.source:5768-5795)."""
+    from _util import assert_aggrows_match, golden, lineitem_fixture_pages
+    from greengage_b200 import aocs, tpch
+    from greengage_b200.engine import ScanAgg
+    from oracle import pyoracle as po
+    from test_oracle_aocs import lineitem_as_column_files
+    from test_oracle_q1_golden import _check_against_golden
+    if variant == "interpreter":
+        monkeypatch.setenv("GGB200_JIT", "0")
+    names = dict(quantity=1, extendedprice=2, discount=3, tax=4, returnflag=5, linestatus=6, shipdate=7)
+    cols = [4, 5, 6, 7, 8, 9, 10]
+
+    def run(desc, files, interval_days, stage=capi.AGGSTAGE_NORMAL, twice=False):
+        dc = aocs.DeviceColumns(eng, desc, cols, files)
+        try:
+            scan, agg, pool = tpch.q1_plan(stage=stage, interval_days=interval_days, desc=dc.rows_tupdesc([1] * len(cols)), cols=names)
+            sa = ScanAgg(eng, scan, agg, pool)
+            try:
+                sa.run_aocs(dc)
+                if twice:
+                    sa.run_aocs(dc)                     # feeds accumulate like gg_scanagg_run
+                return sa.fetch(), sa.variant()
+            finally:
+                sa.free()
+        finally:
+            dc.free()
+
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 400_000)
+    pages, nb, nr = tpch.synth_generate(spec)
+    files, _ = aocs.synth_columns(spec, cols, nr)
+    (got, sc, ps), var = run(capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE), files, 90)
+    assert (var >= 16) == (variant == "specialised")
+    scan_h, agg_h, pool_h = tpch.q1_plan(capi.TAB_LINEITEM_WIDE)
+    want, wsc, wps = po.seqscan_agg(scan_h, agg_h, pool_h, pages)
+    assert (sc, ps) == (wsc, wps)
+    assert_aggrows_match(got, want, agg_h)
+    (got2, sc2, ps2), _ = run(capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE), files, 90, twice=True)
+    assert (sc2, ps2) == (2 * wsc, 2 * wps) and sorted(r.agg[7].i for r in got2) == sorted(2 * r.agg[7].i for r in want)
+    desc, colvals, n = lineitem_as_column_files()
+    files = {c: aocs.write_column(desc.attrs[c], colvals[c]) for c in cols}
+    (got, sc, ps), _ = run(desc, files, golden("q1_expected.json")["interval_days"])
+    assert sc == n
+    _check_against_golden(got)
+
+
+def test_fused_aocs_scan_with_nulls_and_a_ragged_tail(eng):
+    """NULL-bearing blocks (bitmap + prefix popcount), a row count that is no multiple of the tile, min / max / count(col):
+    the nullable kernel variant over column files equals the oracle's AOCS scan."""
+    from _util import assert_aggrows_match, make_desc
+    from greengage_b200 import aocs
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import ScanAgg
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(17)
+    n = 70_001
+    desc = make_desc([(capi.INT4OID, 4, "i", 0), (capi.FLOAT8OID, 8, "d", 0), (capi.BPCHAROID, -1, "i", 0), (capi.INT8OID, 8, "d", 1)])
+    k = rng.integers(0, 7, n)
+    x = rng.integers(-1000, 1000, n).astype(np.float64) / 4
+    f = [bytes([65 + int(c)]) for c in rng.integers(0, 3, n)]
+    y = rng.integers(-10**12, 10**12, n)
+    nulls = [rng.random(n) < 0.2, rng.random(n) < 0.3, rng.random(n) < 0.1, np.zeros(n, bool)]
+    vals = [[int(v) for v in k], [float(v) for v in x], f, [int(v) for v in y]]
+    files = {c: aocs.write_column(desc.attrs[c], vals[c], nulls[c] if c < 3 else None) for c in range(4)}
+    dc = aocs.DeviceColumns(eng, desc, [0, 1, 2, 3], files)
+    try:
+        p = ExprPool()
+        kk, xx, ff, yy = p.var(1, capi.INT4OID), p.var(2, capi.FLOAT8OID), p.var(3, capi.BPCHAROID), p.var(4, capi.INT8OID)
+        qual = p.func(capi.F_INT4GT, capi.BOOLOID, kk, p.const(capi.INT4OID, 0))
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [ff], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, xx), (capi.AGG_COUNT_ANY, xx),
+                                                          (capi.AGG_MAX_INT8, yy), (capi.AGG_MIN_INT4, kk)])
+        scan = capi.make_scan(dc.rows_tupdesc([0, 0, 0, 1]), qual)
+        sa = ScanAgg(eng, scan, agg, p.pool)
+        sa.run_aocs(dc)
+        got, sc, ps = sa.fetch()
+        sa.free()
+        oscan = capi.make_scan(desc, qual)
+        want, wsc, wps = po.aocs_seqscan_agg(oscan, agg, p.pool, [files[c] for c in range(4)], n)
+        assert (sc, ps) == (wsc, wps) and sc == n
+        assert_aggrows_match(got, want, agg)
+    finally:
+        dc.free()
 
 
 def test_flattened_qual_gives_the_references_q6_revenue(eng):
