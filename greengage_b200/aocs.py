@@ -176,21 +176,31 @@ class DeviceColumns:
     files: {attribute number: uint8 array}.  The loader work (checksums, directory, tile plan) runs on the host
     (libgghost.so); the decoding on the device (gg_aocs_decode_rows).  Fails loudly without a GPU like everything else."""
 
-    def __init__(self, eng, desc, cols, files, checksum=True, tile_rows=1024):
+    def __init__(self, eng, desc, cols, files, checksum=True, tile_rows=1024, pinned=False):
+        """pinned: stage the arena in pinned host memory and keep it, so that upload() can repeat the host -> device copy
+        (the end-to-end measurement of bench.py)"""
+        from concurrent.futures import ThreadPoolExecutor
         from .engine import Relation
         self.eng, self.cols, self.tile_rows = eng, list(cols), tile_rows
         self.typids = [desc.attrs[c].atttypid for c in self.cols]
         parts, layout, off, self.nrows = [], [], 0, None
         for c in self.cols:
-            att = desc.attrs[c]
-            if att.atttypid not in KIND_OF_TYPE:
-                raise capi.GGError(-6, "AOCS column %d: type %d is not decodable on the device" % (c, att.atttypid))
+            if desc.attrs[c].atttypid not in KIND_OF_TYPE:
+                raise capi.GGError(-6, "AOCS column %d: type %d is not decodable on the device" % (c, desc.attrs[c].atttypid))
+
+        def load_one(c):
+            # the loader's work for one column file: checksums, block directory, tile plan (libgghost.so releases the GIL)
             f = np.ascontiguousarray(files[c], dtype=np.uint8)
-            d, nrows = index_column(att, f, checksum)
+            d, nrows = index_column(desc.attrs[c], f, checksum)
+            return f, d, nrows, plan_tiles(d, f, tile_rows)
+
+        with ThreadPoolExecutor(max_workers=max(1, min(len(self.cols), os.cpu_count() or 1))) as tp:
+            loaded = list(tp.map(load_one, self.cols))
+        for c, (f, d, nrows, t) in zip(self.cols, loaded):
+            att = desc.attrs[c]
             if self.nrows is not None and nrows != self.nrows:
                 raise capi.GGError(-9, "AOCS column files of one segment file disagree on the row count")
             self.nrows = nrows
-            t = plan_tiles(d, f, tile_rows)
             entry = {"kind": KIND_OF_TYPE[att.atttypid], "nblocks": len(d)}
             for name, arr in (("file", f), ("dir", d.view(np.uint8).reshape(-1)), ("tiles", t.view(np.uint8).reshape(-1))):
                 entry[name] = off
@@ -199,9 +209,16 @@ class DeviceColumns:
             layout.append(entry)
         self.bytes_in = sum(np.ascontiguousarray(files[c]).size for c in self.cols)
         nb = (off + capi.GG_BLCKSZ - 1) // capi.GG_BLCKSZ
-        arena = np.zeros(nb * capi.GG_BLCKSZ, dtype=np.uint8)
+        self.arena_bytes = nb * capi.GG_BLCKSZ
+        self._pinned_addr = None
+        if pinned:
+            from .engine import host_alloc
+            self._pinned_addr, arena = host_alloc(self.arena_bytes)
+        else:
+            arena = np.empty(self.arena_bytes, dtype=np.uint8)
         for o, arr in parts:
             arena[o:o + arr.size] = arr
+        self.arena_host = arena if pinned else None
         self.arena = Relation(eng, host_pages=arena)
         base = self.arena.device_ptr()
         self.devcols = (gg_aocs_devcol * len(self.cols))()
@@ -212,6 +229,12 @@ class DeviceColumns:
 
     def rows_tupdesc(self, notnull=None):
         return capi.rows_tupdesc(self.typids, notnull)
+
+    def upload(self):
+        """host -> device copy of the arena again (column files + directories + tile plans), asynchronous on the engine's
+        stream: the next kernel is ordered behind it.  Needs pinned=True."""
+        assert self.arena_host is not None
+        self.arena.load(0, self.arena_host)
 
     def decode(self):
         """-> engine.RowRelation over the decoded rows (kept until free())"""
@@ -235,3 +258,8 @@ class DeviceColumns:
             if r is not None:
                 r.free()
         self.rows = self.arena = None
+        if self._pinned_addr is not None:
+            from .engine import host_free
+            self.arena_host = None
+            host_free(self._pinned_addr)
+            self._pinned_addr = None
