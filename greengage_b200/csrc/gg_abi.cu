@@ -271,6 +271,20 @@ extern "C" int gg_debug_disasm_scanagg(const gg_scan *scan, const gg_agg *agg, c
 	return ggp_disasm(&prog, buf, cap);
 }
 
+/* the compiled device program of a SeqScan->Agg plan, byte for byte (scripts/gen_plan_cache.py stores it next to each
+ * build-time specialised kernel so that a lookup compares programs, not just their hashes) */
+extern "C" int gg_debug_program_bytes(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool, unsigned char *buf, int cap)
+{
+	ggp_program prog;
+	ggp_aggmap aggmap[GG_MAX_AGGS];
+	char msg[256];
+	int rc = ggp_compile_scanagg(scan, agg, pool, &prog, aggmap, msg, sizeof msg);
+	if (rc != GG_OK) { gg_set_error("%s", msg); return rc; }
+	if (cap < (int) sizeof prog) return GG_ERR_NOMEM;
+	memcpy(buf, &prog, sizeof prog);
+	return (int) sizeof prog;
+}
+
 /* debugging aid: the build and probe programs of a HashJoin -> Agg plan */
 extern "C" int gg_debug_disasm_join(const gg_scan *outer, const gg_scan *inner, const gg_hashjoin *hj, const gg_agg *agg,
                                     const gg_exprpool *pool, char *buf, int cap)

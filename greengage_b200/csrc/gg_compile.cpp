@@ -571,7 +571,7 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 
 	/* ---- aggregate arguments -> deduplicated accumulator columns ---- */
 	int accroot[GGP_MAX_ACCS];
-	bool needsq[GGP_MAX_ACCS];
+	bool needsq[GGP_MAX_ACCS], checksq[GGP_MAX_ACCS];
 	for (int i = 0; i < agg->numAggs && !c.failed; i++)
 	{
 		const gg_aggref &ar = agg->aggs[i];
@@ -611,9 +611,13 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			found = prog->nacc++;
 			accroot[found] = ar.arg;
 			needsq[found] = false;
+			checksq[found] = false;
 			prog->acckind[found] = (uint8_t) kind;
 		}
 		if (sq) needsq[found] = true;
+		/* float8_accum squares every input and CHECKFLOATVALs the running sumX2 (float.c:1895): an avg over a finite value
+		 * whose square is not finite is "value out of range: overflow" in the reference even where sumX2 itself is not kept */
+		if (ar.aggfnoid == GG_AGG_AVG_FLOAT8 && !sq) checksq[found] = true;
 		aggmap[i].col = found;
 	}
 	/* value slots: column j -> slot j; sums of squares get the slots after them */
@@ -649,6 +653,7 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 		o->flags |= GGP_F_OUT;
 		o->out = (uint8_t) j;
 		if (prog->accsq[j] >= 0) { o->flags |= GGP_F_OUTSQ; o->out2 = (uint8_t) prog->accsq[j]; }
+		else if (checksq[j]) { o->flags |= GGP_F_OUTSQ; o->out2 = GGP_OUTSQ_CHECK_ONLY; }
 	}
 	emit(c, GGP_END);
 	c.npersist = 0;
@@ -984,7 +989,7 @@ int ggp_disasm(const ggp_program *p, char *buf, int cap)
 		if (o.flags & GGP_F_GROUP) n += snprintf(buf + n, (size_t) (cap - n), " GROUP");
 		if (o.flags & GGP_F_PROBE) n += snprintf(buf + n, (size_t) (cap - n), " PROBE");
 		if (o.flags & GGP_F_OUT) n += snprintf(buf + n, (size_t) (cap - n), " OUT%d", o.out);
-		if (o.flags & GGP_F_OUTSQ) n += snprintf(buf + n, (size_t) (cap - n), " OUTSQ%d", o.out2);
+		if (o.flags & GGP_F_OUTSQ) n += o.out2 == GGP_OUTSQ_CHECK_ONLY ? snprintf(buf + n, (size_t) (cap - n), " SQCHECK") : snprintf(buf + n, (size_t) (cap - n), " OUTSQ%d", o.out2);
 		n += snprintf(buf + n, (size_t) (cap - n), "\n");
 	}
 	return n;

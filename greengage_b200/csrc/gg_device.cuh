@@ -510,7 +510,15 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 		if (o.flags & GGP_F_KEY) sink.key((o.aux >> 6) & 3, M.acc, M.accnull);
 		if (o.flags & GGP_F_GROUP) M.live = sink.group(M.live);
 		if (o.flags & GGP_F_OUT) sink.out(o.out, GG_ACCD, M.accnull);
-		if (o.flags & GGP_F_OUTSQ) { const double v = GG_ACCD; sink.out(o.out2, __dmul_rn(v, v), M.accnull); }
+		if (o.flags & GGP_F_OUTSQ)
+		{
+			const double v = GG_ACCD, sq = __dmul_rn(v, v);
+			if (o.out2 == GGP_OUTSQ_CHECK_ONLY)
+			{
+				if (!f8_finite(sq) && f8_finite(v) && M.live && !(NULLABLE && M.accnull)) err |= GGP_EF_FLOAT_OVERFLOW;
+			}
+			else sink.out(o.out2, sq, M.accnull);
+		}
 	}
 #undef GG_COLADDR
 #undef GG_ISINNER

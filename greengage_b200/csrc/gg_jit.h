@@ -28,7 +28,7 @@ std::string gg_jit_scanagg_source(const ggp_program *prog, int mode, int threads
 int gg_priv_regslots(const ggp_program *prog, int mode, long long num_groups, int join_probe_pc);
 uint64_t gg_plan_hash(const ggp_program *prog, int mode);
 /* build-time plan cache (csrc/plans/gg_plan_cache.cu): address of the kernel specialised for this hash, or nullptr */
-const void *gg_plan_cache_lookup(uint64_t hash, int threads);
+const void *gg_plan_cache_lookup(uint64_t hash, int threads, const ggp_program *prog);
 /* compile (or fetch from the cache) the specialised scan+agg kernel; returns nullptr and fills err when JIT is
  * unavailable or fails */
 gg_jit_kernel *gg_jit_scanagg(const ggp_program *prog, int mode, int threads, int device, char *err, int errlen, int join_probe_pc = -1,

@@ -71,7 +71,10 @@ enum ggp_cc { GGP_LT = 0, GGP_LE, GGP_EQ, GGP_NE, GGP_GT, GGP_GE };
 #define GGP_F_KEY     0x04     /* grouping key [(aux >> 6) & 3] = acc */
 #define GGP_F_GROUP   0x08     /* all keys known: find/insert the group */
 #define GGP_F_OUT     0x10     /* value slot[out] = acc */
-#define GGP_F_OUTSQ   0x20     /* value slot[out2] = acc * acc  (float8_accum's sumX2, float.c:1878) */
+#define GGP_F_OUTSQ   0x20     /* value slot[out2] = acc * acc  (float8_accum's sumX2, float.c:1878); out2 = GGP_OUTSQ_CHECK_ONLY:
+                                * the square is only tested for overflow (a plan that does not ship sumX2 still raises what
+                                * float8_accum's CHECKFLOATVAL raises for a single input, float.c:1895-1896) */
+#define GGP_OUTSQ_CHECK_ONLY 0xFF
 #define GGP_F_PROBE   0x40     /* join pipelines: the probing row's join keys are complete; what follows runs once per match */
 
 typedef struct ggp_op {

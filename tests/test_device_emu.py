@@ -428,3 +428,21 @@ def test_random_plans_over_datum_rows(emu):
         check(groups, aggcol, want, agg)
         stats["equal"] += 1
     assert stats["equal"] > 120 and stats["errors"] > 10, stats
+
+
+def test_avg_raises_what_float8_accum_raises_for_a_square_that_overflows(emu):
+    """float8_accum squares every input (sumX2 += x*x, CHECKFLOATVAL: float.c:1895-1896): avg over a finite 1e200 is "value out
+    of range: overflow" in the reference — also in a one-stage plan, which never ships sumX2.  sum() of the same column is fine."""
+    desc = make_desc([(capi.INT4OID, 4, "i", 1, 1), (capi.FLOAT8OID, 8, "d", 1, 1)])
+    pages = po.build_pages(desc, [[i % 3, 1e200 if i == 777 else float(i)] for i in range(2000)], None)
+    for fn, raises in ((capi.AGG_AVG_FLOAT8, True), (capi.AGG_SUM_FLOAT8, False)):
+        p = ExprPool()
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(1, capi.INT4OID)], [(fn, p.var(2, capi.FLOAT8OID))])
+        scan = capi.make_scan(desc, -1)
+        try:
+            po.seqscan_agg(scan, agg, p.pool, pages)
+            oracle_raised = False
+        except po.OracleError:
+            oracle_raised = True
+        groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, p.pool, pages)
+        assert oracle_raised == raises and bool(err & 0x01) == raises, (fn, oracle_raised, hex(err))
