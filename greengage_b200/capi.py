@@ -19,6 +19,7 @@ GG_MAX_KEYS = 4
 # type OIDs (pg_type.h)
 BOOLOID, INT8OID, INT4OID, TEXTOID, FLOAT8OID = 16, 20, 23, 25, 701
 BPCHAROID, VARCHAROID, DATEOID, TIMESTAMPOID = 1042, 1043, 1082, 1114
+NUMERICOID = 1700
 
 # function OIDs (pg_proc.h), see gg_plan.h
 F_INT4EQ, F_INT4LT, F_INT4NE, F_INT4GT, F_INT4LE, F_INT4GE = 65, 66, 144, 147, 149, 150
@@ -27,6 +28,8 @@ F_FLOAT8EQ, F_FLOAT8NE, F_FLOAT8LT, F_FLOAT8LE, F_FLOAT8GT, F_FLOAT8GE = 293, 29
 F_I4TOD, F_INT48, F_I8TOD = 316, 481, 482
 F_INT8EQ, F_INT8NE, F_INT8LT, F_INT8GT, F_INT8LE, F_INT8GE = 467, 468, 469, 470, 471, 472
 F_BPCHAREQ, F_BPCHARNE = 1048, 1053
+F_NUMERIC_EQ, F_NUMERIC_NE, F_NUMERIC_GT, F_NUMERIC_GE, F_NUMERIC_LT, F_NUMERIC_LE = 1718, 1719, 1720, 1721, 1722, 1723
+F_NUMERIC_ADD, F_NUMERIC_SUB, F_NUMERIC_MUL = 1724, 1725, 1726
 F_DATE_EQ, F_DATE_LT, F_DATE_LE, F_DATE_GT, F_DATE_GE, F_DATE_NE = 1086, 1087, 1088, 1089, 1090, 1091
 F_DATE_LT_TIMESTAMP, F_DATE_LE_TIMESTAMP, F_DATE_EQ_TIMESTAMP = 2338, 2339, 2340
 F_DATE_GT_TIMESTAMP, F_DATE_GE_TIMESTAMP, F_DATE_NE_TIMESTAMP = 2341, 2342, 2343
@@ -35,6 +38,7 @@ AGG_AVG_FLOAT8, AGG_SUM_INT4, AGG_SUM_FLOAT8 = 2105, 2108, 2111
 AGG_MAX_INT8, AGG_MAX_INT4, AGG_MAX_FLOAT8, AGG_MAX_DATE = 2115, 2116, 2120, 2122
 AGG_MIN_INT8, AGG_MIN_INT4, AGG_MIN_FLOAT8, AGG_MIN_DATE = 2131, 2132, 2136, 2138
 AGG_COUNT_ANY, AGG_COUNT_STAR = 2147, 2803
+AGG_AVG_NUMERIC, AGG_SUM_NUMERIC = 2103, 2114
 
 AGGSTAGE_NORMAL, AGGSTAGE_PARTIAL, AGGSTAGE_FINAL = 0, 1, 3
 JOIN_INNER, JOIN_LEFT, JOIN_FULL, JOIN_RIGHT, JOIN_SEMI, JOIN_ANTI, JOIN_LASJ_NOTIN = 0, 1, 2, 3, 4, 5, 6
@@ -246,6 +250,65 @@ def dev_lib():
     return _dev
 
 
+# ---------------------------------------------------------------------------
+# numeric: text <-> (unscaled integer, display scale) <-> on-disk payload (utils/adt/numeric.c:95-190)
+# ---------------------------------------------------------------------------
+
+def numeric_parse(text):
+    """'12.340' -> (12340, 3): the digits as an integer and the number of digits behind the point (numeric_in keeps them)"""
+    t = str(text).strip()
+    neg = t.startswith("-")
+    t = t.lstrip("+-")
+    ip, _, fp = t.partition(".")
+    v = int((ip or "0") + fp)
+    return (-v if neg else v), len(fp)
+
+
+def numeric_text(unscaled, dscale):
+    """(12340, 3) -> '12.340' (numeric_out: exactly dscale digits behind the point)"""
+    neg = unscaled < 0
+    d = str(abs(int(unscaled))).rjust(dscale + 1, "0")
+    s = d if dscale == 0 else d[:-dscale] + "." + d[-dscale:]
+    return ("-" if neg else "") + s
+
+
+def numeric_payload(unscaled, dscale):
+    """The bytes of a numeric datum behind its varlena header, as numeric_in -> make_result build them (numeric.c:5432 ff):
+    base-10000 digits with leading and trailing zero digits stripped, the 2-byte short header when display scale and weight
+    fit it (NUMERIC_CAN_BE_SHORT), else the 4-byte long one; zero has no digits and weight 0."""
+    neg = unscaled < 0
+    mag = abs(int(unscaled))
+    d = str(mag).rjust(dscale + 1, "0")
+    ip, fp = (d, "") if dscale == 0 else (d[:-dscale], d[-dscale:])
+    ip = ip.lstrip("0")
+    ip = ip.rjust((len(ip) + 3) // 4 * 4, "0")
+    fp = fp.ljust((len(fp) + 3) // 4 * 4, "0")
+    digits = [int(ip[i:i + 4]) for i in range(0, len(ip), 4)] + [int(fp[i:i + 4]) for i in range(0, len(fp), 4)]
+    weight = len(ip) // 4 - 1
+    while digits and digits[0] == 0:
+        digits.pop(0)
+        weight -= 1
+    while digits and digits[-1] == 0:
+        digits.pop()
+    if not digits:
+        weight, neg = 0, False
+    import struct
+    if dscale <= 0x3F and -64 <= weight <= 63:
+        hdr = 0x8000 | (0x2000 if neg else 0) | (dscale << 7) | (0x40 if weight < 0 else 0) | (weight & 0x3F)
+        out = struct.pack("<H", hdr)
+    else:
+        out = struct.pack("<Hh", (0x4000 if neg else 0) | (dscale & 0x3FFF), weight)
+    return out + b"".join(struct.pack("<h", x) for x in digits)
+
+
+def numeric_of_aggval(v):
+    """a numeric sum / avg result (gg_aggval: i = low 64 bits, f[0] = bits of the high 64, f[1] = display scale) -> text"""
+    import struct
+    hi = struct.unpack("<q", struct.pack("<d", v.f[0]))[0]
+    val = (hi << 64) | (v.i & 0xFFFFFFFFFFFFFFFF)
+    return numeric_text(val, int(v.f[1]))
+
+
 def check(rc):
     if rc != 0:
         raise GGError(rc, dev_lib().gg_last_error().decode("utf-8", "replace"))
@@ -296,6 +359,8 @@ class ExprPool:
                 n.constvalue = C.c_int64.from_buffer_copy(C.c_double(float(value))).value
             elif typid in (BPCHAROID, VARCHAROID, TEXTOID):
                 n.constvalue, n.constlen = pack_str(value, typid == BPCHAROID)
+            elif typid == NUMERICOID:
+                n.constvalue, n.constlen = numeric_parse(value)      # unscaled integer + display scale (gg_plan.h "numeric")
             else:
                 n.constvalue = int(value)
         return i

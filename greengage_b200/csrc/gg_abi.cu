@@ -37,6 +37,7 @@ int gg_errflags_to_code(uint32_t f)
 	if (f & GGP_EF_DIV_ZERO) { gg_set_error("division by zero"); return GG_ERR_DIV_ZERO; }
 	if (f & GGP_EF_INT_OVERFLOW) { gg_set_error("bigint out of range"); return GG_ERR_INT_OVERFLOW; }
 	if (f & GGP_EF_DATE_RANGE) { gg_set_error("date out of range for timestamp"); return GG_ERR_DATE_RANGE; }
+	if (f & GGP_EF_NUMERIC_RANGE) { gg_set_error("numeric value outside the scaled 64-bit range of the GPU path (or NaN, or more fractional digits than the column's scale)"); return GG_ERR_UNSUPPORTED; }
 	if (f & GGP_EF_STRING_TOO_LONG) { gg_set_error("string value longer than 8 bytes (or toasted) in a GPU expression"); return GG_ERR_UNSUPPORTED; }
 	if (f & GGP_EF_PEER_FAILED) { gg_set_error("another segment reported an error in its slice below the Motion"); return GG_ERR_PEER; }
 	if (f & GGP_EF_HOSTPATH) { gg_set_error("a segment could not keep its aggregate rows on the device: run the slice with host-row Motions"); return GG_ERR_RETRY_HOST; }

@@ -31,6 +31,7 @@ struct Ctx {
 	int temps_busy;           /* bit t: temporary t holds a live value */
 	int npersist;
 	int persist_root[4], persist_temp[4];   /* common subexpressions kept in temporaries for later aggregate arguments */
+	int persist_scale[4];     /* numeric subexpressions: the scale the temporary holds the value at */
 	bool inner_as_outer;      /* build program of a join: the inner tuple is the scanned one */
 	bool failed;
 };
@@ -54,6 +55,7 @@ int loadtype_of(int32_t typid)
 		case GG_BPCHAROID: return GGP_LT_BPCHAR;
 		case GG_VARCHAROID: case GG_TEXTOID: return GGP_LT_VARCHAR;
 		case GG_BOOLOID: return GGP_LT_BOOL;
+		case GG_NUMERICOID: return GGP_LT_NUM;
 	}
 	return 0;
 }
@@ -127,6 +129,7 @@ int col_slot(Ctx &c, int varno, int attno)
 	if (s->att[a].slot >= 0) return s->att[a].slot;
 	int lt = loadtype_of(d->attrs[a].atttypid);
 	if (!lt) { fail(c, "column %d: type %d not supported on the GPU path", attno, d->attrs[a].atttypid); return 0; }
+	if (d->format == GG_FMT_DATUMROWS && lt == GGP_LT_NUM) { fail(c, "numeric columns do not travel as datum rows yet"); return 0; }
 	if (d->format == GG_FMT_DATUMROWS) lt = GGP_LT_I8;       /* already in loaded form */
 	if (s->ncols >= GGP_MAX_COLS) { fail(c, "too many referenced columns"); return 0; }
 	int slot = s->ncols++;
@@ -156,7 +159,7 @@ bool is_col_op(int op)
 	{
 		case GGP_LD_C4: case GGP_LD_C8: case GGP_LD_BP: case GGP_LD_VS: case GGP_LD_BOOL:
 		case GGP_ADD_C: case GGP_SUB_C: case GGP_RSUB_C: case GGP_MUL_C: case GGP_DIV_C: case GGP_RDIV_C:
-		case GGP_CMPF_C: case GGP_CMPI_C4: case GGP_CMPI_C8:
+		case GGP_CMPF_C: case GGP_CMPI_C4: case GGP_CMPI_C8: case GGP_LD_NUM:
 			return true;
 	}
 	return false;
@@ -238,9 +241,9 @@ Operand operand_of(Ctx &c, int root)
 		int lt = s->coltype[slot];
 		o.idx = slot | (inner ? 0x80 : 0);
 		o.kind = lt == GGP_LT_I4 ? OPD_C4 : lt == GGP_LT_I8 ? OPD_C8 : OPD_STR;
-		if (lt == GGP_LT_BOOL) o.kind = OPD_NONE;
+		if (lt == GGP_LT_BOOL || lt == GGP_LT_NUM) o.kind = OPD_NONE;
 	}
-	else if (e.kind == GG_E_CONST)
+	else if (e.kind == GG_E_CONST && e.rettype != GG_NUMERICOID)
 	{
 		o.kind = OPD_K;
 		o.idx = add_const(c, e.constvalue, e.constisnull != 0);
@@ -254,7 +257,7 @@ int swap_cc(int cc)
 	return cc;
 }
 
-enum { K_F8ADD = 1, K_F8SUB, K_F8MUL, K_F8DIV, K_CMPF, K_CMPI, K_CMPS, K_AND, K_OR };
+enum { K_F8ADD = 1, K_F8SUB, K_F8MUL, K_F8DIV, K_CMPF, K_CMPI, K_CMPS, K_AND, K_OR, K_NADD, K_NSUB, K_NMUL, K_NCMP };
 struct BinInfo { int k, cc; bool isbin; };
 
 bool func_info(int funcid, BinInfo *b, int *unary_op)
@@ -267,6 +270,9 @@ bool func_info(int funcid, BinInfo *b, int *unary_op)
 		case GG_F_FLOAT8MUL: b->k = K_F8MUL; return true;
 		case GG_F_FLOAT8MI:  b->k = K_F8SUB; return true;
 		case GG_F_FLOAT8DIV: b->k = K_F8DIV; return true;
+		case GG_F_NUMERIC_ADD: b->k = K_NADD; return true;
+		case GG_F_NUMERIC_SUB: b->k = K_NSUB; return true;
+		case GG_F_NUMERIC_MUL: b->k = K_NMUL; return true;
 #define CMPCASE(F, K, CC) case F: b->k = K; b->cc = CC; return true;
 		CMPCASE(GG_F_FLOAT8LT, K_CMPF, GGP_LT) CMPCASE(GG_F_FLOAT8LE, K_CMPF, GGP_LE)
 		CMPCASE(GG_F_FLOAT8EQ, K_CMPF, GGP_EQ) CMPCASE(GG_F_FLOAT8NE, K_CMPF, GGP_NE)
@@ -281,6 +287,9 @@ bool func_info(int funcid, BinInfo *b, int *unary_op)
 		CMPCASE(GG_F_DATE_EQ, K_CMPI, GGP_EQ) CMPCASE(GG_F_DATE_NE, K_CMPI, GGP_NE)
 		CMPCASE(GG_F_DATE_GT, K_CMPI, GGP_GT) CMPCASE(GG_F_DATE_GE, K_CMPI, GGP_GE)
 		CMPCASE(GG_F_BPCHAREQ, K_CMPS, GGP_EQ) CMPCASE(GG_F_BPCHARNE, K_CMPS, GGP_NE)
+		CMPCASE(GG_F_NUMERIC_LT, K_NCMP, GGP_LT) CMPCASE(GG_F_NUMERIC_LE, K_NCMP, GGP_LE)
+		CMPCASE(GG_F_NUMERIC_EQ, K_NCMP, GGP_EQ) CMPCASE(GG_F_NUMERIC_NE, K_NCMP, GGP_NE)
+		CMPCASE(GG_F_NUMERIC_GT, K_NCMP, GGP_GT) CMPCASE(GG_F_NUMERIC_GE, K_NCMP, GGP_GE)
 #undef CMPCASE
 		case GG_F_INT48: b->isbin = false; *unary_op = -1; return true;     /* loads already sign-extend */
 		case GG_F_I4TOD: case GG_F_I8TOD: b->isbin = false; *unary_op = GGP_I2F8; return true;
@@ -422,11 +431,136 @@ void gen_binary(Ctx &c, int lroot, int rroot, int k, int cc)
 	}
 }
 
+/* ---- numeric as scaled 64-bit integers (gg_plan.h "numeric") ---- */
+static const int64_t kPow10[19] = { 1LL, 10LL, 100LL, 1000LL, 10000LL, 100000LL, 1000000LL, 10000000LL, 100000000LL, 1000000000LL, 10000000000LL,
+                                    100000000000LL, 1000000000000LL, 10000000000000LL, 100000000000000LL, 1000000000000000LL,
+                                    10000000000000000LL, 100000000000000000LL, 1000000000000000000LL };
+#define GG_NUM_MAX_SCALE 15            /* a load op carries its scale in four bits */
+
+/* display scale of a numeric expression, as numeric.c computes it: a column's declared scale; add / sub: the larger of the
+ * operands' (numeric.c:1659,1698 -> add_var / sub_var: res_dscale = Max); mul: their sum (numeric.c:1735 -> mul_var rscale) */
+int num_scale(Ctx &c, int root)
+{
+	if (c.failed) return 0;
+	if (root < 0 || root >= c.pool->nnodes) { fail(c, "bad expression index %d", root); return 0; }
+	const gg_expr &e = c.pool->nodes[root];
+	if (e.rettype != GG_NUMERICOID) { fail(c, "numeric operator applied to a value of type %d (missing cast)", e.rettype); return 0; }
+	if (e.kind == GG_E_VAR)
+	{
+		const bool inner = e.varno == 1 && !c.inner_as_outer;
+		const gg_tupdesc *d = inner ? c.idesc : c.odesc;
+		if (!d || e.varattno < 1 || e.varattno > d->natts) { fail(c, "Var attno %d out of range", e.varattno); return 0; }
+		const int32_t typmod = d->attrs[e.varattno - 1].atttypmod;
+		if (typmod < 4) { fail(c, "numeric column %d has no declared scale: only numeric(p,s) runs on the GPU path", e.varattno); return 0; }
+		const int sc = (typmod - 4) & 0xFFFF;
+		if (sc > GG_NUM_MAX_SCALE) { fail(c, "numeric column %d: scale %d not supported on the GPU path", e.varattno, sc); return 0; }
+		return sc;
+	}
+	if (e.kind == GG_E_CONST)
+	{
+		if (e.constlen < 0 || e.constlen > GG_NUM_MAX_SCALE) { fail(c, "numeric constant with display scale %d", e.constlen); return 0; }
+		return e.constlen;
+	}
+	if (e.kind == GG_E_FUNC)
+	{
+		BinInfo b; int un;
+		if (func_info(e.funcid, &b, &un) && b.isbin && (b.k == K_NADD || b.k == K_NSUB || b.k == K_NMUL))
+		{
+			const int l = num_scale(c, e.args[0]), r = num_scale(c, e.args[1]);
+			const int sc = b.k == K_NMUL ? l + r : (l > r ? l : r);
+			if (sc > GG_NUM_MAX_SCALE) { fail(c, "numeric expression with display scale %d not supported on the GPU path", sc); return 0; }
+			return sc;
+		}
+	}
+	fail(c, "numeric expression (kind %d, function %d) not supported on the GPU path", e.kind, e.funcid);
+	return 0;
+}
+
+int num_const(Ctx &c, const gg_expr &e, int want)
+{
+	/* the constant at the wanted scale, computed here: a constant that does not fit is a plan this path does not take */
+	__int128 v = (__int128) e.constvalue * (__int128) kPow10[want - e.constlen];
+	if (v > INT64_MAX || v < INT64_MIN) { fail(c, "numeric constant out of the 64-bit range at scale %d", want); return 0; }
+	return add_const(c, (int64_t) v, e.constisnull != 0);
+}
+
+/* acc = value(root) * 10^want, want >= the expression's own scale */
+void gen_num(Ctx &c, int root, int want)
+{
+	if (c.failed) return;
+	const gg_expr &e = c.pool->nodes[root];
+	const int own = num_scale(c, root);
+	if (c.failed) return;
+	if (want < own || want > GG_NUM_MAX_SCALE + 3) { fail(c, "numeric expression needs scale %d", want); return; }
+	for (int i = 0; i < c.npersist; i++)
+		if (expr_equal(c.pool, c.persist_root[i], root))
+		{
+			emit(c, GGP_LD_T, c.persist_temp[i]);
+			if (want > c.persist_scale[i]) emit(c, GGP_IMUL_K, add_const(c, kPow10[want - c.persist_scale[i]], false));
+			return;
+		}
+	if (e.kind == GG_E_VAR)
+	{
+		const int slot = col_slot(c, e.varno, e.varattno);
+		if (c.failed) return;
+		emit(c, GGP_LD_NUM, slot | ((e.varno == 1 && !c.inner_as_outer) ? 0x80 : 0), want & 15);
+		if (want > 15) emit(c, GGP_IMUL_K, add_const(c, kPow10[want - 15], false));
+		return;
+	}
+	if (e.kind == GG_E_CONST) { emit(c, GGP_LD_K, num_const(c, e, want)); return; }
+	BinInfo b; int un;
+	func_info(e.funcid, &b, &un);
+	const gg_expr &l = c.pool->nodes[e.args[0]], &r = c.pool->nodes[e.args[1]];
+	if (b.k == K_NADD || b.k == K_NSUB)
+	{
+		/* (a +- b) * 10^k = a * 10^k +- b * 10^k: both operands are produced at the wanted scale */
+		if (r.kind == GG_E_CONST) { gen_num(c, e.args[0], want); emit(c, b.k == K_NADD ? GGP_IADD_K : GGP_ISUB_K, num_const(c, r, want)); return; }
+		if (l.kind == GG_E_CONST) { gen_num(c, e.args[1], want); emit(c, b.k == K_NADD ? GGP_IADD_K : GGP_IRSUB_K, num_const(c, l, want)); return; }
+		gen_num(c, e.args[0], want);
+		const int t = alloc_temp(c);
+		store_temp(c, t);
+		gen_num(c, e.args[1], want);
+		emit(c, b.k == K_NADD ? GGP_IADD_T : GGP_IRSUB_T, t);
+		c.temps_busy &= ~(1 << t);
+		return;
+	}
+	/* mul: scales add; whatever the caller wants beyond that goes into the left operand */
+	const int ls = num_scale(c, e.args[0]), rs = num_scale(c, e.args[1]);
+	const int extra = want - (ls + rs);
+	if (r.kind == GG_E_CONST) { gen_num(c, e.args[0], ls + extra); emit(c, GGP_IMUL_K, num_const(c, r, rs)); return; }
+	if (l.kind == GG_E_CONST) { gen_num(c, e.args[1], rs + extra); emit(c, GGP_IMUL_K, num_const(c, l, ls)); return; }
+	gen_num(c, e.args[0], ls + extra);
+	const int t = alloc_temp(c);
+	store_temp(c, t);
+	gen_num(c, e.args[1], rs);
+	emit(c, GGP_IMUL_T, t);
+	c.temps_busy &= ~(1 << t);
+}
+
+/* numeric comparison: both sides at the larger scale, then a signed integer compare (numeric_cmp, numeric.c:1512, orders
+ * values, not representations: 1.0 = 1.00) */
+void gen_num_cmp(Ctx &c, int lroot, int rroot, int cc)
+{
+	const int ls = num_scale(c, lroot), rs = num_scale(c, rroot);
+	if (c.failed) return;
+	const int sc = ls > rs ? ls : rs;
+	const gg_expr &r = c.pool->nodes[rroot], &l = c.pool->nodes[lroot];
+	if (r.kind == GG_E_CONST) { gen_num(c, lroot, sc); emit(c, GGP_CMPI_K, num_const(c, r, sc), cc); return; }
+	if (l.kind == GG_E_CONST) { gen_num(c, rroot, sc); emit(c, GGP_CMPI_K, num_const(c, l, sc), swap_cc(cc)); return; }
+	gen_num(c, lroot, sc);
+	const int t = alloc_temp(c);
+	store_temp(c, t);
+	gen_num(c, rroot, sc);
+	emit(c, GGP_CMPI_T, t, swap_cc(cc));          /* acc = right, temp = left: left cc right == right swap(cc) left */
+	c.temps_busy &= ~(1 << t);
+}
+
 void gen(Ctx &c, int root)
 {
 	if (c.failed) return;
 	if (root < 0 || root >= c.pool->nnodes) { fail(c, "bad expression index %d", root); return; }
 	const gg_expr &e = c.pool->nodes[root];
+	if (e.rettype == GG_NUMERICOID && (e.kind == GG_E_VAR || e.kind == GG_E_CONST || e.kind == GG_E_FUNC)) { gen_num(c, root, num_scale(c, root)); return; }
 	Operand o = operand_of(c, root);
 	if (o.kind != OPD_NONE || e.kind == GG_E_VAR) { emit_load(c, o, root); return; }
 
@@ -460,6 +594,7 @@ void gen(Ctx &c, int root)
 			}
 			BinInfo b; int un;
 			if (!func_info(e.funcid, &b, &un)) { fail(c, "function %d not supported on the GPU path", e.funcid); return; }
+			if (b.k == K_NCMP) { gen_num_cmp(c, e.args[0], e.args[1], b.cc); return; }
 			/* the argument types must be the function's own (a planner never emits anything else; a
 			 * hand-built plan that does is refused rather than reinterpreting Datum bits) */
 			{
@@ -571,11 +706,15 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 
 	/* ---- aggregate arguments -> deduplicated accumulator columns ---- */
 	int accroot[GGP_MAX_ACCS];
+	int accnum[GGP_MAX_ACCS];          /* numeric sums live in two int64 columns: 1 = low 32 bits of every input, 2 = the rest */
 	bool needsq[GGP_MAX_ACCS], checksq[GGP_MAX_ACCS];
+	for (int j = 0; j < GGP_MAX_ACCS; j++) accnum[j] = 0;
 	for (int i = 0; i < agg->numAggs && !c.failed; i++)
 	{
 		const gg_aggref &ar = agg->aggs[i];
 		int kind = 0, sq = 0;
+		bool isnum = false;
+		aggmap[i].scale = 0;
 		switch (ar.aggfnoid)
 		{
 			case GG_AGG_COUNT_STAR: aggmap[i].col = -1; continue;
@@ -587,6 +726,12 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			case GG_AGG_MIN_FLOAT8: kind = GGP_ACC_F8MIN; break;
 			case GG_AGG_MAX_FLOAT8: kind = GGP_ACC_F8MAX; break;
 			case GG_AGG_SUM_INT4: kind = GGP_ACC_I8SUM; break;
+			case GG_AGG_SUM_NUMERIC: case GG_AGG_AVG_NUMERIC:
+				/* numeric_avg_accum (numeric.c:3057): N and an exact running sum — here a 128-bit integer at the argument's
+				 * scale, kept as two int64 sums of the inputs' halves */
+				kind = GGP_ACC_I8SUM; isnum = true;
+				if (agg->aggstage != GG_AGGSTAGE_NORMAL) fail(c, "numeric aggregates run as one-stage aggregates on the GPU path");
+				break;
 			case GG_AGG_MIN_INT4: case GG_AGG_MIN_INT8: case GG_AGG_MIN_DATE: kind = GGP_ACC_I8MIN; break;
 			case GG_AGG_MAX_INT4: case GG_AGG_MAX_INT8: case GG_AGG_MAX_DATE: kind = GGP_ACC_I8MAX; break;
 			default: fail(c, "aggregate %d not supported on the GPU path", ar.aggfnoid); continue;
@@ -598,6 +743,10 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			/* every column kind also counts its non-NULL inputs, so count(x) rides on any column over x —
 			 * and a column created for count(x) is upgraded when sum/min/max(x) comes later */
 			bool compat = prog->acckind[j] == kind || kind == GGP_ACC_COUNT || prog->acckind[j] == GGP_ACC_COUNT;
+			/* a numeric sum is a PAIR of columns: another numeric aggregate over the same argument shares it, count(x) rides on
+			 * its low half, nothing else does — and it never takes over a column made for count(x) */
+			if (isnum) compat = accnum[j] == 1;
+			else if (accnum[j] != 0) compat = kind == GGP_ACC_COUNT && accnum[j] == 1;
 			if (compat && expr_equal(pool, accroot[j], ar.arg))
 			{
 				found = j;
@@ -613,7 +762,16 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			needsq[found] = false;
 			checksq[found] = false;
 			prog->acckind[found] = (uint8_t) kind;
+			if (isnum)
+			{
+				if (prog->nacc >= GGP_MAX_ACCS) { fail(c, "too many distinct aggregate arguments"); continue; }
+				accnum[found] = 1;
+				const int hi = prog->nacc++;
+				accroot[hi] = ar.arg; accnum[hi] = 2; needsq[hi] = checksq[hi] = false;
+				prog->acckind[hi] = GGP_ACC_I8SUM;
+			}
 		}
+		if (isnum) aggmap[i].scale = num_scale(c, ar.arg);
 		if (sq) needsq[found] = true;
 		/* float8_accum squares every input and CHECKFLOATVALs the running sumX2 (float.c:1895): an avg over a finite value
 		 * whose square is not finite is "value out of range: overflow" in the reference even where sumX2 itself is not kept */
@@ -633,6 +791,44 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 	c.npersist = 0;
 	for (int j = 0; j < prog->nacc && !c.failed; j++)
 	{
+		if (accnum[j] == 2) continue;          /* written together with its low half */
+		if (accnum[j] == 1)
+		{
+			/* acc = the argument at its own scale; kept in a temporary so that both halves can be taken from it (and, when a
+			 * later argument contains it — Q1's l_extendedprice * (1 - l_discount) inside sum_charge — for that one too) */
+			const int sc = num_scale(c, accroot[j]);
+			c.temps_busy = 0;
+			for (int i = 0; i < c.npersist; i++) c.temps_busy |= 1 << c.persist_temp[i];
+			int t = -1;
+			bool persisted = false;
+			for (int i = 0; i < c.npersist; i++)
+				if (expr_equal(pool, c.persist_root[i], accroot[j]) && c.persist_scale[i] == sc) { t = c.persist_temp[i]; persisted = true; }
+			if (t < 0)
+			{
+				gen_num(c, accroot[j], sc);
+				if (c.failed) break;
+				t = alloc_temp(c);
+				store_temp(c, t);
+				const gg_expr &e = pool->nodes[accroot[j]];
+				bool reused = false;
+				for (int k = j + 2; k < prog->nacc && e.kind == GG_E_FUNC; k++)
+					if (accnum[k] == 1 && contains(pool, accroot[k], accroot[j]) && !expr_equal(pool, accroot[k], accroot[j])) reused = true;
+				if (reused && c.npersist < 2)
+				{
+					c.persist_root[c.npersist] = accroot[j]; c.persist_temp[c.npersist] = t; c.persist_scale[c.npersist] = sc;
+					c.npersist++;
+					persisted = true;
+				}
+			}
+			emit(c, GGP_LD_T, t);
+			emit(c, GGP_LO32);
+			prog->code[prog->ncode - 1].flags |= GGP_F_OUT; prog->code[prog->ncode - 1].out = (uint8_t) j;
+			emit(c, GGP_LD_T, t);
+			emit(c, GGP_SAR32);
+			prog->code[prog->ncode - 1].flags |= GGP_F_OUT; prog->code[prog->ncode - 1].out = (uint8_t) (j + 1);
+			if (!persisted) c.temps_busy &= ~(1 << t);
+			continue;
+		}
 		ggp_op *o = gen_value(c, accroot[j]);
 		if (c.failed) break;
 		const gg_expr &e = pool->nodes[accroot[j]];
@@ -647,6 +843,7 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 			o = &prog->code[prog->ncode - 1];
 			c.persist_root[c.npersist] = accroot[j];
 			c.persist_temp[c.npersist] = t;
+			c.persist_scale[c.npersist] = 0;
 			c.npersist++;
 		}
 		if (o->flags & (GGP_F_OUT | GGP_F_OUTSQ)) { emit(c, GGP_NOP); o = &prog->code[prog->ncode - 1]; }
@@ -976,7 +1173,8 @@ int ggp_disasm(const ggp_program *p, char *buf, int cap)
 		"ADD_C", "ADD_K", "ADD_T", "SUB_C", "SUB_K", "SUB_T", "RSUB_C", "RSUB_K", "RSUB_T", "MUL_C", "MUL_K", "MUL_T",
 		"DIV_C", "DIV_K", "DIV_T", "RDIV_C", "RDIV_K", "RDIV_T", "CMPF_C", "CMPF_K", "CMPF_T",
 		"CMPI_C4", "CMPI_C8", "CMPI_K", "CMPI_T", "CMPS_K", "CMPS_T", "DATE2TS", "I2F8", "AND_T", "OR_T",
-		"NOT", "ISNULL", "ISNOTNULL", "NOP", "GUARD_AND", "GUARD_OR", "UNGUARD" };
+		"NOT", "ISNULL", "ISNOTNULL", "NOP", "GUARD_AND", "GUARD_OR", "UNGUARD",
+		"LD_NUM", "IADD_K", "IADD_T", "ISUB_K", "ISUB_T", "IRSUB_K", "IRSUB_T", "IMUL_K", "IMUL_T", "LO32", "SAR32" };
 	int n = 0;
 	for (int i = 0; i < p->ncode && n < cap - 96; i++)
 	{

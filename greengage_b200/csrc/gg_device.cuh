@@ -292,6 +292,79 @@ __device__ __forceinline__ uint64_t load_str(uint32_t p, bool strip, uint32_t &e
 	return v;
 }
 
+/* numeric column -> 64-bit integer scaled by 10^scale.  On-disk form (utils/adt/numeric.c:95-190): varlena header, then
+ * n_header (short: bit 15 set, sign bit 13, dscale bits 12-7, weight sign bit 6, weight bits 5-0; long: sign bits 15-14,
+ * dscale bits 13-0, followed by int16 weight), then base-10000 digits (int16 each), most significant first, leading and
+ * trailing zero digits stripped.  value = sum digit[i] * 10000^(weight - i). */
+__device__ __forceinline__ int64_t load_numeric(uint32_t p, int scale, uint32_t &err)
+{
+	const uint32_t h = lds8(p);
+	uint32_t len, d;
+	if (h & 0x80)
+	{
+		if (h == 0x80) { err |= GGP_EF_NUMERIC_RANGE; return 0; }           /* TOAST pointer */
+		len = (h & 0x7F) - 1; d = p + 1;
+	}
+	else
+	{
+		if (h & 0x40) { err |= GGP_EF_NUMERIC_RANGE; return 0; }            /* compressed in line */
+		len = ((((h & 0x3F) << 24) | (lds8(p + 1) << 16) | (lds8(p + 2) << 8) | lds8(p + 3))) - 4;
+		d = p + 4;
+	}
+	if (len < 2) { err |= GGP_EF_NUMERIC_RANGE; return 0; }
+	const uint32_t nh = lds8(d) | (lds8(d + 1) << 8);
+	if ((nh & 0xC000) == 0xC000) { err |= GGP_EF_NUMERIC_RANGE; return 0; }     /* NaN */
+	bool neg;
+	int weight;
+	uint32_t dp;
+	if (nh & 0x8000)
+	{
+		neg = (nh & 0x2000) != 0;
+		weight = (int) (nh & 0x3F) | ((nh & 0x40) ? ~0x3F : 0);
+		dp = d + 2;
+	}
+	else
+	{
+		if (len < 4) { err |= GGP_EF_NUMERIC_RANGE; return 0; }
+		neg = (nh & 0xC000) == 0x4000;
+		weight = (int) (int16_t) (lds8(d + 2) | (lds8(d + 3) << 8));
+		dp = d + 4;
+	}
+	const int nd = (int) ((d + len - dp) >> 1);
+	if (nd > 8) { err |= GGP_EF_NUMERIC_RANGE; return 0; }                      /* more than 32 decimal digits never fit */
+	uint64_t v = 0;
+	bool bad = false;
+	for (int i = 0; i < nd; i++)
+	{
+		const uint32_t dig = lds8(dp + 2 * i) | (lds8(dp + 2 * i + 1) << 8);
+		if (__umul64hi(v, 10000ull) != 0) bad = true;
+		v = v * 10000ull + dig;
+	}
+	/* v = value * 10000^(nd - 1 - weight); wanted: value * 10^scale */
+	int e = 4 * (weight - (nd - 1)) + scale;
+	if (nd == 0) e = 0;
+	for (; e > 0; e--) { if (__umul64hi(v, 10ull) != 0) bad = true; v *= 10ull; }
+	for (; e < 0; e++) { if (v % 10ull) bad = true; v /= 10ull; }               /* digits beyond the column's scale must be zeros */
+	if (v >> 63) bad = true;
+	if (bad) { err |= GGP_EF_NUMERIC_RANGE; return 0; }
+	return neg ? -(int64_t) v : (int64_t) v;
+}
+
+/* exact 64-bit integer arithmetic for scaled numerics: overflow is reported, never wrapped */
+__device__ __forceinline__ int64_t i64_add_chk(int64_t a, int64_t b, bool &ovf)
+{
+	const int64_t r = (int64_t) ((uint64_t) a + (uint64_t) b);
+	if (((a ^ r) & (b ^ r)) < 0) ovf = true;
+	return r;
+}
+__device__ __forceinline__ int64_t i64_mul_chk(int64_t a, int64_t b, bool &ovf)
+{
+	const int64_t hi = __mul64hi(a, b);
+	const int64_t lo = (int64_t) ((uint64_t) a * (uint64_t) b);
+	if (hi != (lo >> 63)) ovf = true;
+	return lo;
+}
+
 __device__ __forceinline__ int f8_cmp(double a, double b)
 {
 	/* float8_cmp_internal, float.c:964: NaN = NaN, NaN > everything */
@@ -492,6 +565,32 @@ __device__ __forceinline__ void exec_op(const ggp_op o, const EvalCtx &X, const 
 			break;
 		}
 		case GGP_UNGUARD: M.live = (M.livestk & 1u) != 0; M.livestk >>= 1; break;
+		case GGP_LD_NUM:
+		{
+			uint32_t e2 = 0;
+			M.accnull = GG_COLNULL(o);
+			M.acc = M.accnull ? 0 : (uint64_t) load_numeric(GG_COLADDR(o), o.aux & 15, e2);
+			if (M.live) err |= e2;
+			break;
+		}
+		case GGP_IADD_K: case GGP_IADD_T: case GGP_ISUB_K: case GGP_ISUB_T: case GGP_IRSUB_K: case GGP_IRSUB_T: case GGP_IMUL_K: case GGP_IMUL_T:
+		{
+			const bool isk = op == GGP_IADD_K || op == GGP_ISUB_K || op == GGP_IRSUB_K || op == GGP_IMUL_K;
+			const int64_t x = isk ? (int64_t) KV(o.idx) : (int64_t) GG_TEMP(o.idx), a = (int64_t) M.acc;
+			const bool xn = isk ? GG_KNULL(o.idx) : GG_TNULL(o.idx);
+			bool ovf = false;
+			int64_t r;
+			if (op == GGP_IADD_K || op == GGP_IADD_T) r = i64_add_chk(a, x, ovf);
+			else if (op == GGP_ISUB_K || op == GGP_ISUB_T) { if (x == INT64_MIN) ovf = true; r = i64_add_chk(a, -x, ovf); }
+			else if (op == GGP_IRSUB_K || op == GGP_IRSUB_T) { if (a == INT64_MIN) ovf = true; r = i64_add_chk(x, -a, ovf); }
+			else r = i64_mul_chk(a, x, ovf);
+			const bool isn = NULLABLE && (M.accnull || xn);
+			if (ovf && M.live && !isn) err |= GGP_EF_NUMERIC_RANGE;
+			M.acc = (uint64_t) r; M.accnull = isn;
+			break;
+		}
+		case GGP_LO32: M.acc = M.acc & 0xFFFFFFFFull; break;
+		case GGP_SAR32: M.acc = (uint64_t) ((int64_t) M.acc >> 32); break;
 		case GGP_NOT: M.acc = (M.acc == 0); break;
 		case GGP_ISNULL: M.acc = M.accnull; M.accnull = false; break;
 		case GGP_ISNOTNULL: M.acc = !M.accnull; M.accnull = false; break;

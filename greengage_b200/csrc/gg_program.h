@@ -31,7 +31,8 @@ enum ggp_loadtype {
 	GGP_LT_I8 = 2,       /* int8/timestamp/float8 bits */
 	GGP_LT_BPCHAR = 3,   /* short string, trailing blanks stripped (bcTruelen), <= 8 bytes packed LSB-first */
 	GGP_LT_VARCHAR = 4,  /* short string, not stripped */
-	GGP_LT_BOOL = 5
+	GGP_LT_BOOL = 5,
+	GGP_LT_NUM = 6       /* numeric varlena -> 64-bit integer scaled by 10^scale (scale in the load op's aux, bits 0-3) */
 };
 
 /* Opcodes.  Operation and operand kind are fused into one opcode.  Operand suffixes: _C column (8-byte
@@ -60,6 +61,14 @@ enum ggp_opcode {
 	 * GUARD pushes `live` and clears it where temp[idx] already decides (AND: non-NULL FALSE; OR: non-NULL TRUE);
 	 * UNGUARD pops. */
 	GGP_GUARD_AND, GGP_GUARD_OR, GGP_UNGUARD,
+	/* numeric as scaled 64-bit integers (gg_plan.h "numeric"): exact integer arithmetic; a result that does not fit raises
+	 * GGP_EF_NUMERIC_RANGE (the plan then runs on the CPU path), never a wrong value */
+	GGP_LD_NUM,                                 /* acc = numeric column idx scaled by 10^(aux & 15) */
+	GGP_IADD_K, GGP_IADD_T,                     /* acc + x */
+	GGP_ISUB_K, GGP_ISUB_T,                     /* acc - x */
+	GGP_IRSUB_K, GGP_IRSUB_T,                   /* x - acc */
+	GGP_IMUL_K, GGP_IMUL_T,                     /* acc * x */
+	GGP_LO32, GGP_SAR32,                        /* acc & 0xFFFFFFFF ; acc >> 32 (arithmetic): the two halves a 128-bit sum is kept in */
 	GGP_NOPS
 };
 
@@ -180,6 +189,8 @@ typedef struct ggp_grec {
 #define GGP_EF_HOSTPATH         0x4000  /* a segment could not contribute device-resident records to a Motion (its aggregate
                                          * spilled to the general hash table, or holds more groups than a block carries): every
                                          * segment sees it and the slice is run again with host-row Motions */
+#define GGP_EF_NUMERIC_RANGE    0x8000  /* a numeric value / product outside the scaled 64-bit representation, a NaN, or more
+                                         * fractional digits than the column's scale: not an ERROR of the query — CPU path */
 #define GGP_EF_INFO_MASK        (GGP_EF_SAW_INF | GGP_EF_RECHECK)
 
 /* how a Motion hash key is hashed (cdbhash.c:215-287: the type's default hash opclass function) */
@@ -190,7 +201,8 @@ typedef struct ggp_acckinds { uint8_t k[GGP_MAX_ACCS]; } ggp_acckinds;
 #if defined(__cplusplus) && !defined(__CUDACC_RTC__)
 /* host-side compiler (gg_compile.cpp) */
 struct ggp_aggmap {          /* how each Aggref reads the accumulator columns */
-	int32_t col;             /* accumulator column, -1 for count(*) */
+	int32_t col;             /* accumulator column, -1 for count(*); numeric sum / avg: the low half, col + 1 the high half */
+	int32_t scale;           /* numeric sum / avg: display scale of the summed expression */
 };
 int ggp_compile_scanagg(const gg_scan *scan, const gg_agg *agg, const gg_exprpool *pool,
                         ggp_program *prog, ggp_aggmap *aggmap, char *err, int errlen);

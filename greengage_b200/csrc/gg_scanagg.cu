@@ -751,6 +751,95 @@ static int scanagg_stream_host(gg_scanagg *p, const void *host_pages, uint64_t n
 }
 
 /* finalize_aggregate (nodeAgg.c:871-999) over the merged group records: O(groups) scalar work */
+/* ---- numeric results (gg_plan.h "numeric") ----
+ * The accumulated 128-bit integer (two int64 sums of the inputs' halves) is the exact sum at the argument's scale.
+ * numeric_sum returns it as is; numeric_avg is numeric_div(sum, N::numeric) (numeric.c:3173): the result scale comes from
+ * select_div_scale — NUMERIC_MIN_SIG_DIGITS (16) significant digits judged from the operands' base-10000 weights and first
+ * digits, at least the operands' display scales (numeric.c select_div_scale) — and div_var rounds the quotient half away from
+ * zero at that scale. */
+typedef __int128 gg_i128;
+typedef unsigned __int128 gg_u128;
+
+/* base-10000 weight and first digit of |v| / 10^scale, as a NumericVar would hold them (leading zero digits stripped;
+ * zero has no digits: weight 0, first digit 0) */
+static void nbase_weight_first(gg_u128 mag, int scale, int *weight, int *first)
+{
+	*weight = 0; *first = 0;
+	if (mag == 0) return;
+	gg_u128 p = 1;
+	for (int i = 0; i < scale; i++) p *= 10;
+	gg_u128 ip = mag / p, fp = mag % p;
+	if (ip > 0)
+	{
+		int w = 0;
+		while (ip >= 10000) { ip /= 10000; w++; }
+		*weight = w; *first = (int) ip;
+		return;
+	}
+	/* purely fractional: digit groups of four decimals behind the point */
+	int padded = (scale + 3) / 4 * 4;
+	for (int i = scale; i < padded; i++) fp *= 10;
+	int groups = padded / 4;
+	for (int gi = 0; gi < groups; gi++)
+	{
+		gg_u128 q = 1;
+		for (int k = 0; k < (groups - 1 - gi) * 4; k++) q *= 10;
+		const int d = (int) ((fp / q) % 10000);
+		if (d) { *weight = -(gi + 1); *first = d; return; }
+	}
+}
+
+static void numeric_store(gg_aggval &v, gg_i128 val, int dscale)
+{
+	const uint64_t lo = (uint64_t) (gg_u128) val, hi = (uint64_t) ((gg_u128) val >> 64);
+	v.i = (int64_t) lo;
+	memcpy(&v.f[0], &hi, 8);
+	v.f[1] = (double) dscale;
+}
+
+/* avg = round(sum / n) at select_div_scale's scale; false if the quotient does not fit 128 bits */
+static bool numeric_avg128(gg_i128 sum, int sscale, uint64_t n, gg_i128 *out, int *rscale)
+{
+	const bool neg = sum < 0;
+	const gg_u128 mag = neg ? (gg_u128) (-sum) : (gg_u128) sum;
+	int w1, f1, w2, f2;
+	nbase_weight_first(mag, sscale, &w1, &f1);
+	nbase_weight_first((gg_u128) n, 0, &w2, &f2);
+	int qweight = w1 - w2;
+	if (f1 <= f2) qweight--;
+	int rs = 16 - qweight * 4;                     /* NUMERIC_MIN_SIG_DIGITS - qweight * DEC_DIGITS */
+	if (rs < sscale) rs = sscale;
+	if (rs < 0) rs = 0;
+	if (rs > 1000) rs = 1000;
+	gg_u128 num = mag;
+	for (int i = sscale; i < rs; i++)
+	{
+		if (num > ((gg_u128) ~(gg_u128) 0) / 10) return false;
+		num *= 10;
+	}
+	gg_u128 q = num / n, r = num % n;
+	if (2 * r >= (gg_u128) n) q++;                 /* round_var: half away from zero */
+	if (q >> 127) return false;
+	*out = neg ? -(gg_i128) q : (gg_i128) q;
+	*rscale = rs;
+	return true;
+}
+
+/* finalisation of a numeric sum / avg from the two accumulated halves, callable without a device (tests hold it to the
+ * reference's numeric.o through tests/golden/numeric_kat.json): which = 0 sum, 1 avg.  Returns 0, or 1 when avg does not fit */
+extern "C" int gg_debug_numeric_final(int which, int64_t lo, int64_t hi, int scale, uint64_t n, gg_aggval *out)
+{
+	const gg_i128 sum = (gg_i128) hi * ((gg_i128) 1 << 32) + (gg_i128) lo;
+	memset(out, 0, sizeof *out);
+	if (n == 0) { out->isnull = 1; return 0; }
+	if (which == 0) { numeric_store(*out, sum, scale); return 0; }
+	gg_i128 a = 0;
+	int rs = 0;
+	if (!numeric_avg128(sum, scale, n, &a, &rs)) { out->isnull = 1; return 1; }
+	numeric_store(*out, a, rs);
+	return 0;
+}
+
 static void finalize_rows(const gg_agg *agg, const ggp_aggmap *aggmap, const ggp_program *prog, int final_stage,
                           const ggp_grec *recs, int n, gg_aggrow *out)
 {
@@ -798,6 +887,24 @@ static void finalize_rows(const gg_agg *agg, const ggp_aggmap *aggmap, const ggp
 					v.isnull = nn == 0;
 					v.f[0] = nn ? x.sum[col] : 0.0;
 					break;
+				case GG_AGG_SUM_NUMERIC:
+				case GG_AGG_AVG_NUMERIC:
+				{
+					int64_t lo, hi;
+					memcpy(&lo, &x.sum[col], 8); memcpy(&hi, &x.sum[col + 1], 8);
+					const gg_i128 sum = (gg_i128) hi * ((gg_i128) 1 << 32) + (gg_i128) lo;
+					v.isnull = nn == 0;              /* numeric_sum / numeric_avg over no input: NULL (numeric.c:3181,3213) */
+					if (nn == 0) break;
+					if (fn == GG_AGG_SUM_NUMERIC) numeric_store(v, sum, aggmap[i].scale);
+					else
+					{
+						gg_i128 a = 0;
+						int rs = 0;
+						if (!numeric_avg128(sum, aggmap[i].scale, nn, &a, &rs)) { v.isnull = 1; v.pad = 1; }     /* does not fit: flagged, see fetch */
+						else numeric_store(v, a, rs);
+					}
+					break;
+				}
 				case GG_AGG_AVG_FLOAT8:
 					if (partial)
 					{

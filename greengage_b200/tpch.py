@@ -47,6 +47,36 @@ def q1_plan(table=capi.TAB_LINEITEM_WIDE, stage=capi.AGGSTAGE_NORMAL, interval_d
     return scan, agg, p.pool
 
 
+def numeric_lineitem_desc():
+    """lineitem as the reference's regression suite declares it (input/rpt_tpch.source:16-35): the four measures are
+    numeric(15,2); the rest as in the float8 table"""
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
+    for a in (4, 5, 6, 7):
+        at = desc.attrs[a]
+        at.atttypid, at.attlen, at.attalign, at.attbyval, at.atttypmod = capi.NUMERICOID, -1, ord("i"), 0, ((15 << 16) | 2) + 4
+    return desc
+
+
+def q1_plan_numeric(desc=None, interval_days=90):
+    """The reference's Q1 over numeric columns (output/rpt_tpch.source:288-307): numeric_mul / numeric_sub / numeric_add,
+    sum / avg over numeric — exact arithmetic, results to the last digit of the golden answer."""
+    desc = desc or numeric_lineitem_desc()
+    c = LI_WIDE_COLS
+    N = capi.NUMERICOID
+    p = ExprPool()
+    qty, price, disc, tax = (p.var(c[k], N) for k in ("quantity", "extendedprice", "discount", "tax"))
+    flag, status, shipdate = p.var(c["returnflag"], BPCHAROID), p.var(c["linestatus"], BPCHAROID), p.var(c["shipdate"], DATEOID)
+    qual = p.func(capi.F_DATE_LE_TIMESTAMP, BOOLOID, shipdate, p.const(TIMESTAMPOID, (D_1998_12_01 - interval_days) * USECS_PER_DAY))
+    one = p.const(N, "1")
+    disc_price = p.func(capi.F_NUMERIC_MUL, N, price, p.func(capi.F_NUMERIC_SUB, N, one, disc))
+    disc_price2 = p.func(capi.F_NUMERIC_MUL, N, price, p.func(capi.F_NUMERIC_SUB, N, one, disc))
+    charge = p.func(capi.F_NUMERIC_MUL, N, disc_price2, p.func(capi.F_NUMERIC_ADD, N, one, tax))
+    S, A = capi.AGG_SUM_NUMERIC, capi.AGG_AVG_NUMERIC
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [flag, status], [(S, qty), (S, price), (S, disc_price), (S, charge), (A, qty), (A, price), (A, disc),
+                                                                (AGG_COUNT_STAR, -1)])
+    return capi.make_scan(desc, qual), agg, p.pool
+
+
 def q1_final_agg(agg):
     """The FINAL-stage Agg above the Redistribute Motion: same aggregates, grpCol carries key type OIDs."""
     fin = capi.gg_agg()

@@ -56,6 +56,8 @@ extern "C" {
 #define GG_VARCHAROID    1043
 #define GG_DATEOID       1082
 #define GG_TIMESTAMPOID  1114
+#define GG_NUMERICOID    1700     /* numeric(p,s) columns with a declared scale: evaluated as scaled 64-bit integers (exact), see
+                                   * "numeric" below */
 
 /* ---- function OIDs (pg_proc.h; values checked against the reference's generated fmgroids.h) ---- */
 #define GG_F_INT4EQ 65
@@ -91,6 +93,15 @@ extern "C" {
 #define GG_F_DATE_GT 1089
 #define GG_F_DATE_GE 1090
 #define GG_F_DATE_NE 1091
+#define GG_F_NUMERIC_EQ 1718
+#define GG_F_NUMERIC_NE 1719
+#define GG_F_NUMERIC_GT 1720
+#define GG_F_NUMERIC_GE 1721
+#define GG_F_NUMERIC_LT 1722
+#define GG_F_NUMERIC_LE 1723
+#define GG_F_NUMERIC_ADD 1724
+#define GG_F_NUMERIC_SUB 1725
+#define GG_F_NUMERIC_MUL 1726
 #define GG_F_DATE_LT_TIMESTAMP 2338
 #define GG_F_DATE_LE_TIMESTAMP 2339
 #define GG_F_DATE_EQ_TIMESTAMP 2340
@@ -99,6 +110,8 @@ extern "C" {
 #define GG_F_DATE_NE_TIMESTAMP 2343
 
 /* aggregate OIDs (pg_aggregate.h:156-220) */
+#define GG_AGG_AVG_NUMERIC  2103   /* numeric_avg_accum / numeric_avg: sum / N as numeric_div computes it (numeric.c:3173) */
+#define GG_AGG_SUM_NUMERIC  2114   /* numeric_avg_accum / numeric_sum (numeric.c:3205) */
 #define GG_AGG_AVG_FLOAT8   2105   /* float8_accum / float8_avg / float8_combine, state float8[3] "{0,0,0}" */
 #define GG_AGG_SUM_INT4     2108   /* int4_sum / - / int8pl, state int8 init NULL */
 #define GG_AGG_SUM_FLOAT8   2111   /* float8pl / - / float8pl, state float8 init NULL (strict: first value) */
@@ -112,6 +125,19 @@ extern "C" {
 #define GG_AGG_MIN_DATE     2138
 #define GG_AGG_COUNT_ANY    2147   /* int8inc_any / - / int8pl, init 0 */
 #define GG_AGG_COUNT_STAR   2803   /* int8inc / - / int8pl, init 0 */
+
+/* ---- numeric ----
+ * A numeric(p,s) column (atttypmod = ((p << 16) | s) + 4, utils/adt/numeric.c:650 numeric_typmod) is decoded from its on-disk
+ * base-10000 digits (numeric.c:95-190) into a 64-bit integer scaled by 10^s; numeric_add / _sub / _mul and the comparisons run
+ * on such integers with the result scales numeric.c gives them (add/sub: the larger display scale, :1659,1698; mul: their sum,
+ * :1735) — exact, as the reference's arithmetic is.  sum() accumulates in 128 bits; avg() is numeric_div(sum, N) with
+ * select_div_scale's result scale and div_var's rounding (numeric.c:3173, :6480 ff).  A value, product or sum outside 64 / 128
+ * bits, a NaN, or a stored value with more fractional digits than its column's scale raises GG_ERR_UNSUPPORTED at fetch: the
+ * caller runs the relation on the CPU path.
+ * Constants: gg_expr.constvalue = the unscaled integer, constlen = its display scale.
+ * Results (gg_aggval of sum / avg over numeric): the value is a 128-bit integer scaled by 10^dscale —
+ * i = its low 64 bits, f[0] = the bit pattern of its high 64 bits, f[1] = dscale. */
+#define GG_NUMERIC_TYPMOD(p, s) ((((int32_t) (p)) << 16 | (int32_t) (s)) + 4)
 
 /* ---- limits of the accelerated subset ---- */
 #define GG_MAX_ATTS        32

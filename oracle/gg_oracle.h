@@ -68,7 +68,8 @@ const uint8_t *or_varlena_payload(const uint8_t *datum, int *len);
 int  or_tuple_visible(const uint8_t *tuple);
 
 /* ---------------- expression evaluation (execQual.c) ---------------- */
-typedef struct or_datum { int64_t v; int32_t len; int32_t isnull; const uint8_t *ptr; } or_datum;
+/* numeric values: the 128-bit integer (hi:v), scaled by 10^dscale (or_numeric.c) */
+typedef struct or_datum { int64_t v; int32_t len; int32_t isnull; const uint8_t *ptr; int64_t hi; int32_t dscale; int32_t pad; } or_datum;
 typedef struct or_row {       /* a deformed tuple: one side of a (possibly joined) row */
 	const gg_tupdesc *desc;
 	const uint8_t *tuple;
@@ -78,6 +79,13 @@ typedef struct or_row {       /* a deformed tuple: one side of a (possibly joine
 } or_row;
 /* returns 0 ok, <0 error code (float overflow etc.: OR_ERR_*) */
 int or_eval(const gg_exprpool *pool, int root, or_row *outer, or_row *inner, or_datum *res);
+
+/* numeric (or_numeric.c) */
+int or_numeric_decode(const uint8_t *payload, int len, or_datum *res);
+void or_numeric_const(int64_t unscaled, int dscale, or_datum *res);
+int or_numeric_func(int funcid, const or_datum *a, const or_datum *b, or_datum *res);
+int or_numeric_accum(int64_t *sum_lo, int64_t *sum_hi, int *sum_dscale, int64_t *n, const or_datum *x);
+int or_numeric_avg(int64_t sum_lo, int64_t sum_hi, int sum_dscale, int64_t n, int64_t *out_lo, int64_t *out_hi, int *rscale);
 
 #define OR_ERR_FLOAT_OVERFLOW   (-2)   /* "value out of range: overflow"  float_utils.h:28 */
 #define OR_ERR_FLOAT_UNDERFLOW  (-3)

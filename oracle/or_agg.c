@@ -36,6 +36,9 @@ typedef struct or_aggstate {			/* AggStatePerGroupData, nodeAgg.h:192 (+float8[3
 	int64_t i;
 	int     transValueIsNull;
 	int     noTransValue;
+	/* numeric_avg_accum's state (numeric.c:3057): N and the exact running sum, here 128 bits at display scale nscale */
+	int64_t nlo, nhi, nN;
+	int     nscale;
 } or_aggstate;
 
 typedef struct or_entry {				/* HashAggEntry, execHHashagg.h:41 */
@@ -168,6 +171,13 @@ advance_trans(int aggfnoid, or_aggstate *st, const or_datum *arg)
 			st->f[2] = sumX2;
 			return 0;
 		}
+		case GG_AGG_SUM_NUMERIC:
+		case GG_AGG_AVG_NUMERIC:		/* numeric_avg_accum: NULL inputs are skipped (numeric.c:3063) */
+			if (arg->isnull)
+				return 0;
+			st->transValueIsNull = 0;
+			st->noTransValue = 0;
+			return or_numeric_accum(&st->nlo, &st->nhi, &st->nscale, &st->nN, arg);
 		case GG_AGG_SUM_INT4:			/* int4_sum (numeric.c): not strict, NULL-aware, no overflow check */
 			if (arg->isnull)
 				return 0;
@@ -338,6 +348,27 @@ finalize(int aggfnoid, int stage, const or_aggstate *st, gg_aggval *out)
 	}
 	switch (aggfnoid)
 	{
+		case GG_AGG_SUM_NUMERIC:		/* numeric_sum (numeric.c:3205): NULL without input */
+		case GG_AGG_AVG_NUMERIC:		/* numeric_avg (numeric.c:3173): numeric_div(sum, N) */
+		{
+			int64_t lo = st->nlo, hi = st->nhi;
+			int sc = st->nscale;
+
+			if (st->nN == 0)
+			{
+				out->isnull = 1;
+				return;
+			}
+			if (aggfnoid == GG_AGG_AVG_NUMERIC && or_numeric_avg(st->nlo, st->nhi, st->nscale, st->nN, &lo, &hi, &sc) != 0)
+			{
+				out->isnull = 1; out->pad = 1;		/* does not fit 128 bits */
+				return;
+			}
+			out->i = lo;
+			memcpy(&out->f[0], &hi, 8);
+			out->f[1] = (double) sc;
+			return;
+		}
 		case GG_AGG_AVG_FLOAT8:			/* float8_avg, float.c:1982 */
 			if (st->f[0] == 0.0)
 				out->isnull = 1;

@@ -66,6 +66,12 @@ row_getattr(or_row *r, int attno, or_datum *res)
 	}
 }
 
+static int
+is_numeric_func(int funcid)
+{
+	return funcid >= GG_F_NUMERIC_EQ && funcid <= GG_F_NUMERIC_MUL;
+}
+
 /* float.c:964 */
 static int
 float8_cmp_internal(double a, double b)
@@ -231,12 +237,22 @@ or_eval(const gg_exprpool *pool, int root, or_row *outer, or_row *inner, or_datu
 	{
 		case GG_E_VAR:
 			row_getattr(e->varno == 1 ? inner : outer, e->varattno, res);
+			if (e->rettype == GG_NUMERICOID && !res->isnull)
+			{
+				/* the on-disk digits become a value here (numeric.c:95-190) */
+				const uint8_t *p = res->ptr;
+				int len = res->len;
+
+				return or_numeric_decode(p, len, res);
+			}
 			return 0;
 		case GG_E_CONST:
 			res->isnull = e->constisnull;
 			res->v = e->constvalue;
 			res->len = e->constlen;
 			res->ptr = NULL;
+			if (e->rettype == GG_NUMERICOID && !e->constisnull)
+				or_numeric_const(e->constvalue, e->constlen, res);
 			return 0;
 		case GG_E_FUNC:
 			/* ExecMakeFunctionResultNoSets: a strict function with any NULL argument yields NULL
@@ -253,6 +269,8 @@ or_eval(const gg_exprpool *pool, int root, or_row *outer, or_row *inner, or_datu
 				res->ptr = NULL;
 				return 0;
 			}
+			if (is_numeric_func(e->funcid))
+				return or_numeric_func(e->funcid, &a, &b, res);
 			return eval_func(e->funcid, &a, &b, res);
 		case GG_E_AND:
 			/* ExecEvalAnd (execQual.c:3455): FALSE wins, else NULL if any NULL, else TRUE */

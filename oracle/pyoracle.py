@@ -18,7 +18,8 @@ _ref = None
 
 
 class or_datum(C.Structure):
-    _fields_ = [("v", C.c_int64), ("len", C.c_int32), ("isnull", C.c_int32), ("ptr", C.c_void_p)]
+    _fields_ = [("v", C.c_int64), ("len", C.c_int32), ("isnull", C.c_int32), ("ptr", C.c_void_p),
+                ("hi", C.c_int64), ("dscale", C.c_int32), ("pad", C.c_int32)]
 
 
 def build():
@@ -154,6 +155,15 @@ def eval_expr(pool, root):
     d = or_datum()
     rc = lib().or_eval(C.byref(pool), root, None, None, C.byref(d))
     return rc, d.v, d.isnull
+
+
+def eval_numeric(pool, root):
+    """Evaluate a row-independent numeric expression: (rc, text or None when NULL)"""
+    d = or_datum()
+    rc = lib().or_eval(C.byref(pool), root, None, None, C.byref(d))
+    if rc or d.isnull:
+        return rc, None
+    return rc, capi.numeric_text((d.hi << 64) | (d.v & 0xFFFFFFFFFFFFFFFF), d.dscale)
 
 
 class OracleError(RuntimeError):

@@ -60,3 +60,17 @@ void ref_unreachable(const char *name)
 /* timestamp.c is not among the leaf objects (it needs the int128 configure probe); date.o calls only this
  * comparison, which with integer datetimes is the plain ordering of two int64 (timestamp.c:2536-2539) */
 int timestamp_cmp_internal(long dt1, long dt2) { return (dt1 < dt2) ? -1 : ((dt1 > dt2) ? 1 : 0); }
+
+/* numeric_in asks whether its input spells "NaN" */
+int pg_strncasecmp(const char *a, const char *b, size_t n)
+{
+	while (n-- > 0)
+	{
+		unsigned char x = (unsigned char) *a++, y = (unsigned char) *b++;
+		if (x >= 'A' && x <= 'Z') x += 'a' - 'A';
+		if (y >= 'A' && y <= 'Z') y += 'a' - 'A';
+		if (x != y) return (int) x - (int) y;
+		if (x == 0) break;
+	}
+	return 0;
+}

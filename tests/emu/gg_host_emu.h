@@ -23,6 +23,8 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long) (((unsigned __int128) a * b) >> 64); }
+static inline long long __mul64hi(long long a, long long b) { return (long long) (((__int128) a * b) >> 64); }
 
 #define GG_EMU_SMEM_BYTES (256 * 1024)
 extern uint8_t gg_emu_smem[GG_EMU_SMEM_BYTES];

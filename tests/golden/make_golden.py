@@ -21,6 +21,8 @@
                     NULLs, short and long varlenas, > 32 attributes and tuples beyond the 2-byte-offset limit, the bindings
                     themselves, what memtuple_deform reads back, and the same rows as tuple chunks out of the reference's
                     tupser.o / tupchunklist.o (SerializeTuple, both the MemTuple and the heap-tuple form, several chunk sizes)
+  numeric_kat.json  the reference's numeric.o: text -> on-disk digits (numeric_in), numeric_add / _sub / _mul results with their
+                    display scales, numeric_cmp, and sum / avg (a fold of numeric_add; numeric_div(sum, N) as numeric_avg does)
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
 import ctypes as C
@@ -241,6 +243,41 @@ def memtuple_kat():
             cases.append(rec)
     json.dump({"descs": meta, "cases": cases}, open(os.path.join(HERE, "memtuple_kat.json"), "w"))
     print("memtuple_kat.json", len(cases))
+
+
+def numeric_kat():
+    """numeric goldens out of the reference's numeric.o (oracle/ref_build/refwrap_numeric.c)"""
+    rng = random.Random(20260924)
+    out = {"values": [], "binops": [], "cmp": [], "sumavg": []}
+    buf, txt = (C.c_uint8 * 256)(), C.create_string_buffer(512)
+
+    def rand_text(maxdigits=15, scales=(0, 1, 2, 2, 2, 3, 4, 6)):
+        sc = rng.choice(scales)
+        mag = rng.choice([0, 1, 7, 99, 100, 9999, 10000, rng.getrandbits(rng.randint(1, int(maxdigits * 3.3)))])
+        return capi.numeric_text(mag * rng.choice([1, 1, -1]), sc)
+
+    for t in ["0", "0.00", "1", "-1", "0.01", "-0.05", "12345.60", "9999999999999.99", "10000", "10000.0001", "0.0001", "123456789012345678"] + [rand_text(18, (0, 1, 2, 4, 9, 15, 20, 70)) for _ in range(300)]:
+        n = R.ref_numeric_in(t.encode(), -1, buf, 256)
+        out["values"].append([t, bytes(buf[4:n]).hex()])
+    for _ in range(600):
+        a, b, op = rand_text(), rand_text(), rng.choice("+-*")
+        n = R.ref_numeric_binop(ord(op), a.encode(), b.encode(), txt, 512)
+        assert n > 0
+        out["binops"].append([op, a, b, txt.value.decode()])
+        out["cmp"].append([a, b, R.ref_numeric_cmp(a.encode(), b.encode())])
+    for _ in range(60):
+        sc = rng.choice([0, 2, 2, 4, 6])
+        vals = [capi.numeric_text(rng.randint(-10 ** rng.randint(1, 12), 10 ** rng.randint(1, 12)) if rng.random() < 0.9 else 0, sc) for _ in range(rng.choice([1, 2, 3, 10, 200]))]
+        if rng.random() < 0.2:
+            vals = [capi.numeric_text(rng.randint(0, 99), sc) for _ in vals]           # small sums: fractional averages
+        acc = "0"
+        for v in vals:
+            R.ref_numeric_binop(ord("+"), acc.encode(), v.encode(), txt, 512)
+            acc = txt.value.decode()
+        R.ref_numeric_binop(ord("/"), acc.encode(), str(len(vals)).encode(), txt, 512)
+        out["sumavg"].append({"values": vals, "sum": acc, "avg": txt.value.decode()})
+    json.dump(out, open(os.path.join(HERE, "numeric_kat.json"), "w"))
+    print("numeric_kat.json", {k: len(v) for k, v in out.items()})
 
 
 def float_kat():
@@ -583,3 +620,4 @@ if __name__ == "__main__":
     onek_fixture()
     aocs_kat()
     memtuple_kat()
+    numeric_kat()

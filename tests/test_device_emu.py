@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from _util import make_desc
-from greengage_b200 import capi
+from greengage_b200 import capi, tpch
 from greengage_b200.capi import ExprPool
 from oracle import pyoracle as po
 import test_gpu_random_plans as rp
@@ -446,3 +446,112 @@ def test_avg_raises_what_float8_accum_raises_for_a_square_that_overflows(emu):
             oracle_raised = True
         groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, p.pool, pages)
         assert oracle_raised == raises and bool(err & 0x01) == raises, (fn, oracle_raised, hex(err))
+
+
+def test_numeric_q1_through_the_device_interpreter_is_the_references_golden_answer(emu):
+    """numeric(15,2) columns decoded from their on-disk digits and evaluated as scaled 64-bit integers by the product's
+    compiler + interpreter (host build), the two halves of every sum folded the way the kernels fold them, finalised by the
+    product's host code (gg_debug_numeric_final): the reference's golden Q1 over its numeric heap_lineitem, to the last digit —
+    and the oracle's answer over the same pages."""
+    from test_oracle_numeric import numeric_lineitem_pages
+    from _util import golden
+    desc, pages, n = numeric_lineitem_pages()
+    exp = golden("q1_expected.json")
+    scan, agg, pool = tpch.q1_plan_numeric(desc, interval_days=exp["interval_days"])
+    groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, pool, pages)
+    assert err == 0 and sc == n
+    want, wsc, wps = po.seqscan_agg(scan, agg, pool, pages)
+    assert (sc, ps) == (wsc, wps)
+    D = capi.dev_lib()
+    D.gg_debug_numeric_final.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.POINTER(capi.gg_aggval)]
+    scales = [2, 2, 4, 6, 2, 2, 2]
+    by = {(int(g.key[0]), int(g.key[1])): g for g in groups}
+    names = ["sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "avg_qty", "avg_price", "avg_disc"]
+    for w, o in zip(exp["rows"], sorted(want, key=lambda r: (r.key[0], r.key[1]))):
+        g = by[(capi.pack_str(w["returnflag"])[0], capi.pack_str(w["linestatus"])[0])]
+        assert g.count == w["count_order"]
+        for i, name in enumerate(names):
+            col = aggcol[i]
+            lo = int(np.float64(g.sum[col]).view(np.int64))
+            hi = int(np.float64(g.sum[col + 1]).view(np.int64))
+            v = capi.gg_aggval()
+            assert D.gg_debug_numeric_final(1 if i >= 4 else 0, lo, hi, scales[i], g.n[col], C.byref(v)) == 0
+            assert capi.numeric_of_aggval(v) == w[name], (name, capi.numeric_of_aggval(v), w[name])
+            assert capi.numeric_of_aggval(v) == capi.numeric_of_aggval(o.agg[i])
+
+
+def test_numeric_finalisation_equals_the_references_sum_and_avg():
+    """the product's host finalisation of (low half, high half, N) against numeric_kat.json's sums and averages"""
+    import json
+    kat = json.load(open(os.path.join(HERE, "golden", "numeric_kat.json")))
+    D = capi.dev_lib()
+    D.gg_debug_numeric_final.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.POINTER(capi.gg_aggval)]
+    for case in kat["sumavg"]:
+        parsed = [capi.numeric_parse(t) for t in case["values"]]
+        sc = max(s for _, s in parsed)
+        lo = sum((v * 10 ** (sc - s)) & 0xFFFFFFFF for v, s in parsed)
+        hi = sum((v * 10 ** (sc - s)) >> 32 for v, s in parsed)
+        for which, name in ((0, "sum"), (1, "avg")):
+            v = capi.gg_aggval()
+            assert D.gg_debug_numeric_final(which, lo, hi, sc, len(parsed), C.byref(v)) == 0
+            assert capi.numeric_of_aggval(v) == case[name], (name, capi.numeric_of_aggval(v), case[name])
+
+
+def test_random_numeric_expressions_mean_what_the_oracle_computes(emu):
+    """numeric_add / _sub / _mul trees, comparisons in the qual, NULLs, columns of different scales: sums (both halves) and
+    counts of the device interpreter equal the oracle's exact sums"""
+    rng = np.random.default_rng(99)
+    NUM = capi.NUMERICOID
+    desc = capi.gg_tupdesc()
+    spec = [(capi.INT4OID, 4, "i", 1, -1, 1), (NUM, -1, "i", 0, ((15 << 16) | 2) + 4, 0), (NUM, -1, "i", 0, ((12 << 16) | 0) + 4, 1),
+            (NUM, -1, "i", 0, ((10 << 16) | 4) + 4, 0)]
+    desc.natts = len(spec)
+    for i, (t, l, al, bv, tm, nn) in enumerate(spec):
+        a = desc.attrs[i]
+        a.atttypid, a.attlen, a.attalign, a.attbyval, a.atttypmod, a.attnotnull = t, l, ord(al), bv, tm, nn
+    rows, nulls = [], []
+    for i in range(3000):
+        rows.append([int(rng.integers(0, 4)), capi.numeric_payload(int(rng.integers(-10**7, 10**7)), 2), capi.numeric_payload(int(rng.integers(-500, 500)), 0),
+                     capi.numeric_payload(int(rng.integers(-10**6, 10**6)), 4)])
+        nulls.append([False, rng.random() < 0.1, False, rng.random() < 0.1])
+    pages = po.build_pages(desc, rows, nulls)
+    scale_of = {2: 2, 3: 0, 4: 4}
+
+    def expr(p, depth):
+        if depth == 0 or rng.random() < 0.3:
+            if rng.random() < 0.25:
+                sc = int(rng.integers(0, 3))
+                return p.const(NUM, capi.numeric_text(int(rng.integers(-99, 99)), sc)), sc
+            a = int(rng.integers(2, 5))
+            return p.var(a, NUM), scale_of[a]
+        (l, ls), (r, rs) = expr(p, depth - 1), expr(p, depth - 1)
+        op = rng.choice(["+", "-", "*"])
+        if op == "*" and ls + rs > 8:
+            op = "+"
+        f = {"+": capi.F_NUMERIC_ADD, "-": capi.F_NUMERIC_SUB, "*": capi.F_NUMERIC_MUL}[op]
+        return p.func(f, NUM, l, r), (ls + rs if op == "*" else max(ls, rs))
+
+    ran = 0
+    for seed in range(40):
+        p = ExprPool()
+        args = [expr(p, 2) for _ in range(int(rng.integers(1, 4)))]
+        (ql, _), (qr, _) = expr(p, 1), expr(p, 1)
+        qual = p.func(int(rng.choice([capi.F_NUMERIC_LT, capi.F_NUMERIC_GE, capi.F_NUMERIC_NE])), capi.BOOLOID, ql, qr) if rng.random() < 0.7 else -1
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(1, capi.INT4OID)], [(capi.AGG_COUNT_STAR, -1)] + [(capi.AGG_SUM_NUMERIC, a) for a, _ in args])
+        scan = capi.make_scan(desc, qual)
+        want, wsc, wps = po.seqscan_agg(scan, agg, p.pool, pages)
+        groups, aggcol, sc, ps, err = run_emu(emu, scan, agg, p.pool, pages)
+        assert err == 0 and (sc, ps) == (wsc, wps), (seed, hex(err))
+        by = {int(np.uint64(g.key[0]).astype(np.int64)): g for g in groups}
+        for r in want:
+            g = by[r.key[0]]
+            assert g.count == r.agg[0].i
+            for i, (a, asc) in enumerate(args):
+                col = aggcol[1 + i]
+                lo, hi = int(np.float64(g.sum[col]).view(np.int64)), int(np.float64(g.sum[col + 1]).view(np.int64))
+                if r.agg[1 + i].isnull:
+                    assert g.n[col] == 0
+                else:
+                    assert capi.numeric_text(hi * 2 ** 32 + lo, asc) == capi.numeric_of_aggval(r.agg[1 + i]), (seed, i)
+        ran += 1
+    assert ran == 40

@@ -306,3 +306,59 @@ def test_partial_stage_without_sumsq_gives_the_references_q1(eng):
         assert all(r.agg[4].f[2] == 0.0 for r in rows)        # no sumX2 travels
         parts.extend(rows)
     _check_against_golden(agg_final(eng, tpch.q1_final_agg(part), parts))
+
+
+def test_q1_over_numeric_columns_is_the_references_golden_answer_to_the_last_digit(eng):
+    """The reference's regression lineitem with its measures as numeric(15,2) (input/rpt_tpch.source:16-35): on-disk base-10000
+    digits decoded on the device, numeric_mul / _sub / _add as exact scaled-integer arithmetic, 128-bit sums, avg with
+    numeric_div's scale and rounding — every digit of output/rpt_tpch.source:309-315, not float8 within 1e-6."""
+    from greengage_b200 import tpch
+    from greengage_b200.engine import Relation, ScanAgg
+    from oracle import pyoracle as po
+    from test_oracle_numeric import check_q1_numeric_golden, numeric_lineitem_pages
+    desc, pages, n = numeric_lineitem_pages()
+    scan, agg, pool = tpch.q1_plan_numeric(desc, interval_days=golden("q1_expected.json")["interval_days"])
+    rel = Relation(eng, host_pages=pages)
+    sa = ScanAgg(eng, scan, agg, pool)
+    try:
+        sa.run(rel)
+        got, sc, ps = sa.fetch()
+        assert sc == n
+        check_q1_numeric_golden(got)
+        want, wsc, wps = po.seqscan_agg(scan, agg, pool, pages)
+        assert (sc, ps) == (wsc, wps)
+        by = {(r.key[0], r.key[1]): r for r in want}
+        for r in got:
+            w = by[(r.key[0], r.key[1])]
+            assert [capi.numeric_of_aggval(r.agg[i]) for i in range(7)] == [capi.numeric_of_aggval(w.agg[i]) for i in range(7)]
+    finally:
+        sa.free()
+        rel.free()
+
+
+def test_numeric_values_outside_the_device_range_are_refused_not_miscomputed(eng):
+    """a product beyond 64 bits at its scale raises GG_ERR_UNSUPPORTED at fetch (the relation then runs on the CPU path)"""
+    from greengage_b200.capi import ExprPool, GGError
+    from greengage_b200.engine import Relation, ScanAgg
+    from oracle import pyoracle as po
+    NUM = capi.NUMERICOID
+    desc = capi.gg_tupdesc()
+    desc.natts = 2
+    for i, (t, l, al, bv, tm) in enumerate([(capi.INT4OID, 4, "i", 1, -1), (NUM, -1, "i", 0, ((18 << 16) | 2) + 4)]):
+        a = desc.attrs[i]
+        a.atttypid, a.attlen, a.attalign, a.attbyval, a.atttypmod, a.attnotnull = t, l, ord(al), bv, tm, 1
+    rows = [[i, capi.numeric_payload(10 ** 15 + i, 2)] for i in range(500)]
+    pages = po.build_pages(desc, rows)
+    p = ExprPool()
+    x = p.var(2, NUM)
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [], [(capi.AGG_SUM_NUMERIC, p.func(capi.F_NUMERIC_MUL, NUM, x, x))])
+    rel = Relation(eng, host_pages=pages)
+    sa = ScanAgg(eng, capi.make_scan(desc, -1), agg, p.pool)
+    try:
+        sa.run(rel)
+        with pytest.raises(GGError) as ei:
+            sa.fetch()
+        assert ei.value.code == -6
+    finally:
+        sa.free()
+        rel.free()
