@@ -855,10 +855,11 @@ static void compile_agg_part(Ctx &c, const gg_agg *agg, ggp_aggmap *aggmap)
 	emit(c, GGP_END);
 	c.npersist = 0;
 
-	/* private-accumulator kernel: NOT NULL float8 sums only */
+	/* private-accumulator kernel: NOT NULL float8 sums and int64 sums (int4_sum over a NOT NULL argument, the halves of a
+	 * numeric sum): both are plain adds into a per-thread accumulator */
 	prog->priv_ok = !prog->nullable;
 	for (int j = 0; j < prog->nacc; j++)
-		if (prog->acckind[j] != GGP_ACC_F8SUM) prog->priv_ok = 0;
+		if (prog->acckind[j] != GGP_ACC_F8SUM && prog->acckind[j] != GGP_ACC_I8SUM) prog->priv_ok = 0;
 }
 
 

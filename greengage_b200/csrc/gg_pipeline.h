@@ -47,6 +47,7 @@ struct gg_scanagg {
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
 	int regslots = -1;              /* private-accumulator variant: trailing value slots kept in registers (-1: not decided) */
 	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
+	int items_per_page = 0;         /* line pointers of the sampled page */
 	int team = 0;                   /* consumer warps per team (ScanAggParams.team); 0: chunks dealt across all warps */
 	bool np_forced = false;         /* launch configuration came from GGB200_NP_CONFIG */
 	bool is_join = false;           /* probe side of a gg_joinagg: prog = the probe program, jt = the built table */

@@ -337,7 +337,28 @@ static int scanagg_configure(gg_scanagg *p)
 			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages[,team]" for experiments */
 			int a, b, c = 0;
 			p->team = 0;
+			/* Teams (gg_scanagg_kernel.cuh): sparse pages — every chunk of a page gets its own warp, the teams work on different
+			 * pages of the ring.  The team must cover the fullest page (a warp with two chunks holds its whole team back): the
+			 * sampled page's line pointers + 8 %.  Measured on 10^8-row lineitem-wide (190 +- 6 rows per page, profiles/
+			 * r2c_sweep_teams_wide.jsonl): 3 teams of 7 on a 5-page ring 2.96 ms (0.88 of the measured copy bandwidth) against
+			 * 3.67 ms for 20 warps dealt across pages; teams of 6 (pages with 193+ rows cost a warp two chunks) 4.25 ms. */
+			if (p->chunks_per_page >= 2 && p->chunks_per_page <= 10 && p->items_per_page > 0 && !p->prog.outer.rowwords && !p->is_join)
+			{
+				const int ts = (p->items_per_page + p->items_per_page / 12 + 31) / 32;
+				int nteams = ts > 0 ? 21 / ts : 0;
+				if (nteams > 5) nteams = 5;
+				if (nteams >= 1 && ts <= 10)
+				{
+					const int want = ts * nteams;
+					int st = 5;
+					while (st > nteams && fit(st, want) < want) st--;
+					if (st >= nteams && fit(st, want) >= want) { ncons = want; p->nstage = st; p->team = ts; }
+				}
+			}
 			if (cfg && sscanf(cfg, "%d,%d,%d", &a, &b, &c) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && c >= 0 && c <= a) { ncons = a; p->nstage = b; p->team = c; }
+			/* a team waits for ITS page's phase of a ring slot; an mbarrier tells the current phase from the previous one only,
+			 * so no two teams may be queued on one slot: at most as many teams as stages */
+			if (p->team > 0 && ncons / p->team > p->nstage) ncons = p->team * p->nstage;
 		}
 		p->threads = (ncons + 1) * 32;
 		const int NT = ncons * 32;
@@ -473,6 +494,10 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	prm.nrows = nrows;
 	prm.fill_inner = fill_inner ? 1 : 0;
 	prm.team = p->team;
+	{
+		const char *kc = getenv("GGB200_KEYCACHE");
+		prm.nokeycache = kc && atoi(kc) == 0;
+	}
 	prm.aocs = aocs_tile_rows > 0 ? (const gg_aocs_devcol *) dev_pages : nullptr;
 	prm.aocs_tile_rows = aocs_tile_rows;
 	prm.ha = p->ha;
@@ -546,6 +571,7 @@ static int scanagg_adapt_to_pages(gg_scanagg *p, const uint8_t *dev_page, const 
 	const uint32_t pd_lower = hdr[3] & 0xFFFF;
 	int items = pd_lower >= GG_PAGE_HEADER_SIZE && pd_lower <= GG_BLCKSZ ? (int) ((pd_lower - GG_PAGE_HEADER_SIZE) >> 2) : 0;
 	p->chunks_per_page = items > 0 ? (items + 31) / 32 : 1;
+	p->items_per_page = items;
 	p->regslots = -1;                          /* decided again for this page density */
 	const int threads0 = p->threads, stages0 = p->nstage;
 	int rc = scanagg_configure(p);

@@ -168,6 +168,7 @@ struct ScanAggParams {
 	 * in shared memory and the row program runs over that: no attribute walk, no line pointers, only projected bytes read. */
 	const gg_aocs_devcol *aocs;
 	int32_t aocs_tile_rows;
+	int nokeycache;                       /* experiments: 1 = every row looks its group up in the block table (no register cache) */
 	int team;                             /* > 0: consumer warps work in teams of this many warps, one page per team at a time (a
 	                                       * warp only visits its team's pages); 0: every warp visits every page and the chunks
 	                                       * are dealt round-robin across pages */
@@ -294,6 +295,8 @@ struct RowSink {
 	 * by comparing against registers, and the shared-memory table (and its lock) is only visited for a key no lane of the warp
 	 * has cached yet.  Entries mirror table slots 0 .. cn-1 exactly (slot = group id); a slot with a NULL key ends the cache. */
 	int cn;
+	bool usecache;
+	uint32_t intmask;            /* MODE_PRIV: bit j = value slot j is an int64 sum (int4_sum): added as integers, bit for bit */
 	uint64_t c00, c01, c10, c11, c20, c21, c30, c31;
 	__device__ __forceinline__ void cache_refresh()
 	{
@@ -309,7 +312,7 @@ struct RowSink {
 	{
 		if (JOIN && suppress) live = false;
 		if (nkeys == 0) gid = live ? 0 : -1;
-		else if (nkeys <= 2)
+		else if (nkeys <= 2 && usecache)
 		{
 			int g = -1;
 			if (knull == 0)
@@ -353,7 +356,8 @@ struct RowSink {
 			else if (gid >= 0)
 			{
 				uint32_t a = acc_thread + (uint32_t) gid * gstride + (uint32_t) slot * sstride;
-				stsf64(a, __dadd_rn(ldsf64(a), v));
+				if ((intmask >> slot) & 1) sts64(a, lds64(a) + (uint64_t) __double_as_longlong(v));
+				else stsf64(a, __dadd_rn(ldsf64(a), v));
 			}
 		}
 		else
@@ -661,6 +665,12 @@ struct DynPlan {
 	__device__ static __forceinline__ int ncols(const ggp_program &P) { return P.outer.ncols; }
 	__device__ static __forceinline__ int rowwords(const ggp_program &P) { return P.outer.rowwords; }
 	__device__ static __forceinline__ int regslots(const ggp_program &) { return 0; }       /* interpreter: dynamic slot numbers */
+	__device__ static __forceinline__ uint32_t intmask(const ggp_program &P)
+	{
+		uint32_t m = 0;
+		for (int j = 0; j < P.nacc; j++) if (P.acckind[j] == GGP_ACC_I8SUM) m |= 1u << j;
+		return m;
+	}
 	__device__ static __forceinline__ uint32_t keytypes(const ggp_program &P)
 	{
 		return (uint32_t) P.keytype[0] | ((uint32_t) P.keytype[1] << 2) | ((uint32_t) P.keytype[2] << 4) | ((uint32_t) P.keytype[3] << 6);
@@ -827,6 +837,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			sink.rq.zero();
 			sink.cstride = (uint32_t) NT * 4;
 			sink.cn = 0; sink.c00 = sink.c01 = sink.c10 = sink.c11 = sink.c20 = sink.c21 = sink.c30 = sink.c31 = 0;
+			sink.usecache = prm.nokeycache == 0;
+			sink.intmask = MODE == MODE_PRIV ? PL::intmask(P) : 0;
 			sink.sv = sv;
 			sink.jq = false; sink.nullext = false; sink.suppress = false;
 		}
@@ -1189,6 +1201,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		for (int e = warp; e < G * V; e += (int) (blockDim.x >> 5))
 		{
 			const int g = e / V, sl = e % V;
+			const bool isint = ((PL::intmask(P) >> sl) & 1) != 0;
 			double s0 = 0.0;
 			unsigned long long cnt = 0;
 			for (int t = lane; t < NT; t += 32)
@@ -1197,17 +1210,22 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				{
 					const double pv = sl < nsl ? ldsf64(smem_base + prm.acc_off + (uint32_t) ((g * nsl + sl) * NT + t) * 8)
 					                           : reg_stage[(g * GG_REG_SLOTS + (sl - nsl)) * NT + t];
-					/* a non-finite private sum is either a legitimate +-Inf/NaN input or a float8pl overflow
-					 * (ERROR in the reference, float.c:782): this variant does not track which, so it asks the host
-					 * to decide by replaying the input on the fully checked interpreter kernel */
-					if (!f8_finite(pv)) atomicOr(prm.errflags, GGP_EF_RECHECK);
-					s0 = __dadd_rn(s0, pv);
+					if (isint) s0 = __longlong_as_double(__double_as_longlong(s0) + __double_as_longlong(pv));
+					else
+					{
+						/* a non-finite private sum is either a legitimate +-Inf/NaN input or a float8pl overflow
+						 * (ERROR in the reference, float.c:782): this variant does not track which, so it asks the host
+						 * to decide by replaying the input on the fully checked interpreter kernel */
+						if (!f8_finite(pv)) atomicOr(prm.errflags, GGP_EF_RECHECK);
+						s0 = __dadd_rn(s0, pv);
+					}
 				}
 				if (sl == 0) cnt += lds32(smem_base + prm.cnt_off + (uint32_t) (g * NT + t) * 4);
 			}
 			for (int o = 16; o > 0; o >>= 1)
 			{
-				s0 = __dadd_rn(s0, __shfl_xor_sync(GG_FULL_MASK, s0, o));
+				const double other = __shfl_xor_sync(GG_FULL_MASK, s0, o);
+				s0 = isint ? __longlong_as_double(__double_as_longlong(s0) + __double_as_longlong(other)) : __dadd_rn(s0, other);
 				cnt += __shfl_xor_sync(GG_FULL_MASK, cnt, o);
 			}
 			if (lane == 0)

@@ -17,12 +17,13 @@ os.environ["GGB200_PLAN_CACHE"] = "0"
 eng = Engine(0)
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
+# (GGB200_PRIV_CONFIG "consumer warps,stages,team", GGB200_REG_SLOTS, GGB200_KEYCACHE); None = the engine's own choice
 CONFIGS = {
-    "wide": [("20,5,0", None), ("18,5,6", None), ("18,4,6", None), ("24,4,6", None), ("24,5,6", None), ("12,5,6", None), ("15,5,3", None),
-             ("21,5,7", None), ("20,5,5", None), ("18,5,6", "2"), ("18,4,6", "2"), ("12,5,6", "0"), ("18,3,6", "0"), ("24,3,6", None), ("20,5,0", "2"),
-             ("18,5,9", None), ("16,5,4", None), ("20,5,4", None)],
-    "narrow": [("20,3,0", None), ("20,3,0", "0"), ("21,3,7", None), ("21,4,7", None), ("14,4,7", None), ("14,5,7", None), ("28,4,7", None), ("28,3,14", None),
-               ("21,3,7", "0"), ("14,4,7", "0"), ("20,4,5", None), ("20,4,10", None), ("15,5,5", None), ("24,4,8", None), ("21,5,7", None), ("28,3,7", None)],
+    "wide": [(None, None, None), ("20,5,0", None, None), ("21,5,7", None, None), ("21,5,7", None, "0"), ("20,5,0", None, "0"), ("21,4,7", None, None), ("14,5,7", None, None),
+             ("14,4,7", None, None), ("21,3,7", None, None), ("24,5,8", None, None), ("24,4,8", None, None), ("16,5,8", None, None), ("28,4,7", None, None),
+             ("21,5,7", "2", None), ("21,4,7", "0", None), ("14,5,7", "0", None)],
+    "narrow": [(None, None, None), ("20,3,0", None, None), ("20,3,0", "0", None), ("21,3,7", None, None), ("21,3,7", "0", None), ("24,3,8", None, None), ("24,3,8", "0", None),
+               ("16,3,8", "0", None), ("16,4,8", None, None), ("24,4,8", None, None), ("14,4,7", "0", None), ("15,3,15", "0", None), ("20,4,5", None, None), ("21,4,7", None, None)],
 }
 for tname in which.split(","):
     table = capi.TAB_LINEITEM_WIDE if tname == "wide" else capi.TAB_LINEITEM_NARROW
@@ -31,16 +32,16 @@ for tname in which.split(","):
     del pages
     scan, agg, pool = tpch.q1_plan(table, capi.AGGSTAGE_NORMAL)
     ref = None
-    for cfg, regs in CONFIGS[tname]:
-        os.environ["GGB200_PRIV_CONFIG"] = cfg
-        if regs is None:
-            os.environ.pop("GGB200_REG_SLOTS", None)
-        else:
-            os.environ["GGB200_REG_SLOTS"] = regs
+    for cfg, regs, kc in CONFIGS[tname]:
+        for k, v in (("GGB200_PRIV_CONFIG", cfg), ("GGB200_REG_SLOTS", regs), ("GGB200_KEYCACHE", kc)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         try:
             sa = ScanAgg(eng, scan, agg, pool)
         except Exception as exc:
-            print(json.dumps({"table": tname, "config": cfg, "regslots": regs, "error": str(exc)[:200]}), flush=True)
+            print(json.dumps({"table": tname, "config": cfg, "regslots": regs, "keycache": kc, "error": str(exc)[:200]}), flush=True)
             continue
         best = None
         try:
@@ -56,7 +57,7 @@ for tname in which.split(","):
                 ref = res
             else:
                 ok = len(res) == len(ref) and all(a[:3] == b[:3] and all(abs(x - y) <= 1e-9 * abs(y) for x, y in zip(a[3], b[3])) for a, b in zip(res, ref))
-            print(json.dumps({"table": tname, "config": cfg, "regslots": regs, "variant": sa.variant(), "ms": best, "GBps": nb * 32768 / best / 1e6,
+            print(json.dumps({"table": tname, "config": cfg, "regslots": regs, "keycache": kc, "variant": sa.variant(), "ms": best, "GBps": nb * 32768 / best / 1e6,
                               "frac": nb * 32768 / best / 1e6 / PEAK, "Grows_s": nr / best / 1e6, "scanned": sc, "equal_to_first": ok}), flush=True)
         except Exception as exc:
             print(json.dumps({"table": tname, "config": cfg, "regslots": regs, "error": str(exc)[:200]}), flush=True)
