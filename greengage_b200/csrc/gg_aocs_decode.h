@@ -51,6 +51,44 @@ GG_AOCS_FN int32_t gg_aocs_nulls_between(const uint8_t *bitmap, int32_t from, in
 	return n;
 }
 
+/* a stored value at p -> the 64-bit Datum word of a datum row (enum gg_aocs_kind); 0, or GG_AOCS_E_IRREGULAR for a string that
+ * does not pack into 8 bytes */
+GG_AOCS_FN uint32_t gg_aocs_value(int kind, const uint8_t *p, uint64_t *word)
+{
+	uint64_t v = 0;
+
+	switch (kind)
+	{
+		case GG_AOCS_K_W8:
+			v = *(const uint64_t *) p;						/* data_off is 8-aligned, stride 8 */
+			break;
+		case GG_AOCS_K_I4:
+			v = (uint64_t) (int64_t) *(const int32_t *) p;
+			break;
+		case GG_AOCS_K_I2:
+			v = (uint64_t) (int64_t) *(const int16_t *) p;
+			break;
+		case GG_AOCS_K_B1:
+			v = *p;
+			break;
+		default:
+		{
+			int n = (p[0] & 0x7F) - 1, i;					/* payload bytes after the 1-byte header */
+
+			if (kind == GG_AOCS_K_BPCHAR)
+				while (n > 0 && p[n] == ' ')				/* bcTruelen (varchar.c:653) */
+					n--;
+			if (n > 8)
+				return GG_AOCS_E_IRREGULAR;
+			for (i = 0; i < n; i++)
+				v |= (uint64_t) p[1 + i] << (8 * i);
+			break;
+		}
+	}
+	*word = v;
+	return 0;
+}
+
 /* Row `lane_row` of tile `tile`: 0 and *word / *isnull set, or a GG_AOCS_E_* bit. */
 GG_AOCS_FN uint32_t gg_aocs_fetch(const gg_aocs_devcol *c, int64_t tile, int32_t lane_row, uint64_t *word, int *isnull)
 {
@@ -59,7 +97,6 @@ GG_AOCS_FN uint32_t gg_aocs_fetch(const gg_aocs_devcol *c, int64_t tile, int32_t
 	int64_t j = (int64_t) t.row_in_block + lane_row;
 	int32_t counted_to = t.row_in_block, nulls = t.nulls_before;
 	const uint8_t *p;
-	uint64_t v = 0;
 	gg_aocs_block blk;
 
 	while (b < c->nblocks && j >= c->dir[b].nrows)		/* the column's next storage block; bounded by the directory */
@@ -88,36 +125,7 @@ GG_AOCS_FN uint32_t gg_aocs_fetch(const gg_aocs_devcol *c, int64_t tile, int32_t
 	if (blk.stride <= 0)
 		return GG_AOCS_E_IRREGULAR;
 	p = c->file + blk.data_off + (j - nulls) * (int64_t) blk.stride;
-	switch (c->kind)
-	{
-		case GG_AOCS_K_W8:
-			v = *(const uint64_t *) p;						/* data_off is 8-aligned, stride 8 */
-			break;
-		case GG_AOCS_K_I4:
-			v = (uint64_t) (int64_t) *(const int32_t *) p;
-			break;
-		case GG_AOCS_K_I2:
-			v = (uint64_t) (int64_t) *(const int16_t *) p;
-			break;
-		case GG_AOCS_K_B1:
-			v = *p;
-			break;
-		default:
-		{
-			int n = (p[0] & 0x7F) - 1, i;					/* payload bytes after the 1-byte header */
-
-			if (c->kind == GG_AOCS_K_BPCHAR)
-				while (n > 0 && p[n] == ' ')				/* bcTruelen (varchar.c:653) */
-					n--;
-			if (n > 8)
-				return GG_AOCS_E_IRREGULAR;
-			for (i = 0; i < n; i++)
-				v |= (uint64_t) p[1 + i] << (8 * i);
-			break;
-		}
-	}
-	*word = v;
-	return 0;
+	return gg_aocs_value(c->kind, p, word);
 }
 
 #endif /* GG_AOCS_DECODE_H */

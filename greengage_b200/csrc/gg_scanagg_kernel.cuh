@@ -927,25 +927,53 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					{
 						/* the row is assembled here, from the column files: an odd word stride keeps the lanes on distinct banks */
 						rp = myscr + (uint32_t) prm.scratch_per_warp - (32u - (uint32_t) lane) * ((rowwords | 1u) * 8);      /* the tail of the warp's scratch */
-						uint64_t m = 0;
-						if (live)
+						/* Where the chunk's rows sit in each column file is the same question for all 32 lanes: lane sl answers it for
+						 * column slot sl (tile plan -> storage block -> address of the chunk's first value: two dependent loads, all
+						 * columns at once), the answers are broadcast, and every lane then loads its own row's values — independent
+						 * loads, all in flight together.  A block that ends inside the chunk, or one with a NULL bitmap, sends the
+						 * lanes concerned through the general per-row walk (gg_aocs_fetch). */
+						const int64_t tile = (int64_t) (first + (uint64_t) it * stride);
+						unsigned long long m_addr = 0;
+						int m_left = 0, m_stride = 0, m_kind = 0;
+						if (lane < ncols)
 						{
-							const int64_t tile = (int64_t) (first + (uint64_t) it * stride);
-							uint32_t aerr = 0;
-							for (int sl = 0; sl < ncols; sl++)
+							const gg_aocs_devcol *cd = prm.aocs + P.outer.colatt[lane];
+							const gg_aocs_tile t = cd->tiles[tile];
+							int64_t b = t.block, j = (int64_t) t.row_in_block + (int64_t) c * 32;
+							while (b < cd->nblocks && j >= cd->dir[b].nrows) { j -= cd->dir[b].nrows; b++; }
+							m_kind = cd->kind;
+							if (b < cd->nblocks)
 							{
-								const int a = P.outer.colatt[sl];
-								uint64_t w = 0;
-								int isn = 0;
-								const uint32_t rc = gg_aocs_fetch(prm.aocs + a, tile, idx, &w, &isn);
-								aerr |= rc;
-								if (rc || isn) { w = 0; m |= 1ull << a; }
-								sts64(rp + 8 + (uint32_t) a * 8, w);
+								const gg_aocs_block blk = cd->dir[b];
+								if (blk.null_off < 0 && blk.stride > 0)
+								{
+									m_addr = (unsigned long long) (cd->file + blk.data_off + j * (int64_t) blk.stride);
+									m_left = (int) (blk.nrows - j);
+									m_stride = blk.stride;
+								}
 							}
-							if (aerr & GG_AOCS_E_RANGE) err |= GGP_EF_BADPAGE;
-							if (aerr & GG_AOCS_E_IRREGULAR) err |= GGP_EF_STRING_TOO_LONG;
-							if (aerr) live = false;
 						}
+						uint64_t m = 0;
+						uint32_t aerr = 0;
+						for (int sl = 0; sl < ncols; sl++)
+						{
+							const int a = P.outer.colatt[sl];
+							const unsigned long long base = __shfl_sync(GG_FULL_MASK, m_addr, sl);
+							const int left = __shfl_sync(GG_FULL_MASK, m_left, sl), vstride = __shfl_sync(GG_FULL_MASK, m_stride, sl);
+							const int kind = __shfl_sync(GG_FULL_MASK, m_kind, sl);
+							if (!live) continue;
+							uint64_t w = 0;
+							int isn = 0;
+							uint32_t rc;
+							if (base && lane < left) rc = gg_aocs_value(kind, (const uint8_t *) (base + (unsigned long long) lane * (unsigned long long) vstride), &w);
+							else rc = gg_aocs_fetch(prm.aocs + a, tile, idx, &w, &isn);
+							aerr |= rc;
+							if (rc || isn) { w = 0; m |= 1ull << a; }
+							sts64(rp + 8 + (uint32_t) a * 8, w);
+						}
+						if (aerr & GG_AOCS_E_RANGE) err |= GGP_EF_BADPAGE;
+						if (aerr & GG_AOCS_E_IRREGULAR) err |= GGP_EF_STRING_TOO_LONG;
+						if (aerr) live = false;
 						sts64(rp, m);
 					}
 					X.fast = true;
