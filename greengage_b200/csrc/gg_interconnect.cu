@@ -122,7 +122,13 @@ __global__ void gg_ic_pack_groups_kernel(const ggp_grec *recs, const int *d_n, c
 		const bool over = n > GG_IC_GROUP_CAP;
 		s_n = over ? GG_IC_GROUP_CAP + 1 : n;
 		dst->n = over ? 0u : (uint32_t) n;
-		dst->err = (st ? st->err : 0u) | local_flags | (over ? GGP_EF_HOSTPATH : 0u);
+		/* a pipeline whose result was not fetched before it travelled (the executor leaves that to the top of the slice) may
+		 * carry "replay me on a wider kernel variant": only a fetch on the producing segment can do that, so it becomes
+		 * "this Motion takes the host path" for everybody */
+		uint32_t perr = st ? st->err : 0u;
+		const bool replay = (perr & (GGP_EF_GROUP_OVERFLOW | GGP_EF_RECHECK)) != 0;
+		perr &= ~(uint32_t) (GGP_EF_GROUP_OVERFLOW | GGP_EF_RECHECK);
+		dst->err = perr | local_flags | ((over || replay) ? GGP_EF_HOSTPATH : 0u);
 		dst->counters[0] = st ? st->counters[0] : 0ull;
 		dst->counters[1] = st ? st->counters[1] : 0ull;
 	}

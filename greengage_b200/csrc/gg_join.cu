@@ -517,6 +517,11 @@ int gg_scanagg_groups(gg_scanagg *p, gg_groups **out);
 int gg_joinagg_groups(gg_joinagg *j, gg_groups **out)
 {
 	if (!j) return GG_ERR_ARG;
+	if (!(j->bj && j->nbatch > 1))
+	{
+		int rc = joinagg_fill_inner(j);          /* right / full joins: the unmatched inner rows belong to the result */
+		if (rc) return rc;
+	}
 	return gg_scanagg_groups(j->bj && j->nbatch > 1 ? j->bj->probe : j->probe, out);
 }
 

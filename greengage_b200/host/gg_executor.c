@@ -59,6 +59,9 @@ struct GgPlanState {
 	int nonreceiver;                    /* above a Gather, on a segment that is not its receiver: no rows at all */
 	int dev_groups;                     /* decided at init, from the plan alone (so every segment decides alike): this node hands
 	                                     * its aggregate rows up as device-resident group records */
+	int lazy_fetch;                     /* set by a Motion above that moves this node's records on the device: the pipeline's result
+	                                     * is not fetched to the host before it travels (no host synchronisation between the scan
+	                                     * and the Motion); what a fetch would have decided travels as status flags */
 	int32_t ncols;
 	int64_t nrows, next, markpos;
 	int64_t *values;
@@ -523,6 +526,7 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 				for (c = 0; ok && mo->motionType == GG_MOTIONTYPE_HASH && c < mo->numHashCols; c++)
 					ok = mo->hashCol[c] >= 0 && mo->hashCol[c] < s->child->agg.numCols;
 				s->dev_groups = ok;
+				if (ok && (s->child->kind == K_SCANAGG || s->child->kind == K_JOINAGG)) s->child->lazy_fetch = 1;
 			}
 			return s;
 		}
@@ -763,6 +767,20 @@ static int run_node(GgPlanState *s)
 				/* MultiExecHash + the probe loop; in batches when the table would not fit the operator's memory */
 				rc = gg_joinagg_set_work_mem(s->ja, es->es_operator_mem);
 				if (rc == GG_OK) rc = gg_joinagg_run(s->ja, irel, orel);
+			}
+			if (rc == GG_OK && s->lazy_fetch && !es->motion_on_host)
+			{
+				/* the records go straight into the Motion above; a pipeline that would have to be replayed says so in its
+				 * status, which makes that Motion (on every segment) fall back to host rows — where the fetch below runs */
+				int rg = s->kind == K_SCANAGG ? gg_scanagg_groups(s->sa, &s->groups) : gg_joinagg_groups(s->ja, &s->groups);
+				if (rg == GG_OK)
+				{
+					for (c = 0; c < s->agg.numCols; c++) keytypes[c] = expr_type(es->pool, s->agg.grpCol[c]);
+					if (set_layout_types(s, &s->agg, keytypes)) return -1;
+					s->rows_ready = 0;
+					break;
+				}
+				s->groups = NULL;                     /* general HashAggregate: its groups live in the hash table — fetch rows */
 			}
 			/* fetch decides whether the pipeline has to be replayed on a wider kernel variant (more groups than expected, a
 			 * non-finite sum to attribute), so it runs before anything above consumes the records on the device */
