@@ -11,7 +11,7 @@ using namespace ggd;
 /* HashJoin probe side: the same scan front end; every outer row probes the join hash table and each
  * match runs the per-match piece of the program (join qual, grouping keys, aggregate arguments) */
 template <int MODE>
-__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
+__global__ void __launch_bounds__(MODE == MODE_PRIV ? 704 : 256, MODE == MODE_PRIV ? 1 : 2)
 gg_joinprobe_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
 	scanagg_body<MODE, DynPlan, true>(P, prm);

@@ -14,7 +14,7 @@
 using namespace ggd;
 
 template <int MODE>
-__global__ void __launch_bounds__(MODE == MODE_PRIV ? 672 : 256, MODE == MODE_PRIV ? 1 : 2)
+__global__ void __launch_bounds__(MODE == MODE_PRIV ? 704 : 256, MODE == MODE_PRIV ? 1 : 2)
 gg_scanagg_kernel(const __grid_constant__ ggp_program P, const ScanAggParams prm)
 {
 	scanagg_body<MODE, DynPlan>(P, prm);

@@ -862,7 +862,16 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			const bool aocs = prm.aocs_tile_rows > 0;
 			if (!aocs)
 			{
-				if (lane == 0) mbar_wait(full_bar + s * 8, ph, 20);
+				if (lane == 0)
+				{
+					/* A parity wait tells the current phase of the slot from the one before it, no further.  A warp that visits
+					 * every page has consumed page it - nstage itself; a team has only consumed page it - nteams, which says that
+					 * the copy of page it - nstage was ISSUED before, not that it has landed (bulk copies complete in any order).
+					 * So a team first waits for that earlier phase — the slot is then in the phase of page `it` for certain (it
+					 * cannot be further: this team has not released it) — and only then for its own. */
+					if (prm.team > 0 && it >= (uint32_t) nstage) mbar_wait(full_bar + s * 8, ph ^ 1, 20);
+					mbar_wait(full_bar + s * 8, ph, 20);
+				}
 				__syncwarp();
 			}
 			const uint32_t pg = ring + (uint32_t) s * GG_BLCKSZ;
