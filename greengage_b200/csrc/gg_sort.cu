@@ -32,7 +32,7 @@
 #define SORT_WARPS   (SORT_THREADS / 32)
 #define FULL 0xffffffffu
 
-enum { KEYMODE_VALUE = 0, KEYMODE_NULLBIT = 1 };
+enum { KEYMODE_VALUE = 0, KEYMODE_NULLBIT = 1, KEYMODE_DEADBIT = 2 };
 
 __device__ __forceinline__ uint64_t bswap64(uint64_t v)
 {
@@ -71,21 +71,44 @@ __device__ __forceinline__ uint64_t radix_key(int64_t v, int typid, int desc)
 	return desc ? ~k : k;
 }
 
-/* keys of the current order: kout[i] = key(rows[perm[i]][col]); also OR / AND over all keys (which bits vary) */
+/* keys of the current order: kout[i] = key(rows[perm[i]][col]); also OR / AND over all keys (which bits vary).
+ * datumrows: the rows are GG_FMT_DATUMROWS (ncols + 1 words: NULL mask, columns), as a row-producing scan or a receiving
+ * Motion leaves them on the device; KEYMODE_DEADBIT keys the slots a sending kernel claimed and did not fill (bit 63 of the
+ * mask word) behind everything else and counts them into orand[2]. */
 __global__ void __launch_bounds__(256)
 gg_sort_keys_kernel(const int64_t *rows, const uint8_t *nulls, int ncols, int col, int typid, int desc, int nulls_first,
-                    int mode, const uint32_t *perm, uint64_t n, uint64_t *kout, unsigned long long *orand)
+                    int mode, const uint32_t *perm, uint64_t n, uint64_t *kout, unsigned long long *orand, int datumrows)
 {
 	uint64_t vor = 0, vand = ~0ull;
+	unsigned long long ndead = 0;
 	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
 	{
 		const uint64_t r = perm ? perm[i] : i;
-		const bool isnull = nulls && nulls[r * ncols + col];
 		uint64_t k;
-		if (mode == KEYMODE_VALUE) k = isnull ? 0 : radix_key(rows[r * ncols + col], typid, desc);
-		else k = isnull ? (nulls_first ? 0 : 1) : (nulls_first ? 1 : 0);
+		if (datumrows)
+		{
+			const uint64_t mask = (uint64_t) rows[r * (uint64_t) (ncols + 1)];
+			if (mode == KEYMODE_DEADBIT) { k = mask >> 63; ndead += k; }
+			else
+			{
+				const bool isnull = (mask >> col) & 1;
+				if (mode == KEYMODE_VALUE) k = isnull ? 0 : radix_key(rows[r * (uint64_t) (ncols + 1) + 1 + col], typid, desc);
+				else k = isnull ? (nulls_first ? 0 : 1) : (nulls_first ? 1 : 0);
+			}
+		}
+		else
+		{
+			const bool isnull = nulls && nulls[r * ncols + col];
+			if (mode == KEYMODE_VALUE) k = isnull ? 0 : radix_key(rows[r * ncols + col], typid, desc);
+			else k = isnull ? (nulls_first ? 0 : 1) : (nulls_first ? 1 : 0);
+		}
 		kout[i] = k;
 		vor |= k; vand &= k;
+	}
+	if (mode == KEYMODE_DEADBIT)
+	{
+		for (int o = 16; o > 0; o >>= 1) ndead += __shfl_xor_sync(FULL, ndead, o);
+		if ((threadIdx.x & 31) == 0 && ndead) atomicAdd(&orand[2], ndead);
 	}
 	for (int o = 16; o > 0; o >>= 1)
 	{
@@ -299,6 +322,19 @@ gg_sort_widen_kernel(const uint32_t *perm, uint64_t *out, uint64_t n)
 		out[i] = perm[i];
 }
 
+/* rows in sorted order: out row i = in row perm[i], W words each; a warp moves a row's words with consecutive lanes */
+__global__ void __launch_bounds__(256)
+gg_sort_gather_rows_kernel(const uint64_t *rows, const uint32_t *perm, uint64_t n, int W, uint64_t *out)
+{
+	const uint64_t total = n * (uint64_t) W;
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < total; i += (uint64_t) gridDim.x * blockDim.x)
+	{
+		const uint64_t r = i / (uint64_t) W;
+		const uint32_t w = (uint32_t) (i - r * (uint64_t) W);
+		out[i] = rows[(uint64_t) perm[r] * (uint64_t) W + w];
+	}
+}
+
 /* ===================================================================================== */
 
 static bool sort_type_ok(int32_t t)
@@ -322,7 +358,8 @@ struct SortScratch {                      /* carved out of one allocation the en
 /* sort rows resident on the device; dev_perm receives n uint32 row numbers in sorted order.
  * passes_out (optional): radix passes executed (for the traffic model). */
 static int sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const int64_t *d_rows,
-                       const uint8_t *d_nulls, uint64_t n, uint32_t *dev_perm, int *passes_out)
+                       const uint8_t *d_nulls, uint64_t n, uint32_t *dev_perm, int *passes_out,
+                       bool datumrows = false, uint64_t *ndead_out = nullptr)
 {
 	if (n >= (1ull << 32)) { gg_set_error("sort of %llu rows: row numbers are 32-bit", (unsigned long long) n); return GG_ERR_UNSUPPORTED; }
 	for (int k = 0; k < nkeys; k++)
@@ -368,20 +405,24 @@ static int sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncol
 	gg_sort_iota_kernel<<<grid1d, 256, 0, st>>>(vbuf[0], n);
 	e->launches++;
 	bool first = true;
-	for (int kc = nkeys - 1; kc >= 0; kc--)
+	/* least significant first: the last sort column's value, its NULL digit, ..., the first column's; for datum rows one
+	 * more digit on top puts the dead slots behind every row */
+	for (int kc = nkeys - 1; kc >= (datumrows ? -1 : 0); kc--)
 	{
-		for (int mode = KEYMODE_VALUE; mode <= KEYMODE_NULLBIT; mode++)
+		for (int mode = kc < 0 ? KEYMODE_DEADBIT : KEYMODE_VALUE; mode <= (kc < 0 ? KEYMODE_DEADBIT : KEYMODE_NULLBIT); mode++)
 		{
-			if (mode == KEYMODE_NULLBIT && !d_nulls) break;
-			const unsigned long long init[2] = { 0ull, ~0ull };
-			GG_CUDA(cudaMemcpyAsync(s.orand, init, 16, cudaMemcpyHostToDevice, st));
-			gg_sort_keys_kernel<<<grid1d, 256, 0, st>>>(d_rows, d_nulls, ncols, keys[kc].col, keys[kc].typid, keys[kc].desc,
-			                                            keys[kc].nulls_first, mode, first ? nullptr : vbuf[cur], n, s.k[kcur], s.orand);
+			if (mode == KEYMODE_NULLBIT && !d_nulls && !datumrows) break;
+			const gg_sortkey &K = keys[kc < 0 ? 0 : kc];
+			const unsigned long long init[3] = { 0ull, ~0ull, 0ull };
+			GG_CUDA(cudaMemcpyAsync(s.orand, init, 24, cudaMemcpyHostToDevice, st));
+			gg_sort_keys_kernel<<<grid1d, 256, 0, st>>>(d_rows, d_nulls, ncols, K.col, K.typid, K.desc,
+			                                            K.nulls_first, mode, first ? nullptr : vbuf[cur], n, s.k[kcur], s.orand, datumrows ? 1 : 0);
 			GG_CUDA(cudaGetLastError());
 			e->launches++;
-			unsigned long long oa[2];
-			GG_CUDA(cudaMemcpyAsync(oa, s.orand, 16, cudaMemcpyDeviceToHost, st));
+			unsigned long long oa[3];
+			GG_CUDA(cudaMemcpyAsync(oa, s.orand, 24, cudaMemcpyDeviceToHost, st));
 			GG_CUDA(cudaStreamSynchronize(st));
+			if (mode == KEYMODE_DEADBIT && ndead_out) *ndead_out = oa[2];
 			const uint64_t varying = oa[0] ^ oa[1];          /* bits that are not the same in every key */
 			for (int byte = 0; byte < 8; byte++)
 			{
@@ -421,6 +462,38 @@ int gg_sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, c
 	GG_CUDA(cudaEventRecord(e->ev_stop, e->stream));
 	e->timed = true;
 	return GG_OK;
+}
+
+int gg_sort_datumrows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const void *dev_rows, uint64_t n,
+                      void *dev_out_rows, uint64_t *nlive, int *passes)
+{
+	if (!e || !keys || nkeys < 1 || ncols < 1 || ncols > 63 || !nlive || (n && (!dev_rows || !dev_out_rows))) return GG_ERR_ARG;
+	*nlive = 0;
+	if (n == 0) return GG_OK;
+	GG_CUDA(cudaSetDevice(e->device));
+	uint32_t *d_perm = nullptr;
+	cudaError_t ce = cudaMalloc((void **) &d_perm, n * 4);
+	if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("sort: %llu row numbers do not fit in device memory", (unsigned long long) n); return GG_ERR_NOMEM; }
+	GG_CUDA(cudaEventRecord(e->ev_start, e->stream));
+	uint64_t ndead = 0;
+	int rc = sort_device(e, keys, nkeys, ncols, (const int64_t *) dev_rows, nullptr, n, d_perm, passes, true, &ndead);
+	if (rc == GG_OK)
+	{
+		const uint64_t live = n - ndead;
+		if (live)
+		{
+			gg_sort_gather_rows_kernel<<<e->sm_count * 8, 256, 0, e->stream>>>((const uint64_t *) dev_rows, d_perm, live, ncols + 1, (uint64_t *) dev_out_rows);
+			e->launches++;
+		}
+		ce = cudaGetLastError();
+		if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_stop, e->stream);
+		if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+		if (ce != cudaSuccess) { cudaFree(d_perm); return gg_cuda_fail(ce, "gg_sort_datumrows"); }
+		e->timed = true;
+		*nlive = live;
+	}
+	cudaFree(d_perm);
+	return rc;
 }
 
 int gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols,

@@ -859,7 +859,7 @@ static int run_node(GgPlanState *s)
 			gg_sortkey keys[GG_MAX_SORTKEYS];
 			int64_t r;
 			int k;
-			if (run_child(s) || ensure_rows(ch)) return -1;
+			if (run_child(s)) return -1;
 			s->nonreceiver = ch->nonreceiver;
 			for (k = 0; k < so->numCols; k++)
 			{
@@ -867,6 +867,31 @@ static int run_node(GgPlanState *s)
 				if (keys[k].col < 0 || keys[k].col >= ch->ncols) { exec_fail(GG_ERR_ARG, "Sort key column %d out of range", keys[k].col); return -1; }
 				if (!keys[k].typid) keys[k].typid = ch->typid[keys[k].col];
 			}
+			if (ch->rows_rel && !ch->rows_ready)
+			{
+				/* the input is datum rows on the device (a row-producing SeqScan, or the Motion over one): sort them where they
+				 * are; the sorted rows stay on the device for the node above, or come to the host once, at the top */
+				const uint64_t W = 1 + (uint64_t) ch->rows_ncols;
+				const uint64_t nb = (ch->rows_n * W * 8 + 64 + GG_BLCKSZ - 1) / GG_BLCKSZ;
+				uint64_t live = 0;
+				drop_device_results(s);
+				if (s->rows_send && gg_relation_nblocks(s->rows_send) < nb) { gg_relation_free(s->rows_send); s->rows_send = NULL; }
+				if (!s->rows_send)
+				{
+					rc = gg_relation_create(es->engine, nb, &s->rows_send);
+					if (rc != GG_OK) { exec_fail(rc, "Sort result: %s", gg_last_error()); return -1; }
+				}
+				rc = gg_sort_datumrows(es->engine, keys, so->numCols, ch->rows_ncols, gg_relation_device_ptr(ch->rows_rel), ch->rows_n,
+				                       gg_relation_device_ptr(s->rows_send), &live, NULL);
+				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+				s->rows_n = live; s->rows_ncols = ch->rows_ncols; s->rows_nsegs = 1;
+				s->ncols = ch->ncols;
+				memcpy(s->typid, ch->typid, sizeof s->typid);
+				rc = gg_relation_attach_rows(es->engine, gg_relation_device_ptr(s->rows_send), live, ch->rows_ncols, &s->rows_rel);
+				if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); return -1; }
+				break;
+			}
+			if (ensure_rows(ch)) return -1;
 			if (alloc_result(s, ch->nrows, ch->ncols)) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
 			memcpy(s->typid, ch->typid, sizeof s->typid);
 			perm = malloc(8 * (size_t) (ch->nrows > 0 ? ch->nrows : 1));

@@ -177,6 +177,12 @@ int  gg_sort_rows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols,
  * passes (optional) the number of radix passes executed */
 int  gg_sort_device(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const int64_t *dev_rows,
                     const uint8_t *dev_nulls, uint64_t n, uint32_t *dev_perm, int *passes);
+/* Sort over what a row-producing SeqScan or a receiving Motion left on the device (nodeSort.c:48-256 with its input and its
+ * result in device memory): dev_rows holds n GG_FMT_DATUMROWS rows of ncols columns (1 + ncols words each, NULLs in the mask
+ * word; slots marked GG_DATUMROW_DEAD are dropped); dev_out_rows receives the *nlive rows in sorted order, same format.
+ * keys[].col counts the row's columns from 0. */
+int  gg_sort_datumrows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const void *dev_rows, uint64_t n,
+                       void *dev_out_rows, uint64_t *nlive, int *passes);
 
 /* ---- Motion ----
  * Sending side of a Redistribute Motion (nodeMotion.c:1481-1687, cdbhash.c:173-287) on the device: evaluates the

@@ -238,3 +238,37 @@ def test_bare_seqscan_with_a_target_list_returns_its_rows(eng):
     finally:
         x.end()
         rel.free()
+
+
+def test_sort_over_a_row_producing_seqscan_stays_on_the_device(eng):
+    """Sort <- SeqScan(targets) (nodeSort.c:48 over nodeSeqscan.c:128): the scan leaves datum rows on the device, the Sort orders
+    them there (comparator of tuplesort_mk.c:2816: DESC, then ASC on the second key) and the rows come to the host once."""
+    import numpy as np
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import Relation
+    li, _, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 30_000, seed=11))
+    c = tpch.LI_NARROW_COLS
+    desc = capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW)
+    p = ExprPool()
+    key, price, flag, date = (p.var(c["orderkey"], capi.INT8OID), p.var(c["extendedprice"], capi.FLOAT8OID),
+                              p.var(c["returnflag"], capi.BPCHAROID), p.var(c["shipdate"], capi.DATEOID))
+    qual = p.func(capi.F_FLOAT8GT, capi.BOOLOID, p.var(c["quantity"], capi.FLOAT8OID), p.const(capi.FLOAT8OID, 10.0))
+    rel = Relation(eng, host_pages=li)
+    b = ex.PlanBuilder()
+    scan = b.seqscan(0, desc, qual, targets=[key, price, flag, date])
+    x0 = ex.Executor(eng, p.pool, [rel], scan)
+    x = ex.Executor(eng, p.pool, [rel], b.sort(b.seqscan(0, desc, qual, targets=[key, price, flag, date]),
+                                                 [capi.make_sortkey(2, capi.BPCHAROID, desc=True), capi.make_sortkey(1, capi.FLOAT8OID),
+                                                  capi.make_sortkey(0, capi.INT8OID)]))
+    try:
+        plain = x0.rows()
+        rows = x.rows()
+        assert len(rows) == len(plain) > 20_000
+        assert sorted(tuple(v) for v, nl, ty, ln in rows) == sorted(tuple(v) for v, nl, ty, ln in plain)      # same multiset of rows
+        keys = [(-ord(capi.unpack_str(v[2], ln[2])), b2f(v[1]), v[0]) for v, nl, ty, ln in rows]
+        assert keys == sorted(keys)
+        assert len({k[0] for k in keys}) == 3
+    finally:
+        x.end()
+        x0.end()
+        rel.free()
