@@ -101,6 +101,25 @@ class gg_sortkey(C.Structure):
     _fields_ = [("col", C.c_int32), ("typid", C.c_int32), ("desc", C.c_int32), ("nulls_first", C.c_int32)]
 
 
+class gg_snapshot(C.Structure):
+    """include/gg_plan.h gg_snapshot; make_snapshot() below keeps the arrays it points to alive"""
+    _fields_ = [("xmin", C.c_uint32), ("xmax", C.c_uint32), ("xcnt", C.c_uint32), ("curcid", C.c_uint32), ("own_xid", C.c_uint32),
+                ("clog_base", C.c_uint32), ("clog_n", C.c_uint32), ("suboverflowed", C.c_uint8), ("takenDuringRecovery", C.c_uint8),
+                ("haveDistribSnapshot", C.c_uint8), ("pad", C.c_uint8), ("xip", C.POINTER(C.c_uint32)), ("clog", C.POINTER(C.c_uint8))]
+
+
+def make_snapshot(xmin, xmax, xip=(), curcid=0, own_xid=0, clog_base=0, clog=b"", clog_n=None):
+    """clog: the pg_clog bytes covering xids clog_base .. (2 bits per xid, clog.h:25-28)"""
+    s = gg_snapshot()
+    s.xmin, s.xmax, s.xcnt, s.curcid, s.own_xid = xmin, xmax, len(xip), curcid, own_xid
+    s.clog_base, s.clog_n = clog_base, len(clog) * 4 if clog_n is None else clog_n
+    s._xip = (C.c_uint32 * max(1, len(xip)))(*xip)
+    s._clog = (C.c_uint8 * max(1, len(clog))).from_buffer_copy(bytes(clog) if clog else b"\0")
+    s.xip = C.cast(s._xip, C.POINTER(C.c_uint32))
+    s.clog = C.cast(s._clog, C.POINTER(C.c_uint8))
+    return s
+
+
 class gg_synth_spec(C.Structure):
     _fields_ = [("table", C.c_int32), ("policy", C.c_int32), ("seed", C.c_uint64), ("ncand", C.c_uint64),
                 ("norders", C.c_uint64), ("nsegs", C.c_int32), ("seg", C.c_int32)]
@@ -170,6 +189,7 @@ def dev_lib():
         L.gg_engine_free.argtypes = [vp]
         L.gg_engine_free.restype = None
         L.gg_engine_sm_count.argtypes = [vp]
+        L.gg_engine_set_snapshot.argtypes = [vp, C.POINTER(gg_snapshot)]
         L.gg_engine_sync.argtypes = [vp]
         L.gg_engine_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.gg_engine_launch_count.argtypes = [vp]

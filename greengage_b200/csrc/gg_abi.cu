@@ -112,6 +112,7 @@ void gg_engine_free(gg_engine *e)
 	cudaFree(e->final_scratch);
 	cudaFree(e->sort_scratch);
 	cudaFree(e->motion_state);
+	cudaFree(e->snapshot_buf);
 	for (void *m : e->groups_pool) cudaFree(m);
 	cudaFreeHost(e->groups_mirror);
 	cudaEventDestroy(e->ev_start);
@@ -119,6 +120,38 @@ void gg_engine_free(gg_engine *e)
 	cudaStreamDestroy(e->stream);
 	cudaStreamDestroy(e->copy_stream);
 	delete e;
+}
+
+/* heap_beginscan's snapshot argument (heapam.c:1573) for every scan this engine launches from now on */
+int gg_engine_set_snapshot(gg_engine *e, const gg_snapshot *snap)
+{
+	if (!e) return GG_ERR_ARG;
+	if (!snap) { e->d_snapshot = nullptr; return GG_OK; }
+	if (snap->xcnt > GG_SNAPSHOT_MAX_XIP || (snap->xcnt && !snap->xip) || (snap->clog_n && !snap->clog) || (snap->clog_base & 3))
+	{ gg_set_error("snapshot: %u xids in progress (at most %d), status range must start at a multiple of 4", snap->xcnt, GG_SNAPSHOT_MAX_XIP); return GG_ERR_ARG; }
+	if (snap->suboverflowed || snap->takenDuringRecovery || snap->haveDistribSnapshot)
+	{ gg_set_error("snapshot: subtransaction overflow, recovery and distributed snapshots are decided by the CPU scan"); return GG_ERR_UNSUPPORTED; }
+	const size_t clog_bytes = ((size_t) snap->clog_n + 3) / 4;
+	const size_t bytes = (8 + (size_t) snap->xcnt) * 4 + clog_bytes;
+	GG_CUDA(cudaSetDevice(e->device));
+	if (e->snapshot_cap < bytes)
+	{
+		GG_CUDA(cudaStreamSynchronize(e->stream));
+		cudaFree(e->snapshot_buf);
+		e->snapshot_buf = nullptr; e->snapshot_cap = 0;
+		GG_CUDA(cudaMalloc((void **) &e->snapshot_buf, (bytes + 4095) & ~(size_t) 4095));
+		e->snapshot_cap = (bytes + 4095) & ~(size_t) 4095;
+	}
+	std::vector<uint8_t> h(bytes);
+	uint32_t *w = (uint32_t *) h.data();
+	w[0] = snap->xmin; w[1] = snap->xmax; w[2] = snap->xcnt; w[3] = snap->curcid; w[4] = snap->own_xid;
+	w[5] = snap->clog_base; w[6] = snap->clog_n; w[7] = 0;
+	if (snap->xcnt) memcpy(w + 8, snap->xip, (size_t) snap->xcnt * 4);
+	if (clog_bytes) memcpy(h.data() + (8 + (size_t) snap->xcnt) * 4, snap->clog, clog_bytes);
+	GG_CUDA(cudaMemcpyAsync(e->snapshot_buf, h.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+	GG_CUDA(cudaStreamSynchronize(e->stream));        /* h is pageable and goes out of scope */
+	e->d_snapshot = e->snapshot_buf;
+	return GG_OK;
 }
 
 int gg_engine_sm_count(gg_engine *e) { return e ? e->sm_count : 0; }

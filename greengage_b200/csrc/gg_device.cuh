@@ -171,6 +171,87 @@ __device__ __forceinline__ uint32_t varsize_any(uint32_t p, bool &bad)
 	return l;
 }
 
+/* ---------------- HeapTupleSatisfiesMVCC against a snapshot (tqual.c:997-1238) ----------------
+ * The snapshot in device memory (gg_engine_set_snapshot): 8 header words
+ *     [0] xmin  [1] xmax  [2] xcnt  [3] curcid  [4] the scanning backend's own xid (0: none)  [5] clog_base  [6] clog_n
+ * then xip[xcnt], then the transaction status bits of xids clog_base .. clog_base + clog_n - 1, two per xid as pg_clog keeps
+ * them (clog.h:25-28; clog.c TransactionIdToBIndex: byte xid / 4, shift 2 * (xid % 4); clog_base is a multiple of 4).
+ * What only the server can answer raises GGP_EF_VISIBILITY and the relation stays on the CPU scan: multixact xmax,
+ * combo command ids, sub-committed status (pg_subtrans), HEAP_MOVED_*, an xid outside the status range.  Distributed
+ * snapshots (XidInMVCCSnapshot's first half, tqual.c:1547-1583) are the caller's: it passes the local snapshot only when
+ * that decides alone (haveDistribSnapshot false, or every tuple carries the *_DISTRIBUTED_SNAPSHOT_IGNORE bits).  Hint bits
+ * are not written back (SetHintBits is an optimisation of the next reader). */
+#define GG_SNAP_HDR_WORDS 8
+__device__ __forceinline__ bool xid_precedes(uint32_t a, uint32_t b)          /* TransactionIdPrecedes, transam.c:300 */
+{
+	if (a < 3 || b < 3) return a < b;
+	return (int32_t) (a - b) < 0;
+}
+/* TransactionIdDidCommit (transam.c:125 through TransactionLogFetch :52): 1 committed, 0 not (in progress, aborted, crashed), -1 unknown here */
+__device__ __forceinline__ int xid_did_commit(uint32_t xid, const uint32_t *snap)
+{
+	if (xid == 1 || xid == 2) return 1;                 /* BootstrapTransactionId, FrozenTransactionId */
+	if (xid == 0) return 0;
+	const uint32_t d = xid - snap[5];
+	if (d >= snap[6]) return -1;
+	const uint8_t *clog = (const uint8_t *) (snap + GG_SNAP_HDR_WORDS + snap[2]);
+	const int st = (clog[d >> 2] >> ((d & 3) * 2)) & 3;
+	if (st == 3) return -1;                             /* TRANSACTION_STATUS_SUB_COMMITTED: the parent decides */
+	return st == 1;
+}
+/* XidInMVCCSnapshot_Local (tqual.c:1600-1650), snapshots without subtransaction overflow */
+__device__ __forceinline__ bool xid_in_snapshot(uint32_t xid, const uint32_t *snap)
+{
+	if (xid_precedes(xid, snap[0])) return false;
+	if (!xid_precedes(xid, snap[1])) return true;
+	for (uint32_t i = 0; i < snap[2]; i++)
+		if (snap[GG_SNAP_HDR_WORDS + i] == xid) return true;
+	return false;
+}
+/* tup: shared address of the tuple header.  Returns visibility; err gets GGP_EF_VISIBILITY when the rule cannot be decided here. */
+__device__ __forceinline__ bool heap_tuple_satisfies_mvcc(uint32_t tup, uint32_t infomask, const uint32_t *snap, uint32_t &err)
+{
+	const uint32_t xmin = lds32(tup), xmax = lds32(tup + 4), cid = lds32(tup + 8);
+	const uint32_t curcid = snap[3], own = snap[4];
+	const bool locked_only = (infomask & GG_HEAP_XMAX_LOCK_ONLY) ||
+	                         (infomask & (GG_HEAP_XMAX_IS_MULTI | GG_HEAP_XMAX_EXCL_LOCK | GG_HEAP_XMAX_KEYSHR_LOCK)) == GG_HEAP_XMAX_EXCL_LOCK;
+	if (!(infomask & GG_HEAP_XMIN_COMMITTED))
+	{
+		if (infomask & GG_HEAP_XMIN_INVALID) return false;
+		if (infomask & GG_HEAP_MOVED) { err |= GGP_EF_VISIBILITY; return false; }
+		if (own && xmin == own)
+		{
+			if (infomask & GG_HEAP_COMBOCID) { err |= GGP_EF_VISIBILITY; return false; }
+			if (cid >= curcid) return false;                     /* inserted after the scan started */
+			if (infomask & GG_HEAP_XMAX_INVALID) return true;
+			if (locked_only) return true;
+			if (infomask & GG_HEAP_XMAX_IS_MULTI) { err |= GGP_EF_VISIBILITY; return false; }
+			if (xmax != own) return true;                        /* the deleting subtransaction must have aborted */
+			return cid >= curcid;                                /* deleted after / before the scan started */
+		}
+		const int c = xid_did_commit(xmin, snap);
+		if (c < 0) { err |= GGP_EF_VISIBILITY; return false; }
+		if (!c) return false;                                    /* in progress, aborted or crashed */
+	}
+	/* the inserting transaction has committed — but when? */
+	if ((infomask & GG_HEAP_XMIN_FROZEN) != GG_HEAP_XMIN_FROZEN && xid_in_snapshot(xmin, snap)) return false;
+	if (infomask & GG_HEAP_XMAX_INVALID) return true;
+	if (locked_only) return true;
+	if (infomask & GG_HEAP_XMAX_IS_MULTI) { err |= GGP_EF_VISIBILITY; return false; }
+	if (!(infomask & GG_HEAP_XMAX_COMMITTED))
+	{
+		if (own && xmax == own)
+		{
+			if (infomask & GG_HEAP_COMBOCID) { err |= GGP_EF_VISIBILITY; return false; }
+			return cid >= curcid;
+		}
+		const int c = xid_did_commit(xmax, snap);
+		if (c < 0) { err |= GGP_EF_VISIBILITY; return false; }
+		if (!c) return true;                                     /* deleter in progress, aborted or crashed */
+	}
+	return xid_in_snapshot(xmax, snap);                          /* deleter committed after the snapshot: still visible */
+}
+
 /* Per-lane view of one tuple after the attribute walk */
 struct TupleView {
 	uint32_t tp;            /* shared address of the start of user data (tuple + t_hoff) */

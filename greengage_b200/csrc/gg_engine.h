@@ -25,6 +25,9 @@ struct gg_engine {
 	size_t sort_scratch_bytes = 0;
 	std::vector<void *> groups_pool;     /* gg_groups buffers of the common size, recycled (gg_scanagg.cu) */
 	void *groups_mirror = nullptr;       /* pinned: status + records of one gg_groups_fetch */
+	uint32_t *d_snapshot = nullptr;      /* gg_engine_set_snapshot: the snapshot every scan launched from now on decides visibility with */
+	uint32_t *snapshot_buf = nullptr;    /* the allocation d_snapshot points into when a snapshot is set */
+	size_t snapshot_cap = 0;             /* its size in bytes */
 	void *motion_state = nullptr;        /* gg_motion_partition: region cursors, error flags, counters (device) */
 };
 

@@ -229,6 +229,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	prm.pages = pages;
 	prm.nblocks = nblocks;
 	prm.errflags = j->probe->d_err;
+	prm.snap = e->d_snapshot;
 	prm.counters = j->d_buildcnt;           /* the probe's counters describe the outer side only */
 	const gg_npconfig nc = gg_np_config(7, 2);
 	prm.nstage = nc.nstage;

@@ -59,6 +59,7 @@ int gg_partition_rows(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool
 	prm.pages = r->pages + first_block * GG_BLCKSZ;
 	prm.nblocks = nblocks;
 	prm.nrows = r->nrows;
+	prm.snap = e->d_snapshot;
 	prm.errflags = (uint32_t *) (d_state + nsegs);
 	prm.counters = d_state + nsegs + 1;
 	const gg_npconfig nc = gg_np_config(7, 2);

@@ -494,6 +494,7 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	prm.nrows = nrows;
 	prm.fill_inner = fill_inner ? 1 : 0;
 	prm.team = p->team;
+	prm.snap = e->d_snapshot;
 	{
 		const char *kc = getenv("GGB200_KEYCACHE");
 		prm.nokeycache = kc && atoi(kc) == 0;

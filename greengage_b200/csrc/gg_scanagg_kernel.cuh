@@ -169,6 +169,8 @@ struct ScanAggParams {
 	const gg_aocs_devcol *aocs;
 	int32_t aocs_tile_rows;
 	int nokeycache;                       /* experiments: 1 = every row looks its group up in the block table (no register cache) */
+	const uint32_t *snap;                 /* the scan's snapshot in device memory (gg_device.cuh heap_tuple_satisfies_mvcc), or
+	                                       * nullptr: visibility from hint bits only */
 	int team;                             /* > 0: consumer warps work in teams of this many warps, one page per team at a time (a
 	                                       * warp only visits its team's pages); 0: every warp visits every page and the chunks
 	                                       * are dealt round-robin across pages */
@@ -619,7 +621,7 @@ template <bool JOIN> struct SinkSel<MODE_BUILD, JOIN> { typedef BuildSink type; 
 /* Line pointer -> tuple: ItemId decode, the sanity rules of PageAddItem, the visibility fast path, header checks.
  * Returns whether the lane holds a visible tuple; dead lanes get a harmless view (the page header). */
 __device__ __forceinline__ bool heap_tuple_front(uint32_t pg, int idx, int nitems, uint32_t pd_upper, uint32_t pd_special,
-                                                 bool all_visible, uint32_t &tup, uint32_t &tuplen, bool &hasnulls, uint32_t &err)
+                                                 bool all_visible, const uint32_t *snap, uint32_t &tup, uint32_t &tuplen, bool &hasnulls, uint32_t &err)
 {
 	bool live = false;
 	tup = pg; tuplen = 64;
@@ -648,6 +650,7 @@ __device__ __forceinline__ bool heap_tuple_front(uint32_t pg, int idx, int nitem
 		/* HeapTupleSatisfiesMVCC fast path (tqual.c:1009,1119): frozen xmin + invalid xmax */
 		if ((infomask & GG_HEAP_XMIN_FROZEN) == GG_HEAP_XMIN_FROZEN && (infomask & GG_HEAP_XMAX_INVALID)) { }
 		else if ((infomask & GG_HEAP_XMIN_INVALID) && !(infomask & GG_HEAP_XMIN_COMMITTED)) live = false;
+		else if (snap) live = heap_tuple_satisfies_mvcc(tup, infomask, snap, err);     /* the full rule, against the scan's snapshot */
 		else { err |= GGP_EF_VISIBILITY; live = false; }
 	}
 	if (live && (hoff > tuplen || (hoff & 7) || hoff < 24)) { err |= GGP_EF_BADPAGE; live = false; }
@@ -1002,7 +1005,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				else
 				{
 				bool hasnulls;
-				live = heap_tuple_front(pg, idx, nitems, pd_upper, pd_special, all_visible, tup, tuplen, hasnulls, err);
+				live = heap_tuple_front(pg, idx, nitems, pd_upper, pd_special, all_visible, prm.snap, tup, tuplen, hasnulls, err);
 				const bool fast = !__any_sync(GG_FULL_MASK, hasnulls);
 				X.fast = fast;
 				X.tv.tp = pg;

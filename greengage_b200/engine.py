@@ -27,6 +27,11 @@ class Engine:
     def sm_count(self):
         return dev_lib().gg_engine_sm_count(self.h)
 
+    def set_snapshot(self, snap):
+        """the snapshot every scan launched from now on decides visibility with (capi.make_snapshot); None: hint bits only"""
+        check(dev_lib().gg_engine_set_snapshot(self.h, C.byref(snap) if snap is not None else None))
+        self._snapshot = snap
+
     def last_kernel_ms(self):
         ms = C.c_float(0)
         check(dev_lib().gg_engine_last_kernel_ms(self.h, C.byref(ms)))

@@ -75,7 +75,8 @@ class GgEState(C.Structure):
                 ("nsegs", C.c_int32), ("segindex", C.c_int32), ("transport", C.POINTER(GgMotionTransport)),
                 ("es_processed", C.c_uint64), ("interconnect", C.c_void_p),
                 ("host_pages", C.c_void_p * GG_MAX_RELATIONS), ("host_nblocks", C.c_uint64 * GG_MAX_RELATIONS),
-                ("motion_on_host", C.c_int32), ("pad", C.c_int32), ("es_operator_mem", C.c_uint64)]
+                ("motion_on_host", C.c_int32), ("pad", C.c_int32), ("es_operator_mem", C.c_uint64),
+                ("es_snapshot", C.POINTER(capi.gg_snapshot))]
 
 
 _lib = None
@@ -185,11 +186,14 @@ class PlanBuilder:
 class Executor:
     """One slice on one segment: ExecInitNode at construction, rows() drives ExecProcNode to end of stream."""
 
-    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None, interconnect=None, operator_mem=0):
+    def __init__(self, eng, pool, relations, plan, nsegs=1, segindex=0, transport=None, interconnect=None, operator_mem=0, snapshot=None):
         """relations[i]: a device-resident Relation, or (host address, nblocks) for pages in host memory, or None"""
         L = exec_lib()
         self.es = GgEState()
         self.es.es_operator_mem = int(operator_mem)
+        self._snapshot = snapshot                       # capi.make_snapshot(...): kept alive with the executor
+        if snapshot is not None:
+            self.es.es_snapshot = C.pointer(snapshot)
         self.es.engine = eng.h if hasattr(eng, "h") else eng
         self._pool = pool
         self.es.pool = C.pointer(pool)

@@ -1259,6 +1259,10 @@ GgTupleTableSlot *GgExecProcNode(GgPlanState *s)
 		if (!s->done)
 		{
 			g_err[0] = 0; g_errcode = GG_OK;
+			/* the query's snapshot reaches every scan of the slice through the engine (heap_beginscan's argument,
+			 * heapam.c:1573; EState.es_snapshot) */
+			c = gg_engine_set_snapshot(s->estate->engine, s->estate->es_snapshot);
+			if (c != GG_OK) { exec_fail(c, "%s", gg_last_error()); return NULL; }
 			failed = run_node(s);                     /* the C wrapper on the Postgres side turns a failure into ereport(ERROR) */
 		}
 		if (!failed && !s->rows_ready)

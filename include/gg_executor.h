@@ -152,6 +152,10 @@ typedef struct GgEState {
 	/* the operator's share of statement_mem in bytes (PlanStateOperatorMemKB, execnodes.h:1446): a HashJoin whose table of
 	 * the whole inner side would be larger runs as a hybrid hash join, in batches (gg_joinagg_run); 0 = no limit */
 	uint64_t es_operator_mem;
+	/* es_snapshot (execnodes.h:380): what heap_beginscan hands to HeapTupleSatisfiesMVCC.  NULL: the scans decide from hint
+	 * bits alone and refuse a relation holding a tuple that needs more (GG_ERR_VISIBILITY).  ExecProcNode gives it to the
+	 * engine before it runs the slice (gg_engine_set_snapshot). */
+	const gg_snapshot *es_snapshot;
 } GgEState;
 
 typedef struct GgPlanState GgPlanState;        /* execnodes.h PlanState */

@@ -43,8 +43,29 @@ extern "C" {
 #define GG_HEAP_XMIN_INVALID   0x0200
 #define GG_HEAP_XMIN_FROZEN    0x0300
 #define GG_HEAP_XMAX_INVALID   0x0800
+#define GG_HEAP_XMAX_COMMITTED 0x0400
+#define GG_HEAP_XMAX_IS_MULTI  0x1000
+#define GG_HEAP_XMAX_LOCK_ONLY 0x0080
+#define GG_HEAP_XMAX_EXCL_LOCK 0x0040
+#define GG_HEAP_XMAX_KEYSHR_LOCK 0x0010
+#define GG_HEAP_COMBOCID       0x0020
+#define GG_HEAP_MOVED          0xC000    /* HEAP_MOVED_OFF | HEAP_MOVED_IN: pre-9.0 VACUUM FULL leftovers */
 #define GG_HEAP_NATTS_MASK     0x07FF
 #define GG_FROZEN_XID          2         /* FrozenTransactionId, access/transam.h */
+
+/* ---- the snapshot of a scan (utils/snapshot.h:36-100 as far as tqual.c:997-1238 reads it; see gg_engine_set_snapshot) ---- */
+#define GG_SNAPSHOT_MAX_XIP 1024
+typedef struct gg_snapshot {
+	uint32_t xmin;                 /* all xids < xmin are finished */
+	uint32_t xmax;                 /* all xids >= xmax are in progress */
+	uint32_t xcnt;                 /* xids in progress at snapshot time, xmin <= xip[i] < xmax */
+	uint32_t curcid;               /* command ids >= curcid of the own transaction are invisible */
+	uint32_t own_xid;              /* GetCurrentTransactionIdIfAny() of the scanning backend; 0: none assigned */
+	uint32_t clog_base, clog_n;    /* transaction status is given for xids clog_base .. clog_base + clog_n - 1 (clog_base % 4 == 0) */
+	uint8_t  suboverflowed, takenDuringRecovery, haveDistribSnapshot, pad;      /* any of them set: GG_ERR_UNSUPPORTED */
+	const uint32_t *xip;
+	const uint8_t *clog;           /* 2 bits per xid exactly as pg_clog stores them (clog.h:25-28, clog.c:73-78) */
+} gg_snapshot;
 
 /* ---- type OIDs (src/include/catalog/pg_type.h) ---- */
 #define GG_BOOLOID       16

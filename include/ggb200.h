@@ -58,6 +58,15 @@ const char *gg_strerror(int code);
 int  gg_engine_create(int device, gg_engine **out);
 void gg_engine_free(gg_engine *e);
 int  gg_engine_sm_count(gg_engine *e);
+
+/* ---- snapshot ----
+ * The SnapshotData (utils/snapshot.h:36-100) heap_beginscan receives (heapam.c:1573), as far as HeapTupleSatisfiesMVCC
+ * (tqual.c:997-1238) reads it, plus the transaction status bits the rule asks pg_clog for.  With a snapshot set, a tuple whose
+ * hint bits do not decide alone is judged on the device by the full rule; without one such a tuple raises GG_ERR_VISIBILITY
+ * (the relation stays on the CPU scan).  Still the CPU scan's: multixact xmax, combo command ids, sub-committed status,
+ * HEAP_MOVED_*, xids outside [clog_base, clog_base + clog_n), and the three snapshot kinds flagged below. */
+/* every scan the engine launches after this call uses `snap` (copied); NULL: back to hint bits only */
+int  gg_engine_set_snapshot(gg_engine *e, const gg_snapshot *snap);
 int  gg_engine_sync(gg_engine *e);
 /* CUDA-event timing of the last *_run call on the engine's stream, in milliseconds */
 int  gg_engine_last_kernel_ms(gg_engine *e, float *ms);

@@ -66,6 +66,9 @@ int  or_heap_deform(const gg_tupdesc *desc, const uint8_t *tuple, int natts_want
 const uint8_t *or_varlena_payload(const uint8_t *datum, int *len);
 /* visibility: HeapTupleSatisfiesMVCC fast path (tqual.c:997-1140); 1 visible, 0 invisible, -1 needs clog */
 int  or_tuple_visible(const uint8_t *tuple);
+/* the full rule against a snapshot (tqual.c:997-1238); or_set_snapshot makes the scans that follow use it */
+int  or_tuple_satisfies_mvcc(const uint8_t *tuple, const gg_snapshot *snap);
+void or_set_snapshot(const gg_snapshot *snap);
 
 /* ---------------- expression evaluation (execQual.c) ---------------- */
 /* numeric values: the 128-bit integer (hi:v), scaled by 10^dscale (or_numeric.c) */

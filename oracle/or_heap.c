@@ -365,6 +365,137 @@ or_tuple_visible(const uint8_t *tup)
 	return -1;
 }
 
+/* ---- HeapTupleSatisfiesMVCC (tqual.c:997-1238) against a snapshot ----
+ * The snapshot of the scans that follow, like the one ExecutorStart leaves in es_snapshot for heap_beginscan
+ * (heapam.c:1573); NULL: hint bits only (or_tuple_visible above).  Pinned against the reference's own tqual.o + transam.o
+ * by tests/golden/mvcc_kat.json (oracle/ref_build/refwrap_tqual.c). */
+static const gg_snapshot *or_snapshot;
+
+void
+or_set_snapshot(const gg_snapshot *snap)
+{
+	or_snapshot = snap;
+}
+
+/* TransactionIdPrecedes, transam.c:300: modulo-2^32 for normal xids, plain for the three special ones */
+static int
+or_xid_precedes(uint32_t a, uint32_t b)
+{
+	if (a < 3 || b < 3)
+		return a < b;
+	return (int32_t) (a - b) < 0;
+}
+
+/* TransactionIdDidCommit, transam.c:125 via TransactionLogFetch :52-100: bootstrap and frozen xids count as
+ * committed, the invalid xid as aborted, everything else is what pg_clog says.  -1: not answerable from the bits given
+ * (outside the range, or sub-committed: transam.c:146 would ask pg_subtrans for the parent) */
+static int
+or_xid_did_commit(uint32_t xid, const gg_snapshot *snap)
+{
+	uint32_t d;
+	int st;
+
+	if (xid == 1 || xid == 2)
+		return 1;
+	if (xid == 0)
+		return 0;
+	d = xid - snap->clog_base;
+	if (d >= snap->clog_n)
+		return -1;
+	st = (snap->clog[d >> 2] >> ((d & 3) * 2)) & 3;		/* clog.c:73-78 */
+	if (st == 3)
+		return -1;
+	return st == 1;
+}
+
+/* XidInMVCCSnapshot_Local, tqual.c:1600-1650 (no subxip, not overflowed, not taken during recovery) */
+static int
+or_xid_in_snapshot(uint32_t xid, const gg_snapshot *snap)
+{
+	uint32_t i;
+
+	if (or_xid_precedes(xid, snap->xmin))
+		return 0;
+	if (!or_xid_precedes(xid, snap->xmax))				/* TransactionIdFollowsOrEquals */
+		return 1;
+	for (i = 0; i < snap->xcnt; i++)
+		if (snap->xip[i] == xid)
+			return 1;
+	return 0;
+}
+
+/* 1 visible, 0 not, -1 the rule needs the server (multixact, combo cid, moved tuples, unknown status).
+ * TransactionIdIsInProgress (procarray) and "did not commit" lead to the same answer on both the xmin and the xmax
+ * side (tqual.c:1100-1110, 1198-1209), so the status bits alone decide. */
+int
+or_tuple_satisfies_mvcc(const uint8_t *tup, const gg_snapshot *snap)
+{
+	uint32_t xmin, xmax, cid;
+	uint16_t infomask;
+	int locked_only, c;
+
+	memcpy(&xmin, tup, 4);
+	memcpy(&xmax, tup + 4, 4);
+	memcpy(&cid, tup + 8, 4);
+	memcpy(&infomask, tup + 20, 2);
+	/* HEAP_XMAX_IS_LOCKED_ONLY, htup_details.h:211 */
+	locked_only = (infomask & GG_HEAP_XMAX_LOCK_ONLY) ||
+		(infomask & (GG_HEAP_XMAX_IS_MULTI | GG_HEAP_XMAX_EXCL_LOCK | GG_HEAP_XMAX_KEYSHR_LOCK)) == GG_HEAP_XMAX_EXCL_LOCK;
+
+	if (!(infomask & GG_HEAP_XMIN_COMMITTED))				/* tqual.c:1009 */
+	{
+		if (infomask & GG_HEAP_XMIN_INVALID)				/* :1011 */
+			return 0;
+		if (infomask & GG_HEAP_MOVED)						/* :1015-1052, pre-9.0 VACUUM FULL */
+			return -1;
+		if (snap->own_xid && xmin == snap->own_xid)			/* :1053 TransactionIdIsCurrentTransactionId */
+		{
+			if (infomask & GG_HEAP_COMBOCID)
+				return -1;
+			if (cid >= snap->curcid)						/* :1055 inserted after scan started */
+				return 0;
+			if (infomask & GG_HEAP_XMAX_INVALID)			/* :1058 */
+				return 1;
+			if (locked_only)								/* :1061 */
+				return 1;
+			if (infomask & GG_HEAP_XMAX_IS_MULTI)			/* :1064 */
+				return -1;
+			if (xmax != snap->own_xid)						/* :1083 deleting subtransaction aborted */
+				return 1;
+			return cid >= snap->curcid;						/* :1097-1100 */
+		}
+		c = or_xid_did_commit(xmin, snap);					/* :1102-1113 */
+		if (c < 0)
+			return -1;
+		if (!c)
+			return 0;
+	}
+	/* :1120-1135 the inserting transaction committed: before the snapshot? */
+	if ((infomask & GG_HEAP_XMIN_FROZEN) != GG_HEAP_XMIN_FROZEN && or_xid_in_snapshot(xmin, snap))
+		return 0;
+	if (infomask & GG_HEAP_XMAX_INVALID)					/* :1137 */
+		return 1;
+	if (locked_only)										/* :1140 */
+		return 1;
+	if (infomask & GG_HEAP_XMAX_IS_MULTI)					/* :1143 */
+		return -1;
+	if (!(infomask & GG_HEAP_XMAX_COMMITTED))				/* :1186 */
+	{
+		if (snap->own_xid && xmax == snap->own_xid)			/* :1188 */
+		{
+			if (infomask & GG_HEAP_COMBOCID)
+				return -1;
+			return cid >= snap->curcid;
+		}
+		c = or_xid_did_commit(xmax, snap);					/* :1196-1209 */
+		if (c < 0)
+			return -1;
+		if (!c)
+			return 1;
+	}
+	return or_xid_in_snapshot(xmax, snap);					/* :1219-1233 */
+}
+
 /* ---- forward page-mode scan: heapgetpage (heapam.c:312-463) + heapgettup_pagemode (:767-1006) ---- */
 
 void
@@ -402,6 +533,8 @@ or_scan_getpage(or_heapscan *s, uint64_t blk)
 		{
 			int v = or_tuple_visible(dp + (lp & 0x7FFF));
 
+			if (v < 0 && or_snapshot)
+				v = or_tuple_satisfies_mvcc(dp + (lp & 0x7FFF), or_snapshot);
 			if (v < 0)
 				s->error = OR_ERR_VISIBILITY;
 			if (v <= 0)

@@ -55,6 +55,8 @@ def lib():
         L.or_jump_consistent_hash.argtypes = [u64, i32]
         L.or_cdbhash_reduce.argtypes = [u32, i32]
         L.or_route_datums.argtypes = [C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), i32, i32]
+        L.or_tuple_satisfies_mvcc.argtypes = [C.c_char_p, C.POINTER(capi.gg_snapshot)]
+        L.or_set_snapshot.argtypes = [C.POINTER(capi.gg_snapshot)]
         L.or_heap_form_tuple.argtypes = [C.POINTER(capi.gg_tupdesc), C.POINTER(i64), C.POINTER(i32),
                                          C.POINTER(C.c_uint8), vp, i32]
         L.or_heap_deform.argtypes = [C.POINTER(capi.gg_tupdesc), vp, i32, C.POINTER(i64), C.POINTER(C.c_uint8)]
@@ -415,3 +417,18 @@ def aocs_seqscan_agg(scan, agg, pool, colfiles, nrows, checksum=True, cap=4096):
     _chk(lib().or_aocs_seqscan_agg(C.byref(scan), C.byref(agg), C.byref(pool), ptrs, sizes, int(checksum), nrows, out, cap,
                                    C.byref(n), C.byref(sc), C.byref(ps)))
     return [out[i] for i in range(n.value)], sc.value, ps.value
+
+
+_snapshot_keep = None
+
+
+def set_snapshot(snap):
+    """the snapshot of the scans that follow (capi.make_snapshot), None: hint bits only"""
+    global _snapshot_keep
+    _snapshot_keep = snap
+    lib().or_set_snapshot(C.byref(snap) if snap is not None else None)
+
+
+def tuple_satisfies_mvcc(header, snap):
+    """1 visible, 0 not, -1 undecidable without the server"""
+    return lib().or_tuple_satisfies_mvcc(bytes(header), C.byref(snap))

@@ -334,3 +334,47 @@ def gp_hashagg_case():
         q = p.boolop(capi.E_AND, q, cond)
     agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [grp], [(capi.AGG_SUM_INT4, v)])
     return desc, po.build_pages(desc, rows), capi.make_scan(desc, q), agg, p.pool, {"hi": 9, "there": 6}
+
+
+# (xmin, xmax, visibility bits of t_infomask) patterns over the xids of mvcc_snapshot() below, and what HeapTupleSatisfiesMVCC
+# (tqual.c:997) answers for each: frozen; committed before the snapshot; aborted; in progress; in the snapshot's xip; committed
+# after xmin but not in xip; deleted by a committed-after-snapshot-start xact not in xip (gone); deleted by an xip member (still
+# there); deleted by an aborted xact; deleted, hinted committed
+MVCC_PATTERNS = [(2, 0, 0x0B00, 1), (1001, 0, 0x0800, 1), (1002, 0, 0x0800, 0), (1003, 0, 0x0800, 0), (1004, 0, 0x0800, 0), (1005, 0, 0x0800, 1),
+                 (1001, 1005, 0x0000, 0), (1001, 1004, 0x0000, 1), (1001, 1002, 0x0000, 1), (1001, 1001, 0x0500, 0)]
+
+
+def mvcc_snapshot():
+    """xids 1001 committed, 1002 aborted, 1003 in progress, 1004 committed but in progress at snapshot time (xip), 1005 committed"""
+    from greengage_b200 import capi
+    base, clog = 1000, bytearray(16)
+    for x, st in {1001: 1, 1002: 2, 1003: 0, 1004: 1, 1005: 1}.items():
+        clog[(x - base) >> 2] |= st << (((x - base) & 3) * 2)
+    return capi.make_snapshot(1004, 1006, [1004], 0, 0, base, bytes(clog))
+
+
+def stamp_visibility(pages, all_visible_every=0):
+    """Rewrite xmin / xmax / hint bits of every tuple with MVCC_PATTERNS in turn and clear PD_ALL_VISIBLE (kept on every
+    all_visible_every-th page, where heapgetpage then skips the rule, heapam.c:391).  Returns (pages, [visible per tuple])."""
+    import struct
+    import numpy as np
+    pg = np.frombuffer(pages, dtype=np.uint8).copy() if not isinstance(pages, np.ndarray) else pages.copy()
+    vis, k = [], 0
+    for b in range(len(pg) // 32768):
+        page = pg[b * 32768:(b + 1) * 32768]
+        keep = all_visible_every and b % all_visible_every == 0
+        flags = struct.unpack("<H", page[10:12].tobytes())[0]
+        page[10:12] = np.frombuffer(struct.pack("<H", (flags | 0x0004) if keep else (flags & ~0x0004)), dtype=np.uint8)
+        lower = struct.unpack("<H", page[12:14].tobytes())[0]
+        for i in range((lower - 24) // 4):
+            lp = struct.unpack("<I", page[24 + 4 * i:28 + 4 * i].tobytes())[0]
+            if (lp >> 15) & 3 != 1:
+                continue
+            off = lp & 0x7FFF
+            xmin, xmax, mask, v = MVCC_PATTERNS[k % len(MVCC_PATTERNS)]
+            page[off:off + 8] = np.frombuffer(struct.pack("<II", xmin, xmax), dtype=np.uint8)
+            im = struct.unpack("<H", page[off + 20:off + 22].tobytes())[0]
+            page[off + 20:off + 22] = np.frombuffer(struct.pack("<H", (im & 0x000F) | mask), dtype=np.uint8)
+            vis.append(1 if keep else v)
+            k += 1
+    return pg, vis

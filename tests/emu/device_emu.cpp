@@ -261,3 +261,16 @@ extern "C" int emu_walk(const gg_tupdesc *desc, const uint8_t *tuple, int len, i
 	}
 	return GG_OK;
 }
+
+/* the device's HeapTupleSatisfiesMVCC (gg_device.cuh) over one tuple header and a snapshot in the device layout:
+ * 1 visible, 0 not, -1 GGP_EF_VISIBILITY raised */
+extern "C" int emu_tuple_satisfies_mvcc(const uint8_t *header, const uint32_t *snap_words)
+{
+	memcpy(gg_emu_smem, header, 24);
+	uint16_t infomask;
+	memcpy(&infomask, header + 20, 2);
+	uint32_t err = 0;
+	const bool vis = heap_tuple_satisfies_mvcc(0, infomask, snap_words, err);
+	if (err & GGP_EF_VISIBILITY) return -1;
+	return vis ? 1 : 0;
+}

@@ -23,6 +23,8 @@
                     tupser.o / tupchunklist.o (SerializeTuple, both the MemTuple and the heap-tuple form, several chunk sizes)
   numeric_kat.json  the reference's numeric.o: text -> on-disk digits (numeric_in), numeric_add / _sub / _mul results with their
                     display scales, numeric_cmp, and sum / avg (a fold of numeric_add; numeric_div(sum, N) as numeric_avg does)
+  mvcc_kat.json     the reference's tqual.o + transam.o: HeapTupleSatisfiesMVCC of tuple headers against snapshots and
+                    transaction status tables (oracle/ref_build/refwrap_tqual.c)
   join_j1j2.json    J1_TBL / J2_TBL of sql/join.sql and the golden inner / left / right / full equi-join tables of expected/join.out
 """
 import ctypes as C
@@ -278,6 +280,71 @@ def numeric_kat():
         out["sumavg"].append({"values": vals, "sum": acc, "avg": txt.value.decode()})
     json.dump(out, open(os.path.join(HERE, "numeric_kat.json"), "w"))
     print("numeric_kat.json", {k: len(v) for k, v in out.items()})
+
+
+def mvcc_kat():
+    """HeapTupleSatisfiesMVCC out of the reference's tqual.o + transam.o (oracle/ref_build/refwrap_tqual.c): tuple headers with
+    every combination of the hint and lock bits the rule reads, xmin / xmax drawn around the snapshot's xmin, xmax and xip
+    (one xid universe crosses the 2^32 wrap), the scanning backend's own xid with command ids around curcid, and a random
+    commit / abort / in-progress status per xid.  `unsupported` holds the headers the device refuses (multixact, combo cid,
+    moved tuples, sub-committed or out-of-range status): no reference answer is recorded for those."""
+    rng = random.Random(20260925)
+    R.ref_heap_satisfies_mvcc.restype = C.c_int
+    R.ref_heap_satisfies_mvcc.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p]
+    R.ref_tqual_flush_cache.argtypes = [C.c_uint32]
+    XC, XI, AC, AI, MULTI, LOCK, EXCL, KEYSHR, COMBO, MOVED_OFF, MOVED_IN = 0x100, 0x200, 0x400, 0x800, 0x1000, 0x80, 0x40, 0x10, 0x20, 0x4000, 0x8000
+    snaps, cases, unsupported = [], [], []
+    for si in range(48):
+        base = 0xFFFFFFE0 if si % 6 == 5 else 4 * rng.randint(1, 10 ** 6)
+        n = 64
+        xid = lambda d: (base + d) & 0xFFFFFFFF
+        ok = [d for d in range(n) if xid(d) >= 3]
+        status = [rng.choice([0, 1, 1, 1, 2]) for _ in range(n)]
+        lo = rng.randint(8, 30)
+        hi = rng.randint(lo, 56)
+        xip_d = sorted(rng.sample([d for d in range(lo, hi) if d in ok], min(rng.randint(0, 6), len([d for d in range(lo, hi) if d in ok])))) if hi > lo else []
+        own_d = rng.choice([None, None] + [d for d in ok if d >= lo])
+        if own_d is not None:
+            status[own_d] = 0
+        clog = bytearray((n + 3) // 4)
+        for d, st in enumerate(status):
+            clog[d >> 2] |= st << ((d & 3) * 2)
+        snap = {"xmin": xid(lo) if xid(lo) >= 3 else 3, "xmax": xid(hi) if xid(hi) >= 3 else 3, "xip": [xid(d) for d in xip_d], "curcid": rng.randint(0, 6),
+                "own_xid": xid(own_d) if own_d is not None else 0, "clog_base": base, "clog_n": n, "clog": bytes(clog).hex()}
+        snaps.append(snap)
+        xip_arr = (C.c_uint32 * max(1, len(snap["xip"])))(*snap["xip"])
+        pick = lambda: rng.choice([xid(rng.choice(ok)), xid(rng.choice(ok)), snap["own_xid"] or xid(rng.choice(ok)), 2, 0, snap["xmin"], snap["xmax"]] + snap["xip"])
+        for _ in range(70):
+            infomask = 0x0002
+            for bit, pr in ((XC, 0.35), (XI, 0.2), (AC, 0.3), (AI, 0.35), (LOCK, 0.08), (EXCL, 0.12), (KEYSHR, 0.08)):
+                if rng.random() < pr:
+                    infomask |= bit
+            xmin, xmax, cid = pick(), pick(), rng.randint(0, 7)
+            hdr = struct.pack("<IIIHHHHHB", xmin, xmax, cid, 0, 0, 1, 8, infomask, 24) + b"\0"
+            R.ref_tqual_flush_cache(0x7FFFFFF0)
+            vis = R.ref_heap_satisfies_mvcc(hdr, snap["xmin"], snap["xmax"], len(snap["xip"]), xip_arr, snap["curcid"], snap["own_xid"], base, n, bytes(clog))
+            cases.append([si, infomask, xmin, xmax, cid, vis])
+        for _ in range(8):
+            infomask = 0x0002 | rng.choice([0, XC, AC, XC | AC])
+            kind = rng.choice(["multi", "combo", "moved", "range"])
+            xmin, xmax, cid = xid(rng.choice(ok)), xid(rng.choice(ok)), 1
+            if kind == "multi":
+                infomask = (infomask | MULTI) & ~(AI | LOCK)
+            elif kind == "combo":
+                if not snap["own_xid"]:
+                    continue
+                infomask = (infomask | COMBO) & ~XC
+                xmin = snap["own_xid"]
+            elif kind == "moved":
+                infomask = (infomask | rng.choice([MOVED_OFF, MOVED_IN])) & ~XC
+            elif kind == "range":
+                infomask &= ~XC
+                xmin = (base + n + rng.randint(0, 1000)) & 0xFFFFFFFF
+                if xmin < 3 or xmin == snap["own_xid"]:
+                    continue
+            unsupported.append([si, infomask, xmin, xmax, cid, kind])
+    json.dump({"snapshots": snaps, "cases": cases, "unsupported": unsupported}, open(os.path.join(HERE, "mvcc_kat.json"), "w"))
+    print("mvcc_kat.json", len(snaps), "snapshots,", len(cases), "cases,", sum(c[5] for c in cases), "visible,", len(unsupported), "unsupported")
 
 
 def float_kat():
@@ -621,3 +688,4 @@ if __name__ == "__main__":
     aocs_kat()
     memtuple_kat()
     numeric_kat()
+    mvcc_kat()

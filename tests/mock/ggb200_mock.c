@@ -166,6 +166,7 @@ int gg_motion_partition(gg_engine *e, const gg_scan *scan, const gg_exprpool *po
 { (void) e; (void) scan; (void) pool; (void) hk; (void) nk; (void) pl; (void) np; (void) nsegs; (void) r; (void) fb; (void) nb; (void) out; (void) cap; (void) hc; (void) ho; return unsupported(); }
 int gg_sort_datumrows(gg_engine *e, const gg_sortkey *keys, int nkeys, int ncols, const void *rows, uint64_t n, void *out, uint64_t *nlive, int *passes)
 { (void) e; (void) keys; (void) nkeys; (void) ncols; (void) rows; (void) n; (void) out; (void) nlive; (void) passes; return unsupported(); }
+int gg_engine_set_snapshot(gg_engine *e, const gg_snapshot *s) { (void) e; or_set_snapshot(s); return GG_OK; }   /* the oracle's scans stand in for the device's */
 int gg_relation_count_rows(gg_relation *r, uint64_t *n) { (void) r; (void) n; return unsupported(); }
 int gg_scanagg_scan_kernel_ms(gg_scanagg *p, float *ms, int *launches) { (void) p; if (ms) *ms = 0; if (launches) *launches = 0; return GG_OK; }
 int gg_scanagg_variant(gg_scanagg *p) { (void) p; return -1; }

@@ -169,3 +169,31 @@ def test_a_truncated_stream_is_refused(mock):
     assert mock.GgExecRecvTupleChunks(motion, stream[:-4], len(stream) - 4) != 0        # no end-of-stream chunk
     assert mock.GgExecRecvTupleChunks(motion, stream[:50], 50) != 0
     x.end()
+
+
+def test_es_snapshot_is_handed_to_the_scans(mock):
+    """EState.es_snapshot -> gg_engine_set_snapshot before the slice runs (the stand-in device library scans with the oracle's
+    HeapTupleSatisfiesMVCC); without it the same pages are refused with the visibility code"""
+    from _util import mvcc_snapshot, stamp_visibility
+    pages, _, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 20_000, seed=2), nthreads=1)
+    pg, vis = stamp_visibility(pages, all_visible_every=3)
+    scan, agg, pool = tpch.q1_plan(capi.TAB_LINEITEM_NARROW)
+    snap = mvcc_snapshot()
+    po.set_snapshot(snap)
+    try:
+        want, wsc, _ = po.seqscan_agg(scan, agg, pool, pg)
+    finally:
+        po.set_snapshot(None)
+    assert wsc == sum(vis)
+    eng = type("E", (), {"h": C.c_void_p(mock.mock_engine())})
+    b = ex.PlanBuilder()
+    rel = MockRel(mock, pg)
+    x = ex.Executor(eng, pool, [rel], b.agg(b.seqscan(0, scan.desc, scan.qual), agg), snapshot=snap)
+    rows = x.rows()
+    x.end()
+    assert sorted(v[-1] for v, nl, ty, ln in rows) == sorted(r.agg[7].i for r in want)
+    x = ex.Executor(eng, pool, [rel], b.agg(b.seqscan(0, scan.desc, scan.qual), agg))
+    with pytest.raises(ex.ExecError) as e:
+        x.rows()
+    x.end()
+    assert e.value.code == -7

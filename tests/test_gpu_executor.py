@@ -272,3 +272,40 @@ def test_sort_over_a_row_producing_seqscan_stays_on_the_device(eng):
         x.end()
         x0.end()
         rel.free()
+
+
+def test_es_snapshot_reaches_the_scans_of_the_slice(eng):
+    """EState.es_snapshot -> heap_beginscan -> HeapTupleSatisfiesMVCC (execMain.c / heapam.c:1573 / tqual.c:997): the join's
+    two scans both judge their tuples against the query's snapshot"""
+    from _util import mvcc_snapshot, stamp_visibility
+    from greengage_b200.engine import Relation
+    li, _, nli = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_NARROW, 40_000, norders=10_000, seed=4))
+    od, _, nod = tpch.synth_generate(tpch.synth_spec(capi.TAB_ORDERS, 10_000, seed=4))
+    li, vli = stamp_visibility(li, all_visible_every=5)
+    od, vod = stamp_visibility(od)
+    outer, inner, hj, agg, pool = tpch.join_plan(capi.TAB_LINEITEM_NARROW, "survey", capi.JOIN_INNER)
+    snap = mvcc_snapshot()
+    po.set_snapshot(snap)
+    try:
+        want, wj = po.hashjoin_agg(outer, inner, hj, agg, pool, li, od)
+    finally:
+        po.set_snapshot(None)
+    assert 0 < wj < sum(vli)
+    rl, ro = Relation(eng, host_pages=li), Relation(eng, host_pages=od)
+    b = ex.PlanBuilder()
+    plan = b.agg(b.hashjoin(b.seqscan(0, outer.desc, outer.qual), b.hash(b.seqscan(1, inner.desc, inner.qual)), hj), agg)
+    x = ex.Executor(eng, pool, [rl, ro], plan, snapshot=snap)
+    try:
+        rows = x.rows()
+        assert len(rows) == 1 and rows[0][0][0] == wj == want[0].agg[0].i
+        assert rows[0][0][1] == want[0].agg[1].i
+    finally:
+        x.end()
+    x = ex.Executor(eng, pool, [rl, ro], plan)                  # no snapshot: the relation is not the GPU's to scan
+    try:
+        with pytest.raises(ex.ExecError) as e:
+            x.rows()
+        assert e.value.code == -7
+    finally:
+        x.end()
+        rl.free(); ro.free()

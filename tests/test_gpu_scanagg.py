@@ -213,6 +213,36 @@ def test_visibility_rules(eng):
         po.seqscan_agg(scan, agg, pool, pg3)
 
 
+def test_scan_against_a_snapshot(eng):
+    """HeapTupleSatisfiesMVCC on the device (tqual.c:997-1238; tests/test_mvcc.py pins the rule to the reference's tqual.o):
+    committed / aborted / in-progress inserters and deleters around a snapshot, all-visible pages in between.  Every kernel
+    variant and the join / Motion kernels share the front end; here: the specialised, the run-time compiled and the interpreter
+    scan over wide and narrow pages."""
+    from _util import mvcc_snapshot, stamp_visibility
+    snap = mvcc_snapshot()
+    for table in (capi.TAB_LINEITEM_NARROW, capi.TAB_LINEITEM_WIDE):
+        pages, nb, nr = tpch.synth_generate(tpch.synth_spec(table, 60_000, seed=9))
+        pg, vis = stamp_visibility(pages, all_visible_every=4)
+        scan, agg, pool = tpch.q1_plan(table)
+        po.set_snapshot(snap)
+        try:
+            want, wsc, wps = po.seqscan_agg(scan, agg, pool, pg)
+        finally:
+            po.set_snapshot(None)
+        assert wsc == sum(vis) and 0 < wsc < nr
+        eng.set_snapshot(snap)
+        try:
+            for variant in ("specialised-priv", "nvrtc-priv", "interp-priv"):
+                rows, sc, ps, _ = gpu_scanagg(eng, scan, agg, pool, pg, variant)
+                assert (sc, ps) == (wsc, wps), variant
+                assert_aggrows_match(rows, want, agg)
+        finally:
+            eng.set_snapshot(None)
+        with pytest.raises(capi.GGError) as e:                 # the same pages without a snapshot: refused, not guessed
+            gpu_scanagg(eng, scan, agg, pool, pg)
+        assert e.value.code == -7
+
+
 def test_more_groups_than_private_accumulators_hold(eng):
     """7 x 3 groups: the private-accumulator kernel overflows and the input is replayed on the transposed kernel."""
     pages, nb, nr = tpch.synth_generate(tpch.synth_spec(capi.TAB_LINEITEM_WIDE, 120000, seed=5))
