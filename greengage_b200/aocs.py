@@ -95,10 +95,14 @@ def write_column(att, values, nulls=None, blocksize=DEFAULT_BLOCKSIZE, checksum=
             b = v.encode() if isinstance(v, str) else bytes(v)
             buf = C.create_string_buffer(b, len(b))
             rc = L.gg_aocs_writer_put(w, C.addressof(buf), len(b), 0)
-        elif att.atttypid == capi.FLOAT8OID:
-            rc = L.gg_aocs_writer_put(w, C.c_int64.from_buffer_copy(C.c_double(float(v))).value, 0, 0)
         else:
-            rc = L.gg_aocs_writer_put(w, int(v), 0, 0)
+            word = C.c_int64.from_buffer_copy(C.c_double(float(v))).value if att.atttypid == capi.FLOAT8OID else int(v)
+            if att.attbyval:
+                rc = L.gg_aocs_writer_put(w, word, 0, 0)
+            else:
+                # fixed-width by-reference attribute: the writer takes a pointer to attlen bytes
+                buf = C.create_string_buffer((word & (2**64 - 1)).to_bytes(8, "little"), 8)
+                rc = L.gg_aocs_writer_put(w, C.addressof(buf), 0, 0)
         if rc:
             break
     nbytes = C.c_int64(0)
@@ -176,9 +180,11 @@ class DeviceColumns:
     files: {attribute number: uint8 array}.  The loader work (checksums, directory, tile plan) runs on the host
     (libgghost.so); the decoding on the device (gg_aocs_decode_rows).  Fails loudly without a GPU like everything else."""
 
-    def __init__(self, eng, desc, cols, files, checksum=True, tile_rows=1024, pinned=False):
+    def __init__(self, eng, desc, cols, files, checksum=True, tile_rows=1024, pinned=False, file_shift=0):
         """pinned: stage the arena in pinned host memory and keep it, so that upload() can repeat the host -> device copy
-        (the end-to-end measurement of bench.py)"""
+        (the end-to-end measurement of bench.py).  Column files start on 16-byte boundaries of the arena, which is what the
+        fused scan's bulk copies want; file_shift = 8 puts them 8 bytes off (tests: the scan then reads those files value by
+        value and must give the same answer)."""
         from concurrent.futures import ThreadPoolExecutor
         from .engine import Relation
         self.eng, self.cols, self.tile_rows = eng, list(cols), tile_rows
@@ -203,9 +209,11 @@ class DeviceColumns:
             self.nrows = nrows
             entry = {"kind": KIND_OF_TYPE[att.atttypid], "nblocks": len(d)}
             for name, arr in (("file", f), ("dir", d.view(np.uint8).reshape(-1)), ("tiles", t.view(np.uint8).reshape(-1))):
-                entry[name] = off
-                parts.append((off, arr))
-                off += _pad16(arr.size + 16)              # 16 bytes of slack: 8-byte loads at the tail of a bitmap / value area
+                at = off + (file_shift if name == "file" else 0)
+                entry[name] = at
+                parts.append((at, arr))
+                off += _pad16(arr.size + 16 + file_shift)     # 16 bytes of slack: 8-byte loads at the tail of a bitmap / value area,
+                                                              # bulk copies rounded out to 16 bytes
             layout.append(entry)
         self.bytes_in = sum(np.ascontiguousarray(files[c]).size for c in self.cols)
         nb = (off + capi.GG_BLCKSZ - 1) // capi.GG_BLCKSZ

@@ -97,8 +97,23 @@ def build_host(force=False):
     return out
 
 
+def build_tools(force=False):
+    """build/gather_peak: the random-access rates of this GPU (scripts/gather_peak.cu) that the join / hash-aggregate rooflines
+    of bench.py are held against — a measurement tool, not part of the libraries"""
+    src = os.path.join(ROOT, "scripts", "gather_peak.cu")
+    out = os.path.join(BUILD, "gather_peak")
+    os.makedirs(BUILD, exist_ok=True)
+    if force or _newer(out, [src]):
+        subprocess.check_call([NVCC, "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Wno-deprecated-gpu-targets",
+                               "-o", out + ".tmp", src])
+        os.replace(out + ".tmp", out)
+    return out
+
+
 def build_all(verbose=False, force=False):
-    return build_device(verbose, force), build_host(force), build_exec(force)
+    res = build_device(verbose, force), build_host(force), build_exec(force)
+    build_tools(force)
+    return res
 
 
 if __name__ == "__main__":

@@ -25,6 +25,8 @@ static inline gg_npconfig gg_np_config(int ncons, int nstage)
 	int a, b, t = 0, k = 2;
 	if (env && sscanf(env, "%d,%d,%d,%d", &a, &b, &t, &k) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && t >= 0 && t <= a && k >= 1 && k <= 4)
 	{ c.ncons = a; c.nstage = b; c.team = t; c.ctas = k; c.forced = true; }
+	/* at most one team per ring slot (a team's pages arrive on its own barrier set, BlockTable::teamfull) */
+	if (c.team > 0 && c.ncons / c.team > c.nstage) c.ncons = c.team * c.nstage;
 	return c;
 }
 
@@ -75,6 +77,7 @@ struct gg_scanagg {
 	/* inputs of the current accumulation, kept so that a group-capacity overflow can be replayed on a wider variant */
 	struct Fed { const uint8_t *dev; const void *host; uint64_t nblocks; uint64_t nrows; bool fill; int32_t tile_rows; };   /* tile_rows > 0: dev = the column descriptors of an AOCS feed */
 	gg_aocs_devcol *d_aocs = nullptr;       /* device copy of the column descriptors of gg_scanagg_run_aocs */
+	int32_t aocs_unit_rows = 0;             /* rows of every projected column staged per ring slot (set by gg_scanagg_run_aocs) */
 	std::vector<Fed> fed;
 	bool has_state = false;
 	/* set by a batched join: how to feed the inputs again (its batches, each with its own hash table) when fetch has to

@@ -334,8 +334,8 @@ static int scanagg_configure(gg_scanagg *p)
 			if (ncons < 15) { int w3 = fit(3, 16); if (w3 >= ncons + 3) { p->nstage = 3; ncons = w3; } }
 		}
 		{
-			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages[,team]" for experiments */
-			int a, b, c = 0;
+			const char *cfg = getenv("GGB200_PRIV_CONFIG");     /* "conswarps,stages[,team[,ctas]]" for experiments */
+			int a, b, c = 0, d = 1;
 			p->team = 0;
 			/* Teams (gg_scanagg_kernel.cuh): sparse pages — every chunk of a page gets its own warp, the teams work on different
 			 * pages of the ring.  The team must cover the fullest page (a warp with two chunks holds its whole team back): the
@@ -355,7 +355,8 @@ static int scanagg_configure(gg_scanagg *p)
 					if (st >= nteams && fit(st, want) >= want) { ncons = want; p->nstage = st; p->team = ts; }
 				}
 			}
-			if (cfg && sscanf(cfg, "%d,%d,%d", &a, &b, &c) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && c >= 0 && c <= a) { ncons = a; p->nstage = b; p->team = c; }
+			if (cfg && sscanf(cfg, "%d,%d,%d,%d", &a, &b, &c, &d) >= 2 && a >= 1 && a <= 30 && b >= 2 && b <= 6 && c >= 0 && c <= a && d >= 1 && d <= 2)
+			{ ncons = a; p->nstage = b; p->team = c; p->ctas_per_sm = d; }
 			/* a team waits for ITS page's phase of a ring slot; an mbarrier tells the current phase from the previous one only,
 			 * so no two teams may be queued on one slot: at most as many teams as stages */
 			if (p->team > 0 && ncons / p->team > p->nstage) ncons = p->team * p->nstage;
@@ -364,8 +365,10 @@ static int scanagg_configure(gg_scanagg *p)
 		const int NT = ncons * 32;
 		size_t fixed = (size_t) p->nstage * GG_BLCKSZ + (size_t) p->nstage * 16 + sizeof(BlockTable) + 16 +
 		               (size_t) ncons * p->scratch_per_warp + 16;
-		if (fixed + (size_t) NT * (8 * nslots + 4) > e->smem_optin) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
-		int gcap = (int) ((e->smem_optin - fixed) / ((size_t) NT * (8 * nslots + 4)));
+		/* two blocks per SM (experiments: more warps in flight for the latency-bound probe): each gets half, 1 KB reserved per block */
+		const size_t budget = p->ctas_per_sm > 1 ? (e->smem_optin + 1024) / (size_t) p->ctas_per_sm - 1024 : e->smem_optin;
+		if (fixed + (size_t) NT * (8 * nslots + 4) > budget) { gg_set_error("plan needs too much shared memory"); return GG_ERR_UNSUPPORTED; }
+		int gcap = (int) ((budget - fixed) / ((size_t) NT * (8 * nslots + 4)));
 		if (gcap > GGP_FAST_GROUPS) gcap = GGP_FAST_GROUPS;
 		if (p->regslots > 0 && gcap > GG_REG_GROUPS) gcap = GG_REG_GROUPS;
 		p->gcap = gcap;
@@ -404,7 +407,7 @@ static int scanagg_configure(gg_scanagg *p)
 	{
 		char jmsg[512];
 		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, p->is_join ? p->join_probe_pc : -1, 0,
-		                        p->mode != MODE_PRIV && p->np_forced ? p->ctas_per_sm : 0);
+		                        (p->mode != MODE_PRIV && p->np_forced) || (p->mode == MODE_PRIV && p->ctas_per_sm > 1) ? p->ctas_per_sm : 0);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
 		if (!p->jit && p->mode != MODE_PRIV && p->threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		if (p->jit) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
@@ -418,7 +421,7 @@ static int scanagg_configure(gg_scanagg *p)
 	{
 		char jmsg[512];
 		p->jit = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, -1, p->regslots,
-		                        p->mode != MODE_PRIV && p->np_forced ? p->ctas_per_sm : 0);
+		                        (p->mode != MODE_PRIV && p->np_forced) || (p->mode == MODE_PRIV && p->ctas_per_sm > 1) ? p->ctas_per_sm : 0);
 		if (!p->jit && getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: interpreter kernel in use (%s)\n", jmsg);
 		if (!p->jit && p->mode != MODE_PRIV && p->threads != 256) { gg_set_error("GGB200_NP_CONFIG needs the run-time specialised kernel: %s", jmsg); return GG_ERR_UNSUPPORTED; }
 		if (!p->jit && p->regslots > 0)
@@ -501,6 +504,13 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	}
 	prm.aocs = aocs_tile_rows > 0 ? (const gg_aocs_devcol *) dev_pages : nullptr;
 	prm.aocs_tile_rows = aocs_tile_rows;
+	prm.aocs_unit_rows = 0;
+	if (aocs_tile_rows > 0)
+	{
+		/* the kernel's unit of work is a staging unit, not a tile of the plan (the caller counts tiles) */
+		prm.aocs_unit_rows = p->aocs_unit_rows;
+		prm.nblocks = (nrows + (uint64_t) p->aocs_unit_rows - 1) / (uint64_t) p->aocs_unit_rows;
+	}
 	prm.ha = p->ha;
 	if (p->kev_used == p->kev.size())
 	{
@@ -708,6 +718,21 @@ int gg_scanagg_run_aocs(gg_scanagg *p, const struct gg_aocs_devcol *cols, int nc
 	for (int c = 0; c < ncols; c++)
 		if (!cols[c].file || !cols[c].dir || !cols[c].tiles || cols[c].nblocks < 1 || cols[c].kind < GG_AOCS_K_W8 || cols[c].kind > GG_AOCS_K_TEXT)
 		{ gg_set_error("AOCS column %d: incomplete descriptor", c); return GG_ERR_ARG; }
+	{
+		/* Rows per staging unit: the unit's values of every projected column share one 32 KB ring slot behind the 1.5 KB of run
+		 * records (GG_AOCS_DATA_OFF), each column's range rounded out to 16 bytes and, where it crosses storage blocks, with the
+		 * block headers in between (a block of the default 32 KB holds >= 1 800 values of these widths, so a unit crosses few).
+		 * Strings are counted at the 9 bytes of the longest value the scan packs; a column that does not fit after all is read
+		 * row by row, so this is a matter of speed only. */
+		int rowbytes = 0;
+		for (int c = 0; c < ncols; c++)
+			rowbytes += cols[c].kind == GG_AOCS_K_W8 ? 8 : cols[c].kind == GG_AOCS_K_I4 ? 4 : cols[c].kind == GG_AOCS_K_I2 ? 2 : cols[c].kind == GG_AOCS_K_B1 ? 1 : 9;
+		int ur = (GG_BLCKSZ - 32 * 48 - ncols * (32 + 3 * 64)) / rowbytes;
+		ur &= ~31;
+		if (ur > 1024) ur = 1024;
+		if (ur < 32) ur = 32;
+		p->aocs_unit_rows = ur;
+	}
 	if (!p->d_aocs) GG_CUDA(cudaMalloc((void **) &p->d_aocs, sizeof(gg_aocs_devcol) * GG_MAX_ATTS));
 	GG_CUDA(cudaMemcpyAsync(p->d_aocs, cols, sizeof(gg_aocs_devcol) * (size_t) ncols, cudaMemcpyHostToDevice, e->stream));
 	if (nrows == 0) return GG_OK;

@@ -113,6 +113,19 @@ struct MotionOut {
 };
 #define GG_ROW_DEAD 0x8000000000000000ull  /* datum rows: mask word bit 63 = not a row (skipped by every consumer) */
 
+/* Column files staged in a ring slot (the producer of an AOCS scan writes this, the consumers read it): the slot starts with
+ * one 48-byte record per projected column slot, the copied byte ranges follow from GG_AOCS_DATA_OFF.  A unit's rows of one
+ * column lie in at most four runs (one per storage block touched): run k holds the unit's rows [cum[k-1], cum[k]) at
+ * base + rel[k] + (row - cum[k-1]) * stride[k]. */
+#define GG_AOCS_META_BYTES  48
+#define GG_AOCS_META_CUM    0        /* u32[4]: rows of the unit up to and including run k (0xFFFFFFFF: no such run) */
+#define GG_AOCS_META_REL    16       /* u32[4]: byte offset of run k's first value from `base` */
+#define GG_AOCS_META_STRIDE 32       /* u16[4]: bytes between the values of run k */
+#define GG_AOCS_META_FLAGS  40       /* u32: bit 0 = not staged (consumers take gg_aocs_fetch), bits 8..15 = enum gg_aocs_kind */
+#define GG_AOCS_META_BASE   44       /* u32: shared address of the column's copied range */
+#define GG_AOCS_META_SLOW   1u
+#define GG_AOCS_DATA_OFF    (32 * GG_AOCS_META_BYTES)
+
 /* Join hash table (Hash / HashJoin, nodeHash.c:88-176,906-1222): open addressing, linear probing, one
  * slot per inner row (duplicate keys simply occupy successive slots), entries of `stride` 64-bit words:
  *   [0]            bit 63 occupied | bit 62 NULL join key (kept for right/full joins only: never matches) |
@@ -168,6 +181,9 @@ struct ScanAggParams {
 	 * in shared memory and the row program runs over that: no attribute walk, no line pointers, only projected bytes read. */
 	const gg_aocs_devcol *aocs;
 	int32_t aocs_tile_rows;
+	/* the scan's staging unit: `aocs_unit_rows` consecutive rows (a multiple of 32, at most 1024) of every projected column
+	 * are bulk-copied into one ring slot; nblocks counts these units and every block takes a contiguous run of them */
+	int32_t aocs_unit_rows;
 	int nokeycache;                       /* experiments: 1 = every row looks its group up in the block table (no register cache) */
 	const uint32_t *snap;                 /* the scan's snapshot in device memory (gg_device.cuh heap_tuple_satisfies_mvcc), or
 	                                       * nullptr: visibility from hint bits only */
@@ -176,7 +192,41 @@ struct ScanAggParams {
 	                                       * are dealt round-robin across pages */
 };
 
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+/* gg_aocs_value (gg_aocs_decode.h) over a value staged in shared memory */
+__device__ __forceinline__ uint32_t aocs_value_smem(int kind, uint32_t a, uint64_t &word)
+{
+	uint64_t v = 0;
+	if (kind == GG_AOCS_K_W8) v = lds64(a);
+	else if (kind == GG_AOCS_K_I4) v = (uint64_t) (int64_t) (int32_t) lds32(a);
+	else if (kind == GG_AOCS_K_I2) v = (uint64_t) (int64_t) (int16_t) lds16(a);
+	else if (kind == GG_AOCS_K_B1) v = lds8(a);
+	else
+	{
+		int n = (int) (lds8(a) & 0x7F) - 1;                 /* payload bytes after the 1-byte header */
+		if (kind == GG_AOCS_K_BPCHAR)
+			while (n > 0 && lds8(a + (uint32_t) n) == ' ') n--;      /* bcTruelen (varchar.c:653) */
+		if (n > 8) return GG_AOCS_E_IRREGULAR;
+		for (int i = 0; i < n; i++) v |= (uint64_t) lds8(a + 1 + (uint32_t) i) << (8 * i);
+	}
+	word = v;
+	return 0;
+}
+
+#define GG_MAX_TEAMS 6                    /* consumer teams per block (at most one per ring slot) */
+#define GG_MAX_STAGES 6                   /* ring slots */
 struct BlockTable {                       /* per-block group table in shared memory */
+	/* teams only: the "page has landed" barriers, one set per team — [team][use of the team's barrier set mod nstage].  A parity
+	 * wait tells a barrier's current phase from the one before it and no further, so it is exact only for a waiter that has
+	 * itself seen every earlier phase of that barrier complete.  The per-slot barriers are that for a warp visiting every page;
+	 * a team sees only its own pages, hence its own barriers, which nobody else waits on (the data still lands in ring slot
+	 * page mod nstage, released through the slot's `empty` barrier as always). */
+	unsigned long long teamfull[GG_MAX_TEAMS * GG_MAX_STAGES];
 	uint64_t key[GGP_FAST_GROUPS][GG_MAX_KEYS];
 	uint32_t keynull[GGP_FAST_GROUPS];
 	volatile int n;
@@ -728,6 +778,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			mbar_init(full_bar + s * 8, 1);
 			mbar_init(empty_bar + s * 8, prm.team > 0 ? prm.team : ncons);
 		}
+		if (prm.team > 0)
+			for (int i = 0; i < GG_MAX_TEAMS * GG_MAX_STAGES; i++) mbar_init(smem_u32(&T->teamfull[i]), 1);
 		T->n = (nkeys == 0) ? 1 : 0;               /* plain aggregation: the single group always exists */
 		T->lock = 0;
 		if (nkeys == 0) { T->keynull[0] = 0; for (int c = 0; c < GG_MAX_KEYS; c++) T->key[0][c] = 0; }
@@ -756,7 +808,16 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 
 	/* pages of this block: blockIdx.x, +gridDim.x, ... */
 	const uint64_t first = blockIdx.x, stride = gridDim.x;
-	const uint32_t npages = (uint32_t) (first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0);
+	/* column files: a block takes the contiguous run of units [aocs_u0, aocs_u0 + npages) — consecutive rows, so the producer
+	 * walks each column's block directory forwards instead of looking every unit up */
+	const uint64_t aocs_per = (prm.nblocks + stride - 1) / stride;
+	const uint64_t aocs_u0 = first * aocs_per;
+	/* column files feed SeqScan -> Agg pipelines over a datum-row descriptor: folds away in join kernels and in kernels specialised
+	 * for a heap plan */
+	const bool aocs_feed = !JOIN && MODE != MODE_BUILD && MODE != MODE_PART && PL::rowwords(P) != 0 && prm.aocs_tile_rows > 0;
+	const uint32_t npages = aocs_feed
+		? (uint32_t) (aocs_u0 < prm.nblocks ? (prm.nblocks - aocs_u0 < aocs_per ? prm.nblocks - aocs_u0 : aocs_per) : 0)
+		: (uint32_t) (first < prm.nblocks ? (prm.nblocks - first + stride - 1) / stride : 0);
 
 	/* MODE_TR accumulators: round r of this lane owns pair p = r*32+lane -> (g = p / V, slot = p % V) */
 	double acc_sum[TRMODE ? GG_NROUNDS : 1];
@@ -782,11 +843,112 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 	if (warp == ncons)
 	{
 		/* ===== producer: one elected lane streams pages through the ring ===== */
-		if (lane == 0 && prm.aocs_tile_rows == 0)
+		if (aocs_feed)
+		{
+			/* Column files (aocs_getnext, aocsam.c:661): lane sl owns projected column sl.  It keeps its place in the column's
+			 * block directory (block b, row j inside it) across the block's consecutive units; per unit it finds the byte range
+			 * of the unit's values in the file (values of a block are packed: data_off + row * stride; the range may run over
+			 * block ends, the headers in between are copied along), publishes where each run of rows landed (GG_AOCS_META_*
+			 * at the head of the slot) and bulk-copies the range.  A column whose unit cannot be staged this way — NULL
+			 * bitmaps, values without a common stride, more than four blocks, a misaligned file, no room left in the slot —
+			 * is flagged and read by the consumers row by row through gg_aocs_fetch. */
+			const int UR = prm.aocs_unit_rows;
+			const bool active = lane < ncols;
+			const gg_aocs_devcol *cd = prm.aocs + (active ? P.outer.colatt[lane] : 0);
+			const int kind = active ? cd->kind : 0;
+			const uint32_t valign = kind == GG_AOCS_K_W8 ? 7u : kind == GG_AOCS_K_I4 ? 3u : kind == GG_AOCS_K_I2 ? 1u : 0u;
+			const bool misaligned = (((unsigned long long) cd->file) & 15ull) != 0;
+			int64_t b = 0, nb = active ? cd->nblocks : 0;
+			int32_t j = 0;
+			gg_aocs_block blk;
+			blk.first_row = 0; blk.data_off = 0; blk.null_off = -1; blk.nrows = 0; blk.data_len = 0; blk.stride = 0; blk.pad = 0;
+			if (active && npages > 0)
+			{
+				const uint64_t row0 = aocs_u0 * (uint64_t) UR;
+				const uint64_t tile = row0 / (uint64_t) prm.aocs_tile_rows;
+				const gg_aocs_tile t = cd->tiles[tile];
+				int64_t jj = (int64_t) t.row_in_block + (int64_t) (row0 - tile * (uint64_t) prm.aocs_tile_rows);
+				b = t.block;
+				while (b < nb) { blk = cd->dir[b]; if (jj < blk.nrows) break; jj -= blk.nrows; b++; }
+				j = (int32_t) jj;
+			}
+			int s = 0;
+			uint32_t ph = 0;
+			for (uint32_t it = 0; it < npages; it++)
+			{
+				if (lane == 0) mbar_wait(empty_bar + s * 8, ph ^ 1, 128);
+				__syncwarp();
+				const uint32_t slot = ring + (uint32_t) s * GG_BLCKSZ;
+				const uint64_t left = prm.nrows - (aocs_u0 + it) * (uint64_t) UR;
+				const int nitems = (int) (left < (uint64_t) UR ? left : (uint64_t) UR);
+				uint32_t nbytes = 0;
+				bool slow = misaligned;
+				int64_t a0 = 0;
+				if (active)
+				{
+					const uint32_t meta = slot + (uint32_t) lane * GG_AOCS_META_BYTES;
+					int rem = nitems, nseg = 0;
+					int64_t end_off = 0;
+					while (rem > 0)
+					{
+						if (b >= nb) { slow = true; break; }
+						const int take = rem < blk.nrows - j ? rem : blk.nrows - j;
+						const int64_t off = blk.data_off + (int64_t) j * blk.stride;
+						if (blk.null_off >= 0 || blk.stride <= 0 || blk.stride > 0xFFFF || ((off | (int64_t) blk.stride) & valign)) slow = true;
+						if (nseg == 0) a0 = off & ~(int64_t) 15;
+						if (nseg < 4)
+						{
+							sts32(meta + GG_AOCS_META_CUM + (uint32_t) nseg * 4, (uint32_t) (nitems - rem + take));
+							sts32(meta + GG_AOCS_META_REL + (uint32_t) nseg * 4, (uint32_t) (off - a0));
+							sts16(meta + GG_AOCS_META_STRIDE + (uint32_t) nseg * 2, (uint32_t) blk.stride);
+						}
+						else slow = true;
+						nseg++;
+						end_off = off + (int64_t) take * blk.stride;
+						rem -= take; j += take;
+						if (j >= blk.nrows) { b++; j = 0; if (b < nb) blk = cd->dir[b]; }
+					}
+					for (; nseg < 4; nseg++)
+					{
+						sts32(meta + GG_AOCS_META_CUM + (uint32_t) nseg * 4, 0xFFFFFFFFu);
+						sts32(meta + GG_AOCS_META_REL + (uint32_t) nseg * 4, 0);
+						sts16(meta + GG_AOCS_META_STRIDE + (uint32_t) nseg * 2, 0);
+					}
+					if (!slow && end_off - a0 > (int64_t) (GG_BLCKSZ - GG_AOCS_DATA_OFF)) slow = true;
+					if (!slow) nbytes = (uint32_t) (((end_off + 15) & ~(int64_t) 15) - a0);
+				}
+				/* the columns' ranges one after the other in the slot's data area */
+				uint32_t at = nbytes;
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t up = __shfl_up_sync(GG_FULL_MASK, at, o);
+					if (lane >= o) at += up;
+				}
+				at -= nbytes;
+				if (at + nbytes > (uint32_t) (GG_BLCKSZ - GG_AOCS_DATA_OFF)) { slow = true; nbytes = 0; }
+				uint32_t total = nbytes;
+				for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(GG_FULL_MASK, total, o);
+				if (active)
+				{
+					const uint32_t meta = slot + (uint32_t) lane * GG_AOCS_META_BYTES;
+					sts32(meta + GG_AOCS_META_FLAGS, (slow ? GG_AOCS_META_SLOW : 0u) | ((uint32_t) kind << 8));
+					sts32(meta + GG_AOCS_META_BASE, slot + GG_AOCS_DATA_OFF + at);
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive_expect_tx(full_bar + s * 8, total);
+				__syncwarp();
+				if (nbytes) tma_load_1d(slot + GG_AOCS_DATA_OFF + at, cd->file + a0, nbytes, full_bar + s * 8);
+				if (++s == nstage) { s = 0; ph ^= 1; }
+			}
+		}
+		else if (lane == 0)
 		{
 			int s = 0;
 			uint32_t ph = 0;
 			const uint8_t *src = prm.pages + first * (uint64_t) chunk_bytes;
+			/* teams: page `it` is team (it mod nteams)'s; its arrival is signalled on that team's barrier tq = (it / nteams) mod nstage */
+			const int pnteams = prm.team > 0 ? ncons / prm.team : 1;
+			int tm = 0, tq = 0;
 			for (uint32_t it = 0; it < npages; it++)
 			{
 				mbar_wait(empty_bar + s * 8, ph ^ 1, 128);
@@ -794,10 +956,12 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				uint32_t nbytes = chunk_bytes;
 				if (rowwords && first + (uint64_t) it * stride == prm.nblocks - 1)
 					nbytes = (uint32_t) (((prm.nrows - (prm.nblocks - 1) * (uint64_t) rows_per_chunk) * rowbytes + 15) & ~15ull);
-				mbar_arrive_expect_tx(full_bar + s * 8, nbytes);
-				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, nbytes, full_bar + s * 8);
+				const uint32_t fb = prm.team > 0 ? smem_u32(&T->teamfull[tm * GG_MAX_STAGES + tq]) : full_bar + s * 8;
+				mbar_arrive_expect_tx(fb, nbytes);
+				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, nbytes, fb);
 				src += stride * (uint64_t) chunk_bytes;
 				if (++s == nstage) { s = 0; ph ^= 1; }
+				if (++tm == pnteams) { tm = 0; if (++tq == nstage) tq = 0; }
 			}
 		}
 	}
@@ -860,20 +1024,17 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 		int s = team, dealt = 0;
 		uint32_t ph = 0;
 		while (s >= nstage) { s -= nstage; ph ^= 1; }
+		/* teams: `dealt` counts which of the team's own barriers the next page arrives on and `ph` is that barrier's phase (a team
+		 * never waits on the slots' barriers, and it deals nothing: the two modes share the registers) */
 		for (uint32_t it = (uint32_t) team; it < npages && team < nteams; it += (uint32_t) nteams)
 		{
-			const bool aocs = prm.aocs_tile_rows > 0;
-			if (!aocs)
+			const bool aocs = aocs_feed;
 			{
 				if (lane == 0)
 				{
-					/* A parity wait tells the current phase of the slot from the one before it, no further.  A warp that visits
-					 * every page has consumed page it - nstage itself; a team has only consumed page it - nteams, which says that
-					 * the copy of page it - nstage was ISSUED before, not that it has landed (bulk copies complete in any order).
-					 * So a team first waits for that earlier phase — the slot is then in the phase of page `it` for certain (it
-					 * cannot be further: this team has not released it) — and only then for its own. */
-					if (prm.team > 0 && it >= (uint32_t) nstage) mbar_wait(full_bar + s * 8, ph ^ 1, 20);
-					mbar_wait(full_bar + s * 8, ph, 20);
+					/* a team waits on its own barrier set (BlockTable::teamfull): exact, it has seen every earlier phase itself */
+					if (prm.team > 0) mbar_wait(smem_u32(&T->teamfull[team * GG_MAX_STAGES + dealt]), ph, 20);
+					else mbar_wait(full_bar + s * 8, ph, 20);
 				}
 				__syncwarp();
 			}
@@ -885,9 +1046,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			int nitems = 0;
 			if (aocs)
 			{
-				const uint64_t tile = first + (uint64_t) it * stride;
-				const uint64_t left = prm.nrows - tile * (uint64_t) prm.aocs_tile_rows;
-				nitems = (int) (left < (uint64_t) prm.aocs_tile_rows ? left : (uint64_t) prm.aocs_tile_rows);
+				const uint64_t left = prm.nrows - (aocs_u0 + it) * (uint64_t) prm.aocs_unit_rows;
+				nitems = (int) (left < (uint64_t) prm.aocs_unit_rows ? left : (uint64_t) prm.aocs_unit_rows);
 			}
 			else if (rowwords)
 			{
@@ -939,46 +1099,38 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					{
 						/* the row is assembled here, from the column files: an odd word stride keeps the lanes on distinct banks */
 						rp = myscr + (uint32_t) prm.scratch_per_warp - (32u - (uint32_t) lane) * ((rowwords | 1u) * 8);      /* the tail of the warp's scratch */
-						/* Where the chunk's rows sit in each column file is the same question for all 32 lanes: lane sl answers it for
-						 * column slot sl (tile plan -> storage block -> address of the chunk's first value: two dependent loads, all
-						 * columns at once), the answers are broadcast, and every lane then loads its own row's values — independent
-						 * loads, all in flight together.  A block that ends inside the chunk, or one with a NULL bitmap, sends the
-						 * lanes concerned through the general per-row walk (gg_aocs_fetch). */
-						const int64_t tile = (int64_t) (first + (uint64_t) it * stride);
-						unsigned long long m_addr = 0;
-						int m_left = 0, m_stride = 0, m_kind = 0;
-						if (lane < ncols)
-						{
-							const gg_aocs_devcol *cd = prm.aocs + P.outer.colatt[lane];
-							const gg_aocs_tile t = cd->tiles[tile];
-							int64_t b = t.block, j = (int64_t) t.row_in_block + (int64_t) c * 32;
-							while (b < cd->nblocks && j >= cd->dir[b].nrows) { j -= cd->dir[b].nrows; b++; }
-							m_kind = cd->kind;
-							if (b < cd->nblocks)
-							{
-								const gg_aocs_block blk = cd->dir[b];
-								if (blk.null_off < 0 && blk.stride > 0)
-								{
-									m_addr = (unsigned long long) (cd->file + blk.data_off + j * (int64_t) blk.stride);
-									m_left = (int) (blk.nrows - j);
-									m_stride = blk.stride;
-								}
-							}
-						}
+						/* The producer has copied the unit's values of every projected column into this slot and says where each run
+						 * of rows landed; a lane picks its row's run and loads the value from shared memory.  A column the producer
+						 * could not stage (NULL bitmaps, no common stride, ...) goes through the general per-row walk over the file in
+						 * device memory (gg_aocs_fetch, the function the CPU tests run over the reference-written files). */
 						uint64_t m = 0;
 						uint32_t aerr = 0;
 						for (int sl = 0; sl < ncols; sl++)
 						{
 							const int a = P.outer.colatt[sl];
-							const unsigned long long base = __shfl_sync(GG_FULL_MASK, m_addr, sl);
-							const int left = __shfl_sync(GG_FULL_MASK, m_left, sl), vstride = __shfl_sync(GG_FULL_MASK, m_stride, sl);
-							const int kind = __shfl_sync(GG_FULL_MASK, m_kind, sl);
+							const uint32_t meta = pg + (uint32_t) sl * GG_AOCS_META_BYTES;
+							const uint32_t flags = lds32(meta + GG_AOCS_META_FLAGS);
 							if (!live) continue;
 							uint64_t w = 0;
 							int isn = 0;
 							uint32_t rc;
-							if (base && lane < left) rc = gg_aocs_value(kind, (const uint8_t *) (base + (unsigned long long) lane * (unsigned long long) vstride), &w);
-							else rc = gg_aocs_fetch(prm.aocs + a, tile, idx, &w, &isn);
+							if (flags & GG_AOCS_META_SLOW)
+							{
+								const uint64_t row = (aocs_u0 + it) * (uint64_t) prm.aocs_unit_rows + (uint64_t) idx;
+								const uint64_t tile = row / (uint64_t) prm.aocs_tile_rows;
+								rc = gg_aocs_fetch(prm.aocs + a, (int64_t) tile, (int32_t) (row - tile * (uint64_t) prm.aocs_tile_rows), &w, &isn);
+							}
+							else
+							{
+								const uint4 cum = lds128(meta + GG_AOCS_META_CUM), rel = lds128(meta + GG_AOCS_META_REL);
+								const uint64_t st4 = lds64(meta + GG_AOCS_META_STRIDE);
+								const uint32_t r = (uint32_t) idx;
+								const int k = (r >= cum.x) + (r >= cum.y) + (r >= cum.z);
+								const uint32_t prev = k == 0 ? 0u : k == 1 ? cum.x : k == 2 ? cum.y : cum.z;
+								const uint32_t relk = k == 0 ? rel.x : k == 1 ? rel.y : k == 2 ? rel.z : rel.w;
+								const uint32_t stk = (uint32_t) (st4 >> (16 * k)) & 0xFFFFu;
+								rc = aocs_value_smem((int) (flags >> 8) & 0xFF, lds32(meta + GG_AOCS_META_BASE) + relk + (r - prev) * stk, w);
+							}
 							aerr |= rc;
 							if (rc || isn) { w = 0; m |= 1ull << a; }
 							sts64(rp + 8 + (uint32_t) a * 8, w);
@@ -1172,9 +1324,15 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				}
 			}
 			__syncwarp();
-			if (lane == 0 && !aocs) mbar_arrive(empty_bar + s * 8);
+			if (lane == 0) mbar_arrive(empty_bar + s * 8);
 			s += nteams;
-			while (s >= nstage) { s -= nstage; ph ^= 1; }
+			if (prm.team > 0)
+			{
+				while (s >= nstage) s -= nstage;
+				if (++dealt == nstage) { dealt = 0; ph ^= 1; }
+			}
+			else
+				while (s >= nstage) { s -= nstage; ph ^= 1; }
 		}
 		if constexpr (MODE == MODE_PART)
 		{

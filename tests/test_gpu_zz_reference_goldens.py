@@ -242,7 +242,7 @@ def test_fused_aocs_scan_with_nulls_and_a_ragged_tail(eng):
     from oracle import pyoracle as po
     rng = np.random.default_rng(17)
     n = 70_001
-    desc = make_desc([(capi.INT4OID, 4, "i", 0), (capi.FLOAT8OID, 8, "d", 0), (capi.BPCHAROID, -1, "i", 0), (capi.INT8OID, 8, "d", 1)])
+    desc = make_desc([(capi.INT4OID, 4, "i", 1), (capi.FLOAT8OID, 8, "d", 1), (capi.BPCHAROID, -1, "i", 0), (capi.INT8OID, 8, "d", 1)])
     k = rng.integers(0, 7, n)
     x = rng.integers(-1000, 1000, n).astype(np.float64) / 4
     f = [bytes([65 + int(c)]) for c in rng.integers(0, 3, n)]
@@ -264,6 +264,51 @@ def test_fused_aocs_scan_with_nulls_and_a_ragged_tail(eng):
         sa.free()
         oscan = capi.make_scan(desc, qual)
         want, wsc, wps = po.aocs_seqscan_agg(oscan, agg, p.pool, [files[c] for c in range(4)], n)
+        assert (sc, ps) == (wsc, wps) and sc == n
+        assert_aggrows_match(got, want, agg)
+    finally:
+        dc.free()
+
+
+@pytest.mark.parametrize("blocksize,file_shift", [(8192, 0), (32768, 0), (32768, 8)])
+def test_fused_aocs_scan_staged_and_row_by_row_columns_mix(eng, blocksize, file_shift):
+    """The fused scan stages a unit's values of a column in shared memory when the storage blocks it touches are plain
+    (no NULL bitmap, one stride) and reads the column row by row otherwise: NULLs only in the middle third of the rows make
+    both happen inside one column file, small storage blocks make a unit run over several of them, and files that do not
+    start on a 16-byte boundary take the row-by-row path altogether.  Every combination equals the oracle's AOCS scan."""
+    from _util import assert_aggrows_match, make_desc
+    from greengage_b200 import aocs
+    from greengage_b200.capi import ExprPool
+    from greengage_b200.engine import ScanAgg
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(23)
+    n = 100_003
+    desc = make_desc([(capi.INT4OID, 4, "i", 1), (capi.FLOAT8OID, 8, "d", 1), (capi.BPCHAROID, -1, "i", 0), (capi.INT8OID, 8, "d", 1),
+                      (capi.BOOLOID, 1, "c", 1)])
+    k = rng.integers(0, 9, n)
+    x = rng.integers(-1000, 1000, n).astype(np.float64) / 8
+    f = [bytes([65 + int(c)]) * 2 for c in rng.integers(0, 3, n)]
+    y = rng.integers(-10**12, 10**12, n)
+    t = rng.integers(0, 2, n)
+    mid = (np.arange(n) > n // 3) & (np.arange(n) < 2 * n // 3)
+    nulls = [mid & (rng.random(n) < 0.2), mid & (rng.random(n) < 0.3), np.zeros(n, bool), None, None]
+    vals = [[int(v) for v in k], [float(v) for v in x], f, [int(v) for v in y], [int(v) for v in t]]
+    files = {c: aocs.write_column(desc.attrs[c], vals[c], nulls[c], blocksize=blocksize) for c in range(5)}
+    dc = aocs.DeviceColumns(eng, desc, [0, 1, 2, 3, 4], files, file_shift=file_shift)
+    try:
+        p = ExprPool()
+        kk, xx, ff, yy, tt = (p.var(1, capi.INT4OID), p.var(2, capi.FLOAT8OID), p.var(3, capi.BPCHAROID), p.var(4, capi.INT8OID),
+                              p.var(5, capi.BOOLOID))
+        qual = p.func(capi.F_INT4GT, capi.BOOLOID, kk, p.const(capi.INT4OID, 1))
+        agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [ff, tt], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, xx), (capi.AGG_COUNT_ANY, xx),
+                                                              (capi.AGG_MAX_INT8, yy), (capi.AGG_MIN_INT4, kk)])
+        scan = capi.make_scan(dc.rows_tupdesc([0, 0, 0, 1, 1]), qual)
+        sa = ScanAgg(eng, scan, agg, p.pool)
+        sa.run_aocs(dc)
+        got, sc, ps = sa.fetch()
+        sa.free()
+        oscan = capi.make_scan(desc, qual)
+        want, wsc, wps = po.aocs_seqscan_agg(oscan, agg, p.pool, [files[c] for c in range(5)], n)
         assert (sc, ps) == (wsc, wps) and sc == n
         assert_aggrows_match(got, want, agg)
     finally:
