@@ -177,7 +177,8 @@ def dev_lib():
     """libggb200.so: the CUDA engine behind the C-ABI.  Loading needs no GPU; running does."""
     global _dev
     if _dev is None:
-        path = os.path.join(_HERE, "libggb200.so")
+        # GGB200_DEVLIB: an A/B build of the same sources (scripts/ab_build.sh) for measurements; never set in product use
+        path = os.environ.get("GGB200_DEVLIB") or os.path.join(_HERE, "libggb200.so")
         if not os.path.exists(path):
             raise ImportError("greengage_b200/libggb200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
         L = C.CDLL(path)

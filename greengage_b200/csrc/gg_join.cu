@@ -163,7 +163,7 @@ int gg_joinagg_create(gg_engine *e, const gg_scan *outer, const gg_scan *inner, 
 	rc = scanagg_finish_create(p, &j->probe);
 	if (rc) { delete j; return rc; }
 	j->outer_scan = *outer; j->inner_scan = *inner; j->hj = *hj; j->agg = *agg; j->pool = *pool;
-	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 3 * sizeof(unsigned long long)));
+	GG_CUDA(cudaMalloc((void **) &j->d_cnt, 4 * sizeof(unsigned long long)));      /* line pointers | nbuilt[0..2] (JoinTable) */
 	GG_CUDA(cudaMalloc((void **) &j->d_buildcnt, 2 * sizeof(unsigned long long)));
 	GG_CUDA(cudaEventCreate(&j->ev0));
 	GG_CUDA(cudaEventCreate(&j->ev1));
@@ -183,7 +183,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	cudaStream_t st = e->stream;
 	GG_CUDA(cudaSetDevice(e->device));
 	const uint8_t *pages = inner->pages + first_block * GG_BLCKSZ;
-	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 3 * sizeof(unsigned long long), st));
+	GG_CUDA(cudaMemsetAsync(j->d_cnt, 0, 4 * sizeof(unsigned long long), st));
 	GG_CUDA(cudaEventRecord(j->ev0, st));
 	unsigned long long nlp = inner->nrows;
 	if (!inner->rowwords)
@@ -258,13 +258,20 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	GG_CUDA(cudaGetLastError());
 	e->launches++;
 	GG_CUDA(cudaEventRecord(j->ev1, st));
-	unsigned long long nb[2] = { 0, 0 };
+	unsigned long long nb[3] = { 0, 0, 0 };
 	GG_CUDA(cudaMemcpyAsync(nb, j->d_cnt + 1, sizeof nb, cudaMemcpyDeviceToHost, st));
 	GG_CUDA(cudaStreamSynchronize(st));
 	GG_CUDA(cudaEventElapsedTime(&j->build_ms, j->ev0, j->ev1));
 	j->rows_built = nb[0];
 	j->null_keys = nb[1];
 	jt.inner_empty = nb[0] == 0;
+	{
+		/* no insert passed an entry with its own hash tag: the inner join keys are pairwise distinct (orders.o_orderkey under
+		 * lineitem) and a probing row stops at its first key match.  GGB200_JOIN_UNIQUE=0 keeps the full scan to the empty slot
+		 * (experiments). */
+		const char *ju = getenv("GGB200_JOIN_UNIQUE");
+		jt.unique = nb[2] == 0 && !(ju && atoi(ju) == 0);
+	}
 	j->lasj_empty = j->jp.jointype == GG_JOIN_LASJ_NOTIN && nb[1] > 0;      /* nodeHashjoin.c:238 */
 	j->filled = false;
 	j->probe->jt = jt;

@@ -142,7 +142,10 @@ struct JoinTable {
 	int jointype;                         /* gg_jointype */
 	int probe_pc;                         /* probe program: first op of the per-match segment */
 	uint32_t keytypes;                    /* join keys, 2 bits each */
-	unsigned long long *nbuilt;           /* [0] rows inserted, [1] inner rows with a NULL join key */
+	unsigned long long *nbuilt;           /* [0] rows inserted, [1] inner rows with a NULL join key, [2] != 0: two inserted rows may
+	                                       * share a join key (an insert passed an entry with its own hash tag) */
+	int unique;                           /* probe side: the table's join keys are pairwise distinct (nbuilt[2] stayed 0), so a row's
+	                                       * first key match is its only one and the probe need not run on to an empty slot */
 	int keepnull;                         /* right / full join: rows with NULL keys are inserted too (nodeHashjoin.c:209) */
 	int mark_matched;                     /* right / full join: a qualifying match marks the entry */
 	int inner_empty;                      /* LASJ_NOTIN needs to know (nodeHashjoin.c:361) */
@@ -463,12 +466,18 @@ struct BuildSink {
 		const uint64_t h = join_hash(k0, k1);
 		const unsigned long long hdr = GG_HT_OCCUPIED | (knull ? GG_HT_NULLKEY : 0ull) | (uint32_t) h;
 		uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
+		bool maybe_dup = false;
 		for (uint32_t tries = 0; tries <= jt.mask; tries++)
 		{
 			unsigned long long *c = jt.ent + (size_t) slot * jt.stride;
-			if (atomicCAS(c, 0ull, hdr) == 0ull) { e = c; break; }
+			const unsigned long long seen = atomicCAS(c, 0ull, hdr);
+			if (seen == 0ull) { e = c; break; }
+			/* rows with equal keys hash alike, start at the same slot and so pass each other's entries: an equal tag on the way
+			 * is the only way two equal keys can get in (the keys themselves may not be written yet, so the tag decides) */
+			if ((uint32_t) seen == (uint32_t) h && !knull && !(seen & GG_HT_NULLKEY)) maybe_dup = true;
 			slot = (slot + 1) & jt.mask;
 		}
+		if (maybe_dup) *(volatile unsigned long long *) (jt.nbuilt + 2) = 1ull;
 		if (!e) { *err |= GGP_EF_TABLE_FULL; return false; }
 		e[1] = k0;
 		if (jt.nkeys > 1) e[2] = k1;
@@ -700,7 +709,9 @@ __device__ __forceinline__ bool heap_tuple_front(uint32_t pg, int idx, int nitem
 		/* HeapTupleSatisfiesMVCC fast path (tqual.c:1009,1119): frozen xmin + invalid xmax */
 		if ((infomask & GG_HEAP_XMIN_FROZEN) == GG_HEAP_XMIN_FROZEN && (infomask & GG_HEAP_XMAX_INVALID)) { }
 		else if ((infomask & GG_HEAP_XMIN_INVALID) && !(infomask & GG_HEAP_XMIN_COMMITTED)) live = false;
+#ifndef GG_AB_NO_MVCC        /* A/B builds only (scripts/ab_build.sh): what the snapshot rule costs the rows that never reach it */
 		else if (snap) live = heap_tuple_satisfies_mvcc(tup, infomask, snap, err);     /* the full rule, against the scan's snapshot */
+#endif
 		else { err |= GGP_EF_VISIBILITY; live = false; }
 	}
 	if (live && (hoff > tuplen || (hoff & 7) || hoff < 24)) { err |= GGP_EF_BADPAGE; live = false; }
@@ -956,7 +967,11 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				uint32_t nbytes = chunk_bytes;
 				if (rowwords && first + (uint64_t) it * stride == prm.nblocks - 1)
 					nbytes = (uint32_t) (((prm.nrows - (prm.nblocks - 1) * (uint64_t) rows_per_chunk) * rowbytes + 15) & ~15ull);
+#ifdef GG_AB_SLOTBAR         /* A/B builds only: teams on the slots' barriers (inexact phases: measurement, not product) */
+				const uint32_t fb = full_bar + s * 8;
+#else
 				const uint32_t fb = prm.team > 0 ? smem_u32(&T->teamfull[tm * GG_MAX_STAGES + tq]) : full_bar + s * 8;
+#endif
 				mbar_arrive_expect_tx(fb, nbytes);
 				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, nbytes, fb);
 				src += stride * (uint64_t) chunk_bytes;
@@ -1033,8 +1048,12 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				if (lane == 0)
 				{
 					/* a team waits on its own barrier set (BlockTable::teamfull): exact, it has seen every earlier phase itself */
+#ifdef GG_AB_SLOTBAR
+					mbar_wait(full_bar + s * 8, ph, 20);
+#else
 					if (prm.team > 0) mbar_wait(smem_u32(&T->teamfull[team * GG_MAX_STAGES + dealt]), ph, 20);
 					else mbar_wait(full_bar + s * 8, ph, 20);
+#endif
 				}
 				__syncwarp();
 			}
@@ -1283,22 +1302,31 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 						const unsigned long long *e = jt.ent;
 						if (probing)
 						{
+							/* One round trip to HBM covers two probe steps: the entry at `slot` and its successor are requested
+							 * together (header and first key of an entry in one 16-byte load where entries are 16-byte aligned).
+							 * The 32 lanes of a warp wait for the slowest of them, so what counts is the longest chain in the warp,
+							 * and with the table at most half full few chains are longer than two. */
 							for (;;)
 							{
-								/* header and keys are fetched together (one round trip to HBM per probe step, not two) */
-								e = jt.ent + (size_t) slot * jt.stride;
-								unsigned long long ek0;
+								const unsigned long long *ea = jt.ent + (size_t) slot * jt.stride;
+								const uint32_t slot_b = (slot + 1) & jt.mask;
+								const unsigned long long *eb = jt.ent + (size_t) slot_b * jt.stride;
+								unsigned long long hdr_a, ka0, hdr_b, kb0;
 								if ((jt.stride & 1) == 0)
 								{
-									/* entries of an even number of words start 16-byte aligned: header and first key in one request */
-									const ulonglong2 hk = __ldg((const ulonglong2 *) e);
-									hdr = hk.x; ek0 = hk.y;
+									const ulonglong2 ha = __ldg((const ulonglong2 *) ea), hb = __ldg((const ulonglong2 *) eb);
+									hdr_a = ha.x; ka0 = ha.y; hdr_b = hb.x; kb0 = hb.y;
 								}
-								else { hdr = __ldg(e); ek0 = __ldg(e + 1); }
-								const unsigned long long ek1 = jt.nkeys > 1 ? __ldg(e + 2) : 0ull;
-								slot = (slot + 1) & jt.mask;
-								if (hdr == 0) { probing = false; break; }
-								if ((uint32_t) hdr == (uint32_t) h && !(hdr & GG_HT_NULLKEY) && ek0 == jk0 && (jt.nkeys < 2 || ek1 == jk1)) { have = true; break; }
+								else { hdr_a = __ldg(ea); ka0 = __ldg(ea + 1); hdr_b = __ldg(eb); kb0 = __ldg(eb + 1); }
+								const unsigned long long ka1 = jt.nkeys > 1 ? __ldg(ea + 2) : 0ull, kb1 = jt.nkeys > 1 ? __ldg(eb + 2) : 0ull;
+								e = ea; hdr = hdr_a;
+								slot = slot_b;
+								if (hdr_a == 0) { probing = false; break; }
+								if ((uint32_t) hdr_a == (uint32_t) h && !(hdr_a & GG_HT_NULLKEY) && ka0 == jk0 && (jt.nkeys < 2 || ka1 == jk1)) { have = true; break; }
+								e = eb; hdr = hdr_b;
+								slot = (slot_b + 1) & jt.mask;
+								if (hdr_b == 0) { probing = false; break; }
+								if ((uint32_t) hdr_b == (uint32_t) h && !(hdr_b & GG_HT_NULLKEY) && kb0 == jk0 && (jt.nkeys < 2 || kb1 == jk1)) { have = true; break; }
 							}
 						}
 						bool nullext = false;
@@ -1319,6 +1347,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 							if (jt.mark_matched && !(hdr & GG_HT_MATCHED)) atomicOr((unsigned long long *) e, GG_HT_MATCHED);
 							if (single) { probing = false; pending = false; }
 						}
+						/* distinct inner keys: this key match was the row's only one, whatever the join qual said of it */
+						if (have && jt.unique) probing = false;
 						if constexpr (TRMODE) tr_accumulate();
 					}
 				}
@@ -1326,7 +1356,11 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
 			s += nteams;
+#ifdef GG_AB_SLOTBAR
+			if (false)
+#else
 			if (prm.team > 0)
+#endif
 			{
 				while (s >= nstage) s -= nstage;
 				if (++dealt == nstage) { dealt = 0; ph ^= 1; }

@@ -65,8 +65,14 @@ if "build" in which or "probe" in which:
                 emit(op="build", config=cfg, error=str(exc)[:200])
     if "probe" in which:
         setenv(GGB200_NP_CONFIG=None)
-        for cfg in [None, "20,5,0", "18,5,6", "18,4,6", "24,4,6", "12,5,6", "24,3,6", "21,5,7", "30,3,6", "30,4,6", "27,4,9"]:
-            setenv(GGB200_PRIV_CONFIG=cfg)
+        # SWEEP_PROBE="cfg;cfg;..." overrides the list; a cfg is "ncons,stages,team[,ctas]", "-" = the engine's own choice, and a
+        # trailing "/u0" runs it with GGB200_JOIN_UNIQUE=0 (the probe scans on to the empty slot although the keys are distinct)
+        plist = os.environ.get("SWEEP_PROBE")
+        plist = plist.split(";") if plist else ["-", "20,5,0", "18,5,6", "18,4,6", "24,4,6", "12,5,6", "24,3,6", "21,5,7", "30,3,6", "30,4,6", "27,4,9"]
+        for ent in plist:
+            cfg, _, flag = ent.partition("/")
+            cfg = None if cfg == "-" else cfg
+            setenv(GGB200_PRIV_CONFIG=cfg, GGB200_JOIN_UNIQUE="0" if flag == "u0" else None)
             try:
                 ja = JoinAgg(eng, outer, inner, hj, agg, pool)
                 ja.build(od)
@@ -79,11 +85,11 @@ if "build" in which or "probe" in which:
                     best = ms if best is None or ms < best else best
                 res = (nj, got[0].agg[0].i, got[0].agg[1].i)
                 ref = ref or res
-                emit(op="probe", config=cfg, variant=capi.dev_lib().gg_joinagg_variant(ja.h), ms=best, rows=lnr, frac=(lnb * 32768 + 32 * lnr) / best / 1e6 / PEAK, equal=res == ref)
+                emit(op="probe", config=ent, variant=capi.dev_lib().gg_joinagg_variant(ja.h), ms=best, rows=lnr, frac=(lnb * 32768 + 32 * lnr) / best / 1e6 / PEAK, equal=res == ref)
                 ja.free()
             except Exception as exc:
-                emit(op="probe", config=cfg, error=str(exc)[:200])
-        setenv(GGB200_PRIV_CONFIG=None)
+                emit(op="probe", config=ent, error=str(exc)[:200])
+        setenv(GGB200_PRIV_CONFIG=None, GGB200_JOIN_UNIQUE=None)
 
 if "motion" in which:
     desc = capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE)
