@@ -96,6 +96,50 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_random_rates = None
+
+
+def random_access_rates():
+    """What this GPU sustains for the random accesses of the hash kernels, measured now by build/gather_peak (scripts/
+    gather_peak.cu: random 32-byte-entry gathers, CAS inserts and atomic pairs over a 2 GB table, nothing else in the kernel):
+    {"gather_g_per_s", "cas_insert_g_per_s", "atomic_pair_g_per_s"} in 10^9 accesses per second, or None without the tool."""
+    global _random_rates
+    if _random_rates is None:
+        _random_rates = {}
+        exe = os.path.join(ROOT, "build", "gather_peak")
+        if os.path.exists(exe):
+            try:
+                env = dict(os.environ)
+                if "LOCAL_RANK" in env and "CUDA_VISIBLE_DEVICES" not in env:
+                    env["CUDA_VISIBLE_DEVICES"] = env["LOCAL_RANK"]
+                out = subprocess.run([exe, "2048", "2e8"], capture_output=True, timeout=120, env=env, text=True)
+                d = json.loads(out.stdout.strip().splitlines()[-1])
+                _random_rates = {"gather_g_per_s": max(d["gather_g_per_s"].values()), "cas_insert_g_per_s": d["cas_insert_g_per_s"],
+                                 "atomic_pair_g_per_s": d["atomic_pair_g_per_s"], "table_bytes": d["table_bytes"],
+                                 "source": "build/gather_peak (scripts/gather_peak.cu), this run"}
+            except Exception as exc:
+                _random_rates = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return _random_rates if "gather_g_per_s" in _random_rates else None
+
+
+def join_random_bound(stream_bytes_build, inserts, stream_bytes_probe, probes, build_ms, probe_ms, peak):
+    """The join's bound when its random accesses are counted at the rate this GPU sustains for them instead of at streaming
+    bandwidth: build = inner pages at copy bandwidth + one CAS insert per inner row; probe = outer pages at copy bandwidth +
+    one 32-byte table entry per outer row (the load factor's extra steps are the kernel's business).  The two terms of each are
+    ADDED (both draw on the same HBM), so frac_of_bound can exceed what a kernel overlapping them perfectly would show."""
+    rr = random_access_rates()
+    if not rr:
+        return None
+    b_ms = stream_bytes_build / (peak * 1e9) * 1e3 + inserts / (rr["cas_insert_g_per_s"] * 1e9) * 1e3
+    p_ms = stream_bytes_probe / (peak * 1e9) * 1e3 + probes / (rr["gather_g_per_s"] * 1e9) * 1e3
+    out = {"rates": rr, "build_bound_ms": b_ms, "probe_bound_ms": p_ms}
+    if build_ms:
+        out["build_frac_of_bound"] = b_ms / build_ms
+    if probe_ms:
+        out["probe_frac_of_bound"] = p_ms / probe_ms
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -655,7 +699,8 @@ def sec_join(ctx):
                          "frac": algo / ((build_ms + probe_ms) / 1e3) / 1e9 / peak,
                          "probe_frac": (nb * BLCKSZ + 32 * nr) / (probe_ms / 1e3) / 1e9 / peak,
                          "build_frac": (onb * BLCKSZ + 16 * onr) / (build_ms / 1e3) / 1e9 / peak,
-                         "note": "SURVEY §8d: both relations' pages once + 16 B/inner row written + one 32 B table sector per probe, over build + probe kernel time"},
+                         "note": "SURVEY §8d: both relations' pages once + 16 B/inner row written + one 32 B table sector per probe, over build + probe kernel time",
+                         "random_access_bound": join_random_bound(onb * BLCKSZ, onr, nb * BLCKSZ, nr, build_ms, probe_ms, peak)},
             "parity": par, "setup_s": round(setup, 1)}
 
 

@@ -24,7 +24,11 @@ struct gg_jit_kernel {
 /* C++ source of the specialised translation unit (also used to pre-generate kernels offline) */
 /* mode: the kernel role (MODE_* of gg_scanagg_kernel.cuh); join_probe_pc >= 0: the probe side of a join pipeline */
 /* ctas: resident blocks per SM the launch bounds ask for (0: one for the private-accumulator variant, else two) */
-std::string gg_jit_scanagg_source(const ggp_program *prog, int mode, int threads, const char *suffix, int join_probe_pc = -1, int regslots = 0, int ctas = 0);
+/* mvcc: the kernel carries HeapTupleSatisfiesMVCC for tuples whose hint bits do not decide (needed when the scan has a snapshot);
+ * without it such a tuple raises GGP_EF_VISIBILITY as it does when no snapshot was given — the rule's code stays out of the
+ * kernels that never reach it (it cost the headline scan 7 % through sheer code size, profiles/r2g_ab_scan.jsonl) */
+std::string gg_jit_scanagg_source(const ggp_program *prog, int mode, int threads, const char *suffix, int join_probe_pc = -1, int regslots = 0, int ctas = 0,
+                                  int mvcc = 0);
 int gg_priv_regslots(const ggp_program *prog, int mode, long long num_groups, int join_probe_pc);
 uint64_t gg_plan_hash(const ggp_program *prog, int mode);
 /* build-time plan cache (csrc/plans/gg_plan_cache.cu): address of the kernel specialised for this hash, or nullptr */
@@ -32,4 +36,4 @@ const void *gg_plan_cache_lookup(uint64_t hash, int threads, const ggp_program *
 /* compile (or fetch from the cache) the specialised scan+agg kernel; returns nullptr and fills err when JIT is
  * unavailable or fails */
 gg_jit_kernel *gg_jit_scanagg(const ggp_program *prog, int mode, int threads, int device, char *err, int errlen, int join_probe_pc = -1,
-                              int regslots = 0, int ctas = 0);
+                              int regslots = 0, int ctas = 0, int mvcc = 0);

@@ -244,7 +244,7 @@ int gg_joinagg_build(gg_joinagg *j, gg_relation *inner, uint64_t first_block, ui
 	{
 		char jmsg[512];
 		const int threads = (ncons + 1) * 32;
-		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0);
+		gg_jit_kernel *jk = gg_jit_scanagg(&j->jp.build, MODE_BUILD, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0, e->d_snapshot != nullptr);
 		if (jk)
 		{
 			void *args[] = { (void *) &j->jp.build, (void *) &prm };

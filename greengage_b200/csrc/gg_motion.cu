@@ -94,7 +94,7 @@ int gg_partition_rows(gg_engine *e, const gg_scan *scan, const gg_exprpool *pool
 	if (ce == cudaSuccess)
 	{
 		char jmsg[512];
-		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0);
+		gg_jit_kernel *jk = gg_jit_scanagg(&prog, MODE_PART, threads, e->device, jmsg, sizeof jmsg, -1, 0, nc.forced ? nc.ctas : 0, e->d_snapshot != nullptr);
 		if (jk)
 		{
 			void *args[] = { (void *) &prog, (void *) &prm };

@@ -47,6 +47,9 @@ struct gg_scanagg {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;   /* events around every scan kernel launch since reset */
 	size_t kev_used = 0;
 	gg_jit_kernel *jit = nullptr;   /* plan-specialised kernel for the current variant, or nullptr: interpreter */
+	gg_jit_kernel *jit_snap = nullptr;  /* the same with the snapshot rule built in (gg_jit.h mvcc), compiled when a launch first finds
+	                                     * the engine holding a snapshot; follows `jit` through every reconfiguration */
+	const gg_jit_kernel *jit_snap_of = nullptr;     /* the `jit` that jit_snap was compiled next to */
 	int regslots = -1;              /* private-accumulator variant: trailing value slots kept in registers (-1: not decided) */
 	int chunks_per_page = 0;        /* 32-row chunks per page of the relation being scanned (0: not sampled yet) */
 	int items_per_page = 0;         /* line pointers of the sampled page */

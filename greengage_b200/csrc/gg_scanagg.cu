@@ -523,9 +523,24 @@ int scanagg_launch(gg_scanagg *p, const uint8_t *dev_pages, uint64_t nblocks, cu
 	if (p->is_join && !p->jt.ent) { gg_set_error("probe before build"); return GG_ERR_ARG; }
 	if (p->jit)
 	{
-		/* plan-specialised kernel (any role) */
+		/* plan-specialised kernel (any role).  With a snapshot on the engine the scan needs the kernel that carries the snapshot
+		 * rule; the plain one raises GGP_EF_VISIBILITY for every tuple whose hint bits do not decide. */
+		gg_jit_kernel *jk = p->jit;
+		if (e->d_snapshot)
+		{
+			if (p->jit_snap_of != p->jit)
+			{
+				char jmsg[512];
+				p->jit_snap = gg_jit_scanagg(&p->prog, p->mode, p->threads, e->device, jmsg, sizeof jmsg, p->is_join ? p->join_probe_pc : -1, p->regslots,
+				                             (p->mode != MODE_PRIV && p->np_forced) || (p->mode == MODE_PRIV && p->ctas_per_sm > 1) ? p->ctas_per_sm : 0, 1);
+				p->jit_snap_of = p->jit;
+				if (p->jit_snap) GG_CUDA(cudaFuncSetAttribute((const void *) p->jit_snap->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p->smem));
+				else if (getenv("GGB200_JIT_VERBOSE")) fprintf(stderr, "ggb200: no specialised kernel with the snapshot rule (%s)\n", jmsg);
+			}
+			if (p->jit_snap) jk = p->jit_snap;       /* else: the plain kernel; undecided tuples make the scan fail, never pass */
+		}
 		void *args[] = { (void *) &p->prog, (void *) &prm };
-		GG_CUDA(cudaLaunchKernel((const void *) p->jit->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
+		GG_CUDA(cudaLaunchKernel((const void *) jk->kernel, dim3(p->grid), dim3(p->threads), args, p->smem, st));
 	}
 	else if (p->is_join)
 	{

@@ -465,7 +465,7 @@ struct BuildSink {
 		}
 		const uint64_t h = join_hash(k0, k1);
 		const unsigned long long hdr = GG_HT_OCCUPIED | (knull ? GG_HT_NULLKEY : 0ull) | (uint32_t) h;
-		uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
+		uint32_t slot = (uint32_t) (h >> 32) & jt.mask & ~1u;       /* chains start on even slots: see the probe loop */
 		bool maybe_dup = false;
 		for (uint32_t tries = 0; tries <= jt.mask; tries++)
 		{
@@ -680,7 +680,7 @@ template <bool JOIN> struct SinkSel<MODE_BUILD, JOIN> { typedef BuildSink type; 
 /* Line pointer -> tuple: ItemId decode, the sanity rules of PageAddItem, the visibility fast path, header checks.
  * Returns whether the lane holds a visible tuple; dead lanes get a harmless view (the page header). */
 __device__ __forceinline__ bool heap_tuple_front(uint32_t pg, int idx, int nitems, uint32_t pd_upper, uint32_t pd_special,
-                                                 bool all_visible, const uint32_t *snap, uint32_t &tup, uint32_t &tuplen, bool &hasnulls, uint32_t &err)
+                                                 bool all_visible, bool with_mvcc, const uint32_t *snap, uint32_t &tup, uint32_t &tuplen, bool &hasnulls, uint32_t &err)
 {
 	bool live = false;
 	tup = pg; tuplen = 64;
@@ -709,9 +709,9 @@ __device__ __forceinline__ bool heap_tuple_front(uint32_t pg, int idx, int nitem
 		/* HeapTupleSatisfiesMVCC fast path (tqual.c:1009,1119): frozen xmin + invalid xmax */
 		if ((infomask & GG_HEAP_XMIN_FROZEN) == GG_HEAP_XMIN_FROZEN && (infomask & GG_HEAP_XMAX_INVALID)) { }
 		else if ((infomask & GG_HEAP_XMIN_INVALID) && !(infomask & GG_HEAP_XMIN_COMMITTED)) live = false;
-#ifndef GG_AB_NO_MVCC        /* A/B builds only (scripts/ab_build.sh): what the snapshot rule costs the rows that never reach it */
-		else if (snap) live = heap_tuple_satisfies_mvcc(tup, infomask, snap, err);     /* the full rule, against the scan's snapshot */
-#endif
+		/* the full rule, against the scan's snapshot — in the kernels built with it (PL::mvcc: the interpreter kernels, and the
+		 * specialised ones of a pipeline whose engine has a snapshot); elsewhere the branch folds away */
+		else if (with_mvcc && snap) live = heap_tuple_satisfies_mvcc(tup, infomask, snap, err);
 		else { err |= GGP_EF_VISIBILITY; live = false; }
 	}
 	if (live && (hoff > tuplen || (hoff & 7) || hoff < 24)) { err |= GGP_EF_BADPAGE; live = false; }
@@ -729,6 +729,7 @@ struct DynPlan {
 	__device__ static __forceinline__ int ncols(const ggp_program &P) { return P.outer.ncols; }
 	__device__ static __forceinline__ int rowwords(const ggp_program &P) { return P.outer.rowwords; }
 	__device__ static __forceinline__ int regslots(const ggp_program &) { return 0; }       /* interpreter: dynamic slot numbers */
+	__device__ static __forceinline__ bool mvcc(const ggp_program &) { return true; }        /* interpreter: every rule built in */
 	__device__ static __forceinline__ uint32_t intmask(const ggp_program &P)
 	{
 		uint32_t m = 0;
@@ -1176,7 +1177,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				else
 				{
 				bool hasnulls;
-				live = heap_tuple_front(pg, idx, nitems, pd_upper, pd_special, all_visible, prm.snap, tup, tuplen, hasnulls, err);
+				live = heap_tuple_front(pg, idx, nitems, pd_upper, pd_special, all_visible, PL::mvcc(P), prm.snap, tup, tuplen, hasnulls, err);
 				const bool fast = !__any_sync(GG_FULL_MASK, hasnulls);
 				X.fast = fast;
 				X.tv.tp = pg;
@@ -1294,7 +1295,9 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 					bool probing = pending && !jknull;
 					bool matched = false;
 					const uint64_t h = join_hash(jk0, jk1);
-					uint32_t slot = (uint32_t) (h >> 32) & jt.mask;
+					/* a chain starts on an even slot and the probe takes slots in pairs: with entries of 32 bytes a pair is one
+					 * aligned 64-byte piece of memory, which is what HBM delivers per access anyway */
+					uint32_t slot = (uint32_t) (h >> 32) & jt.mask & ~1u;
 					for (;;)
 					{
 						bool have = false;
