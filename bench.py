@@ -349,6 +349,7 @@ def main():
     ap.add_argument("--secondary", default="all", help="all | none | comma list of narrow,join,rjoin,sort,paths,aocs")
     ap.add_argument("--narrow-rows", type=float, default=1e9)
     ap.add_argument("--rjoin-rows", type=float, default=2e8, help="lineitem rows of the Redistribute-HashJoin, TOTAL over all GPUs")
+    ap.add_argument("--rjoin-child", default=None, help=argparse.SUPPRESS)      # internal: see rjoin_in_children
     args = ap.parse_args()
     args.rows = int(args.rows)
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -380,6 +381,27 @@ def main():
         if ic is not None:
             ic.allgather_u64(0)               # device-side barrier on the engine's stream
             eng.sync()
+
+    if args.rjoin_child:
+        # one of the child processes of rjoin_in_children: this measurement and nothing else.  Should it hang, where it hangs is
+        # in its log shortly before the parent gives up on it.
+        import faulthandler
+        faulthandler.dump_traceback_later(max(10, int(os.environ.get("GGB200_RJOIN_TIMEOUT", "300")) - 10), exit=False)
+        ctx = dict(eng=eng, ic=ic, plumb=plumb, rank=rank, world=world, rel=None, nb=0, nr=0, args=args, barrier=barrier,
+                   nthreads=nthreads, table=table, hview=None)
+        try:
+            r = sec_rjoin(ctx)
+        except Exception as exc:
+            r = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        if rank == 0:
+            with open(args.rjoin_child + ".tmp", "w") as f:
+                json.dump(r, f)
+            os.replace(args.rjoin_child + ".tmp", args.rjoin_child)
+        if ic is not None:
+            ic.close()
+        eng.close()
+        plumb.close()
+        return
 
     # ---- the segment's relation: generated on the host (pinned), loaded into HBM ----
     t_setup = time.time()
@@ -529,7 +551,7 @@ def main():
             ctx["rel"] = None
         try:
             t0 = time.time()
-            r = SECONDARY[name](ctx)
+            r = rjoin_in_children(args, rank, world) if (name == "rjoin" and world > 1) else SECONDARY[name](ctx)
             if r is not None and rank == 0:
                 r["wall_s"] = round(time.time() - t0, 1)
                 secondary[name] = r
@@ -592,6 +614,49 @@ def main():
 # --------------------------------------------------------------------------------------------------------------------
 # secondary measurements
 # --------------------------------------------------------------------------------------------------------------------
+
+def rjoin_in_children(args, rank, world, timeout_s=None):
+    """At N > 1 the Redistribute-HashJoin is measured in child processes — one per rank on the rank's GPU, with their own gloo
+    group and their own NCCL communicator — so that a fault there (an exchange that never completes) costs this entry and not the
+    headline line: a child that does not come back within timeout_s is killed.  The numbers are the child's own CUDA-event
+    timings, max over ranks, exactly as sec_rjoin takes them."""
+    if timeout_s is None:
+        timeout_s = int(os.environ.get("GGB200_RJOIN_TIMEOUT", "300"))
+    port = int(os.environ.get("MASTER_PORT", "29500"))
+    out = os.path.join(tempfile.gettempdir(), "ggb200_rjoin_%d.json" % port)
+    log = os.path.join(tempfile.gettempdir(), "ggb200_rjoin_%d_rank%d.err" % (port, rank))
+    if rank == 0 and os.path.exists(out):
+        os.remove(out)
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(port + 173 if port + 173 < 65000 else port - 173)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)        # the children's rank 0 hosts their store itself
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(world), "--rjoin-child", out, "--rjoin-rows", repr(float(args.rjoin_rows))]
+    with open(log, "w") as lf:
+        proc = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=lf)
+        try:
+            rc = proc.wait(timeout=timeout_s)
+            note = None if rc == 0 else "child exited with %d" % rc
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            proc.wait()
+            note = "no answer within %d s: the child processes were killed" % timeout_s
+    if rank != 0:
+        return None
+    if os.path.exists(out):
+        with open(out) as f:
+            r = json.load(f)
+        r["isolation"] = "child processes (one per rank), own NCCL communicator"
+        return r
+    tails = []
+    for r in range(world):            # one box: every rank's log is in the same temporary directory
+        try:
+            t = open(os.path.join(tempfile.gettempdir(), "ggb200_rjoin_%d_rank%d.err" % (port, r))).read().strip()
+            if t:
+                tails.append("rank %d: %s" % (r, t[-700:]))
+        except Exception:
+            pass
+    return {"error": (note or "the child wrote no result") + ((" | " + " | ".join(tails)) if tails else "")}
+
 
 def _timed_steps(ctx, x, steps=5, warmup=3):
     """(ms per step: max over ranks of the CUDA-event time of `steps` executions, rows the last one returned, launches per step)"""
