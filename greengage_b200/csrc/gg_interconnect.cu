@@ -290,6 +290,16 @@ int gg_ic_nsegs(gg_interconnect *ic) { return ic ? ic->nsegs : 0; }
 int gg_ic_segindex(gg_interconnect *ic) { return ic ? ic->seg : -1; }
 uint64_t gg_ic_collective_count(gg_interconnect *ic) { return ic ? ic->ncollectives : 0; }
 
+/* GGB200_IC_TRACE=1: one line on stderr per collective entered / left, with the segment — what a stuck exchange looks like
+ * from each side (debugging only; the lines are flushed at once) */
+static bool ic_trace_on()
+{
+	static int on = -1;
+	if (on < 0) { const char *t = getenv("GGB200_IC_TRACE"); on = t && atoi(t) != 0; }
+	return on != 0;
+}
+#define IC_TRACE(ic, ...) do { if (ic_trace_on()) { fprintf(stderr, "[ic seg %d] ", (ic)->seg); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
 /* all-gather of `bytes` per segment on the engine's stream (loopback: a copy) */
 static int ic_allgather(gg_interconnect *ic, const void *send, void *recv, size_t bytes)
 {
@@ -299,6 +309,7 @@ static int ic_allgather(gg_interconnect *ic, const void *send, void *recv, size_
 		GG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
 		return GG_OK;
 	}
+	IC_TRACE(ic, "allgather #%llu of %zu bytes", (unsigned long long) ic->ncollectives, bytes);
 	GG_NCCL(nccl().AllGather(send, recv, bytes, ncclUint8_, ic->comm, st));
 	ic->ncollectives++;
 	return GG_OK;
@@ -316,6 +327,7 @@ int gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all /* [ns
 	GG_CUDA(cudaMemcpyAsync(ic->h_counts, ic->d_counts + ic->nsegs, 8 * (size_t) ic->nsegs, cudaMemcpyDeviceToHost, st));
 	GG_CUDA(cudaStreamSynchronize(st));
 	memcpy(all, ic->h_counts, 8 * (size_t) ic->nsegs);
+	IC_TRACE(ic, "allgather_u64 done (mine %llu)", (unsigned long long) mine);
 	return GG_OK;
 }
 
@@ -350,6 +362,7 @@ int gg_ic_motion_groups(gg_interconnect *ic, int motion_type, int root, int nhas
 	gg_engine *e = ic->eng;
 	GG_CUDA(cudaSetDevice(e->device));
 	cudaStream_t st = e->stream;
+	IC_TRACE(ic, "motion_groups type %d root %d in %p local_error %d", motion_type, root, (void *) in, local_error);
 	RouteSpec spec;
 	memset(&spec, 0, sizeof spec);
 	spec.nhash = nhash;
@@ -405,6 +418,8 @@ int gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64
 		return GG_OK;
 	}
 	/* count exchange: row d of the matrix = what segment d sends to everybody */
+	IC_TRACE(ic, "exchange_rows: rowwords %d region_cap %llu recv_cap %llu counts[0] %llu", rowwords, (unsigned long long) region_cap,
+	         (unsigned long long) recv_cap, (unsigned long long) counts[0]);
 	GG_CUDA(cudaMemcpyAsync(ic->d_counts, counts, 8 * (size_t) N, cudaMemcpyHostToDevice, st));
 	int rc = ic_allgather(ic, ic->d_counts, ic->d_counts + N, 8 * (size_t) N);
 	if (rc) return rc;
@@ -447,6 +462,7 @@ int gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64
 	}
 	GG_NCCL(n.GroupEnd());
 	ic->ncollectives++;
+	IC_TRACE(ic, "exchange_rows: sends and receives issued, %llu rows arrive here", (unsigned long long) total);
 	return GG_OK;
 }
 
@@ -456,6 +472,7 @@ int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int
                         const int32_t *dest, int my_error, int64_t *out_nrows, int64_t **out_values, uint8_t **out_isnull)
 {
 	if (my_error) nrows = 0;
+	if (ic) IC_TRACE(ic, "exchange_host: ncols %d nrows %lld my_error %d", ncols, (long long) nrows, my_error);
 	if (!ic || ncols < 1 || nrows < 0 || (nrows && (!values || !isnull || !dest)) || !out_nrows || !out_values || !out_isnull) return GG_ERR_ARG;
 	gg_engine *e = ic->eng;
 	GG_CUDA(cudaSetDevice(e->device));

@@ -740,6 +740,12 @@ static int run_node(GgPlanState *s)
 {
 	GgEState *es = s->estate;
 	int rc;
+	{
+		/* GGB200_EXEC_TRACE=1: which node of which segment starts running (debugging a stuck slice) */
+		static int trace = -1;
+		if (trace < 0) { const char *t = getenv("GGB200_EXEC_TRACE"); trace = t && atoi(t) != 0; }
+		if (trace) { fprintf(stderr, "[exec seg %d] run node kind %d (motion on host: %d)\n", es->segindex, (int) s->kind, es->motion_on_host); fflush(stderr); }
+	}
 	switch (s->kind)
 	{
 		case K_SCANROWS:
