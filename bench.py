@@ -386,7 +386,7 @@ def main():
         # one of the child processes of rjoin_in_children: this measurement and nothing else.  Should it hang, where it hangs is
         # in its log shortly before the parent gives up on it.
         import faulthandler
-        faulthandler.dump_traceback_later(max(10, int(os.environ.get("GGB200_RJOIN_TIMEOUT", "300")) - 10), exit=False)
+        faulthandler.dump_traceback_later(max(10, int(os.environ.get("GGB200_RJOIN_TIMEOUT", "180")) - 10), exit=False)
         ctx = dict(eng=eng, ic=ic, plumb=plumb, rank=rank, world=world, rel=None, nb=0, nr=0, args=args, barrier=barrier,
                    nthreads=nthreads, table=table, hview=None)
         try:
@@ -621,7 +621,7 @@ def rjoin_in_children(args, rank, world, timeout_s=None):
     headline line: a child that does not come back within timeout_s is killed.  The numbers are the child's own CUDA-event
     timings, max over ranks, exactly as sec_rjoin takes them."""
     if timeout_s is None:
-        timeout_s = int(os.environ.get("GGB200_RJOIN_TIMEOUT", "300"))
+        timeout_s = int(os.environ.get("GGB200_RJOIN_TIMEOUT", "180"))
     port = int(os.environ.get("MASTER_PORT", "29500"))
     out = os.path.join(tempfile.gettempdir(), "ggb200_rjoin_%d.json" % port)
     log = os.path.join(tempfile.gettempdir(), "ggb200_rjoin_%d_rank%d.err" % (port, rank))

@@ -24,7 +24,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "gg_pipeline.h"
 #include "gg_groups.h"
@@ -103,6 +107,15 @@ struct gg_interconnect {
 	void *stage = nullptr;           /* host-row exchange: device staging, grown on demand */
 	size_t stage_bytes = 0;
 	uint64_t ncollectives = 0;
+	/* Row exchanges (Redistribute Motion) are personalised: every segment sends a different run of rows to every other.
+	 * ncclSend / ncclRecv do that — over a communicator of their own (`p2p`), proven at creation time by a tiny exchange among
+	 * all segments (ic_p2p_preflight): point-to-point connections are set up on first use, and where that fails on one segment
+	 * the others would wait for it for ever.  Where the proof fails (or times out) on ANY segment, all of them move rows with
+	 * ncclAllGather over `comm` instead — N times the traffic, but the collective every Motion of group records already uses. */
+	ncclComm_t p2p = nullptr;
+	bool p2p_ok = false;
+	uint8_t *ag_buf = nullptr;       /* all-gather path: [nsegs] packed regions to send ++ [nsegs * nsegs] regions received */
+	size_t ag_bytes = 0;
 };
 
 /* ---------------- kernels ---------------- */
@@ -243,6 +256,66 @@ int gg_ic_unique_id(void *out, int len)
 	return GG_OK;
 }
 
+/* GGB200_IC_TRACE=1: one line on stderr per collective entered / left, with the segment — what a stuck exchange looks like
+ * from each side (debugging only; the lines are flushed at once) */
+static bool ic_trace_on()
+{
+	static int on = -1;
+	if (on < 0) { const char *t = getenv("GGB200_IC_TRACE"); on = t && atoi(t) != 0; }
+	return on != 0;
+}
+#define IC_TRACE(ic, ...) do { if (ic_trace_on()) { fprintf(stderr, "[ic seg %d] ", (ic)->seg); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
+static int ic_allgather(gg_interconnect *ic, const void *send, void *recv, size_t bytes);
+
+/* The proof that ncclSend / ncclRecv work among these segments, on a communicator of its own and in a thread of its own, so that
+ * a segment where it never returns can give up on it (gg_interconnect::p2p). */
+struct P2pPreflight {
+	std::mutex mu;
+	std::condition_variable cv;
+	bool done = false;
+	int rc = -1;
+	ncclComm_t comm = nullptr;
+	int device = 0, nsegs = 0, seg = 0;
+	ncclUniqueId id;
+};
+
+static void ic_p2p_preflight(std::shared_ptr<P2pPreflight> pf)
+{
+	Nccl &n = nccl();
+	int rc = cudaSetDevice(pf->device) == cudaSuccess ? 0 : 1000;
+	ncclComm_t comm = nullptr;
+	cudaStream_t st = nullptr;
+	unsigned char *buf = nullptr;
+	if (!rc) rc = n.CommInitRank(&comm, pf->nsegs, pf->id, pf->seg);
+	{
+		std::lock_guard<std::mutex> lk(pf->mu);
+		pf->comm = comm;
+	}
+	if (!rc && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = 1001;
+	if (!rc && cudaMalloc((void **) &buf, (size_t) 2 * 64 * (size_t) pf->nsegs) != cudaSuccess) rc = 1002;
+	if (!rc)
+	{
+		/* the shape of a row exchange: every segment to every segment, itself included, in one group */
+		rc = n.GroupStart();
+		for (int p = 0; p < pf->nsegs && !rc; p++)
+		{
+			rc = n.Send(buf + 64 * (size_t) p, 64, ncclUint8_, p, comm, st);
+			if (!rc) rc = n.Recv(buf + 64 * (size_t) (pf->nsegs + p), 64, ncclUint8_, p, comm, st);
+		}
+		const int rc2 = n.GroupEnd();            /* always: an open group would swallow every later call of this thread */
+		if (!rc) rc = rc2;
+	}
+	if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = 1003;
+	cudaFree(buf);
+	if (st) cudaStreamDestroy(st);
+	cudaGetLastError();
+	std::lock_guard<std::mutex> lk(pf->mu);
+	pf->rc = rc;
+	pf->done = true;
+	pf->cv.notify_all();
+}
+
 /* SetupInterconnect (ic_common.c:522): join the query's communicator as segment `segindex` of `nsegs` */
 int gg_ic_create(gg_engine *e, const void *unique_id, int nsegs, int segindex, gg_interconnect **out)
 {
@@ -265,6 +338,54 @@ int gg_ic_create(gg_engine *e, const void *unique_id, int nsegs, int segindex, g
 	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_counts, 8 * (size_t) (nsegs + nsegs * nsegs));
 	if (ce == cudaSuccess) ce = cudaHostAlloc((void **) &ic->h_counts, 8 * (size_t) (nsegs * nsegs), cudaHostAllocDefault);
 	if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
+	if (nsegs > 1)
+	{
+		/* how rows will travel (gg_interconnect::p2p).  GGB200_IC_ROWS = p2p | allgather skips the proof and takes that path on
+		 * `comm` (every segment must be given the same value); default: prove, then agree. */
+		const char *mode = getenv("GGB200_IC_ROWS");
+		if (mode && !strcmp(mode, "p2p")) { ic->p2p = ic->comm; ic->p2p_ok = true; }
+		else if (mode && !strcmp(mode, "allgather")) ic->p2p_ok = false;
+		else
+		{
+			Nccl &n = nccl();
+			cudaStream_t st = e->stream;
+			auto pf = std::make_shared<P2pPreflight>();
+			pf->device = e->device; pf->nsegs = nsegs; pf->seg = segindex;
+			/* segment 0 makes the second communicator's id; it travels over the first */
+			ncclUniqueId id2;
+			memset(&id2, 0, sizeof id2);
+			int rc = segindex == 0 ? n.GetUniqueId(&id2) : 0;
+			if (rc != ncclSuccess_) { gg_ic_free(ic); return nccl_fail(rc, "ncclGetUniqueId"); }
+			ce = cudaMemcpyAsync(ic->d_send, &id2, sizeof id2, cudaMemcpyHostToDevice, st);
+			if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+			if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
+			rc = ic_allgather(ic, ic->d_send, ic->d_all, sizeof(GroupBlock));
+			if (rc) { gg_ic_free(ic); return rc; }
+			ce = cudaMemcpyAsync(&pf->id, ic->d_all, sizeof pf->id, cudaMemcpyDeviceToHost, st);      /* segment 0's block */
+			if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+			if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
+			int wait_s = 20;
+			{ const char *t = getenv("GGB200_IC_P2P_TIMEOUT"); if (t && atoi(t) > 0) wait_s = atoi(t); }
+			std::thread th(ic_p2p_preflight, pf);
+			bool finished;
+			{
+				std::unique_lock<std::mutex> lk(pf->mu);
+				finished = pf->cv.wait_for(lk, std::chrono::seconds(wait_s), [&] { return pf->done; });
+			}
+			const int mine = finished && pf->rc == 0;
+			if (finished) th.join(); else th.detach();          /* a stuck proof is left behind; nothing else uses its communicator */
+			IC_TRACE(ic, "point-to-point proof: %s (rc %d)", finished ? "finished" : "timed out", finished ? pf->rc : -1);
+			uint64_t all[1024];
+			if (nsegs > 1024) { gg_ic_free(ic); return GG_ERR_UNSUPPORTED; }
+			rc = gg_ic_allgather_u64(ic, (uint64_t) mine, all);
+			if (rc) { gg_ic_free(ic); return rc; }
+			bool ok = true;
+			for (int sidx = 0; sidx < nsegs; sidx++) ok = ok && all[sidx] != 0;
+			if (ok) { ic->p2p = pf->comm; ic->p2p_ok = true; }
+			else if (finished && pf->comm) n.CommAbort(pf->comm);       /* proven here, not everywhere: of no use */
+			IC_TRACE(ic, "rows travel by %s", ok ? "ncclSend/ncclRecv" : "ncclAllGather");
+		}
+	}
 	*out = ic;
 	return GG_OK;
 }
@@ -274,13 +395,19 @@ void gg_ic_teardown(gg_interconnect *ic, int has_errors)
 {
 	if (!ic) return;
 	cudaSetDevice(ic->eng->device);
+	if (ic->p2p && ic->p2p != ic->comm)
+	{
+		if (has_errors) nccl().CommAbort(ic->p2p);
+		else { cudaStreamSynchronize(ic->eng->stream); nccl().CommDestroy(ic->p2p); }
+	}
+	ic->p2p = nullptr;
 	if (ic->comm)
 	{
 		if (has_errors) nccl().CommAbort(ic->comm);
 		else { cudaStreamSynchronize(ic->eng->stream); nccl().CommDestroy(ic->comm); }
 		ic->comm = nullptr;
 	}
-	cudaFree(ic->d_send); cudaFree(ic->d_all); cudaFree(ic->d_counts); cudaFreeHost(ic->h_counts); cudaFree(ic->stage);
+	cudaFree(ic->d_send); cudaFree(ic->d_all); cudaFree(ic->d_counts); cudaFreeHost(ic->h_counts); cudaFree(ic->stage); cudaFree(ic->ag_buf);
 	delete ic;
 }
 
@@ -289,16 +416,6 @@ void gg_ic_free(gg_interconnect *ic) { gg_ic_teardown(ic, 0); }
 int gg_ic_nsegs(gg_interconnect *ic) { return ic ? ic->nsegs : 0; }
 int gg_ic_segindex(gg_interconnect *ic) { return ic ? ic->seg : -1; }
 uint64_t gg_ic_collective_count(gg_interconnect *ic) { return ic ? ic->ncollectives : 0; }
-
-/* GGB200_IC_TRACE=1: one line on stderr per collective entered / left, with the segment — what a stuck exchange looks like
- * from each side (debugging only; the lines are flushed at once) */
-static bool ic_trace_on()
-{
-	static int on = -1;
-	if (on < 0) { const char *t = getenv("GGB200_IC_TRACE"); on = t && atoi(t) != 0; }
-	return on != 0;
-}
-#define IC_TRACE(ic, ...) do { if (ic_trace_on()) { fprintf(stderr, "[ic seg %d] ", (ic)->seg); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 /* all-gather of `bytes` per segment on the engine's stream (loopback: a copy) */
 static int ic_allgather(gg_interconnect *ic, const void *send, void *recv, size_t bytes)
@@ -328,6 +445,68 @@ int gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all /* [ns
 	GG_CUDA(cudaStreamSynchronize(st));
 	memcpy(all, ic->h_counts, 8 * (size_t) ic->nsegs);
 	IC_TRACE(ic, "allgather_u64 done (mine %llu)", (unsigned long long) mine);
+	return GG_OK;
+}
+
+/* The personalised exchange behind every Motion of rows, on the engine's stream.  ic->h_counts holds the count matrix
+ * (h_counts[s * N + d] = units segment s sends to segment d, already exchanged); this segment's part for d starts at
+ * send_base + send_off[d] (bytes); what arrives is laid out at recv_base in sender order.  unit = bytes per counted unit.
+ *   p2p_ok       grouped ncclSend / ncclRecv on the proven communicator: every byte travels once
+ *   otherwise    ncclAllGather: every segment packs its N parts at a common stride (the largest entry of the matrix), all
+ *                segments receive all parts and keep theirs — N times the traffic of the above, the price of not depending
+ *                on point-to-point connections */
+static int ic_alltoallv(gg_interconnect *ic, const uint8_t *send_base, const size_t *send_off, uint8_t *recv_base, size_t unit)
+{
+	gg_engine *e = ic->eng;
+	cudaStream_t st = e->stream;
+	const int N = ic->nsegs;
+	Nccl &n = nccl();
+	if (ic->p2p_ok)
+	{
+		int rc = n.GroupStart();
+		size_t at = 0;
+		for (int s = 0; s < N && rc == ncclSuccess_; s++)
+		{
+			const size_t sendb = (size_t) ic->h_counts[(size_t) ic->seg * N + s] * unit, recvb = (size_t) ic->h_counts[(size_t) s * N + ic->seg] * unit;
+			if (sendb) rc = n.Send(send_base + send_off[s], sendb, ncclUint8_, s, ic->p2p, st);
+			if (recvb && rc == ncclSuccess_) rc = n.Recv(recv_base + at, recvb, ncclUint8_, s, ic->p2p, st);
+			at += recvb;
+		}
+		const int rc2 = n.GroupEnd();                /* always: a group left open would swallow every later collective */
+		if (rc == ncclSuccess_) rc = rc2;
+		if (rc != ncclSuccess_) return nccl_fail(rc, "ncclSend / ncclRecv (row exchange)");
+		ic->ncollectives++;
+		return GG_OK;
+	}
+	uint64_t maxc = 0;
+	for (int i = 0; i < N * N; i++) if (ic->h_counts[i] > maxc) maxc = ic->h_counts[i];
+	if (maxc == 0) return GG_OK;
+	const size_t part = (size_t) maxc * unit;
+	const size_t need = part * (size_t) N * (size_t) (N + 1);
+	if (ic->ag_bytes < need)
+	{
+		GG_CUDA(cudaStreamSynchronize(st));
+		cudaFree(ic->ag_buf);
+		ic->ag_buf = nullptr; ic->ag_bytes = 0;
+		cudaError_t ce = cudaMalloc((void **) &ic->ag_buf, need);
+		if (ce != cudaSuccess) { cudaGetLastError(); gg_set_error("row exchange by all-gather: %zu bytes of staging do not fit in device memory", need); return GG_ERR_NOMEM; }
+		ic->ag_bytes = need;
+	}
+	uint8_t *mine = ic->ag_buf, *all = ic->ag_buf + part * (size_t) N;
+	for (int d = 0; d < N; d++)
+	{
+		const size_t b = (size_t) ic->h_counts[(size_t) ic->seg * N + d] * unit;
+		if (b) GG_CUDA(cudaMemcpyAsync(mine + part * (size_t) d, send_base + send_off[d], b, cudaMemcpyDeviceToDevice, st));
+	}
+	int rc = ic_allgather(ic, mine, all, part * (size_t) N);
+	if (rc) return rc;
+	size_t at = 0;
+	for (int s = 0; s < N; s++)
+	{
+		const size_t b = (size_t) ic->h_counts[(size_t) s * N + ic->seg] * unit;
+		if (b) GG_CUDA(cudaMemcpyAsync(recv_base + at, all + part * ((size_t) s * N + (size_t) ic->seg), b, cudaMemcpyDeviceToDevice, st));
+		at += b;
+	}
 	return GG_OK;
 }
 
@@ -450,19 +629,13 @@ int gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64
 		             (unsigned long long) total, (unsigned long long) recv_cap);
 		return GG_ERR_NOMEM;
 	}
-	Nccl &n = nccl();
-	GG_NCCL(n.GroupStart());
-	uint64_t at = 0;
-	for (int s = 0; s < N; s++)
 	{
-		const uint64_t sendn = counts[s], recvn = ic->h_counts[(size_t) s * N + ic->seg];
-		if (sendn) GG_NCCL(n.Send((const uint8_t *) send_rows + (size_t) s * region_cap * rb, sendn * rb, ncclUint8_, s, ic->comm, st));
-		if (recvn) GG_NCCL(n.Recv((uint8_t *) recv_rows + at * rb, recvn * rb, ncclUint8_, s, ic->comm, st));
-		at += recvn;
+		size_t send_off[1024];
+		for (int s = 0; s < N; s++) send_off[s] = (size_t) s * region_cap * rb;
+		rc = ic_alltoallv(ic, (const uint8_t *) send_rows, send_off, (uint8_t *) recv_rows, rb);
+		if (rc) return rc;
 	}
-	GG_NCCL(n.GroupEnd());
-	ic->ncollectives++;
-	IC_TRACE(ic, "exchange_rows: sends and receives issued, %llu rows arrive here", (unsigned long long) total);
+	IC_TRACE(ic, "exchange_rows: issued (%s), %llu rows arrive here", ic->p2p_ok ? "send/recv" : "all-gather", (unsigned long long) total);
 	return GG_OK;
 }
 
@@ -533,18 +706,10 @@ int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int
 	}
 	else
 	{
-		Nccl &n = nccl();
-		GG_NCCL(n.GroupStart());
-		uint64_t at = 0;
-		for (int s = 0; s < N; s++)
-		{
-			const uint64_t sendn = counts[(size_t) s], recvn = ic->h_counts[(size_t) s * N + ic->seg];
-			if (sendn) GG_NCCL(n.Send(d_send + offs[(size_t) s] * W, sendn * W * 8, ncclUint8_, s, ic->comm, st));
-			if (recvn) GG_NCCL(n.Recv(d_recv + at * W, recvn * W * 8, ncclUint8_, s, ic->comm, st));
-			at += recvn;
-		}
-		GG_NCCL(n.GroupEnd());
-		ic->ncollectives++;
+		size_t send_off[1024];
+		for (int s = 0; s < N; s++) send_off[s] = (size_t) offs[(size_t) s] * W * 8;
+		rc = ic_alltoallv(ic, (const uint8_t *) d_send, send_off, (uint8_t *) d_recv, W * 8);
+		if (rc) return rc;
 	}
 	std::vector<uint64_t> got((size_t) (nrecv ? nrecv : 1) * W);
 	if (nrecv) GG_CUDA(cudaMemcpyAsync(got.data(), d_recv, (size_t) nrecv * W * 8, cudaMemcpyDeviceToHost, st));
