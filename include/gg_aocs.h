@@ -1,7 +1,7 @@
 /*
  * gg_aocs.h — host side of the append-only column-oriented (AOCS) scan: what the loader does with a segment's column
  * files before they go to the device (libgghost.so, host C, no GPU needed).  SURVEY §8f rank 1; DESIGN.md §8.1.
- * The device kernel that consumes the directory is round-2 work; nothing here computes query results.
+ * The device kernels that consume the directory: gg_aocs_decode_rows (two-pass) and the fused scan gg_scanagg_run_aocs (ggb200.h).
  *
  * On-disk format handled (compresstype=none):
  *   storage blocks   AOSmallContentHeader + optional CRC-32C checksums + first row number
@@ -98,7 +98,11 @@ enum gg_aocs_kind {
 #define GG_AOCS_E_RANGE     1u      /* the walk ran off the directory: plan and directory disagree */
 #define GG_AOCS_E_IRREGULAR 2u      /* a block whose values have no common stride (stride 0) or a string too long to pack */
 
-/* one projected column as the kernel sees it (device pointers) */
+/* one projected column as the kernel sees it (device pointers).
+ * The fused scan (gg_scanagg_run_aocs) bulk-copies runs of a column's values into shared memory in 16-byte units: `file` should
+ * start on a 16-byte boundary and be readable up to the next multiple of 16 past its last byte (any cudaMalloc'ed buffer is; a
+ * loader that packs several files into one allocation pads each to 16).  A file that does not start on such a boundary is
+ * read value by value instead — same answer, slower. */
 typedef struct gg_aocs_devcol {
 	const uint8_t *file;
 	const gg_aocs_block *dir;

@@ -167,7 +167,9 @@ void gg_joinagg_free(gg_joinagg *p);
  * mixed length); GG_ERR_BADPAGE: plan and directory disagree. */
 struct gg_aocs_devcol;
 /* The fused scan: SeqScan over the column files -> qual -> Agg in ONE kernel (aocs_getnext, aocsam.c:661, feeding the same
- * row program as heap pages): a lane loads the referenced columns of its row straight from the files, nothing is written
+ * row program as heap pages): the kernel's producer warp walks the columns' block directories and bulk-copies each unit of
+ * ~500 rows of every referenced column into shared memory, consumer lanes assemble their rows from there (a column whose
+ * blocks carry NULL bitmaps or values of unequal size is read row by row from device memory instead); nothing is written
  * back to device memory, only the projected columns' bytes are read.  The pipeline must have been created over the
  * GG_FMT_DATUMROWS descriptor of the ncols projected columns (column i of the descriptor = cols[i]); tile_rows = the tile
  * size the tile plans were made for (a multiple of 32).  Accumulates like gg_scanagg_run; fetch as usual. */
