@@ -102,18 +102,20 @@ struct gg_interconnect {
 	int nsegs = 1, seg = 0;
 	GroupBlock *d_send = nullptr;    /* [1] */
 	GroupBlock *d_all = nullptr;     /* [nsegs] */
-	unsigned long long *d_counts = nullptr;   /* [nsegs] mine, [nsegs * nsegs] everybody's */
-	unsigned long long *h_counts = nullptr;   /* pinned mirror of the matrix */
+	unsigned long long *d_counts = nullptr;   /* [nsegs] mine, [nsegs * nsegs] everybody's; then the words of gg_ic_allgather_u64: [1] mine, [nsegs] everybody's */
+	unsigned long long *h_counts = nullptr;   /* pinned mirror of the matrix [nsegs * nsegs], then of gg_ic_allgather_u64's words [nsegs] */
 	void *stage = nullptr;           /* host-row exchange: device staging, grown on demand */
 	size_t stage_bytes = 0;
 	uint64_t ncollectives = 0;
 	/* Row exchanges (Redistribute Motion) are personalised: every segment sends a different run of rows to every other.
-	 * ncclSend / ncclRecv do that — over a communicator of their own (`p2p`), proven at creation time by a tiny exchange among
-	 * all segments (ic_p2p_preflight): point-to-point connections are set up on first use, and where that fails on one segment
-	 * the others would wait for it for ever.  Where the proof fails (or times out) on ANY segment, all of them move rows with
-	 * ncclAllGather over `comm` instead — N times the traffic, but the collective every Motion of group records already uses. */
+	 * Grouped ncclSend / ncclRecv do that (`p2p` = the communicator they run on: `comm`, or with GGB200_IC_ROWS=auto one of
+	 * their own, proven by a tiny all-pairs exchange when rows first travel — point-to-point connections are set up on first use,
+	 * and a segment where that fails leaves the others waiting); p2p_ok == false: rows move with ncclAllGather over `comm`
+	 * instead, N times the traffic, the collective every Motion of group records already uses (ic_decide_row_transport). */
 	ncclComm_t p2p = nullptr;
 	bool p2p_ok = false;
+	bool rows_decided = false;       /* the proof has run (it runs when rows first travel: a Motion of rows is collective, so every
+	                                  * segment is at the same point; plans that only move group records never pay for it) */
 	uint8_t *ag_buf = nullptr;       /* all-gather path: [nsegs] packed regions to send ++ [nsegs * nsegs] regions received */
 	size_t ag_bytes = 0;
 };
@@ -335,57 +337,9 @@ int gg_ic_create(gg_engine *e, const void *unique_id, int nsegs, int segindex, g
 	}
 	cudaError_t ce = cudaMalloc((void **) &ic->d_send, sizeof(GroupBlock));
 	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_all, sizeof(GroupBlock) * (size_t) nsegs);
-	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_counts, 8 * (size_t) (nsegs + nsegs * nsegs));
-	if (ce == cudaSuccess) ce = cudaHostAlloc((void **) &ic->h_counts, 8 * (size_t) (nsegs * nsegs), cudaHostAllocDefault);
+	if (ce == cudaSuccess) ce = cudaMalloc((void **) &ic->d_counts, 8 * (size_t) (nsegs + nsegs * nsegs + 2 + nsegs));
+	if (ce == cudaSuccess) ce = cudaHostAlloc((void **) &ic->h_counts, 8 * (size_t) (nsegs * nsegs + nsegs), cudaHostAllocDefault);
 	if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
-	if (nsegs > 1)
-	{
-		/* how rows will travel (gg_interconnect::p2p).  GGB200_IC_ROWS = p2p | allgather skips the proof and takes that path on
-		 * `comm` (every segment must be given the same value); default: prove, then agree. */
-		const char *mode = getenv("GGB200_IC_ROWS");
-		if (mode && !strcmp(mode, "p2p")) { ic->p2p = ic->comm; ic->p2p_ok = true; }
-		else if (mode && !strcmp(mode, "allgather")) ic->p2p_ok = false;
-		else
-		{
-			Nccl &n = nccl();
-			cudaStream_t st = e->stream;
-			auto pf = std::make_shared<P2pPreflight>();
-			pf->device = e->device; pf->nsegs = nsegs; pf->seg = segindex;
-			/* segment 0 makes the second communicator's id; it travels over the first */
-			ncclUniqueId id2;
-			memset(&id2, 0, sizeof id2);
-			int rc = segindex == 0 ? n.GetUniqueId(&id2) : 0;
-			if (rc != ncclSuccess_) { gg_ic_free(ic); return nccl_fail(rc, "ncclGetUniqueId"); }
-			ce = cudaMemcpyAsync(ic->d_send, &id2, sizeof id2, cudaMemcpyHostToDevice, st);
-			if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-			if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
-			rc = ic_allgather(ic, ic->d_send, ic->d_all, sizeof(GroupBlock));
-			if (rc) { gg_ic_free(ic); return rc; }
-			ce = cudaMemcpyAsync(&pf->id, ic->d_all, sizeof pf->id, cudaMemcpyDeviceToHost, st);      /* segment 0's block */
-			if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-			if (ce != cudaSuccess) { gg_ic_free(ic); return gg_cuda_fail(ce, "gg_ic_create"); }
-			int wait_s = 20;
-			{ const char *t = getenv("GGB200_IC_P2P_TIMEOUT"); if (t && atoi(t) > 0) wait_s = atoi(t); }
-			std::thread th(ic_p2p_preflight, pf);
-			bool finished;
-			{
-				std::unique_lock<std::mutex> lk(pf->mu);
-				finished = pf->cv.wait_for(lk, std::chrono::seconds(wait_s), [&] { return pf->done; });
-			}
-			const int mine = finished && pf->rc == 0;
-			if (finished) th.join(); else th.detach();          /* a stuck proof is left behind; nothing else uses its communicator */
-			IC_TRACE(ic, "point-to-point proof: %s (rc %d)", finished ? "finished" : "timed out", finished ? pf->rc : -1);
-			uint64_t all[1024];
-			if (nsegs > 1024) { gg_ic_free(ic); return GG_ERR_UNSUPPORTED; }
-			rc = gg_ic_allgather_u64(ic, (uint64_t) mine, all);
-			if (rc) { gg_ic_free(ic); return rc; }
-			bool ok = true;
-			for (int sidx = 0; sidx < nsegs; sidx++) ok = ok && all[sidx] != 0;
-			if (ok) { ic->p2p = pf->comm; ic->p2p_ok = true; }
-			else if (finished && pf->comm) n.CommAbort(pf->comm);       /* proven here, not everywhere: of no use */
-			IC_TRACE(ic, "rows travel by %s", ok ? "ncclSend/ncclRecv" : "ncclAllGather");
-		}
-	}
 	*out = ic;
 	return GG_OK;
 }
@@ -438,13 +392,75 @@ int gg_ic_allgather_u64(gg_interconnect *ic, uint64_t mine, uint64_t *all /* [ns
 	if (!ic || !all) return GG_ERR_ARG;
 	GG_CUDA(cudaSetDevice(ic->eng->device));
 	cudaStream_t st = ic->eng->stream;
-	GG_CUDA(cudaMemcpyAsync(ic->d_counts, &mine, 8, cudaMemcpyHostToDevice, st));
-	int rc = ic_allgather(ic, ic->d_counts, ic->d_counts + ic->nsegs, 8);
+	/* its own words behind the count matrix, on the device and in the pinned mirror: a row exchange calls this between building
+	 * the matrix and using it (the overflow agreement).  It used to share the matrix's first row — and zeroed what segment 0
+	 * sends to everybody, which left one segment's group invalid and the others waiting for it (profiles/r2j_p2p_stuck_trace.log) */
+	const size_t N = (size_t) ic->nsegs;
+	unsigned long long *d_mine = ic->d_counts + N + N * N, *d_all = d_mine + 2, *h_all = ic->h_counts + N * N;
+	GG_CUDA(cudaMemcpyAsync(d_mine, &mine, 8, cudaMemcpyHostToDevice, st));
+	int rc = ic_allgather(ic, d_mine, d_all, 8);
 	if (rc) return rc;
-	GG_CUDA(cudaMemcpyAsync(ic->h_counts, ic->d_counts + ic->nsegs, 8 * (size_t) ic->nsegs, cudaMemcpyDeviceToHost, st));
+	GG_CUDA(cudaMemcpyAsync(h_all, d_all, 8 * N, cudaMemcpyDeviceToHost, st));
 	GG_CUDA(cudaStreamSynchronize(st));
-	memcpy(all, ic->h_counts, 8 * (size_t) ic->nsegs);
+	memcpy(all, h_all, 8 * N);
 	IC_TRACE(ic, "allgather_u64 done (mine %llu)", (unsigned long long) mine);
+	return GG_OK;
+}
+
+/* Decide, once and together, how rows travel (gg_interconnect::p2p).  GGB200_IC_ROWS (every segment must be given the same value):
+ *   p2p (default)  grouped ncclSend / ncclRecv on `comm`
+ *   auto           prove point-to-point first, on a communicator of its own (ic_p2p_preflight), agree on the outcome, and fall
+ *                  back to all-gather where the proof failed or timed out on any segment — for installations where setting up
+ *                  point-to-point connections is known to be fragile
+ *   allgather      ncclAllGather of equal-stride parts, N times the traffic */
+static int ic_decide_row_transport(gg_interconnect *ic)
+{
+	if (ic->rows_decided) return GG_OK;
+	ic->rows_decided = true;
+	gg_engine *e = ic->eng;
+	const int nsegs = ic->nsegs, segindex = ic->seg;
+	cudaError_t ce;
+	const char *mode = getenv("GGB200_IC_ROWS");
+	if (!mode || !mode[0] || !strcmp(mode, "p2p")) { ic->p2p = ic->comm; ic->p2p_ok = true; return GG_OK; }
+	if (!strcmp(mode, "allgather")) { ic->p2p_ok = false; return GG_OK; }
+	if (strcmp(mode, "auto")) { gg_set_error("GGB200_IC_ROWS must be p2p, auto or allgather"); return GG_ERR_ARG; }
+	Nccl &n = nccl();
+	cudaStream_t st = e->stream;
+	auto pf = std::make_shared<P2pPreflight>();
+	pf->device = e->device; pf->nsegs = nsegs; pf->seg = segindex;
+	/* segment 0 makes the second communicator's id; it travels over the first */
+	ncclUniqueId id2;
+	memset(&id2, 0, sizeof id2);
+	int rc = segindex == 0 ? n.GetUniqueId(&id2) : 0;
+	if (rc != ncclSuccess_) return nccl_fail(rc, "ncclGetUniqueId");
+	ce = cudaMemcpyAsync(ic->d_send, &id2, sizeof id2, cudaMemcpyHostToDevice, st);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+	if (ce != cudaSuccess) return gg_cuda_fail(ce, "row transport proof");
+	rc = ic_allgather(ic, ic->d_send, ic->d_all, sizeof(GroupBlock));
+	if (rc) return rc;
+	ce = cudaMemcpyAsync(&pf->id, ic->d_all, sizeof pf->id, cudaMemcpyDeviceToHost, st);      /* segment 0's block */
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+	if (ce != cudaSuccess) return gg_cuda_fail(ce, "row transport proof");
+	int wait_s = 20;
+	{ const char *t = getenv("GGB200_IC_P2P_TIMEOUT"); if (t && atoi(t) > 0) wait_s = atoi(t); }
+	std::thread th(ic_p2p_preflight, pf);
+	bool finished;
+	{
+		std::unique_lock<std::mutex> lk(pf->mu);
+		finished = pf->cv.wait_for(lk, std::chrono::seconds(wait_s), [&] { return pf->done; });
+	}
+	const int mine = finished && pf->rc == 0;
+	if (finished) th.join(); else th.detach();          /* a stuck proof is left behind; nothing else uses its communicator */
+	IC_TRACE(ic, "point-to-point proof: %s (rc %d)", finished ? "finished" : "timed out", finished ? pf->rc : -1);
+	uint64_t all[1024];
+	if (nsegs > 1024) return GG_ERR_UNSUPPORTED;
+	rc = gg_ic_allgather_u64(ic, (uint64_t) mine, all);
+	if (rc) return rc;
+	bool ok = true;
+	for (int sidx = 0; sidx < nsegs; sidx++) ok = ok && all[sidx] != 0;
+	if (ok) { ic->p2p = pf->comm; ic->p2p_ok = true; }
+	else if (finished && pf->comm) n.CommAbort(pf->comm);       /* proven here, not everywhere: of no use */
+	IC_TRACE(ic, "rows travel by %s", ok ? "ncclSend/ncclRecv" : "ncclAllGather");
 	return GG_OK;
 }
 
@@ -596,6 +612,10 @@ int gg_ic_exchange_rows(gg_interconnect *ic, const void *send_rows, const uint64
 		*nrecv = counts[0];
 		return GG_OK;
 	}
+	{
+		int rcd = ic_decide_row_transport(ic);
+		if (rcd) return rcd;
+	}
 	/* count exchange: row d of the matrix = what segment d sends to everybody */
 	IC_TRACE(ic, "exchange_rows: rowwords %d region_cap %llu recv_cap %llu counts[0] %llu", rowwords, (unsigned long long) region_cap,
 	         (unsigned long long) recv_cap, (unsigned long long) counts[0]);
@@ -661,6 +681,11 @@ int gg_ic_exchange_host(gg_interconnect *ic, int ncols, int64_t nrows, const int
 		if (rcs) return rcs;
 		for (int s = 0; s < N; s++)
 			if (all[s]) { gg_set_error("segment %d reported an error in its slice below the Motion", s); return GG_ERR_PEER; }
+	}
+	if (ic->comm)
+	{
+		int rcd = ic_decide_row_transport(ic);
+		if (rcd) return rcd;
 	}
 	for (int64_t r = 0; r < nrows; r++)
 	{
