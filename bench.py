@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="profiling runs only: the line then carries parity.checked = false")
-    ap.add_argument("--secondary", default="all", help="all | none | comma list of narrow,join,rjoin,sort,paths,aocs")
+    ap.add_argument("--secondary", default="all", help="all | none | comma list of narrow,join,rjoin,sort,paths,aocs,groupby,motion")
     ap.add_argument("--narrow-rows", type=float, default=1e9)
     ap.add_argument("--rjoin-rows", type=float, default=2e8, help="lineitem rows of the Redistribute-HashJoin, TOTAL over all GPUs")
     ap.add_argument("--rjoin-child", default=None, help=argparse.SUPPRESS)      # internal: see rjoin_in_children
@@ -538,7 +538,7 @@ def main():
 
     # ---- the other BASELINE configurations ----
     secondary = {}
-    want_sec = [] if args.secondary == "none" else (["join", "paths", "aocs", "rjoin", "narrow", "sort"] if args.secondary == "all" else args.secondary.split(","))
+    want_sec = [] if args.secondary == "none" else (["join", "paths", "aocs", "rjoin", "narrow", "sort", "groupby", "motion"] if args.secondary == "all" else args.secondary.split(","))
     ctx = dict(eng=eng, ic=ic, plumb=plumb, rank=rank, world=world, rel=rel, nb=nb, nr=nr, args=args, barrier=barrier,
                nthreads=nthreads, table=table, hview=hview)
     for name in want_sec:
@@ -1019,7 +1019,123 @@ def sec_paths(ctx):
     return out
 
 
-SECONDARY = {"join": sec_join, "rjoin": sec_rjoin, "narrow": sec_narrow, "sort": sec_sort, "paths": sec_paths, "aocs": sec_aocs}
+def _side_relation(ctx, rows):
+    """A lineitem-wide relation of `rows` rows for the last two secondaries (the headline's relation is gone by then): host
+    pages (kept for the parity samples) and the resident relation"""
+    from greengage_b200.engine import Relation
+    spec = tpch.synth_spec(capi.TAB_LINEITEM_WIDE, rows, norders=max(rows // 4, 1), seed=11)
+    pages, nb, nr = tpch.synth_generate(spec, nthreads=ctx["nthreads"])
+    rel = Relation(ctx["eng"], host_pages=pages)
+    return pages, rel, nb, nr
+
+
+def sec_groupby(ctx):
+    """SURVEY §8a row 9, the general HashAggregate (lookup_agg_hash_entry, execHHashagg.c:456): GROUP BY l_orderkey — a quarter
+    as many groups as rows, one table in HBM — with count(*) and sum(l_extendedprice).  Parity: the same plan over a prefix of
+    the pages against the oracle, group by group."""
+    from greengage_b200.engine import Relation, ScanAgg
+    from oracle import pyoracle as po
+    eng = ctx["eng"]
+    rows = max(int(ctx["args"].rows) // 4, 100_000)
+    pages, rel, nb, nr = _side_relation(ctx, rows)
+    c = tpch.LI_WIDE_COLS
+    p = capi.ExprPool()
+    agg = capi.make_agg(capi.AGGSTAGE_NORMAL, [p.var(c["orderkey"], capi.INT8OID)],
+                        [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, p.var(c["extendedprice"], capi.FLOAT8OID))], num_groups=max(rows // 4, 1))
+    scan = capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE), -1)
+    sa = ScanAgg(eng, scan, agg, p.pool)
+    ms = []
+    for it in range(8):
+        sa.reset()
+        sa.run(rel)
+        eng.sync()
+        if it >= 3:
+            ms.append(sa.scan_kernel_ms()[0])
+    t = float(np.mean(ms))
+    variant = sa.variant()
+    # parity on a prefix small enough for the oracle's row-at-a-time table and a full fetch of the groups
+    k = min(nb, 300)
+    sub = Relation(eng, nblocks=k, device_ptr=rel.device_ptr())
+    sa.reset()
+    sa.run(sub)
+    got, sc, ps = sa.fetch(cap=1 << 17)
+    want, wsc, wps = po.seqscan_agg(scan, agg, p.pool, pages[:k * BLCKSZ], cap=1 << 17)
+    g = {r.key[0]: (r.agg[0].i, r.agg[1].f[0]) for r in got}
+    w = {r.key[0]: (r.agg[0].i, r.agg[1].f[0]) for r in want}
+    rel_err = max([abs(g[kk][1] - w[kk][1]) / max(abs(w[kk][1]), 1e-300) for kk in w if kk in g] or [0.0])
+    par = {"checked": True, "how": "the same plan over the first %d pages vs the CPU oracle, group by group" % k, "groups": len(w),
+           "groups_equal": bool(set(g) == set(w)), "counts_equal": bool(all(kk in g and g[kk][0] == w[kk][0] for kk in w)),
+           "rows_scanned_equal": bool((sc, ps) == (wsc, wps)), "max_rel_err": rel_err}
+    par["ok"] = bool(par["groups_equal"] and par["counts_equal"] and par["rows_scanned_equal"] and rel_err <= 1e-9)
+    sa.free()
+    sub.free()
+    rel.free()
+    peak, _ = measured_peak()
+    rr = random_access_rates()
+    bound = None
+    if rr:
+        b_ms = nb * BLCKSZ / (peak * 1e9) * 1e3 + nr / (rr["gather_g_per_s"] * 1e9) * 1e3 + nr / (rr["atomic_pair_g_per_s"] * 1e9) * 1e3
+        bound = {"rates": rr, "bound_ms": b_ms, "frac_of_bound": b_ms / t,
+                 "note": "pages at copy bandwidth + one random 32-byte table entry read per row + one atomic pair (count, sum) per row, terms added"}
+    return {"workload": "general HashAggregate: GROUP BY l_orderkey over %d lineitem-wide rows (~%d groups), count(*) + sum(l_extendedprice)" % (nr, rows // 4),
+            "api": "gg_scanagg_run (C-ABI), table in HBM", "ms": t, "rows_per_s": nr / (t / 1e3), "kernel_variant": variant,
+            "roofline": {"bound": "hbm", "algorithmic_bytes": nb * BLCKSZ, "achieved": nb * BLCKSZ / (t / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": nb * BLCKSZ / (t / 1e3) / 1e9 / peak, "note": "pages read once; the table's random traffic is in random_access_bound",
+                         "random_access_bound": bound},
+            "parity": par}
+
+
+def sec_motion(ctx):
+    """SURVEY §8a rows 15-16, the sending half of a Redistribute Motion (execMotionSender, nodeMotion.c:270; cdbhash +
+    jump consistent hash): lineitem-wide on l_orderkey to 8 destinations, two columns travel.  Parity: rows per destination over
+    a prefix of the pages (exact claims) against the oracle's routing."""
+    from greengage_b200.engine import Relation, motion_partition
+    from oracle import pyoracle as po
+    eng = ctx["eng"]
+    rows = max(int(ctx["args"].rows) // 4, 100_000)
+    pages, rel, nb, nr = _side_relation(ctx, rows)
+    nsegs = 8
+    c = tpch.LI_WIDE_COLS
+    p = capi.ExprPool()
+    key = p.var(c["orderkey"], capi.INT8OID)
+    payload = [key, p.var(c["extendedprice"], capi.FLOAT8OID)]
+    W = 1 + len(payload)
+    scan = capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_WIDE), -1)
+    cap = (int(nr / nsegs * 1.25) + 8192) * nsegs
+    out = Relation(eng, nblocks=(cap * W * 8 + 64 + BLCKSZ - 1) // BLCKSZ)
+    ms = []
+    for it in range(8):
+        counts, offs = motion_partition(eng, scan, p.pool, [key], payload, nsegs, rel, out.device_ptr(), cap)
+        if it >= 3:
+            ms.append(eng.last_kernel_ms())
+    t = float(np.mean(ms))
+    k = min(nb, 2000)
+    old = os.environ.get("GGB200_MOTION_WINDOW")
+    os.environ["GGB200_MOTION_WINDOW"] = "0"          # exact claims: the counts are the rows, no dead slots
+    try:
+        pc, _ = motion_partition(eng, scan, p.pool, [key], payload, nsegs, rel, out.device_ptr(), cap, first_block=0, nblocks=k)
+    finally:
+        if old is None:
+            os.environ.pop("GGB200_MOTION_WINDOW", None)
+        else:
+            os.environ["GGB200_MOTION_WINDOW"] = old
+    dest = po.motion_route(scan, p.pool, [key], nsegs, pages[:k * BLCKSZ])
+    want = np.bincount(dest, minlength=nsegs).tolist()
+    par = {"checked": True, "how": "rows per destination over the first %d pages (exact claims) vs the oracle's cdbhash routing" % k,
+           "counts": [int(x) for x in pc], "counts_equal": bool([int(x) for x in pc] == want), "ok": bool([int(x) for x in pc] == want)}
+    out.free()
+    rel.free()
+    peak, _ = measured_peak()
+    algo = nb * BLCKSZ + nr * W * 8
+    return {"workload": "Motion send: lineitem-wide (%d rows) redistributed on l_orderkey to %d destinations, %d columns travel" % (nr, nsegs, len(payload)),
+            "api": "gg_motion_partition (C-ABI)", "ms": t, "rows_per_s": nr / (t / 1e3), "slots_claimed": int(sum(counts)),
+            "roofline": {"bound": "hbm", "algorithmic_bytes": algo, "achieved": algo / (t / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (t / 1e3) / 1e9 / peak, "note": "pages read once + %d B/row written" % (W * 8)},
+            "parity": par}
+
+
+SECONDARY = {"join": sec_join, "rjoin": sec_rjoin, "narrow": sec_narrow, "sort": sec_sort, "paths": sec_paths, "aocs": sec_aocs,
+             "groupby": sec_groupby, "motion": sec_motion}
 
 
 if __name__ == "__main__":
