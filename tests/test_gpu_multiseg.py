@@ -79,7 +79,13 @@ def run(world, case):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    try:
+        res = [q.get(timeout=240) for _ in procs]          # the cases take seconds; a stuck exchange must not cost the box
+    except Exception:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        raise AssertionError("a segment did not answer within 240 s (GGB200_IC_TRACE=1 GGB200_EXEC_TRACE=1 show where each one is)")
     for p in procs:
         p.join(timeout=60)
     for r in res:
