@@ -52,3 +52,31 @@ def test_slot_rows_decode_like_oracle_rows():
     rows = [([65, 70, f(1.5), f(2.5), f(3.5), f(4.5), f(5.5), f(6.5), f(7.5), 42], [0] * 10, [0] * 10, [0] * 10)]
     got = bench.q1_rows_from_slots(rows)
     assert got == {(65, 70): ([1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5], 42)}
+
+
+def test_cpulist_and_numa_lookup_degrade_quietly():
+    assert bench._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench._cpulist("") == set()
+    # no GPU here: the lookup says so instead of raising, and bench.py then leaves the affinity alone
+    assert bench.gpu_numa_cpus(0) is None or isinstance(bench.gpu_numa_cpus(0), tuple)
+
+
+def test_a_failing_rjoin_child_costs_the_entry_not_the_run(monkeypatch):
+    """rjoin_in_children: a child that exits with an error (here: no CUDA device) yields an error entry carrying the tail of its
+    log; nothing raises, nothing hangs."""
+    import time
+    import types
+    monkeypatch.setenv("MASTER_PORT", "29611")
+    monkeypatch.setenv("GGB200_RJOIN_TIMEOUT", "120")
+    t0 = time.time()
+    r = bench.rjoin_in_children(types.SimpleNamespace(rjoin_rows=2e6), 0, 1)
+    assert "error" in r and "child exited" in r["error"] and time.time() - t0 < 110
+
+
+def test_random_access_bound_needs_the_measured_rates(monkeypatch):
+    monkeypatch.setattr(bench, "_random_rates", {"gather_g_per_s": 40.0, "cas_insert_g_per_s": 9.0, "atomic_pair_g_per_s": 18.0})
+    b = bench.join_random_bound(3.7e9, 25e6, 16.9e9, 1e8, 2.77, 7.96, 6486.1)
+    assert abs(b["build_bound_ms"] - (3.7e9 / 6486.1e9 * 1e3 + 25e6 / 9e9 * 1e3)) < 1e-9
+    assert 0.9 < b["build_frac_of_bound"] < 1.3 and 0.5 < b["probe_frac_of_bound"] < 0.8
+    monkeypatch.setattr(bench, "_random_rates", {"error": "no tool"})
+    assert bench.join_random_bound(1, 1, 1, 1, 1.0, 1.0, 6486.1) is None
