@@ -259,3 +259,17 @@ def test_flattening_a_shared_and_chain_is_bounded():
     with pytest.raises(capi.GGError) as e:
         disasm(capi.make_scan(desc, q), capi.make_agg(0, [], [(capi.AGG_COUNT_STAR, -1)]), p.pool)
     assert e.value.code == -6 and "too many clauses" in str(e.value)
+
+
+def test_the_build_time_plan_cache_is_what_the_generator_writes(tmp_path):
+    """csrc/plans/gg_plan_cache.cu holds the kernels specialised at build time for the registered plans; it is generated from the
+    product's own compiler and source generator (scripts/gen_plan_cache.py) and must not lag behind them: a stale file would run
+    yesterday's program for today's plan hash (the lookup compares program bytes, so it would simply stop hitting — and the bench
+    would silently fall back to run-time compilation)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "gg_plan_cache.cu"
+    subprocess.check_call([sys.executable, os.path.join(root, "scripts", "gen_plan_cache.py"), str(out)], stdout=subprocess.DEVNULL)
+    committed = open(os.path.join(root, "greengage_b200", "csrc", "plans", "gg_plan_cache.cu")).read()
+    assert out.read_text() == committed
