@@ -968,11 +968,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				uint32_t nbytes = chunk_bytes;
 				if (rowwords && first + (uint64_t) it * stride == prm.nblocks - 1)
 					nbytes = (uint32_t) (((prm.nrows - (prm.nblocks - 1) * (uint64_t) rows_per_chunk) * rowbytes + 15) & ~15ull);
-#ifdef GG_AB_SLOTBAR         /* A/B builds only: teams on the slots' barriers (inexact phases: measurement, not product) */
-				const uint32_t fb = full_bar + s * 8;
-#else
 				const uint32_t fb = prm.team > 0 ? smem_u32(&T->teamfull[tm * GG_MAX_STAGES + tq]) : full_bar + s * 8;
-#endif
 				mbar_arrive_expect_tx(fb, nbytes);
 				tma_load_1d(ring + (uint32_t) s * GG_BLCKSZ, src, nbytes, fb);
 				src += stride * (uint64_t) chunk_bytes;
@@ -1049,12 +1045,8 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 				if (lane == 0)
 				{
 					/* a team waits on its own barrier set (BlockTable::teamfull): exact, it has seen every earlier phase itself */
-#ifdef GG_AB_SLOTBAR
-					mbar_wait(full_bar + s * 8, ph, 20);
-#else
 					if (prm.team > 0) mbar_wait(smem_u32(&T->teamfull[team * GG_MAX_STAGES + dealt]), ph, 20);
 					else mbar_wait(full_bar + s * 8, ph, 20);
-#endif
 				}
 				__syncwarp();
 			}
@@ -1359,11 +1351,7 @@ __device__ __forceinline__ void scanagg_body(const ggp_program &P, const ScanAgg
 			__syncwarp();
 			if (lane == 0) mbar_arrive(empty_bar + s * 8);
 			s += nteams;
-#ifdef GG_AB_SLOTBAR
-			if (false)
-#else
 			if (prm.team > 0)
-#endif
 			{
 				while (s >= nstage) s -= nstage;
 				if (++dealt == nstage) { dealt = 0; ph ^= 1; }

@@ -1,6 +1,9 @@
 #!/bin/bash
-# A/B builds of libggb200.so from the same sources with one -D switch each, into build/ab_<name>/libggb200.so; measured with
-#   GGB200_DEVLIB=build/ab_<name>/libggb200.so python scripts/sweep_teams.py 1e8 wide default
+# A/B builds of libggb200.so from the same sources with extra compiler switches (a -D that an experiment's #ifdef reads, a different
+# -maxrregcount, ...) into build/ab_<name>/libggb200.so; measured with
+#   GGB200_DEVLIB=build/ab_<name>/libggb200.so python scripts/ab_scan.py 1e8
+# (profiles/r2g_ab_scan.jsonl was made this way: the snapshot rule compiled out, teams on the slots' barriers; the switches went
+# with the experiment — delete the build/ab_* directories before a gpurun call, they travel with the snapshot)
 # usage: scripts/ab_build.sh NAME -DFLAG [...]
 set -e
 cd "$(dirname "$0")/.."
