@@ -1135,6 +1135,72 @@ static int wire_layout(const GgPlanState *s, gg_attr *attrs, int *map, int *arr)
 	return s->ncols;
 }
 
+/* the MemTuple binding of a row of these column types (what the reference builds from the node's result tuple descriptor) */
+static int slot_binding(const int32_t *typids, int ncols, gg_memtuple_binding *b)
+{
+	gg_attr attrs[GG_MAX_OUTCOLS];
+	int c;
+	if (ncols < 1 || ncols > GG_MAX_OUTCOLS || ncols > GG_MT_MAX_ATTS) return GG_ERR_UNSUPPORTED;
+	for (c = 0; c < ncols; c++)
+	{
+		if (typids[c] == GG_FLOAT8ARRAYOID) return GG_ERR_UNSUPPORTED;      /* a transition array is three slot columns, not one */
+		wire_attr(&attrs[c], typids[c]);
+	}
+	return gg_memtuple_bind(attrs, ncols, b);
+}
+
+int64_t GgExecFetchSlotMemTuple(const GgTupleTableSlot *slot, uint8_t *out, uint64_t cap, uint32_t *need)
+{
+	gg_memtuple_binding *b;
+	uint32_t len = 0;
+	int rc;
+	if (!slot || slot->tts_isempty || slot->tts_nvalid < 1 || (!out && cap)) { exec_fail(GG_ERR_ARG, "empty slot"); return GG_ERR_ARG; }
+	b = malloc(sizeof *b);
+	if (!b) { exec_fail(GG_ERR_NOMEM, "out of memory"); return GG_ERR_NOMEM; }
+	rc = slot_binding(slot->tts_typid, slot->tts_nvalid, b);
+	if (rc == GG_OK)
+		rc = gg_memtuple_form(b, slot->tts_values, slot->tts_isnull, slot->tts_len, NULL, out, cap > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t) cap, &len);
+	free(b);
+	if (need) *need = len;
+	if (rc != GG_OK) { exec_fail(rc, rc == GG_ERR_NOMEM ? "output buffer too small for the MemTuple" : "row layout has no MemTuple form"); return rc; }
+	return (int64_t) len;
+}
+
+int GgExecStoreMemTuple(GgTupleTableSlot *slot, const int32_t *typids, int ncols, const uint8_t *mt, uint32_t len)
+{
+	gg_memtuple_binding *b;
+	int32_t lens[GG_MAX_OUTCOLS];
+	int rc, c;
+	if (!slot || !typids || !mt) { exec_fail(GG_ERR_ARG, "bad arguments"); return GG_ERR_ARG; }
+	b = malloc(sizeof *b);
+	if (!b) { exec_fail(GG_ERR_NOMEM, "out of memory"); return GG_ERR_NOMEM; }
+	rc = slot_binding(typids, ncols, b);
+	if (rc == GG_OK) rc = gg_memtuple_deform(b, mt, len, slot->tts_values, slot->tts_isnull, lens);
+	free(b);
+	if (rc != GG_OK) { exec_fail(rc, "not a MemTuple of these %d columns", ncols); return rc; }
+	for (c = 0; c < ncols; c++)
+	{
+		slot->tts_typid[c] = typids[c];
+		slot->tts_len[c] = 0;
+		if (slot->tts_isnull[c]) { slot->tts_values[c] = 0; continue; }
+		if (is_string_type(typids[c]))
+		{
+			/* deform left the payload's offset and length: the slot keeps short strings packed in the Datum word */
+			const int64_t off = slot->tts_values[c];
+			uint64_t v = 0;
+			int i;
+			if (lens[c] < 0 || lens[c] > 8 || off < 0 || (uint64_t) off + (uint64_t) lens[c] > len)
+			{ exec_fail(GG_ERR_UNSUPPORTED, "column %d: a string of %d bytes does not fit a slot", c, lens[c]); return GG_ERR_UNSUPPORTED; }
+			for (i = 0; i < lens[c]; i++) v |= (uint64_t) mt[off + i] << (8 * i);
+			slot->tts_values[c] = (int64_t) v;
+			slot->tts_len[c] = lens[c];
+		}
+	}
+	slot->tts_nvalid = ncols;
+	slot->tts_isempty = 0;
+	return GG_OK;
+}
+
 int64_t GgExecSendTupleChunks(GgPlanState *s, int max_chunk, uint8_t *out, uint64_t cap, int64_t *nrows)
 {
 	gg_attr attrs[GG_MAX_OUTCOLS];

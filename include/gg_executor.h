@@ -229,6 +229,15 @@ int  GgExecReScanHash(GgPlanState *node);
  * GgExecRecvTupleChunks: the reverse for a Motion node's receiving half — what CPU senders produced (RecvTupleFrom ->
  * CvtChunksToTup, cdbmotion.c:559, tupser.c:609; MemTuple or heap-tuple form), up to and including the end-of-stream chunk,
  * becomes the node's result as if its exchange had delivered it. */
+/* The other physical form of a slot (tuptable.h:117-175: a slot holds a virtual tuple, a MemTuple or a heap tuple; GPDB's
+ * executor hands MemTuples to Sort, Hash spill files, Material and the Motion layer):
+ * GgExecFetchSlotMemTuple = ExecFetchSlotMemTuple (execTuples.c:770): the slot's virtual tuple formed as a MemTuple under the
+ * binding of its column types (create_memtuple_binding + memtuple_form_to, memtuple.c:420,551) — byte for byte what the
+ * reference forms for the same Datums; returns its length, GG_ERR_NOMEM when cap is too small (*need then says how much).
+ * GgExecStoreMemTuple = ExecStoreMemTuple + slot_getallattrs (execTuples.c:560, memtuple.c:917): a MemTuple of ncols columns
+ * of the given types back into a virtual slot (strings come back packed: at most 8 bytes, else GG_ERR_UNSUPPORTED). */
+int64_t GgExecFetchSlotMemTuple(const GgTupleTableSlot *slot, uint8_t *out, uint64_t cap, uint32_t *need);
+int GgExecStoreMemTuple(GgTupleTableSlot *slot, const int32_t *typids, int ncols, const uint8_t *mt, uint32_t len);
 int64_t GgExecSendTupleChunks(GgPlanState *node, int max_chunk, uint8_t *out, uint64_t cap, int64_t *nrows);
 int GgExecRecvTupleChunks(GgPlanState *node, const uint8_t *chunks, uint64_t nbytes);
 

@@ -204,3 +204,107 @@ def test_float8_array_state_is_the_references_array_layout():
     assert bytes(out) == struct.pack("<iiIii3d", 1, 0, 701, 3, 1, 3.0, 1.5, 9.25)
     back = (C.c_double * 3)()
     assert L.gg_float8_array3_read(out, 44, back) == 0 and list(back) == [3.0, 1.5, 9.25]
+
+
+# ---- the slot's MemTuple form at the node surface (GgExecFetchSlotMemTuple / GgExecStoreMemTuple, libggexec.so) ----
+
+def _exec_lib():
+    from greengage_b200 import executor as ex
+    L = ex.exec_lib() if hasattr(ex, "exec_lib") else C.CDLL(os.path.join(os.path.dirname(capi.__file__), "libggexec.so"))
+    L.GgExecFetchSlotMemTuple.restype = C.c_int64
+    L.GgExecFetchSlotMemTuple.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    L.GgExecStoreMemTuple.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.c_uint32]
+    return L
+
+
+def _slot_type():
+    from greengage_b200 import executor as ex
+    for name in ("GgTupleTableSlot", "gg_slot", "Slot"):
+        if hasattr(ex, name):
+            return getattr(ex, name)
+    raise AssertionError("executor.py has no slot structure")
+
+
+def test_a_slots_memtuple_is_the_references_byte_for_byte_and_comes_back():
+    """ExecFetchSlotMemTuple / ExecStoreMemTuple for the node surface's virtual slots: over the reference-written cases whose
+    columns are slot types (int4, date, short bpchar) the formed MemTuple is the reference's, and storing it back gives the slot."""
+    L = _exec_lib()
+    Slot = _slot_type()
+    used = 0
+    for case in KAT["cases"]:
+        cols = KAT["descs"][case["desc"]]["cols"]
+        if case["desc"] != "ints4" or "memtuple" not in case:
+            continue
+        pay = [None if v is None else (bytes.fromhex(v) if not str(v).startswith("x") else bytes([int(v[1:].split(":")[1])]) * int(v[1:].split(":")[0]))
+               if l == -1 else int(v) for (t, l, al, bv), v in zip(cols, case["values"])]
+        if any(isinstance(p, bytes) and len(p) > 8 for p in pay):
+            continue
+        s = Slot()
+        s.tts_nvalid, s.tts_isempty = len(cols), 0
+        for i, ((t, l, al, bv), p) in enumerate(zip(cols, pay)):
+            s.tts_typid[i] = t
+            if p is None:
+                s.tts_isnull[i] = 1
+            elif isinstance(p, bytes):
+                s.tts_values[i] = int.from_bytes(p.ljust(8, b"\0"), "little", signed=True)
+                s.tts_len[i] = len(p)
+            else:
+                s.tts_values[i] = p
+        out = (C.c_uint8 * 4096)()
+        need = C.c_uint32(0)
+        n = L.GgExecFetchSlotMemTuple(C.byref(s), out, len(out), C.byref(need))
+        assert n > 0 and need.value == n and bytes(out[:n]).hex() == case["memtuple"], case
+        assert L.GgExecFetchSlotMemTuple(C.byref(s), out, 4, C.byref(need)) == -8 and need.value == n      # too small: says how much
+        back = Slot()
+        typids = (C.c_int32 * len(cols))(*[c[0] for c in cols])
+        assert L.GgExecStoreMemTuple(C.byref(back), typids, len(cols), bytes(out[:n]), n) == 0
+        assert back.tts_nvalid == len(cols) and not back.tts_isempty
+        for i in range(len(cols)):
+            assert back.tts_isnull[i] == s.tts_isnull[i]
+            if not s.tts_isnull[i]:
+                assert (back.tts_values[i], back.tts_len[i], back.tts_typid[i]) == (s.tts_values[i], s.tts_len[i], s.tts_typid[i])
+        used += 1
+    assert used >= 10
+
+
+def test_slot_memtuples_of_every_slot_type_round_trip_and_malformed_ones_are_refused():
+    import random
+    L = _exec_lib()
+    Slot = _slot_type()
+    rnd = random.Random(5)
+    types = [capi.BOOLOID, capi.INT4OID, capi.DATEOID, capi.INT8OID, capi.FLOAT8OID, capi.TIMESTAMPOID, capi.BPCHAROID, capi.VARCHAROID, capi.TEXTOID]
+    for _ in range(300):
+        n = rnd.randint(1, 16)
+        s = Slot()
+        s.tts_nvalid, s.tts_isempty = n, 0
+        for i in range(n):
+            t = rnd.choice(types)
+            s.tts_typid[i] = t
+            if rnd.random() < 0.2:
+                s.tts_isnull[i] = 1
+            elif t in (capi.BPCHAROID, capi.VARCHAROID, capi.TEXTOID):
+                ln = rnd.randint(0, 8)
+                b = bytes(rnd.randint(1, 255) for _ in range(ln))
+                s.tts_values[i], s.tts_len[i] = int.from_bytes(b.ljust(8, b"\0"), "little", signed=True), ln
+            elif t == capi.BOOLOID:
+                s.tts_values[i] = rnd.randint(0, 1)
+            elif t in (capi.INT4OID, capi.DATEOID):
+                s.tts_values[i] = rnd.randint(-2**31, 2**31 - 1)
+            else:
+                s.tts_values[i] = rnd.randint(-2**63, 2**63 - 1)
+        out = (C.c_uint8 * 4096)()
+        need = C.c_uint32(0)
+        ln = L.GgExecFetchSlotMemTuple(C.byref(s), out, len(out), C.byref(need))
+        assert ln > 0
+        back = Slot()
+        typids = (C.c_int32 * n)(*[s.tts_typid[i] for i in range(n)])
+        assert L.GgExecStoreMemTuple(C.byref(back), typids, n, bytes(out[:ln]), ln) == 0
+        for i in range(n):
+            assert back.tts_isnull[i] == s.tts_isnull[i]
+            if not s.tts_isnull[i]:
+                assert (back.tts_values[i], back.tts_len[i]) == (s.tts_values[i], s.tts_len[i]), (i, s.tts_typid[i])
+        # a truncated tuple is refused, not read past its end
+        assert L.GgExecStoreMemTuple(C.byref(back), typids, n, bytes(out[:ln]), max(ln - 5, 1)) != 0
+    empty = Slot()
+    empty.tts_isempty = 1
+    assert L.GgExecFetchSlotMemTuple(C.byref(empty), None, 0, None) == -10
