@@ -54,6 +54,7 @@ struct GgPlanState {
 	int32_t rows_nsegs;                 /* destinations the rows are partitioned for (1: plain projection) */
 	/* result set: filled on demand, then handed out row by row */
 	int done;                           /* pipeline has run */
+	int sort_runs;                      /* Sort over host rows: sorted runs the last execution merged (1: it fitted the operator's memory) */
 	int rows_ready;                     /* host arrays below are filled */
 	int squelched;
 	int nonreceiver;                    /* above a Gather, on a segment that is not its receiver: no rows at all */
@@ -549,6 +550,134 @@ static GgPlanState *init_node(GgPlan *node, GgEState *estate, int eflags, int de
 	return NULL;
 }
 
+/* ---- external sort of host rows ----
+ * tuplesort_mk.c: rows beyond the operator's memory go to sorted runs on tape (puttuple -> dumptuples, :1154,:2390) and the
+ * runs are merged through a heap of their heads (mergeruns / mergeonerun, :2019).  Here a run is as many rows as the operator's
+ * memory holds, sorted on the device (gg_sort_rows: the stable radix sort of gg_sort.cu); the runs stay in host memory — where
+ * the reference writes its workfile — and a heap merges them.  The merge compares rows by the same order-preserving keys the
+ * device sorts by, so the outcome is what one big sort would have produced, ties included (runs are consecutive input ranges,
+ * a run's order is stable, and between runs the earlier one wins a tie). */
+static uint64_t sort_radix_key(int64_t v, int32_t typid, int desc)
+{
+	uint64_t k;
+	switch (typid)
+	{
+		case GG_INT4OID: case GG_DATEOID:
+			k = (uint64_t) (int64_t) (int32_t) v ^ 0x8000000000000000ull;
+			break;
+		case GG_FLOAT8OID:
+		{
+			double d;
+			memcpy(&d, &v, 8);
+			if (d != d) k = ~0ull;                                   /* NaN sorts after everything (float8_cmp_internal, float.c:964) */
+			else
+			{
+				if (d == 0.0) v = 0;                                 /* -0 = +0 */
+				k = (uint64_t) v;
+				k = (k >> 63) ? ~k : (k ^ 0x8000000000000000ull);
+			}
+			break;
+		}
+		case GG_BPCHAROID: case GG_VARCHAROID: case GG_TEXTOID:
+			k = __builtin_bswap64((uint64_t) v);                     /* packed bytes, first character most significant */
+			break;
+		default:
+			k = (uint64_t) v ^ 0x8000000000000000ull;
+			break;
+	}
+	return desc ? ~k : k;
+}
+
+/* < 0, 0, > 0: row a against row b of the same row array under the sort keys */
+static int sort_row_cmp(const gg_sortkey *keys, int nkeys, int ncols, const int64_t *values, const uint8_t *isnull, uint64_t a, uint64_t b)
+{
+	int k;
+	for (k = 0; k < nkeys; k++)
+	{
+		const int c = keys[k].col;
+		const int na = isnull[a * (uint64_t) ncols + c] != 0, nb = isnull[b * (uint64_t) ncols + c] != 0;
+		const int da = na ? (keys[k].nulls_first ? 0 : 1) : (keys[k].nulls_first ? 1 : 0);
+		const int db = nb ? (keys[k].nulls_first ? 0 : 1) : (keys[k].nulls_first ? 1 : 0);
+		uint64_t ka, kb;
+		if (da != db) return da < db ? -1 : 1;
+		if (na) continue;                                         /* both NULL: equal on this key */
+		ka = sort_radix_key(values[a * (uint64_t) ncols + c], keys[k].typid, keys[k].desc);
+		kb = sort_radix_key(values[b * (uint64_t) ncols + c], keys[k].typid, keys[k].desc);
+		if (ka != kb) return ka < kb ? -1 : 1;
+	}
+	return 0;
+}
+
+typedef struct { uint64_t pos, end; } SortRun;         /* the run's head and its end, as indices into perm[] */
+
+/* perm[] = the sorted order of `n` rows: run by run through gg_sort_rows, then merged.  run_rows >= 1. */
+static int sort_rows_external(gg_engine *eng, const gg_sortkey *keys, int nkeys, int ncols, const int64_t *values, const uint8_t *isnull,
+                              uint64_t n, uint64_t run_rows, uint64_t *perm, int *nruns_out)
+{
+	const uint64_t nruns = (n + run_rows - 1) / run_rows;
+	uint64_t *runperm, r, i, out = 0;
+	SortRun *runs;
+	uint32_t *heap;                                             /* run numbers, smallest head on top */
+	uint32_t hn = 0;
+	int rc = GG_OK;
+	if (nruns_out) *nruns_out = (int) nruns;
+	if (nruns > 0x7FFFFFFFu) return GG_ERR_UNSUPPORTED;
+	runperm = malloc(8 * (size_t) (n ? n : 1));
+	runs = malloc(sizeof *runs * (size_t) (nruns ? nruns : 1));
+	heap = malloc(4 * (size_t) (nruns ? nruns : 1));
+	if (!runperm || !runs || !heap) { free(runperm); free(runs); free(heap); return GG_ERR_NOMEM; }
+	for (r = 0; r < nruns && rc == GG_OK; r++)
+	{
+		const uint64_t first = r * run_rows, len = first + run_rows <= n ? run_rows : n - first;
+		rc = gg_sort_rows(eng, keys, nkeys, ncols, values + first * (uint64_t) ncols, isnull + first * (uint64_t) ncols, len, runperm + first);
+		for (i = 0; i < len && rc == GG_OK; i++) runperm[first + i] += first;      /* row numbers of the whole input */
+		runs[r].pos = first; runs[r].end = first + len;
+	}
+	if (rc == GG_OK)
+	{
+		/* build the heap of run heads, then pop the smallest head, advance its run, sift down: mergeonerun */
+		for (r = 0; r < nruns; r++)
+		{
+			uint32_t at = hn++;
+			heap[at] = (uint32_t) r;
+			while (at > 0)
+			{
+				const uint32_t up = (at - 1) / 2;
+				const int c = sort_row_cmp(keys, nkeys, ncols, values, isnull, runperm[runs[heap[at]].pos], runperm[runs[heap[up]].pos]);
+				if (c > 0 || (c == 0 && heap[at] > heap[up])) break;
+				{ const uint32_t t = heap[at]; heap[at] = heap[up]; heap[up] = t; }
+				at = up;
+			}
+		}
+		while (hn > 0)
+		{
+			const uint32_t top = heap[0];
+			uint32_t at = 0;
+			perm[out++] = runperm[runs[top].pos++];
+			if (runs[top].pos == runs[top].end) heap[0] = heap[--hn];
+			for (;;)
+			{
+				uint32_t l = 2 * at + 1, rr = l + 1, m = at;
+				if (l < hn)
+				{
+					const int c = sort_row_cmp(keys, nkeys, ncols, values, isnull, runperm[runs[heap[l]].pos], runperm[runs[heap[m]].pos]);
+					if (c < 0 || (c == 0 && heap[l] < heap[m])) m = l;
+				}
+				if (rr < hn)
+				{
+					const int c = sort_row_cmp(keys, nkeys, ncols, values, isnull, runperm[runs[heap[rr]].pos], runperm[runs[heap[m]].pos]);
+					if (c < 0 || (c == 0 && heap[rr] < heap[m])) m = rr;
+				}
+				if (m == at) break;
+				{ const uint32_t t = heap[at]; heap[at] = heap[m]; heap[m] = t; }
+				at = m;
+			}
+		}
+	}
+	free(runperm); free(runs); free(heap);
+	return rc;
+}
+
 static int run_node(GgPlanState *s);
 
 static int run_child(GgPlanState *s)
@@ -902,8 +1031,19 @@ static int run_node(GgPlanState *s)
 			memcpy(s->typid, ch->typid, sizeof s->typid);
 			perm = malloc(8 * (size_t) (ch->nrows > 0 ? ch->nrows : 1));
 			if (!perm) { exec_fail(GG_ERR_NOMEM, "out of memory"); return -1; }
-			rc = gg_sort_rows(es->engine, keys, so->numCols, ch->ncols, ch->values, ch->isnull, (uint64_t) ch->nrows, perm);
-			if (rc != GG_OK) { exec_fail(rc, "%s", gg_last_error()); free(perm); return -1; }
+			{
+				/* what the rows take in this node's memory: values, NULL flags, lengths — against the operator's memory
+				 * (PlanStateOperatorMemKB, execnodes.h:1446): beyond it the sort goes external, never below 256 rows a run */
+				const uint64_t rowbytes = (uint64_t) ch->ncols * 13u;
+				uint64_t run_rows = es->es_operator_mem ? es->es_operator_mem / (rowbytes ? rowbytes : 1) : 0;
+				if (run_rows && run_rows < 256) run_rows = 256;
+				s->sort_runs = 1;
+				if (run_rows && (uint64_t) ch->nrows > run_rows)
+					rc = sort_rows_external(es->engine, keys, so->numCols, ch->ncols, ch->values, ch->isnull, (uint64_t) ch->nrows, run_rows, perm, &s->sort_runs);
+				else
+					rc = gg_sort_rows(es->engine, keys, so->numCols, ch->ncols, ch->values, ch->isnull, (uint64_t) ch->nrows, perm);
+			}
+			if (rc != GG_OK) { exec_fail(rc, "%s", rc == GG_ERR_NOMEM ? "out of memory" : gg_last_error()); free(perm); return -1; }
 			for (r = 0; r < ch->nrows; r++)
 			{
 				memcpy(s->values + (size_t) r * ch->ncols, ch->values + (size_t) perm[r] * ch->ncols, 8 * (size_t) ch->ncols);
@@ -1148,6 +1288,8 @@ static int slot_binding(const int32_t *typids, int ncols, gg_memtuple_binding *b
 	}
 	return gg_memtuple_bind(attrs, ncols, b);
 }
+
+int GgExecSortRuns(GgPlanState *s) { return s && s->kind == K_SORT ? s->sort_runs : 0; }
 
 int64_t GgExecFetchSlotMemTuple(const GgTupleTableSlot *slot, uint8_t *out, uint64_t cap, uint32_t *need)
 {

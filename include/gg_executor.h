@@ -175,6 +175,9 @@ const char *GgExecNodeKind(GgPlanState *node);
 const char *GgExecNodeResultLocation(GgPlanState *node);
 /* the state of a node's outer / inner child (outerPlanState / innerPlanState, execnodes.h:1441), NULL if fused away */
 int GgExecPipelineKernelMs(GgPlanState *node, float *ms, int *launches, int *variant, float *build_ms);   /* benchmarks */
+/* a Sort node over host rows: how many sorted runs its last execution merged (tuplesort's external path, taken when the rows
+ * exceed GgEState.es_operator_mem: each run sorted on the device, the runs merged on the host); 1 = one in-memory sort */
+int GgExecSortRuns(GgPlanState *node);
 GgPlanState *GgExecOuterPlanState(GgPlanState *node);
 GgPlanState *GgExecInnerPlanState(GgPlanState *node);
 

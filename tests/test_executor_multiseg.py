@@ -166,6 +166,30 @@ def single_segment_checks(L, eng, ex):
         assert v[1] == byk[v[0]].agg[0].i and v[3] == byk[v[0]].agg[2].i
     x.end()
     done.append("join-sort-desc")
+    # a Sort whose rows exceed the operator's memory goes external: sorted runs, merged on the host (tuplesort_mk.c:2019) —
+    # same rows, same order as the in-memory sort, for a total order and for one with many ties and NULLS FIRST / DESC keys
+    p = capi.ExprPool()
+    c = tpch.LI_NARROW_COLS
+    okey, price = p.var(c["orderkey"], capi.INT8OID), p.var(c["extendedprice"], capi.FLOAT8OID)
+    gagg = capi.make_agg(capi.AGGSTAGE_NORMAL, [okey], [(capi.AGG_COUNT_STAR, -1), (capi.AGG_SUM_FLOAT8, price)], num_groups=6000)
+    lscan = capi.make_scan(capi.synth_tupdesc(capi.TAB_LINEITEM_NARROW), -1)
+    L.GgExecSortRuns.argtypes = [C.c_void_p]
+    for keys in ([capi.make_sortkey(1, capi.INT8OID, desc=True), capi.make_sortkey(0, capi.INT8OID)],           # count desc, orderkey: total
+                 [capi.make_sortkey(1, capi.INT8OID)],                                                            # count only: ties keep input order
+                 [capi.make_sortkey(2, capi.FLOAT8OID, desc=True, nulls_first=True), capi.make_sortkey(0, capi.INT8OID, desc=True)]):
+        got = []
+        for mem in (0, 16 * 1024):
+            b = ex.PlanBuilder()
+            x = ex.Executor(eng, p.pool, [MockRel(L, li)], b.sort(b.agg(b.seqscan(0, lscan.desc, lscan.qual), gagg), keys), operator_mem=mem)
+            got.append([tuple(v) for v, nl, ty, ln in x.rows()])
+            runs = L.GgExecSortRuns(x.state)
+            assert (runs == 1) if mem == 0 else (runs >= 10), (mem, runs)
+            x.end()
+        assert len(got[0]) > 4000 and got[0] == got[1]
+        k0 = keys[0]
+        col = [r[k0.col] if k0.typid != capi.FLOAT8OID else b2f(r[k0.col]) for r in got[1]]
+        assert col == sorted(col, reverse=bool(k0.desc))
+    done.append("external-sort")
     # a Motion over several segments without a transport is refused at init, not at run time
     try:
         ex.Executor(eng, pool, [MockRel(L, pages)], q1_sorted_plan(ex.PlanBuilder(), scan, agg, True), nsegs=2, segindex=0)
@@ -278,7 +302,7 @@ def test_node_surface_control_flow_on_one_segment(tmp_path):
     """ReScan, end of stream, Squelch after a LIMIT, Sort DESC above a join pipeline, the loopback Motions of the two-stage
     plan — tests/test_gpu_executor.py's checks with the oracle behind the C-ABI, in a child process"""
     by = run(1, "single", tmp_path)
-    assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "motion-needs-transport", "malformed-trees-refused"]
+    assert by[0][3] == ["q1-one-stage", "q1-two-stage", "join-sort-desc", "external-sort", "motion-needs-transport", "malformed-trees-refused"]
 
 
 def test_a_failing_segment_does_not_leave_its_peers_in_the_exchange(tmp_path):
