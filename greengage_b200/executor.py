@@ -59,6 +59,11 @@ class GgTupleTableSlot(C.Structure):
                 ("tts_len", C.c_int32 * GG_MAX_OUTCOLS)]
 
 
+class GgInstrumentation(C.Structure):
+    _fields_ = [("ntuples", C.c_double), ("nloops", C.c_double), ("kernel_ms", C.c_float), ("sort_runs", C.c_int32),
+                ("hash_batches", C.c_int32), ("pad", C.c_int32)]
+
+
 class GgRowBatch(C.Structure):
     _fields_ = [("ncols", C.c_int32), ("nrows", C.c_int64), ("values", C.POINTER(C.c_int64)), ("isnull", C.POINTER(C.c_uint8))]
 
@@ -222,6 +227,18 @@ class Executor:
         out, st = [], self.state
         while st:
             out.append((L.GgExecNodeKind(st).decode(), L.GgExecNodeResultLocation(st).decode()))
+            st = L.GgExecOuterPlanState(st)
+        return out
+
+    def instrumentation(self):
+        """[(node kind, GgInstrumentation)] from the top node down the outer children: what EXPLAIN ANALYZE would print"""
+        L = exec_lib()
+        L.GgExecNodeInstrumentation.argtypes = [C.c_void_p, C.POINTER(GgInstrumentation)]
+        out, st = [], self.state
+        while st:
+            ins = GgInstrumentation()
+            capi.check(L.GgExecNodeInstrumentation(st, C.byref(ins)))
+            out.append((L.GgExecNodeKind(st).decode(), ins))
             st = L.GgExecOuterPlanState(st)
         return out
 

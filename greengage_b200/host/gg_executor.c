@@ -55,6 +55,7 @@ struct GgPlanState {
 	/* result set: filled on demand, then handed out row by row */
 	int done;                           /* pipeline has run */
 	int sort_runs;                      /* Sort over host rows: sorted runs the last execution merged (1: it fitted the operator's memory) */
+	double instr_ntuples, instr_nloops; /* Instrumentation: tuples handed up, executions */
 	int rows_ready;                     /* host arrays below are filled */
 	int squelched;
 	int nonreceiver;                    /* above a Gather, on a segment that is not its receiver: no rows at all */
@@ -875,6 +876,7 @@ static int run_node(GgPlanState *s)
 		if (trace < 0) { const char *t = getenv("GGB200_EXEC_TRACE"); trace = t && atoi(t) != 0; }
 		if (trace) { fprintf(stderr, "[exec seg %d] run node kind %d (motion on host: %d)\n", es->segindex, (int) s->kind, es->motion_on_host); fflush(stderr); }
 	}
+	s->instr_nloops += 1.0;
 	switch (s->kind)
 	{
 		case K_SCANROWS:
@@ -1291,6 +1293,21 @@ static int slot_binding(const int32_t *typids, int ncols, gg_memtuple_binding *b
 
 int GgExecSortRuns(GgPlanState *s) { return s && s->kind == K_SORT ? s->sort_runs : 0; }
 
+int GgExecNodeInstrumentation(GgPlanState *s, GgInstrumentation *out)
+{
+	float ms = 0.0f, bms = 0.0f;
+	int launches = 0, variant = 0;
+	if (!s || !out) return GG_ERR_ARG;
+	memset(out, 0, sizeof *out);
+	out->ntuples = s->instr_ntuples;
+	out->nloops = s->instr_nloops;
+	out->sort_runs = s->kind == K_SORT ? s->sort_runs : 0;
+	if (s->kind == K_JOINAGG && s->ja) out->hash_batches = gg_joinagg_nbatch(s->ja);
+	if ((s->kind == K_SCANAGG && s->sa) || (s->kind == K_JOINAGG && s->ja))
+		if (GgExecPipelineKernelMs(s, &ms, &launches, &variant, &bms) == GG_OK) out->kernel_ms = ms + bms;
+	return GG_OK;
+}
+
 int64_t GgExecFetchSlotMemTuple(const GgTupleTableSlot *slot, uint8_t *out, uint64_t cap, uint32_t *need)
 {
 	gg_memtuple_binding *b;
@@ -1511,6 +1528,7 @@ GgTupleTableSlot *GgExecProcNode(GgPlanState *s)
 	}
 	s->next++;
 	s->estate->es_processed++;
+	s->instr_ntuples += 1.0;
 	return &s->slot;
 }
 

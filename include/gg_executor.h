@@ -175,6 +175,18 @@ const char *GgExecNodeKind(GgPlanState *node);
 const char *GgExecNodeResultLocation(GgPlanState *node);
 /* the state of a node's outer / inner child (outerPlanState / innerPlanState, execnodes.h:1441), NULL if fused away */
 int GgExecPipelineKernelMs(GgPlanState *node, float *ms, int *launches, int *variant, float *build_ms);   /* benchmarks */
+/* What EXPLAIN ANALYZE reads per node (Instrumentation, executor/instrument.h:38-66, filled by InstrStopNode; explain_gp.c turns
+ * it into "Rows out", "Sort Method", "(slice...) ... batches"): counted by the node surface itself. */
+typedef struct GgInstrumentation {
+	double   ntuples;           /* tuples this node handed up through ExecProcNode, all executions */
+	double   nloops;            /* executions: the first one plus every ExecReScan that ran the node again */
+	float    kernel_ms;         /* GPU time of the node's own pipeline in its last execution (scan / probe kernels), 0 if it has none */
+	int32_t  sort_runs;         /* Sort: runs the last execution merged (1 = in memory; GgExecSortRuns) */
+	int32_t  hash_batches;      /* HashJoin pipeline: batches of the last execution (1 = one table; nodeHash.c:713), 0 otherwise */
+	int32_t  pad;
+} GgInstrumentation;
+int GgExecNodeInstrumentation(GgPlanState *node, GgInstrumentation *out);
+
 /* a Sort node over host rows: how many sorted runs its last execution merged (tuplesort's external path, taken when the rows
  * exceed GgEState.es_operator_mem: each run sorted on the device, the runs merged on the host); 1 = one in-memory sort */
 int GgExecSortRuns(GgPlanState *node);

@@ -108,6 +108,7 @@ int gg_joinagg_probe(gg_joinagg *p, gg_relation *outer, uint64_t first_block, ui
 }
 
 int gg_joinagg_set_work_mem(gg_joinagg *p, uint64_t bytes) { (void) p; (void) bytes; return GG_OK; }
+int gg_joinagg_nbatch(gg_joinagg *p) { (void) p; return 1; }
 int gg_joinagg_run(gg_joinagg *p, gg_relation *inner, gg_relation *outer)
 {
 	p->ipages = inner->pages; p->inb = inner->nblocks;

@@ -33,15 +33,16 @@ def test_struct_sizes_match_the_header():
     src = r'''
     #include <stdio.h>
     #include "gg_executor.h"
-    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(GgPlan), sizeof(GgSeqScan), sizeof(GgAgg), sizeof(GgHashJoin),
-                            sizeof(GgSort), sizeof(GgMotion), sizeof(GgTupleTableSlot), sizeof(GgEState)); return 0; }
+    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(GgPlan), sizeof(GgSeqScan), sizeof(GgAgg), sizeof(GgHashJoin),
+                            sizeof(GgSort), sizeof(GgMotion), sizeof(GgTupleTableSlot), sizeof(GgEState), sizeof(GgInstrumentation)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
-    want = [C.sizeof(t) for t in (ex.GgPlan, ex.GgSeqScan, ex.GgAgg, ex.GgHashJoin, ex.GgSort, ex.GgMotion, ex.GgTupleTableSlot, ex.GgEState)]
+    want = [C.sizeof(t) for t in (ex.GgPlan, ex.GgSeqScan, ex.GgAgg, ex.GgHashJoin, ex.GgSort, ex.GgMotion, ex.GgTupleTableSlot, ex.GgEState,
+                                  ex.GgInstrumentation)]
     assert got == want
 
 

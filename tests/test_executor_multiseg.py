@@ -184,6 +184,14 @@ def single_segment_checks(L, eng, ex):
             got.append([tuple(v) for v, nl, ty, ln in x.rows()])
             runs = L.GgExecSortRuns(x.state)
             assert (runs == 1) if mem == 0 else (runs >= 10), (mem, runs)
+            # Instrumentation the way EXPLAIN ANALYZE reads it: the Sort handed up every row once, in one execution; a ReScan
+            # and a second drain double the rows and the loops
+            ins = dict((k, i) for k, i in x.instrumentation())
+            assert ins["sort"].ntuples == len(got[-1]) and ins["sort"].nloops == 1 and ins["sort"].sort_runs == runs
+            x.rescan()
+            assert len(x.rows()) == len(got[-1])
+            ins = dict((k, i) for k, i in x.instrumentation())
+            assert ins["sort"].ntuples == 2 * len(got[-1]) and ins["sort"].nloops == 2
             x.end()
         assert len(got[0]) > 4000 and got[0] == got[1]
         k0 = keys[0]
