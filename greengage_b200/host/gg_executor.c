@@ -1293,6 +1293,12 @@ static int slot_binding(const int32_t *typids, int ncols, gg_memtuple_binding *b
 
 int GgExecSortRuns(GgPlanState *s) { return s && s->kind == K_SORT ? s->sort_runs : 0; }
 
+/* the external sort's merge order on its own (tests hold it to the reference's comparators): < 0, 0, > 0 for row a against row b */
+int GgExecDebugSortCompare(const gg_sortkey *keys, int nkeys, int ncols, const int64_t *values, const uint8_t *isnull, uint64_t a, uint64_t b)
+{
+	return sort_row_cmp(keys, nkeys, ncols, values, isnull, a, b);
+}
+
 int GgExecNodeInstrumentation(GgPlanState *s, GgInstrumentation *out)
 {
 	float ms = 0.0f, bms = 0.0f;

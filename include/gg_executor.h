@@ -190,6 +190,8 @@ int GgExecNodeInstrumentation(GgPlanState *node, GgInstrumentation *out);
 /* a Sort node over host rows: how many sorted runs its last execution merged (tuplesort's external path, taken when the rows
  * exceed GgEState.es_operator_mem: each run sorted on the device, the runs merged on the host); 1 = one in-memory sort */
 int GgExecSortRuns(GgPlanState *node);
+/* debugging / tests: the order that merge uses, for two rows of one [nrows][ncols] array */
+int GgExecDebugSortCompare(const gg_sortkey *keys, int nkeys, int ncols, const int64_t *values, const uint8_t *isnull, uint64_t a, uint64_t b);
 GgPlanState *GgExecOuterPlanState(GgPlanState *node);
 GgPlanState *GgExecInnerPlanState(GgPlanState *node);
 

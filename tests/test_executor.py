@@ -134,3 +134,37 @@ def test_c_example_builds_as_plain_c_and_fails_loudly_without_a_gpu(tmp_path):
         assert r.returncode == 0 and "count" in r.stdout
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_the_external_sorts_merge_order_is_the_references_comparators():
+    """sort_row_cmp (gg_executor.c) orders rows by the keys the device sorts by; held here, pair by pair, to the order the oracle's
+    restatement of the reference's comparators (btint8cmp, btfloat8cmp with NaN last and -0 = +0, bpcharcmp on packed strings,
+    date_cmp, NULLS FIRST / LAST, DESC) gives the same rows."""
+    import random
+    from oracle import pyoracle as po
+    L = ex.exec_lib()
+    L.GgExecDebugSortCompare.argtypes = [C.POINTER(capi.gg_sortkey), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+    rnd = random.Random(3)
+    f8 = lambda d: int(np.float64(d).view(np.int64))
+    specials = [0.0, -0.0, float("nan"), float("inf"), float("-inf"), 1.5, -1.5, 1e300, -1e-300]
+    n = 400
+    rows = np.zeros((n, 4), dtype=np.int64)
+    nulls = (np.array([[rnd.random() < 0.15 for _ in range(4)] for _ in range(n)])).astype(np.uint8)
+    for i in range(n):
+        rows[i, 0] = rnd.choice([-5, 0, 7, 2**40, -2**40, rnd.randint(-100, 100)])                          # int8
+        rows[i, 1] = f8(rnd.choice(specials) if rnd.random() < 0.5 else rnd.uniform(-10, 10))               # float8
+        s = bytes(rnd.choice(b"AB ab") for _ in range(rnd.randint(0, 8))).rstrip(b" ")
+        rows[i, 2] = int.from_bytes(s.ljust(8, b"\0"), "little", signed=True)                               # packed bpchar
+        rows[i, 3] = rnd.randint(-3000, 3000)                                                                # date
+    for trial in range(20):
+        cols = rnd.sample(range(4), rnd.randint(1, 4))
+        typ = {0: capi.INT8OID, 1: capi.FLOAT8OID, 2: capi.BPCHAROID, 3: capi.DATEOID}
+        keys = [capi.make_sortkey(c, typ[c], desc=rnd.random() < 0.5, nulls_first=rnd.choice([None, True, False])) for c in cols]
+        perm = po.sort_perm(keys, 4, rows, nulls)
+        ka = (capi.gg_sortkey * len(keys))(*keys)
+        cmp = lambda a, b: L.GgExecDebugSortCompare(ka, len(keys), 4, rows.ctypes.data, nulls.ctypes.data, int(a), int(b))
+        # the oracle's order never goes down under the product's comparator, and equal neighbours are equal both ways
+        for a, b in zip(perm[:-1], perm[1:]):
+            c = cmp(a, b)
+            assert c <= 0, (trial, [(k.col, k.desc, k.nulls_first) for k in keys], rows[a], rows[b])
+            assert cmp(b, a) == -c
